@@ -1,0 +1,475 @@
+/*
+ * TEST INFRASTRUCTURE (oracle/_ref) -- not part of the product.
+ *
+ * Thin C wrapper around the UNMODIFIED lucille reference libraries so that Python
+ * (ctypes) can (a) run ray batches through the reference's ri_bvh_intersect(),
+ * (b) dump the reference-built BVH, (c) read the reference's traversal counters and
+ * (d) render a RIB through the reference's own Ri*() -> ri_render_frame() path with
+ * float pixels captured by ri_dd_callback().
+ *
+ * Embedding pattern follows the reference's own testbed
+ * (src/testbed/main.cpp:53-65, src/testbed/simplerender.cpp:170-238) and lsh
+ * (src/lsh/main.c:105-242).  All arithmetic below this file is reference code.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <time.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#include "ri.h"
+#include "render.h"
+#include "scene.h"
+#include "geom.h"
+#include "accel.h"
+#include "bvh.h"
+#include "camera.h"
+#include "option.h"
+#include "display.h"
+#include "backdoor.h"
+#include "parallel.h"
+#include "timer.h"
+#include "list.h"
+#include "log.h"
+#include "raytrace.h"
+#include "beam.h"
+
+extern int lref_rib_parse_file(const char *path);
+
+/* ------------------------------------------------------------------ ray level */
+
+typedef struct {
+    int32_t  hit;
+    uint32_t index;          /* state.index = 3 * (triangle number in its geom), bvh.c:1813 */
+    uint32_t geom_id;
+    uint32_t pad;
+    double   t, u, v;
+    double   P[3], Ng[3], Ns[3], tangent[3], binormal[3];
+} lref_hit_t;
+
+typedef struct {
+    int32_t is_leaf;
+    int32_t axis;
+    int64_t child0, child1;      /* indices into the DFS-preorder dump (inner nodes) */
+    int64_t tri_start, ntris;    /* leaves: slice of the post-build triangle array */
+    double  lbox[6];             /* slot 0: min xyz, max xyz */
+    double  rbox[6];             /* slot 1 */
+} lref_node_t;
+
+typedef struct {
+    ri_scene_t    *scene;
+    ri_geom_t    **geoms;
+    int            ngeoms;
+    ri_bvh_t      *bvh;
+    ri_triangle_t *tri_base;
+    uint64_t       ntris;
+    double         build_seconds;
+} lref_scene_t;
+
+static int g_inited = 0;
+
+static double now_sec(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int lref_init(void)
+{
+    if (!g_inited) {
+        int argc = 1; char *argv0 = "lref"; char **argv = &argv0;
+        ri_parallel_init(&argc, &argv);
+        ri_render_init();
+        ri_log_set_debug(0);
+        g_inited = 1;
+    }
+    return 0;
+}
+
+/* tri_xyz: [ntris][3][3] doubles. geom_sizes: triangles per geom (ngeoms entries) or NULL for one geom.
+ * Each geom gets unshared vertices: positions 3 per triangle, indices 0..3n-1, exactly what
+ * create_triangle_list (bvh.c:1736-1826) flattens again. */
+void *lref_scene_build(const double *tri_xyz, uint64_t ntris, const uint64_t *geom_sizes, int ngeoms)
+{
+    lref_scene_t *s;
+    uint64_t one = ntris;
+    uint64_t off = 0;
+    int g;
+    double t0;
+
+    lref_init();
+    s = (lref_scene_t *)calloc(1, sizeof(lref_scene_t));
+    s->scene = ri_scene_new();
+    if (!geom_sizes) { geom_sizes = &one; ngeoms = 1; }
+    s->geoms = (ri_geom_t **)calloc(ngeoms > 0 ? ngeoms : 1, sizeof(ri_geom_t *));
+    s->ngeoms = ngeoms;
+    s->ntris = ntris;
+
+    for (g = 0; g < ngeoms; g++) {
+        uint64_t n = geom_sizes[g], i;
+        ri_geom_t *geom = ri_geom_new();
+        if (n > 0) {
+            ri_vector_t  *pos = (ri_vector_t *)malloc(sizeof(ri_vector_t) * 3 * n);
+            unsigned int *idx = (unsigned int *)malloc(sizeof(unsigned int) * 3 * n);
+            for (i = 0; i < 3 * n; i++) {
+                pos[i][0] = tri_xyz[3 * (3 * off + i) + 0];
+                pos[i][1] = tri_xyz[3 * (3 * off + i) + 1];
+                pos[i][2] = tri_xyz[3 * (3 * off + i) + 2];
+                pos[i][3] = 1.0;
+                idx[i] = (unsigned int)i;
+            }
+            ri_geom_add_positions(geom, (unsigned int)(3 * n), (const ri_vector_t *)pos);
+            ri_geom_add_indices(geom, (unsigned int)(3 * n), idx);
+            free(pos); free(idx);
+        }
+        s->geoms[g] = geom;
+        ri_scene_add_geom(s->scene, geom);
+        off += n;
+    }
+
+    {
+        ri_accel_t *accel = ri_accel_new();
+        ri_accel_bind(accel, RI_ACCEL_BVH);
+        ri_scene_set_accel(s->scene, accel);
+        t0 = now_sec();
+        ri_scene_build_accel(s->scene);
+        s->build_seconds = now_sec() - t0;
+        s->bvh = (ri_bvh_t *)s->scene->accel->data;
+    }
+    if (!s->bvh->empty) {
+        const ri_qbvh_node_t *n = s->bvh->root;
+        while (!n->is_leaf) n = n->child[0];           /* leftmost leaf starts the array */
+        s->tri_base = (ri_triangle_t *)n->child[0];
+    }
+    return s;
+}
+
+double lref_build_seconds(void *h) { return ((lref_scene_t *)h)->build_seconds; }
+int    lref_is_empty(void *h)      { return ((lref_scene_t *)h)->bvh->empty; }
+
+void lref_scene_bbox(void *h, double *bmin, double *bmax)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    int k;
+    for (k = 0; k < 3; k++) { bmin[k] = s->bvh->bmin[k]; bmax[k] = s->bvh->bmax[k]; }
+}
+
+static void count_nodes(const ri_qbvh_node_t *n, int depth, int64_t *ninner, int64_t *nleaf, int *maxdepth)
+{
+    if (depth > *maxdepth) *maxdepth = depth;
+    if (n->is_leaf) { (*nleaf)++; return; }
+    (*ninner)++;
+    count_nodes(n->child[0], depth + 1, ninner, nleaf, maxdepth);
+    count_nodes(n->child[1], depth + 1, ninner, nleaf, maxdepth);
+}
+
+void lref_tree_count(void *h, int64_t *ninner, int64_t *nleaf, int *maxdepth)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    *ninner = 0; *nleaf = 0; *maxdepth = 0;
+    if (s->bvh->empty) return;
+    count_nodes(s->bvh->root, 0, ninner, nleaf, maxdepth);
+}
+
+static int64_t dump_node(lref_scene_t *s, const ri_qbvh_node_t *n, lref_node_t *out, int64_t *cursor)
+{
+    int64_t me = (*cursor)++;
+    lref_node_t *o = &out[me];
+    memset(o, 0, sizeof(*o));
+    o->is_leaf = n->is_leaf;
+    if (n->is_leaf) {
+        o->ntris = *((uint32_t *)&n->bbox[0]);
+        o->tri_start = (ri_triangle_t *)n->child[0] - s->tri_base;
+        o->child0 = o->child1 = -1;
+        return me;
+    }
+    o->axis = n->axis0;
+    o->lbox[0] = n->bbox[BMIN_X0]; o->lbox[1] = n->bbox[BMIN_Y0]; o->lbox[2] = n->bbox[BMIN_Z0];
+    o->lbox[3] = n->bbox[BMAX_X0]; o->lbox[4] = n->bbox[BMAX_Y0]; o->lbox[5] = n->bbox[BMAX_Z0];
+    o->rbox[0] = n->bbox[BMIN_X1]; o->rbox[1] = n->bbox[BMIN_Y1]; o->rbox[2] = n->bbox[BMIN_Z1];
+    o->rbox[3] = n->bbox[BMAX_X1]; o->rbox[4] = n->bbox[BMAX_Y1]; o->rbox[5] = n->bbox[BMAX_Z1];
+    o->child0 = dump_node(s, n->child[0], out, cursor);
+    o = &out[me];
+    o->child1 = dump_node(s, n->child[1], out, cursor);
+    return me;
+}
+
+/* DFS preorder dump; `out` must hold ninner+nleaf entries. */
+int64_t lref_tree_dump(void *h, lref_node_t *out)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    int64_t cursor = 0;
+    if (s->bvh->empty) return 0;
+    dump_node(s, s->bvh->root, out, &cursor);
+    return cursor;
+}
+
+/* for each position p of the post-build triangle array: flattened input triangle number */
+void lref_tree_triorder(void *h, uint32_t *orig)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    uint64_t p;
+    uint64_t *geom_off = (uint64_t *)calloc(s->ngeoms + 1, sizeof(uint64_t));
+    int g;
+    for (g = 0; g < s->ngeoms; g++) geom_off[g + 1] = geom_off[g] + s->geoms[g]->nindices / 3;
+    for (p = 0; p < s->ntris; p++) {
+        const ri_triangle_t *t = &s->tri_base[p];
+        for (g = 0; g < s->ngeoms; g++) if (s->geoms[g] == t->geom) break;
+        orig[p] = (uint32_t)(geom_off[g] + t->index / 3);
+    }
+    free(geom_off);
+}
+
+typedef struct {
+    lref_scene_t *s;
+    const double *rays;      /* [n][6] org.xyz dir.xyz */
+    lref_hit_t   *out;
+    uint64_t      begin, end;
+    int           want_state;
+} job_t;
+
+static void *job_run(void *arg)
+{
+    job_t *j = (job_t *)arg;
+    uint64_t i;
+    int g, k;
+    ri_ray_t ray;
+    ri_intersection_state_t state;
+    memset(&ray, 0, sizeof(ray));
+    for (i = j->begin; i < j->end; i++) {
+        const double *r = j->rays + 6 * i;
+        lref_hit_t *o = j->out ? &j->out[i] : NULL;
+        int hit;
+        ray.org[0] = r[0]; ray.org[1] = r[1]; ray.org[2] = r[2]; ray.org[3] = 1.0;
+        ray.dir[0] = r[3]; ray.dir[1] = r[4]; ray.dir[2] = r[5]; ray.dir[3] = 0.0;
+        hit = ri_bvh_intersect(j->s->bvh, &ray, &state, NULL);
+        if (!o) continue;
+        o->hit = hit;
+        if (hit) {
+            o->index = state.index;
+            for (g = 0; g < j->s->ngeoms; g++) if (j->s->geoms[g] == state.geom) break;
+            o->geom_id = (uint32_t)g;
+            o->t = state.t; o->u = state.u; o->v = state.v;
+            for (k = 0; k < 3; k++) {
+                o->P[k] = state.P[k]; o->Ng[k] = state.Ng[k]; o->Ns[k] = state.Ns[k];
+                o->tangent[k] = state.tangent[k]; o->binormal[k] = state.binormal[k];
+            }
+        } else {
+            memset(&o->index, 0, sizeof(*o) - sizeof(int32_t));
+        }
+    }
+    return NULL;
+}
+
+/* returns seconds spent inside the query loop (build excluded) */
+double lref_intersect(void *h, const double *rays, uint64_t n, int nthreads, lref_hit_t *out)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    pthread_t th[256];
+    job_t jobs[256];
+    int t;
+    double t0;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    t0 = now_sec();
+    for (t = 0; t < nthreads; t++) {
+        jobs[t].s = s; jobs[t].rays = rays; jobs[t].out = out;
+        jobs[t].begin = n * (uint64_t)t / nthreads;
+        jobs[t].end   = n * (uint64_t)(t + 1) / nthreads;
+        if (nthreads == 1) job_run(&jobs[t]);
+        else pthread_create(&th[t], NULL, job_run, &jobs[t]);
+    }
+    if (nthreads > 1) for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    return now_sec() - t0;
+}
+
+/* reference traversal counters (only meaningful in libluciref_stat.so; bvh.c:146,686-688) */
+extern ri_bvh_stat_traversal_t g_stattrav;
+void lref_stats_reset(void) { memset(&g_stattrav, 0, sizeof(g_stattrav)); }
+void lref_stats_get(uint64_t *out6)
+{
+    out6[0] = g_stattrav.nrays;
+    out6[1] = g_stattrav.ninner_node_traversals;
+    out6[2] = g_stattrav.nleaf_node_traversals;
+    out6[3] = g_stattrav.ntested_triangles;
+    out6[4] = g_stattrav.nactually_hit_triangles;
+    out6[5] = 0;
+}
+int lref_has_stats(void)
+{
+#ifdef RI_BVH_TRACE_STATISTICS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+/* beam visibility query (bvh.c:612-667): org[3], dirs[4][3]; returns RI_BEAM_* code */
+int lref_beam_visibility(void *h, const double *org, const double *dirs)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_beam_t beam;
+    ri_vector_t o, d[4];
+    int i, k;
+    memset(&beam, 0, sizeof(beam));
+    for (k = 0; k < 3; k++) o[k] = org[k];
+    o[3] = 1.0;
+    for (i = 0; i < 4; i++) { for (k = 0; k < 3; k++) d[i][k] = dirs[3 * i + k]; d[i][3] = 0.0; }
+    ri_beam_set(&beam, o, d);
+    return ri_bvh_intersect_beam_visibility(s->bvh, &beam, NULL);
+}
+
+/* ------------------------------------------------------------------ frame level */
+
+typedef struct {
+    int      nthreads, width, height, pixelsamples, gather_nsamples;
+    float   *rgb;            /* [h][w][3], rows as the display driver receives them (y already flipped) */
+    int      w, h;
+    double   render_seconds;
+    uint64_t nrays;
+    /* scene capture (taken in the display-open callback, before the build) */
+    double  *tri_xyz; uint64_t ntris; uint32_t *tri_geom; int ngeoms;
+    double   c2w[16]; double flength; int is_rh; int ortho; double fov;
+    int      xsamples, ysamples, gather, bucket_size, bucket_order;
+    int      has_normals;
+} frame_t;
+
+static frame_t g_frame;
+
+static void world_begin_cb(void)
+{
+    ri_option_t  *opt  = ri_render_get()->context->option;
+    ri_display_t *disp = ri_option_get_curr_display(opt);
+    if (g_frame.pixelsamples > 0) {
+        disp->sampling_rates[0] = g_frame.pixelsamples;
+        disp->sampling_rates[1] = g_frame.pixelsamples;
+    }
+    if (g_frame.nthreads > 0) opt->nthreads = g_frame.nthreads;
+    if (g_frame.gather_nsamples > 0) opt->gather_nsamples = g_frame.gather_nsamples;
+    if (g_frame.width > 0 && g_frame.height > 0) {
+        opt->camera->horizontal_resolution = g_frame.width;
+        opt->camera->vertical_resolution   = g_frame.height;
+    }
+    disp->display_type   = strdup("callback");
+    disp->display_format = strdup("float");
+}
+
+static int dd_open(const char *name, int width, int height, int bits, RtToken component, const char *format)
+{
+    ri_render_t *r = ri_render_get();
+    ri_option_t *opt = r->context->option;
+    ri_display_t *disp = ri_option_get_curr_display(opt);
+    ri_camera_t *cam = opt->camera;
+    ri_list_t *itr;
+    uint64_t n = 0, idx = 0;
+    int g = 0, i, j;
+
+    g_frame.w = width; g_frame.h = height;
+    g_frame.rgb = (float *)calloc((size_t)width * height * 3, sizeof(float));
+
+    /* capture the triangle soup exactly as create_triangle_list() will flatten it */
+    for (itr = ri_list_first(r->scene->geom_list); itr; itr = ri_list_next(itr)) {
+        ri_geom_t *geom = (ri_geom_t *)itr->data;
+        n += geom->nindices / 3; g++;
+    }
+    g_frame.ntris = n; g_frame.ngeoms = g;
+    g_frame.tri_xyz  = (double *)malloc(sizeof(double) * 9 * (n ? n : 1));
+    g_frame.tri_geom = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    g = 0;
+    for (itr = ri_list_first(r->scene->geom_list); itr; itr = ri_list_next(itr)) {
+        ri_geom_t *geom = (ri_geom_t *)itr->data;
+        unsigned int t;
+        if (geom->normals) g_frame.has_normals = 1;
+        for (t = 0; t < geom->nindices / 3; t++) {
+            for (i = 0; i < 3; i++)
+                for (j = 0; j < 3; j++)
+                    g_frame.tri_xyz[9 * idx + 3 * i + j] = geom->positions[geom->indices[3 * t + i]][j];
+            g_frame.tri_geom[idx] = (uint32_t)g;
+            idx++;
+        }
+        g++;
+    }
+
+    /* camera: ri_camera_setup() is what ri_render_frame() calls next (render.c:337); it is idempotent */
+    ri_camera_setup(cam);
+    for (i = 0; i < 4; i++) for (j = 0; j < 4; j++) g_frame.c2w[4 * i + j] = cam->camera_to_world.f[i][j];
+    g_frame.flength = cam->flength;
+    g_frame.is_rh   = cam->is_rh;
+    g_frame.ortho   = (cam->camera_projection == RI_ORTHOGRAPHIC);
+    g_frame.fov     = cam->fov;
+    g_frame.xsamples = (int)disp->sampling_rates[0];
+    g_frame.ysamples = (int)disp->sampling_rates[1];
+    g_frame.gather   = opt->gather_nsamples;
+    g_frame.bucket_size  = r->bucket_size;
+    g_frame.bucket_order = r->bucket_order;
+    return 1;
+}
+
+static int dd_write(int x, int y, const void *pixel)
+{
+    const float *p = (const float *)pixel;
+    float *dst = g_frame.rgb + 3 * ((size_t)y * g_frame.w + x);
+    dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2];
+    return 1;
+}
+
+static int dd_close(void)
+{
+    /* ri_raytrace_statistics() has just printed; the counters are still live here */
+    g_frame.nrays = ri_render_get()->stat.nrays;
+    g_frame.render_seconds = ri_timer_elapsed(ri_render_get()->context->timer, "Render frame");
+    return 1;
+}
+
+/* One frame per process (the reference keeps one-shot statics, e.g. spiral.c:17 g_n). */
+int lref_render_rib(const char *path, int nthreads, int width, int height, int pixelsamples, int gather_nsamples)
+{
+    char buf[2048];
+    const char *slash;
+    int argc = 1; char *argv0 = "lref"; char **argv = &argv0;
+
+    memset(&g_frame, 0, sizeof(g_frame));
+    g_frame.nthreads = nthreads; g_frame.width = width; g_frame.height = height;
+    g_frame.pixelsamples = pixelsamples; g_frame.gather_nsamples = gather_nsamples;
+
+    ri_parallel_init(&argc, &argv);                     /* lsh/main.c:119 */
+    RiBegin(RI_NULL);                                   /* lsh/main.c:153 */
+    ri_dd_callback(dd_open, dd_close, dd_write);        /* ri/display.c:118-136 */
+    ri_backdoor_world_begin_cb(world_begin_cb);         /* lsh/main.c:162 */
+    ri_timer_start(ri_render_get()->context->timer, "RIB parsing");   /* lsh/main.c:165 */
+
+    slash = strrchr(path, '/');                         /* set_ribpath, lsh/main.c:78-101 */
+    if (slash) {
+        size_t len = (size_t)(slash - path) + 1;
+        memcpy(buf, path, len); buf[len] = 0;
+        strcpy(ri_render_get()->ribpath, buf);
+        ri_option_add_searchpath(ri_render_get()->context->option, buf);
+    }
+    if (getcwd(buf, sizeof(buf) - 1)) ri_option_add_searchpath(ri_render_get()->context->option, buf);
+
+    if (lref_rib_parse_file(path) != 0) return -1;
+    RiEnd();
+    return 0;
+}
+
+int      lref_frame_width(void)  { return g_frame.w; }
+int      lref_frame_height(void) { return g_frame.h; }
+float   *lref_frame_rgb(void)    { return g_frame.rgb; }
+double   lref_frame_seconds(void){ return g_frame.render_seconds; }
+uint64_t lref_frame_nrays(void)  { return g_frame.nrays; }
+uint64_t lref_frame_ntris(void)  { return g_frame.ntris; }
+double  *lref_frame_tris(void)   { return g_frame.tri_xyz; }
+uint32_t*lref_frame_trigeom(void){ return g_frame.tri_geom; }
+/* out: c2w[16], flength, is_rh, ortho, fov, xsamples, ysamples, gather, bucket_size, bucket_order, has_normals, ngeoms */
+void lref_frame_camera(double *out27)
+{
+    int i;
+    for (i = 0; i < 16; i++) out27[i] = g_frame.c2w[i];
+    out27[16] = g_frame.flength; out27[17] = g_frame.is_rh; out27[18] = g_frame.ortho; out27[19] = g_frame.fov;
+    out27[20] = g_frame.xsamples; out27[21] = g_frame.ysamples; out27[22] = g_frame.gather;
+    out27[23] = g_frame.bucket_size; out27[24] = g_frame.bucket_order; out27[25] = g_frame.has_normals;
+    out27[26] = g_frame.ngeoms;
+}
