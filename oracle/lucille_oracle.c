@@ -1,0 +1,686 @@
+/*
+ * lucille_oracle.c -- TEST INFRASTRUCTURE, not product code.  See lucille_oracle.h.
+ *
+ * CPU restatement (plain C) of the lucille hot path.  Written from the behaviour of the
+ * reference, function by function, with the reference file:line each piece follows.
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (oracle/Makefile).
+ */
+#include <assert.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "lucille_oracle.h"
+
+#define ORC_STACK 128          /* reference reserves 101 entries, bvh.c:80,126 */
+
+typedef struct {
+    double   bmin[3], bmax[3];
+    uint64_t index;            /* tri_bbox_t, bvh.c:107-114 */
+} tbox_t;
+
+struct orc_tree {
+    int         empty;
+    uint64_t    ntris;
+    double      bmin[3], bmax[3];
+    orc_node_t *nodes;
+    int64_t     nnodes, cap;
+    int         max_depth;
+    double     *tri_xyz;       /* post-build order, [ntris][9] v0 v1 v2 */
+    uint32_t   *orig;          /* post-build position -> input triangle */
+    /* per-precision views, built once after construction */
+    double     *lbox64, *rbox64, *tri64;
+    float      *lbox32, *rbox32, *tri32;
+    float       smin32[3], smax32[3];
+};
+
+/* ------------------------------------------------------------------ build (double, as the reference) */
+
+/* bvh.c:1697-1731 bbox_add_margin */
+static void add_margin(double bmin[3], double bmax[3])
+{
+    int i;
+    double margin[3];
+    const double eps = ORC_EPS;
+    for (i = 0; i < 3; i++) {
+        double scale = bmax[i] - bmin[i];
+        margin[i] = (scale < eps) ? eps : eps * scale;
+    }
+    for (i = 0; i < 3; i++) { bmin[i] -= margin[i]; bmax[i] += margin[i]; }
+}
+
+/* bvh.c:1870-1895 calc_bbox_of_triangles (vmin/vmax are `(a<b)?a:b` selects, vector.h) */
+static void bbox_of_range(double bmin[3], double bmax[3], const tbox_t *b, uint64_t n)
+{
+    uint64_t i; int k;
+    for (k = 0; k < 3; k++) { bmin[k] = b[0].bmin[k]; bmax[k] = b[0].bmax[k]; }
+    for (i = 1; i < n; i++) {
+        for (k = 0; k < 3; k++) {
+            bmin[k] = (bmin[k] < b[i].bmin[k]) ? bmin[k] : b[i].bmin[k];
+            bmax[k] = (bmax[k] > b[i].bmax[k]) ? bmax[k] : b[i].bmax[k];
+        }
+    }
+}
+
+/* bvh.c:1190-1208 calc_surface_area */
+static double surface_area(const double bmin[3], const double bmax[3])
+{
+    double sa = (bmax[0] - bmin[0]) * (bmax[1] - bmin[1]) +
+                (bmax[1] - bmin[1]) * (bmax[2] - bmin[2]) +
+                (bmax[2] - bmin[2]) * (bmax[0] - bmin[0]);
+    sa *= 2.0;
+    return sa;
+}
+
+/* bvh.c:1210-1228 SAH: evaluated in double, *stored in a float* before it is compared */
+static double sah_cost(int ns1, double left_area, int ns2, double right_area, double s)
+{
+    const float Taabb = 0.2f;
+    const float Ttri  = 0.8f;
+    float T;
+    T = 2.0f * Taabb
+      + (left_area / s) * (double)ns1 * Ttri
+      + (right_area / s) * (double)ns2 * Ttri;
+    return T;
+}
+
+typedef struct { uint32_t bin[2][3][ORC_BINS]; } binbuf_t;
+
+/* bvh.c:1571-1692 bin_triangle_edge */
+static void bin_edges(binbuf_t *bb, const double bmin[3], const double bmax[3], const tbox_t *b, uint64_t n)
+{
+    uint64_t i; int k;
+    const double eps = 1.0e-14;
+    const double binsize = (double)ORC_BINS;
+    double size[3], invsize[3];
+    for (k = 0; k < 3; k++) {
+        size[k] = bmax[k] - bmin[k];
+        invsize[k] = (size[k] > eps) ? binsize / size[k] : 0.0;
+    }
+    memset(bb, 0, sizeof(*bb));
+    for (i = 0; i < n; i++) {
+        for (k = 0; k < 3; k++) {
+            double qmin = (b[i].bmin[k] - bmin[k]) * invsize[k];
+            double qmax = (b[i].bmax[k] - bmin[k]) * invsize[k];
+            uint32_t imin = (uint32_t)qmin;
+            uint32_t imax = (uint32_t)qmax;
+            if (imin >= ORC_BINS) imin = ORC_BINS - 1;
+            if (imax >= ORC_BINS) imax = ORC_BINS - 1;
+            bb->bin[0][k][imin]++;
+            bb->bin[1][k][imax]++;
+        }
+    }
+}
+
+/* bvh.c:1230-1326 find_cut_from_bin */
+static void find_cut(double *cut_pos, int *cut_axis, const binbuf_t *bb,
+                     const double bmin[3], const double bmax[3], uint64_t ntris)
+{
+    int i, j, k;
+    double min_cost = ORC_INFINITY, min_pos = 0.0;
+    int    min_axis = 0;
+    double bstep[3], sa_total;
+    for (k = 0; k < 3; k++) bstep[k] = (bmax[k] - bmin[k]) / (double)ORC_BINS;
+    sa_total = surface_area(bmin, bmax);
+
+    for (j = 0; j < 3; j++) {
+        uint64_t left = 0, right = ntris;
+        double lmin[3], lmax[3], rmin[3], rmax[3];
+        for (k = 0; k < 3; k++) { lmin[k] = rmin[k] = bmin[k]; lmax[k] = rmax[k] = bmax[k]; }
+        for (i = 0; i < ORC_BINS - 1; i++) {
+            double pos, cost;
+            left  += bb->bin[0][j][i];
+            right -= bb->bin[1][j][i];
+            pos = bmin[j] + (i + 1) * bstep[j];
+            lmax[j] = pos;
+            rmin[j] = pos;
+            cost = sah_cost((int)left, surface_area(lmin, lmax), (int)right, surface_area(rmin, rmax), sa_total);
+            if (cost < min_cost) { min_cost = cost; min_axis = j; min_pos = pos; }
+        }
+    }
+    *cut_axis = min_axis;
+    *cut_pos  = min_pos;
+}
+
+typedef struct {
+    orc_tree *T;
+    tbox_t   *boxes, *boxes_buf;
+    const double *tri_in;      /* input order */
+} build_ctx;
+
+static int64_t new_node(orc_tree *T)
+{
+    if (T->nnodes == T->cap) {
+        T->cap = T->cap ? 2 * T->cap : 1024;
+        T->nodes = (orc_node_t *)realloc(T->nodes, sizeof(orc_node_t) * (size_t)T->cap);
+    }
+    memset(&T->nodes[T->nnodes], 0, sizeof(orc_node_t));
+    return T->nnodes++;
+}
+
+/* bvh.c:1328-1564 bvh_construct; returns the node's index in DFS preorder */
+static int64_t construct(build_ctx *B, const double bmin[3], const double bmax[3],
+                         uint64_t left, uint64_t right, int depth)
+{
+    orc_tree *T = B->T;
+    uint64_t n = right - left, i;
+    int64_t me = new_node(T);
+    if (depth > T->max_depth) T->max_depth = depth;
+
+    if (n <= ORC_LEAF_TRIS) {                                 /* bvh.c:1352-1403 */
+        for (i = 0; i < n; i++) {                             /* gather_triangles, bvh.c:1897-1917 */
+            uint64_t src = B->boxes[left + i].index;
+            memcpy(T->tri_xyz + 9 * (left + i), B->tri_in + 9 * src, sizeof(double) * 9);
+            T->orig[left + i] = (uint32_t)src;
+        }
+        T->nodes[me].is_leaf = 1;
+        T->nodes[me].tri_start = (int64_t)left;
+        T->nodes[me].ntris = (int64_t)n;
+        T->nodes[me].child0 = T->nodes[me].child1 = -1;
+        return me;
+    }
+
+    {
+        binbuf_t bb;
+        double cut_pos; int cut_axis;
+        uint64_t nl = 0, nr = n - 1;
+        double lmin[3], lmax[3], rmin[3], rmax[3];
+        int64_t c0, c1;
+        int k;
+
+        bin_edges(&bb, bmin, bmax, B->boxes + left, n);
+        find_cut(&cut_pos, &cut_axis, &bb, bmin, bmax, n);
+
+        memcpy(B->boxes_buf, B->boxes + left, sizeof(tbox_t) * n);        /* bvh.c:1438 */
+        for (i = 0; i < n; i++) {
+            if (B->boxes_buf[i].bmax[cut_axis] < cut_pos) {               /* bvh.c:1442 */
+                B->boxes[left + nl] = B->boxes_buf[i];
+                nl++;
+            } else {
+                B->boxes[left + nr] = B->boxes_buf[i];                    /* right part fills from the back */
+                nr--;
+            }
+        }
+        if (nl == 0 || nl == n) nl = n / 2;                               /* bvh.c:1471-1478 */
+
+        T->nodes[me].axis = cut_axis;
+
+        bbox_of_range(lmin, lmax, B->boxes + left, nl);
+        add_margin(lmin, lmax);
+        for (k = 0; k < 3; k++) { T->nodes[me].lbox[k] = lmin[k]; T->nodes[me].lbox[3 + k] = lmax[k]; }
+        c0 = construct(B, lmin, lmax, left, left + nl, depth + 1);
+        T->nodes[me].child0 = c0;
+
+        bbox_of_range(rmin, rmax, B->boxes + left + nl, n - nl);
+        add_margin(rmin, rmax);
+        for (k = 0; k < 3; k++) { T->nodes[me].rbox[k] = rmin[k]; T->nodes[me].rbox[3 + k] = rmax[k]; }
+        c1 = construct(B, rmin, rmax, left + nl, right, depth + 1);
+        T->nodes[me].child1 = c1;
+    }
+    return me;
+}
+
+static float f32_down(double x) { float f = (float)x; if ((double)f > x) f = nextafterf(f, -INFINITY); return f; }
+static float f32_up(double x)   { float f = (float)x; if ((double)f < x) f = nextafterf(f,  INFINITY); return f; }
+
+/* Per-precision views.  double: the reference's own numbers.  float: boxes rounded OUTWARD
+ * (min down, max up) so fp32 culling stays conservative w.r.t. the double tree; vertices rounded
+ * to nearest; e1/e2 subtracted in fp32 (the same subtraction triangle_isect does per test). */
+static void make_views(orc_tree *T)
+{
+    int64_t i; uint64_t p; int k;
+    T->lbox64 = (double *)malloc(sizeof(double) * 6 * (size_t)T->nnodes);
+    T->rbox64 = (double *)malloc(sizeof(double) * 6 * (size_t)T->nnodes);
+    T->lbox32 = (float *)malloc(sizeof(float) * 6 * (size_t)T->nnodes);
+    T->rbox32 = (float *)malloc(sizeof(float) * 6 * (size_t)T->nnodes);
+    T->tri64  = (double *)malloc(sizeof(double) * 9 * (size_t)T->ntris);
+    T->tri32  = (float *)malloc(sizeof(float) * 9 * (size_t)T->ntris);
+    for (i = 0; i < T->nnodes; i++) {
+        const orc_node_t *n = &T->nodes[i];
+        for (k = 0; k < 6; k++) { T->lbox64[6 * i + k] = n->lbox[k]; T->rbox64[6 * i + k] = n->rbox[k]; }
+        for (k = 0; k < 3; k++) {
+            T->lbox32[6 * i + k]     = f32_down(n->lbox[k]);
+            T->lbox32[6 * i + 3 + k] = f32_up(n->lbox[3 + k]);
+            T->rbox32[6 * i + k]     = f32_down(n->rbox[k]);
+            T->rbox32[6 * i + 3 + k] = f32_up(n->rbox[3 + k]);
+        }
+    }
+    for (p = 0; p < T->ntris; p++) {
+        const double *v = T->tri_xyz + 9 * p;
+        double *d = T->tri64 + 9 * p;
+        float  *f = T->tri32 + 9 * p;
+        float v0[3], v1[3], v2[3];
+        for (k = 0; k < 3; k++) {
+            d[k] = v[k]; d[3 + k] = v[3 + k] - v[k]; d[6 + k] = v[6 + k] - v[k];
+            v0[k] = (float)v[k]; v1[k] = (float)v[3 + k]; v2[k] = (float)v[6 + k];
+            f[k] = v0[k]; f[3 + k] = v1[k] - v0[k]; f[6 + k] = v2[k] - v0[k];
+        }
+    }
+    for (k = 0; k < 3; k++) { T->smin32[k] = f32_down(T->bmin[k]); T->smax32[k] = f32_up(T->bmax[k]); }
+}
+
+/* bvh.c:276-379 ri_bvh_build (+ create_triangle_list 1736-1826, calc_scene_bbox 1829-1849) */
+orc_tree *orc_build(const double *tri_xyz, uint64_t ntris)
+{
+    orc_tree *T = (orc_tree *)calloc(1, sizeof(orc_tree));
+    build_ctx B;
+    uint64_t i; int k, c;
+
+    T->ntris = ntris;
+    if (ntris == 0) { T->empty = 1; return T; }               /* bvh.c:311-315 */
+
+    B.T = T; B.tri_in = tri_xyz;
+    B.boxes     = (tbox_t *)malloc(sizeof(tbox_t) * ntris);
+    B.boxes_buf = (tbox_t *)malloc(sizeof(tbox_t) * ntris);
+    T->tri_xyz  = (double *)malloc(sizeof(double) * 9 * ntris);
+    T->orig     = (uint32_t *)malloc(sizeof(uint32_t) * ntris);
+
+    for (i = 0; i < ntris; i++) {                             /* get_bbox_of_triangle, bvh.c:1852-1868 */
+        const double *v = tri_xyz + 9 * i;
+        for (k = 0; k < 3; k++) {
+            double mn = v[k], mx = v[k];
+            for (c = 1; c < 3; c++) {
+                mn = (mn < v[3 * c + k]) ? mn : v[3 * c + k];
+                mx = (mx > v[3 * c + k]) ? mx : v[3 * c + k];
+            }
+            B.boxes[i].bmin[k] = mn; B.boxes[i].bmax[k] = mx;
+        }
+        B.boxes[i].index = i;
+    }
+    bbox_of_range(T->bmin, T->bmax, B.boxes, ntris);          /* calc_scene_bbox */
+    add_margin(T->bmin, T->bmax);                             /* bvh.c:330 */
+
+    construct(&B, T->bmin, T->bmax, 0, ntris, 0);
+
+    free(B.boxes); free(B.boxes_buf);
+    make_views(T);
+    return T;
+}
+
+void orc_free(orc_tree *T)
+{
+    if (!T) return;
+    free(T->nodes); free(T->tri_xyz); free(T->orig);
+    free(T->lbox64); free(T->rbox64); free(T->tri64);
+    free(T->lbox32); free(T->rbox32); free(T->tri32);
+    free(T);
+}
+
+int     orc_is_empty(const orc_tree *T)  { return T->empty; }
+int64_t orc_num_nodes(const orc_tree *T) { return T->nnodes; }
+int     orc_max_depth(const orc_tree *T) { return T->max_depth; }
+int64_t orc_get_nodes(const orc_tree *T, orc_node_t *out)
+{
+    if (T->nnodes) memcpy(out, T->nodes, sizeof(orc_node_t) * (size_t)T->nnodes);
+    return T->nnodes;
+}
+void orc_get_triorder(const orc_tree *T, uint32_t *orig)
+{
+    if (T->ntris && !T->empty) memcpy(orig, T->orig, sizeof(uint32_t) * T->ntris);
+}
+void orc_scene_bbox(const orc_tree *T, double *bmin, double *bmax)
+{
+    int k; for (k = 0; k < 3; k++) { bmin[k] = T->bmin[k]; bmax[k] = T->bmax[k]; }
+}
+
+/* ------------------------------------------------------------------ traversal, both precisions */
+
+#define REAL double
+#define SFX(x) x##_f64
+#define R(x) x
+#define REAL_MAX DBL_MAX
+#define RFABS fabs
+#define RSQRT sqrt
+#include "oracle_trav.inc"
+#undef REAL
+#undef SFX
+#undef R
+#undef REAL_MAX
+#undef RFABS
+#undef RSQRT
+
+#define REAL float
+#define SFX(x) x##_f32
+#define R(x) x##f
+#define REAL_MAX FLT_MAX
+#define RFABS fabsf
+#define RSQRT sqrtf
+#include "oracle_trav.inc"
+#undef REAL
+#undef SFX
+#undef R
+#undef REAL_MAX
+#undef RFABS
+#undef RSQRT
+
+static void view64(const orc_tree *T, view_t_f64 *V)
+{
+    int k;
+    V->lbox = T->lbox64; V->rbox = T->rbox64; V->tri = T->tri64;
+    for (k = 0; k < 3; k++) { V->smin[k] = T->bmin[k]; V->smax[k] = T->bmax[k]; }
+}
+static void view32(const orc_tree *T, view_t_f32 *V)
+{
+    int k;
+    V->lbox = T->lbox32; V->rbox = T->rbox32; V->tri = T->tri32;
+    for (k = 0; k < 3; k++) { V->smin[k] = T->smin32[k]; V->smax[k] = T->smax32[k]; }
+}
+
+void orc_intersect_f64(const orc_tree *T, const double *rays, uint64_t n, orc_hit_f64 *out, orc_counters_t *c)
+{
+    view_t_f64 V = {0}; uint64_t i;
+    if (!T->empty) view64(T, &V);
+    for (i = 0; i < n; i++) {
+        double t = 1.0e38, u = 0, v = 0; uint32_t prim = ORC_MISS_PRIM;
+        int hit = trace_f64(T, &V, rays + 6 * i, rays + 6 * i + 3, 0, &t, &u, &v, &prim, c);
+        out[i].t = hit ? t : 1.0e38; out[i].u = hit ? u : 0.0; out[i].v = hit ? v : 0.0;
+        out[i].prim = hit ? prim : ORC_MISS_PRIM; out[i].hit = (uint32_t)hit;
+    }
+}
+
+void orc_intersect_f32(const orc_tree *T, const float *rays, uint64_t n, orc_hit_f32 *out, orc_counters_t *c)
+{
+    view_t_f32 V = {0}; uint64_t i;
+    if (!T->empty) view32(T, &V);
+    for (i = 0; i < n; i++) {
+        float t = 1.0e38f, u = 0, v = 0; uint32_t prim = ORC_MISS_PRIM;
+        int hit = trace_f32(T, &V, rays + 8 * i, rays + 8 * i + 4, 0, &t, &u, &v, &prim, c);
+        out[i].t = hit ? t : 1.0e38f; out[i].u = hit ? u : 0.0f; out[i].v = hit ? v : 0.0f;
+        out[i].prim = hit ? prim : ORC_MISS_PRIM;
+    }
+}
+
+void orc_occluded_f64(const orc_tree *T, const double *rays, uint64_t n, uint8_t *out, orc_counters_t *c)
+{
+    view_t_f64 V = {0}; uint64_t i;
+    if (!T->empty) view64(T, &V);
+    for (i = 0; i < n; i++) {
+        double t, u, v; uint32_t prim;
+        out[i] = (uint8_t)trace_f64(T, &V, rays + 6 * i, rays + 6 * i + 3, 1, &t, &u, &v, &prim, c);
+    }
+}
+
+void orc_occluded_f32(const orc_tree *T, const float *rays, uint64_t n, uint8_t *out, orc_counters_t *c)
+{
+    view_t_f32 V = {0}; uint64_t i;
+    if (!T->empty) view32(T, &V);
+    for (i = 0; i < n; i++) {
+        float t, u, v; uint32_t prim;
+        out[i] = (uint8_t)trace_f32(T, &V, rays + 8 * i, rays + 8 * i + 4, 1, &t, &u, &v, &prim, c);
+    }
+}
+
+/* ------------------------------------------------------------------ hit state (double) */
+
+/* intersection_state.c:99-248 for geometry carrying only "P": Ns = Ng, tangent/binormal from ri_ortho_basis(Ng).
+ * Ng = normalize((v1-v0) x (v2-v0)), base/geometric.c:20-33.  No face-forwarding. */
+static void state_build(const orc_tree *T, const double org[3], const double dir[3], double t, uint32_t prim, orc_state_f64 *s)
+{
+    const double *v = T->tri_xyz + 9 * (size_t)prim;
+    double v01[3], v02[3], basis[3][3];
+    int k;
+    for (k = 0; k < 3; k++) s->P[k] = org[k] + dir[k] * t;
+    for (k = 0; k < 3; k++) { v01[k] = v[3 + k] - v[k]; v02[k] = v[6 + k] - v[k]; }
+    cross_f64(s->Ng, v01, v02);
+    normalize_f64(s->Ng);
+    for (k = 0; k < 3; k++) s->Ns[k] = s->Ng[k];
+    ortho_basis_f64(basis, s->Ng);
+    for (k = 0; k < 3; k++) { s->tangent[k] = basis[0][k]; s->binormal[k] = basis[1][k]; }
+}
+
+void orc_state_build_f64(const orc_tree *T, const double *rays, const orc_hit_f64 *hits, uint64_t n, orc_state_f64 *out)
+{
+    uint64_t i;
+    for (i = 0; i < n; i++) {
+        if (hits[i].hit) state_build(T, rays + 6 * i, rays + 6 * i + 3, hits[i].t, hits[i].prim, &out[i]);
+        else memset(&out[i], 0, sizeof(out[i]));
+    }
+}
+
+/* ------------------------------------------------------------------ MT19937 (random.c) */
+
+typedef struct { uint32_t mt[624]; int mti; } mt_t;
+
+/* random.c:98-112 seedMT2: mt[i] = 69069 * mt[i-1] (1998 seeding) */
+static void mt_seed(mt_t *m, uint32_t seed)
+{
+    int i;
+    m->mt[0] = seed;
+    for (i = 1; i < 624; i++) m->mt[i] = 69069u * m->mt[i - 1];
+    m->mti = 624;
+}
+
+/* random.c:211-247 randomMT2 (integer part) */
+static uint32_t mt_next_u32(mt_t *m)
+{
+    static const uint32_t mag01[2] = { 0x0u, 0x9908b0dfu };
+    uint32_t y;
+    if (m->mti >= 624) {
+        int kk;
+        for (kk = 0; kk < 624 - 397; kk++) {
+            y = (m->mt[kk] & 0x80000000u) | (m->mt[kk + 1] & 0x7fffffffu);
+            m->mt[kk] = m->mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1];
+        }
+        for (; kk < 623; kk++) {
+            y = (m->mt[kk] & 0x80000000u) | (m->mt[kk + 1] & 0x7fffffffu);
+            m->mt[kk] = m->mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1];
+        }
+        y = (m->mt[623] & 0x80000000u) | (m->mt[0] & 0x7fffffffu);
+        m->mt[623] = m->mt[396] ^ (y >> 1) ^ mag01[y & 1];
+        m->mti = 0;
+    }
+    y = m->mt[m->mti++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+static double mt_next(mt_t *m) { return (double)mt_next_u32(m) * 2.3283064365386963e-10; }
+
+void orc_mt_stream(uint32_t seed, uint64_t n, double *out)
+{
+    mt_t m; uint64_t i;
+    mt_seed(&m, seed);
+    for (i = 0; i < n; i++) out[i] = mt_next(&m);
+}
+
+void orc_mt_stream_u32(uint32_t seed, uint64_t n, uint32_t *out)
+{
+    mt_t m; uint64_t i;
+    mt_seed(&m, seed);
+    for (i = 0; i < n; i++) out[i] = mt_next_u32(&m);
+}
+
+/* ------------------------------------------------------------------ pixel loop */
+
+/* spiral.c:97-140 NthBucketSpiral */
+static void nth_bucket_spiral(int n, int nxb, int nyb, int *bx, int *by)
+{
+    int nx, ny, nxny, minnxny, x, y;
+    int minnb = (nxb < nyb) ? nxb : nyb;
+    int center = (minnb - 1) / 2;
+    nx = nxb; ny = nyb;
+    while (n < nx * ny) { nx = nx - 1; ny = ny - 1; }
+    nxny = nx * ny;
+    minnxny = (nx < ny) ? nx : ny;
+    if (minnxny % 2 == 1) {
+        if (n <= (nxny + ny)) { x = nx - minnxny / 2; y = -minnxny / 2 + n - nxny; }
+        else { x = nx - minnxny / 2 - (n - (nxny + ny)); y = ny - minnxny / 2; }
+    } else {
+        if (n <= (nxny + ny)) { x = -minnxny / 2; y = ny - minnxny / 2 - (n - nxny); }
+        else { x = -minnxny / 2 + (n - (nxny + ny)); y = -minnxny / 2; }
+    }
+    *bx = x + center; *by = y + center;
+}
+
+/* render.c:582-710 create_bucket_list with BUCKET_ORDER_SPIRAL */
+int orc_bucket_list(int width, int height, int bucket_size, int32_t *out, int max_buckets)
+{
+    int nxb = width / bucket_size + ((width % bucket_size) ? 1 : 0);
+    int nyb = height / bucket_size + ((height % bucket_size) ? 1 : 0);
+    int wrem = width % bucket_size, hrem = height % bucket_size;
+    int n, nb = nxb * nyb;
+    if (nb > max_buckets) return -nb;
+    for (n = 0; n < nb; n++) {
+        int bx, by, w, h;
+        nth_bucket_spiral(n, nxb, nyb, &bx, &by);
+        w = (bx == nxb - 1 && wrem) ? wrem : bucket_size;
+        h = (by == nyb - 1 && hrem) ? hrem : bucket_size;
+        out[4 * n + 0] = bx * bucket_size; out[4 * n + 1] = by * bucket_size;
+        out[4 * n + 2] = w; out[4 * n + 3] = h;
+    }
+    return nb;
+}
+
+/* render.c:870-917 init_sigma (one table) */
+static void sigma_table(unsigned int period, unsigned int *sigma)
+{
+    unsigned int i, inverse, digit, bits;
+    for (i = 0; i < period; i++) {
+        digit = period; inverse = 0;
+        for (bits = i; bits; bits >>= 1) {
+            digit >>= 1;
+            if (bits & 1) inverse += digit;
+        }
+        sigma[i] = inverse;
+    }
+}
+
+/* render.c:830-861 sample_subpixel (note: periodx masks both indices) */
+void orc_subpixel_jitter(int xs, int ys, int xsamples, int ysamples, double *jx, double *jy)
+{
+    unsigned int sx[256], sy[256];
+    unsigned int periodx = (unsigned int)xsamples, periody = (unsigned int)ysamples;
+    unsigned int j, k;
+    double a, b;
+    sigma_table(periodx, sx);
+    sigma_table(periody, sy);
+    j = (unsigned int)xs & (periodx - 1);
+    k = (unsigned int)ys & (periodx - 1);
+    a = (double)xs + (double)sx[k] / (double)periodx;
+    b = (double)ys + (double)sy[j] / (double)periody;
+    a /= (double)xsamples;
+    b /= (double)ysamples;
+    a += 0.5 / (xsamples * xsamples);
+    b += 0.5 / (ysamples * ysamples);
+    *jx = a; *jy = b;
+}
+
+/* camera.c:248-352 (perspective, flength > 0) + render.c:770-781 */
+void orc_camera_ray(const orc_frame_t *f, double x, double y, double *org, double *dir)
+{
+    double v[4], pos[4], dirpos[4];
+    double w = f->width, h = f->height;
+    float sign = f->is_rh ? -1.0 : 1.0;
+    int i, j;
+    v[0] = (2.0f * x - w) / w;
+    v[1] = (2.0f * y - h) / h;
+    v[2] = sign * f->flength;
+    v[3] = 1.0;
+    for (j = 0; j < 4; j++) {                  /* ri_vector_transform(pos, (0,0,0,1), c2w), vector.h:182-210 */
+        double o[4] = { 0.0, 0.0, 0.0, 1.0 };
+        pos[j] = 0.0;
+        for (i = 0; i < 4; i++) pos[j] += o[i] * f->c2w[4 * i + j];
+    }
+    for (j = 0; j < 4; j++) {
+        dirpos[j] = 0.0;
+        for (i = 0; i < 4; i++) dirpos[j] += v[i] * f->c2w[4 * i + j];
+    }
+    for (j = 0; j < 3; j++) { org[j] = pos[j]; dir[j] = dirpos[j] - pos[j]; }
+    normalize_f64(dir);
+}
+
+/* ambientocclusion.c:42-151 calculate_occlusion */
+static double ao_radiance(const orc_tree *T, const view_t_f64 *V, const orc_state_f64 *s,
+                          int ntheta, int nphi, mt_t *rng, uint64_t *nrays)
+{
+    double basis[3][3], org[3], dirl[3], dir[3];
+    const double eps = 1.0e-6;
+    double occlusion = 0.0, nsamples;
+    uint32_t i, j; int k;
+
+    ortho_basis_f64(basis, s->Ns);
+    for (k = 0; k < 3; k++) org[k] = s->P[k];
+    for (k = 0; k < 3; k++) org[k] += s->Ns[k] * eps;
+
+    for (j = 0; j < (uint32_t)nphi; j++) {
+        for (i = 0; i < (uint32_t)ntheta; i++) {
+            double z0 = (i + mt_next(rng)) / (double)ntheta;
+            double z1 = (j + mt_next(rng)) / (double)nphi;
+            double cos_theta = sqrt(z0);
+            double phi = 2.0 * M_PI * z1;
+            double t, u, v; uint32_t prim;
+            dirl[0] = cos(phi) * cos_theta;
+            dirl[1] = sin(phi) * cos_theta;
+            dirl[2] = sqrt(1.0 - cos_theta * cos_theta);
+            for (k = 0; k < 3; k++)
+                dir[k] = dirl[0] * basis[0][k] + dirl[1] * basis[1][k] + dirl[2] * basis[2][k];
+            (*nrays)++;
+            if (trace_f64(T, V, org, dir, 0, &t, &u, &v, &prim, NULL)) occlusion += 1.0;
+        }
+    }
+    nsamples = ntheta * nphi;
+    return 1.0 * (nsamples - occlusion) / nsamples;
+}
+
+/* render.c:1107-1146 render_bucket, 715-823 subsample, 919-979 bucket_write;
+ * ambientocclusion.c:332-415 ri_transport_ambientocclusion (no sun-sky, no texture). */
+void orc_render_ao(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t *nrays_out)
+{
+    int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(f->width, f->height, f->bucket_size, buckets, nb_max);
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t nrays = 0;
+    int b;
+
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, 4357);                                       /* random.c:221 */
+
+    for (b = 0; b < nb; b++) {
+        int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        int u, v;
+        for (v = by; v < by + bh; v++) {
+            for (u = bx; u < bx + bw; u++) {
+                double accum = 0.0, px;
+                int xs, ys;
+                for (ys = 0; ys < f->ysamples; ys++) {
+                    for (xs = 0; xs < f->xsamples; xs++) {
+                        double jx, jy, org[3], dir[3], t, uu, vv, rad = 0.0;
+                        uint32_t prim;
+                        orc_subpixel_jitter(xs, ys, f->xsamples, f->ysamples, &jx, &jy);
+                        orc_camera_ray(f, (double)(u + jx), (double)(v + jy), org, dir);
+                        nrays++;
+                        if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+                            orc_state_f64 s;
+                            state_build(T, org, dir, t, prim, &s);
+                            rad = ao_radiance(T, &V, &s, f->ntheta, f->nphi, &rng, &nrays);
+                        }
+                        accum = accum + rad;
+                    }
+                }
+                px = accum * ((double)1.0 / (f->xsamples * f->ysamples));
+                {
+                    float *dst = rgb + 3 * ((size_t)(f->height - v - 1) * f->width + u);
+                    dst[0] = dst[1] = dst[2] = (float)px;
+                }
+            }
+        }
+    }
+    free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
+/* counter-based generator shared with the product for the synthetic configs */
+uint64_t orc_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}

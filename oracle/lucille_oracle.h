@@ -1,0 +1,110 @@
+/*
+ * lucille_oracle.h -- TEST INFRASTRUCTURE, not product code.
+ *
+ * CPU restatement of lucille's ray-intersection hot path (BVH build, ray traversal,
+ * leaf Moeller-Trumbore, hit-state build, ambient-occlusion sample loop, pixel loop).
+ * Every function cites the reference file:line it follows (paths relative to the
+ * reference root).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (lucille_b200/) never does.
+ *
+ * PARITY PINNING: the double-precision instantiation is pinned bit-for-bit against the
+ * compiled, unmodified reference (oracle/_ref/libluciref.so, built by oracle/build_ref.sh)
+ * -- identical trees, identical (hit,t,u,v,triangle) per ray, identical AO frames -- by
+ * tests/test_oracle_vs_reference.py and, where /root/reference is absent, against the
+ * golden vectors those runs produced (tests/golden/, generator: tests/golden/make_golden.py).
+ * The reference's own tests hold no numbers for this path.
+ *
+ * The single-precision instantiation is the same code with REAL=float (no FMA contraction:
+ * compile with -ffp-contract=off).  It is the bit-exact target for the fp32 CUDA kernels.
+ */
+#ifndef LUCILLE_ORACLE_H
+#define LUCILLE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_INFINITY   1.0e38      /* RI_INFINITY, include/ri.h:47 */
+#define ORC_EPS        1.0e-14     /* RI_EPS, src/base/common.h:27 */
+#define ORC_LEAF_TRIS  16          /* BVH_NTRIS_LEAF, src/render/bvh.c:81 */
+#define ORC_BINS       64          /* BVH_BIN_SIZE,  src/render/bvh.c:82 */
+#define ORC_MISS_PRIM  0xffffffffu
+
+/* canonical interchange form of a tree: DFS preorder, same layout as ref_shim.c's lref_node_t */
+typedef struct {
+    int32_t is_leaf;
+    int32_t axis;
+    int64_t child0, child1;
+    int64_t tri_start, ntris;
+    double  lbox[6];             /* slot 0: min xyz, max xyz */
+    double  rbox[6];             /* slot 1 */
+} orc_node_t;
+
+typedef struct { double t, u, v; uint32_t prim; uint32_t hit; } orc_hit_f64;   /* prim = position in post-build order */
+typedef struct { float  t, u, v; uint32_t prim; } orc_hit_f32;                 /* miss: t=1e38, prim=ORC_MISS_PRIM */
+
+/* hit-state subset the AO transport consumes (intersection_state.h:34-61) */
+typedef struct { double P[3], Ng[3], Ns[3], tangent[3], binormal[3]; } orc_state_f64;
+
+typedef struct {
+    uint64_t nrays, ninner, nleaf, ntris, nhit_tris;   /* g_stattrav fields, bvh.h:119-130 */
+} orc_counters_t;
+
+typedef struct {
+    double c2w[16];              /* camera_to_world, row-vector convention (vector.h:182-) */
+    double flength;              /* 1/tan(fov*3.141592/360), camera.c:219 */
+    int32_t is_rh;               /* Orientation "rh" -> sign -1, camera.c:269 */
+    int32_t width, height;
+    int32_t xsamples, ysamples;  /* PixelSamples */
+    int32_t ntheta, nphi;        /* (int)sqrt(gather_nsamples) each, ambientocclusion.c:378-387 */
+    int32_t bucket_size;         /* 32, render.c:197 */
+} orc_frame_t;
+
+typedef struct orc_tree orc_tree;
+
+orc_tree *orc_build(const double *tri_xyz, uint64_t ntris);           /* bvh.c:276-379 */
+void      orc_free(orc_tree *t);
+int       orc_is_empty(const orc_tree *t);
+int64_t   orc_num_nodes(const orc_tree *t);
+int64_t   orc_get_nodes(const orc_tree *t, orc_node_t *out);          /* DFS preorder */
+void      orc_get_triorder(const orc_tree *t, uint32_t *orig);        /* post-build position -> input triangle */
+void      orc_scene_bbox(const orc_tree *t, double *bmin, double *bmax);
+int       orc_max_depth(const orc_tree *t);
+
+/* closest hit, reference order (bvh.c:430-542, 1092-1188). rays f64: [n][6] org,dir. f32: [n][8] ox,oy,oz,tmin,dx,dy,dz,tmax
+ * (tmin/tmax are carried but never read, exactly like ri_ray_t.min_t/max_t). counters may be NULL. */
+void orc_intersect_f64(const orc_tree *t, const double *rays, uint64_t n, orc_hit_f64 *out, orc_counters_t *c);
+void orc_intersect_f32(const orc_tree *t, const float  *rays, uint64_t n, orc_hit_f32 *out, orc_counters_t *c);
+/* occlusion boolean = (closest-hit found a hit); traversal stops at the first leaf that records a hit */
+void orc_occluded_f64(const orc_tree *t, const double *rays, uint64_t n, uint8_t *out, orc_counters_t *c);
+void orc_occluded_f32(const orc_tree *t, const float  *rays, uint64_t n, uint8_t *out, orc_counters_t *c);
+
+/* post-hit state (intersection_state.c:99-248, geometry without normals/colours/st) */
+void orc_state_build_f64(const orc_tree *t, const double *rays, const orc_hit_f64 *hits, uint64_t n, orc_state_f64 *out);
+
+/* MT19937 stream of randomMT2() (random.c:98-112, 211-247): n doubles in [0,1) from seed 4357 */
+void orc_mt_stream(uint32_t seed, uint64_t n, double *out);
+void orc_mt_stream_u32(uint32_t seed, uint64_t n, uint32_t *out);
+
+/* spiral bucket order (spiral.c:68-130, render.c:582-710): writes nb (x,y,w,h) int32 quadruples, returns nb */
+int orc_bucket_list(int width, int height, int bucket_size, int32_t *out_xywh, int max_buckets);
+
+/* Hammersley sub-pixel jitter (render.c:830-917) */
+void orc_subpixel_jitter(int xs, int ys, int xsamples, int ysamples, double *jx, double *jy);
+
+/* camera ray (camera.c:248-352 perspective branch + render.c:770-781 normalise) */
+void orc_camera_ray(const orc_frame_t *f, double x, double y, double *org3, double *dir3);
+
+/* full ambient-occlusion frame, single MT stream, spiral bucket order = the reference at --nthreads 1
+ * (render.c:715-823,1107-1146; ambientocclusion.c:42-151,332-415). rgb: [h][w][3] float, row (H-1-y). */
+void orc_render_ao(const orc_tree *t, const orc_frame_t *f, float *rgb, uint64_t *nrays_out);
+
+/* counter-based uniform for the synthetic configs (shared definition with the product) */
+uint64_t orc_splitmix64(uint64_t x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,334 @@
+"""ctypes bindings for the two checkers (TEST INFRASTRUCTURE):
+
+* ``Oracle``    -- oracle/liblucille_oracle.so, the CPU restatement (oracle/lucille_oracle.c)
+* ``Reference`` -- oracle/_ref/libluciref{,_stat}.so, the compiled unmodified reference (oracle/build_ref.sh)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liblucille_oracle.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_SO = os.path.join(REF_DIR, "libluciref.so")
+REF_STAT_SO = os.path.join(REF_DIR, "libluciref_stat.so")
+ORACLE_RIB = os.path.join(REF_DIR, "oracle_rib")
+
+NODE_DTYPE = np.dtype([("is_leaf", "<i4"), ("axis", "<i4"), ("child0", "<i8"), ("child1", "<i8"),
+                       ("tri_start", "<i8"), ("ntris", "<i8"), ("lbox", "<f8", 6), ("rbox", "<f8", 6)])
+HIT64_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim", "<u4"), ("hit", "<u4")])
+HIT32_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
+STATE_DTYPE = np.dtype([("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
+COUNTERS_DTYPE = np.dtype([("nrays", "<u8"), ("ninner", "<u8"), ("nleaf", "<u8"), ("ntris", "<u8"), ("nhit_tris", "<u8")])
+REFHIT_DTYPE = np.dtype([("hit", "<i4"), ("index", "<u4"), ("geom_id", "<u4"), ("pad", "<u4"),
+                         ("t", "<f8"), ("u", "<f8"), ("v", "<f8"),
+                         ("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
+MISS_PRIM = 0xFFFFFFFF
+
+
+class FrameParams(C.Structure):
+    _fields_ = [("c2w", C.c_double * 16), ("flength", C.c_double), ("is_rh", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("xsamples", C.c_int32), ("ysamples", C.c_int32),
+                ("ntheta", C.c_int32), ("nphi", C.c_int32), ("bucket_size", C.c_int32)]
+
+
+def oracle_available() -> bool:
+    return os.path.exists(ORACLE_SO)
+
+
+def reference_available() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleTree:
+    def __init__(self, lib, handle, ntris):
+        self.lib, self.h, self.ntris = lib, handle, ntris
+
+    def __del__(self):
+        try:
+            self.lib.orc_free(self.h)
+        except Exception:
+            pass
+
+    @property
+    def empty(self):
+        return bool(self.lib.orc_is_empty(self.h))
+
+    def nodes(self) -> np.ndarray:
+        n = self.lib.orc_num_nodes(self.h)
+        out = np.zeros(n, dtype=NODE_DTYPE)
+        if n:
+            self.lib.orc_get_nodes(self.h, _ptr(out))
+        return out
+
+    def triorder(self) -> np.ndarray:
+        out = np.zeros(self.ntris, dtype=np.uint32)
+        self.lib.orc_get_triorder(self.h, _ptr(out))
+        return out
+
+    def bbox(self):
+        a, b = np.zeros(3), np.zeros(3)
+        self.lib.orc_scene_bbox(self.h, _ptr(a), _ptr(b))
+        return a, b
+
+    def max_depth(self):
+        return self.lib.orc_max_depth(self.h)
+
+    def intersect_f64(self, rays6: np.ndarray, counters: bool = False):
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        out = np.zeros(len(rays6), dtype=HIT64_DTYPE)
+        cnt = np.zeros(1, dtype=COUNTERS_DTYPE)
+        self.lib.orc_intersect_f64(self.h, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out), _ptr(cnt) if counters else None)
+        return (out, cnt[0]) if counters else out
+
+    def intersect_f32(self, rays8: np.ndarray, counters: bool = False):
+        rays8 = np.ascontiguousarray(rays8, dtype=np.float32)
+        out = np.zeros(len(rays8), dtype=HIT32_DTYPE)
+        cnt = np.zeros(1, dtype=COUNTERS_DTYPE)
+        self.lib.orc_intersect_f32(self.h, _ptr(rays8), C.c_uint64(len(rays8)), _ptr(out), _ptr(cnt) if counters else None)
+        return (out, cnt[0]) if counters else out
+
+    def occluded_f64(self, rays6: np.ndarray, counters: bool = False):
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        out = np.zeros(len(rays6), dtype=np.uint8)
+        cnt = np.zeros(1, dtype=COUNTERS_DTYPE)
+        self.lib.orc_occluded_f64(self.h, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out), _ptr(cnt) if counters else None)
+        return (out, cnt[0]) if counters else out
+
+    def occluded_f32(self, rays8: np.ndarray, counters: bool = False):
+        rays8 = np.ascontiguousarray(rays8, dtype=np.float32)
+        out = np.zeros(len(rays8), dtype=np.uint8)
+        cnt = np.zeros(1, dtype=COUNTERS_DTYPE)
+        self.lib.orc_occluded_f32(self.h, _ptr(rays8), C.c_uint64(len(rays8)), _ptr(out), _ptr(cnt) if counters else None)
+        return (out, cnt[0]) if counters else out
+
+    def state_build(self, rays6: np.ndarray, hits: np.ndarray) -> np.ndarray:
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        out = np.zeros(len(rays6), dtype=STATE_DTYPE)
+        self.lib.orc_state_build_f64(self.h, _ptr(rays6), _ptr(hits), C.c_uint64(len(rays6)), _ptr(out))
+        return out
+
+    def render_ao(self, frame: "FrameParams"):
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_ao(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
+
+class Oracle:
+    def __init__(self):
+        if not oracle_available():
+            raise RuntimeError(f"{ORACLE_SO} missing: run `make -C oracle liblucille_oracle.so` or __graft_entry__.build()")
+        lib = C.CDLL(ORACLE_SO)
+        lib.orc_build.restype = C.c_void_p
+        lib.orc_build.argtypes = [C.c_void_p, C.c_uint64]
+        lib.orc_free.argtypes = [C.c_void_p]
+        lib.orc_is_empty.argtypes = [C.c_void_p]
+        lib.orc_num_nodes.restype = C.c_int64
+        lib.orc_num_nodes.argtypes = [C.c_void_p]
+        lib.orc_get_nodes.restype = C.c_int64
+        lib.orc_get_nodes.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_get_triorder.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_scene_bbox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_max_depth.argtypes = [C.c_void_p]
+        for name in ("orc_intersect_f64", "orc_intersect_f32", "orc_occluded_f64", "orc_occluded_f32"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+            getattr(lib, name).restype = None
+        lib.orc_state_build_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_mt_stream.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
+        lib.orc_mt_stream_u32.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
+        lib.orc_bucket_list.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        lib.orc_subpixel_jitter.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.orc_camera_ray.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        lib.orc_render_ao.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_splitmix64.restype = C.c_uint64
+        lib.orc_splitmix64.argtypes = [C.c_uint64]
+        self.lib = lib
+
+    def build(self, tris: np.ndarray) -> OracleTree:
+        tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 9)
+        return OracleTree(self.lib, self.lib.orc_build(_ptr(tris), C.c_uint64(len(tris))), len(tris))
+
+    def mt_stream(self, n: int, seed: int = 4357) -> np.ndarray:
+        out = np.zeros(n, dtype=np.float64)
+        self.lib.orc_mt_stream(seed, n, _ptr(out))
+        return out
+
+    def mt_stream_u32(self, n: int, seed: int = 4357) -> np.ndarray:
+        out = np.zeros(n, dtype=np.uint32)
+        self.lib.orc_mt_stream_u32(seed, n, _ptr(out))
+        return out
+
+    def bucket_list(self, w: int, h: int, bucket: int = 32) -> np.ndarray:
+        nb = ((w + bucket - 1) // bucket) * ((h + bucket - 1) // bucket)
+        out = np.zeros((nb, 4), dtype=np.int32)
+        n = self.lib.orc_bucket_list(w, h, bucket, _ptr(out), nb)
+        assert n == nb
+        return out
+
+    def subpixel_jitter(self, xs, ys, xsamples, ysamples):
+        a, b = C.c_double(), C.c_double()
+        self.lib.orc_subpixel_jitter(xs, ys, xsamples, ysamples, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def camera_ray(self, frame: FrameParams, x: float, y: float):
+        o, d = np.zeros(3), np.zeros(3)
+        self.lib.orc_camera_ray(C.byref(frame), x, y, _ptr(o), _ptr(d))
+        return o, d
+
+
+class ReferenceScene:
+    def __init__(self, lib, handle, ntris):
+        self.lib, self.h, self.ntris = lib, handle, ntris
+
+    @property
+    def empty(self):
+        return bool(self.lib.lref_is_empty(self.h))
+
+    def build_seconds(self):
+        return self.lib.lref_build_seconds(self.h)
+
+    def nodes(self) -> np.ndarray:
+        ninner, nleaf, depth = C.c_int64(), C.c_int64(), C.c_int()
+        self.lib.lref_tree_count(self.h, C.byref(ninner), C.byref(nleaf), C.byref(depth))
+        out = np.zeros(ninner.value + nleaf.value, dtype=NODE_DTYPE)
+        if len(out):
+            self.lib.lref_tree_dump(self.h, _ptr(out))
+        return out
+
+    def max_depth(self):
+        ninner, nleaf, depth = C.c_int64(), C.c_int64(), C.c_int()
+        self.lib.lref_tree_count(self.h, C.byref(ninner), C.byref(nleaf), C.byref(depth))
+        return depth.value
+
+    def triorder(self) -> np.ndarray:
+        out = np.zeros(self.ntris, dtype=np.uint32)
+        if not self.empty:
+            self.lib.lref_tree_triorder(self.h, _ptr(out))
+        return out
+
+    def bbox(self):
+        a, b = np.zeros(3), np.zeros(3)
+        self.lib.lref_scene_bbox(self.h, _ptr(a), _ptr(b))
+        return a, b
+
+    def intersect(self, rays6: np.ndarray, nthreads: int = 1, want_hits: bool = True):
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        out = np.zeros(len(rays6), dtype=REFHIT_DTYPE) if want_hits else None
+        sec = self.lib.lref_intersect(self.h, _ptr(rays6), C.c_uint64(len(rays6)), nthreads,
+                                      _ptr(out) if want_hits else None)
+        return out, sec
+
+    def beam_visibility(self, org, dirs) -> int:
+        org = np.ascontiguousarray(org, dtype=np.float64)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float64)
+        return self.lib.lref_beam_visibility(self.h, _ptr(org), _ptr(dirs))
+
+
+class Reference:
+    """The compiled reference.  ``stats=True`` loads the -DRI_BVH_TRACE_STATISTICS build (single-threaded counters)."""
+
+    def __init__(self, stats: bool = False):
+        path = REF_STAT_SO if stats else REF_SO
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run oracle/build_ref.sh where /root/reference exists")
+        lib = C.CDLL(path)
+        lib.lref_scene_build.restype = C.c_void_p
+        lib.lref_scene_build.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        lib.lref_build_seconds.restype = C.c_double
+        lib.lref_build_seconds.argtypes = [C.c_void_p]
+        lib.lref_is_empty.argtypes = [C.c_void_p]
+        lib.lref_scene_bbox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_tree_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_tree_dump.restype = C.c_int64
+        lib.lref_tree_dump.argtypes = [C.c_void_p, C.c_void_p]
+        lib.lref_tree_triorder.argtypes = [C.c_void_p, C.c_void_p]
+        lib.lref_intersect.restype = C.c_double
+        lib.lref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        lib.lref_stats_get.argtypes = [C.c_void_p]
+        lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib = lib
+        self.stats = stats
+
+    def build(self, tris: np.ndarray, geom_sizes=None) -> ReferenceScene:
+        tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 9)
+        if geom_sizes is None:
+            h = self.lib.lref_scene_build(_ptr(tris), C.c_uint64(len(tris)), None, 1)
+        else:
+            gs = np.ascontiguousarray(geom_sizes, dtype=np.uint64)
+            h = self.lib.lref_scene_build(_ptr(tris), C.c_uint64(len(tris)), _ptr(gs), len(gs))
+        return ReferenceScene(self.lib, h, len(tris))
+
+    def stats_reset(self):
+        self.lib.lref_stats_reset()
+
+    def stats_get(self):
+        out = np.zeros(6, dtype=np.uint64)
+        self.lib.lref_stats_get(_ptr(out))
+        return dict(nrays=int(out[0]), ninner=int(out[1]), nleaf=int(out[2]), ntris=int(out[3]), nhit_tris=int(out[4]))
+
+
+def read_frame(path: str):
+    with open(path, "rb") as f:
+        assert f.read(4) == b"LFRM"
+        w, h, _ = np.frombuffer(f.read(12), dtype="<u4")
+        sec = np.frombuffer(f.read(8), dtype="<f8")[0]
+        nrays = int(np.frombuffer(f.read(8), dtype="<u8")[0])
+        rgb = np.frombuffer(f.read(), dtype="<f4").reshape(int(h), int(w), 3).copy()
+    return rgb, float(sec), nrays
+
+
+def read_scene(path: str):
+    with open(path, "rb") as f:
+        assert f.read(4) == b"LSCN"
+        f.read(4)
+        n = int(np.frombuffer(f.read(8), dtype="<u8")[0])
+        cam = np.frombuffer(f.read(8 * 27), dtype="<f8").copy()
+        tris = np.frombuffer(f.read(8 * 9 * n), dtype="<f8").reshape(n, 3, 3).copy()
+        geom = np.frombuffer(f.read(4 * n), dtype="<u4").copy()
+    return tris, geom, cam
+
+
+def run_oracle_rib(rib: str, out: str, scene: str | None = None, nthreads: int = 1, width: int = 0, height: int = 0,
+                   pixelsamples: int = 0, gather: int = 0, timeout: int = 3600):
+    """Run the compiled reference renderer on a RIB in a subprocess (one frame per process)."""
+    cmd = [ORACLE_RIB, rib, "--nthreads", str(nthreads), "--out", out]
+    if scene:
+        cmd += ["--scene", scene]
+    if width and height:
+        cmd += ["--width", str(width), "--height", str(height)]
+    if pixelsamples:
+        cmd += ["--pixelsamples", str(pixelsamples)]
+    if gather:
+        cmd += ["--gather", str(gather)]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
+    return read_frame(out)
+
+
+def frame_params(cam: np.ndarray, width: int, height: int, xsamples: int | None = None, ysamples: int | None = None,
+                 gather: int | None = None, bucket_size: int | None = None) -> FrameParams:
+    """Build FrameParams from the 27-double camera record written by oracle_rib --scene."""
+    import math
+    fp = FrameParams()
+    for i in range(16):
+        fp.c2w[i] = cam[i]
+    fp.flength = cam[16]
+    fp.is_rh = int(cam[17])
+    fp.width, fp.height = width, height
+    fp.xsamples = int(cam[20]) if xsamples is None else xsamples
+    fp.ysamples = int(cam[21]) if ysamples is None else ysamples
+    g = int(cam[22]) if gather is None else gather
+    n = int(math.sqrt(float(g)))
+    fp.ntheta = fp.nphi = n
+    fp.bucket_size = int(cam[23]) if bucket_size is None else bucket_size
+    return fp
