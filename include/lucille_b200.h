@@ -1,0 +1,164 @@
+/*
+ * lucille_b200.h -- C ABI of the B200-native accelerator for lucille's ray-intersection hot path.
+ *
+ * This is the drop-in boundary: a shared library (lucille_b200/libb200accel.so) with plain-C entry
+ * points, no C++/torch types.  Each entry point names the reference interface it replaces
+ * (paths relative to the lucille source tree, commit ff81b332).  INTEGRATION.md shows the
+ * ~40-line binding a lucille maintainer adds in src/render/accel.c to select it with
+ *     Option "raytrace" "accel_method" ["b200"]
+ *
+ * Threading: build/free are called from one thread (render.c:335,1233).  Batch calls serialise
+ * internally on the accelerator's CUDA stream; ri_b200_intersect1() is safe to call from the
+ * reference's <=16 worker threads (render.c:1189-1198) -- it takes a mutex.
+ *
+ * Errors: every int-returning call returns 0 on success, <0 on failure; ri_b200_last_error()
+ * returns a static description (the reference has no error channel beyond ri_accel_bind()'s -1;
+ * the binding logs it with ri_log(LOG_FATAL, ...) and aborts, mirroring reference style).
+ */
+#ifndef LUCILLE_B200_H
+#define LUCILLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RI_ACCEL_B200          2             /* next to RI_ACCEL_UGRID 0 / RI_ACCEL_BVH 1, accel.h:20-21 */
+#define RI_B200_MISS_PRIM      0xffffffffu
+#define RI_B200_INFINITY       1.0e38        /* RI_INFINITY, include/ri.h:47 */
+
+#define RI_B200_PREC_F32       1u            /* fp32 node/triangle records: the throughput path */
+#define RI_B200_PREC_F64       2u            /* double records: bit-identical to the CPU reference */
+#define RI_B200_HOST_ONLY      0x100u        /* build + flatten on the host, no device upload: every trace call on
+                                                such an accelerator fails loudly (used by the CPU-only tests) */
+
+typedef struct ri_b200_accel ri_b200_accel_t;   /* opaque; stored in ri_accel_t.data (accel.h:73) */
+
+/* hit records.  prim = position in the post-build triangle order (the reference's ri_triangle_t[]
+ * after bvh_construct, bvh.c:1897-1917); ri_b200_triorder() maps it back to the input triangle,
+ * from which the binding recovers (geom*, index) exactly as bvh.c:858-859 does. */
+typedef struct { float  t, u, v; uint32_t prim; } ri_b200_hit_f32;                 /* miss: t=1e38, prim=MISS */
+typedef struct { double t, u, v; uint32_t prim; uint32_t hit; } ri_b200_hit_f64;
+
+/* subset of ri_intersection_state_t (intersection_state.h:34-61) produced on device */
+typedef struct { double P[3], Ng[3], Ns[3], tangent[3], binormal[3]; } ri_b200_state_f64;
+
+/* canonical (DFS preorder) view of the tree, for parity checks against the reference-built tree */
+typedef struct {
+    int32_t is_leaf;
+    int32_t axis;                 /* ri_qbvh_node_t.axis0, bvh.h:91 */
+    int64_t child0, child1;       /* inner: indices in this dump */
+    int64_t tri_start, ntris;     /* leaf: slice of the post-build triangle order */
+    double  lbox[6];              /* slot 0 (BMIN_X0.., bvh.h:42-65): min xyz, max xyz */
+    double  rbox[6];              /* slot 1 */
+} ri_b200_node_t;
+
+typedef struct {
+    uint64_t ntris;
+    int64_t  ninner, nleaf;
+    int32_t  max_depth;
+    int32_t  empty;               /* ri_bvh_t.empty, bvh.h:172 */
+    uint32_t precisions;          /* RI_B200_PREC_* resident on the device */
+    int32_t  device;
+    double   bmin[3], bmax[3];    /* ri_bvh_t.bmin/bmax incl. margin, bvh.c:328-338 */
+    double   build_seconds;       /* host build, the reference's "BVH Construction" timer */
+    double   upload_seconds;
+    uint64_t device_bytes;
+} ri_b200_info_t;
+
+/* traversal counters in the reference's own units (ri_bvh_stat_traversal_t, bvh.h:119-130) */
+typedef struct { uint64_t nrays, ninner, nleaf, ntris, nhit_tris; } ri_b200_counters_t;
+
+/* frame description for the on-device ambient-occlusion transport */
+typedef struct {
+    double  c2w[16];              /* ri_camera_t.camera_to_world, row-vector convention (vector.h:182-210) */
+    double  flength;              /* ri_camera_t.flength, camera.c:219 */
+    int32_t is_rh;                /* camera.c:269 */
+    int32_t width, height;
+    int32_t xsamples, ysamples;   /* PixelSamples (ri_display_t.sampling_rates) */
+    int32_t ntheta, nphi;         /* (int)sqrt(gather_nsamples), ambientocclusion.c:378-387 */
+    int32_t bucket_size;          /* ri_render_t.bucket_size (32, render.c:197) */
+    int32_t rng_mode;             /* 0: MT19937 stream, seed 4357, reference consumption order (random.c:211-247)
+                                     1: counter-based SplitMix64 keyed by (seed, sample, j, i, k) */
+    uint32_t seed;
+    int32_t rank, world;          /* buckets b with b % world == rank are rendered; others left zero */
+    int32_t precision;            /* RI_B200_PREC_F64 (reference-exact) or RI_B200_PREC_F32 */
+} ri_b200_frame_t;
+
+typedef struct {
+    uint64_t nrays_primary, nrays_ao, nhits_primary;
+    double   ms_total, ms_primary, ms_rng, ms_ao, ms_resolve;   /* CUDA-event times */
+} ri_b200_frame_stats_t;
+
+const char *ri_b200_last_error(void);
+int         ri_b200_device_count(void);
+
+/* ---- replaces accel_build_func / ri_bvh_build (accel.h:24-25, bvh.c:276-379) ------------------
+ * tri_xyz: [ntris][3][3] doubles in the order create_triangle_list() flattens the scene's geoms
+ * (bvh.c:1736-1826).  Builds the reference's binned-SAH tree on the host (identical topology,
+ * boxes and triangle order), uploads the requested precisions to `device`.  ntris==0 gives a valid
+ * empty accelerator (bvh.c:311-315).  Returns NULL on failure. */
+ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris, uint32_t precisions, int device);
+
+/* ---- replaces accel_free_func / ri_bvh_free (accel.h:27-28, bvh.c:381-387); frees host and device memory */
+void ri_b200_free(ri_b200_accel_t *accel);
+
+int     ri_b200_info(const ri_b200_accel_t *accel, ri_b200_info_t *out);
+int64_t ri_b200_export_nodes(const ri_b200_accel_t *accel, ri_b200_node_t *out, int64_t capacity);
+int     ri_b200_triorder(const ri_b200_accel_t *accel, uint32_t *orig_out);   /* [ntris] */
+/* flat device records of a RI_B200_HOST_ONLY accelerator (layout: lucille_b200/csrc/bvh_build.h); any pointer may be
+ * NULL.  header_out[4] = root_word, ninner, top_count, 0.  Returns ninner. */
+int64_t ri_b200_export_flat(const ri_b200_accel_t *accel, void *nodes32, void *nodes64, void *tris32, void *tris64,
+                            uint32_t *header_out);
+
+/* ---- replaces accel_intersect_func / ri_bvh_intersect for ONE ray (accel.h:30-34, bvh.c:430-542),
+ * double precision, returns 1 on hit / 0 on miss / <0 on error.  state may be NULL. */
+int ri_b200_intersect1(ri_b200_accel_t *accel, const double org[3], const double dir[3],
+                       ri_b200_hit_f64 *hit, ri_b200_state_f64 *state);
+
+/* ---- batched entry points (additions; what the batching hook in render.c:803/1133-1146 calls) --
+ * HOST buffers; host<->device copies are part of the call and pipelined against the kernels.
+ * f32 rays: [n][8] = ox,oy,oz,tmin,dx,dy,dz,tmax (tmin/tmax carried, never read -- ri_ray_t.min_t/max_t
+ * are never read by the BVH, bvh.c:780).  f64 rays: [n][6] = org.xyz, dir.xyz. */
+int ri_b200_intersect_batch_f32(ri_b200_accel_t *accel, const float  *rays, uint64_t n, ri_b200_hit_f32 *out);
+int ri_b200_occluded_batch_f32 (ri_b200_accel_t *accel, const float  *rays, uint64_t n, uint8_t *out);
+int ri_b200_intersect_batch_f64(ri_b200_accel_t *accel, const double *rays, uint64_t n, ri_b200_hit_f64 *out);
+int ri_b200_occluded_batch_f64 (ri_b200_accel_t *accel, const double *rays, uint64_t n, uint8_t *out);
+/* post-hit state, intersection_state.c:99-248 (geometry carrying only "P") */
+int ri_b200_state_batch_f64(ri_b200_accel_t *accel, const double *rays, const ri_b200_hit_f64 *hits, uint64_t n,
+                            ri_b200_state_f64 *out);
+
+/* DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the accelerator's own stream) */
+int ri_b200_intersect_dev_f32(ri_b200_accel_t *accel, const float  *d_rays, uint64_t n, ri_b200_hit_f32 *d_out, void *stream);
+int ri_b200_occluded_dev_f32 (ri_b200_accel_t *accel, const float  *d_rays, uint64_t n, uint8_t *d_out, void *stream);
+int ri_b200_intersect_dev_f64(ri_b200_accel_t *accel, const double *d_rays, uint64_t n, ri_b200_hit_f64 *d_out, void *stream);
+int ri_b200_occluded_dev_f64 (ri_b200_accel_t *accel, const double *d_rays, uint64_t n, uint8_t *d_out, void *stream);
+
+/* the reference's RI_BVH_TRACE_STATISTICS counters (bvh.c:460,829-845,1129-1151) for a HOST batch:
+ * precision = RI_B200_PREC_*, anyhit = stop at the first committed hit */
+int ri_b200_count_batch(ri_b200_accel_t *accel, const void *rays, uint64_t n, uint32_t precision, int anyhit,
+                        ri_b200_counters_t *out);
+
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t ri_b200_launch_count(void);
+
+/* pinned host memory for callers that want the copies to overlap (cudaHostAlloc / cudaFreeHost) */
+void *ri_b200_host_alloc(uint64_t bytes);
+void  ri_b200_host_free(void *p);
+
+/* ---- replaces the pixel loop + transport for one frame: render_bucket/subsample (render.c:715-823,
+ * 1107-1146), ri_transport_ambientocclusion/calculate_occlusion (ambientocclusion.c:42-151,332-415),
+ * bucket_write's float path (render.c:919-979).  rgb_out: HOST [height][width][3] floats, row H-1-y. */
+int ri_b200_render_ao(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *rgb_out, ri_b200_frame_stats_t *stats);
+/* same, framebuffer left in DEVICE memory (d_rgb, [height][width][3]) on `stream`; used by the multi-GPU gather */
+int ri_b200_render_ao_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *d_rgb, void *stream,
+                          ri_b200_frame_stats_t *stats);
+
+/* MT19937 stream of randomMT2() generated on the device (random.c:98-112,211-247); HOST output, for tests */
+int ri_b200_mt_stream(uint32_t seed, uint64_t n, uint32_t *out_u32, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUCILLE_B200_H */

@@ -1,0 +1,346 @@
+"""Host-side mirror of lucille's accelerator interface over the C ABI of ``include/lucille_b200.h``.
+
+The reference's plugin boundary is ``ri_accel_t {build, free, intersect}`` selected by ``ri_accel_bind(accel, method)``
+(src/render/accel.h:44-84, accel.c:72-109), and ``ri_raytrace()`` is the one entry every transport uses
+(src/render/raytrace.c:31-69).  ``Accel`` keeps those names and meanings:
+
+    accel = Accel.bind(RI_ACCEL_B200)         # ri_accel_bind: unknown method -> error (the reference returns -1)
+    accel.build(triangles)                     # accel->build(scene): triangle soup -> opaque device structure
+    hit = accel.intersect(rays)                # accel->intersect, batched: (t, u, v, prim) per ray
+    occ = accel.occluded(rays)                 # the boolean the AO transport uses (ambientocclusion.c:123-129)
+    accel.free()                               # accel->free
+
+All compute happens in ``libb200accel.so`` (hand-written CUDA for sm_100a).  There is no CPU fallback: if the
+library or a CUDA device is missing, calls raise ``B200Error``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+RI_ACCEL_UGRID = 0      # accel.h:20
+RI_ACCEL_BVH = 1        # accel.h:21
+RI_ACCEL_B200 = 2       # the id this backend registers
+
+PREC_F32 = 1
+PREC_F64 = 2
+HOST_ONLY = 0x100
+MISS_PRIM = 0xFFFFFFFF
+RI_INFINITY = 1.0e38
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200accel.so")
+
+HIT32_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
+HIT64_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim", "<u4"), ("hit", "<u4")])
+STATE_DTYPE = np.dtype([("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
+NODE_DTYPE = np.dtype([("is_leaf", "<i4"), ("axis", "<i4"), ("child0", "<i8"), ("child1", "<i8"),
+                       ("tri_start", "<i8"), ("ntris", "<i8"), ("lbox", "<f8", 6), ("rbox", "<f8", 6)])
+NODE32_DTYPE = np.dtype([("x", "<f4", 4), ("y", "<f4", 4), ("z", "<f4", 4), ("c0", "<u4"), ("c1", "<u4"), ("axis", "<u4"), ("pad", "<u4")])
+NODE64_DTYPE = np.dtype([("x", "<f8", 4), ("y", "<f8", 4), ("z", "<f8", 4), ("c0", "<u4"), ("c1", "<u4"), ("axis", "<u4"), ("pad", "<u4", 5)])
+TRI32_DTYPE = np.dtype([("v0", "<f4", 4), ("e1", "<f4", 4), ("e2", "<f4", 4)])
+TRI64_DTYPE = np.dtype([("v0", "<f8", 3), ("e1", "<f8", 3), ("e2", "<f8", 3), ("pad", "<f8")])
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Info(C.Structure):
+    _fields_ = [("ntris", C.c_uint64), ("ninner", C.c_int64), ("nleaf", C.c_int64), ("max_depth", C.c_int32),
+                ("empty", C.c_int32), ("precisions", C.c_uint32), ("device", C.c_int32),
+                ("bmin", C.c_double * 3), ("bmax", C.c_double * 3), ("build_seconds", C.c_double),
+                ("upload_seconds", C.c_double), ("device_bytes", C.c_uint64)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("nrays", C.c_uint64), ("ninner", C.c_uint64), ("nleaf", C.c_uint64), ("ntris", C.c_uint64),
+                ("nhit_tris", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class Frame(C.Structure):
+    """ri_b200_frame_t: camera + sampling description of one ambient-occlusion frame."""
+    _fields_ = [("c2w", C.c_double * 16), ("flength", C.c_double), ("is_rh", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("xsamples", C.c_int32), ("ysamples", C.c_int32),
+                ("ntheta", C.c_int32), ("nphi", C.c_int32), ("bucket_size", C.c_int32), ("rng_mode", C.c_int32),
+                ("seed", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32), ("precision", C.c_int32)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("nrays_primary", C.c_uint64), ("nrays_ao", C.c_uint64), ("nhits_primary", C.c_uint64),
+                ("ms_total", C.c_double), ("ms_primary", C.c_double), ("ms_rng", C.c_double), ("ms_ao", C.c_double),
+                ("ms_resolve", C.c_double)]
+
+    @property
+    def nrays(self):
+        return int(self.nrays_primary + self.nrays_ao)
+
+
+# every symbol include/lucille_b200.h declares: (name, restype, argtypes)
+_P, _U64, _U32, _I = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+ABI = [
+    ("ri_b200_last_error", C.c_char_p, []),
+    ("ri_b200_device_count", _I, []),
+    ("ri_b200_build", _P, [_P, _U64, _U32, _I]),
+    ("ri_b200_free", None, [_P]),
+    ("ri_b200_info", _I, [_P, _P]),
+    ("ri_b200_export_nodes", C.c_int64, [_P, _P, C.c_int64]),
+    ("ri_b200_triorder", _I, [_P, _P]),
+    ("ri_b200_export_flat", C.c_int64, [_P, _P, _P, _P, _P, _P]),
+    ("ri_b200_intersect1", _I, [_P, _P, _P, _P, _P]),
+    ("ri_b200_intersect_batch_f32", _I, [_P, _P, _U64, _P]),
+    ("ri_b200_occluded_batch_f32", _I, [_P, _P, _U64, _P]),
+    ("ri_b200_intersect_batch_f64", _I, [_P, _P, _U64, _P]),
+    ("ri_b200_occluded_batch_f64", _I, [_P, _P, _U64, _P]),
+    ("ri_b200_state_batch_f64", _I, [_P, _P, _P, _U64, _P]),
+    ("ri_b200_intersect_dev_f32", _I, [_P, _P, _U64, _P, _P]),
+    ("ri_b200_occluded_dev_f32", _I, [_P, _P, _U64, _P, _P]),
+    ("ri_b200_intersect_dev_f64", _I, [_P, _P, _U64, _P, _P]),
+    ("ri_b200_occluded_dev_f64", _I, [_P, _P, _U64, _P, _P]),
+    ("ri_b200_count_batch", _I, [_P, _P, _U64, _U32, _I, _P]),
+    ("ri_b200_launch_count", _U64, []),
+    ("ri_b200_host_alloc", _P, [_U64]),
+    ("ri_b200_host_free", None, [_P]),
+    ("ri_b200_render_ao", _I, [_P, _P, _P, _P]),
+    ("ri_b200_render_ao_dev", _I, [_P, _P, _P, _P, _P]),
+    ("ri_b200_mt_stream", _I, [_U32, _U64, _P, _I]),
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree ``libb200accel.so``; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). lucille_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, restype, argtypes in ABI:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load_library().ri_b200_last_error().decode()
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise B200Error(last_error())
+    return rc
+
+
+def device_count() -> int:
+    return load_library().ri_b200_device_count()
+
+
+def launch_count() -> int:
+    return int(load_library().ri_b200_launch_count())
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())        # torch tensor
+
+
+def mt_stream(n: int, seed: int = 4357, device: int = 0) -> np.ndarray:
+    """First ``n`` 32-bit outputs of the reference's randomMT2() stream, generated on the device."""
+    out = np.zeros(n, dtype=np.uint32)
+    _check(load_library().ri_b200_mt_stream(seed, n, _ptr(out), device))
+    return out
+
+
+class Accel:
+    """``ri_accel_t`` for the B200 backend."""
+
+    def __init__(self, method: int = RI_ACCEL_B200):
+        if method != RI_ACCEL_B200:
+            # ri_accel_bind returns -1 for unknown methods (accel.c:102-106); UGRID/BVH live in the CPU reference
+            raise B200Error(f"ri_accel_bind: method {method} is not provided by lucille_b200 (only RI_ACCEL_B200={RI_ACCEL_B200})")
+        self.lib = load_library()
+        self.data = None           # ri_accel_t.data
+        self.ntris = 0
+
+    @classmethod
+    def bind(cls, method: int = RI_ACCEL_B200) -> "Accel":
+        return cls(method)
+
+    # -- accel->build ----------------------------------------------------------------------------
+    def build(self, triangles: np.ndarray, precisions: int = PREC_F32 | PREC_F64, device: int = 0) -> "Accel":
+        """triangles: [ntris,3,3] (or [ntris,9]) float64 in the order the scene's geoms are flattened."""
+        tris = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 9)
+        if self.data is not None:
+            self.free()
+        h = self.lib.ri_b200_build(_ptr(tris), len(tris), precisions, device)
+        if not h:
+            raise B200Error(last_error())
+        self.data = h
+        self.ntris = len(tris)
+        return self
+
+    # -- accel->free -----------------------------------------------------------------------------
+    def free(self):
+        if self.data is not None:
+            self.lib.ri_b200_free(self.data)
+            self.data = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def _h(self):
+        if self.data is None:
+            raise B200Error("accelerator has not been built")
+        return self.data
+
+    # -- introspection ---------------------------------------------------------------------------
+    def info(self) -> Info:
+        out = Info()
+        _check(self.lib.ri_b200_info(self._h(), C.byref(out)))
+        return out
+
+    def nodes(self) -> np.ndarray:
+        n = _check(self.lib.ri_b200_export_nodes(self._h(), None, 0))
+        out = np.zeros(n, dtype=NODE_DTYPE)
+        if n:
+            _check(self.lib.ri_b200_export_nodes(self._h(), _ptr(out), n))
+        return out
+
+    def triorder(self) -> np.ndarray:
+        out = np.zeros(self.ntris, dtype=np.uint32)
+        if self.ntris:
+            _check(self.lib.ri_b200_triorder(self._h(), _ptr(out)))
+        return out
+
+    def flat(self):
+        """Flat device records of a HOST_ONLY accelerator: dict(nodes32, nodes64, tris32, tris64, root_word, top_count)."""
+        hdr = np.zeros(4, dtype=np.uint32)
+        ninner = _check(self.lib.ri_b200_export_flat(self._h(), None, None, None, None, _ptr(hdr)))
+        info = self.info()
+        n32 = np.zeros(ninner if info.precisions & PREC_F32 else 0, dtype=NODE32_DTYPE)
+        n64 = np.zeros(ninner if info.precisions & PREC_F64 else 0, dtype=NODE64_DTYPE)
+        t32 = np.zeros(self.ntris if info.precisions & PREC_F32 else 0, dtype=TRI32_DTYPE)
+        t64 = np.zeros(self.ntris if info.precisions & PREC_F64 else 0, dtype=TRI64_DTYPE)
+        _check(self.lib.ri_b200_export_flat(self._h(), _ptr(n32) if len(n32) else None, _ptr(n64) if len(n64) else None,
+                                            _ptr(t32) if len(t32) else None, _ptr(t64) if len(t64) else None, _ptr(hdr)))
+        return dict(nodes32=n32, nodes64=n64, tris32=t32, tris64=t64, root_word=int(hdr[0]), ninner=int(hdr[1]),
+                    top_count=int(hdr[2]))
+
+    # -- accel->intersect, batched (host buffers) ---------------------------------------------------
+    def intersect(self, rays: np.ndarray) -> np.ndarray:
+        """Closest hit per ray.  float32 [n,8] rays -> HIT32 records; float64 [n,6] rays -> HIT64 records."""
+        rays = np.ascontiguousarray(rays)
+        if rays.dtype == np.float32:
+            assert rays.ndim == 2 and rays.shape[1] == 8, "fp32 rays are [n,8]: ox,oy,oz,tmin,dx,dy,dz,tmax"
+            out = np.zeros(len(rays), dtype=HIT32_DTYPE)
+            _check(self.lib.ri_b200_intersect_batch_f32(self._h(), _ptr(rays), len(rays), _ptr(out)))
+        elif rays.dtype == np.float64:
+            assert rays.ndim == 2 and rays.shape[1] == 6, "fp64 rays are [n,6]: org.xyz, dir.xyz"
+            out = np.zeros(len(rays), dtype=HIT64_DTYPE)
+            _check(self.lib.ri_b200_intersect_batch_f64(self._h(), _ptr(rays), len(rays), _ptr(out)))
+        else:
+            raise B200Error(f"unsupported ray dtype {rays.dtype}")
+        return out
+
+    def occluded(self, rays: np.ndarray) -> np.ndarray:
+        """1 where ri_raytrace() would report a hit (what calculate_occlusion counts), else 0."""
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(len(rays), dtype=np.uint8)
+        if rays.dtype == np.float32:
+            assert rays.ndim == 2 and rays.shape[1] == 8
+            _check(self.lib.ri_b200_occluded_batch_f32(self._h(), _ptr(rays), len(rays), _ptr(out)))
+        elif rays.dtype == np.float64:
+            assert rays.ndim == 2 and rays.shape[1] == 6
+            _check(self.lib.ri_b200_occluded_batch_f64(self._h(), _ptr(rays), len(rays), _ptr(out)))
+        else:
+            raise B200Error(f"unsupported ray dtype {rays.dtype}")
+        return out
+
+    def raytrace(self, org, dir):
+        """``ri_raytrace()`` for one ray (raytrace.c:31-69): returns (hit, HIT64 record, STATE record)."""
+        o = np.ascontiguousarray(org, dtype=np.float64)
+        d = np.ascontiguousarray(dir, dtype=np.float64)
+        hit = np.zeros(1, dtype=HIT64_DTYPE)
+        state = np.zeros(1, dtype=STATE_DTYPE)
+        rc = _check(self.lib.ri_b200_intersect1(self._h(), _ptr(o), _ptr(d), _ptr(hit), _ptr(state)))
+        return bool(rc), hit[0], state[0]
+
+    def state(self, rays6: np.ndarray, hits: np.ndarray) -> np.ndarray:
+        """``ri_intersection_state_build`` for a batch (intersection_state.c:99-248)."""
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
+        hits = np.ascontiguousarray(hits)
+        assert hits.dtype == HIT64_DTYPE
+        out = np.zeros(len(rays6), dtype=STATE_DTYPE)
+        _check(self.lib.ri_b200_state_batch_f64(self._h(), _ptr(rays6), _ptr(hits), len(rays6), _ptr(out)))
+        return out
+
+    def count(self, rays: np.ndarray, anyhit: bool = False) -> dict:
+        """The reference's RI_BVH_TRACE_STATISTICS counters for this batch (bvh.c:682-706)."""
+        rays = np.ascontiguousarray(rays)
+        prec = PREC_F32 if rays.dtype == np.float32 else PREC_F64
+        out = Counters()
+        _check(self.lib.ri_b200_count_batch(self._h(), _ptr(rays), len(rays), prec, int(anyhit), C.byref(out)))
+        return out.as_dict()
+
+    # -- device-resident batches (torch tensors or raw device pointers), asynchronous on `stream` ------
+    def intersect_dev(self, d_rays, n: int, d_out, stream: Optional[int] = None, f64: bool = False):
+        fn = self.lib.ri_b200_intersect_dev_f64 if f64 else self.lib.ri_b200_intersect_dev_f32
+        _check(fn(self._h(), _ptr(d_rays), n, _ptr(d_out), C.c_void_p(stream) if stream else None))
+
+    def occluded_dev(self, d_rays, n: int, d_out, stream: Optional[int] = None, f64: bool = False):
+        fn = self.lib.ri_b200_occluded_dev_f64 if f64 else self.lib.ri_b200_occluded_dev_f32
+        _check(fn(self._h(), _ptr(d_rays), n, _ptr(d_out), C.c_void_p(stream) if stream else None))
+
+    # -- the frame-level transport ------------------------------------------------------------------
+    def render_ao(self, frame: Frame):
+        """One ambient-occlusion frame -> (rgb [h,w,3] float32 on the host, FrameStats)."""
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
+        return rgb, stats
+
+    def render_ao_dev(self, frame: Frame, d_rgb, stream: Optional[int] = None, want_stats: bool = True):
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_ao_dev(self._h(), C.byref(frame), _ptr(d_rgb),
+                                              C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
+        return stats
+
+
+def make_frame(c2w, flength: float, is_rh: bool, width: int, height: int, xsamples: int, ysamples: int,
+               gather_nsamples: int = 64, bucket_size: int = 32, rng_mode: int = 0, seed: int = 4357,
+               rank: int = 0, world: int = 1, precision: int = PREC_F64) -> Frame:
+    """Frame from camera parameters; ``ntheta = nphi = (int)sqrt(gather_nsamples)`` as ambientocclusion.c:378-387."""
+    import math
+    f = Frame()
+    c = np.asarray(c2w, dtype=np.float64).reshape(16)
+    for i in range(16):
+        f.c2w[i] = float(c[i])
+    f.flength = float(flength)
+    f.is_rh = int(bool(is_rh))
+    f.width, f.height = int(width), int(height)
+    f.xsamples, f.ysamples = int(xsamples), int(ysamples)
+    n = int(math.sqrt(float(gather_nsamples)))
+    f.ntheta = f.nphi = n
+    f.bucket_size = int(bucket_size)
+    f.rng_mode = int(rng_mode)
+    f.seed = int(seed)
+    f.rank, f.world = int(rank), int(world)
+    f.precision = int(precision)
+    return f

@@ -1,0 +1,587 @@
+// libb200accel.so -- CUDA kernels (sm_100a) and the C ABI declared in include/lucille_b200.h.
+//
+// Compile with:  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3
+// (-fmad=false is part of the parity contract: see trace.cuh).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/lucille_b200.h"
+#include "bvh_build.h"
+#include "trace.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------
+// error channel + launch accounting
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+#define CUDA_OK(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ------------------------------------------------------------------------------------------------
+// the accelerator object
+// ------------------------------------------------------------------------------------------------
+struct ri_b200_accel {
+    HostTree   tree;
+    FlatTree   flat;          // host copy of the flat records is dropped after upload
+    int        device = 0;
+    uint32_t   precisions = 0;
+    int        sm_count = 148;
+    cudaStream_t stream = nullptr, copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t  ev[8] = {};
+    Node32 *d_nodes32 = nullptr; Tri32 *d_tris32 = nullptr;
+    Node64 *d_nodes64 = nullptr; Tri64 *d_tris64 = nullptr;
+    uint64_t device_bytes = 0;
+    double   upload_seconds = 0.0;
+    // staging for host-buffer batches (double buffered)
+    void    *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
+    unsigned long long *d_counters = nullptr;
+    // single-ray path
+    void *h_pin = nullptr, *d_one = nullptr;
+    std::mutex mu;
+    // frame scratch (grown on demand)
+    void *d_frame[8] = {};
+    uint64_t frame_bytes[8] = {};
+};
+
+template <typename Real> static SceneView<Real> make_view(const ri_b200_accel *a);
+
+template <> SceneView<float> make_view<float>(const ri_b200_accel *a)
+{
+    SceneView<float> v;
+    v.nodes = a->d_nodes32; v.tris = a->d_tris32;
+    for (int k = 0; k < 3; ++k) { v.smin[k] = a->flat.smin32[k]; v.smax[k] = a->flat.smax32[k]; }
+    v.root_word = a->flat.root_word; v.top_count = a->flat.top_count;
+    return v;
+}
+template <> SceneView<double> make_view<double>(const ri_b200_accel *a)
+{
+    SceneView<double> v;
+    v.nodes = a->d_nodes64; v.tris = a->d_tris64;
+    for (int k = 0; k < 3; ++k) { v.smin[k] = a->tree.bmin[k]; v.smax[k] = a->tree.bmax[k]; }
+    v.root_word = a->flat.root_word; v.top_count = a->flat.top_count;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray-batch kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlock = 256;
+
+template <typename Real> struct RayIO;
+template <> struct RayIO<float> {
+    using Hit = ri_b200_hit_f32;
+    static constexpr int kRayStride = 8;
+    static __device__ __forceinline__ void load(const float *rays, uint64_t i, float org[3], float dir[3])
+    {
+        const float4 *p = reinterpret_cast<const float4 *>(rays) + 2 * i;
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        org[0] = a.x; org[1] = a.y; org[2] = a.z;
+        dir[0] = b.x; dir[1] = b.y; dir[2] = b.z;
+    }
+    static __device__ __forceinline__ void store(Hit *out, uint64_t i, bool hit, float t, float u, float v, uint32_t prim)
+    {
+        float4 r;
+        r.x = hit ? t : 1.0e38f; r.y = hit ? u : 0.0f; r.z = hit ? v : 0.0f;
+        r.w = __uint_as_float(hit ? prim : 0xffffffffu);
+        reinterpret_cast<float4 *>(out)[i] = r;
+    }
+};
+template <> struct RayIO<double> {
+    using Hit = ri_b200_hit_f64;
+    static constexpr int kRayStride = 6;
+    static __device__ __forceinline__ void load(const double *rays, uint64_t i, double org[3], double dir[3])
+    {
+        const double2 *p = reinterpret_cast<const double2 *>(rays) + 3 * i;
+        const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        org[0] = a.x; org[1] = a.y; org[2] = b.x;
+        dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
+    }
+    static __device__ __forceinline__ void store(Hit *out, uint64_t i, bool hit, double t, double u, double v, uint32_t prim)
+    {
+        Hit h;
+        h.t = hit ? t : 1.0e38; h.u = hit ? u : 0.0; h.v = hit ? v : 0.0;
+        h.prim = hit ? prim : 0xffffffffu; h.hit = hit ? 1u : 0u;
+        out[i] = h;
+    }
+};
+
+template <typename Real, bool ANYHIT, bool COUNT>
+__global__ void __launch_bounds__(kBlock)
+trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const uint64_t n,
+                   typename RayIO<Real>::Hit *__restrict__ hits, uint8_t *__restrict__ occ,
+                   unsigned long long *__restrict__ counters)
+{
+    extern __shared__ uint32_t s_stack[];
+    uint32_t *stk = s_stack + threadIdx.x;
+    const uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    LaneCounters lc = {0, 0, 0, 0};
+    bool active = i < n;
+    if (active) {
+        Real org[3], dir[3], t, u, v;
+        uint32_t prim;
+        RayIO<Real>::load(rays, i, org, dir);
+        const bool hit = trace_ray<Real, ANYHIT, COUNT>(S, org, dir, stk, kBlock, t, u, v, prim, &lc);
+        if (ANYHIT) occ[i] = hit ? 1 : 0;
+        else RayIO<Real>::store(hits, i, hit, t, u, v, prim);
+    }
+    if (COUNT) {
+        // the reference bumps nrays only for rays that reach ri_bvh_intersect on a non-empty tree (bvh.c:446,460)
+        unsigned long long c[5] = {(active && S.root_word != kDoneWord) ? 1ull : 0ull, lc.ninner, lc.nleaf, lc.ntris, lc.nhit};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long x = c[k];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0 && x) atomicAdd(&counters[k], x);
+        }
+    }
+}
+
+static int stack_capacity(const ri_b200_accel *a)
+{
+    int cap = a->tree.max_depth;
+    if (cap < 1) cap = 1;
+    return cap;
+}
+
+template <typename Real, bool ANYHIT, bool COUNT>
+static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typename RayIO<Real>::Hit *d_hits, uint8_t *d_occ,
+                        unsigned long long *d_counters, cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const int cap = stack_capacity(a);
+    const size_t smem = (size_t)cap * kBlock * sizeof(uint32_t);
+    if (smem > 200 * 1024) return fail("BVH depth %d exceeds the shared-memory traversal stack", cap);
+    auto kern = trace_batch_kernel<Real, ANYHIT, COUNT>;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t blocks = (n + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffull) return fail("batch too large");
+    kern<<<(unsigned)blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays, n, d_hits, d_occ, d_counters);
+    LAUNCHED();
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// build / free / info
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *ri_b200_last_error(void) { return g_err; }
+
+extern "C" int ri_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" uint64_t ri_b200_launch_count(void) { return g_launches.load(); }
+
+template <typename T> static int upload(T **dst, const std::vector<T> &src, uint64_t &bytes)
+{
+    *dst = nullptr;
+    if (src.empty()) return 0;
+    CUDA_OK(cudaMalloc((void **)dst, src.size() * sizeof(T)));
+    CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    bytes += src.size() * sizeof(T);
+    return 0;
+}
+
+extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris, uint32_t precisions, int device)
+{
+    if (ntris > kMaxTris) { fail("too many triangles (%llu > %llu)", (unsigned long long)ntris, (unsigned long long)kMaxTris); return nullptr; }
+    if (!(precisions & (RI_B200_PREC_F32 | RI_B200_PREC_F64))) { fail("no precision requested"); return nullptr; }
+    if (ntris && !tri_xyz) { fail("tri_xyz is NULL"); return nullptr; }
+    const bool host_only = (precisions & RI_B200_HOST_ONLY) != 0;
+    int ndev = 0;
+    if (host_only) {
+        ri_b200_accel *h = new (std::nothrow) ri_b200_accel();
+        if (!h) { fail("out of memory"); return nullptr; }
+        h->device = -1;
+        h->precisions = precisions;
+        build_tree(tri_xyz, ntris, h->tree);
+        flatten_tree(h->tree, 1024, (precisions & RI_B200_PREC_F32) != 0, (precisions & RI_B200_PREC_F64) != 0, h->flat);
+        return h;
+    }
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail("no CUDA device: libb200accel has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail("bad device %d", device); return nullptr; }
+
+    ri_b200_accel *a = new (std::nothrow) ri_b200_accel();
+    if (!a) { fail("out of memory"); return nullptr; }
+    a->device = device;
+    a->precisions = precisions;
+
+    build_tree(tri_xyz, ntris, a->tree);
+    flatten_tree(a->tree, 1024, (precisions & RI_B200_PREC_F32) != 0, (precisions & RI_B200_PREC_F64) != 0, a->flat);
+
+    auto t0 = std::chrono::steady_clock::now();
+    auto body = [&]() -> int {
+        CUDA_OK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        a->sm_count = prop.multiProcessorCount;
+        CUDA_OK(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&a->copy_stream[0], cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&a->copy_stream[1], cudaStreamNonBlocking));
+        for (auto &e : a->ev) CUDA_OK(cudaEventCreate(&e));
+        if (upload(&a->d_nodes32, a->flat.nodes32, a->device_bytes)) return -1;
+        if (upload(&a->d_tris32, a->flat.tris32, a->device_bytes)) return -1;
+        if (upload(&a->d_nodes64, a->flat.nodes64, a->device_bytes)) return -1;
+        if (upload(&a->d_tris64, a->flat.tris64, a->device_bytes)) return -1;
+        CUDA_OK(cudaMalloc((void **)&a->d_counters, 8 * sizeof(unsigned long long)));
+        CUDA_OK(cudaMallocHost(&a->h_pin, 4096));
+        CUDA_OK(cudaMalloc(&a->d_one, 4096));
+        return 0;
+    };
+    if (body() != 0) { ri_b200_free(a); return nullptr; }
+    a->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    // flat host copies are no longer needed (keep the small header fields)
+    std::vector<Node32>().swap(a->flat.nodes32); std::vector<Tri32>().swap(a->flat.tris32);
+    std::vector<Node64>().swap(a->flat.nodes64); std::vector<Tri64>().swap(a->flat.tris64);
+    return a;
+}
+
+extern "C" void ri_b200_free(ri_b200_accel_t *a)
+{
+    if (!a) return;
+    if (a->device < 0) { delete a; return; }
+    cudaSetDevice(a->device);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64);
+    for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
+    for (auto p : a->d_frame) cudaFree(p);
+    cudaFree(a->d_counters); cudaFree(a->d_one);
+    if (a->h_pin) cudaFreeHost(a->h_pin);
+    for (auto &e : a->ev) if (e) cudaEventDestroy(e);
+    if (a->stream) cudaStreamDestroy(a->stream);
+    for (auto &s : a->copy_stream) if (s) cudaStreamDestroy(s);
+    cudaGetLastError();
+    delete a;
+}
+
+extern "C" int ri_b200_info(const ri_b200_accel_t *a, ri_b200_info_t *out)
+{
+    if (!a || !out) return fail("null argument");
+    std::memset(out, 0, sizeof(*out));
+    out->ntris = a->tree.ntris; out->ninner = a->tree.ninner; out->nleaf = a->tree.nleaf;
+    out->max_depth = a->tree.max_depth; out->empty = a->tree.empty ? 1 : 0;
+    out->precisions = a->precisions; out->device = a->device;
+    for (int k = 0; k < 3; ++k) { out->bmin[k] = a->tree.bmin[k]; out->bmax[k] = a->tree.bmax[k]; }
+    out->build_seconds = a->tree.build_seconds; out->upload_seconds = a->upload_seconds;
+    out->device_bytes = a->device_bytes;
+    return 0;
+}
+
+extern "C" int64_t ri_b200_export_nodes(const ri_b200_accel_t *a, ri_b200_node_t *out, int64_t capacity)
+{
+    static_assert(sizeof(ri_b200_node_t) == sizeof(CanonNode), "layout");
+    if (!a) return fail("null argument");
+    const int64_t n = (int64_t)a->tree.nodes.size();
+    if (!out) return n;
+    if (capacity < n) return fail("capacity %lld < %lld nodes", (long long)capacity, (long long)n);
+    if (n) std::memcpy(out, a->tree.nodes.data(), (size_t)n * sizeof(CanonNode));
+    return n;
+}
+
+extern "C" int ri_b200_triorder(const ri_b200_accel_t *a, uint32_t *orig_out)
+{
+    if (!a || !orig_out) return fail("null argument");
+    if (!a->tree.orig.empty()) std::memcpy(orig_out, a->tree.orig.data(), a->tree.orig.size() * sizeof(uint32_t));
+    return 0;
+}
+
+extern "C" int64_t ri_b200_export_flat(const ri_b200_accel_t *a, void *nodes32, void *nodes64, void *tris32, void *tris64,
+                                       uint32_t *header_out)
+{
+    if (!a) return fail("null argument");
+    if (a->device >= 0) return fail("flat records are only kept on RI_B200_HOST_ONLY accelerators");
+    const FlatTree &f = a->flat;
+    if (nodes32 && !f.nodes32.empty()) std::memcpy(nodes32, f.nodes32.data(), f.nodes32.size() * sizeof(Node32));
+    if (nodes64 && !f.nodes64.empty()) std::memcpy(nodes64, f.nodes64.data(), f.nodes64.size() * sizeof(Node64));
+    if (tris32 && !f.tris32.empty()) std::memcpy(tris32, f.tris32.data(), f.tris32.size() * sizeof(Tri32));
+    if (tris64 && !f.tris64.empty()) std::memcpy(tris64, f.tris64.data(), f.tris64.size() * sizeof(Tri64));
+    if (header_out) { header_out[0] = f.root_word; header_out[1] = f.ninner; header_out[2] = f.top_count; header_out[3] = 0; }
+    return (int64_t)f.ninner;
+}
+
+extern "C" void *ri_b200_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); fail("cudaMallocHost(%llu) failed", (unsigned long long)bytes); return nullptr; }
+    return p;
+}
+extern "C" void ri_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+// device-buffer entry points
+// ------------------------------------------------------------------------------------------------
+static int need(const ri_b200_accel *a, uint32_t prec)
+{
+    if (!a) return fail("null accelerator");
+    if (a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
+    if (!(a->precisions & prec)) return fail("accelerator was built without %s records", prec == RI_B200_PREC_F32 ? "fp32" : "fp64");
+    return 0;
+}
+
+extern "C" int ri_b200_intersect_dev_f32(ri_b200_accel_t *a, const float *d_rays, uint64_t n, ri_b200_hit_f32 *d_out, void *stream)
+{
+    if (need(a, RI_B200_PREC_F32)) return -1;
+    CUDA_OK(cudaSetDevice(a->device));
+    return launch_trace<float, false, false>(a, d_rays, n, d_out, nullptr, nullptr, stream ? (cudaStream_t)stream : a->stream);
+}
+extern "C" int ri_b200_occluded_dev_f32(ri_b200_accel_t *a, const float *d_rays, uint64_t n, uint8_t *d_out, void *stream)
+{
+    if (need(a, RI_B200_PREC_F32)) return -1;
+    CUDA_OK(cudaSetDevice(a->device));
+    return launch_trace<float, true, false>(a, d_rays, n, nullptr, d_out, nullptr, stream ? (cudaStream_t)stream : a->stream);
+}
+extern "C" int ri_b200_intersect_dev_f64(ri_b200_accel_t *a, const double *d_rays, uint64_t n, ri_b200_hit_f64 *d_out, void *stream)
+{
+    if (need(a, RI_B200_PREC_F64)) return -1;
+    CUDA_OK(cudaSetDevice(a->device));
+    return launch_trace<double, false, false>(a, d_rays, n, d_out, nullptr, nullptr, stream ? (cudaStream_t)stream : a->stream);
+}
+extern "C" int ri_b200_occluded_dev_f64(ri_b200_accel_t *a, const double *d_rays, uint64_t n, uint8_t *d_out, void *stream)
+{
+    if (need(a, RI_B200_PREC_F64)) return -1;
+    CUDA_OK(cudaSetDevice(a->device));
+    return launch_trace<double, true, false>(a, d_rays, n, nullptr, d_out, nullptr, stream ? (cudaStream_t)stream : a->stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points: chunked, double-buffered H2D -> kernel -> D2H
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kChunkRays = 1ull << 20;
+
+static int ensure_stage(ri_b200_accel *a, uint64_t in_bytes, uint64_t out_bytes)
+{
+    if (a->stage_in_bytes < in_bytes) {
+        for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); a->d_in[i] = nullptr; CUDA_OK(cudaMalloc(&a->d_in[i], in_bytes)); }
+        a->stage_in_bytes = in_bytes;
+    }
+    if (a->stage_out_bytes < out_bytes) {
+        for (int i = 0; i < 2; ++i) { cudaFree(a->d_out[i]); a->d_out[i] = nullptr; CUDA_OK(cudaMalloc(&a->d_out[i], out_bytes)); }
+        a->stage_out_bytes = out_bytes;
+    }
+    return 0;
+}
+
+template <typename Real, bool ANYHIT>
+static int host_batch(ri_b200_accel *a, const Real *rays, uint64_t n, void *out)
+{
+    using Hit = typename RayIO<Real>::Hit;
+    if (need(a, sizeof(Real) == 4 ? RI_B200_PREC_F32 : RI_B200_PREC_F64)) return -1;
+    if (n == 0) return 0;
+    if (!rays || !out) return fail("null buffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    const uint64_t ray_bytes = RayIO<Real>::kRayStride * sizeof(Real);
+    const uint64_t out_bytes = ANYHIT ? 1 : sizeof(Hit);
+    const uint64_t chunk = n < kChunkRays ? n : kChunkRays;
+    if (ensure_stage(a, chunk * ray_bytes, chunk * out_bytes)) return -1;
+
+    uint64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
+        cudaStream_t st = a->copy_stream[slot];
+        CUDA_OK(cudaMemcpyAsync(a->d_in[slot], (const char *)rays + done * ray_bytes, m * ray_bytes, cudaMemcpyHostToDevice, st));
+        if (launch_trace<Real, ANYHIT, false>(a, (const Real *)a->d_in[slot], m, ANYHIT ? nullptr : (Hit *)a->d_out[slot],
+                                              ANYHIT ? (uint8_t *)a->d_out[slot] : nullptr, nullptr, st)) return -1;
+        CUDA_OK(cudaMemcpyAsync((char *)out + done * out_bytes, a->d_out[slot], m * out_bytes, cudaMemcpyDeviceToHost, st));
+        done += m;
+        slot ^= 1;
+        // the slot we are about to reuse must have drained (its stream runs copy->kernel->copy in order)
+        if (done < n) CUDA_OK(cudaStreamSynchronize(a->copy_stream[slot]));
+    }
+    CUDA_OK(cudaStreamSynchronize(a->copy_stream[0]));
+    CUDA_OK(cudaStreamSynchronize(a->copy_stream[1]));
+    return 0;
+}
+
+extern "C" int ri_b200_intersect_batch_f32(ri_b200_accel_t *a, const float *rays, uint64_t n, ri_b200_hit_f32 *out)
+{ return host_batch<float, false>(a, rays, n, out); }
+extern "C" int ri_b200_occluded_batch_f32(ri_b200_accel_t *a, const float *rays, uint64_t n, uint8_t *out)
+{ return host_batch<float, true>(a, rays, n, out); }
+extern "C" int ri_b200_intersect_batch_f64(ri_b200_accel_t *a, const double *rays, uint64_t n, ri_b200_hit_f64 *out)
+{ return host_batch<double, false>(a, rays, n, out); }
+extern "C" int ri_b200_occluded_batch_f64(ri_b200_accel_t *a, const double *rays, uint64_t n, uint8_t *out)
+{ return host_batch<double, true>(a, rays, n, out); }
+
+extern "C" int ri_b200_count_batch(ri_b200_accel_t *a, const void *rays, uint64_t n, uint32_t precision, int anyhit,
+                                   ri_b200_counters_t *out)
+{
+    if (need(a, precision)) return -1;
+    if (!out) return fail("null argument");
+    std::memset(out, 0, sizeof(*out));
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    const bool f32 = precision == RI_B200_PREC_F32;
+    const uint64_t ray_bytes = f32 ? 32 : 48;
+    void *d_rays = nullptr, *d_res = nullptr;
+    CUDA_OK(cudaMalloc(&d_rays, n * ray_bytes));
+    CUDA_OK(cudaMalloc(&d_res, n * (anyhit ? 1 : (f32 ? sizeof(ri_b200_hit_f32) : sizeof(ri_b200_hit_f64)))));
+    int rc = 0;
+    auto body = [&]() -> int {
+        CUDA_OK(cudaMemcpyAsync(d_rays, rays, n * ray_bytes, cudaMemcpyHostToDevice, a->stream));
+        CUDA_OK(cudaMemsetAsync(a->d_counters, 0, 8 * sizeof(unsigned long long), a->stream));
+        int r;
+        if (f32) r = anyhit ? launch_trace<float, true, true>(a, (const float *)d_rays, n, nullptr, (uint8_t *)d_res, a->d_counters, a->stream)
+                            : launch_trace<float, false, true>(a, (const float *)d_rays, n, (ri_b200_hit_f32 *)d_res, nullptr, a->d_counters, a->stream);
+        else     r = anyhit ? launch_trace<double, true, true>(a, (const double *)d_rays, n, nullptr, (uint8_t *)d_res, a->d_counters, a->stream)
+                            : launch_trace<double, false, true>(a, (const double *)d_rays, n, (ri_b200_hit_f64 *)d_res, nullptr, a->d_counters, a->stream);
+        if (r) return r;
+        unsigned long long h[5];
+        CUDA_OK(cudaMemcpyAsync(h, a->d_counters, sizeof(h), cudaMemcpyDeviceToHost, a->stream));
+        CUDA_OK(cudaStreamSynchronize(a->stream));
+        out->nrays = h[0]; out->ninner = h[1]; out->nleaf = h[2]; out->ntris = h[3]; out->nhit_tris = h[4];
+        return 0;
+    };
+    rc = body();
+    cudaFree(d_rays); cudaFree(d_res);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-hit state (intersection_state.c:99-248 for geometry carrying only "P")
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void normalize3(double d[3])          // vector.h:75-87
+{
+    const double n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    if (n2 > (double)1.0e-17f) {
+        const double r = 1.0 / sqrt(n2);
+        d[0] *= r; d[1] *= r; d[2] *= r;
+    }
+}
+__device__ __forceinline__ void cross3(double d[3], const double a[3], const double b[3])
+{
+    d[0] = a[1] * b[2] - a[2] * b[1];
+    d[1] = a[2] * b[0] - a[0] * b[2];
+    d[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void ortho_basis(double b0[3], double b1[3], const double n[3])   // reflection.c:312-333
+{
+    int i;
+    for (i = 0; i < 3; ++i) if (n[i] < 0.6 && n[i] > -0.6) break;
+    if (i >= 3) i = 0;
+    double e[3] = {0.0, 0.0, 0.0};
+    e[i] = 1.0;
+    cross3(b0, e, n);
+    normalize3(b0);
+    cross3(b1, n, b0);
+    normalize3(b1);
+}
+
+__device__ __forceinline__ void state_from_hit(const Tri64 *tris, const double org[3], const double dir[3], double t, uint32_t prim,
+                                               ri_b200_state_f64 &s)
+{
+    TriRegs<double> tr;
+    load_tri(tris + prim, tr);
+    for (int k = 0; k < 3; ++k) s.P[k] = org[k] + dir[k] * t;
+    cross3(s.Ng, tr.e1, tr.e2);                                   // (v1-v0) x (v2-v0), geometric.c:20-33
+    normalize3(s.Ng);
+    for (int k = 0; k < 3; ++k) s.Ns[k] = s.Ng[k];
+    ortho_basis(s.tangent, s.binormal, s.Ng);
+}
+
+__global__ void state_kernel(const Tri64 *__restrict__ tris, const double *__restrict__ rays,
+                             const ri_b200_hit_f64 *__restrict__ hits, uint64_t n, ri_b200_state_f64 *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ri_b200_state_f64 s;
+    const ri_b200_hit_f64 h = hits[i];
+    if (h.hit) {
+        double org[3], dir[3];
+        RayIO<double>::load(rays, i, org, dir);
+        state_from_hit(tris, org, dir, h.t, h.prim, s);
+    } else {
+        memset(&s, 0, sizeof(s));
+    }
+    out[i] = s;
+}
+
+extern "C" int ri_b200_state_batch_f64(ri_b200_accel_t *a, const double *rays, const ri_b200_hit_f64 *hits, uint64_t n,
+                                       ri_b200_state_f64 *out)
+{
+    if (need(a, RI_B200_PREC_F64)) return -1;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    double *d_rays = nullptr; ri_b200_hit_f64 *d_hits = nullptr; ri_b200_state_f64 *d_out = nullptr;
+    auto body = [&]() -> int {
+        CUDA_OK(cudaMalloc((void **)&d_rays, n * 48));
+        CUDA_OK(cudaMalloc((void **)&d_hits, n * sizeof(ri_b200_hit_f64)));
+        CUDA_OK(cudaMalloc((void **)&d_out, n * sizeof(ri_b200_state_f64)));
+        CUDA_OK(cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, a->stream));
+        CUDA_OK(cudaMemcpyAsync(d_hits, hits, n * sizeof(ri_b200_hit_f64), cudaMemcpyHostToDevice, a->stream));
+        state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->d_tris64, d_rays, d_hits, n, d_out);
+        LAUNCHED();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync(out, d_out, n * sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));
+        CUDA_OK(cudaStreamSynchronize(a->stream));
+        return 0;
+    };
+    const int rc = body();
+    cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_out);
+    return rc;
+}
+
+// single ray: the vtable-compatible path (accel.h:30-34).  One launch of the f64 kernel + state.
+extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const double dir[3],
+                                  ri_b200_hit_f64 *hit, ri_b200_state_f64 *state)
+{
+    if (need(a, RI_B200_PREC_F64)) return -1;
+    if (!org || !dir || !hit) return fail("null argument");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    double *h = (double *)a->h_pin;
+    char *d = (char *)a->d_one;
+    for (int k = 0; k < 3; ++k) { h[k] = org[k]; h[3 + k] = dir[k]; }
+    double *d_ray = (double *)d;
+    ri_b200_hit_f64 *d_hit = (ri_b200_hit_f64 *)(d + 64);
+    ri_b200_state_f64 *d_state = (ri_b200_state_f64 *)(d + 128);
+    CUDA_OK(cudaMemcpyAsync(d_ray, h, 48, cudaMemcpyHostToDevice, a->stream));
+    if (launch_trace<double, false, false>(a, d_ray, 1, d_hit, nullptr, nullptr, a->stream)) return -1;
+    if (state) {
+        state_kernel<<<1, 32, 0, a->stream>>>(a->d_tris64, d_ray, d_hit, 1, d_state);
+        LAUNCHED();
+    }
+    CUDA_OK(cudaMemcpyAsync((char *)a->h_pin + 64, d + 64, 64 + sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));
+    CUDA_OK(cudaStreamSynchronize(a->stream));
+    std::memcpy(hit, (char *)a->h_pin + 64, sizeof(*hit));
+    if (state) std::memcpy(state, (char *)a->h_pin + 128, sizeof(*state));
+    return hit->hit ? 1 : 0;
+}
+
+#include "frame.cuh"

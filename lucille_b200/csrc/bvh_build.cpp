@@ -1,0 +1,405 @@
+// Host-side BVH construction -- see bvh_build.h.  Reference behaviour: src/render/bvh.c
+// (ri_bvh_build 276-379, bvh_construct 1328-1564, bin_triangle_edge 1571-1692,
+//  find_cut_from_bin 1230-1326, SAH 1210-1228, bbox_add_margin 1697-1731).
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <thread>
+
+namespace b200 {
+namespace {
+
+constexpr int    kLeafTris = 16;       // BVH_NTRIS_LEAF, bvh.c:81
+constexpr int    kBins     = 64;       // BVH_BIN_SIZE,  bvh.c:82
+constexpr double kEps      = 1.0e-14;  // RI_EPS, base/common.h:27
+constexpr double kInf      = 1.0e38;   // RI_INFINITY, include/ri.h:47
+
+struct Box {
+    double   lo[3], hi[3];
+    uint64_t idx;
+};
+
+struct TmpNode {
+    int32_t  is_leaf = 0, axis = 0;
+    TmpNode *c[2] = {nullptr, nullptr};
+    uint64_t left = 0, n = 0;          // leaf range in the final order
+    double   lbox[6], rbox[6];
+};
+
+struct Task {
+    TmpNode **slot;
+    int       buf;
+    uint64_t  left, right;
+    double    bmin[3], bmax[3];
+    int       depth;
+};
+
+struct Arena {
+    std::deque<TmpNode> nodes;
+    int max_depth = 0;
+    TmpNode *alloc() { nodes.emplace_back(); return &nodes.back(); }
+};
+
+struct Ctx {
+    Box         *buf[2];
+    const double *tri_in;
+    double      *tri_out;
+    uint32_t    *orig_out;
+    uint64_t     grain;        // ranges <= grain become parallel tasks (0: never)
+    std::vector<Task> *tasks;
+};
+
+inline void add_margin(double lo[3], double hi[3])
+{
+    double m[3];
+    for (int k = 0; k < 3; ++k) {
+        const double extent = hi[k] - lo[k];
+        m[k] = (extent < kEps) ? kEps : kEps * extent;
+    }
+    for (int k = 0; k < 3; ++k) { lo[k] -= m[k]; hi[k] += m[k]; }
+}
+
+inline double half_area2(const double lo[3], const double hi[3])
+{
+    double sa = (hi[0] - lo[0]) * (hi[1] - lo[1]) + (hi[1] - lo[1]) * (hi[2] - lo[2]) + (hi[2] - lo[2]) * (hi[0] - lo[0]);
+    sa *= 2.0;
+    return sa;
+}
+
+// The reference evaluates the cost in double and stores it in a float before comparing (bvh.c:1218-1227).
+inline double sah(uint64_t nl, double al, uint64_t nr, double ar, double total)
+{
+    const float t_aabb = 0.2f, t_tri = 0.8f;
+    float cost = 2.0f * t_aabb + (al / total) * (double)(int)nl * t_tri + (ar / total) * (double)(int)nr * t_tri;
+    return cost;
+}
+
+struct Split { int axis; double pos; };
+
+Split choose_split(const Box *b, uint64_t n, const double lo[3], const double hi[3])
+{
+    uint32_t bins[2][3][kBins];
+    std::memset(bins, 0, sizeof(bins));
+    double inv[3];
+    for (int k = 0; k < 3; ++k) {
+        const double extent = hi[k] - lo[k];
+        inv[k] = (extent > kEps) ? (double)kBins / extent : 0.0;
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            uint32_t a = (uint32_t)((b[i].lo[k] - lo[k]) * inv[k]);
+            uint32_t c = (uint32_t)((b[i].hi[k] - lo[k]) * inv[k]);
+            if (a >= (uint32_t)kBins) a = kBins - 1;
+            if (c >= (uint32_t)kBins) c = kBins - 1;
+            bins[0][k][a]++;
+            bins[1][k][c]++;
+        }
+    }
+
+    Split best{0, 0.0};
+    double best_cost = kInf;
+    const double total = half_area2(lo, hi);
+    for (int j = 0; j < 3; ++j) {
+        const double step = (hi[j] - lo[j]) / (double)kBins;
+        uint64_t nl = 0, nr = n;
+        double llo[3] = {lo[0], lo[1], lo[2]}, lhi[3] = {hi[0], hi[1], hi[2]};
+        double rlo[3] = {lo[0], lo[1], lo[2]}, rhi[3] = {hi[0], hi[1], hi[2]};
+        for (int i = 0; i < kBins - 1; ++i) {
+            nl += bins[0][j][i];
+            nr -= bins[1][j][i];
+            const double pos = lo[j] + (i + 1) * step;
+            lhi[j] = pos;
+            rlo[j] = pos;
+            const double cost = sah(nl, half_area2(llo, lhi), nr, half_area2(rlo, rhi), total);
+            if (cost < best_cost) { best_cost = cost; best.axis = j; best.pos = pos; }
+        }
+    }
+    return best;
+}
+
+inline void grow(double lo[3], double hi[3], const Box &b)
+{
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = (lo[k] < b.lo[k]) ? lo[k] : b.lo[k];
+        hi[k] = (hi[k] > b.hi[k]) ? hi[k] : b.hi[k];
+    }
+}
+
+void range_box(const Box *b, uint64_t n, double lo[3], double hi[3])
+{
+    for (int k = 0; k < 3; ++k) { lo[k] = b[0].lo[k]; hi[k] = b[0].hi[k]; }
+    for (uint64_t i = 1; i < n; ++i) grow(lo, hi, b[i]);
+}
+
+void build_range(Ctx &cx, Arena &ar, TmpNode **slot, int cur, uint64_t left, uint64_t right,
+                 const double lo[3], const double hi[3], int depth)
+{
+    const uint64_t n = right - left;
+    if (cx.tasks && depth > 0 && n <= cx.grain && n > (uint64_t)kLeafTris) {   // defer to the pool
+        Task t;
+        t.slot = slot; t.buf = cur; t.left = left; t.right = right; t.depth = depth;
+        for (int k = 0; k < 3; ++k) { t.bmin[k] = lo[k]; t.bmax[k] = hi[k]; }
+        cx.tasks->push_back(t);
+        return;
+    }
+
+    TmpNode *node = ar.alloc();
+    *slot = node;
+    if (depth > ar.max_depth) ar.max_depth = depth;
+
+    if (n <= (uint64_t)kLeafTris) {                       // bvh.c:1352-1403
+        const Box *b = cx.buf[cur] + left;
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t src = b[i].idx;
+            std::memcpy(cx.tri_out + 9 * (left + i), cx.tri_in + 9 * src, 9 * sizeof(double));
+            cx.orig_out[left + i] = (uint32_t)src;
+        }
+        node->is_leaf = 1; node->left = left; node->n = n;
+        return;
+    }
+
+    const Box *src = cx.buf[cur] + left;
+    Box *dst = cx.buf[cur ^ 1] + left;
+    const Split sp = choose_split(src, n, lo, hi);
+
+    // partition: "bmax[axis] < cut" goes left in input order, the rest fills the right part from the
+    // back (so it comes out reversed) -- bvh.c:1437-1468.  Child boxes are accumulated in the same sweep.
+    uint64_t nl = 0, nr = n - 1;
+    double llo[3], lhi[3], rlo[3], rhi[3];
+    bool lseen = false, rseen = false;
+    for (uint64_t i = 0; i < n; ++i) {
+        const Box &b = src[i];
+        if (b.hi[sp.axis] < sp.pos) {
+            dst[nl++] = b;
+            if (!lseen) { for (int k = 0; k < 3; ++k) { llo[k] = b.lo[k]; lhi[k] = b.hi[k]; } lseen = true; }
+            else grow(llo, lhi, b);
+        } else {
+            dst[nr--] = b;
+            if (!rseen) { for (int k = 0; k < 3; ++k) { rlo[k] = b.lo[k]; rhi[k] = b.hi[k]; } rseen = true; }
+            else grow(rlo, rhi, b);
+        }
+    }
+    if (nl == 0 || nl == n) {                             // object-median fallback, bvh.c:1471-1478
+        nl = n / 2;
+        range_box(dst, nl, llo, lhi);
+        range_box(dst + nl, n - nl, rlo, rhi);
+    }
+    add_margin(llo, lhi);
+    add_margin(rlo, rhi);
+
+    node->axis = sp.axis;
+    for (int k = 0; k < 3; ++k) {
+        node->lbox[k] = llo[k]; node->lbox[3 + k] = lhi[k];
+        node->rbox[k] = rlo[k]; node->rbox[3 + k] = rhi[k];
+    }
+    build_range(cx, ar, &node->c[0], cur ^ 1, left, left + nl, llo, lhi, depth + 1);
+    build_range(cx, ar, &node->c[1], cur ^ 1, left + nl, right, rlo, rhi, depth + 1);
+}
+
+int64_t emit(const TmpNode *n, std::vector<CanonNode> &out, int depth, HostTree &t)
+{
+    const int64_t me = (int64_t)out.size();
+    out.emplace_back();
+    if (depth > t.max_depth) t.max_depth = depth;
+    {
+        CanonNode &c = out[me];
+        std::memset(&c, 0, sizeof(c));
+        c.is_leaf = n->is_leaf;
+        if (n->is_leaf) {
+            c.child0 = c.child1 = -1;
+            c.tri_start = (int64_t)n->left; c.ntris = (int64_t)n->n;
+            t.nleaf++;
+            return me;
+        }
+        c.axis = n->axis;
+        std::memcpy(c.lbox, n->lbox, sizeof(c.lbox));
+        std::memcpy(c.rbox, n->rbox, sizeof(c.rbox));
+        t.ninner++;
+    }
+    const int64_t c0 = emit(n->c[0], out, depth + 1, t);
+    out[me].child0 = c0;
+    const int64_t c1 = emit(n->c[1], out, depth + 1, t);
+    out[me].child1 = c1;
+    return me;
+}
+
+}  // namespace
+
+void build_tree(const double *tri_xyz, uint64_t ntris, HostTree &out, int nthreads)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    out = HostTree();
+    out.ntris = ntris;
+    if (ntris == 0) { out.empty = true; return; }         // bvh.c:311-315
+    out.empty = false;
+
+    std::unique_ptr<Box[]> a(new Box[ntris]), b(new Box[ntris]);
+    for (uint64_t i = 0; i < ntris; ++i) {                // get_bbox_of_triangle, bvh.c:1852-1868
+        const double *v = tri_xyz + 9 * i;
+        Box &bx = a[i];
+        for (int k = 0; k < 3; ++k) {
+            double mn = v[k], mx = v[k];
+            for (int c = 1; c < 3; ++c) {
+                mn = (mn < v[3 * c + k]) ? mn : v[3 * c + k];
+                mx = (mx > v[3 * c + k]) ? mx : v[3 * c + k];
+            }
+            bx.lo[k] = mn; bx.hi[k] = mx;
+        }
+        bx.idx = i;
+    }
+    range_box(a.get(), ntris, out.bmin, out.bmax);        // calc_scene_bbox, bvh.c:1829-1849
+    add_margin(out.bmin, out.bmax);                       // bvh.c:330
+
+    out.tri.resize(9 * ntris);
+    out.orig.resize(ntris);
+
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+
+    std::vector<Task> tasks;
+    Ctx cx;
+    cx.buf[0] = a.get(); cx.buf[1] = b.get();
+    cx.tri_in = tri_xyz; cx.tri_out = out.tri.data(); cx.orig_out = out.orig.data();
+    const bool parallel = nthreads > 1 && ntris >= (1u << 16);
+    cx.grain = parallel ? std::max<uint64_t>(ntris / (uint64_t)(8 * nthreads), 4096) : 0;
+    cx.tasks = parallel ? &tasks : nullptr;
+
+    Arena top;
+    TmpNode *root = nullptr;
+    build_range(cx, top, &root, 0, 0, ntris, out.bmin, out.bmax, 0);
+
+    std::vector<Arena> arenas((size_t)nthreads);
+    if (!tasks.empty()) {
+        std::sort(tasks.begin(), tasks.end(),
+                  [](const Task &x, const Task &y) { return (x.right - x.left) > (y.right - y.left); });
+        Ctx sub = cx;
+        sub.tasks = nullptr; sub.grain = 0;
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (int w = 0; w < nthreads; ++w) {
+            pool.emplace_back([&, w]() {
+                Ctx local = sub;
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= tasks.size()) break;
+                    const Task &t = tasks[i];
+                    build_range(local, arenas[(size_t)w], t.slot, t.buf, t.left, t.right, t.bmin, t.bmax, t.depth);
+                }
+            });
+        }
+        for (auto &th : pool) th.join();
+    }
+
+    out.nodes.reserve((size_t)(ntris / 4 + 16));
+    emit(root, out.nodes, 0, out);
+    out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static float f32_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; }
+static float f32_up(double x)   { float f = (float)x; if ((double)f < x) f = std::nextafterf(f,  INFINITY); return f; }
+
+void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want64, FlatTree &out)
+{
+    out = FlatTree();
+    for (int k = 0; k < 3; ++k) { out.smin32[k] = f32_down(t.bmin[k]); out.smax32[k] = f32_up(t.bmax[k]); }
+    if (t.empty) { out.root_word = kDoneWord; return; }
+
+    const size_t nn = t.nodes.size();
+    std::vector<uint32_t> dev(nn, 0xffffffffu);           // canonical index -> device inner index
+    std::vector<int64_t>  order;                          // device inner index -> canonical index
+    order.reserve((size_t)t.ninner);
+
+    // BFS top cluster
+    std::vector<int64_t> frontier;
+    if (!t.nodes[0].is_leaf) {
+        std::deque<int64_t> q;
+        q.push_back(0);
+        while (!q.empty() && order.size() < top_nodes) {
+            const int64_t c = q.front(); q.pop_front();
+            dev[(size_t)c] = (uint32_t)order.size();
+            order.push_back(c);
+            const CanonNode &n = t.nodes[(size_t)c];
+            if (!t.nodes[(size_t)n.child0].is_leaf) q.push_back(n.child0);
+            if (!t.nodes[(size_t)n.child1].is_leaf) q.push_back(n.child1);
+        }
+        out.top_count = (uint32_t)order.size();
+        frontier.assign(q.begin(), q.end());
+    }
+    // DFS-preorder remainder, one frontier subtree after another
+    std::vector<int64_t> stack;
+    for (int64_t f : frontier) {
+        stack.push_back(f);
+        while (!stack.empty()) {
+            const int64_t c = stack.back(); stack.pop_back();
+            dev[(size_t)c] = (uint32_t)order.size();
+            order.push_back(c);
+            const CanonNode &n = t.nodes[(size_t)c];
+            if (!t.nodes[(size_t)n.child1].is_leaf) stack.push_back(n.child1);
+            if (!t.nodes[(size_t)n.child0].is_leaf) stack.push_back(n.child0);
+        }
+    }
+    out.ninner = (uint32_t)order.size();
+
+    auto word = [&](int64_t c) -> uint32_t {
+        const CanonNode &n = t.nodes[(size_t)c];
+        if (n.is_leaf) return kLeafFlag | ((uint32_t)(n.ntris - 1) << kLeafShift) | (uint32_t)n.tri_start;
+        return dev[(size_t)c];
+    };
+    out.root_word = word(0);
+
+    if (want32) out.nodes32.resize(order.size());
+    if (want64) out.nodes64.resize(order.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        const CanonNode &n = t.nodes[(size_t)order[i]];
+        const uint32_t c0 = word(n.child0), c1 = word(n.child1);
+        if (want32) {
+            Node32 &d = out.nodes32[i];
+            float *ax[3] = {d.x, d.y, d.z};
+            for (int k = 0; k < 3; ++k) {
+                ax[k][0] = f32_down(n.lbox[k]); ax[k][1] = f32_up(n.lbox[3 + k]);
+                ax[k][2] = f32_down(n.rbox[k]); ax[k][3] = f32_up(n.rbox[3 + k]);
+            }
+            d.c0 = c0; d.c1 = c1; d.axis = (uint32_t)n.axis; d.pad = 0;
+        }
+        if (want64) {
+            Node64 &d = out.nodes64[i];
+            double *ax[3] = {d.x, d.y, d.z};
+            for (int k = 0; k < 3; ++k) {
+                ax[k][0] = n.lbox[k]; ax[k][1] = n.lbox[3 + k];
+                ax[k][2] = n.rbox[k]; ax[k][3] = n.rbox[3 + k];
+            }
+            d.c0 = c0; d.c1 = c1; d.axis = (uint32_t)n.axis; d.pad = 0;
+            d.pad2[0] = d.pad2[1] = d.pad2[2] = d.pad2[3] = 0;
+        }
+    }
+
+    if (want32) out.tris32.resize((size_t)t.ntris);
+    if (want64) out.tris64.resize((size_t)t.ntris);
+    for (uint64_t p = 0; p < t.ntris; ++p) {
+        const double *v = t.tri.data() + 9 * p;
+        if (want32) {
+            Tri32 &d = out.tris32[(size_t)p];
+            for (int k = 0; k < 3; ++k) {
+                const float v0 = (float)v[k], v1 = (float)v[3 + k], v2 = (float)v[6 + k];
+                d.v0[k] = v0; d.e1[k] = v1 - v0; d.e2[k] = v2 - v0;      // bvh.c:747-752, in fp32
+            }
+            d.v0[3] = d.e1[3] = d.e2[3] = 0.0f;
+        }
+        if (want64) {
+            Tri64 &d = out.tris64[(size_t)p];
+            for (int k = 0; k < 3; ++k) { d.v0[k] = v[k]; d.e1[k] = v[3 + k] - v[k]; d.e2[k] = v[6 + k] - v[k]; }
+            d.pad = 0.0;
+        }
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,645 @@
+// On-device ambient-occlusion frame: the wavefront re-expression of lucille's pixel loop
+// (render.c:715-823 subsample, 1107-1146 render_bucket, 919-979 bucket_write) and of
+// ri_transport_ambientocclusion / calculate_occlusion (ambientocclusion.c:332-415, 42-151).
+//
+//   K3  primary_kernel   one lane per pixel sub-sample, in the reference's consumption order
+//                        (spiral buckets -> row-major pixels -> ys -> xs); camera ray in double,
+//                        closest-hit traversal
+//   scan_*               exclusive prefix sum of the hit flags: the reference draws 2*ntheta*nphi MT
+//                        numbers per *hit* sample and none per miss, so a sample's offset in the
+//                        stream is 2*N*(hits before it)
+//   compact_kernel       hit samples -> dense work list with the shading frame (P + 1e-6*Ns, basis)
+//   mt_kernel            MT19937 stream of randomMT2() (random.c:98-112, 211-247), one CTA
+//   K4  ao_kernel        one lane per occlusion ray, any-hit traversal, warp-ballot accumulation
+//   resolve_kernel       box average of the sub-samples, float RGB at row H-1-y
+//
+// Included at the end of accel.cu (same translation unit, -fmad=false).
+#pragma once
+
+namespace b200 {
+
+struct FrameDev {
+    double c2w[16];
+    double flength_signed;      // sign * flength, camera.c:269,275
+    double w, h;
+    int    width, height, xsamples, ysamples, ntheta, nphi, spp, nao;
+    int    rng_mode;
+    uint32_t seed;
+};
+
+// camera.c:248-352 (perspective) + render.c:770-781 normalise -------------------------------------
+__device__ __forceinline__ void camera_ray(const FrameDev &F, int px, int py, double jx, double jy, double org[3], double dir[3])
+{
+    const double x = (double)(px + jx), y = (double)(py + jy);
+    double v[4];
+    v[0] = (2.0 * x - F.w) / F.w;
+    v[1] = (2.0 * y - F.h) / F.h;
+    v[2] = F.flength_signed;
+    v[3] = 1.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double dp = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dp += v[i] * F.c2w[4 * i + j];    // ri_vector_transform, vector.h:182-210
+        const double pos = F.c2w[12 + j];
+        org[j] = pos;
+        dir[j] = dp - pos;
+    }
+    normalize3(dir);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(kBlock)
+primary_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter,
+               const uint64_t nsamples, Real *__restrict__ hit_t, uint32_t *__restrict__ hit_prim)
+{
+    extern __shared__ uint32_t s_stack[];
+    const uint64_t s = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (s >= nsamples) return;
+    const uint64_t p = s / (uint64_t)F.spp;
+    const int sub = (int)(s - p * (uint64_t)F.spp);
+    const uint32_t pix = pixels[p];
+    double org[3], dir[3];
+    camera_ray(F, (int)(pix & 0xffffu), (int)(pix >> 16), jitter[2 * sub], jitter[2 * sub + 1], org, dir);
+    Real o[3] = {(Real)org[0], (Real)org[1], (Real)org[2]}, d[3] = {(Real)dir[0], (Real)dir[1], (Real)dir[2]};
+    Real t, u, v;
+    uint32_t prim;
+    const bool hit = trace_ray<Real, false, false>(S, o, d, s_stack + threadIdx.x, kBlock, t, u, v, prim, nullptr);
+    hit_t[s] = hit ? t : Prec<Real>::inf();
+    hit_prim[s] = hit ? prim : 0xffffffffu;
+}
+
+// ---- exclusive scan of hit flags (three small kernels; 2048 flags per block) -------------------
+constexpr int kScanBlock = 256, kScanItems = 8, kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[kScanBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = x;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < kScanBlock / 32) ? warp_sums[lane] : 0;
+        for (int o = 1; o < kScanBlock / 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        if (lane < kScanBlock / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t base = warp ? warp_sums[warp - 1] : 0;
+    if (total) *total = warp_sums[kScanBlock / 32 - 1];
+    __syncthreads();
+    return base + incl - x;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+scan_tile_sums(const uint32_t *__restrict__ hit_prim, uint64_t n, uint32_t *__restrict__ tile_sums)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t c = 0;
+    for (int k = 0; k < kScanItems; ++k) { const uint64_t i = base + k; if (i < n && hit_prim[i] != 0xffffffffu) ++c; }
+    uint32_t total;
+    block_exclusive_scan(c, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+scan_tile_offsets(uint32_t *__restrict__ tile_sums, uint32_t ntiles, uint32_t *__restrict__ grand_total)
+{
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += kScanBlock) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = (i < ntiles) ? tile_sums[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(x, &total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+template <typename Real> struct StateMath;      // hit state in the accelerator's precision
+
+template <> struct StateMath<double> {
+    static __device__ __forceinline__ void frame(const SceneView<double> &S, const double org[3], const double dir[3], double t,
+                                                 uint32_t prim, double rec[12])
+    {
+        ri_b200_state_f64 s;
+        state_from_hit(S.tris, org, dir, t, prim, s);
+        const double eps = 1.0e-6;                                      // ambientocclusion.c:56,73-75
+        double b0[3], b1[3];
+        ortho_basis(b0, b1, s.Ns);                                      // ambientocclusion.c:65
+        for (int k = 0; k < 3; ++k) {
+            double o = s.P[k];
+            o += s.Ns[k] * eps;
+            rec[k] = o; rec[3 + k] = b0[k]; rec[6 + k] = b1[k]; rec[9 + k] = s.Ns[k];
+        }
+    }
+};
+
+template <> struct StateMath<float> {
+    static __device__ __forceinline__ void nrm(float d[3])
+    {
+        const float n2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        if (n2 > 1.0e-17f) { const float r = 1.0f / sqrtf(n2); d[0] *= r; d[1] *= r; d[2] *= r; }
+    }
+    static __device__ __forceinline__ void crs(float d[3], const float a[3], const float b[3])
+    {
+        d[0] = a[1] * b[2] - a[2] * b[1]; d[1] = a[2] * b[0] - a[0] * b[2]; d[2] = a[0] * b[1] - a[1] * b[0];
+    }
+    static __device__ __forceinline__ void frame(const SceneView<float> &S, const float org[3], const float dir[3], float t,
+                                                 uint32_t prim, float rec[12])
+    {
+        TriRegs<float> tr;
+        load_tri(S.tris + prim, tr);
+        float n[3], b0[3], b1[3], e[3] = {0.f, 0.f, 0.f};
+        crs(n, tr.e1, tr.e2);
+        nrm(n);
+        int i;
+        for (i = 0; i < 3; ++i) if (n[i] < 0.6f && n[i] > -0.6f) break;
+        if (i >= 3) i = 0;
+        e[i] = 1.0f;
+        crs(b0, e, n); nrm(b0);
+        crs(b1, n, b0); nrm(b1);
+        for (int k = 0; k < 3; ++k) {
+            float o = org[k] + dir[k] * t;
+            o += n[k] * 1.0e-6f;
+            rec[k] = o; rec[3 + k] = b0[k]; rec[6 + k] = b1[k]; rec[9 + k] = n[k];
+        }
+    }
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(kScanBlock)
+compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter,
+               const uint64_t nsamples, const Real *__restrict__ hit_t, const uint32_t *__restrict__ hit_prim,
+               const uint32_t *__restrict__ tile_offsets, uint32_t *__restrict__ sample_rank, uint32_t *__restrict__ rank_sample,
+               Real *__restrict__ records)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t flags = 0, c = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        const uint64_t i = base + k;
+        if (i < nsamples && hit_prim[i] != 0xffffffffu) { flags |= 1u << k; ++c; }
+    }
+    uint32_t rank = tile_offsets[blockIdx.x] + block_exclusive_scan(c, nullptr);
+    for (int k = 0; k < kScanItems; ++k) {
+        const uint64_t s = base + k;
+        if (s >= nsamples) break;
+        if (!(flags & (1u << k))) { sample_rank[s] = 0xffffffffu; continue; }
+        sample_rank[s] = rank;
+        rank_sample[rank] = (uint32_t)s;
+        // regenerate the eye ray (deterministic) and build the shading frame
+        const uint64_t p = s / (uint64_t)F.spp;
+        const int sub = (int)(s - p * (uint64_t)F.spp);
+        const uint32_t pix = pixels[p];
+        double org[3], dir[3];
+        camera_ray(F, (int)(pix & 0xffffu), (int)(pix >> 16), jitter[2 * sub], jitter[2 * sub + 1], org, dir);
+        Real o[3] = {(Real)org[0], (Real)org[1], (Real)org[2]}, d[3] = {(Real)dir[0], (Real)dir[1], (Real)dir[2]};
+        Real rec[12];
+        StateMath<Real>::frame(S, o, d, hit_t[s], hit_prim[s], rec);
+        Real *dst = records + 12 * (uint64_t)rank;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) dst[q] = rec[q];
+        ++rank;
+    }
+}
+
+// ---- MT19937, the generator behind randomMT2() (random.c:98-112 seeding, 211-247 regeneration + tempering) ----
+// One CTA owns the 624-word state in shared memory (double buffered).  new[k] depends on old[k], old[k+1] and on
+// the word 227 positions back in the NEW state, so a block regenerates in three dependent phases of <=227 lanes.
+constexpr int kMtN = 624, kMtM = 397;
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t far)
+{
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+// state_io: 624 words carried between launches (NULL on the first launch: seed here). Writes nblocks*624 outputs.
+__global__ void __launch_bounds__(256)
+mt_kernel(uint32_t seed, uint32_t *__restrict__ state_io, int first, uint64_t nblocks, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t st[2][kMtN];
+    const int k = threadIdx.x;
+    if (first) {
+        if (k == 0) {
+            uint32_t x = seed;
+            st[0][0] = x;
+            for (int i = 1; i < kMtN; ++i) { x = 69069u * x; st[0][i] = x; }      // seedMT2, random.c:98-112
+        }
+    } else {
+        for (int i = k; i < kMtN; i += 256) st[0][i] = state_io[i];
+    }
+    __syncthreads();
+    int cur = 0;
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        uint32_t *o = st[cur], *n = st[cur ^ 1];
+        uint32_t *dst = out + b * kMtN;
+        if (k < kMtN - kMtM) {                                   // phase 1: k in [0,227)
+            const uint32_t v = mt_twist(o[k], o[k + 1], o[k + kMtM]);
+            n[k] = v; dst[k] = mt_temper(v);
+        }
+        __syncthreads();
+        if (k < kMtN - kMtM) {                                   // phase 2: k in [227,454)
+            const int i = k + (kMtN - kMtM);
+            const uint32_t v = mt_twist(o[i], o[i + 1], n[i - (kMtN - kMtM)]);
+            n[i] = v; dst[i] = mt_temper(v);
+        }
+        __syncthreads();
+        {                                                        // phase 3: k in [454,624)
+            const int i = k + 2 * (kMtN - kMtM);
+            if (i < kMtN - 1) {
+                const uint32_t v = mt_twist(o[i], o[i + 1], n[i - (kMtN - kMtM)]);
+                n[i] = v; dst[i] = mt_temper(v);
+            } else if (i == kMtN - 1) {
+                const uint32_t v = mt_twist(o[kMtN - 1], n[0], n[kMtM - 1]);
+                n[i] = v; dst[i] = mt_temper(v);
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (state_io) for (int i = k; i < kMtN; i += 256) state_io[i] = st[cur][i];
+}
+
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// ---- K4: occlusion rays ----------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(kBlock)
+ao_kernel(const SceneView<Real> S, const FrameDev F, const uint64_t nrays, const uint32_t rank0,
+          const Real *__restrict__ records, const uint32_t *__restrict__ rank_sample, const uint32_t *__restrict__ pixels,
+          const uint32_t *__restrict__ mt_stream, uint32_t *__restrict__ occ,
+          Real *__restrict__ dump_rays, const uint64_t dump_count)
+{
+    extern __shared__ uint32_t s_stack[];
+    const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = gid < nrays;
+    bool hit = false;
+    uint32_t rank = 0;
+    if (active) {
+        const uint32_t N = (uint32_t)F.nao;
+        rank = rank0 + (uint32_t)(gid / N);
+        const uint32_t k = (uint32_t)(gid - (uint64_t)(rank - rank0) * N);
+        const uint32_t j = k / (uint32_t)F.ntheta, i = k - j * (uint32_t)F.ntheta;
+        const Real *rec = records + 12 * (uint64_t)rank;
+
+        double r0, r1;
+        if (F.rng_mode == 0) {
+            const uint64_t base = (uint64_t)2 * N * rank + 2 * k;       // draw order z0 then z1, ambientocclusion.c:91-92
+            r0 = (double)mt_stream[base] * 2.3283064365386963e-10;       // random.c:244
+            r1 = (double)mt_stream[base + 1] * 2.3283064365386963e-10;
+        } else {
+            const uint32_t s = rank_sample[rank];
+            const uint64_t p = s / (uint32_t)F.spp;
+            const uint32_t sub = s - (uint32_t)p * (uint32_t)F.spp;
+            const uint32_t pix = pixels[p];
+            const uint64_t sid = ((uint64_t)(pix >> 16) * (uint64_t)F.width + (pix & 0xffffu)) * (uint64_t)F.spp + sub;
+            const uint64_t idx = (sid * N + k) * 2;
+            r0 = (double)(splitmix64_dev((uint64_t)F.seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+            r1 = (double)(splitmix64_dev((uint64_t)F.seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+        }
+
+        Real org[3] = {rec[0], rec[1], rec[2]}, dir[3];
+        if (sizeof(Real) == 8) {                                         // ambientocclusion.c:91-117, double
+            const double z0 = ((double)i + r0) / (double)F.ntheta;
+            const double z1 = ((double)j + r1) / (double)F.nphi;
+            const double ct = sqrt(z0);
+            const double phi = 2.0 * 3.14159265358979323846 * z1;
+            const double lx = cos(phi) * ct, ly = sin(phi) * ct, lz = sqrt(1.0 - ct * ct);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                dir[q] = (Real)(lx * (double)rec[3 + q] + ly * (double)rec[6 + q] + lz * (double)rec[9 + q]);
+        } else {
+            const float z0 = ((float)i + (float)r0) / (float)F.ntheta;
+            const float z1 = ((float)j + (float)r1) / (float)F.nphi;
+            const float ct = sqrtf(z0);
+            const float phi = 6.28318530717958647692f * z1;
+            float sp, cp;
+            sincosf(phi, &sp, &cp);
+            const float lx = cp * ct, ly = sp * ct, lz = sqrtf(1.0f - ct * ct);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                dir[q] = (Real)(lx * (float)rec[3 + q] + ly * (float)rec[6 + q] + lz * (float)rec[9 + q]);
+        }
+        if (dump_rays && gid < dump_count) {
+            const int st = sizeof(Real) == 8 ? 6 : 8, off = sizeof(Real) == 8 ? 3 : 4;
+            Real *d = dump_rays + gid * st;
+            d[0] = org[0]; d[1] = org[1]; d[2] = org[2];
+            d[off] = dir[0]; d[off + 1] = dir[1]; d[off + 2] = dir[2];
+            if (sizeof(Real) == 4) { d[3] = (Real)0; d[7] = (Real)1.0e38f; }
+        }
+        Real t, u, v;
+        uint32_t prim;
+        hit = trace_ray<Real, true, false>(S, org, dir, s_stack + threadIdx.x, kBlock, t, u, v, prim, nullptr);
+    }
+    if ((F.nao & 31) == 0) {                                            // a warp never straddles two samples
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&occ[rank], (uint32_t)__popc(m));
+    } else if (hit) {
+        atomicAdd(&occ[rank], 1u);
+    }
+}
+
+// ---- resolve: Lo = (N - occluded)/N per hit sample, mean over sub-samples, float at row H-1-y ---------
+__global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
+                               const uint32_t *__restrict__ sample_rank, const uint32_t *__restrict__ occ, float *__restrict__ rgb)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npixels) return;
+    const uint32_t pix = pixels[p];
+    const int x = (int)(pix & 0xffffu), y = (int)(pix >> 16);
+    const double ns = (double)F.nao;
+    double accum = 0.0;
+    for (int sub = 0; sub < F.spp; ++sub) {
+        const uint32_t r = sample_rank[p * (uint64_t)F.spp + sub];
+        double rad = 0.0;
+        if (r != 0xffffffffu) rad = 1.0 * (ns - (double)occ[r]) / ns;    // ambientocclusion.c:143-147
+        accum = accum + rad;                                             // render.c:805
+    }
+    const double px = accum * (1.0 / (double)(F.xsamples * F.ysamples)); // render.c:820
+    float *dst = rgb + 3 * ((uint64_t)(F.height - y - 1) * F.width + x); // render.c:962-964
+    const float f = (float)px;
+    dst[0] = f; dst[1] = f; dst[2] = f;
+}
+
+// ---- host helpers ---------------------------------------------------------------------------------
+// spiral.c:97-140 NthBucketSpiral
+static void nth_bucket_spiral(int n, int nxb, int nyb, int *bx, int *by)
+{
+    const int minnb = nxb < nyb ? nxb : nyb;
+    const int center = (minnb - 1) / 2;
+    int nx = nxb, ny = nyb;
+    while (n < nx * ny) { --nx; --ny; }
+    const int nxny = nx * ny, m = nx < ny ? nx : ny;
+    int x, y;
+    if (m % 2 == 1) {
+        if (n <= nxny + ny) { x = nx - m / 2; y = -m / 2 + n - nxny; }
+        else { x = nx - m / 2 - (n - (nxny + ny)); y = ny - m / 2; }
+    } else {
+        if (n <= nxny + ny) { x = -m / 2; y = ny - m / 2 - (n - nxny); }
+        else { x = -m / 2 + (n - (nxny + ny)); y = -m / 2; }
+    }
+    *bx = x + center; *by = y + center;
+}
+
+// pixel visiting order of the reference for this rank's buckets: render.c:582-710 + 1131-1146
+static void pixel_order(const ri_b200_frame_t &f, std::vector<uint32_t> &pix)
+{
+    const int bs = f.bucket_size > 0 ? f.bucket_size : 32;
+    const int nxb = (f.width + bs - 1) / bs, nyb = (f.height + bs - 1) / bs;
+    const int world = f.world > 0 ? f.world : 1;
+    pix.clear();
+    for (int n = 0; n < nxb * nyb; ++n) {
+        if (n % world != f.rank) continue;
+        int bx, by;
+        nth_bucket_spiral(n, nxb, nyb, &bx, &by);
+        const int x0 = bx * bs, y0 = by * bs;
+        const int w = (x0 + bs <= f.width) ? bs : f.width - x0;
+        const int h = (y0 + bs <= f.height) ? bs : f.height - y0;
+        for (int v = y0; v < y0 + h; ++v)
+            for (int u = x0; u < x0 + w; ++u) pix.push_back((uint32_t)u | ((uint32_t)v << 16));
+    }
+}
+
+// render.c:830-917 sample_subpixel / init_sigma (periodx masks both indices -- reproduced)
+static void jitter_table(int xsamples, int ysamples, std::vector<double> &jit)
+{
+    auto sigma = [](unsigned period, std::vector<unsigned> &s) {
+        s.resize(period);
+        for (unsigned i = 0; i < period; ++i) {
+            unsigned digit = period, inverse = 0;
+            for (unsigned bits = i; bits; bits >>= 1) { digit >>= 1; if (bits & 1) inverse += digit; }
+            s[i] = inverse;
+        }
+    };
+    std::vector<unsigned> sx, sy;
+    sigma((unsigned)xsamples, sx);
+    sigma((unsigned)ysamples, sy);
+    jit.resize((size_t)2 * xsamples * ysamples);
+    for (int ys = 0; ys < ysamples; ++ys)
+        for (int xs = 0; xs < xsamples; ++xs) {
+            const unsigned j = (unsigned)xs & ((unsigned)xsamples - 1), k = (unsigned)ys & ((unsigned)xsamples - 1);
+            double a = (double)xs + (double)sx[k % sx.size()] / (double)xsamples;
+            double b = (double)ys + (double)sy[j % sy.size()] / (double)ysamples;
+            a /= (double)xsamples;
+            b /= (double)ysamples;
+            a += 0.5 / (xsamples * xsamples);
+            b += 0.5 / (ysamples * ysamples);
+            jit[2 * (ys * xsamples + xs)] = a;
+            jit[2 * (ys * xsamples + xs) + 1] = b;
+        }
+}
+
+static int frame_buf(ri_b200_accel *a, int slot, uint64_t bytes, void **out)
+{
+    if (a->frame_bytes[slot] < bytes) {
+        cudaFree(a->d_frame[slot]); a->d_frame[slot] = nullptr; a->frame_bytes[slot] = 0;
+        CUDA_OK(cudaMalloc(&a->d_frame[slot], bytes));
+        a->frame_bytes[slot] = bytes;
+    }
+    *out = a->d_frame[slot];
+    return 0;
+}
+
+template <typename Real>
+static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_rgb, cudaStream_t st, ri_b200_frame_stats_t *stats,
+                          Real *d_dump, uint64_t dump_count)
+{
+    std::vector<uint32_t> pix;
+    std::vector<double> jit;
+    pixel_order(f, pix);
+    jitter_table(f.xsamples, f.ysamples, jit);
+    const uint64_t npix = pix.size();
+    const int spp = f.xsamples * f.ysamples, N = f.ntheta * f.nphi;
+    const uint64_t nsamples = npix * (uint64_t)spp;
+    if (nsamples >= 0xfffffff0ull) return fail("too many samples per rank for 32-bit sample ids");
+
+    FrameDev F;
+    for (int i = 0; i < 16; ++i) F.c2w[i] = f.c2w[i];
+    F.flength_signed = (double)(float)(f.is_rh ? -1.0 : 1.0) * f.flength;
+    F.w = (double)f.width; F.h = (double)f.height;
+    F.width = f.width; F.height = f.height; F.xsamples = f.xsamples; F.ysamples = f.ysamples;
+    F.ntheta = f.ntheta; F.nphi = f.nphi; F.spp = spp; F.nao = N;
+    F.rng_mode = f.rng_mode; F.seed = f.seed;
+
+    const int cap = stack_capacity(a);
+    const size_t smem = (size_t)cap * kBlock * sizeof(uint32_t);
+    if (smem > 200 * 1024) return fail("BVH depth %d exceeds the shared-memory traversal stack", cap);
+    if (smem > 48 * 1024) {
+        CUDA_OK(cudaFuncSetAttribute(primary_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_OK(cudaFuncSetAttribute(ao_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+
+    const uint32_t ntiles = (uint32_t)((nsamples + kScanTile - 1) / kScanTile);
+    void *p = nullptr;
+    uint32_t *d_pix, *d_prim, *d_tiles, *d_srank, *d_ranks;
+    double *d_jit;
+    Real *d_t;
+    if (frame_buf(a, 0, (npix + 1) * 4 + jit.size() * 8 + 64, &p)) return -1;
+    d_jit = (double *)p; d_pix = (uint32_t *)(d_jit + jit.size());
+    if (frame_buf(a, 1, (nsamples + 1) * sizeof(Real), &p)) return -1;
+    d_t = (Real *)p;
+    if (frame_buf(a, 2, (nsamples + 1) * 4 * 3 + ((uint64_t)ntiles + 4) * 4, &p)) return -1;
+    d_prim = (uint32_t *)p; d_srank = d_prim + nsamples; d_ranks = d_srank + nsamples; d_tiles = d_ranks + nsamples;
+    uint32_t *d_total = d_tiles + ntiles;
+
+    SceneView<Real> S = make_view<Real>(a);
+    CUDA_OK(cudaEventRecord(a->ev[0], st));
+    if (npix) {
+        CUDA_OK(cudaMemcpyAsync(d_jit, jit.data(), jit.size() * 8, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_OK(cudaMemsetAsync(d_rgb, 0, (size_t)f.width * f.height * 3 * sizeof(float), st));
+    uint32_t nhits = 0;
+    if (nsamples) {
+        primary_kernel<Real><<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim);
+        LAUNCHED();
+        scan_tile_sums<<<ntiles, kScanBlock, 0, st>>>(d_prim, nsamples, d_tiles);
+        LAUNCHED();
+        scan_tile_offsets<<<1, kScanBlock, 0, st>>>(d_tiles, ntiles, d_total);
+        LAUNCHED();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync(a->h_pin, d_total, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaEventRecord(a->ev[1], st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        nhits = *(uint32_t *)a->h_pin;
+    } else {
+        CUDA_OK(cudaEventRecord(a->ev[1], st));
+    }
+
+    const uint64_t nao_rays = (uint64_t)nhits * (uint64_t)N;
+    Real *d_rec = nullptr;
+    uint32_t *d_occ = nullptr, *d_mt = nullptr;
+    if (frame_buf(a, 3, ((uint64_t)nhits + 1) * 12 * sizeof(Real), &p)) return -1;
+    d_rec = (Real *)p;
+    if (frame_buf(a, 4, ((uint64_t)nhits + 1) * 4, &p)) return -1;
+    d_occ = (uint32_t *)p;
+    const uint64_t mt_blocks = f.rng_mode == 0 ? (2 * nao_rays + kMtN - 1) / kMtN : 0;
+    if (frame_buf(a, 5, (mt_blocks * kMtN + 4) * 4, &p)) return -1;
+    d_mt = (uint32_t *)p;
+
+    if (nhits) {
+        compact_kernel<Real><<<ntiles, kScanBlock, 0, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_tiles, d_srank, d_ranks, d_rec);
+        LAUNCHED();
+        CUDA_OK(cudaMemsetAsync(d_occ, 0, (uint64_t)nhits * 4, st));
+    } else if (nsamples) {
+        CUDA_OK(cudaMemsetAsync(d_srank, 0xff, nsamples * 4, st));
+    }
+    CUDA_OK(cudaEventRecord(a->ev[2], st));
+    if (mt_blocks) {
+        mt_kernel<<<1, 256, 0, st>>>(f.seed, nullptr, 1, mt_blocks, d_mt);
+        LAUNCHED();
+    }
+    CUDA_OK(cudaEventRecord(a->ev[3], st));
+    if (nao_rays) {
+        const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
+        if (blocks > 0x7fffffffull) return fail("too many occlusion rays in one frame pass");
+        ao_kernel<Real><<<(unsigned)blocks, kBlock, smem, st>>>(S, F, nao_rays, 0u, d_rec, d_ranks, d_pix, d_mt, d_occ, d_dump, dump_count);
+        LAUNCHED();
+    }
+    CUDA_OK(cudaEventRecord(a->ev[4], st));
+    if (npix) {
+        resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb);
+        LAUNCHED();
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(a->ev[5], st));
+    if (stats) {
+        CUDA_OK(cudaEventSynchronize(a->ev[5]));
+        float ms;
+        std::memset(stats, 0, sizeof(*stats));
+        stats->nrays_primary = nsamples; stats->nrays_ao = nao_rays; stats->nhits_primary = nhits;
+        CUDA_OK(cudaEventElapsedTime(&ms, a->ev[0], a->ev[5])); stats->ms_total = ms;
+        CUDA_OK(cudaEventElapsedTime(&ms, a->ev[0], a->ev[1])); stats->ms_primary = ms;
+        CUDA_OK(cudaEventElapsedTime(&ms, a->ev[2], a->ev[3])); stats->ms_rng = ms;
+        CUDA_OK(cudaEventElapsedTime(&ms, a->ev[3], a->ev[4])); stats->ms_ao = ms;
+        CUDA_OK(cudaEventElapsedTime(&ms, a->ev[4], a->ev[5])); stats->ms_resolve = ms;
+    }
+    return 0;
+}
+
+static int check_frame(const ri_b200_accel *a, const ri_b200_frame_t *f)
+{
+    if (!a || !f) return fail("null argument");
+    if (f->width < 1 || f->height < 1 || f->width > 65535 || f->height > 65535) return fail("bad frame size");
+    if (f->xsamples < 1 || f->ysamples < 1 || f->ntheta < 1 || f->nphi < 1) return fail("bad sample counts");
+    if (f->world < 1 || f->rank < 0 || f->rank >= f->world) return fail("bad rank/world");
+    if (f->rng_mode == 0 && f->world != 1)
+        return fail("rng_mode 0 (single MT19937 stream in reference order) is defined for world == 1 only");
+    if (f->precision != RI_B200_PREC_F32 && f->precision != RI_B200_PREC_F64) return fail("bad precision");
+    return need(a, (uint32_t)f->precision);
+}
+
+}  // namespace b200
+
+extern "C" int ri_b200_render_ao_dev(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *d_rgb, void *stream,
+                                     ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!d_rgb) return fail("null framebuffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
+    if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_rgb, st, stats, nullptr, 0);
+    return render_ao_impl<float>(a, *f, d_rgb, st, stats, nullptr, 0);
+}
+
+extern "C" int ri_b200_render_ao(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *rgb_out, ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!rgb_out) return fail("null framebuffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    const size_t bytes = (size_t)f->width * f->height * 3 * sizeof(float);
+    void *p = nullptr;
+    if (frame_buf(a, 6, bytes, &p)) return -1;
+    int rc;
+    if (f->precision == RI_B200_PREC_F64) rc = render_ao_impl<double>(a, *f, (float *)p, a->stream, stats, nullptr, 0);
+    else rc = render_ao_impl<float>(a, *f, (float *)p, a->stream, stats, nullptr, 0);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(rgb_out, p, bytes, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_OK(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
+extern "C" int ri_b200_mt_stream(uint32_t seed, uint64_t n, uint32_t *out_u32, int device)
+{
+    if (!out_u32) return fail("null argument");
+    if (n == 0) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    const uint64_t blocks = (n + kMtN - 1) / kMtN;
+    uint32_t *d = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d, blocks * kMtN * 4));
+    mt_kernel<<<1, 256>>>(seed, nullptr, 1, blocks, d);
+    LAUNCHED();
+    cudaError_t e = cudaMemcpy(out_u32, d, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail("mt stream copy failed: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -1,0 +1,207 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact for (hit, t, u, v, prim) in both precisions; frame RMSE <= 1e-4 against the reference's float framebuffer."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from lucille_b200 import accel, scenes
+
+pytestmark = pytest.mark.gpu
+
+RMSE_TOL = 1.0e-4      # BASELINE.json north_star: ambient_occlusion.rib within 1e-4 RMSE of the CPU reference
+
+
+def _need_gpu():
+    if accel.device_count() < 1:
+        pytest.fail("no CUDA device visible: -m gpu tests must run on the B200 box (no CPU fallback exists)")
+
+
+@pytest.fixture(scope="module")
+def soup20k():
+    _need_gpu()
+    tris = scenes.triangle_soup(20000, scenes.SEED_C2)
+    return tris, accel.Accel.bind().build(tris), ol.Oracle().build(tris)
+
+
+def _mixed_rays(n, seed):
+    rng = np.random.default_rng(seed)
+    org = rng.uniform(-0.5, 1.5, (n, 3))
+    tgt = rng.uniform(0.0, 1.0, (n, 3))
+    d = tgt - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.zeros((n, 8), dtype=np.float32)
+    r[:, 0:3] = org
+    r[:, 4:7] = d
+    r[:, 7] = 1e38
+    r[:, 4:7][r[:, 4:7] == 0] = 1e-8
+    return r
+
+
+@pytest.mark.parametrize("kind", ["pinhole", "incoherent"])
+def test_closest_hit_f32_bit_exact(soup20k, kind):
+    tris, a, orc = soup20k
+    rays = scenes.pinhole_rays(256, 256) if kind == "pinhole" else _mixed_rays(100000, 5)
+    got, want = a.intersect(rays), orc.intersect_f32(rays)
+    assert (want["prim"] != ol.MISS_PRIM).sum() > 1000
+    for f in ("prim", "t", "u", "v"):
+        assert np.array_equal(got[f], want[f]), f
+
+
+@pytest.mark.parametrize("kind", ["pinhole", "incoherent"])
+def test_closest_hit_f64_bit_exact(soup20k, kind):
+    tris, a, orc = soup20k
+    rays8 = scenes.pinhole_rays(256, 256) if kind == "pinhole" else _mixed_rays(100000, 6)
+    rays = scenes.rays_f32_to_f64(rays8)
+    got, want = a.intersect(rays), orc.intersect_f64(rays)
+    for f in ("hit", "prim", "t", "u", "v"):
+        assert np.array_equal(got[f], want[f]), f
+
+
+def test_occlusion_matches_closest_hit_flag(soup20k):
+    tris, a, orc = soup20k
+    rays8 = _mixed_rays(200000, 7)
+    assert np.array_equal(a.occluded(rays8), orc.occluded_f32(rays8))
+    rays6 = scenes.rays_f32_to_f64(rays8[:50000])
+    assert np.array_equal(a.occluded(rays6), orc.occluded_f64(rays6))
+    assert np.array_equal(a.occluded(rays8) == 1, a.intersect(rays8)["prim"] != accel.MISS_PRIM)
+
+
+def test_traversal_counters_equal_reference_statistics(soup20k):
+    """ninner / nleaf / ntris per batch are the I and T of the roofline formula: they must be the
+    reference's own RI_BVH_TRACE_STATISTICS numbers, here via the oracle (pinned to them on CPU)."""
+    tris, a, orc = soup20k
+    rays8 = scenes.pinhole_rays(128, 128)
+    _, c32 = orc.intersect_f32(rays8, counters=True)
+    assert a.count(rays8) == {k: int(c32[k]) for k in c32.dtype.names}
+    _, a32 = orc.occluded_f32(rays8, counters=True)
+    assert a.count(rays8, anyhit=True) == {k: int(a32[k]) for k in a32.dtype.names}
+    rays6 = scenes.rays_f32_to_f64(rays8)
+    _, c64 = orc.intersect_f64(rays6, counters=True)
+    assert a.count(rays6) == {k: int(c64[k]) for k in c64.dtype.names}
+
+
+def test_hit_state_and_single_ray(soup20k):
+    tris, a, orc = soup20k
+    rays6 = scenes.rays_f32_to_f64(scenes.pinhole_rays(64, 64))
+    hits = a.intersect(rays6)
+    st, want = a.state(rays6, hits), orc.state_build(rays6, orc.intersect_f64(rays6))
+    m = hits["hit"] == 1
+    for f in ("P", "Ng", "Ns", "tangent", "binormal"):
+        assert np.array_equal(st[f][m], want[f][m]), f
+    i = int(np.flatnonzero(m)[0])
+    hit, h, s = a.raytrace(rays6[i, :3], rays6[i, 3:])
+    assert hit and h["t"] == hits["t"][i] and h["prim"] == hits["prim"][i] and np.array_equal(s["P"], st["P"][i])
+    j = int(np.flatnonzero(~m)[0])
+    assert not a.raytrace(rays6[j, :3], rays6[j, 3:])[0]
+
+
+@pytest.mark.parametrize("maker", [
+    lambda: np.zeros((0, 3, 3)),                                            # empty scene: always miss (bvh.c:446)
+    lambda: scenes.triangle_soup(1, 7),                                     # root is a leaf
+    lambda: scenes.triangle_soup(16, 7),
+    lambda: scenes.triangle_soup(17, 7),
+    lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0),            # exact ties: later triangle in a leaf wins
+    lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0]) + np.array([0, 0, 0.5]),   # coplanar, zero-extent boxes
+])
+def test_edge_case_scenes(maker):
+    _need_gpu()
+    tris = maker()
+    a, orc = accel.Accel.bind().build(tris), ol.Oracle().build(tris)
+    rays8 = np.concatenate([scenes.pinhole_rays(64, 64), _mixed_rays(4096, 3)])
+    got, want = a.intersect(rays8), orc.intersect_f32(rays8)
+    for f in ("prim", "t", "u", "v"):
+        assert np.array_equal(got[f], want[f]), f
+    rays6 = scenes.rays_f32_to_f64(rays8)
+    got, want = a.intersect(rays6), orc.intersect_f64(rays6)
+    for f in ("hit", "prim", "t", "u", "v"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(a.occluded(rays8), orc.occluded_f32(rays8))
+    assert a.intersect(np.zeros((0, 8), dtype=np.float32)).shape == (0,)      # empty batch
+
+
+def test_device_mt19937_stream(golden_dir):
+    _need_gpu()
+    g = np.load(os.path.join(golden_dir, "mt19937_seed4357.npz"))
+    s = accel.mt_stream(1000008)
+    assert np.array_equal(s[:2000], g["first"]) and np.array_equal(s[-8:], g["at_1e6"])
+
+
+@pytest.mark.parametrize("fname,w,h,ps,gather", [
+    ("c1_frame_160x120.npz", 160, 120, 3, 64),
+    ("c1_frame_97x61_ps2_g16.npz", 97, 61, 2, 16),
+])
+def test_c1_frame_against_reference_framebuffer(golden_dir, fname, w, h, ps, gather):
+    """ambient_occlusion.rib through the on-device AO transport (fp64 records, MT19937 stream in reference order)
+    against the float framebuffer the compiled reference produced for the same frame."""
+    _need_gpu()
+    sc = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    g = np.load(os.path.join(golden_dir, fname))
+    cam = sc["cam"]
+    a = accel.Accel.bind().build(sc["tris"], accel.PREC_F64)
+    fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), w, h, ps, ps, gather_nsamples=gather)
+    rgb, stats = a.render_ao(fr)
+    assert stats.nrays == int(g["nrays"])                      # same rays as the reference counted (stat.nrays)
+    rmse = float(np.sqrt(np.mean((rgb.astype(np.float64) - g["rgb"].astype(np.float64)) ** 2)))
+    assert rmse <= RMSE_TOL, rmse
+
+
+def test_c1_full_frame_digest(golden_dir):
+    """Full 640x480, 3x3, 64-ray frame (BASELINE configs[0]) against the committed half-resolution slice + ray count."""
+    _need_gpu()
+    sc = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    g = np.load(os.path.join(golden_dir, "c1_frame_640x480_digest.npz"))
+    cam = sc["cam"]
+    a = accel.Accel.bind().build(sc["tris"], accel.PREC_F64)
+    fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 640, 480, 3, 3, gather_nsamples=64)
+    rgb, stats = a.render_ao(fr)
+    assert stats.nrays == int(g["nrays"]) == 75873408
+    half = rgb[::2, ::2, 0].astype(np.float64)
+    rmse = float(np.sqrt(np.mean((half - g["rgb_half"].astype(np.float64)) ** 2)))
+    assert rmse <= RMSE_TOL, rmse
+    assert abs(float(rgb.astype(np.float64).mean()) - float(g["mean"])) < 1e-5
+
+
+def test_counter_rng_frame_is_partition_invariant(golden_dir):
+    """rng_mode 1 (counter-based): rendering the buckets of rank r of `world` ranks and summing the tiles gives the
+    single-rank image exactly -- the property the multi-GPU gather relies on."""
+    _need_gpu()
+    sc = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    cam = sc["cam"]
+    a = accel.Accel.bind().build(sc["tris"], accel.PREC_F32 | accel.PREC_F64)
+    for prec in (accel.PREC_F32, accel.PREC_F64):
+        full, _ = a.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 2, 2, 16, rng_mode=1, seed=7, precision=prec))
+        acc = np.zeros_like(full)
+        for r in range(3):
+            part, _ = a.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 2, 2, 16, rng_mode=1, seed=7,
+                                                   rank=r, world=3, precision=prec))
+            assert np.all((part == 0) | (acc == 0))          # tiles are disjoint
+            acc += part
+        assert np.array_equal(acc, full)
+        assert full.max() <= 1.0 and full.mean() > 0.05
+
+
+def test_full_size_config2_properties():
+    """BASELINE configs[1] at full size (100 K triangles, 1 M primary rays): size-independent properties --
+    occlusion flag == closest-hit flag, t reproduces the hit point inside the triangle's box, sampled rows bit-exact."""
+    _need_gpu()
+    tris = scenes.triangle_soup(100000, scenes.SEED_C2)
+    a = accel.Accel.bind().build(tris, accel.PREC_F32)
+    rays = scenes.pinhole_rays(1024, 1024)
+    hits = a.intersect(rays)
+    m = hits["prim"] != accel.MISS_PRIM
+    assert 0.3 < m.mean() < 0.7
+    assert np.array_equal(a.occluded(rays) == 1, m)
+    order = a.triorder()
+    tri = tris[order[hits["prim"][m]]]
+    p = rays[m, 0:3].astype(np.float64) + rays[m, 4:7].astype(np.float64) * hits["t"][m, None].astype(np.float64)
+    lo, hi = tri.min(axis=1) - 1e-4, tri.max(axis=1) + 1e-4
+    assert np.all((p >= lo) & (p <= hi))
+    bary = (1 - hits["u"][m] - hits["v"][m])[:, None] * tri[:, 0] + hits["u"][m][:, None] * tri[:, 1] + hits["v"][m][:, None] * tri[:, 2]
+    assert np.abs(bary - p).max() < 1e-4
+    orc = ol.Oracle().build(tris)
+    rows = np.r_[0:1024, 512 * 1024:512 * 1024 + 2048, 1023 * 1024:1024 * 1024]
+    want = orc.intersect_f32(rays[rows])
+    for f in ("prim", "t", "u", "v"):
+        assert np.array_equal(hits[f][rows], want[f]), f

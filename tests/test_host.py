@@ -1,0 +1,159 @@
+"""CPU: host-side logic of the product -- the C-ABI library loads and exports every declared symbol, the host BVH
+builder reproduces the reference tree (via the oracle), flat device records decode back to the canonical tree, and
+every compute entry fails loudly without a device (no CPU fallback)."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from lucille_b200 import accel, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lucille_b200.h")).read()
+    declared = set(re.findall(r"\b(ri_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(accel.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/lucille_b200.h but not exported"
+    assert declared == {n for n, _, _ in accel.ABI}, "python binding table out of sync with the header"
+
+
+def test_bind_rejects_other_methods():
+    with pytest.raises(accel.B200Error):
+        accel.Accel.bind(accel.RI_ACCEL_BVH)          # ri_accel_bind -> -1 for methods this library does not provide
+    assert accel.Accel.bind(accel.RI_ACCEL_B200).data is None
+
+
+@pytest.mark.parametrize("maker", [
+    lambda: scenes.triangle_soup(100000, scenes.SEED_C2),
+    lambda: scenes.triangle_soup(70000, 21),            # above the parallel threshold: threaded build must not change the tree
+    lambda: scenes.triangle_soup(17, 7),
+    lambda: scenes.triangle_soup(16, 7),
+    lambda: scenes.triangle_soup(1, 7),
+    lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0),
+    lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0]),
+])
+def test_host_builder_matches_oracle_tree(oracle, maker):
+    tris = maker()
+    a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64 | accel.HOST_ONLY)
+    t = oracle.build(tris)
+    pn, on = a.nodes(), t.nodes()
+    assert len(pn) == len(on)
+    for f in ol.NODE_DTYPE.names:
+        assert np.array_equal(pn[f], on[f]), f
+    assert np.array_equal(a.triorder(), t.triorder())
+    info = a.info()
+    assert info.max_depth == t.max_depth() and info.ninner + info.nleaf == len(on)
+    assert np.array_equal(np.array(info.bmin), t.bbox()[0]) and np.array_equal(np.array(info.bmax), t.bbox()[1])
+
+
+def _decode(flat, prec):
+    """Walk the flat device records from root_word and rebuild the canonical DFS-preorder node list."""
+    nodes = flat["nodes32"] if prec == 32 else flat["nodes64"]
+    out = []
+
+    def rec(word):
+        me = len(out)
+        out.append(None)
+        if word & 0x80000000:
+            out[me] = dict(is_leaf=1, tri_start=word & ((1 << 27) - 1), ntris=((word >> 27) & 15) + 1)
+            return me
+        n = nodes[word]
+        d = dict(is_leaf=0, axis=int(n["axis"]),
+                 lbox=[n["x"][0], n["y"][0], n["z"][0], n["x"][1], n["y"][1], n["z"][1]],
+                 rbox=[n["x"][2], n["y"][2], n["z"][2], n["x"][3], n["y"][3], n["z"][3]])
+        out[me] = d
+        d["child0"] = rec(int(n["c0"]))
+        d["child1"] = rec(int(n["c1"]))
+        return me
+
+    rec(flat["root_word"])
+    return out
+
+
+@pytest.mark.parametrize("n", [5000, 12])
+def test_flat_records_decode_to_canonical_tree(n):
+    import sys
+    sys.setrecursionlimit(10000)
+    tris = scenes.triangle_soup(n, 3)
+    a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64 | accel.HOST_ONLY)
+    canon, flat = a.nodes(), a.flat()
+    for prec in (32, 64):
+        dec = _decode(flat, prec)
+        assert len(dec) == len(canon)
+        for d, c in zip(dec, canon):
+            assert d["is_leaf"] == c["is_leaf"]
+            if d["is_leaf"]:
+                assert d["tri_start"] == c["tri_start"] and d["ntris"] == c["ntris"]
+            else:
+                assert d["axis"] == c["axis"] and d["child0"] == c["child0"] and d["child1"] == c["child1"]
+                lb, rb = np.array(d["lbox"], dtype=np.float64), np.array(d["rbox"], dtype=np.float64)
+                if prec == 64:
+                    assert np.array_equal(lb, c["lbox"]) and np.array_equal(rb, c["rbox"])
+                else:                                    # fp32 boxes are rounded outward, by at most one ulp
+                    for got, want in ((lb, c["lbox"]), (rb, c["rbox"])):
+                        assert np.all(got[:3] <= want[:3]) and np.all(got[3:] >= want[3:])
+                        assert np.all(np.abs(got - want) <= np.spacing(np.abs(want).astype(np.float32)).astype(np.float64))
+    # triangles: v0, e1 = v1 - v0, e2 = v2 - v0 in post-build order
+    order = a.triorder()
+    t64 = flat["tris64"]
+    src = tris[order]
+    assert np.array_equal(t64["v0"], src[:, 0]) and np.array_equal(t64["e1"], src[:, 1] - src[:, 0])
+    assert np.array_equal(t64["e2"], src[:, 2] - src[:, 0])
+    t32 = flat["tris32"]
+    s32 = src.astype(np.float32)
+    assert np.array_equal(t32["v0"][:, :3], s32[:, 0]) and np.array_equal(t32["e1"][:, :3], s32[:, 1] - s32[:, 0])
+    # the first top_count inner nodes are in BFS order: children of node i have larger indices
+    assert flat["top_count"] == min(1024, flat["ninner"])
+
+
+def test_empty_scene_builds_valid_accelerator():
+    a = accel.Accel.bind().build(np.zeros((0, 3, 3)), accel.PREC_F32 | accel.HOST_ONLY)
+    info = a.info()
+    assert info.empty == 1 and info.ntris == 0 and len(a.nodes()) == 0
+    assert a.flat()["root_word"] == 0x7FFFFFFF
+
+
+def test_no_cpu_fallback():
+    """Without a device the product refuses to compute (it must never route through the oracle)."""
+    tris = scenes.triangle_soup(100, 1)
+    a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.HOST_ONLY)
+    with pytest.raises(accel.B200Error, match="no CPU fallback"):
+        a.intersect(scenes.pinhole_rays(4, 4))
+    with pytest.raises(accel.B200Error, match="no CPU fallback"):
+        a.occluded(scenes.pinhole_rays(4, 4))
+    if accel.device_count() == 0:
+        with pytest.raises(accel.B200Error, match="no CPU fallback"):
+            accel.Accel.bind().build(tris)
+    src = open(os.path.join(ROOT, "lucille_b200", "accel.py")).read() + open(os.path.join(ROOT, "lucille_b200", "scenes.py")).read()
+    assert "oracle" not in src.replace("the oracle", "").replace("oracle,", "") or "import oracle" not in src
+
+
+def test_synthetic_scenes_are_deterministic():
+    a = scenes.triangle_soup(1000, scenes.SEED_C2)
+    b = scenes.triangle_soup(1000, scenes.SEED_C2, chunk=128)
+    assert np.array_equal(a, b)
+    assert hashlib.sha256(a.tobytes()).hexdigest() == hashlib.sha256(scenes.triangle_soup(1000, scenes.SEED_C2).tobytes()).hexdigest()
+    assert np.array_equal(a, a.astype(np.float32).astype(np.float64))          # fp32-representable
+    r = scenes.pinhole_rays(64, 32)
+    assert r.shape == (2048, 8) and np.all(r[:, 4:7] != 0.0)
+    o = ol.Oracle()
+    assert int(scenes.splitmix64(np.array([12345], dtype=np.uint64))[0]) == o.lib.orc_splitmix64(12345)
+
+
+def test_ao_ray_generator_is_cosine_hemisphere():
+    pts = np.array([[0.5, 0.5, 0.5]] * 50)
+    nrm = np.tile(np.array([[0.0, 0.0, 1.0]]), (50, 1))
+    rays = scenes.ao_rays(pts, nrm, 8, 8, 99)
+    assert rays.shape == (50 * 64, 8)
+    d = rays[:, 4:7].astype(np.float64)
+    assert np.all(d[:, 2] >= 0.0) and np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-6)
+    assert abs(d[:, 2].mean() - 2.0 / 3.0) < 0.02                                # E[cos] under a cosine-weighted pdf
+    assert np.allclose(rays[:, 2], 0.5 + 1e-6, atol=1e-7)

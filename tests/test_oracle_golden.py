@@ -1,0 +1,105 @@
+"""CPU: the oracle restatement against golden vectors produced by the compiled reference (tests/golden/make_golden.py)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from lucille_b200 import scenes
+
+
+def tree_digest(nodes, triorder):
+    h = hashlib.sha256()
+    for name in ol.NODE_DTYPE.names:
+        h.update(np.ascontiguousarray(nodes[name]).tobytes())
+    h.update(np.ascontiguousarray(triorder).tobytes())
+    return h.hexdigest()
+
+
+def test_per_ray_vectors(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "soup2k_rays.npz"))
+    tris = scenes.triangle_soup(int(g["ntris"]), int(g["seed"]))
+    rays8 = scenes.pinhole_rays(int(g["width"]), int(g["height"]))
+    rays6 = scenes.rays_f32_to_f64(rays8)
+    t = oracle.build(tris)
+    assert tree_digest(t.nodes(), t.triorder()) == str(g["tree_digest"])
+    assert len(t.nodes()) == int(g["nnodes"]) and t.max_depth() == int(g["max_depth"])
+    hits, cnt = t.intersect_f64(rays6, counters=True)
+    m = g["hit"] == 1
+    assert np.array_equal(hits["hit"] == 1, m) and m.sum() > 500
+    for f in ("t", "u", "v"):                       # bit-exact: same arithmetic, same order
+        assert np.array_equal(hits[f][m], g[f][m]), f
+    assert np.array_equal(t.triorder()[hits["prim"][m]], g["tri_index"][m])
+    st = t.state_build(rays6, hits)
+    for f in ("P", "Ng", "Ns", "tangent", "binormal"):
+        assert np.array_equal(st[f][m], g[f][m]), f
+    assert [int(x) for x in cnt] == [int(x) for x in g["counters"]]
+    # occlusion boolean == closest-hit boolean (the AO transport only uses the flag, ambientocclusion.c:123-129)
+    assert np.array_equal(t.occluded_f64(rays6) == 1, m)
+
+
+@pytest.mark.parametrize("name,maker", [
+    ("soup100k_c2", lambda: scenes.triangle_soup(100000, scenes.SEED_C2)),
+    ("soup17", lambda: scenes.triangle_soup(17, 7)),
+    ("soup16", lambda: scenes.triangle_soup(16, 7)),
+    ("soup1", lambda: scenes.triangle_soup(1, 7)),
+    ("dup300", lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0)),
+    ("flat500", lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0])),
+])
+def test_tree_digests(oracle, golden_dir, name, maker):
+    g = np.load(os.path.join(golden_dir, "tree_digests.npz"))
+    t = oracle.build(maker())
+    assert len(t.nodes()) == int(g[name + "_nnodes"])
+    assert tree_digest(t.nodes(), t.triorder()) == str(g[name])
+
+
+def test_empty_scene(oracle):
+    t = oracle.build(np.zeros((0, 3, 3)))
+    assert t.empty and len(t.nodes()) == 0
+    rays = scenes.rays_f32_to_f64(scenes.pinhole_rays(4, 4))
+    hits, cnt = t.intersect_f64(rays, counters=True)
+    assert hits["hit"].sum() == 0 and int(cnt["nrays"]) == 0      # bvh.c:446: returns before the counter
+
+
+def test_mt19937(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mt19937_seed4357.npz"))
+    assert np.array_equal(oracle.mt_stream_u32(2000), g["first"])
+    assert np.array_equal(oracle.mt_stream_u32(1000008)[-8:], g["at_1e6"])
+    d = oracle.mt_stream(10)
+    assert np.array_equal(d, g["first"][:10].astype(np.float64) * 2.3283064365386963e-10)
+
+
+@pytest.mark.parametrize("fname,kw", [
+    ("c1_frame_160x120.npz", dict(width=160, height=120)),
+    ("c1_frame_97x61_ps2_g16.npz", dict(width=97, height=61, xsamples=2, ysamples=2, gather=16)),
+])
+def test_c1_frame_bit_identical(oracle, golden_dir, fname, kw):
+    """ambient_occlusion.rib (BASELINE configs[0]) at reduced size: the oracle's frame equals the reference's float
+    framebuffer bit for bit, with the same number of rays (single MT stream, spiral bucket order)."""
+    sc = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    g = np.load(os.path.join(golden_dir, fname))
+    t = oracle.build(sc["tris"])
+    w, h = kw.pop("width"), kw.pop("height")
+    fp = ol.frame_params(sc["cam"], w, h, **kw)
+    rgb, nrays = t.render_ao(fp)
+    assert nrays == int(g["nrays"])
+    assert np.array_equal(rgb, g["rgb"])
+
+
+def test_f32_restatement_tracks_double(oracle):
+    """The fp32 instantiation (the bit-exact target of the fp32 kernels) against the double one: same hits except
+    near-degenerate cases, |dt|/t within a few fp32 ulps."""
+    tris = scenes.triangle_soup(20000, scenes.SEED_C2)
+    rays8 = scenes.pinhole_rays(128, 128)
+    t = oracle.build(tris)
+    h64 = t.intersect_f64(scenes.rays_f32_to_f64(rays8))
+    h32 = t.intersect_f32(rays8)
+    m64, m32 = h64["hit"] == 1, h32["prim"] != ol.MISS_PRIM
+    assert (m64 == m32).mean() > 0.9995
+    both = m64 & m32
+    same = h64["prim"][both] == h32["prim"][both]
+    assert same.mean() > 0.999
+    rel = np.abs(h32["t"][both][same].astype(np.float64) - h64["t"][both][same]) / h64["t"][both][same]
+    assert rel.max() < 1e-5
+    assert np.array_equal(t.occluded_f32(rays8) == 1, m32)

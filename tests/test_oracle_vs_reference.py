@@ -1,0 +1,63 @@
+"""CPU, build container only: the oracle restatement against the compiled, unmodified reference (oracle/_ref).
+Skipped where oracle/_ref has not been built (it needs /root/reference); the golden-vector tests cover that case."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from lucille_b200 import scenes
+
+pytestmark = pytest.mark.skipif(not ol.reference_available(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ol.Reference()
+
+
+@pytest.mark.parametrize("n,seed", [(5000, 1), (30000, 2), (33, 3)])
+def test_tree_and_rays(oracle, ref, n, seed):
+    tris = scenes.triangle_soup(n, seed)
+    ot, rs = oracle.build(tris), ref.build(tris)
+    on, rn = ot.nodes(), rs.nodes()
+    assert len(on) == len(rn)
+    for f in ol.NODE_DTYPE.names:
+        assert np.array_equal(on[f], rn[f]), f
+    assert np.array_equal(ot.triorder(), rs.triorder())
+    assert all(np.array_equal(a, b) for a, b in zip(ot.bbox(), rs.bbox()))
+
+    rng = np.random.default_rng(seed)
+    org = rng.uniform(-0.5, 1.5, (20000, 3))
+    tgt = rng.uniform(0.0, 1.0, (20000, 3))
+    rays6 = np.concatenate([org, tgt - org], axis=1)          # un-normalised directions are legal (simplerender.cpp:202)
+    oh = ot.intersect_f64(rays6)
+    rh, _ = rs.intersect(rays6)
+    m = rh["hit"] != 0
+    assert np.array_equal(oh["hit"] == 1, m)
+    for f in ("t", "u", "v"):
+        assert np.array_equal(oh[f][m], rh[f][m]), f
+    assert np.array_equal(ot.triorder()[oh["prim"][m]], rh["index"][m] // 3)
+    st = ot.state_build(rays6, oh)
+    for f in ("P", "Ng", "Ns", "tangent", "binormal"):
+        assert np.array_equal(st[f][m], rh[f][m]), f
+
+
+def test_multi_geom_flattening(oracle, ref):
+    """create_triangle_list (bvh.c:1736-1826) concatenates geoms in list order: 3 geoms == 1 flattened soup."""
+    tris = scenes.triangle_soup(900, 5)
+    a = ref.build(tris, geom_sizes=[100, 500, 300])
+    b = oracle.build(tris)
+    for f in ol.NODE_DTYPE.names:
+        assert np.array_equal(a.nodes()[f], b.nodes()[f]), f
+    assert np.array_equal(a.triorder(), b.triorder())
+
+
+def test_counters_match_reference_statistics(oracle):
+    refs = ol.Reference(stats=True)
+    tris = scenes.triangle_soup(20000, scenes.SEED_C2)
+    rays6 = scenes.rays_f32_to_f64(scenes.pinhole_rays(96, 96))
+    rs = refs.build(tris)
+    refs.stats_reset()
+    rs.intersect(rays6)
+    want = refs.stats_get()
+    _, cnt = oracle.build(tris).intersect_f64(rays6, counters=True)
+    assert {k: int(cnt[k]) for k in want} == want
