@@ -213,7 +213,12 @@ def main():
     d_occ = torch.empty((nrays,), dtype=torch.uint8, device="cuda")
     d_hits = torch.empty((nrays, 4), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the C ABI treats a NULL stream as "the accelerator's own stream", and CUDA events
+    # only see work on the stream they are recorded on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     # counters of the reference traversal order on this exact batch (outside the timed region)
     cnt = a.count(rays_np, anyhit=True)

