@@ -62,6 +62,8 @@ struct ri_b200_accel {
     void    *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
     uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
     unsigned long long *d_counters = nullptr;
+    unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
+    unsigned work_slot = 0;
     // single-ray path
     void *h_pin = nullptr, *d_one = nullptr;
     std::mutex mu;
@@ -163,6 +165,8 @@ trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const
     }
 }
 
+#include "persistent.cuh"
+
 static int stack_capacity(const ri_b200_accel *a)
 {
     int cap = a->tree.max_depth;
@@ -178,6 +182,29 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
     const int cap = stack_capacity(a);
     const size_t smem = (size_t)cap * kBlock * sizeof(uint32_t);
     if (smem > 200 * 1024) return fail("BVH depth %d exceeds the shared-memory traversal stack", cap);
+    if (!COUNT) {
+        // production path: persistent warps with ray replacement; batches above 2^31 rays are split
+        auto pk = trace_persistent_kernel<Real, ANYHIT>;
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kBlock, smem));
+        if (per_sm < 1) return fail("persistent traversal kernel does not fit on an SM");
+        const uint64_t kMax = 1ull << 31;
+        for (uint64_t done = 0; done < n; done += kMax) {
+            const uint32_t m = (uint32_t)((n - done) < kMax ? (n - done) : kMax);
+            uint64_t want = ((uint64_t)m + kChunk - 1) / kChunk;           // one chunk per warp at least
+            want = (want + (kBlock / 32) - 1) / (kBlock / 32);
+            const uint64_t cap = (uint64_t)per_sm * (uint64_t)a->sm_count;
+            const unsigned blocks = (unsigned)(want < cap ? want : cap);
+            unsigned int *ctr = a->d_work + (a->work_slot++ & 63u);
+            CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+            pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m,
+                                           d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr, ctr);
+            LAUNCHED();
+            CUDA_OK(cudaGetLastError());
+        }
+        return 0;
+    }
     auto kern = trace_batch_kernel<Real, ANYHIT, COUNT>;
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t blocks = (n + kBlock - 1) / kBlock;
@@ -258,6 +285,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         if (upload(&a->d_nodes64, a->flat.nodes64, a->device_bytes)) return -1;
         if (upload(&a->d_tris64, a->flat.tris64, a->device_bytes)) return -1;
         CUDA_OK(cudaMalloc((void **)&a->d_counters, 8 * sizeof(unsigned long long)));
+        CUDA_OK(cudaMalloc((void **)&a->d_work, 64 * sizeof(unsigned int)));
         CUDA_OK(cudaMallocHost(&a->h_pin, 4096));
         CUDA_OK(cudaMalloc(&a->d_one, 4096));
         return 0;
@@ -279,7 +307,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     for (auto p : a->d_frame) cudaFree(p);
-    cudaFree(a->d_counters); cudaFree(a->d_one);
+    cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work);
     if (a->h_pin) cudaFreeHost(a->h_pin);
     for (auto &e : a->ev) if (e) cudaEventDestroy(e);
     if (a->stream) cudaStreamDestroy(a->stream);
