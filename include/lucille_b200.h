@@ -108,7 +108,7 @@ int     ri_b200_info(const ri_b200_accel_t *accel, ri_b200_info_t *out);
 int64_t ri_b200_export_nodes(const ri_b200_accel_t *accel, ri_b200_node_t *out, int64_t capacity);
 int     ri_b200_triorder(const ri_b200_accel_t *accel, uint32_t *orig_out);   /* [ntris] */
 /* flat device records of a RI_B200_HOST_ONLY accelerator (layout: lucille_b200/csrc/bvh_build.h); any pointer may be
- * NULL.  header_out[4] = root_word, ninner, top_count, 0.  Returns ninner. */
+ * NULL.  header_out[4] = root_word, ninner, top_count, number of triangle slots.  Returns ninner. */
 int64_t ri_b200_export_flat(const ri_b200_accel_t *accel, void *nodes32, void *nodes64, void *tris32, void *tris64,
                             uint32_t *header_out);
 

@@ -40,8 +40,8 @@ NODE_DTYPE = np.dtype([("is_leaf", "<i4"), ("axis", "<i4"), ("child0", "<i8"), (
                        ("tri_start", "<i8"), ("ntris", "<i8"), ("lbox", "<f8", 6), ("rbox", "<f8", 6)])
 NODE32_DTYPE = np.dtype([("x", "<f4", 4), ("y", "<f4", 4), ("z", "<f4", 4), ("c0", "<u4"), ("c1", "<u4"), ("axis", "<u4"), ("pad", "<u4")])
 NODE64_DTYPE = np.dtype([("x", "<f8", 4), ("y", "<f8", 4), ("z", "<f8", 4), ("c0", "<u4"), ("c1", "<u4"), ("axis", "<u4"), ("pad", "<u4", 5)])
-TRI32_DTYPE = np.dtype([("v0", "<f4", 4), ("e1", "<f4", 4), ("e2", "<f4", 4)])
-TRI64_DTYPE = np.dtype([("v0", "<f8", 3), ("e1", "<f8", 3), ("e2", "<f8", 3), ("pad", "<f8")])
+TRI32_DTYPE = np.dtype([("v0", "<f4", 3), ("prim", "<u4"), ("e1", "<f4", 3), ("pad1", "<u4"), ("e2", "<f4", 3), ("pad2", "<u4")])
+TRI64_DTYPE = np.dtype([("v0", "<f8", 3), ("prim", "<u8"), ("e1", "<f8", 3), ("pad1", "<u8"), ("e2", "<f8", 3), ("pad2", "<u8")])
 
 
 class B200Error(RuntimeError):
@@ -236,12 +236,13 @@ class Accel:
         info = self.info()
         n32 = np.zeros(ninner if info.precisions & PREC_F32 else 0, dtype=NODE32_DTYPE)
         n64 = np.zeros(ninner if info.precisions & PREC_F64 else 0, dtype=NODE64_DTYPE)
-        t32 = np.zeros(self.ntris if info.precisions & PREC_F32 else 0, dtype=TRI32_DTYPE)
-        t64 = np.zeros(self.ntris if info.precisions & PREC_F64 else 0, dtype=TRI64_DTYPE)
+        nslots = int(hdr[3])
+        t32 = np.zeros(nslots if info.precisions & PREC_F32 else 0, dtype=TRI32_DTYPE)
+        t64 = np.zeros(nslots if info.precisions & PREC_F64 else 0, dtype=TRI64_DTYPE)
         _check(self.lib.ri_b200_export_flat(self._h(), _ptr(n32) if len(n32) else None, _ptr(n64) if len(n64) else None,
                                             _ptr(t32) if len(t32) else None, _ptr(t64) if len(t64) else None, _ptr(hdr)))
         return dict(nodes32=n32, nodes64=n64, tris32=t32, tris64=t64, root_word=int(hdr[0]), ninner=int(hdr[1]),
-                    top_count=int(hdr[2]))
+                    top_count=int(hdr[2]), nslots=nslots)
 
     # -- accel->intersect, batched (host buffers) ---------------------------------------------------
     def intersect(self, rays: np.ndarray) -> np.ndarray:

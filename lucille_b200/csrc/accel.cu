@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -56,6 +57,7 @@ struct ri_b200_accel {
     cudaEvent_t  ev[8] = {};
     Node32 *d_nodes32 = nullptr; Tri32 *d_tris32 = nullptr;
     Node64 *d_nodes64 = nullptr; Tri64 *d_tris64 = nullptr;
+    uint32_t *d_slot_of_prim = nullptr;
     uint64_t device_bytes = 0;
     double   upload_seconds = 0.0;
     // staging for host-buffer batches (double buffered)
@@ -77,7 +79,7 @@ template <typename Real> static SceneView<Real> make_view(const ri_b200_accel *a
 template <> SceneView<float> make_view<float>(const ri_b200_accel *a)
 {
     SceneView<float> v;
-    v.nodes = a->d_nodes32; v.tris = a->d_tris32;
+    v.nodes = a->d_nodes32; v.tris = a->d_tris32; v.slot_of_prim = a->d_slot_of_prim;
     for (int k = 0; k < 3; ++k) { v.smin[k] = a->flat.smin32[k]; v.smax[k] = a->flat.smax32[k]; }
     v.root_word = a->flat.root_word; v.top_count = a->flat.top_count;
     return v;
@@ -85,7 +87,7 @@ template <> SceneView<float> make_view<float>(const ri_b200_accel *a)
 template <> SceneView<double> make_view<double>(const ri_b200_accel *a)
 {
     SceneView<double> v;
-    v.nodes = a->d_nodes64; v.tris = a->d_tris64;
+    v.nodes = a->d_nodes64; v.tris = a->d_tris64; v.slot_of_prim = a->d_slot_of_prim;
     for (int k = 0; k < 3; ++k) { v.smin[k] = a->tree.bmin[k]; v.smax[k] = a->tree.bmax[k]; }
     v.root_word = a->flat.root_word; v.top_count = a->flat.top_count;
     return v;
@@ -192,13 +194,18 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         const uint64_t kMax = 1ull << 31;
         for (uint64_t done = 0; done < n; done += kMax) {
             const uint32_t m = (uint32_t)((n - done) < kMax ? (n - done) : kMax);
-            uint64_t want = ((uint64_t)m + kChunk - 1) / kChunk;           // one chunk per warp at least
-            want = (want + (kBlock / 32) - 1) / (kBlock / 32);
             const uint64_t cap = (uint64_t)per_sm * (uint64_t)a->sm_count;
+            const uint64_t warps = cap * (kBlock / 32);
+            // rays per atomic fetch: ~16 fetches per warp for load balance, between one warp-load and 128 rays
+            uint32_t chunk = (uint32_t)((uint64_t)m / (warps * 16));
+            chunk = chunk < 32u ? 32u : (chunk > 128u ? 128u : chunk);
+            chunk &= ~31u;
+            uint64_t want = ((uint64_t)m + chunk - 1) / chunk;             // one chunk per warp at least
+            want = (want + (kBlock / 32) - 1) / (kBlock / 32);
             const unsigned blocks = (unsigned)(want < cap ? want : cap);
             unsigned int *ctr = a->d_work + (a->work_slot++ & 63u);
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
-            pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m,
+            pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                            d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr, ctr);
             LAUNCHED();
             CUDA_OK(cudaGetLastError());
@@ -284,6 +291,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         if (upload(&a->d_tris32, a->flat.tris32, a->device_bytes)) return -1;
         if (upload(&a->d_nodes64, a->flat.nodes64, a->device_bytes)) return -1;
         if (upload(&a->d_tris64, a->flat.tris64, a->device_bytes)) return -1;
+        if (upload(&a->d_slot_of_prim, a->flat.slot_of_prim, a->device_bytes)) return -1;
         CUDA_OK(cudaMalloc((void **)&a->d_counters, 8 * sizeof(unsigned long long)));
         CUDA_OK(cudaMalloc((void **)&a->d_work, 64 * sizeof(unsigned int)));
         CUDA_OK(cudaMallocHost(&a->h_pin, 4096));
@@ -295,6 +303,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
     // flat host copies are no longer needed (keep the small header fields)
     std::vector<Node32>().swap(a->flat.nodes32); std::vector<Tri32>().swap(a->flat.tris32);
     std::vector<Node64>().swap(a->flat.nodes64); std::vector<Tri64>().swap(a->flat.tris64);
+    std::vector<uint32_t>().swap(a->flat.slot_of_prim);
     return a;
 }
 
@@ -304,7 +313,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
-    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64);
+    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_slot_of_prim);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     for (auto p : a->d_frame) cudaFree(p);
     cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work);
@@ -357,7 +366,7 @@ extern "C" int64_t ri_b200_export_flat(const ri_b200_accel_t *a, void *nodes32, 
     if (nodes64 && !f.nodes64.empty()) std::memcpy(nodes64, f.nodes64.data(), f.nodes64.size() * sizeof(Node64));
     if (tris32 && !f.tris32.empty()) std::memcpy(tris32, f.tris32.data(), f.tris32.size() * sizeof(Tri32));
     if (tris64 && !f.tris64.empty()) std::memcpy(tris64, f.tris64.data(), f.tris64.size() * sizeof(Tri64));
-    if (header_out) { header_out[0] = f.root_word; header_out[1] = f.ninner; header_out[2] = f.top_count; header_out[3] = 0; }
+    if (header_out) { header_out[0] = f.root_word; header_out[1] = f.ninner; header_out[2] = f.top_count; header_out[3] = (uint32_t)f.nslots; }
     return (int64_t)f.ninner;
 }
 
@@ -530,11 +539,11 @@ __device__ __forceinline__ void ortho_basis(double b0[3], double b1[3], const do
     normalize3(b1);
 }
 
-__device__ __forceinline__ void state_from_hit(const Tri64 *tris, const double org[3], const double dir[3], double t, uint32_t prim,
-                                               ri_b200_state_f64 &s)
+__device__ __forceinline__ void state_from_hit(const Tri64 *tris, const uint32_t *slot_of_prim, const double org[3], const double dir[3],
+                                               double t, uint32_t prim, ri_b200_state_f64 &s)
 {
     TriRegs<double> tr;
-    load_tri(tris + prim, tr);
+    load_tri(tris + slot_of_prim[prim], tr);
     for (int k = 0; k < 3; ++k) s.P[k] = org[k] + dir[k] * t;
     cross3(s.Ng, tr.e1, tr.e2);                                   // (v1-v0) x (v2-v0), geometric.c:20-33
     normalize3(s.Ng);
@@ -542,7 +551,7 @@ __device__ __forceinline__ void state_from_hit(const Tri64 *tris, const double o
     ortho_basis(s.tangent, s.binormal, s.Ng);
 }
 
-__global__ void state_kernel(const Tri64 *__restrict__ tris, const double *__restrict__ rays,
+__global__ void state_kernel(const Tri64 *__restrict__ tris, const uint32_t *__restrict__ slot_of_prim, const double *__restrict__ rays,
                              const ri_b200_hit_f64 *__restrict__ hits, uint64_t n, ri_b200_state_f64 *__restrict__ out)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -552,7 +561,7 @@ __global__ void state_kernel(const Tri64 *__restrict__ tris, const double *__res
     if (h.hit) {
         double org[3], dir[3];
         RayIO<double>::load(rays, i, org, dir);
-        state_from_hit(tris, org, dir, h.t, h.prim, s);
+        state_from_hit(tris, slot_of_prim, org, dir, h.t, h.prim, s);
     } else {
         memset(&s, 0, sizeof(s));
     }
@@ -573,7 +582,7 @@ extern "C" int ri_b200_state_batch_f64(ri_b200_accel_t *a, const double *rays, c
         CUDA_OK(cudaMalloc((void **)&d_out, n * sizeof(ri_b200_state_f64)));
         CUDA_OK(cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, a->stream));
         CUDA_OK(cudaMemcpyAsync(d_hits, hits, n * sizeof(ri_b200_hit_f64), cudaMemcpyHostToDevice, a->stream));
-        state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->d_tris64, d_rays, d_hits, n, d_out);
+        state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->d_tris64, a->d_slot_of_prim, d_rays, d_hits, n, d_out);
         LAUNCHED();
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaMemcpyAsync(out, d_out, n * sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));
@@ -602,7 +611,7 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
     CUDA_OK(cudaMemcpyAsync(d_ray, h, 48, cudaMemcpyHostToDevice, a->stream));
     if (launch_trace<double, false, false>(a, d_ray, 1, d_hit, nullptr, nullptr, a->stream)) return -1;
     if (state) {
-        state_kernel<<<1, 32, 0, a->stream>>>(a->d_tris64, d_ray, d_hit, 1, d_state);
+        state_kernel<<<1, 32, 0, a->stream>>>(a->d_tris64, a->d_slot_of_prim, d_ray, d_hit, 1, d_state);
         LAUNCHED();
     }
     CUDA_OK(cudaMemcpyAsync((char *)a->h_pin + 64, d + 64, 64 + sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));

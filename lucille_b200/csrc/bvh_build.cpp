@@ -349,9 +349,21 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
     }
     out.ninner = (uint32_t)order.size();
 
+    // triangle slots: each leaf starts at an even slot (DFS order of leaves == post-build triangle order)
+    std::vector<uint32_t> slot_of(nn, 0);
+    uint64_t nslots = 0;
+    for (size_t c = 0; c < nn; ++c) {
+        const CanonNode &n = t.nodes[c];
+        if (!n.is_leaf) continue;
+        slot_of[c] = (uint32_t)nslots;
+        nslots += (uint64_t)((n.ntris + 1) & ~1ll);
+    }
+    out.nslots = nslots;
+    out.slot_of_prim.assign((size_t)t.ntris, 0);
+
     auto word = [&](int64_t c) -> uint32_t {
         const CanonNode &n = t.nodes[(size_t)c];
-        if (n.is_leaf) return kLeafFlag | ((uint32_t)(n.ntris - 1) << kLeafShift) | (uint32_t)n.tri_start;
+        if (n.is_leaf) return kLeafFlag | ((uint32_t)(n.ntris - 1) << kLeafShift) | slot_of[(size_t)c];
         return dev[(size_t)c];
     };
     out.root_word = word(0);
@@ -382,22 +394,33 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
         }
     }
 
-    if (want32) out.tris32.resize((size_t)t.ntris);
-    if (want64) out.tris64.resize((size_t)t.ntris);
-    for (uint64_t p = 0; p < t.ntris; ++p) {
-        const double *v = t.tri.data() + 9 * p;
-        if (want32) {
-            Tri32 &d = out.tris32[(size_t)p];
-            for (int k = 0; k < 3; ++k) {
-                const float v0 = (float)v[k], v1 = (float)v[3 + k], v2 = (float)v[6 + k];
-                d.v0[k] = v0; d.e1[k] = v1 - v0; d.e2[k] = v2 - v0;      // bvh.c:747-752, in fp32
+    if (want32) { out.tris32.resize((size_t)nslots); std::memset(out.tris32.data(), 0, out.tris32.size() * sizeof(Tri32)); }
+    if (want64) { out.tris64.resize((size_t)nslots); std::memset(out.tris64.data(), 0, out.tris64.size() * sizeof(Tri64)); }
+    for (size_t c = 0; c < nn; ++c) {
+        const CanonNode &n = t.nodes[c];
+        if (!n.is_leaf) continue;
+        for (int64_t i = 0; i < n.ntris; ++i) {
+            const uint64_t p = (uint64_t)(n.tri_start + i), slot = (uint64_t)slot_of[c] + (uint64_t)i;
+            const double *v = t.tri.data() + 9 * p;
+            out.slot_of_prim[(size_t)p] = (uint32_t)slot;
+            if (want32) {
+                Tri32 &d = out.tris32[(size_t)slot];
+                for (int k = 0; k < 3; ++k) {
+                    const float v0 = (float)v[k], v1 = (float)v[3 + k], v2 = (float)v[6 + k];
+                    d.v0[k] = v0; d.e1[k] = v1 - v0; d.e2[k] = v2 - v0;      // bvh.c:747-752, in fp32
+                }
+                d.prim = (uint32_t)p;
             }
-            d.v0[3] = d.e1[3] = d.e2[3] = 0.0f;
+            if (want64) {
+                Tri64 &d = out.tris64[(size_t)slot];
+                for (int k = 0; k < 3; ++k) { d.v0[k] = v[k]; d.e1[k] = v[3 + k] - v[k]; d.e2[k] = v[6 + k] - v[k]; }
+                d.prim = p;
+            }
         }
-        if (want64) {
-            Tri64 &d = out.tris64[(size_t)p];
-            for (int k = 0; k < 3; ++k) { d.v0[k] = v[k]; d.e1[k] = v[3 + k] - v[k]; d.e2[k] = v[6 + k] - v[k]; }
-            d.pad = 0.0;
+        if (n.ntris & 1) {                                   // filler slot: zero-area triangle, prim = MISS
+            const uint64_t slot = (uint64_t)slot_of[c] + (uint64_t)n.ntris;
+            if (want32) out.tris32[(size_t)slot].prim = 0xffffffffu;
+            if (want64) out.tris64[(size_t)slot].prim = 0xffffffffull;
         }
     }
 }

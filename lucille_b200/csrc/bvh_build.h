@@ -42,8 +42,8 @@ void build_tree(const double *tri_xyz, uint64_t ntris, HostTree &out, int nthrea
 
 constexpr uint32_t kLeafFlag  = 0x80000000u;
 constexpr uint32_t kDoneWord  = 0x7fffffffu;
-constexpr uint32_t kLeafShift = 27;                  // word = flag | (ntris-1)<<27 | tri_start
-constexpr uint64_t kMaxTris   = (1ull << 27) - 1;
+constexpr uint32_t kLeafShift = 27;                  // word = flag | (ntris-1)<<27 | first triangle SLOT (always even)
+constexpr uint64_t kMaxTris   = (1ull << 27) / 17 * 16 - 2;   // slots = sum over leaves of ntris rounded up to even
 
 struct Node32 {                 // 64 B, read as 4 x LDG.128
     float    x[4];              // lo0.x hi0.x lo1.x hi1.x   (slot 0 = left child, slot 1 = right child)
@@ -58,8 +58,11 @@ struct Node64 {                 // 128 B
     uint32_t c0, c1, axis, pad;
     uint32_t pad2[4];
 };
-struct Tri32 { float v0[4], e1[4], e2[4]; };          // 48 B, 3 x LDG.128
-struct Tri64 { double v0[3], e1[3], e2[3], pad; };    // 80 B, 5 x LDG.128
+// Triangle SLOTS.  Every leaf starts at an even slot and owns round_up(ntris, 2) slots, so a pair of fp32 slots is one
+// 32-byte-aligned 96-byte run = 3 x LDG.256; the odd leftover slot of a leaf holds a zero-area triangle (never hit:
+// |det| <= 1e-14 rejects it, bvh.c:759-763).  `prim` = position in the post-build triangle order (the hit id).
+struct Tri32 { float v0[3]; uint32_t prim; float e1[3]; uint32_t pad1; float e2[3]; uint32_t pad2; };          // 48 B
+struct Tri64 { double v0[3]; uint64_t prim; double e1[3]; uint64_t pad1; double e2[3]; uint64_t pad2; };       // 96 B = 3 x LDG.256
 
 struct FlatTree {
     uint32_t root_word = kDoneWord;  // inner index, leaf word, or kDoneWord for an empty scene
@@ -67,8 +70,10 @@ struct FlatTree {
     uint32_t top_count = 0;          // the first top_count inner nodes are in BFS order (SMEM-resident cluster)
     std::vector<Node32> nodes32;
     std::vector<Node64> nodes64;
-    std::vector<Tri32>  tris32;
+    std::vector<Tri32>  tris32;      // nslots entries
     std::vector<Tri64>  tris64;
+    uint64_t nslots = 0;
+    std::vector<uint32_t> slot_of_prim;   // post-build triangle position -> slot
     float  smin32[3], smax32[3];
 };
 

@@ -135,7 +135,7 @@ template <> struct StateMath<double> {
                                                  uint32_t prim, double rec[12])
     {
         ri_b200_state_f64 s;
-        state_from_hit(S.tris, org, dir, t, prim, s);
+        state_from_hit(S.tris, S.slot_of_prim, org, dir, t, prim, s);
         const double eps = 1.0e-6;                                      // ambientocclusion.c:56,73-75
         double b0[3], b1[3];
         ortho_basis(b0, b1, s.Ns);                                      // ambientocclusion.c:65
@@ -161,7 +161,7 @@ template <> struct StateMath<float> {
                                                  uint32_t prim, float rec[12])
     {
         TriRegs<float> tr;
-        load_tri(S.tris + prim, tr);
+        load_tri(S.tris + S.slot_of_prim[prim], tr);
         float n[3], b0[3], b1[3], e[3] = {0.f, 0.f, 0.f};
         crs(n, tr.e1, tr.e2);
         nrm(n);

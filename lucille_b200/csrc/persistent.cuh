@@ -1,23 +1,47 @@
 // Persistent-threads wavefront traverser (the production ray-batch kernel).
 //
-// The grid is sized to the machine (resident CTAs per SM x 148 SMs) and every warp loops:
-//   fetch    idle lanes are refilled from the ray batch: the warp takes chunks of kChunk consecutive rays
-//            with ONE global atomicAdd per chunk and hands them to idle lanes by ballot rank, so a lane
-//            whose ray terminates (any-hit found, or the stack ran dry) is replaced at once instead of
-//            idling until the slowest ray of its warp finishes
-//   traverse synchronised while-while: all lanes descend inner nodes until each holds a leaf word,
-//            then all lanes run their leaf's Moeller-Trumbore loop, pop, and the warp re-ballots
-// Per-ray arithmetic, visiting order and tie rules are exactly those of trace_ray() (trace.cuh); only
-// the assignment of rays to lanes changes, so results are bit-identical to the one-ray-per-thread kernel.
+// The grid is sized to the machine (resident CTAs per SM x 148 SMs) and every warp loops over three kinds of step:
+//   fetch     idle lanes are refilled from the ray batch: the warp takes chunks of consecutive rays with ONE global
+//             atomicAdd per chunk and hands them to idle lanes by ballot rank, so a lane whose ray terminates (any-hit
+//             found, or the stack ran dry) is replaced at once instead of idling until the slowest ray of its warp ends
+//   node step every lane that holds an inner-node word tests the two child boxes of ITS node (2 x LDG.256 per fp32 node)
+//             and descends / pushes / pops
+//   leaf step every lane that holds a leaf word tests the next PAIR of triangles of ITS leaf (3 x LDG.256 per fp32 pair)
+// Which of node/leaf step runs next is decided by a warp vote (__ballot_sync + __popc): the kind more lanes are waiting
+// for.  A lane's own sequence of box tests, triangle tests, pushes and pops -- and therefore its arithmetic, visiting
+// order and tie rules -- is exactly that of trace_ray() (trace.cuh) / bvh_traverse (bvh.c:1092-1188); only the
+// interleaving between lanes changes, so results are bit-identical to the one-ray-per-thread kernel.
 #pragma once
 
 namespace b200 {
 
-constexpr unsigned kChunk = 128;        // rays per atomic fetch (one warp)
+template <typename Real> struct LeafStep;
+
+template <> struct LeafStep<float> {                 // two slots per step
+    static constexpr uint32_t kPerStep = 2;
+    static __device__ __forceinline__ void run(const Tri32 *tris, uint32_t slot, uint32_t left, const float org[3], const float dir[3],
+                                               float &tl, float &ul, float &vl, uint32_t &tprim)
+    {
+        TriRegs<float> a, b;
+        load_tri_pair(tris + slot, a, b);
+        if (tri_test<float>(a, org, dir, tl, ul, vl)) tprim = a.prim;
+        if (left > 1u) { if (tri_test<float>(b, org, dir, tl, ul, vl)) tprim = b.prim; }
+    }
+};
+template <> struct LeafStep<double> {                // one slot per step
+    static constexpr uint32_t kPerStep = 1;
+    static __device__ __forceinline__ void run(const Tri64 *tris, uint32_t slot, uint32_t left, const double org[3], const double dir[3],
+                                               double &tl, double &ul, double &vl, uint32_t &tprim)
+    {
+        TriRegs<double> a;
+        load_tri_wide(tris + slot, a);
+        if (tri_test<double>(a, org, dir, tl, ul, vl)) tprim = a.prim;
+    }
+};
 
 template <typename Real, bool ANYHIT>
 __global__ void __launch_bounds__(kBlock)
-trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const uint32_t n,
+trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const uint32_t n, const uint32_t chunk,
                         typename RayIO<Real>::Hit *__restrict__ hits, uint8_t *__restrict__ occ,
                         unsigned int *__restrict__ work_counter)
 {
@@ -28,32 +52,53 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
     const unsigned lt_mask = (1u << lane) - 1u;
 
     uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
-    bool exhausted = (S.root_word == kDoneWord) && false;
+    bool exhausted = false;                      // warp-uniform
 
-    // per-lane ray state
-    bool busy = false;
-    uint32_t idx = 0, cur = kDoneWord, sp = 0, best_prim = 0xffffffffu;
+    // per-lane ray state.  mode: 0 idle, 1 holds an inner-node word in `cur`, 2 inside a leaf
+    uint32_t mode = 0, idx = 0, cur = 0, sp = 0, best_prim = 0xffffffffu;
+    uint32_t leaf_slot = 0, leaf_left = 0, tprim = 0xffffffffu;
     Real org[3], dir[3], inv[3], best_t = P::inf(), best_u = Real(0), best_v = Real(0);
+    Real tl = P::inf(), ul = Real(0), vl = Real(0);
     bool sx = false, sy = false, sz = false;
     org[0] = org[1] = org[2] = dir[0] = dir[1] = dir[2] = inv[0] = inv[1] = inv[2] = Real(0);
 
+    // enter `word`: inner node -> mode 1, leaf -> mode 2 with a fresh leaf-local closest t (bvh.c:833-836)
+#define B200_ENTER(word)                                                                        \
+    do {                                                                                        \
+        cur = (word);                                                                           \
+        if (cur & kLeafFlag) {                                                                  \
+            mode = 2u; leaf_slot = cur & ((1u << kLeafShift) - 1u);                             \
+            leaf_left = ((cur >> kLeafShift) & 15u) + 1u;                                       \
+            tl = P::inf(); ul = Real(0); vl = Real(0); tprim = 0xffffffffu;                     \
+        } else mode = 1u;                                                                       \
+    } while (0)
+
+    // retire this lane's ray: write the result, go idle
+#define B200_RETIRE()                                                                           \
+    do {                                                                                        \
+        const bool hit__ = best_t < P::inf();                                                   \
+        if (ANYHIT) occ[idx] = hit__ ? 1 : 0;                                                   \
+        else RayIO<Real>::store(hits, idx, hit__, best_t, best_u, best_v, best_prim);           \
+        mode = 0u;                                                                              \
+    } while (0)
+
     for (;;) {
         // ------------------------------------------------------------------ fetch
-        unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        unsigned idle = __ballot_sync(0xffffffffu, mode == 0u);
         while (idle && !exhausted) {
             if (chunk_next >= chunk_end) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(work_counter, kChunk);
+                if (lane == 0) base = atomicAdd(work_counter, chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (base >= n) { exhausted = true; break; }
                 chunk_next = base;
-                chunk_end = (n - base < kChunk) ? n : base + kChunk;
+                chunk_end = (n - base < chunk) ? n : base + chunk;
             }
             const unsigned avail = chunk_end - chunk_next;
             const unsigned n_idle = __popc(idle);
             const unsigned take = n_idle < avail ? n_idle : avail;
             const unsigned rank = __popc(idle & lt_mask);
-            if (!busy && rank < take) {
+            if (mode == 0u && rank < take) {
                 idx = chunk_next + rank;
                 RayIO<Real>::load(rays, idx, org, dir);
                 best_t = P::inf(); best_u = Real(0); best_v = Real(0); best_prim = 0xffffffffu;
@@ -64,77 +109,69 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
                 Real tmin;
                 const bool in_scene = (S.root_word != kDoneWord) &&
                     slab<Real>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
-                if (in_scene) {
-                    busy = true; cur = S.root_word; sp = 0;
-                } else {                           // bvh.c:446 / 522-526: miss without traversal
-                    if (ANYHIT) occ[idx] = 0;
-                    else RayIO<Real>::store(hits, idx, false, best_t, best_u, best_v, best_prim);
-                }
+                sp = 0;
+                if (in_scene) B200_ENTER(S.root_word);
+                else B200_RETIRE();              // bvh.c:446 / 522-526: miss without traversal
             }
             chunk_next += take;
-            idle = __ballot_sync(0xffffffffu, !busy);
+            idle = __ballot_sync(0xffffffffu, mode == 0u);
         }
         if (idle == 0xffffffffu) break;          // nothing in flight and nothing left to fetch
 
-        // ------------------------------------------------------------------ traverse
+        // ------------------------------------------------------------------ traverse: vote, step, repeat
         for (;;) {
-            // inner phase: every busy lane descends until it holds a leaf word (or finishes)
-            while (busy && !(cur & kLeafFlag)) {
-                NodeRegs<Real> nd;
-                load_node(S.nodes + cur, nd);
-                Real tmin0, tmin1;
-                const bool h0 = slab<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, tmin0) && (tmin0 < best_t);
-                const bool h1 = slab<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, tmin1) && (tmin1 < best_t);
-                if (h0 && h1) {
-                    const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);
-                    stk[sp * kBlock] = order ? nd.c0 : nd.c1;
-                    ++sp;
-                    cur = order ? nd.c1 : nd.c0;
-                } else if (h0) {
-                    cur = nd.c0;
-                } else if (h1) {
-                    cur = nd.c1;
-                } else if (sp == 0) {
-                    busy = false;                 // stack ran dry: this ray is finished
-                } else {
-                    --sp;
-                    cur = stk[sp * kBlock];
+            const unsigned want_node = __ballot_sync(0xffffffffu, mode == 1u);
+            const unsigned want_leaf = __ballot_sync(0xffffffffu, mode == 2u);
+            if ((want_node | want_leaf) == 0u) break;
+            if (!exhausted && (want_node | want_leaf) != 0xffffffffu) break;     // a lane idles and rays remain: refill
+
+            if (__popc(want_node) >= __popc(want_leaf)) {
+                if (mode == 1u) {                // ---- node step: bvh.c:1153-1179
+                    NodeRegs<Real> nd;
+                    load_node_wide(S.nodes + cur, nd);
+                    const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
+                    const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
+                    if (h0 && h1) {
+                        const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);
+                        stk[sp * kBlock] = order ? nd.c0 : nd.c1;
+                        ++sp;
+                        B200_ENTER(order ? nd.c1 : nd.c0);
+                    } else if (h0) {
+                        B200_ENTER(nd.c0);
+                    } else if (h1) {
+                        B200_ENTER(nd.c1);
+                    } else if (sp == 0) {
+                        B200_RETIRE();
+                    } else {
+                        --sp;
+                        B200_ENTER(stk[sp * kBlock]);
+                    }
+                }
+            } else {
+                if (mode == 2u) {                // ---- leaf step: bvh.c:838-861
+                    LeafStep<Real>::run(S.tris, leaf_slot, leaf_left, org, dir, tl, ul, vl, tprim);
+                    leaf_slot += LeafStep<Real>::kPerStep;
+                    // occlusion query: the first accepted triangle already decides the answer -- the rest of the leaf
+                    // could only lower the leaf-local t, and the commit test of bvh.c:850 is tl < 1e38 here
+                    const bool decided = ANYHIT && (tl < P::inf());
+                    if (leaf_left > LeafStep<Real>::kPerStep && !decided) {
+                        leaf_left -= LeafStep<Real>::kPerStep;
+                    } else {                     // leaf finished: commit (bvh.c:850), then pop or retire
+                        bool done = false;
+                        if (tprim != 0xffffffffu && (tl < best_t)) {
+                            best_t = tl; best_u = ul; best_v = vl; best_prim = tprim;
+                            if (ANYHIT) done = true;
+                        }
+                        if (!done && sp == 0) done = true;
+                        if (done) B200_RETIRE();
+                        else { --sp; B200_ENTER(stk[sp * kBlock]); }
+                    }
                 }
             }
-            // leaf phase
-            if (busy) {
-                const uint32_t start = cur & ((1u << kLeafShift) - 1u);
-                const uint32_t count = ((cur >> kLeafShift) & 15u) + 1u;
-                Real tl = P::inf(), ul = Real(0), vl = Real(0);
-                uint32_t tid = 0;
-                bool any = false;
-                for (uint32_t i = 0; i < count; ++i) {
-                    TriRegs<Real> tr;
-                    load_tri(S.tris + start + i, tr);
-                    if (tri_test<Real>(tr, org, dir, tl, ul, vl)) { tid = i; any = true; }
-                }
-                if (any && (tl < best_t)) {       // bvh.c:850
-                    best_t = tl; best_u = ul; best_v = vl; best_prim = start + tid;
-                    if (ANYHIT) busy = false;
-                }
-                if (busy) {
-                    if (sp == 0) busy = false;
-                    else { --sp; cur = stk[sp * kBlock]; }
-                }
-            }
-            // retire finished rays
-            const bool finished = !busy && (cur != kDoneWord);
-            if (finished) {
-                const bool hit = best_t < P::inf();
-                if (ANYHIT) occ[idx] = hit ? 1 : 0;
-                else RayIO<Real>::store(hits, idx, hit, best_t, best_u, best_v, best_prim);
-                cur = kDoneWord;
-            }
-            const unsigned live = __ballot_sync(0xffffffffu, busy);
-            if (live == 0u) break;
-            if (!exhausted && live != 0xffffffffu) break;     // some lane idles and rays remain: refill
         }
     }
+#undef B200_ENTER
+#undef B200_RETIRE
 }
 
 }  // namespace b200

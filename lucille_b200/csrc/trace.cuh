@@ -2,7 +2,7 @@
 //
 // One ray per lane, ordered depth-first traversal of the reference-identical binary BVH with a
 // per-lane short stack kept in shared memory ([depth][lane] layout: conflict-free), 128-bit loads
-// of node records (4 x LDG.128 per fp32 node) and triangle records (3 x LDG.128), leaf
+// of node records and triangle slots (this reference kernel: LDG.128; the persistent kernel: LDG.256), leaf
 // Moeller-Trumbore with the reference's acceptance window and tie rules.
 //
 // Semantics follow lucille's src/render/bvh.c exactly (430-542 ray setup + scene-box rejection,
@@ -40,6 +40,7 @@ template <> struct Prec<double> {
 template <typename Real> struct SceneView {
     const typename Prec<Real>::Node *nodes;
     const typename Prec<Real>::Tri  *tris;
+    const uint32_t *slot_of_prim;      // hit id (post-build triangle position) -> triangle slot
     Real     smin[3], smax[3];
     uint32_t root_word;
     uint32_t top_count;
@@ -72,13 +73,13 @@ __device__ __forceinline__ void load_node(const Node64 *p, NodeRegs<double> &r)
     r.c0 = d.x; r.c1 = d.y; r.axis = d.z;
 }
 
-template <typename Real> struct TriRegs { Real v0[3], e1[3], e2[3]; };
+template <typename Real> struct TriRegs { Real v0[3], e1[3], e2[3]; uint32_t prim; };
 
 __device__ __forceinline__ void load_tri(const Tri32 *p, TriRegs<float> &r)
 {
     const float4 *q = reinterpret_cast<const float4 *>(p);
     const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    r.v0[0] = a.x; r.v0[1] = a.y; r.v0[2] = a.z;
+    r.v0[0] = a.x; r.v0[1] = a.y; r.v0[2] = a.z; r.prim = __float_as_uint(a.w);
     r.e1[0] = b.x; r.e1[1] = b.y; r.e1[2] = b.z;
     r.e2[0] = c.x; r.e2[1] = c.y; r.e2[2] = c.z;
 }
@@ -86,10 +87,70 @@ __device__ __forceinline__ void load_tri(const Tri32 *p, TriRegs<float> &r)
 __device__ __forceinline__ void load_tri(const Tri64 *p, TriRegs<double> &r)
 {
     const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
-    r.v0[0] = a.x; r.v0[1] = a.y; r.v0[2] = b.x;
-    r.e1[0] = b.y; r.e1[1] = c.x; r.e1[2] = c.y;
-    r.e2[0] = d.x; r.e2[1] = d.y; r.e2[2] = e.x;
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+    r.v0[0] = a.x; r.v0[1] = a.y; r.v0[2] = b.x; r.prim = (uint32_t)__double_as_longlong(b.y);
+    r.e1[0] = c.x; r.e1[1] = c.y; r.e1[2] = d.x;
+    r.e2[0] = e.x; r.e2[1] = e.y; r.e2[2] = f.x;
+}
+
+// 256-bit global loads (sm_100: LDG.E.256): one L1 wavefront moves 32 bytes of a lane's record instead of 16 ---------
+struct __align__(32) F8 { float v[8]; };
+struct __align__(32) D4 { double v[4]; };
+
+__device__ __forceinline__ F8 ldg256(const void *p)
+{
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ D4 ldg256d(const void *p)
+{
+    D4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void load_node_wide(const Node32 *p, NodeRegs<float> &r)
+{
+    const F8 a = ldg256(p), b = ldg256(reinterpret_cast<const char *>(p) + 32);
+    r.x[0] = a.v[0]; r.x[1] = a.v[1]; r.x[2] = a.v[2]; r.x[3] = a.v[3];
+    r.y[0] = a.v[4]; r.y[1] = a.v[5]; r.y[2] = a.v[6]; r.y[3] = a.v[7];
+    r.z[0] = b.v[0]; r.z[1] = b.v[1]; r.z[2] = b.v[2]; r.z[3] = b.v[3];
+    r.c0 = __float_as_uint(b.v[4]); r.c1 = __float_as_uint(b.v[5]); r.axis = __float_as_uint(b.v[6]);
+}
+__device__ __forceinline__ void load_node_wide(const Node64 *p, NodeRegs<double> &r)
+{
+    const char *c = reinterpret_cast<const char *>(p);
+    const D4 a = ldg256d(c), b = ldg256d(c + 32), d = ldg256d(c + 64);
+    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(c + 96));
+    r.x[0] = a.v[0]; r.x[1] = a.v[1]; r.x[2] = a.v[2]; r.x[3] = a.v[3];
+    r.y[0] = b.v[0]; r.y[1] = b.v[1]; r.y[2] = b.v[2]; r.y[3] = b.v[3];
+    r.z[0] = d.v[0]; r.z[1] = d.v[1]; r.z[2] = d.v[2]; r.z[3] = d.v[3];
+    r.c0 = w.x; r.c1 = w.y; r.axis = w.z;
+}
+
+// a PAIR of fp32 triangle slots (even slot first): 96 contiguous, 32-byte-aligned bytes = 3 x LDG.256
+__device__ __forceinline__ void load_tri_pair(const Tri32 *p, TriRegs<float> &a, TriRegs<float> &b)
+{
+    const char *c = reinterpret_cast<const char *>(p);
+    const F8 q0 = ldg256(c), q1 = ldg256(c + 32), q2 = ldg256(c + 64);
+    a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = __float_as_uint(q0.v[3]);
+    a.e1[0] = q0.v[4]; a.e1[1] = q0.v[5]; a.e1[2] = q0.v[6];
+    a.e2[0] = q1.v[0]; a.e2[1] = q1.v[1]; a.e2[2] = q1.v[2];
+    b.v0[0] = q1.v[4]; b.v0[1] = q1.v[5]; b.v0[2] = q1.v[6]; b.prim = __float_as_uint(q1.v[7]);
+    b.e1[0] = q2.v[0]; b.e1[1] = q2.v[1]; b.e1[2] = q2.v[2];
+    b.e2[0] = q2.v[4]; b.e2[1] = q2.v[5]; b.e2[2] = q2.v[6];
+}
+// one fp64 triangle slot: 96 bytes, 32-byte aligned = 3 x LDG.256
+__device__ __forceinline__ void load_tri_wide(const Tri64 *p, TriRegs<double> &a)
+{
+    const char *c = reinterpret_cast<const char *>(p);
+    const D4 q0 = ldg256d(c), q1 = ldg256d(c + 32), q2 = ldg256d(c + 64);
+    a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = (uint32_t)__double_as_longlong(q0.v[3]);
+    a.e1[0] = q1.v[0]; a.e1[1] = q1.v[1]; a.e1[2] = q1.v[2];
+    a.e2[0] = q2.v[0]; a.e2[1] = q2.v[1]; a.e2[2] = q2.v[2];
 }
 
 // bvh.c:869-936: one child's slab test; lo/hi picked by the ray's sign bits ---------------------
@@ -109,6 +170,29 @@ __device__ __forceinline__ bool slab(Real lox, Real hix, Real loy, Real hiy, Rea
     tmax = (tmax < tfz) ? tmax : tfz;
     tmin_out = tmin;
     return (tmax > Real(0)) && (tmin <= tmax);
+}
+
+// Same test with hardware min/max (FMNMX).  `(a > b) ? a : b` and fmax(a, b) return the same VALUE for every non-NaN
+// pair (they can differ only in the sign of a zero, which the comparisons that consume tmin/tmax do not see), and no NaN
+// can arise here: 1/dir is finite (|dir| > 1e-14 or +-REAL_MAX), so (plane - org) * inv is finite or +-inf, never 0 * inf.
+__device__ __forceinline__ float  rmax(float a, float b)   { return fmaxf(a, b); }
+__device__ __forceinline__ float  rmin(float a, float b)   { return fminf(a, b); }
+__device__ __forceinline__ double rmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double rmin(double a, double b) { return fmin(a, b); }
+
+template <typename Real>
+__device__ __forceinline__ bool slab_mm(Real lox, Real hix, Real loy, Real hiy, Real loz, Real hiz,
+                                        const Real org[3], const Real inv[3], bool sx, bool sy, bool sz, Real best_t)
+{
+    const Real nx = sx ? hix : lox, fx = sx ? lox : hix;
+    const Real ny = sy ? hiy : loy, fy = sy ? loy : hiy;
+    const Real nz = sz ? hiz : loz, fz = sz ? loz : hiz;
+    const Real tnx = (nx - org[0]) * inv[0], tfx = (fx - org[0]) * inv[0];
+    const Real tny = (ny - org[1]) * inv[1], tfy = (fy - org[1]) * inv[1];
+    const Real tnz = (nz - org[2]) * inv[2], tfz = (fz - org[2]) * inv[2];
+    const Real tmin = rmax(rmax(tnx, tny), tnz);
+    const Real tmax = rmin(rmin(tfx, tfy), tfz);
+    return (tmax > Real(0)) && (tmin <= tmax) && (tmin < best_t);          // bvh.c:925 and 1038-1044
 }
 
 // bvh.c:730-791 triangle_isect against the leaf-local closest t ------------------------------
@@ -195,16 +279,16 @@ __device__ __forceinline__ bool trace_ray(const SceneView<Real> &S, const Real o
             const uint32_t start = cur & ((1u << kLeafShift) - 1u);
             const uint32_t count = ((cur >> kLeafShift) & 15u) + 1u;
             Real tl = P::inf(), ul = Real(0), vl = Real(0);
-            uint32_t tid = 0;
+            uint32_t tprim = 0;
             bool any = false;
             if (COUNT) { cnt->nleaf++; cnt->ntris += count; }
             for (uint32_t i = 0; i < count; ++i) {
                 TriRegs<Real> tr;
                 load_tri(S.tris + start + i, tr);
-                if (tri_test<Real>(tr, org, dir, tl, ul, vl)) { tid = i; any = true; if (COUNT) cnt->nhit++; }
+                if (tri_test<Real>(tr, org, dir, tl, ul, vl)) { tprim = tr.prim; any = true; if (COUNT) cnt->nhit++; }
             }
             if (any && (tl < best_t)) {                       // bvh.c:850
-                best_t = tl; best_u = ul; best_v = vl; best_prim = start + tid;
+                best_t = tl; best_u = ul; best_v = vl; best_prim = tprim;
                 if (ANYHIT) break;
             }
         }

@@ -91,7 +91,7 @@ def test_flat_records_decode_to_canonical_tree(n):
         for d, c in zip(dec, canon):
             assert d["is_leaf"] == c["is_leaf"]
             if d["is_leaf"]:
-                assert d["tri_start"] == c["tri_start"] and d["ntris"] == c["ntris"]
+                assert d["ntris"] == c["ntris"]          # the word's start is a SLOT index, checked below
             else:
                 assert d["axis"] == c["axis"] and d["child0"] == c["child0"] and d["child1"] == c["child1"]
                 lb, rb = np.array(d["lbox"], dtype=np.float64), np.array(d["rbox"], dtype=np.float64)
@@ -101,16 +101,27 @@ def test_flat_records_decode_to_canonical_tree(n):
                     for got, want in ((lb, c["lbox"]), (rb, c["rbox"])):
                         assert np.all(got[:3] <= want[:3]) and np.all(got[3:] >= want[3:])
                         assert np.all(np.abs(got - want) <= np.spacing(np.abs(want).astype(np.float32)).astype(np.float64))
-    # triangles: v0, e1 = v1 - v0, e2 = v2 - v0 in post-build order
+    # triangle slots: every leaf starts at an even slot, owns round_up(ntris, 2) slots, carries prim ids in post-build
+    # order; v0, e1 = v1 - v0, e2 = v2 - v0; the odd filler slot is a zero-area triangle with prim = MISS
     order = a.triorder()
-    t64 = flat["tris64"]
     src = tris[order]
-    assert np.array_equal(t64["v0"], src[:, 0]) and np.array_equal(t64["e1"], src[:, 1] - src[:, 0])
-    assert np.array_equal(t64["e2"], src[:, 2] - src[:, 0])
-    t32 = flat["tris32"]
-    s32 = src.astype(np.float32)
-    assert np.array_equal(t32["v0"][:, :3], s32[:, 0]) and np.array_equal(t32["e1"][:, :3], s32[:, 1] - s32[:, 0])
-    # the first top_count inner nodes are in BFS order: children of node i have larger indices
+    leaves = canon[canon["is_leaf"] == 1]
+    t64, t32 = flat["tris64"], flat["tris32"]
+    assert flat["nslots"] == int(((leaves["ntris"] + 1) // 2 * 2).sum()) == len(t32) == len(t64)
+    leaf_words = [d for d in _decode(flat, 32) if d["is_leaf"]]
+    for d, c in zip(leaf_words, leaves):
+        s0, cnt, p0 = d["tri_start"], int(c["ntris"]), int(c["tri_start"])
+        assert s0 % 2 == 0
+        assert np.array_equal(t32["prim"][s0:s0 + cnt], np.arange(p0, p0 + cnt))
+        assert np.array_equal(t64["prim"][s0:s0 + cnt], np.arange(p0, p0 + cnt))
+        assert np.array_equal(t64["v0"][s0:s0 + cnt], src[p0:p0 + cnt, 0])
+        assert np.array_equal(t64["e1"][s0:s0 + cnt], src[p0:p0 + cnt, 1] - src[p0:p0 + cnt, 0])
+        assert np.array_equal(t64["e2"][s0:s0 + cnt], src[p0:p0 + cnt, 2] - src[p0:p0 + cnt, 0])
+        s32 = src[p0:p0 + cnt].astype(np.float32)
+        assert np.array_equal(t32["v0"][s0:s0 + cnt], s32[:, 0]) and np.array_equal(t32["e1"][s0:s0 + cnt], s32[:, 1] - s32[:, 0])
+        assert np.array_equal(t32["e2"][s0:s0 + cnt], s32[:, 2] - s32[:, 0])
+        if cnt & 1:
+            assert t32["prim"][s0 + cnt] == 0xFFFFFFFF and not t32["e1"][s0 + cnt].any() and not t32["e2"][s0 + cnt].any()
     assert flat["top_count"] == min(1024, flat["ninner"])
 
 
