@@ -155,8 +155,18 @@ int ri_b200_render_ao(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, floa
 int ri_b200_render_ao_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *d_rgb, void *stream,
                           ri_b200_frame_stats_t *stats);
 
-/* MT19937 stream of randomMT2() generated on the device (random.c:98-112,211-247); HOST output, for tests */
-int ri_b200_mt_stream(uint32_t seed, uint64_t n, uint32_t *out_u32, int device);
+/* multi-GPU form: only this rank's pixels, PACKED in visiting order ([npixels][3] floats, the NCCL send buffer -- the
+ * resolve kernel writes it directly, no staging copy).  ri_b200_frame_pixels() gives that order for any (rank, world):
+ * out[i] = x | y << 16 for the i-th pixel of rank `frame->rank` (spiral bucket b belongs to rank b % world, pixels
+ * row-major inside a bucket: render.c:582-710, 1131-1146); pure host logic.  Returns the pixel count. */
+int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *d_packed, void *stream,
+                                    ri_b200_frame_stats_t *stats);
+int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
+
+/* MT19937 stream of randomMT2() generated on the device (random.c:98-112,211-247); HOST output, for tests.
+ * accel == NULL: one CTA walks the stream on `device`; accel != NULL: the frame path -- window states at segment starts
+ * by GF(2) jump-ahead (doubling tree, cached per seed in the accelerator), then one CTA per 638 976-word segment. */
+int ri_b200_mt_stream(ri_b200_accel_t *accel, uint32_t seed, uint64_t n, uint32_t *out_u32, int device);
 
 #ifdef __cplusplus
 }

@@ -108,7 +108,9 @@ ABI = [
     ("ri_b200_host_free", None, [_P]),
     ("ri_b200_render_ao", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_ao_dev", _I, [_P, _P, _P, _P, _P]),
-    ("ri_b200_mt_stream", _I, [_U32, _U64, _P, _I]),
+    ("ri_b200_render_ao_tiles_dev", _I, [_P, _P, _P, _P, _P]),
+    ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
+    ("ri_b200_mt_stream", _I, [_P, _U32, _U64, _P, _I]),
 ]
 
 _lib = None
@@ -158,10 +160,11 @@ def _ptr(a):
     return C.c_void_p(a.data_ptr())        # torch tensor
 
 
-def mt_stream(n: int, seed: int = 4357, device: int = 0) -> np.ndarray:
-    """First ``n`` 32-bit outputs of the reference's randomMT2() stream, generated on the device."""
+def mt_stream(n: int, seed: int = 4357, device: int = 0, accel: "Accel" = None) -> np.ndarray:
+    """First ``n`` 32-bit outputs of the reference's randomMT2() stream, generated on the device (sequentially by one
+    CTA, or -- with ``accel`` -- by the frame path: jump-ahead states + one CTA per segment)."""
     out = np.zeros(n, dtype=np.uint32)
-    _check(load_library().ri_b200_mt_stream(seed, n, _ptr(out), device))
+    _check(load_library().ri_b200_mt_stream(accel.data if accel is not None else None, seed, n, _ptr(out), device))
     return out
 
 
@@ -317,11 +320,28 @@ class Accel:
         _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
         return rgb, stats
 
+    def render_ao_tiles_dev(self, frame: Frame, d_packed, stream: Optional[int] = None, want_stats: bool = True):
+        """This rank's pixels only, packed [npixels,3] in visiting order, left in device memory."""
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_ao_tiles_dev(self._h(), C.byref(frame), _ptr(d_packed),
+                                                    C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
+        return stats
+
     def render_ao_dev(self, frame: Frame, d_rgb, stream: Optional[int] = None, want_stats: bool = True):
         stats = FrameStats()
         _check(self.lib.ri_b200_render_ao_dev(self._h(), C.byref(frame), _ptr(d_rgb),
                                               C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
         return stats
+
+
+def frame_pixels(frame: Frame) -> np.ndarray:
+    """Pixels (x | y << 16) rendered by ``frame.rank`` of ``frame.world`` ranks, in visiting order (host logic only)."""
+    lib = load_library()
+    n = _check(lib.ri_b200_frame_pixels(C.byref(frame), None, 0))
+    out = np.zeros(n, dtype=np.uint32)
+    if n:
+        _check(lib.ri_b200_frame_pixels(C.byref(frame), _ptr(out), n))
+    return out
 
 
 def make_frame(c2w, flength: float, is_rh: bool, width: int, height: int, xsamples: int, ysamples: int,

@@ -64,6 +64,9 @@ struct ri_b200_accel {
     void    *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
     uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
     unsigned long long *d_counters = nullptr;
+    // MT19937 jump-ahead: polynomial table and cached window states at segment starts (frame.cuh)
+    uint32_t *d_mt_polys = nullptr, *d_mt_states = nullptr;
+    uint32_t  mt_states_cap = 0, mt_states_seed = 0;
     unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
     unsigned work_slot = 0;
     // single-ray path
@@ -316,7 +319,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_slot_of_prim);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     for (auto p : a->d_frame) cudaFree(p);
-    cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work);
+    cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work); cudaFree(a->d_mt_polys); cudaFree(a->d_mt_states);
     if (a->h_pin) cudaFreeHost(a->h_pin);
     for (auto &e : a->ev) if (e) cudaEventDestroy(e);
     if (a->stream) cudaStreamDestroy(a->stream);

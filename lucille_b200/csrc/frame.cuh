@@ -219,6 +219,9 @@ compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__rest
 // One CTA owns the 624-word state in shared memory (double buffered).  new[k] depends on old[k], old[k+1] and on
 // the word 227 positions back in the NEW state, so a block regenerates in three dependent phases of <=227 lanes.
 constexpr int kMtN = 624, kMtM = 397;
+}  // namespace b200
+#include "mt_jump_table.h"
+namespace b200 {
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t far)
 {
@@ -234,22 +237,28 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// state_io: 624 words carried between launches (NULL on the first launch: seed here). Writes nblocks*624 outputs.
+// Segment generator: CTA `blockIdx.x` starts from the window states[blockIdx.x] (624 words: x_m .. x_{m+623}, only the top
+// bit of word 0 is significant) and writes its blocks of the stream.  states == NULL: one CTA, seeded here (seedMT2).
+// Segment k covers stream words [k*seg_blocks*624, ...); the last segment may be shorter (total_blocks).
 __global__ void __launch_bounds__(256)
-mt_kernel(uint32_t seed, uint32_t *__restrict__ state_io, int first, uint64_t nblocks, uint32_t *__restrict__ out)
+mt_kernel(uint32_t seed, const uint32_t *__restrict__ states, uint64_t seg_blocks, uint64_t total_blocks, uint32_t *__restrict__ out)
 {
     __shared__ uint32_t st[2][kMtN];
     const int k = threadIdx.x;
-    if (first) {
+    if (!states) {
         if (k == 0) {
             uint32_t x = seed;
             st[0][0] = x;
             for (int i = 1; i < kMtN; ++i) { x = 69069u * x; st[0][i] = x; }      // seedMT2, random.c:98-112
         }
     } else {
-        for (int i = k; i < kMtN; i += 256) st[0][i] = state_io[i];
+        for (int i = k; i < kMtN; i += 256) st[0][i] = states[(uint64_t)blockIdx.x * kMtN + i];
     }
     __syncthreads();
+    const uint64_t first_block = (uint64_t)blockIdx.x * seg_blocks;
+    if (first_block >= total_blocks) return;
+    const uint64_t nblocks = (total_blocks - first_block) < seg_blocks ? (total_blocks - first_block) : seg_blocks;
+    out += first_block * kMtN;
     int cur = 0;
     for (uint64_t b = 0; b < nblocks; ++b) {
         uint32_t *o = st[cur], *n = st[cur ^ 1];
@@ -278,7 +287,44 @@ mt_kernel(uint32_t seed, uint32_t *__restrict__ state_io, int first, uint64_t nb
         __syncthreads();
         cur ^= 1;
     }
-    if (state_io) for (int i = k; i < kMtN; i += 256) state_io[i] = st[cur][i];
+}
+
+// Jump ahead: dst = g(T) src, g = poly (x^J mod phi, tools/gen_mt_jump.py), by Horner's rule 32 coefficients at a time:
+//     r <- T^32 r  xor  sum_{j<32} g[32w+j] * T^j src            for w = 623 .. 0
+// T^j src is the source window slid by j words, so the sum is a XOR of shifted reads of the source extended by 31 words;
+// T^32 r regenerates 32 words at once (they depend only on old words).  r lives in shared memory as a ring with head h.
+// CTA b computes states[b + stride] from states[b]  (b + stride < nstates): one level of the doubling tree.
+__global__ void __launch_bounds__(256)
+mt_jump_kernel(const uint32_t *__restrict__ poly, uint32_t *__restrict__ states, uint32_t stride, uint32_t nstates)
+{
+    __shared__ uint32_t r[kMtN], ext[kMtN + 32], g[kMtN];
+    const uint32_t src = blockIdx.x, dst = blockIdx.x + stride;
+    if (dst >= nstates) return;
+    const int t = threadIdx.x;
+    for (int i = t; i < kMtN; i += 256) { ext[i] = states[(uint64_t)src * kMtN + i]; g[i] = poly[i]; r[i] = 0u; }
+    __syncthreads();
+    if (t < 31) ext[kMtN + t] = mt_twist(ext[t], ext[t + 1], ext[t + kMtM]);       // x_{624+t}: inputs are all old words
+    __syncthreads();
+    uint32_t h = 0;
+    for (int w = kMtN - 1; w >= 0; --w) {
+        if (t < 32) {                                   // r <- T^32 r
+            const uint32_t a = r[(h + t) % kMtN], b = r[(h + t + 1) % kMtN], far = r[(h + t + kMtM) % kMtN];
+            __syncwarp();
+            r[(h + t) % kMtN] = mt_twist(a, b, far);
+        }
+        h = (h + 32) % kMtN;
+        __syncthreads();
+        const uint32_t bits = g[w];
+        if (bits) {
+            for (int p = t; p < kMtN; p += 256) {
+                uint32_t acc = 0, m = bits;
+                while (m) { const int j = __ffs(m) - 1; m &= m - 1; acc ^= ext[p + j]; }
+                r[(h + p) % kMtN] ^= acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = t; i < kMtN; i += 256) states[(uint64_t)dst * kMtN + i] = r[(h + i) % kMtN];
 }
 
 __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x)
@@ -368,7 +414,8 @@ ao_kernel(const SceneView<Real> S, const FrameDev F, const uint64_t nrays, const
 
 // ---- resolve: Lo = (N - occluded)/N per hit sample, mean over sub-samples, float at row H-1-y ---------
 __global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
-                               const uint32_t *__restrict__ sample_rank, const uint32_t *__restrict__ occ, float *__restrict__ rgb)
+                               const uint32_t *__restrict__ sample_rank, const uint32_t *__restrict__ occ, float *__restrict__ rgb,
+                               const int packed)
 {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npixels) return;
@@ -383,7 +430,8 @@ __global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pi
         accum = accum + rad;                                             // render.c:805
     }
     const double px = accum * (1.0 / (double)(F.xsamples * F.ysamples)); // render.c:820
-    float *dst = rgb + 3 * ((uint64_t)(F.height - y - 1) * F.width + x); // render.c:962-964
+    // full framebuffer: row H-1-y (render.c:962-964); packed: this rank's pixels in visiting order (the NCCL send buffer)
+    float *dst = packed ? rgb + 3 * p : rgb + 3 * ((uint64_t)(F.height - y - 1) * F.width + x);
     const float f = (float)px;
     dst[0] = f; dst[1] = f; dst[2] = f;
 }
@@ -467,9 +515,49 @@ static int frame_buf(ri_b200_accel *a, int slot, uint64_t bytes, void **out)
     return 0;
 }
 
+// The whole stream in parallel: window states at every segment start come from the doubling tree of jumps
+// (log2(segments) launches, cached per seed in the accelerator), then one CTA per segment regenerates its blocks.
+static int mt_stream_launch(ri_b200_accel *a, uint32_t seed, uint32_t segments, uint64_t total_blocks, uint32_t *d_out, cudaStream_t st)
+{
+    if (segments <= 1) {
+        mt_kernel<<<1, 256, 0, st>>>(seed, nullptr, total_blocks, total_blocks, d_out);
+        LAUNCHED();
+        return 0;
+    }
+    if (segments > (1u << kMtJumpPolys)) return fail("MT19937 stream too long for the jump table (%u segments)", segments);
+    if (!a->d_mt_polys) {
+        CUDA_OK(cudaMalloc((void **)&a->d_mt_polys, sizeof(kMtJumpPoly)));
+        CUDA_OK(cudaMemcpyAsync(a->d_mt_polys, kMtJumpPoly, sizeof(kMtJumpPoly), cudaMemcpyHostToDevice, st));
+    }
+    if (a->mt_states_seed != seed || a->mt_states_cap < segments) {          // (re)build the table of window states
+        uint32_t cap = 1;
+        while (cap < segments) cap <<= 1;
+        if (a->mt_states_cap < cap) {
+            cudaFree(a->d_mt_states); a->d_mt_states = nullptr; a->mt_states_cap = 0;
+            CUDA_OK(cudaMalloc((void **)&a->d_mt_states, (size_t)cap * kMtN * sizeof(uint32_t)));
+            a->mt_states_cap = cap;
+        }
+        uint32_t w0[kMtN];
+        w0[0] = seed;
+        for (int i = 1; i < kMtN; ++i) w0[i] = 69069u * w0[i - 1];                 // seedMT2, random.c:98-112
+        CUDA_OK(cudaMemcpyAsync(a->d_mt_states, w0, sizeof(w0), cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaStreamSynchronize(st));                                        // w0 is on the stack
+        int m = 0;
+        for (uint32_t have = 1; have < a->mt_states_cap; have <<= 1, ++m) {
+            mt_jump_kernel<<<have, 256, 0, st>>>(a->d_mt_polys + (size_t)m * kMtN, a->d_mt_states, have, a->mt_states_cap);
+            LAUNCHED();
+        }
+        a->mt_states_seed = seed;
+    }
+    mt_kernel<<<segments, 256, 0, st>>>(seed, a->d_mt_states, (uint64_t)kMtSegBlocks, total_blocks, d_out);
+    LAUNCHED();
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <typename Real>
 static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_rgb, cudaStream_t st, ri_b200_frame_stats_t *stats,
-                          Real *d_dump, uint64_t dump_count)
+                          Real *d_dump, uint64_t dump_count, int packed = 0)
 {
     std::vector<uint32_t> pix;
     std::vector<double> jit;
@@ -515,7 +603,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         CUDA_OK(cudaMemcpyAsync(d_jit, jit.data(), jit.size() * 8, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
     }
-    CUDA_OK(cudaMemsetAsync(d_rgb, 0, (size_t)f.width * f.height * 3 * sizeof(float), st));
+    if (!packed) CUDA_OK(cudaMemsetAsync(d_rgb, 0, (size_t)f.width * f.height * 3 * sizeof(float), st));
     uint32_t nhits = 0;
     if (nsamples) {
         primary_kernel<Real><<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim);
@@ -543,6 +631,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     const uint64_t mt_blocks = f.rng_mode == 0 ? (2 * nao_rays + kMtN - 1) / kMtN : 0;
     if (frame_buf(a, 5, (mt_blocks * kMtN + 4) * 4, &p)) return -1;
     d_mt = (uint32_t *)p;
+    const uint32_t mt_segments = (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks);
 
     if (nhits) {
         compact_kernel<Real><<<ntiles, kScanBlock, 0, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_tiles, d_srank, d_ranks, d_rec);
@@ -553,8 +642,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
     CUDA_OK(cudaEventRecord(a->ev[2], st));
     if (mt_blocks) {
-        mt_kernel<<<1, 256, 0, st>>>(f.seed, nullptr, 1, mt_blocks, d_mt);
-        LAUNCHED();
+        if (mt_stream_launch(a, f.seed, mt_segments, mt_blocks, d_mt, st)) return -1;
     }
     CUDA_OK(cudaEventRecord(a->ev[3], st));
     if (nao_rays) {
@@ -565,7 +653,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
     CUDA_OK(cudaEventRecord(a->ev[4], st));
     if (npix) {
-        resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb);
+        resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed);
         LAUNCHED();
     }
     CUDA_OK(cudaGetLastError());
@@ -610,6 +698,31 @@ extern "C" int ri_b200_render_ao_dev(ri_b200_accel_t *a, const ri_b200_frame_t *
     return render_ao_impl<float>(a, *f, d_rgb, st, stats, nullptr, 0);
 }
 
+extern "C" int ri_b200_render_ao_tiles_dev(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *d_packed, void *stream,
+                                           ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!d_packed) return fail("null buffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
+    if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_packed, st, stats, nullptr, 0, 1);
+    return render_ao_impl<float>(a, *f, d_packed, st, stats, nullptr, 0, 1);
+}
+
+extern "C" int64_t ri_b200_frame_pixels(const ri_b200_frame_t *f, uint32_t *out, int64_t capacity)
+{
+    if (!f) return fail("null argument");
+    if (f->width < 1 || f->height < 1 || f->width > 65535 || f->height > 65535) return fail("bad frame size");
+    if (f->world < 1 || f->rank < 0 || f->rank >= f->world) return fail("bad rank/world");
+    std::vector<uint32_t> pix;
+    pixel_order(*f, pix);
+    if (!out) return (int64_t)pix.size();
+    if (capacity < (int64_t)pix.size()) return fail("capacity too small");
+    if (!pix.empty()) std::memcpy(out, pix.data(), pix.size() * sizeof(uint32_t));
+    return (int64_t)pix.size();
+}
+
 extern "C" int ri_b200_render_ao(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *rgb_out, ri_b200_frame_stats_t *stats)
 {
     if (check_frame(a, f)) return -1;
@@ -628,18 +741,27 @@ extern "C" int ri_b200_render_ao(ri_b200_accel_t *a, const ri_b200_frame_t *f, f
     return 0;
 }
 
-extern "C" int ri_b200_mt_stream(uint32_t seed, uint64_t n, uint32_t *out_u32, int device)
+extern "C" int ri_b200_mt_stream(ri_b200_accel_t *a, uint32_t seed, uint64_t n, uint32_t *out_u32, int device)
 {
     if (!out_u32) return fail("null argument");
     if (n == 0) return 0;
-    CUDA_OK(cudaSetDevice(device));
+    if (a && a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
+    CUDA_OK(cudaSetDevice(a ? a->device : device));
     const uint64_t blocks = (n + kMtN - 1) / kMtN;
     uint32_t *d = nullptr;
     CUDA_OK(cudaMalloc((void **)&d, blocks * kMtN * 4));
-    mt_kernel<<<1, 256>>>(seed, nullptr, 1, blocks, d);
-    LAUNCHED();
-    cudaError_t e = cudaMemcpy(out_u32, d, n * 4, cudaMemcpyDeviceToHost);
+    int rc = 0;
+    if (a) {                                     // parallel: jump-ahead tree + one CTA per segment
+        std::lock_guard<std::mutex> lock(a->mu);
+        rc = mt_stream_launch(a, seed, (uint32_t)((blocks + kMtSegBlocks - 1) / kMtSegBlocks), blocks, d, a->stream);
+        if (!rc && cudaStreamSynchronize(a->stream) != cudaSuccess) rc = fail("mt stream failed");
+    } else {                                     // sequential: one CTA walks the whole stream
+        mt_kernel<<<1, 256>>>(seed, nullptr, blocks, blocks, d);
+        LAUNCHED();
+    }
+    cudaError_t e = rc ? cudaSuccess : cudaMemcpy(out_u32, d, n * 4, cudaMemcpyDeviceToHost);
     cudaFree(d);
+    if (rc) return rc;
     if (e != cudaSuccess) return fail("mt stream copy failed: %s", cudaGetErrorString(e));
     return 0;
 }

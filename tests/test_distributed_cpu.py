@@ -1,0 +1,79 @@
+"""CPU: the multi-GPU sharding and gather logic with world_size 2 over gloo (no GPU needed): tile ownership is a
+partition of the image in the reference's visiting order, and gathering packed slabs reassembles the frame."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as ol
+from lucille_b200 import accel, distributed
+
+
+def _frame(w, h, rank=0, world=1):
+    return accel.make_frame(np.eye(4).reshape(16), 2.0, True, w, h, 2, 2, 16, rng_mode=1, rank=rank, world=world)
+
+
+@pytest.mark.parametrize("w,h,world", [(640, 480, 1), (640, 480, 8), (97, 61, 3), (33, 200, 2), (31, 17, 4)])
+def test_tiles_partition_the_image(w, h, world):
+    seen = np.zeros((h, w), dtype=np.int32)
+    for r in range(world):
+        pix = accel.frame_pixels(_frame(w, h, r, world))
+        seen[(pix >> 16).astype(np.int64), (pix & 0xFFFF).astype(np.int64)] += 1
+    assert np.all(seen == 1)
+    assert sum(distributed.shard_counts(_frame(w, h), world)) == w * h
+
+
+def test_single_rank_order_is_the_reference_bucket_order(oracle):
+    """world == 1: spiral buckets, row-major pixels inside a bucket -- checked against the oracle's bucket list
+    (itself bit-pinned to the reference renderer through the C1 frames)."""
+    w, h = 640, 480
+    pix = accel.frame_pixels(_frame(w, h))
+    want = []
+    for bx, by, bw, bh in oracle.bucket_list(w, h, 32):
+        ys, xs = np.mgrid[by:by + bh, bx:bx + bw]
+        want.append((xs.ravel().astype(np.uint32) | (ys.ravel().astype(np.uint32) << 16)))
+    assert np.array_equal(pix, np.concatenate(want))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, w, h, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = _frame(w, h, rank, world)
+    pix = accel.frame_pixels(f)
+    x, y = (pix & 0xFFFF).astype(np.float32), (pix >> 16).astype(np.float32)
+    slab = torch.from_numpy(np.stack([x, y, x * 1000 + y], axis=1))         # a fake renderer: colour = f(x, y)
+    out = distributed.gather_frame(slab, f, rank, world)
+    if rank == 0:
+        q.put(out)
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_over_gloo_world2():
+    w, h, world = 100, 70, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, w, h, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rgb = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ys, xs = np.mgrid[0:h, 0:w]
+    want = np.stack([xs, ys, xs * 1000 + ys], axis=-1).astype(np.float32)[::-1]   # row H-1-y
+    assert np.array_equal(rgb, want)

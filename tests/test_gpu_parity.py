@@ -126,6 +126,35 @@ def test_device_mt19937_stream(golden_dir):
     g = np.load(os.path.join(golden_dir, "mt19937_seed4357.npz"))
     s = accel.mt_stream(1000008)
     assert np.array_equal(s[:2000], g["first"]) and np.array_equal(s[-8:], g["at_1e6"])
+    # the frame path: GF(2) jump-ahead to every segment start, one CTA per segment -- 5.3 segments, two seeds
+    a = accel.Accel.bind().build(scenes.triangle_soup(10, 1), accel.PREC_F32)
+    orc = ol.Oracle()
+    for seed in (4357, 12345):
+        n = 624 * 1024 * 5 + 200000
+        assert np.array_equal(accel.mt_stream(n, seed=seed, accel=a), orc.mt_stream_u32(n, seed=seed))
+
+
+def test_tiles_render_and_reassemble(golden_dir):
+    """The multi-GPU form on one GPU: three ranks' packed tile slabs, scattered by frame_pixels(), equal the full frame."""
+    _need_gpu()
+    import torch
+    from lucille_b200 import distributed
+    sc = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    cam = sc["cam"]
+    a = accel.Accel.bind().build(sc["tris"], accel.PREC_F32)
+    mk = lambda r, w: accel.make_frame(cam[:16], cam[16], bool(cam[17]), 200, 150, 2, 2, 16, rng_mode=1, seed=3, rank=r, world=w,
+                                       precision=accel.PREC_F32)
+    full, _ = a.render_ao(mk(0, 1))
+    lists, slabs = [], []
+    for r in range(3):
+        f = mk(r, 3)
+        pix = accel.frame_pixels(f)
+        slab = torch.zeros((len(pix), 3), dtype=torch.float32, device="cuda")
+        a.render_ao_tiles_dev(f, slab)
+        torch.cuda.synchronize()
+        lists.append(pix)
+        slabs.append(slab.cpu().numpy())
+    assert np.array_equal(distributed.scatter_tiles(200, 150, lists, slabs), full)
 
 
 @pytest.mark.parametrize("fname,w,h,ps,gather", [
