@@ -181,7 +181,7 @@ static int stack_capacity(const ri_b200_accel *a)
 
 template <typename Real, bool ANYHIT, bool COUNT>
 static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typename RayIO<Real>::Hit *d_hits, uint8_t *d_occ,
-                        unsigned long long *d_counters, cudaStream_t st)
+                        unsigned long long *d_counters, cudaStream_t st, uint32_t *d_counts = nullptr, uint32_t rays_per_count = 1)
 {
     if (n == 0) return 0;
     const int cap = stack_capacity(a);
@@ -209,7 +209,8 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             unsigned int *ctr = a->d_work + (a->work_slot++ & 63u);
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
-                                           d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr, ctr);
+                                           d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
+                                           d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr);
             LAUNCHED();
             CUDA_OK(cudaGetLastError());
         }

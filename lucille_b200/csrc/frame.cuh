@@ -412,6 +412,70 @@ ao_kernel(const SceneView<Real> S, const FrameDev F, const uint64_t nrays, const
     }
 }
 
+// ---- K4 (wavefront form): write the occlusion rays of hit samples [rank0, rank0 + nrays/N) as a ray batch; the batch is
+// then traced by the persistent any-hit kernel, which accumulates straight into the per-sample counters.
+template <typename Real>
+__global__ void __launch_bounds__(kBlock)
+ao_gen_kernel(const FrameDev F, const uint64_t nrays, const uint32_t rank0, const Real *__restrict__ records,
+              const uint32_t *__restrict__ rank_sample, const uint32_t *__restrict__ pixels,
+              const uint32_t *__restrict__ mt_stream, Real *__restrict__ rays_out)
+{
+    const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (gid >= nrays) return;
+    const uint32_t N = (uint32_t)F.nao;
+    const uint32_t rank = rank0 + (uint32_t)(gid / N);
+    const uint32_t k = (uint32_t)(gid - (uint64_t)(rank - rank0) * N);
+    const uint32_t j = k / (uint32_t)F.ntheta, i = k - j * (uint32_t)F.ntheta;
+    const Real *rec = records + 12 * (uint64_t)rank;
+    double r0, r1;
+    if (F.rng_mode == 0) {
+        const uint64_t base = (uint64_t)2 * N * rank + 2 * k;               // z0 then z1, ambientocclusion.c:91-92
+        r0 = (double)mt_stream[base] * 2.3283064365386963e-10;               // random.c:244
+        r1 = (double)mt_stream[base + 1] * 2.3283064365386963e-10;
+    } else {
+        const uint32_t s = rank_sample[rank];
+        const uint64_t p = s / (uint32_t)F.spp;
+        const uint32_t sub = s - (uint32_t)p * (uint32_t)F.spp;
+        const uint32_t pix = pixels[p];
+        const uint64_t sid = ((uint64_t)(pix >> 16) * (uint64_t)F.width + (pix & 0xffffu)) * (uint64_t)F.spp + sub;
+        const uint64_t idx = (sid * N + k) * 2;
+        r0 = (double)(splitmix64_dev((uint64_t)F.seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+        r1 = (double)(splitmix64_dev((uint64_t)F.seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+    }
+    Real dir[3];
+    if (sizeof(Real) == 8) {                                                 // ambientocclusion.c:91-117, double
+        const double z0 = ((double)i + r0) / (double)F.ntheta;
+        const double z1 = ((double)j + r1) / (double)F.nphi;
+        const double ct = sqrt(z0);
+        const double phi = 2.0 * 3.14159265358979323846 * z1;
+        const double lx = cos(phi) * ct, ly = sin(phi) * ct, lz = sqrt(1.0 - ct * ct);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            dir[q] = (Real)(lx * (double)rec[3 + q] + ly * (double)rec[6 + q] + lz * (double)rec[9 + q]);
+    } else {
+        const float z0 = ((float)i + (float)r0) / (float)F.ntheta;
+        const float z1 = ((float)j + (float)r1) / (float)F.nphi;
+        const float ct = sqrtf(z0);
+        const float phi = 6.28318530717958647692f * z1;
+        float sp, cp;
+        sincosf(phi, &sp, &cp);
+        const float lx = cp * ct, ly = sp * ct, lz = sqrtf(1.0f - ct * ct);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            dir[q] = (Real)(lx * (float)rec[3 + q] + ly * (float)rec[6 + q] + lz * (float)rec[9 + q]);
+    }
+    if (sizeof(Real) == 8) {
+        double2 *o = reinterpret_cast<double2 *>(rays_out) + 3 * gid;
+        o[0] = make_double2((double)rec[0], (double)rec[1]);
+        o[1] = make_double2((double)rec[2], (double)dir[0]);
+        o[2] = make_double2((double)dir[1], (double)dir[2]);
+    } else {
+        float4 *o = reinterpret_cast<float4 *>(rays_out) + 2 * gid;
+        o[0] = make_float4((float)rec[0], (float)rec[1], (float)rec[2], 0.0f);
+        o[1] = make_float4((float)dir[0], (float)dir[1], (float)dir[2], 1.0e38f);
+    }
+}
+
 // ---- resolve: Lo = (N - occluded)/N per hit sample, mean over sub-samples, float at row H-1-y ---------
 __global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
                                const uint32_t *__restrict__ sample_rank, const uint32_t *__restrict__ occ, float *__restrict__ rgb,
@@ -645,11 +709,30 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         if (mt_stream_launch(a, f.seed, mt_segments, mt_blocks, d_mt, st)) return -1;
     }
     CUDA_OK(cudaEventRecord(a->ev[3], st));
-    if (nao_rays) {
+    // tiny scenes (a few hundred triangles, rays that end after a handful of steps): the fused one-ray-per-thread kernel
+    // wins (C1: 11.5 ms vs 17.9 ms); everything else goes through the persistent traverser (1M-triangle soup: 167 ms vs 278 ms)
+    static const char *force = getenv("B200_FUSED_AO");
+    const bool fused_ao = force ? atoi(force) != 0 : (a->tree.ntris < 4096);
+    if (nao_rays && fused_ao) {                   // one lane per ray, generation fused with a one-ray-per-thread traversal
         const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
         if (blocks > 0x7fffffffull) return fail("too many occlusion rays in one frame pass");
         ao_kernel<Real><<<(unsigned)blocks, kBlock, smem, st>>>(S, F, nao_rays, 0u, d_rec, d_ranks, d_pix, d_mt, d_occ, d_dump, dump_count);
         LAUNCHED();
+    } else if (nao_rays) {                        // wavefront: ray batches of <= 2^24 rays through the persistent traverser
+        const uint32_t chunk_samples = (1u << 24) / (uint32_t)N ? (1u << 24) / (uint32_t)N : 1u;
+        const uint64_t ray_words = sizeof(Real) == 8 ? 6 : 8;
+        const uint64_t buf_rays = (uint64_t)(nhits < chunk_samples ? nhits : chunk_samples) * (uint64_t)N;
+        if (frame_buf(a, 7, buf_rays * ray_words * sizeof(Real), &p)) return -1;
+        Real *d_rays = (Real *)p;
+        for (uint32_t r0 = 0; r0 < nhits; r0 += chunk_samples) {
+            const uint32_t ns = (nhits - r0) < chunk_samples ? (nhits - r0) : chunk_samples;
+            const uint64_t nr = (uint64_t)ns * (uint64_t)N;
+            ao_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(F, nr, r0, d_rec, d_ranks, d_pix, d_mt, d_rays);
+            LAUNCHED();
+            if (d_dump && r0 == 0 && dump_count)
+                CUDA_OK(cudaMemcpyAsync(d_dump, d_rays, (dump_count < nr ? dump_count : nr) * ray_words * sizeof(Real), cudaMemcpyDeviceToDevice, st));
+            if (launch_trace<Real, true, false>(a, d_rays, nr, nullptr, nullptr, nullptr, st, d_occ + r0, (uint32_t)N)) return -1;
+        }
     }
     CUDA_OK(cudaEventRecord(a->ev[4], st));
     if (npix) {

@@ -7,6 +7,8 @@
 //   node step every lane that holds an inner-node word tests the two child boxes of ITS node (2 x LDG.256 per fp32 node)
 //             and descends / pushes / pops
 //   leaf step every lane that holds a leaf word tests the next PAIR of triangles of ITS leaf (3 x LDG.256 per fp32 pair)
+// Occlusion results go out as one byte per ray, or -- for the AO transport -- are accumulated with atomicAdd into one
+// counter per `rays_per_count` consecutive rays (the per-sample "occlusion += 1.0" of ambientocclusion.c:125-129).
 // Which of node/leaf step runs next is decided by a warp vote (__ballot_sync + __popc): the kind more lanes are waiting
 // for.  A lane's own sequence of box tests, triangle tests, pushes and pops -- and therefore its arithmetic, visiting
 // order and tie rules -- is exactly that of trace_ray() (trace.cuh) / bvh_traverse (bvh.c:1092-1188); only the
@@ -43,6 +45,7 @@ template <typename Real, bool ANYHIT>
 __global__ void __launch_bounds__(kBlock)
 trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const uint32_t n, const uint32_t chunk,
                         typename RayIO<Real>::Hit *__restrict__ hits, uint8_t *__restrict__ occ,
+                        uint32_t *__restrict__ counts, const uint32_t rays_per_count,
                         unsigned int *__restrict__ work_counter)
 {
     using P = Prec<Real>;
@@ -77,7 +80,8 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
 #define B200_RETIRE()                                                                           \
     do {                                                                                        \
         const bool hit__ = best_t < P::inf();                                                   \
-        if (ANYHIT) occ[idx] = hit__ ? 1 : 0;                                                   \
+        if (ANYHIT && counts) { if (hit__) atomicAdd(&counts[idx / rays_per_count], 1u); }      \
+        else if (ANYHIT) occ[idx] = hit__ ? 1 : 0;                                              \
         else RayIO<Real>::store(hits, idx, hit__, best_t, best_u, best_v, best_prim);           \
         mode = 0u;                                                                              \
     } while (0)

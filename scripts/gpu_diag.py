@@ -41,3 +41,13 @@ for prec, mode in ((accel.PREC_F64, 0), (accel.PREC_F64, 1), (accel.PREC_F32, 1)
     c1.render_ao(fr)
     rgb, s = c1.render_ao(fr)
     print(f"C1 prec={prec} rng={mode}: total {s.ms_total:.2f} ms (primary {s.ms_primary:.2f}, rng {s.ms_rng:.2f}, ao {s.ms_ao:.2f}, resolve {s.ms_resolve:.2f}) rays {s.nrays} -> {s.nrays/s.ms_total/1e3:.1f} Mrays/s")
+# synthetic frame (C5-like, scaled): 1M-triangle soup, 1024x1024, 2x2 sub-samples, 8x8 AO rays, counter RNG, fp32
+c2w = np.eye(4); c2w[3, :3] = (0.5, 0.5, -2.0)
+import math, os
+for label, env in (("wavefront", "0"), ("fused", "1")):
+    os.environ["B200_FUSED_AO"] = env
+for prec in (accel.PREC_F32, accel.PREC_F64):
+    fr = accel.make_frame(c2w.reshape(16), 1.0 / math.tan(math.radians(40.0) / 2), False, 1024, 1024, 2, 2, 64, rng_mode=1, seed=5, precision=prec)
+    a.render_ao(fr)
+    rgb, s = a.render_ao(fr)
+    print(f"soup frame prec={prec}: total {s.ms_total:.2f} ms (primary {s.ms_primary:.2f}, ao {s.ms_ao:.2f}) rays {s.nrays} hits {s.nhits_primary} -> {s.nrays/s.ms_total/1e3:.1f} Mrays/s  mean {rgb.mean():.4f}")
