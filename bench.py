@@ -39,6 +39,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+class quiet_stdout:
+    """The compiled reference logs with printf ("[lucille] info ..."): send fd 1 to stderr while it runs so that this
+    process prints exactly ONE line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -116,7 +136,8 @@ def run_reference(args, rank, world):
     rays8 = scenes.ao_rays(P[:sample_pts], n[:sample_pts], NTHETA, NPHI, scenes.SEED_C3)
     rays6 = scenes.rays_f32_to_f64(rays8)
     if ol.reference_available():
-        kind, scene = "reference", ol.Reference().build(tris)
+        with quiet_stdout():
+            kind, scene = "reference", ol.Reference().build(tris)
         step = lambda: scene.intersect(rays6, nthreads=cores, want_hits=False)[1]   # noqa: E731
         threads = cores
     else:
@@ -151,7 +172,8 @@ def cpu_baseline(tris, rays8_sample):
     cores = os.cpu_count() or 1
     rays6 = scenes.rays_f32_to_f64(rays8_sample)
     if ol.reference_available():
-        scene = ol.Reference().build(tris)
+        with quiet_stdout():
+            scene = ol.Reference().build(tris)
         scene.intersect(rays6[:20000], nthreads=cores, want_hits=False)
         sec = min(scene.intersect(rays6, nthreads=cores, want_hits=False)[1] for _ in range(2))
         kind, threads = "reference", cores
@@ -223,8 +245,8 @@ def main():
     # counters of the reference traversal order on this exact batch (outside the timed region)
     cnt = a.count(rays_np, anyhit=True)
     cnt["nrays_total"] = nrays
-    cnt_closest = a.count(rays_np[: nrays // 16], anyhit=False)
-    cnt_closest["nrays_total"] = nrays // 16
+    cnt_closest = a.count(rays_np, anyhit=False)
+    cnt_closest["nrays_total"] = nrays
     b_ray, I, T = algorithmic_bytes_per_ray(cnt, anyhit=True)
     b_ray_c, Ic, Tc = algorithmic_bytes_per_ray(cnt_closest, anyhit=False)
 
@@ -292,6 +314,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes of ONE launch of this kernel on this batch (ncu --set full)
+        if os.path.exists(tp) and npoints == NPOINTS:
+            with open(tp) as f:
+                traffic = json.load(f).get("occluded_f32_c3_bytes_per_launch")
         per_gpu_rays_s = nrays * args.steps / (ms * 1e-3)
         achieved = per_gpu_rays_s * b_ray / 1e9
         out = {
@@ -306,7 +333,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": world * nrays * 32, "d2h_bytes_per_step": world * nrays,
                     "ms_per_step": e2e_ms / esteps, "api": "ri_b200_occluded_batch_f32 (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "bytes_per_ray": b_ray, "inner_visits_per_ray": I, "tri_tests_per_ray": T,
                          "closest_hit": {"bytes_per_ray": b_ray_c, "inner_visits_per_ray": Ic, "tri_tests_per_ray": Tc,
                                          "achieved": nrays * max(3, args.steps // 2) / (ms_c * 1e-3) * b_ray_c / 1e9,

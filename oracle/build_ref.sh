@@ -67,6 +67,16 @@ gcc -O2 -g -std=gnu99 -fPIC -w -D__64bit__ -D__x86__ -DLINUX -DWITH_PTHREAD -DWI
     -lm -ldl -lpthread -o "$OUT/libluciref_stat.so"
 gcc -O2 -g -std=gnu99 -w "$DRV/oracle_rib_main.c" -L"$OUT" -Wl,-rpath,'$ORIGIN' -lluciref -lm -ldl -lpthread -o "$OUT/oracle_rib"
 
+# drop-in proof: the same front end + the UNMODIFIED reference renderer, with ri_accel_bind() interposed so that accel
+# method 2 selects the GPU accelerator (integration/ri_b200_binding.c -> lucille_b200/libb200accel.so).  Needs the product
+# library to exist; skipped otherwise.
+if [ -f "$HERE/../lucille_b200/libb200accel.so" ]; then
+    gcc -O2 -g -std=gnu99 -w -D__64bit__ -D__x86__ -DLINUX -DWITH_PTHREAD -DWITH_SSE -DLREF_WITH_B200 $INC -I"$HERE/../include" \
+        "$DRV/oracle_rib_main.c" "$DRV/ref_shim.c" "$DRV/rib_reader.c" "$HERE/../integration/ri_b200_binding.c" \
+        -Wl,--wrap=ri_accel_bind -Wl,--whole-archive "$OUT/libluciref_core.a" -Wl,--no-whole-archive \
+        -L"$HERE/../lucille_b200" -lb200accel -Wl,-rpath,'$ORIGIN/../../lucille_b200' -lm -ldl -lpthread -o "$OUT/lsh_b200"
+fi
+
 # measurement inputs (BASELINE.json configs[0], configs[3]); not sources
 cp -f "$REF/examples/ambient_occlusion/ambient_occlusion.rib" "$OUT/scenes/"
 rm -rf "$OUT/scenes/plane_sphere"; cp -r "$REF/examples/plane_sphere" "$OUT/scenes/plane_sphere"

@@ -6,7 +6,7 @@
  * Stands in for `lsh` (src/lsh/main.c), whose flex/bison front end cannot be generated here.
  *
  *   oracle_rib scene.rib [--nthreads N] [--width W --height H] [--pixelsamples P]
- *                        [--gather G] [--out frame.bin] [--scene scene.bin]
+ *                        [--gather G] [--out frame.bin] [--scene scene.bin] [--accel bvh|b200]
  *
  * frame.bin : "LFRM" u32 w, u32 h, u32 0, f64 seconds("Render frame"), u64 nrays(stat.nrays), f32 rgb[h][w][3]
  * scene.bin : "LSCN" u32 0, u64 ntris, f64 cam[27], f64 tri[ntris][9], u32 geom[ntris]
@@ -16,6 +16,7 @@
 #include <string.h>
 #include <stdint.h>
 
+extern void     lref_set_accel_method(int m);
 extern int      lref_render_rib(const char *path, int nthreads, int width, int height, int pixelsamples, int gather);
 extern int      lref_frame_width(void);
 extern int      lref_frame_height(void);
@@ -37,6 +38,10 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--height") && i + 1 < argc) height = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--pixelsamples") && i + 1 < argc) ps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gather") && i + 1 < argc) gather = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--accel") && i + 1 < argc) {     /* bvh (default) | b200: Option "raytrace" "accel_method" */
+            const char *m = argv[++i];
+            lref_set_accel_method(!strcmp(m, "b200") ? 2 : 1);
+        }
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
         else if (!strcmp(argv[i], "--scene") && i + 1 < argc) scene = argv[++i];
         else rib = argv[i];

@@ -325,7 +325,7 @@ int lref_beam_visibility(void *h, const double *org, const double *dirs)
 /* ------------------------------------------------------------------ frame level */
 
 typedef struct {
-    int      nthreads, width, height, pixelsamples, gather_nsamples;
+    int      nthreads, width, height, pixelsamples, gather_nsamples, accel_method;
     float   *rgb;            /* [h][w][3], rows as the display driver receives them (y already flipped) */
     int      w, h;
     double   render_seconds;
@@ -349,6 +349,7 @@ static void world_begin_cb(void)
     }
     if (g_frame.nthreads > 0) opt->nthreads = g_frame.nthreads;
     if (g_frame.gather_nsamples > 0) opt->gather_nsamples = g_frame.gather_nsamples;
+    if (g_frame.accel_method >= 0) opt->accel_method = g_frame.accel_method;      /* what option.c:453-461 sets from the RIB */
     if (g_frame.width > 0 && g_frame.height > 0) {
         opt->camera->horizontal_resolution = g_frame.width;
         opt->camera->vertical_resolution   = g_frame.height;
@@ -425,6 +426,9 @@ static int dd_close(void)
 }
 
 /* One frame per process (the reference keeps one-shot statics, e.g. spiral.c:17 g_n). */
+static int g_accel_method = -1;
+void lref_set_accel_method(int m) { g_accel_method = m; }
+
 int lref_render_rib(const char *path, int nthreads, int width, int height, int pixelsamples, int gather_nsamples)
 {
     char buf[2048];
@@ -434,6 +438,7 @@ int lref_render_rib(const char *path, int nthreads, int width, int height, int p
     memset(&g_frame, 0, sizeof(g_frame));
     g_frame.nthreads = nthreads; g_frame.width = width; g_frame.height = height;
     g_frame.pixelsamples = pixelsamples; g_frame.gather_nsamples = gather_nsamples;
+    g_frame.accel_method = g_accel_method;
 
     ri_parallel_init(&argc, &argv);                     /* lsh/main.c:119 */
     RiBegin(RI_NULL);                                   /* lsh/main.c:153 */

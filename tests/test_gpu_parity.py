@@ -234,3 +234,25 @@ def test_full_size_config2_properties():
     want = orc.intersect_f32(rays[rows])
     for f in ("prim", "t", "u", "v"):
         assert np.array_equal(hits[f][rows], want[f]), f
+
+
+def test_drop_in_through_the_reference_renderer(tmp_path):
+    """The real boundary: the UNMODIFIED reference renderer (Ri layer, pixel loop, AO transport, MT19937) with accel
+    method RI_ACCEL_B200 bound by integration/ri_b200_binding.c -- every ri_raytrace() is answered by the GPU through
+    ri_b200_intersect1() -- produces the same float framebuffer, bit for bit, as the reference's own CPU BVH."""
+    _need_gpu()
+    lsh_b200 = os.path.join(ol.REF_DIR, "lsh_b200")
+    rib = os.path.join(ol.REF_DIR, "scenes", "ambient_occlusion.rib")
+    if not (os.path.exists(lsh_b200) and os.path.exists(rib)):
+        pytest.skip("oracle/_ref/lsh_b200 not built (needs /root/reference at build time)")
+    import subprocess
+    args = ["--nthreads", "1", "--width", "64", "--height", "48", "--pixelsamples", "2", "--gather", "16"]
+    out_gpu, out_cpu = str(tmp_path / "gpu.bin"), str(tmp_path / "cpu.bin")
+    subprocess.run([lsh_b200, rib, "--accel", "b200", "--out", out_gpu] + args, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=600)
+    subprocess.run([lsh_b200, rib, "--accel", "bvh", "--out", out_cpu] + args, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=600)
+    g, _, ng = ol.read_frame(out_gpu)
+    c, _, nc = ol.read_frame(out_cpu)
+    assert ng == nc and ng > 50000
+    assert np.array_equal(g, c) and g.max() > 0.5
