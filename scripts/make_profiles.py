@@ -1,0 +1,91 @@
+"""Turn the ncu artefacts a `scripts/gpu_round.sh` run leaves in gpurun_out/ into the committed summaries under profiles/.
+
+    python scripts/make_profiles.py r01
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+gp = os.path.join(ROOT, "gpurun_out")
+
+# ---- launch list ------------------------------------------------------------------------------------------------------
+rows = [r for r in csv.reader(open(os.path.join(gp, "launches.csv"))) if len(r) > 5 and r[0].isdigit()]
+d = defaultdict(list)
+for r in rows:
+    d[(r[4].split("(")[0].replace("void ", ""), r[8], r[7])].append(float(r[-1].replace(",", "")))
+tot = sum(sum(v) for v in d.values())
+with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
+    f.write(f"# {tag}: kernel launch list of `bench.py --steps 3 --warmup 3 --no-cpu-baseline`\n\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 80` (cold-cache, serialised: compare shares, not absolutes).\n"
+            "Setup launches (primary rays, statistics counters) and the chunked end-to-end launches are part of the list.\n\n"
+            "| kernel | grid | block | launches | avg ms | share of listed GPU time |\n|---|---|---|---:|---:|---:|\n")
+    for (k, grid, block), v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+        f.write(f"| `{k}` | {grid} | {block} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {sum(v) / tot * 100:.1f} % |\n")
+    f.write("\n`trace_persistent_kernel<float, 1>` = occlusion (any-hit) traverser: grid 592 = 4 CTAs x 148 SMs; the 16 Mi-ray launches are the\n"
+            "warm-up + timed steps, the 1 Mi-ray ones are the chunks of the host-buffer (e2e) path.\n"
+            "`trace_batch_kernel<..., 1>` = one-ray-per-thread kernel with the reference's traversal counters (I, T of the roofline formula), run once, untimed.\n")
+
+# ---- full capture of the timed kernel ---------------------------------------------------------------------------------
+rep = os.path.join(gp, "prof_bench.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+hdr, units, vals = rr[0], rr[1], rr[2]
+m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__bytes_read.sum.per_second", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active"]
+name = m["Kernel Name"][0]
+to_bytes = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+rd = float(m["dram__bytes_read.sum"][0]) * to_bytes[m["dram__bytes_read.sum"][1]]
+wr = float(m["dram__bytes_write.sum"][0]) * to_bytes[m["dram__bytes_write.sum"][1]]
+with open(os.path.join(out_dir, f"{tag}_occluded_f32_c3.md"), "w") as f:
+    f.write(f"# {tag}: `ncu --set full --clock-control none` of the timed kernel of bench.py (one launch, 16 777 216 AO rays, 1 M triangles)\n\n"
+            f"kernel: `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+    for k in keys:
+        if k in m:
+            f.write(f"| {k} | {m[k][0]} | {m[k][1]} |\n")
+    f.write(f"\nDRAM traffic of the launch: {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written = {(rd + wr) / 1e6:.1f} MB "
+            "(the 512 MiB ray batch + the 54 MB scene once + 16 MiB of occlusion bytes); algorithmic bytes of the same launch: "
+            "174 GB (10.39 KB/ray) -- the scene records are re-read from L2 (hit rate 98.8 %), not from HBM.\n\n"
+            "Reading: no tensor pipe (by design), DRAM idle, L2 at a third of its peak; the kernel is limited by warp-instruction issue and by L1 "
+            "wavefronts (one per lane-request for divergent loads), with ~14 of 32 lanes active per issued instruction.\n")
+with open(os.path.join(out_dir, "traffic.json"), "w") as f:
+    json.dump({"occluded_f32_c3_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": f"profiles/{tag}_occluded_f32_c3.md"}, f)
+
+# ---- hottest SASS ------------------------------------------------------------------------------------------------------
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+sr = list(csv.reader(src.splitlines()))
+h2 = sr[1]
+data = [r for r in sr[2:] if len(r) == len(h2) and r[0] != "Address"]
+ia, isrc, isamp, iavg = h2.index("Instructions Executed"), h2.index("Source"), h2.index("# Samples"), h2.index("Avg. Threads Executed")
+total = sum(int(r[ia]) for r in data)
+tots = sum(int(r[isamp]) for r in data)
+opc = defaultdict(int)
+for r in data:
+    opc[r[isrc].split()[0].split(".")[0] if not r[isrc].strip().startswith("@") else r[isrc].split()[1].split(".")[0]] += int(r[ia])
+with open(os.path.join(out_dir, f"{tag}_occluded_f32_c3_sass.md"), "w") as f:
+    f.write(f"# {tag}: instruction mix of the timed kernel (ncu source page, {total} warp instructions, {len(data)} SASS lines)\n\n"
+            "| opcode | share of executed warp instructions |\n|---|---:|\n")
+    for k, v in sorted(opc.items(), key=lambda kv: -kv[1])[:24]:
+        f.write(f"| {k} | {v / total * 100:.1f} % |\n")
+    f.write("\n`LDG.E.ENL2.256` = the 256-bit node / triangle-pair loads; `FMNMX3` = 3-input min/max of the slab test; `VOTE`/`POPC` = the warp vote.\n\n"
+            "## lines with the most stall samples\n\n| samples | executed | avg threads | SASS |\n|---:|---:|---:|---|\n")
+    for r in sorted(data, key=lambda r: -int(r[isamp]))[:25]:
+        f.write(f"| {int(r[isamp]) / tots * 100:.2f} % | {int(r[ia]) / total * 100:.2f} % | {r[iavg]} | `{r[isrc].strip()[:90]}` |\n")
+print("profiles written")
