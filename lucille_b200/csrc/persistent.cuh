@@ -5,17 +5,21 @@
 //             atomicAdd per chunk and hands them to idle lanes by ballot rank, so a lane whose ray terminates (any-hit
 //             found, or the stack ran dry) is replaced at once instead of idling until the slowest ray of its warp ends
 //   node step every lane that holds an inner-node word tests the two child boxes of ITS node (2 x LDG.256 per fp32 node)
-//             and descends / pushes / pops
-//   leaf step every lane that holds a leaf word tests the next PAIR of triangles of ITS leaf (3 x LDG.256 per fp32 pair)
-// Occlusion results go out as one byte per ray, or -- for the AO transport -- are accumulated with atomicAdd into one
-// counter per `rays_per_count` consecutive rays (the per-sample "occlusion += 1.0" of ambientocclusion.c:125-129).
+//             and descends / pushes / pops -- written branch-free (selects + predicated stack accesses)
+//   leaf step every lane that holds a leaf word tests the next PAIR of triangles of ITS leaf (3 x LDG.256 per fp32 pair),
+//             branch-free as well; progress through the leaf lives in the leaf word itself (slot += 2, count -= 2)
 // Which of node/leaf step runs next is decided by a warp vote (__ballot_sync + __popc): the kind more lanes are waiting
 // for.  A lane's own sequence of box tests, triangle tests, pushes and pops -- and therefore its arithmetic, visiting
 // order and tie rules -- is exactly that of trace_ray() (trace.cuh) / bvh_traverse (bvh.c:1092-1188); only the
 // interleaving between lanes changes, so results are bit-identical to the one-ray-per-thread kernel.
+// Occlusion results go out as one byte per ray, or -- for the AO transport -- are accumulated with atomicAdd into one
+// counter per `rays_per_count` consecutive rays (the per-sample "occlusion += 1.0" of ambientocclusion.c:125-129).
 #pragma once
 
 namespace b200 {
+
+constexpr uint32_t kIdle = kDoneWord;                 // lane holds no ray (bit 31 clear, never a valid node index)
+constexpr uint32_t kSlotMask = (1u << kLeafShift) - 1u;
 
 template <typename Real> struct LeafStep;
 
@@ -26,8 +30,8 @@ template <> struct LeafStep<float> {                 // two slots per step
     {
         TriRegs<float> a, b;
         load_tri_pair(tris + slot, a, b);
-        if (tri_test<float>(a, org, dir, tl, ul, vl)) tprim = a.prim;
-        if (left > 1u) { if (tri_test<float>(b, org, dir, tl, ul, vl)) tprim = b.prim; }
+        tri_test_bf<float>(a, org, dir, true, tl, ul, vl, tprim);
+        tri_test_bf<float>(b, org, dir, left > 1u, tl, ul, vl, tprim);
     }
 };
 template <> struct LeafStep<double> {                // one slot per step
@@ -37,7 +41,7 @@ template <> struct LeafStep<double> {                // one slot per step
     {
         TriRegs<double> a;
         load_tri_wide(tris + slot, a);
-        if (tri_test<double>(a, org, dir, tl, ul, vl)) tprim = a.prim;
+        tri_test_bf<double>(a, org, dir, true, tl, ul, vl, tprim);
     }
 };
 
@@ -57,38 +61,23 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
     uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
     bool exhausted = false;                      // warp-uniform
 
-    // per-lane ray state.  mode: 0 idle, 1 holds an inner-node word in `cur`, 2 inside a leaf
-    uint32_t mode = 0, idx = 0, cur = 0, sp = 0, best_prim = 0xffffffffu;
-    uint32_t leaf_slot = 0, leaf_left = 0, tprim = 0xffffffffu;
+    // per-lane ray state.  cur: kIdle | inner-node index | leaf word (flag | (triangles left - 1) << 27 | next slot)
+    uint32_t cur = kIdle, idx = 0, sp = 0, best_prim = 0xffffffffu, tprim = 0xffffffffu;
     Real org[3], dir[3], inv[3], best_t = P::inf(), best_u = Real(0), best_v = Real(0);
     Real tl = P::inf(), ul = Real(0), vl = Real(0);
     bool sx = false, sy = false, sz = false;
     org[0] = org[1] = org[2] = dir[0] = dir[1] = dir[2] = inv[0] = inv[1] = inv[2] = Real(0);
 
-    // enter `word`: inner node -> mode 1, leaf -> mode 2 with a fresh leaf-local closest t (bvh.c:833-836)
-#define B200_ENTER(word)                                                                        \
-    do {                                                                                        \
-        cur = (word);                                                                           \
-        if (cur & kLeafFlag) {                                                                  \
-            mode = 2u; leaf_slot = cur & ((1u << kLeafShift) - 1u);                             \
-            leaf_left = ((cur >> kLeafShift) & 15u) + 1u;                                       \
-            tl = P::inf(); ul = Real(0); vl = Real(0); tprim = 0xffffffffu;                     \
-        } else mode = 1u;                                                                       \
-    } while (0)
-
-    // retire this lane's ray: write the result, go idle
-#define B200_RETIRE()                                                                           \
-    do {                                                                                        \
-        const bool hit__ = best_t < P::inf();                                                   \
-        if (ANYHIT && counts) { if (hit__) atomicAdd(&counts[idx / rays_per_count], 1u); }      \
-        else if (ANYHIT) occ[idx] = hit__ ? 1 : 0;                                              \
-        else RayIO<Real>::store(hits, idx, hit__, best_t, best_u, best_v, best_prim);           \
-        mode = 0u;                                                                              \
-    } while (0)
+    auto retire = [&]() {                         // write the result of this lane's ray
+        const bool hit = best_t < P::inf();       // bvh.c:1187
+        if (ANYHIT && counts) { if (hit) atomicAdd(&counts[idx / rays_per_count], 1u); }
+        else if (ANYHIT) occ[idx] = hit ? 1 : 0;
+        else RayIO<Real>::store(hits, idx, hit, best_t, best_u, best_v, best_prim);
+    };
 
     for (;;) {
         // ------------------------------------------------------------------ fetch
-        unsigned idle = __ballot_sync(0xffffffffu, mode == 0u);
+        unsigned idle = __ballot_sync(0xffffffffu, cur == kIdle);
         while (idle && !exhausted) {
             if (chunk_next >= chunk_end) {
                 uint32_t base = 0;
@@ -102,10 +91,11 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
             const unsigned n_idle = __popc(idle);
             const unsigned take = n_idle < avail ? n_idle : avail;
             const unsigned rank = __popc(idle & lt_mask);
-            if (mode == 0u && rank < take) {
+            if (cur == kIdle && rank < take) {
                 idx = chunk_next + rank;
                 RayIO<Real>::load(rays, idx, org, dir);
                 best_t = P::inf(); best_u = Real(0); best_v = Real(0); best_prim = 0xffffffffu;
+                tl = P::inf(); ul = Real(0); vl = Real(0); tprim = 0xffffffffu;
                 sx = dir[0] < Real(0); sy = dir[1] < Real(0); sz = dir[2] < Real(0);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)      // bvh.c:473-497
@@ -114,68 +104,65 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
                 const bool in_scene = (S.root_word != kDoneWord) &&
                     slab<Real>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
                 sp = 0;
-                if (in_scene) B200_ENTER(S.root_word);
-                else B200_RETIRE();              // bvh.c:446 / 522-526: miss without traversal
+                if (in_scene) cur = S.root_word;
+                else retire();                   // bvh.c:446 / 522-526: miss without traversal
             }
             chunk_next += take;
-            idle = __ballot_sync(0xffffffffu, mode == 0u);
+            idle = __ballot_sync(0xffffffffu, cur == kIdle);
         }
         if (idle == 0xffffffffu) break;          // nothing in flight and nothing left to fetch
 
         // ------------------------------------------------------------------ traverse: vote, step, repeat
         for (;;) {
-            const unsigned want_node = __ballot_sync(0xffffffffu, mode == 1u);
-            const unsigned want_leaf = __ballot_sync(0xffffffffu, mode == 2u);
+            const bool in_leaf = (cur & kLeafFlag) != 0u;
+            const bool in_node = !in_leaf && (cur != kIdle);
+            const unsigned want_node = __ballot_sync(0xffffffffu, in_node);
+            const unsigned want_leaf = __ballot_sync(0xffffffffu, in_leaf);
             if ((want_node | want_leaf) == 0u) break;
             if (!exhausted && (want_node | want_leaf) != 0xffffffffu) break;     // a lane idles and rays remain: refill
 
             if (__popc(want_node) >= __popc(want_leaf)) {
-                if (mode == 1u) {                // ---- node step: bvh.c:1153-1179
+                if (in_node) {                   // ---- node step: bvh.c:1153-1179
                     NodeRegs<Real> nd;
                     load_node_wide(S.nodes + cur, nd);
                     const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
                     const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
-                    if (h0 && h1) {
-                        const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);
-                        stk[sp * kBlock] = order ? nd.c0 : nd.c1;
-                        ++sp;
-                        B200_ENTER(order ? nd.c1 : nd.c0);
-                    } else if (h0) {
-                        B200_ENTER(nd.c0);
-                    } else if (h1) {
-                        B200_ENTER(nd.c1);
-                    } else if (sp == 0) {
-                        B200_RETIRE();
-                    } else {
-                        --sp;
-                        B200_ENTER(stk[sp * kBlock]);
-                    }
+                    const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);     // near child = child[sign[axis0]]
+                    const bool both = h0 && h1, none = !h0 && !h1;
+                    const bool pop = none && (sp != 0u);
+                    if (both) stk[sp * kBlock] = order ? nd.c0 : nd.c1;
+                    const uint32_t popped = pop ? stk[(sp - 1u) * kBlock] : kIdle;
+                    sp = sp + (both ? 1u : 0u) - (pop ? 1u : 0u);
+                    const uint32_t one = h0 ? nd.c0 : nd.c1;
+                    const uint32_t next = both ? (order ? nd.c1 : nd.c0) : (none ? popped : one);
+                    if (next == kIdle) retire();                                  // stack ran dry
+                    if (next & kLeafFlag) { tl = P::inf(); ul = Real(0); vl = Real(0); tprim = 0xffffffffu; }   // bvh.c:833-836
+                    cur = next;
                 }
             } else {
-                if (mode == 2u) {                // ---- leaf step: bvh.c:838-861
-                    LeafStep<Real>::run(S.tris, leaf_slot, leaf_left, org, dir, tl, ul, vl, tprim);
-                    leaf_slot += LeafStep<Real>::kPerStep;
+                if (in_leaf) {                   // ---- leaf step: bvh.c:838-861
+                    const uint32_t left = ((cur >> kLeafShift) & 15u) + 1u;
+                    LeafStep<Real>::run(S.tris, cur & kSlotMask, left, org, dir, tl, ul, vl, tprim);
                     // occlusion query: the first accepted triangle already decides the answer -- the rest of the leaf
                     // could only lower the leaf-local t, and the commit test of bvh.c:850 is tl < 1e38 here
                     const bool decided = ANYHIT && (tl < P::inf());
-                    if (leaf_left > LeafStep<Real>::kPerStep && !decided) {
-                        leaf_left -= LeafStep<Real>::kPerStep;
+                    if (left > LeafStep<Real>::kPerStep && !decided) {
+                        cur += LeafStep<Real>::kPerStep - (LeafStep<Real>::kPerStep << kLeafShift);
                     } else {                     // leaf finished: commit (bvh.c:850), then pop or retire
-                        bool done = false;
-                        if (tprim != 0xffffffffu && (tl < best_t)) {
-                            best_t = tl; best_u = ul; best_v = vl; best_prim = tprim;
-                            if (ANYHIT) done = true;
-                        }
-                        if (!done && sp == 0) done = true;
-                        if (done) B200_RETIRE();
-                        else { --sp; B200_ENTER(stk[sp * kBlock]); }
+                        const bool commit = (tprim != 0xffffffffu) && (tl < best_t);
+                        best_t = commit ? tl : best_t; best_u = commit ? ul : best_u; best_v = commit ? vl : best_v;
+                        best_prim = commit ? tprim : best_prim;
+                        const bool done = (ANYHIT && commit) || (sp == 0u);
+                        const uint32_t popped = done ? kIdle : stk[(sp - 1u) * kBlock];
+                        sp -= done ? 0u : 1u;
+                        if (done) retire();
+                        tl = P::inf(); ul = Real(0); vl = Real(0); tprim = 0xffffffffu;
+                        cur = popped;
                     }
                 }
             }
         }
     }
-#undef B200_ENTER
-#undef B200_RETIRE
 }
 
 }  // namespace b200

@@ -220,6 +220,32 @@ __device__ __forceinline__ bool tri_test(const TriRegs<Real> &tr, const Real org
     return true;
 }
 
+// Branch-free form of the same test for the persistent kernel: every lane computes the whole expression tree (in SIMT the
+// warp pays for it as soon as one lane needs it) and the acceptance window becomes one predicate.  The NEGATED comparisons
+// are the reference's own (`if ((u < 0) || (u > 1)) return 0;` ...), so NaNs fall the same way.  `valid` masks the filler
+// slot of an odd leaf.  Returns the updated leaf-local (t, u, v, prim) through the references.
+template <typename Real>
+__device__ __forceinline__ void tri_test_bf(const TriRegs<Real> &tr, const Real org[3], const Real dir[3], const bool valid,
+                                            Real &t_io, Real &u_io, Real &v_io, uint32_t &prim_io)
+{
+    const Real px = dir[1] * tr.e2[2] - dir[2] * tr.e2[1];
+    const Real py = dir[2] * tr.e2[0] - dir[0] * tr.e2[2];
+    const Real pz = dir[0] * tr.e2[1] - dir[1] * tr.e2[0];
+    const Real a  = tr.e1[0] * px + tr.e1[1] * py + tr.e1[2] * pz;
+    const Real inva = Real(1) / a;
+    const Real sx = org[0] - tr.v0[0], sy = org[1] - tr.v0[1], sz = org[2] - tr.v0[2];
+    const Real qx = sy * tr.e1[2] - sz * tr.e1[1];
+    const Real qy = sz * tr.e1[0] - sx * tr.e1[2];
+    const Real qz = sx * tr.e1[1] - sy * tr.e1[0];
+    const Real u = (sx * px + sy * py + sz * pz) * inva;
+    const Real v = (qx * dir[0] + qy * dir[1] + qz * dir[2]) * inva;
+    const Real t = (tr.e2[0] * qx + tr.e2[1] * qy + tr.e2[2] * qz) * inva;
+    const bool ok = valid && (Prec<Real>::rabs(a) > Prec<Real>::eps())
+                    && !(u < Real(0)) && !(u > Real(1)) && !(v < Real(0)) && !((u + v) > Real(1))
+                    && !(t < Real(0)) && !(t > t_io);
+    t_io = ok ? t : t_io; u_io = ok ? u : u_io; v_io = ok ? v : v_io; prim_io = ok ? tr.prim : prim_io;
+}
+
 // One ray through the tree.  `stk` points at this lane's column of the shared stack, entries are
 // `stride` words apart.  Returns hit flag; on hit fills t,u,v,prim (post-build triangle position).
 template <typename Real, bool ANYHIT, bool COUNT>
