@@ -101,6 +101,13 @@ int         ri_b200_device_count(void);
  * empty accelerator (bvh.c:311-315).  Returns NULL on failure. */
 ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris, uint32_t precisions, int device);
 
+/* optional per-corner vertex normals, [ntris][3][3] doubles in the same (input) triangle order as tri_xyz: what
+ * ri_geom_t.normals holds behind the index list (polygon.c:677-733).  With them the shading normal of a hit is
+ * Ns = (1-u-v) n0 + u n1 + v n2 (ri_lerp_vector, base/geometric.c:40-62; intersection_state.c:152-180), not normalised, and
+ * the AO transport samples about Ns; Ng stays geometric.  A triangle whose nine components are all zero has no normals
+ * (its geom's `normals` is NULL).  NULL removes them. */
+int ri_b200_set_normals(ri_b200_accel_t *accel, const double *tri_normals);
+
 /* ---- replaces accel_free_func / ri_bvh_free (accel.h:27-28, bvh.c:381-387); frees host and device memory */
 void ri_b200_free(ri_b200_accel_t *accel);
 
@@ -162,6 +169,25 @@ int ri_b200_render_ao_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, 
 int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *d_packed, void *stream,
                                     ri_b200_frame_stats_t *stats);
 int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
+
+/* ---- path-trace transport (src/transport/pathtrace.c:131-537; NOT in the reference build): the sketch's control
+ * flow with builder-stated inputs -- Lambert kd, constant environment Le, counter-based RNG keyed by (pixel, sample, draw),
+ * deterministic sin/cos.  fp64 records.  rgb_out: HOST [height][width][3], row H-1-y (pathtrace.c:183). */
+typedef struct {
+    double  c2w[16];
+    double  flength;
+    int32_t is_rh;
+    int32_t width, height;
+    int32_t spp;                  /* ri_option_t.pt_nsamples (option.c:142, 551-556) */
+    int32_t max_vertices;         /* MAX_PATH_VERTICES 10 (pathtrace.c:66) */
+    uint32_t seed;
+    double  kd, Le;
+    int32_t rank, world;          /* tile sharding as in ri_b200_frame_t */
+    int32_t bucket_size;
+} ri_b200_path_frame_t;
+int ri_b200_render_pathtrace(ri_b200_accel_t *accel, const ri_b200_path_frame_t *frame, float *rgb_out, ri_b200_frame_stats_t *stats);
+int ri_b200_render_pathtrace_tiles_dev(ri_b200_accel_t *accel, const ri_b200_path_frame_t *frame, float *d_packed, void *stream,
+                                       ri_b200_frame_stats_t *stats);
 
 /* MT19937 stream of randomMT2() generated on the device (random.c:98-112,211-247); HOST output, for tests.
  * accel == NULL: one CTA walks the stream on `device`; accel != NULL: the frame path -- window states at segment starts

@@ -46,7 +46,8 @@ void *ri_b200_accel_build(const void *data)
     b200_binding_t *b = (b200_binding_t *)ri_mem_alloc(sizeof(b200_binding_t));
     ri_list_t *itr;
     uint64_t n = 0, idx = 0;
-    double *xyz;
+    double *xyz, *nrm;
+    int any_normals = 0;
     unsigned int i;
     int k, c;
 
@@ -55,6 +56,7 @@ void *ri_b200_accel_build(const void *data)
         n += ((ri_geom_t *)itr->data)->nindices / 3;
     b->ntris = n;
     xyz          = (double *)malloc(sizeof(double) * 9 * (n ? n : 1));
+    nrm          = (double *)calloc(9 * (n ? n : 1), sizeof(double));
     b->tri_geom  = (ri_geom_t **)malloc(sizeof(ri_geom_t *) * (n ? n : 1));
     b->tri_index = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
     b->orig      = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
@@ -63,7 +65,10 @@ void *ri_b200_accel_build(const void *data)
         for (i = 0; i < geom->nindices / 3; i++) {
             for (c = 0; c < 3; c++)
                 for (k = 0; k < 3; k++)
+                {
                     xyz[9 * idx + 3 * c + k] = geom->positions[geom->indices[3 * i + c]][k];
+                    if (geom->normals) { nrm[9 * idx + 3 * c + k] = geom->normals[geom->indices[3 * i + c]][k]; any_normals = 1; }
+                }
             b->tri_geom[idx]  = geom;
             b->tri_index[idx] = 3 * i;
             idx++;
@@ -72,6 +77,8 @@ void *ri_b200_accel_build(const void *data)
     ri_log(LOG_INFO, "(B200  ) Building accelerator on the GPU side: %llu triangles", (unsigned long long)n);
     b->dev = ri_b200_build(xyz, n, RI_B200_PREC_F64 | RI_B200_PREC_F32, 0);
     free(xyz);
+    if (b->dev && any_normals) ri_b200_set_normals(b->dev, nrm);     /* used by the batched frame path */
+    free(nrm);
     if (!b->dev) {                       /* no error channel in the reference: log and abort (memory.c:87-97 style) */
         ri_log(LOG_FATAL, "(B200  ) %s", ri_b200_last_error());
         abort();

@@ -71,6 +71,13 @@ class Frame(C.Structure):
                 ("seed", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32), ("precision", C.c_int32)]
 
 
+class PathFrame(C.Structure):
+    """ri_b200_path_frame_t: one path-traced frame (row P of the scope table)."""
+    _fields_ = [("c2w", C.c_double * 16), ("flength", C.c_double), ("is_rh", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("spp", C.c_int32), ("max_vertices", C.c_int32), ("seed", C.c_uint32), ("kd", C.c_double), ("Le", C.c_double),
+                ("rank", C.c_int32), ("world", C.c_int32), ("bucket_size", C.c_int32)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("nrays_primary", C.c_uint64), ("nrays_ao", C.c_uint64), ("nhits_primary", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_primary", C.c_double), ("ms_rng", C.c_double), ("ms_ao", C.c_double),
@@ -88,6 +95,7 @@ ABI = [
     ("ri_b200_device_count", _I, []),
     ("ri_b200_build", _P, [_P, _U64, _U32, _I]),
     ("ri_b200_free", None, [_P]),
+    ("ri_b200_set_normals", _I, [_P, _P]),
     ("ri_b200_info", _I, [_P, _P]),
     ("ri_b200_export_nodes", C.c_int64, [_P, _P, C.c_int64]),
     ("ri_b200_triorder", _I, [_P, _P]),
@@ -110,6 +118,8 @@ ABI = [
     ("ri_b200_render_ao_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_ao_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
+    ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
+    ("ri_b200_render_pathtrace_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_mt_stream", _I, [_P, _U32, _U64, _P, _I]),
 ]
 
@@ -194,6 +204,16 @@ class Accel:
             raise B200Error(last_error())
         self.data = h
         self.ntris = len(tris)
+        return self
+
+    def set_normals(self, tri_normals) -> "Accel":
+        """Per-corner vertex normals [ntris,3,3] in input order (ri_geom_t.normals); None removes them."""
+        if tri_normals is None:
+            _check(self.lib.ri_b200_set_normals(self._h(), None))
+        else:
+            n = np.ascontiguousarray(tri_normals, dtype=np.float64).reshape(-1, 9)
+            assert len(n) == self.ntris
+            _check(self.lib.ri_b200_set_normals(self._h(), _ptr(n)))
         return self
 
     # -- accel->free -----------------------------------------------------------------------------
@@ -320,6 +340,13 @@ class Accel:
         _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
         return rgb, stats
 
+    def render_pathtrace(self, frame: "PathFrame"):
+        """One path-traced frame -> (rgb [h,w,3] float32 on the host, FrameStats with the ray count)."""
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_pathtrace(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
+        return rgb, stats
+
     def render_ao_tiles_dev(self, frame: Frame, d_packed, stream: Optional[int] = None, want_stats: bool = True):
         """This rank's pixels only, packed [npixels,3] in visiting order, left in device memory."""
         stats = FrameStats()
@@ -342,6 +369,18 @@ def frame_pixels(frame: Frame) -> np.ndarray:
     if n:
         _check(lib.ri_b200_frame_pixels(C.byref(frame), _ptr(out), n))
     return out
+
+
+def make_path_frame(c2w, flength: float, is_rh: bool, width: int, height: int, spp: int = 4, max_vertices: int = 10,
+                    seed: int = 1, kd: float = 1.0, Le: float = 1.0, rank: int = 0, world: int = 1, bucket_size: int = 32) -> PathFrame:
+    f = PathFrame()
+    c = np.asarray(c2w, dtype=np.float64).reshape(16)
+    for i in range(16):
+        f.c2w[i] = float(c[i])
+    f.flength, f.is_rh, f.width, f.height = float(flength), int(bool(is_rh)), int(width), int(height)
+    f.spp, f.max_vertices, f.seed, f.kd, f.Le = int(spp), int(max_vertices), int(seed), float(kd), float(Le)
+    f.rank, f.world, f.bucket_size = int(rank), int(world), int(bucket_size)
+    return f
 
 
 def make_frame(c2w, flength: float, is_rh: bool, width: int, height: int, xsamples: int, ysamples: int,

@@ -58,6 +58,7 @@ struct ri_b200_accel {
     Node32 *d_nodes32 = nullptr; Tri32 *d_tris32 = nullptr;
     Node64 *d_nodes64 = nullptr; Tri64 *d_tris64 = nullptr;
     uint32_t *d_slot_of_prim = nullptr;
+    double *d_nrm64 = nullptr; float *d_nrm32 = nullptr;     // optional vertex normals, [prim][9]
     uint64_t device_bytes = 0;
     double   upload_seconds = 0.0;
     // staging for host-buffer batches (double buffered)
@@ -82,7 +83,7 @@ template <typename Real> static SceneView<Real> make_view(const ri_b200_accel *a
 template <> SceneView<float> make_view<float>(const ri_b200_accel *a)
 {
     SceneView<float> v;
-    v.nodes = a->d_nodes32; v.tris = a->d_tris32; v.slot_of_prim = a->d_slot_of_prim;
+    v.nodes = a->d_nodes32; v.tris = a->d_tris32; v.slot_of_prim = a->d_slot_of_prim; v.normals = a->d_nrm32;
     for (int k = 0; k < 3; ++k) { v.smin[k] = a->flat.smin32[k]; v.smax[k] = a->flat.smax32[k]; }
     v.root_word = a->flat.root_word; v.top_count = a->flat.top_count;
     return v;
@@ -90,7 +91,7 @@ template <> SceneView<float> make_view<float>(const ri_b200_accel *a)
 template <> SceneView<double> make_view<double>(const ri_b200_accel *a)
 {
     SceneView<double> v;
-    v.nodes = a->d_nodes64; v.tris = a->d_tris64; v.slot_of_prim = a->d_slot_of_prim;
+    v.nodes = a->d_nodes64; v.tris = a->d_tris64; v.slot_of_prim = a->d_slot_of_prim; v.normals = a->d_nrm64;
     for (int k = 0; k < 3; ++k) { v.smin[k] = a->tree.bmin[k]; v.smax[k] = a->tree.bmax[k]; }
     v.root_word = a->flat.root_word; v.top_count = a->flat.top_count;
     return v;
@@ -317,7 +318,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
-    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_slot_of_prim);
+    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     for (auto p : a->d_frame) cudaFree(p);
     cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work); cudaFree(a->d_mt_polys); cudaFree(a->d_mt_states);
@@ -372,6 +373,33 @@ extern "C" int64_t ri_b200_export_flat(const ri_b200_accel_t *a, void *nodes32, 
     if (tris64 && !f.tris64.empty()) std::memcpy(tris64, f.tris64.data(), f.tris64.size() * sizeof(Tri64));
     if (header_out) { header_out[0] = f.root_word; header_out[1] = f.ninner; header_out[2] = f.top_count; header_out[3] = (uint32_t)f.nslots; }
     return (int64_t)f.ninner;
+}
+
+extern "C" int ri_b200_set_normals(ri_b200_accel_t *a, const double *tri_normals)
+{
+    if (!a) return fail("null argument");
+    if (a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); a->d_nrm64 = nullptr; a->d_nrm32 = nullptr;
+    if (!tri_normals || a->tree.empty) return 0;
+    const size_t n = (size_t)a->tree.ntris;
+    std::vector<double> h64(9 * n);
+    std::vector<float> h32(9 * n);
+    for (size_t p = 0; p < n; ++p)
+        for (int k = 0; k < 9; ++k) {
+            const double v = tri_normals[9 * (size_t)a->tree.orig[p] + k];
+            h64[9 * p + k] = v; h32[9 * p + k] = (float)v;
+        }
+    if (a->precisions & RI_B200_PREC_F64) {
+        CUDA_OK(cudaMalloc((void **)&a->d_nrm64, h64.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(a->d_nrm64, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (a->precisions & RI_B200_PREC_F32) {
+        CUDA_OK(cudaMalloc((void **)&a->d_nrm32, h32.size() * sizeof(float)));
+        CUDA_OK(cudaMemcpy(a->d_nrm32, h32.data(), h32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
 }
 
 extern "C" void *ri_b200_host_alloc(uint64_t bytes)
@@ -543,19 +571,35 @@ __device__ __forceinline__ void ortho_basis(double b0[3], double b1[3], const do
     normalize3(b1);
 }
 
+// normals: optional [prim][9]; a triangle with nine zero components has none (its geom's `normals` is NULL) -> Ns = Ng
 __device__ __forceinline__ void state_from_hit(const Tri64 *tris, const uint32_t *slot_of_prim, const double org[3], const double dir[3],
-                                               double t, uint32_t prim, ri_b200_state_f64 &s)
+                                               double t, uint32_t prim, ri_b200_state_f64 &s,
+                                               const double *normals = nullptr, double bu = 0.0, double bv = 0.0)
 {
     TriRegs<double> tr;
     load_tri(tris + slot_of_prim[prim], tr);
     for (int k = 0; k < 3; ++k) s.P[k] = org[k] + dir[k] * t;
     cross3(s.Ng, tr.e1, tr.e2);                                   // (v1-v0) x (v2-v0), geometric.c:20-33
     normalize3(s.Ng);
-    for (int k = 0; k < 3; ++k) s.Ns[k] = s.Ng[k];
+    bool has_n = false;
+    double n[9];
+    if (normals) {
+        for (int k = 0; k < 9; ++k) { n[k] = normals[9 * (size_t)prim + k]; has_n = has_n || (n[k] != 0.0); }
+    }
+    if (has_n) {                                                  // ri_lerp_vector, geometric.c:40-62 (not normalised)
+        const double w0 = 1.0 - bu - bv;
+        for (int k = 0; k < 3; ++k) {
+            const double a = n[k] * w0, b = n[3 + k] * bu, c = n[6 + k] * bv;
+            s.Ns[k] = (a + b) + c;
+        }
+    } else {
+        for (int k = 0; k < 3; ++k) s.Ns[k] = s.Ng[k];
+    }
     ortho_basis(s.tangent, s.binormal, s.Ng);
 }
 
-__global__ void state_kernel(const Tri64 *__restrict__ tris, const uint32_t *__restrict__ slot_of_prim, const double *__restrict__ rays,
+__global__ void state_kernel(const Tri64 *__restrict__ tris, const uint32_t *__restrict__ slot_of_prim, const double *__restrict__ normals,
+                             const double *__restrict__ rays,
                              const ri_b200_hit_f64 *__restrict__ hits, uint64_t n, ri_b200_state_f64 *__restrict__ out)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,7 +609,7 @@ __global__ void state_kernel(const Tri64 *__restrict__ tris, const uint32_t *__r
     if (h.hit) {
         double org[3], dir[3];
         RayIO<double>::load(rays, i, org, dir);
-        state_from_hit(tris, slot_of_prim, org, dir, h.t, h.prim, s);
+        state_from_hit(tris, slot_of_prim, org, dir, h.t, h.prim, s, normals, h.u, h.v);
     } else {
         memset(&s, 0, sizeof(s));
     }
@@ -586,7 +630,7 @@ extern "C" int ri_b200_state_batch_f64(ri_b200_accel_t *a, const double *rays, c
         CUDA_OK(cudaMalloc((void **)&d_out, n * sizeof(ri_b200_state_f64)));
         CUDA_OK(cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, a->stream));
         CUDA_OK(cudaMemcpyAsync(d_hits, hits, n * sizeof(ri_b200_hit_f64), cudaMemcpyHostToDevice, a->stream));
-        state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->d_tris64, a->d_slot_of_prim, d_rays, d_hits, n, d_out);
+        state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->d_tris64, a->d_slot_of_prim, a->d_nrm64, d_rays, d_hits, n, d_out);
         LAUNCHED();
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaMemcpyAsync(out, d_out, n * sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));
@@ -615,7 +659,7 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
     CUDA_OK(cudaMemcpyAsync(d_ray, h, 48, cudaMemcpyHostToDevice, a->stream));
     if (launch_trace<double, false, false>(a, d_ray, 1, d_hit, nullptr, nullptr, a->stream)) return -1;
     if (state) {
-        state_kernel<<<1, 32, 0, a->stream>>>(a->d_tris64, a->d_slot_of_prim, d_ray, d_hit, 1, d_state);
+        state_kernel<<<1, 32, 0, a->stream>>>(a->d_tris64, a->d_slot_of_prim, a->d_nrm64, d_ray, d_hit, 1, d_state);
         LAUNCHED();
     }
     CUDA_OK(cudaMemcpyAsync((char *)a->h_pin + 64, d + 64, 64 + sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));
@@ -626,3 +670,4 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
 }
 
 #include "frame.cuh"
+#include "pathtrace.cuh"

@@ -51,7 +51,7 @@ __device__ __forceinline__ void camera_ray(const FrameDev &F, int px, int py, do
 template <typename Real>
 __global__ void __launch_bounds__(kBlock)
 primary_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter,
-               const uint64_t nsamples, Real *__restrict__ hit_t, uint32_t *__restrict__ hit_prim)
+               const uint64_t nsamples, Real *__restrict__ hit_t, uint32_t *__restrict__ hit_prim, Real *__restrict__ hit_uv)
 {
     extern __shared__ uint32_t s_stack[];
     const uint64_t s = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -67,6 +67,7 @@ primary_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__rest
     const bool hit = trace_ray<Real, false, false>(S, o, d, s_stack + threadIdx.x, kBlock, t, u, v, prim, nullptr);
     hit_t[s] = hit ? t : Prec<Real>::inf();
     hit_prim[s] = hit ? prim : 0xffffffffu;
+    if (hit_uv) { hit_uv[2 * s] = u; hit_uv[2 * s + 1] = v; }    // only needed when the scene carries vertex normals
 }
 
 // ---- exclusive scan of hit flags (three small kernels; 2048 flags per block) -------------------
@@ -132,10 +133,10 @@ template <typename Real> struct StateMath;      // hit state in the accelerator'
 
 template <> struct StateMath<double> {
     static __device__ __forceinline__ void frame(const SceneView<double> &S, const double org[3], const double dir[3], double t,
-                                                 uint32_t prim, double rec[12])
+                                                 double bu, double bv, uint32_t prim, double rec[12])
     {
         ri_b200_state_f64 s;
-        state_from_hit(S.tris, S.slot_of_prim, org, dir, t, prim, s);
+        state_from_hit(S.tris, S.slot_of_prim, org, dir, t, prim, s, S.normals, bu, bv);
         const double eps = 1.0e-6;                                      // ambientocclusion.c:56,73-75
         double b0[3], b1[3];
         ortho_basis(b0, b1, s.Ns);                                      // ambientocclusion.c:65
@@ -158,13 +159,22 @@ template <> struct StateMath<float> {
         d[0] = a[1] * b[2] - a[2] * b[1]; d[1] = a[2] * b[0] - a[0] * b[2]; d[2] = a[0] * b[1] - a[1] * b[0];
     }
     static __device__ __forceinline__ void frame(const SceneView<float> &S, const float org[3], const float dir[3], float t,
-                                                 uint32_t prim, float rec[12])
+                                                 float bu, float bv, uint32_t prim, float rec[12])
     {
         TriRegs<float> tr;
         load_tri(S.tris + S.slot_of_prim[prim], tr);
         float n[3], b0[3], b1[3], e[3] = {0.f, 0.f, 0.f};
         crs(n, tr.e1, tr.e2);
         nrm(n);
+        if (S.normals) {                                                // interpolated shading normal (geometric.c:40-62)
+            float vn[9];
+            bool has_n = false;
+            for (int k = 0; k < 9; ++k) { vn[k] = S.normals[9 * (size_t)prim + k]; has_n = has_n || (vn[k] != 0.0f); }
+            if (has_n) {
+                const float w0 = 1.0f - bu - bv;
+                for (int k = 0; k < 3; ++k) n[k] = (vn[k] * w0 + vn[3 + k] * bu) + vn[6 + k] * bv;
+            }
+        }
         int i;
         for (i = 0; i < 3; ++i) if (n[i] < 0.6f && n[i] > -0.6f) break;
         if (i >= 3) i = 0;
@@ -183,7 +193,7 @@ template <typename Real>
 __global__ void __launch_bounds__(kScanBlock)
 compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter,
                const uint64_t nsamples, const Real *__restrict__ hit_t, const uint32_t *__restrict__ hit_prim,
-               const uint32_t *__restrict__ tile_offsets, uint32_t *__restrict__ sample_rank, uint32_t *__restrict__ rank_sample,
+               const Real *__restrict__ hit_uv, const uint32_t *__restrict__ tile_offsets, uint32_t *__restrict__ sample_rank, uint32_t *__restrict__ rank_sample,
                Real *__restrict__ records)
 {
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
@@ -207,7 +217,7 @@ compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__rest
         camera_ray(F, (int)(pix & 0xffffu), (int)(pix >> 16), jitter[2 * sub], jitter[2 * sub + 1], org, dir);
         Real o[3] = {(Real)org[0], (Real)org[1], (Real)org[2]}, d[3] = {(Real)dir[0], (Real)dir[1], (Real)dir[2]};
         Real rec[12];
-        StateMath<Real>::frame(S, o, d, hit_t[s], hit_prim[s], rec);
+        StateMath<Real>::frame(S, o, d, hit_t[s], hit_uv ? hit_uv[2 * s] : Real(0), hit_uv ? hit_uv[2 * s + 1] : Real(0), hit_prim[s], rec);
         Real *dst = records + 12 * (uint64_t)rank;
 #pragma unroll
         for (int q = 0; q < 12; ++q) dst[q] = rec[q];
@@ -655,8 +665,10 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     Real *d_t;
     if (frame_buf(a, 0, (npix + 1) * 4 + jit.size() * 8 + 64, &p)) return -1;
     d_jit = (double *)p; d_pix = (uint32_t *)(d_jit + jit.size());
-    if (frame_buf(a, 1, (nsamples + 1) * sizeof(Real), &p)) return -1;
+    const bool with_normals = make_view<Real>(a).normals != nullptr;
+    if (frame_buf(a, 1, (nsamples + 1) * sizeof(Real) * (with_normals ? 3 : 1), &p)) return -1;
     d_t = (Real *)p;
+    Real *d_uv = with_normals ? d_t + nsamples : nullptr;
     if (frame_buf(a, 2, (nsamples + 1) * 4 * 3 + ((uint64_t)ntiles + 4) * 4, &p)) return -1;
     d_prim = (uint32_t *)p; d_srank = d_prim + nsamples; d_ranks = d_srank + nsamples; d_tiles = d_ranks + nsamples;
     uint32_t *d_total = d_tiles + ntiles;
@@ -670,7 +682,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     if (!packed) CUDA_OK(cudaMemsetAsync(d_rgb, 0, (size_t)f.width * f.height * 3 * sizeof(float), st));
     uint32_t nhits = 0;
     if (nsamples) {
-        primary_kernel<Real><<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim);
+        primary_kernel<Real><<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_uv);
         LAUNCHED();
         scan_tile_sums<<<ntiles, kScanBlock, 0, st>>>(d_prim, nsamples, d_tiles);
         LAUNCHED();
@@ -698,7 +710,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     const uint32_t mt_segments = (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks);
 
     if (nhits) {
-        compact_kernel<Real><<<ntiles, kScanBlock, 0, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_tiles, d_srank, d_ranks, d_rec);
+        compact_kernel<Real><<<ntiles, kScanBlock, 0, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_uv, d_tiles, d_srank, d_ranks, d_rec);
         LAUNCHED();
         CUDA_OK(cudaMemsetAsync(d_occ, 0, (uint64_t)nhits * 4, st));
     } else if (nsamples) {
@@ -711,7 +723,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     CUDA_OK(cudaEventRecord(a->ev[3], st));
     // tiny scenes (a few hundred triangles, rays that end after a handful of steps): the fused one-ray-per-thread kernel
     // wins (C1: 11.5 ms vs 17.9 ms); everything else goes through the persistent traverser (1M-triangle soup: 167 ms vs 278 ms)
-    static const char *force = getenv("B200_FUSED_AO");
+    const char *force = getenv("B200_FUSED_AO_TEST");         // test hook: exercise both paths on the same scene
     const bool fused_ao = force ? atoi(force) != 0 : (a->tree.ntris < 4096);
     if (nao_rays && fused_ao) {                   // one lane per ray, generation fused with a one-ray-per-thread traversal
         const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;

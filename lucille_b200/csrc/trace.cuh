@@ -41,6 +41,7 @@ template <typename Real> struct SceneView {
     const typename Prec<Real>::Node *nodes;
     const typename Prec<Real>::Tri  *tris;
     const uint32_t *slot_of_prim;      // hit id (post-build triangle position) -> triangle slot
+    const Real     *normals;           // optional [prim][9] vertex normals n0 n1 n2 (NULL: Ns = Ng)
     Real     smin[3], smax[3];
     uint32_t root_word;
     uint32_t top_count;

@@ -29,6 +29,7 @@ struct orc_tree {
     int64_t     nnodes, cap;
     int         max_depth;
     double     *tri_xyz;       /* post-build order, [ntris][9] v0 v1 v2 */
+    double     *tri_nrm;       /* post-build order, [ntris][9] n0 n1 n2, or NULL */
     uint32_t   *orig;          /* post-build position -> input triangle */
     /* per-precision views, built once after construction */
     double     *lbox64, *rbox64, *tri64;
@@ -302,10 +303,19 @@ orc_tree *orc_build(const double *tri_xyz, uint64_t ntris)
 void orc_free(orc_tree *T)
 {
     if (!T) return;
-    free(T->nodes); free(T->tri_xyz); free(T->orig);
+    free(T->nodes); free(T->tri_xyz); free(T->orig); free(T->tri_nrm);
     free(T->lbox64); free(T->rbox64); free(T->tri64);
     free(T->lbox32); free(T->rbox32); free(T->tri32);
     free(T);
+}
+
+void orc_set_normals(orc_tree *T, const double *tri_normals)
+{
+    uint64_t p;
+    free(T->tri_nrm); T->tri_nrm = NULL;
+    if (!tri_normals || T->empty) return;
+    T->tri_nrm = (double *)malloc(sizeof(double) * 9 * T->ntris);
+    for (p = 0; p < T->ntris; p++) memcpy(T->tri_nrm + 9 * p, tri_normals + 9 * (size_t)T->orig[p], sizeof(double) * 9);
 }
 
 int     orc_is_empty(const orc_tree *T)  { return T->empty; }
@@ -416,7 +426,8 @@ void orc_occluded_f32(const orc_tree *T, const float *rays, uint64_t n, uint8_t 
 
 /* intersection_state.c:99-248 for geometry carrying only "P": Ns = Ng, tangent/binormal from ri_ortho_basis(Ng).
  * Ng = normalize((v1-v0) x (v2-v0)), base/geometric.c:20-33.  No face-forwarding. */
-static void state_build(const orc_tree *T, const double org[3], const double dir[3], double t, uint32_t prim, orc_state_f64 *s)
+static void state_build_uv(const orc_tree *T, const double org[3], const double dir[3], double t, double bu, double bv, uint32_t prim,
+                           orc_state_f64 *s)
 {
     const double *v = T->tri_xyz + 9 * (size_t)prim;
     double v01[3], v02[3], basis[3][3];
@@ -425,16 +436,37 @@ static void state_build(const orc_tree *T, const double org[3], const double dir
     for (k = 0; k < 3; k++) { v01[k] = v[3 + k] - v[k]; v02[k] = v[6 + k] - v[k]; }
     cross_f64(s->Ng, v01, v02);
     normalize_f64(s->Ng);
-    for (k = 0; k < 3; k++) s->Ns[k] = s->Ng[k];
+    /* a triangle whose nine normal components are all zero belongs to a geom without normals (geom->normals == NULL) */
+    const double *nn = T->tri_nrm ? T->tri_nrm + 9 * (size_t)prim : NULL;
+    int has_n = 0;
+    if (nn) for (k = 0; k < 9; k++) if (nn[k] != 0.0) has_n = 1;
+    if (has_n) {                                              /* ri_lerp_vector, geometric.c:40-62 */
+        const double *n = nn;
+        const double w0 = 1.0 - bu - bv;
+        for (k = 0; k < 3; k++) {
+            const double a = n[k] * w0, b = n[3 + k] * bu, c = n[6 + k] * bv;
+            s->Ns[k] = (a + b) + c;
+        }
+    } else {
+        for (k = 0; k < 3; k++) s->Ns[k] = s->Ng[k];
+    }
     ortho_basis_f64(basis, s->Ng);
     for (k = 0; k < 3; k++) { s->tangent[k] = basis[0][k]; s->binormal[k] = basis[1][k]; }
+}
+
+static void state_build(const orc_tree *T, const double org[3], const double dir[3], double t, uint32_t prim, orc_state_f64 *s)
+{
+    double *saved = ((orc_tree *)T)->tri_nrm;          /* callers without (u, v): geometric normal only (path tracer uses Ng) */
+    ((orc_tree *)T)->tri_nrm = NULL;
+    state_build_uv(T, org, dir, t, 0.0, 0.0, prim, s);
+    ((orc_tree *)T)->tri_nrm = saved;
 }
 
 void orc_state_build_f64(const orc_tree *T, const double *rays, const orc_hit_f64 *hits, uint64_t n, orc_state_f64 *out)
 {
     uint64_t i;
     for (i = 0; i < n; i++) {
-        if (hits[i].hit) state_build(T, rays + 6 * i, rays + 6 * i + 3, hits[i].t, hits[i].prim, &out[i]);
+        if (hits[i].hit) state_build_uv(T, rays + 6 * i, rays + 6 * i + 3, hits[i].t, hits[i].u, hits[i].v, hits[i].prim, &out[i]);
         else memset(&out[i], 0, sizeof(out[i]));
     }
 }
@@ -658,7 +690,7 @@ void orc_render_ao(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t
                         nrays++;
                         if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
                             orc_state_f64 s;
-                            state_build(T, org, dir, t, prim, &s);
+                            state_build_uv(T, org, dir, t, uu, vv, prim, &s);
                             rad = ao_radiance(T, &V, &s, f->ntheta, f->nphi, &rng, &nrays);
                         }
                         accum = accum + rad;
@@ -673,6 +705,123 @@ void orc_render_ao(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t
         }
     }
     free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
+/* ------------------------------------------------------------------ path trace (row P) */
+
+/* sin/cos of 2*pi*r, r in [0,1): quadrant reduction + Taylor polynomials evaluated with plain IEEE multiplies and adds in a
+ * fixed order (no libm), so the CUDA kernel reproduces it bit for bit.  |error| < 1e-15. */
+void orc_det_sincos2pi(double r, double *s_out, double *c_out)
+{
+    const double q = floor(4.0 * r + 0.5);
+    const double y = r - 0.25 * q;                       /* |y| <= 1/8 */
+    const double th = 6.283185307179586476925286766559 * y;
+    const double z = th * th;
+    double sp = -7.6471637318198164759e-13;              /* -1/15! */
+    sp = sp * z + 1.6059043836821614599e-10;             /*  1/13! */
+    sp = sp * z + -2.5052108385441718775e-08;            /* -1/11! */
+    sp = sp * z + 2.7557319223985890653e-06;             /*  1/9!  */
+    sp = sp * z + -1.9841269841269841270e-04;            /* -1/7!  */
+    sp = sp * z + 8.3333333333333333333e-03;             /*  1/5!  */
+    sp = sp * z + -1.6666666666666666667e-01;            /* -1/3!  */
+    const double sn = th + th * (z * sp);
+    double cp = 4.7794773323873852974e-14;               /*  1/16! */
+    cp = cp * z + -1.1470745597729724714e-11;            /* -1/14! */
+    cp = cp * z + 2.0876756987868098979e-09;             /*  1/12! */
+    cp = cp * z + -2.7557319223985890653e-07;            /* -1/10! */
+    cp = cp * z + 2.4801587301587301587e-05;             /*  1/8!  */
+    cp = cp * z + -1.3888888888888888889e-03;            /* -1/6!  */
+    cp = cp * z + 4.1666666666666666667e-02;             /*  1/4!  */
+    cp = cp * z + -0.5;
+    const double cs = 1.0 + z * cp;
+    const int qi = ((int)q) & 3;
+    if (qi == 0)      { *s_out = sn;  *c_out = cs; }
+    else if (qi == 1) { *s_out = cs;  *c_out = -sn; }
+    else if (qi == 2) { *s_out = -sn; *c_out = -cs; }
+    else              { *s_out = -cs; *c_out = sn; }
+}
+
+static double path_uniform(uint32_t seed, uint64_t sample_id, uint32_t k)
+{
+    const uint64_t idx = sample_id * 64u + k;
+    return (double)(orc_splitmix64((uint64_t)seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* pathtrace.c:480-508 sample_cosweight */
+static void path_cosweight(double out[3], const double n[3], double r0, double r1)
+{
+    double basis[3][3], sn, cs;
+    const double cost = sqrt(r0), sint = sqrt(1.0 - r0);
+    int i;
+    ortho_basis_f64(basis, n);
+    orc_det_sincos2pi(r1, &sn, &cs);
+    {
+        const double v0 = (double)(float)(cs * sint), v1 = (double)(float)(sn * sint), v2 = (double)(float)cost;
+        for (i = 0; i < 3; i++) out[i] = v0 * basis[0][i] + v1 * basis[1][i] + v2 * basis[2][i];
+    }
+}
+
+void orc_render_pathtrace(const orc_tree *T, const orc_path_frame_t *f, float *rgb, uint64_t *nrays_out)
+{
+    view_t_f64 V = {0};
+    orc_frame_t cam;
+    uint64_t nrays = 0;
+    int x, y, s;
+    const double inv_pi = 1.0 / 3.14159265358979323846;
+    if (!T->empty) view64(T, &V);
+    memset(&cam, 0, sizeof(cam));
+    memcpy(cam.c2w, f->c2w, sizeof(cam.c2w));
+    cam.flength = f->flength; cam.is_rh = f->is_rh; cam.width = f->width; cam.height = f->height;
+
+    for (y = 0; y < f->height; y++) {
+        for (x = 0; x < f->width; x++) {
+            double sum = 0.0;
+            for (s = 0; s < f->spp; s++) {
+                const uint64_t sid = ((uint64_t)y * (uint64_t)f->width + (uint64_t)x) * (uint64_t)f->spp + (uint64_t)s;
+                uint32_t k = 0;
+                double org[3], dir[3], t, u, v, G = 1.0, rad;
+                uint32_t prim;
+                int depth = 2, alive;
+                orc_state_f64 st;
+                const double jx = path_uniform(f->seed, sid, k++), jy = path_uniform(f->seed, sid, k++);
+                orc_camera_ray(&cam, (double)(x + jx), (double)(y + jy), org, dir);
+                nrays++;
+                if (!trace_f64(T, &V, org, dir, 0, &t, &u, &v, &prim, NULL)) { sum = sum + f->Le; continue; }
+                state_build(T, org, dir, t, prim, &st);
+                alive = 1;
+                while (alive && depth < f->max_vertices) {                       /* trace_path */
+                    double out[3], r0, r1;
+                    if (path_uniform(f->seed, sid, k++) > f->kd) break;          /* russian roulette */
+                    (void)path_uniform(f->seed, sid, k++);                       /* lobe pick: always 'D' */
+                    r0 = path_uniform(f->seed, sid, k++); r1 = path_uniform(f->seed, sid, k++);
+                    path_cosweight(out, st.Ng, r0, r1);
+                    nrays++;
+                    if (!trace_f64(T, &V, st.P, out, 0, &t, &u, &v, &prim, NULL)) { alive = 0; break; }
+                    G = G * (f->kd * inv_pi);
+                    depth++;
+                    {
+                        double o2[3] = { st.P[0], st.P[1], st.P[2] };
+                        state_build(T, o2, out, t, prim, &st);
+                    }
+                }
+                {                                                                /* connect to the environment */
+                    double out[3], r0, r1;
+                    (void)path_uniform(f->seed, sid, k++);
+                    r0 = path_uniform(f->seed, sid, k++); r1 = path_uniform(f->seed, sid, k++);
+                    path_cosweight(out, st.Ng, r0, r1);
+                    G = G * (f->kd * inv_pi);
+                    nrays++;
+                    rad = trace_f64(T, &V, st.P, out, 0, &t, &u, &v, &prim, NULL) ? 0.0 : f->Le;
+                }
+                sum = sum + rad * G;
+            }
+            {
+                float *dst = rgb + 3 * ((size_t)(f->height - y - 1) * f->width + x);
+                dst[0] = dst[1] = dst[2] = (float)(sum / (double)f->spp);
+            }
+        }
+    }
     if (nrays_out) *nrays_out = nrays;
 }
 

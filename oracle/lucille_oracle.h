@@ -73,6 +73,12 @@ void      orc_get_triorder(const orc_tree *t, uint32_t *orig);        /* post-bu
 void      orc_scene_bbox(const orc_tree *t, double *bmin, double *bmax);
 int       orc_max_depth(const orc_tree *t);
 
+/* optional per-corner vertex normals, [ntris][3][3] in INPUT triangle order (ri_geom_t.normals through the index list).
+ * With normals the shading normal is Ns = (1-u-v) n0 + u n1 + v n2 (ri_lerp_vector, base/geometric.c:40-62), NOT normalised;
+ * Ng stays the geometric normal (intersection_state.c:152-180).  A triangle with nine zero components has no normals
+ * (its geom's `normals` is NULL) and keeps Ns = Ng.  NULL removes them all. */
+void orc_set_normals(orc_tree *t, const double *tri_normals);
+
 /* closest hit, reference order (bvh.c:430-542, 1092-1188). rays f64: [n][6] org,dir. f32: [n][8] ox,oy,oz,tmin,dx,dy,dz,tmax
  * (tmin/tmax are carried but never read, exactly like ri_ray_t.min_t/max_t). counters may be NULL. */
 void orc_intersect_f64(const orc_tree *t, const double *rays, uint64_t n, orc_hit_f64 *out, orc_counters_t *c);
@@ -100,6 +106,31 @@ void orc_camera_ray(const orc_frame_t *f, double x, double y, double *org3, doub
 /* full ambient-occlusion frame, single MT stream, spiral bucket order = the reference at --nthreads 1
  * (render.c:715-823,1107-1146; ambientocclusion.c:42-151,332-415). rgb: [h][w][3] float, row (H-1-y). */
 void orc_render_ao(const orc_tree *t, const orc_frame_t *f, float *rgb, uint64_t *nrays_out);
+
+/* Path-trace transport.  The reference's pathtrace.c is not in its build and does not
+ * compile against its current headers, so there is no reference binary: this is a restatement of the SKETCH's
+ * control flow with builder-stated inputs -- Lambert kd (grey), constant environment Le, counter-based RNG, and a
+ * deterministic sin/cos (plain IEEE mul/add polynomial) so that CPU and GPU paths are bit-identical:
+ *   trace_pixel (pathtrace.c:189-244): 2 draws jitter the pixel; eye ray; miss -> Le; else trace_path, then one more sampled
+ *     direction from the last vertex, G *= brdf, visibility ray, radiance = (hit ? 0 : Le) * G
+ *   trace_path (246-314): stop at MAX_PATH_VERTICES (depth starts at 2); russian roulette on kd (1 draw, 386-405); lobe pick
+ *     (1 draw, always 'D' here, 407-433); cosine sampling about the UN-flipped Ng with float-rounded local vector (2 draws,
+ *     480-508); next ray starts AT P, no offset (289-290); on hit G *= kd/pi (brdf, 510-537), recurse
+ * PARITY UNPINNED against the reference (nothing to run); pinned only between this restatement and the CUDA kernel. */
+typedef struct {
+    double  c2w[16];
+    double  flength;
+    int32_t is_rh;
+    int32_t width, height;
+    int32_t spp;                 /* pt_nsamples, option.c:142 (default 4; C4 uses 256) */
+    int32_t max_vertices;        /* MAX_PATH_VERTICES 10, pathtrace.c:66 */
+    uint32_t seed;
+    double  kd, Le;
+    int32_t rank, world;         /* product only (tile sharding); the oracle renders everything */
+    int32_t bucket_size;
+} orc_path_frame_t;
+void orc_render_pathtrace(const orc_tree *t, const orc_path_frame_t *f, float *rgb, uint64_t *nrays_out);
+void orc_det_sincos2pi(double r, double *s, double *c);
 
 /* counter-based uniform for the synthetic configs (shared definition with the product) */
 uint64_t orc_splitmix64(uint64_t x);

@@ -9,7 +9,7 @@
  *                        [--gather G] [--out frame.bin] [--scene scene.bin] [--accel bvh|b200]
  *
  * frame.bin : "LFRM" u32 w, u32 h, u32 0, f64 seconds("Render frame"), u64 nrays(stat.nrays), f32 rgb[h][w][3]
- * scene.bin : "LSCN" u32 0, u64 ntris, f64 cam[27], f64 tri[ntris][9], u32 geom[ntris]
+ * scene.bin : "LSCN" u32 0, u64 ntris, f64 cam[27], f64 tri[ntris][9], u32 geom[ntris], f64 normals[ntris][9] (zeros if none)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +26,7 @@ extern uint64_t lref_frame_nrays(void);
 extern uint64_t lref_frame_ntris(void);
 extern double  *lref_frame_tris(void);
 extern uint32_t*lref_frame_trigeom(void);
+extern double  *lref_frame_normals(void);
 extern void     lref_frame_camera(double *out27);
 
 int main(int argc, char **argv)
@@ -73,6 +74,7 @@ int main(int argc, char **argv)
             fwrite(cam, 8, 27, fp);
             fwrite(lref_frame_tris(), 8, (size_t)n * 9, fp);
             fwrite(lref_frame_trigeom(), 4, (size_t)n, fp);
+            fwrite(lref_frame_normals(), 8, (size_t)n * 9, fp);
             fclose(fp);
         }
     }

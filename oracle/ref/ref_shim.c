@@ -332,6 +332,7 @@ typedef struct {
     uint64_t nrays;
     /* scene capture (taken in the display-open callback, before the build) */
     double  *tri_xyz; uint64_t ntris; uint32_t *tri_geom; int ngeoms;
+    double  *tri_nrm;        /* [ntris][3][3] vertex normals per corner (zeros where the geom has none) */
     double   c2w[16]; double flength; int is_rh; int ortho; double fov;
     int      xsamples, ysamples, gather, bucket_size, bucket_order;
     int      has_normals;
@@ -379,6 +380,7 @@ static int dd_open(const char *name, int width, int height, int bits, RtToken co
     g_frame.ntris = n; g_frame.ngeoms = g;
     g_frame.tri_xyz  = (double *)malloc(sizeof(double) * 9 * (n ? n : 1));
     g_frame.tri_geom = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    g_frame.tri_nrm  = (double *)calloc(9 * (n ? n : 1), sizeof(double));
     g = 0;
     for (itr = ri_list_first(r->scene->geom_list); itr; itr = ri_list_next(itr)) {
         ri_geom_t *geom = (ri_geom_t *)itr->data;
@@ -387,7 +389,10 @@ static int dd_open(const char *name, int width, int height, int bits, RtToken co
         for (t = 0; t < geom->nindices / 3; t++) {
             for (i = 0; i < 3; i++)
                 for (j = 0; j < 3; j++)
+                {
                     g_frame.tri_xyz[9 * idx + 3 * i + j] = geom->positions[geom->indices[3 * t + i]][j];
+                    if (geom->normals) g_frame.tri_nrm[9 * idx + 3 * i + j] = geom->normals[geom->indices[3 * t + i]][j];
+                }
             g_frame.tri_geom[idx] = (uint32_t)g;
             idx++;
         }
@@ -468,6 +473,7 @@ uint64_t lref_frame_nrays(void)  { return g_frame.nrays; }
 uint64_t lref_frame_ntris(void)  { return g_frame.ntris; }
 double  *lref_frame_tris(void)   { return g_frame.tri_xyz; }
 uint32_t*lref_frame_trigeom(void){ return g_frame.tri_geom; }
+double  *lref_frame_normals(void){ return g_frame.tri_nrm; }
 /* out: c2w[16], flength, is_rh, ortho, fov, xsamples, ysamples, gather, bucket_size, bucket_order, has_normals, ngeoms */
 void lref_frame_camera(double *out27)
 {

@@ -70,7 +70,7 @@ def main():
     rib = os.path.join(ol.REF_DIR, "scenes", "ambient_occlusion.rib")
     with tempfile.TemporaryDirectory() as tmp:
         rgb, sec, nrays = ol.run_oracle_rib(rib, os.path.join(tmp, "f.bin"), scene=os.path.join(tmp, "s.bin"), width=160, height=120)
-        tris_c1, geom, cam = ol.read_scene(os.path.join(tmp, "s.bin"))
+        tris_c1, geom, cam, _ = ol.read_scene(os.path.join(tmp, "s.bin"))
         np.savez_compressed(os.path.join(HERE, "c1_scene.npz"), tris=tris_c1, geom=geom, cam=cam)
         np.savez_compressed(os.path.join(HERE, "c1_frame_160x120.npz"), rgb=rgb, nrays=np.uint64(nrays))
         rgb2, sec2, nrays2 = ol.run_oracle_rib(rib, os.path.join(tmp, "g.bin"), width=97, height=61, pixelsamples=2, gather=16)
@@ -81,6 +81,17 @@ def main():
                             sha256=hashlib.sha256(rgb3.tobytes()).hexdigest(), nrays=np.uint64(nrays3),
                             mean=np.float64(rgb3.astype(np.float64).mean()), seconds_1thread=np.float64(sec3),
                             rgb_half=rgb3[::2, ::2, 0].copy())
+
+    # 3b. C4 scene: examples/plane_sphere (1986 triangles) -- scene dump + the reference's AO render of it at reduced size
+    #     (the shipped reference renders every RIB with the AO transport, render.c:800-804: "C4'" in SURVEY 6.2)
+    rib4 = os.path.join(ol.REF_DIR, "scenes", "plane_sphere", "Scene_DEFAULT_Set0.rib")
+    with tempfile.TemporaryDirectory() as tmp:
+        rgb4, _, nrays4 = ol.run_oracle_rib(rib4, os.path.join(tmp, "f.bin"), scene=os.path.join(tmp, "s.bin"), width=96, height=96,
+                                            pixelsamples=2, gather=16)
+        tris4, geom4, cam4, nrm4 = ol.read_scene(os.path.join(tmp, "s.bin"))
+        # cam4[25] == 1: polygon.c gave this geometry vertex normals, so the AO transport shades with interpolated Ns
+        np.savez_compressed(os.path.join(HERE, "c4_scene.npz"), tris=tris4, geom=geom4, cam=cam4, normals=nrm4)
+        np.savez_compressed(os.path.join(HERE, "c4_ao_frame_96x96_ps2_g16.npz"), rgb=rgb4, nrays=np.uint64(nrays4))
 
     # 4. MT19937: first outputs of randomMT2() as consumed by the reference (checked indirectly by the frames above;
     #    committed as integers for the device generator test)

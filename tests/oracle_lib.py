@@ -38,6 +38,12 @@ class FrameParams(C.Structure):
                 ("ntheta", C.c_int32), ("nphi", C.c_int32), ("bucket_size", C.c_int32)]
 
 
+class PathFrameParams(C.Structure):
+    _fields_ = [("c2w", C.c_double * 16), ("flength", C.c_double), ("is_rh", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("spp", C.c_int32), ("max_vertices", C.c_int32), ("seed", C.c_uint32), ("kd", C.c_double), ("Le", C.c_double),
+                ("rank", C.c_int32), ("world", C.c_int32), ("bucket_size", C.c_int32)]
+
+
 def oracle_available() -> bool:
     return os.path.exists(ORACLE_SO)
 
@@ -84,6 +90,14 @@ class OracleTree:
     def max_depth(self):
         return self.lib.orc_max_depth(self.h)
 
+    def set_normals(self, tri_normals):
+        if tri_normals is None:
+            self.lib.orc_set_normals(self.h, None)
+        else:
+            n = np.ascontiguousarray(tri_normals, dtype=np.float64).reshape(-1, 9)
+            assert len(n) == self.ntris
+            self.lib.orc_set_normals(self.h, _ptr(n))
+
     def intersect_f64(self, rays6: np.ndarray, counters: bool = False):
         rays6 = np.ascontiguousarray(rays6, dtype=np.float64)
         out = np.zeros(len(rays6), dtype=HIT64_DTYPE)
@@ -118,6 +132,12 @@ class OracleTree:
         self.lib.orc_state_build_f64(self.h, _ptr(rays6), _ptr(hits), C.c_uint64(len(rays6)), _ptr(out))
         return out
 
+    def render_pathtrace(self, frame: "PathFrameParams"):
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_pathtrace(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
     def render_ao(self, frame: "FrameParams"):
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         nrays = C.c_uint64(0)
@@ -141,6 +161,7 @@ class Oracle:
         lib.orc_get_triorder.argtypes = [C.c_void_p, C.c_void_p]
         lib.orc_scene_bbox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_max_depth.argtypes = [C.c_void_p]
+        lib.orc_set_normals.argtypes = [C.c_void_p, C.c_void_p]
         for name in ("orc_intersect_f64", "orc_intersect_f32", "orc_occluded_f64", "orc_occluded_f32"):
             getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
             getattr(lib, name).restype = None
@@ -151,6 +172,7 @@ class Oracle:
         lib.orc_subpixel_jitter.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_camera_ray.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_render_ao.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_render_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_splitmix64.restype = C.c_uint64
         lib.orc_splitmix64.argtypes = [C.c_uint64]
         self.lib = lib
@@ -296,7 +318,9 @@ def read_scene(path: str):
         cam = np.frombuffer(f.read(8 * 27), dtype="<f8").copy()
         tris = np.frombuffer(f.read(8 * 9 * n), dtype="<f8").reshape(n, 3, 3).copy()
         geom = np.frombuffer(f.read(4 * n), dtype="<u4").copy()
-    return tris, geom, cam
+        rest = f.read(8 * 9 * n)
+        normals = np.frombuffer(rest, dtype="<f8").reshape(n, 3, 3).copy() if len(rest) == 8 * 9 * n else np.zeros((n, 3, 3))
+    return tris, geom, cam, normals
 
 
 def run_oracle_rib(rib: str, out: str, scene: str | None = None, nthreads: int = 1, width: int = 0, height: int = 0,

@@ -103,3 +103,17 @@ def test_f32_restatement_tracks_double(oracle):
     rel = np.abs(h32["t"][both][same].astype(np.float64) - h64["t"][both][same]) / h64["t"][both][same]
     assert rel.max() < 1e-5
     assert np.array_equal(t.occluded_f32(rays8) == 1, m32)
+
+
+def test_plane_sphere_ao_frame_with_vertex_normals(oracle, golden_dir):
+    """examples/plane_sphere (BASELINE configs[3] scene; the shipped reference renders it with the AO transport): the sphere
+    carries vertex normals, so calculate_occlusion samples about the interpolated, un-normalised Ns -- bit-identical frame."""
+    sc = np.load(os.path.join(golden_dir, "c4_scene.npz"))
+    g = np.load(os.path.join(golden_dir, "c4_ao_frame_96x96_ps2_g16.npz"))
+    t = oracle.build(sc["tris"])
+    t.set_normals(sc["normals"])
+    rgb, nrays = t.render_ao(ol.frame_params(sc["cam"], 96, 96, xsamples=2, ysamples=2, gather=16))
+    assert nrays == int(g["nrays"]) and np.array_equal(rgb, g["rgb"])
+    t.set_normals(None)
+    flat, _ = t.render_ao(ol.frame_params(sc["cam"], 96, 96, xsamples=2, ysamples=2, gather=16))
+    assert not np.array_equal(flat, g["rgb"])          # the normals matter
