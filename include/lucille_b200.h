@@ -170,6 +170,12 @@ int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
                                     ri_b200_frame_stats_t *stats);
 int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
 
+/* ---- replaces ri_beam_set + ri_bvh_intersect_beam_visibility (beam.c:332-466, bvh.c:612-667) for a batch of beams.
+ * beams: HOST [n][15] doubles = org.xyz, dir0.xyz .. dir3.xyz (consecutive corners of the frustum).  out[i] = RI_BEAM_MISS_COMPLETELY 0 /
+ * RI_BEAM_HIT_COMPLETELY 1 / RI_BEAM_HIT_PARTIALLY 2 (beam.h:27-29), or -1 where ri_beam_set would fail (corner directions
+ * not in one octant, beam.c:356-377).  fp64 records. */
+int ri_b200_beam_visibility_batch(ri_b200_accel_t *accel, const double *beams, uint64_t n, int32_t *out);
+
 /* ---- path-trace transport (src/transport/pathtrace.c:131-537; NOT in the reference build): the sketch's control
  * flow with builder-stated inputs -- Lambert kd, constant environment Le, counter-based RNG keyed by (pixel, sample, draw),
  * deterministic sin/cos.  fp64 records.  rgb_out: HOST [height][width][3], row H-1-y (pathtrace.c:183). */

@@ -118,6 +118,7 @@ ABI = [
     ("ri_b200_render_ao_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_ao_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
+    ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_pathtrace_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_mt_stream", _I, [_P, _U32, _U64, _P, _I]),
@@ -339,6 +340,13 @@ class Accel:
         stats = FrameStats()
         _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
         return rgb, stats
+
+    def beam_visibility(self, beams15: np.ndarray) -> np.ndarray:
+        """``ri_bvh_intersect_beam_visibility`` for a batch: [n,15] float64 beams -> int32 codes (0 miss, 1 full hit, 2 partial, -1 invalid)."""
+        beams15 = np.ascontiguousarray(beams15, dtype=np.float64).reshape(-1, 15)
+        out = np.zeros(len(beams15), dtype=np.int32)
+        _check(self.lib.ri_b200_beam_visibility_batch(self._h(), _ptr(beams15), len(beams15), _ptr(out)))
+        return out
 
     def render_pathtrace(self, frame: "PathFrame"):
         """One path-traced frame -> (rgb [h,w,3] float32 on the host, FrameStats with the ray count)."""

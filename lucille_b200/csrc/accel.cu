@@ -671,3 +671,4 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
 
 #include "frame.cuh"
 #include "pathtrace.cuh"
+#include "beam.cuh"

@@ -132,3 +132,20 @@ def rays_f32_to_f64(rays: np.ndarray) -> np.ndarray:
     """[n,8] float32 ray records -> [n,6] float64 (org, dir) with identical values."""
     rays = np.asarray(rays, dtype=np.float32)
     return np.ascontiguousarray(np.concatenate([rays[:, 0:3], rays[:, 4:7]], axis=1).astype(np.float64))
+
+
+def random_beams(n: int, seed: int, eye=(0.5, 0.5, -2.0), spread: float = 0.35, width: float = 0.02) -> np.ndarray:
+    """Small square frusta from ``eye`` (the testbed's use of beams: one beam per pixel block, simplerender.cpp:540-580),
+    shape [n, 15] float64 = org.xyz + 4 corner directions in the winding ri_beam_set expects (consecutive corners)."""
+    u = uniform01(seed, 0, 3 * n).reshape(n, 3)
+    cx = (2.0 * u[:, 0] - 1.0) * spread
+    cy = (2.0 * u[:, 1] - 1.0) * spread
+    w = width * (0.25 + u[:, 2])
+    out = np.zeros((n, 15), dtype=np.float64)
+    out[:, 0:3] = np.asarray(eye, dtype=np.float64)
+    corners = [(-1, -1), (1, -1), (1, 1), (-1, 1)]
+    for j, (sx, sy) in enumerate(corners):
+        out[:, 3 + 3 * j + 0] = cx + sx * w
+        out[:, 3 + 3 * j + 1] = cy + sy * w
+        out[:, 3 + 3 * j + 2] = 1.0
+    return out

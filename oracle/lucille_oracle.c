@@ -708,6 +708,153 @@ void orc_render_ao(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ beam visibility (row a10) */
+
+typedef struct {
+    double org[3], dir[4][3], normal[4][3], t_max;
+    int    dominant_axis, dirsign[3];
+} beam_t;
+
+/* beam.c:332-466 ri_beam_set (the parts the visibility query reads) */
+static int beam_set(beam_t *b, const double org[3], const double dir[4][3])
+{
+    int i, j, k;
+    double maxval;
+    const double d = 1024.0;
+    b->t_max = ORC_INFINITY;
+    for (i = 0; i < 3; i++) {                                  /* all four directions in one octant? */
+        int zeros = 0, mask = 0;
+        for (j = 0; j < 4; j++) {
+            if (fabs(dir[j][i]) < ORC_EPS) zeros++;
+            else mask += (dir[j][i] < 0.0) ? 1 : -1;
+        }
+        if ((mask != -(4 - zeros)) && (mask != (4 - zeros))) return -1;
+    }
+    for (k = 0; k < 3; k++) b->org[k] = org[k];
+    maxval = fabs(dir[0][0]);
+    b->dominant_axis = 0;
+    if (maxval < fabs(dir[0][1])) { maxval = fabs(dir[0][0]); b->dominant_axis = 1; }     /* sic: beam.c:389-392 keeps |x| */
+    if (maxval < fabs(dir[0][2])) { maxval = fabs(dir[0][2]); b->dominant_axis = 2; }
+    for (k = 0; k < 3; k++) b->dirsign[k] = (dir[0][k] < 0.0) ? 1 : 0;
+    {
+        double normal[3] = { 0.0, 0.0, 0.0 };
+        normal[b->dominant_axis] = 1.0;
+        if (b->dirsign[b->dominant_axis]) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
+        for (i = 0; i < 4; i++) {
+            const double t = dir[i][0] * normal[0] + dir[i][1] * normal[1] + dir[i][2] * normal[2];
+            const double kk = (fabs(t) > ORC_EPS) ? d / t : 1.0;
+            for (k = 0; k < 3; k++) b->dir[i][k] = kk * dir[i][k];
+        }
+    }
+    cross_f64(b->normal[0], b->dir[1], b->dir[0]);
+    cross_f64(b->normal[1], b->dir[2], b->dir[1]);
+    cross_f64(b->normal[2], b->dir[3], b->dir[2]);
+    cross_f64(b->normal[3], b->dir[0], b->dir[3]);
+    return 0;
+}
+
+/* bvh.c:2012-2089 test_beam_aabb / test_beam_aabb_misses / get_n_point: 1 = may hit */
+static int beam_aabb(const double *box /* min xyz, max xyz */, const beam_t *b)
+{
+    int i, k;
+    for (i = 0; i < 4; i++) {
+        const double *n = b->normal[i];
+        double np[3], no[3], d;
+        for (k = 0; k < 3; k++) np[k] = (n[k] > 0.0) ? box[k] : box[3 + k];
+        for (k = 0; k < 3; k++) no[k] = np[k] - b->org[k];
+        d = no[0] * n[0] + no[1] * n[1] + no[2] * n[2];
+        if (d > 0.0) return 0;
+    }
+    return 1;
+}
+
+/* bvh.c:2139-2281 test_beam_triangle */
+static int beam_triangle(const double *v /* v0 v1 v2 */, const beam_t *b)
+{
+    double e1[3], e2[3], u[4], vv[4], t[4];
+    int i, k, mask = 0, cnt;
+    for (k = 0; k < 3; k++) { e1[k] = v[3 + k] - v[k]; e2[k] = v[6 + k] - v[k]; }
+    for (i = 0; i < 4; i++) {
+        double p[3], q[3], s[3], a, inva;
+        cross_f64(p, b->dir[i], e2);
+        a = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2];
+        inva = (fabs(a) > ORC_EPS) ? 1.0 / a : 0.0;
+        for (k = 0; k < 3; k++) s[k] = b->org[k] - v[k];
+        cross_f64(q, s, e1);
+        u[i]  = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) * inva;
+        vv[i] = (q[0] * b->dir[i][0] + q[1] * b->dir[i][1] + q[2] * b->dir[i][2]) * inva;
+        t[i]  = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inva;
+        if ((u[i] < 0.0) || (u[i] > 1.0)) continue;
+        if ((vv[i] < 0.0) || ((u[i] + vv[i]) > 1.0)) continue;
+        if ((t[i] < 0.0) || (t[i] > b->t_max)) continue;
+        mask |= (1 << i);
+    }
+    if (mask == 0) {
+        cnt = 0; for (i = 0; i < 4; i++) if (t[i] < 0.0) cnt++;
+        if (cnt == 4) return ORC_BEAM_MISS_COMPLETELY;
+        cnt = 0; for (i = 0; i < 4; i++) if (u[i] < 0.0) cnt++;
+        if ((cnt != 0) && (cnt != 4)) return ORC_BEAM_HIT_PARTIALLY;
+        cnt = 0; for (i = 0; i < 4; i++) if (u[i] > 1.0) cnt++;
+        if ((cnt != 0) && (cnt != 4)) return ORC_BEAM_HIT_PARTIALLY;
+        cnt = 0; for (i = 0; i < 4; i++) if (vv[i] < 0.0) cnt++;
+        if ((cnt != 0) && (cnt != 4)) return ORC_BEAM_HIT_PARTIALLY;
+        cnt = 0; for (i = 0; i < 4; i++) if ((u[i] + vv[i]) >= 1.0) cnt++;
+        if ((cnt != 0) && (cnt != 4)) return ORC_BEAM_HIT_PARTIALLY;
+        return ORC_BEAM_MISS_COMPLETELY;
+    }
+    return (mask == 0xf) ? ORC_BEAM_HIT_COMPLETELY : ORC_BEAM_HIT_PARTIALLY;
+}
+
+/* bvh.c:612-667 + 2648-2746 + 2435-2542 */
+static int beam_query(const orc_tree *T, const beam_t *b)
+{
+    int64_t stack[ORC_STACK], node = 0, i;
+    int depth = 0;
+    double sb[6];
+    int k;
+    if (T->empty) return 0;
+    for (k = 0; k < 3; k++) { sb[k] = T->bmin[k]; sb[3 + k] = T->bmax[k]; }
+    if (!beam_aabb(sb, b)) return ORC_BEAM_MISS_COMPLETELY;
+    for (;;) {
+        const orc_node_t *n = &T->nodes[node];
+        if (n->is_leaf) {
+            for (i = 0; i < n->ntris; i++) {
+                const int r = beam_triangle(T->tri_xyz + 9 * (n->tri_start + i), b);
+                if (r == ORC_BEAM_HIT_COMPLETELY || r == ORC_BEAM_HIT_PARTIALLY) return r;
+            }
+            if (depth < 1) return ORC_BEAM_MISS_COMPLETELY;
+            node = stack[--depth];
+        } else {
+            const int hl = beam_aabb(n->lbox, b), hr = beam_aabb(n->rbox, b);
+            const int ret = hl | (hr << 1);
+            if (ret == 0) {
+                if (depth < 1) return ORC_BEAM_MISS_COMPLETELY;
+                node = stack[--depth];
+            } else if (ret == 1) node = n->child0;
+            else if (ret == 2) node = n->child1;
+            else {
+                const int order = b->dirsign[b->dominant_axis];
+                stack[depth++] = order ? n->child0 : n->child1;
+                node = order ? n->child1 : n->child0;
+            }
+        }
+    }
+}
+
+void orc_beam_visibility(const orc_tree *T, const double *beams, uint64_t n, int32_t *out)
+{
+    uint64_t i;
+    for (i = 0; i < n; i++) {
+        const double *p = beams + 15 * i;
+        double dir[4][3];
+        beam_t b;
+        int j, k;
+        for (j = 0; j < 4; j++) for (k = 0; k < 3; k++) dir[j][k] = p[3 + 3 * j + k];
+        if (beam_set(&b, p, dir) != 0) { out[i] = ORC_BEAM_INVALID; continue; }
+        out[i] = beam_query(T, &b);
+    }
+}
+
 /* ------------------------------------------------------------------ path trace (row P) */
 
 /* sin/cos of 2*pi*r, r in [0,1): quadrant reduction + Taylor polynomials evaluated with plain IEEE multiplies and adds in a

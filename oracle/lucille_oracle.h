@@ -107,6 +107,18 @@ void orc_camera_ray(const orc_frame_t *f, double x, double y, double *org3, doub
  * (render.c:715-823,1107-1146; ambientocclusion.c:42-151,332-415). rgb: [h][w][3] float, row (H-1-y). */
 void orc_render_ao(const orc_tree *t, const orc_frame_t *f, float *rgb, uint64_t *nrays_out);
 
+/* Beam (4-corner frustum) visibility query, SURVEY 8a row a10: ri_beam_set (beam.c:332-466) + ri_bvh_intersect_beam_visibility
+ * (bvh.c:612-667) -> test_beam_aabb (n-vertex against the 4 frustum planes, bvh.c:1997-2089), bvh_traverse_beam_visibility
+ * (2648-2746, near child = child[dirsign[dominant_axis]]), leaf: test_beam_triangle on the 4 corner rays (2139-2281), first
+ * triangle that is not a complete miss decides.  beams: [n][15] doubles = org.xyz, dir0.xyz .. dir3.xyz.
+ * out[i]: ORC_BEAM_MISS_COMPLETELY / HIT_COMPLETELY / HIT_PARTIALLY (beam.h:27-29), or ORC_BEAM_INVALID (-1) when the four
+ * directions do not share a sign on every axis (ri_beam_set returns -1, beam.c:356-377). */
+#define ORC_BEAM_MISS_COMPLETELY 0
+#define ORC_BEAM_HIT_COMPLETELY  1
+#define ORC_BEAM_HIT_PARTIALLY   2
+#define ORC_BEAM_INVALID        (-1)
+void orc_beam_visibility(const orc_tree *t, const double *beams, uint64_t n, int32_t *out);
+
 /* Path-trace transport.  The reference's pathtrace.c is not in its build and does not
  * compile against its current headers, so there is no reference binary: this is a restatement of the SKETCH's
  * control flow with builder-stated inputs -- Lambert kd (grey), constant environment Le, counter-based RNG, and a

@@ -318,7 +318,7 @@ int lref_beam_visibility(void *h, const double *org, const double *dirs)
     for (k = 0; k < 3; k++) o[k] = org[k];
     o[3] = 1.0;
     for (i = 0; i < 4; i++) { for (k = 0; k < 3; k++) d[i][k] = dirs[3 * i + k]; d[i][3] = 0.0; }
-    ri_beam_set(&beam, o, d);
+    if (ri_beam_set(&beam, o, d) != 0) return -1;            /* directions not in one octant (beam.c:356-377) */
     return ri_bvh_intersect_beam_visibility(s->bvh, &beam, NULL);
 }
 

@@ -93,6 +93,16 @@ def main():
         np.savez_compressed(os.path.join(HERE, "c4_scene.npz"), tris=tris4, geom=geom4, cam=cam4, normals=nrm4)
         np.savez_compressed(os.path.join(HERE, "c4_ao_frame_96x96_ps2_g16.npz"), rgb=rgb4, nrays=np.uint64(nrays4))
 
+    # 3c. beam visibility codes from ri_beam_set + ri_bvh_intersect_beam_visibility (all four outcome classes)
+    cfg = [(20000, scenes.SEED_C2, 5, 0.35, 0.02), (300, 3, 6, 0.35, 0.002), (20000, scenes.SEED_C2, 7, 0.001, 0.05)]
+    beams_out = dict(ntris=np.array([c[0] for c in cfg]), soup_seed=np.array([c[1] for c in cfg], dtype=np.uint64),
+                     beam_seed=np.array([c[2] for c in cfg]), spread=np.array([c[3] for c in cfg]), width=np.array([c[4] for c in cfg]))
+    for k, (nt, ss, bs, spread, width) in enumerate(cfg):
+        rs = ref.build(scenes.triangle_soup(nt, ss))
+        bb = scenes.random_beams(1500, bs, spread=spread, width=width)
+        beams_out[f"codes{k}"] = np.array([rs.beam_visibility(b[:3], b[3:]) for b in bb], dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "beams.npz"), **beams_out)
+
     # 4. MT19937: first outputs of randomMT2() as consumed by the reference (checked indirectly by the frames above;
     #    committed as integers for the device generator test)
     orc = ol.Oracle()

@@ -132,6 +132,12 @@ class OracleTree:
         self.lib.orc_state_build_f64(self.h, _ptr(rays6), _ptr(hits), C.c_uint64(len(rays6)), _ptr(out))
         return out
 
+    def beam_visibility(self, beams15: np.ndarray) -> np.ndarray:
+        beams15 = np.ascontiguousarray(beams15, dtype=np.float64).reshape(-1, 15)
+        out = np.zeros(len(beams15), dtype=np.int32)
+        self.lib.orc_beam_visibility(self.h, _ptr(beams15), C.c_uint64(len(beams15)), _ptr(out))
+        return out
+
     def render_pathtrace(self, frame: "PathFrameParams"):
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         nrays = C.c_uint64(0)
@@ -172,6 +178,7 @@ class Oracle:
         lib.orc_subpixel_jitter.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_camera_ray.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_render_ao.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_splitmix64.restype = C.c_uint64
         lib.orc_splitmix64.argtypes = [C.c_uint64]

@@ -320,3 +320,17 @@ def test_plane_sphere_ao_frame_with_vertex_normals(golden_dir):
     a32, _ = a.render_ao(fr32)
     a64, _ = a.render_ao(fr64)
     assert np.isfinite(a32).all() and a32.shape == a64.shape and 0.0 <= a32.min() and a32.max() <= 1.0
+
+
+def test_beam_visibility_batch(soup20k):
+    """Row a10 on the device (fp64 records) against the oracle (pinned to ri_bvh_intersect_beam_visibility on CPU)."""
+    tris, a, orc = soup20k
+    for seed, kw in [(5, {}), (7, dict(spread=0.001, width=0.05)), (9, dict(width=0.0005))]:
+        beams = scenes.random_beams(20000, seed, **kw)
+        assert np.array_equal(a.beam_visibility(beams), orc.beam_visibility(beams))
+    sparse = scenes.triangle_soup(300, 3)
+    b = scenes.random_beams(20000, 6, width=0.002)
+    got = accel.Accel.bind().build(sparse, accel.PREC_F64).beam_visibility(b)
+    assert np.array_equal(got, ol.Oracle().build(sparse).beam_visibility(b))
+    assert set(np.unique(got)) == {0, 1, 2}
+    assert np.all(accel.Accel.bind().build(np.zeros((0, 3, 3)), accel.PREC_F64).beam_visibility(b[:64]) == 0)

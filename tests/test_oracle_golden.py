@@ -117,3 +117,12 @@ def test_plane_sphere_ao_frame_with_vertex_normals(oracle, golden_dir):
     t.set_normals(None)
     flat, _ = t.render_ao(ol.frame_params(sc["cam"], 96, 96, xsamples=2, ysamples=2, gather=16))
     assert not np.array_equal(flat, g["rgb"])          # the normals matter
+
+
+def test_beam_visibility_golden(oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "beams.npz"))
+    for k in range(3):
+        tris = scenes.triangle_soup(int(g["ntris"][k]), int(g["soup_seed"][k]))
+        beams = scenes.random_beams(1500, int(g["beam_seed"][k]), spread=float(g["spread"][k]), width=float(g["width"][k]))
+        assert np.array_equal(oracle.build(tris).beam_visibility(beams), g[f"codes{k}"])
+    assert set(np.unique(np.concatenate([g["codes0"], g["codes1"], g["codes2"]]))) == {-1, 0, 1, 2}

@@ -61,3 +61,14 @@ def test_counters_match_reference_statistics(oracle):
     want = refs.stats_get()
     _, cnt = oracle.build(tris).intersect_f64(rays6, counters=True)
     assert {k: int(cnt[k]) for k in want} == want
+
+
+def test_beam_visibility(oracle, ref):
+    """Row a10: frustum visibility query (ri_beam_set + ri_bvh_intersect_beam_visibility) -- every outcome class."""
+    for ntris, seed, kw in [(20000, 5, {}), (300, 6, dict(width=0.002)), (20000, 7, dict(spread=0.001, width=0.05))]:
+        tris = scenes.triangle_soup(ntris, scenes.SEED_C2 if ntris > 1000 else 3)
+        beams = scenes.random_beams(1500, seed, **kw)
+        got = oracle.build(tris).beam_visibility(beams)
+        rs = ref.build(tris)
+        want = np.array([rs.beam_visibility(b[:3], b[3:]) for b in beams], dtype=np.int32)
+        assert np.array_equal(got, want)
