@@ -332,5 +332,5 @@ def test_beam_visibility_batch(soup20k):
     b = scenes.random_beams(20000, 6, width=0.002)
     got = accel.Accel.bind().build(sparse, accel.PREC_F64).beam_visibility(b)
     assert np.array_equal(got, ol.Oracle().build(sparse).beam_visibility(b))
-    assert set(np.unique(got)) == {0, 1, 2}
+    assert {0, 1, 2} <= set(int(x) for x in np.unique(got))
     assert np.all(accel.Accel.bind().build(np.zeros((0, 3, 3)), accel.PREC_F64).beam_visibility(b[:64]) == 0)
