@@ -53,6 +53,7 @@ struct Ctx {
     uint32_t    *orig_out;
     uint64_t     grain;        // ranges <= grain become parallel tasks (0: never)
     std::vector<Task> *tasks;
+    int          nthreads;     // for the big top-level ranges
 };
 
 inline void add_margin(double lo[3], double hi[3])
@@ -82,25 +83,56 @@ inline double sah(uint64_t nl, double al, uint64_t nr, double ar, double total)
 
 struct Split { int axis; double pos; };
 
-Split choose_split(const Box *b, uint64_t n, const double lo[3], const double hi[3])
+// Ranges of at least kBigRange boxes (the top few levels of a large scene) are binned and partitioned by all host threads;
+// integer bin counts, min/max box unions and the stable-left / reversed-right placement are order-independent, so the
+// result is the same tree.
+constexpr uint64_t kBigRange = 1ull << 19;
+
+template <typename F> void parallel_chunks(int nthreads, uint64_t n, F fn)
 {
-    uint32_t bins[2][3][kBins];
-    std::memset(bins, 0, sizeof(bins));
-    double inv[3];
-    for (int k = 0; k < 3; ++k) {
-        const double extent = hi[k] - lo[k];
-        inv[k] = (extent > kEps) ? (double)kBins / extent : 0.0;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const uint64_t lo = n * (uint64_t)w / (uint64_t)nthreads, hi = n * (uint64_t)(w + 1) / (uint64_t)nthreads;
+        pool.emplace_back([=]() { fn(w, lo, hi); });
     }
-    for (uint64_t i = 0; i < n; ++i) {
+    for (auto &t : pool) t.join();
+}
+
+struct Bins { uint32_t c[2][3][kBins]; };
+
+void count_bins(const Box *b, uint64_t lo_i, uint64_t hi_i, const double lo[3], const double inv[3], Bins &bins)
+{
+    std::memset(&bins, 0, sizeof(bins));
+    for (uint64_t i = lo_i; i < hi_i; ++i) {
         for (int k = 0; k < 3; ++k) {
             uint32_t a = (uint32_t)((b[i].lo[k] - lo[k]) * inv[k]);
             uint32_t c = (uint32_t)((b[i].hi[k] - lo[k]) * inv[k]);
             if (a >= (uint32_t)kBins) a = kBins - 1;
             if (c >= (uint32_t)kBins) c = kBins - 1;
-            bins[0][k][a]++;
-            bins[1][k][c]++;
+            bins.c[0][k][a]++;
+            bins.c[1][k][c]++;
         }
     }
+}
+
+Split choose_split(const Box *b, uint64_t n, const double lo[3], const double hi[3], int nthreads)
+{
+    double inv[3];
+    for (int k = 0; k < 3; ++k) {
+        const double extent = hi[k] - lo[k];
+        inv[k] = (extent > kEps) ? (double)kBins / extent : 0.0;
+    }
+    Bins tot;
+    if (nthreads > 1 && n >= kBigRange) {
+        std::vector<Bins> part((size_t)nthreads);
+        parallel_chunks(nthreads, n, [&](int w, uint64_t a, uint64_t c) { count_bins(b, a, c, lo, inv, part[(size_t)w]); });
+        std::memset(&tot, 0, sizeof(tot));
+        for (const Bins &p : part)
+            for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) for (int i = 0; i < kBins; ++i) tot.c[s][k][i] += p.c[s][k][i];
+    } else {
+        count_bins(b, 0, n, lo, inv, tot);
+    }
+    uint32_t (*bins)[3][kBins] = tot.c;
 
     Split best{0, 0.0};
     double best_cost = kInf;
@@ -166,13 +198,60 @@ void build_range(Ctx &cx, Arena &ar, TmpNode **slot, int cur, uint64_t left, uin
 
     const Box *src = cx.buf[cur] + left;
     Box *dst = cx.buf[cur ^ 1] + left;
-    const Split sp = choose_split(src, n, lo, hi);
+    const Split sp = choose_split(src, n, lo, hi, cx.nthreads);
 
     // partition: "bmax[axis] < cut" goes left in input order, the rest fills the right part from the
     // back (so it comes out reversed) -- bvh.c:1437-1468.  Child boxes are accumulated in the same sweep.
     uint64_t nl = 0, nr = n - 1;
     double llo[3], lhi[3], rlo[3], rhi[3];
     bool lseen = false, rseen = false;
+    if (cx.nthreads > 1 && n >= kBigRange) {
+        // two passes: per-chunk left counts, then every chunk writes its elements where the sequential sweep would have
+        const int T = cx.nthreads;
+        std::vector<uint64_t> cnt((size_t)T, 0);
+        parallel_chunks(T, n, [&](int w, uint64_t a, uint64_t c) {
+            uint64_t k = 0;
+            for (uint64_t i = a; i < c; ++i) k += (src[i].hi[sp.axis] < sp.pos) ? 1 : 0;
+            cnt[(size_t)w] = k;
+        });
+        std::vector<uint64_t> lbase((size_t)T, 0), rbase((size_t)T, 0);      // elements placed before this chunk
+        uint64_t lsum = 0, rsum = 0;
+        for (int w = 0; w < T; ++w) {
+            const uint64_t a = n * (uint64_t)w / (uint64_t)T, c = n * (uint64_t)(w + 1) / (uint64_t)T;
+            lbase[(size_t)w] = lsum; rbase[(size_t)w] = rsum;
+            lsum += cnt[(size_t)w]; rsum += (c - a) - cnt[(size_t)w];
+        }
+        struct Acc { double llo[3], lhi[3], rlo[3], rhi[3]; bool ls, rs; };
+        std::vector<Acc> acc((size_t)T);
+        parallel_chunks(T, n, [&](int w, uint64_t a, uint64_t c) {
+            Acc &A = acc[(size_t)w];
+            A.ls = A.rs = false;
+            uint64_t l = lbase[(size_t)w], r = n - 1 - rbase[(size_t)w];
+            for (uint64_t i = a; i < c; ++i) {
+                const Box &b = src[i];
+                if (b.hi[sp.axis] < sp.pos) {
+                    dst[l++] = b;
+                    if (!A.ls) { for (int k = 0; k < 3; ++k) { A.llo[k] = b.lo[k]; A.lhi[k] = b.hi[k]; } A.ls = true; }
+                    else grow(A.llo, A.lhi, b);
+                } else {
+                    dst[r--] = b;
+                    if (!A.rs) { for (int k = 0; k < 3; ++k) { A.rlo[k] = b.lo[k]; A.rhi[k] = b.hi[k]; } A.rs = true; }
+                    else grow(A.rlo, A.rhi, b);
+                }
+            }
+        });
+        nl = lsum; nr = n - 1 - rsum;
+        for (const Acc &A : acc) {
+            if (A.ls) {
+                if (!lseen) { for (int k = 0; k < 3; ++k) { llo[k] = A.llo[k]; lhi[k] = A.lhi[k]; } lseen = true; }
+                else for (int k = 0; k < 3; ++k) { llo[k] = (llo[k] < A.llo[k]) ? llo[k] : A.llo[k]; lhi[k] = (lhi[k] > A.lhi[k]) ? lhi[k] : A.lhi[k]; }
+            }
+            if (A.rs) {
+                if (!rseen) { for (int k = 0; k < 3; ++k) { rlo[k] = A.rlo[k]; rhi[k] = A.rhi[k]; } rseen = true; }
+                else for (int k = 0; k < 3; ++k) { rlo[k] = (rlo[k] < A.rlo[k]) ? rlo[k] : A.rlo[k]; rhi[k] = (rhi[k] > A.rhi[k]) ? rhi[k] : A.rhi[k]; }
+            }
+        }
+    } else
     for (uint64_t i = 0; i < n; ++i) {
         const Box &b = src[i];
         if (b.hi[sp.axis] < sp.pos) {
@@ -270,6 +349,7 @@ void build_tree(const double *tri_xyz, uint64_t ntris, HostTree &out, int nthrea
     const bool parallel = nthreads > 1 && ntris >= (1u << 16);
     cx.grain = parallel ? std::max<uint64_t>(ntris / (uint64_t)(8 * nthreads), 4096) : 0;
     cx.tasks = parallel ? &tasks : nullptr;
+    cx.nthreads = parallel ? nthreads : 1;
 
     Arena top;
     TmpNode *root = nullptr;
@@ -280,7 +360,7 @@ void build_tree(const double *tri_xyz, uint64_t ntris, HostTree &out, int nthrea
         std::sort(tasks.begin(), tasks.end(),
                   [](const Task &x, const Task &y) { return (x.right - x.left) > (y.right - y.left); });
         Ctx sub = cx;
-        sub.tasks = nullptr; sub.grain = 0;
+        sub.tasks = nullptr; sub.grain = 0; sub.nthreads = 1;
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
         for (int w = 0; w < nthreads; ++w) {

@@ -34,6 +34,7 @@ def test_bind_rejects_other_methods():
 @pytest.mark.parametrize("maker", [
     lambda: scenes.triangle_soup(100000, scenes.SEED_C2),
     lambda: scenes.triangle_soup(70000, 21),            # above the parallel threshold: threaded build must not change the tree
+    lambda: scenes.triangle_soup(600000, 22),           # above 2^19: the top ranges are binned/partitioned by all threads
     lambda: scenes.triangle_soup(17, 7),
     lambda: scenes.triangle_soup(16, 7),
     lambda: scenes.triangle_soup(1, 7),
