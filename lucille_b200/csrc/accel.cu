@@ -191,6 +191,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
     if (!COUNT) {
         // production path: persistent warps with ray replacement; batches above 2^31 rays are split
         auto pk = trace_persistent_kernel<Real, ANYHIT>;
+        static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kBlock, smem));
@@ -211,7 +212,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                            d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
-                                           d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr);
+                                           d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, refill_at);
             LAUNCHED();
             CUDA_OK(cudaGetLastError());
         }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kBlock)
 trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const uint32_t n, const uint32_t chunk,
                         typename RayIO<Real>::Hit *__restrict__ hits, uint8_t *__restrict__ occ,
                         uint32_t *__restrict__ counts, const uint32_t rays_per_count,
-                        unsigned int *__restrict__ work_counter)
+                        unsigned int *__restrict__ work_counter, const uint32_t refill_at)
 {
     using P = Prec<Real>;
     extern __shared__ uint32_t s_stack[];
@@ -119,7 +119,9 @@ trace_persistent_kernel(const SceneView<Real> S, const Real *__restrict__ rays, 
             const unsigned want_node = __ballot_sync(0xffffffffu, in_node);
             const unsigned want_leaf = __ballot_sync(0xffffffffu, in_leaf);
             if ((want_node | want_leaf) == 0u) break;
-            if (!exhausted && (want_node | want_leaf) != 0xffffffffu) break;     // a lane idles and rays remain: refill
+            // refill once `refill_at` lanes idle and rays remain (rays fetched together start in lock step: their first
+            // node and leaf loads coalesce)
+            if (!exhausted && (uint32_t)__popc(~(want_node | want_leaf)) >= refill_at) break;
 
             if (__popc(want_node) >= __popc(want_leaf)) {
                 if (in_node) {                   // ---- node step: bvh.c:1153-1179
