@@ -51,3 +51,17 @@ for prec in (accel.PREC_F32, accel.PREC_F64):
     a.render_ao(fr)
     rgb, s = a.render_ao(fr)
     print(f"soup frame prec={prec}: total {s.ms_total:.2f} ms (primary {s.ms_primary:.2f}, ao {s.ms_ao:.2f}) rays {s.nrays} hits {s.nhits_primary} -> {s.nrays/s.ms_total/1e3:.1f} Mrays/s  mean {rgb.mean():.4f}")
+# C2: 100K-triangle soup, 1024x1024 coherent primary rays, closest hit (BASELINE configs[1])
+t2 = scenes.triangle_soup(100_000, scenes.SEED_C2)
+a2 = accel.Accel.bind().build(t2, accel.PREC_F32 | accel.PREC_F64)
+pr2 = torch.from_numpy(scenes.pinhole_rays(1024, 1024)).cuda(); ph2 = torch.empty((1 << 20, 4), dtype=torch.float32, device="cuda")
+ms = ev(lambda: a2.intersect_dev(pr2, 1 << 20, ph2, st.cuda_stream), reps=20); print(f"C2 closest f32 (100K tris, 1M primary rays) {ms:.3f} ms  {(1<<20)/ms/1e3:.1f} Mrays/s")
+c2cnt = a2.count(scenes.pinhole_rays(1024, 1024)); print("C2 counters", c2cnt, "bytes/ray", 32 + 16 + 64 * c2cnt["ninner"] / c2cnt["nrays"] + 48 * c2cnt["ntris"] / c2cnt["nrays"])
+pr2d = torch.from_numpy(scenes.rays_f32_to_f64(scenes.pinhole_rays(1024, 1024))).cuda(); ph2d = torch.empty((1 << 20, 4), dtype=torch.float64, device="cuda")
+ms = ev(lambda: a2.intersect_dev(pr2d, 1 << 20, ph2d, st.cuda_stream, f64=True), reps=20); print(f"C2 closest f64 {ms:.3f} ms  {(1<<20)/ms/1e3:.1f} Mrays/s")
+# C4: plane_sphere path trace, 256x256, 256 spp
+g4 = np.load("tests/golden/c4_scene.npz"); cam4 = g4["cam"]
+a4 = accel.Accel.bind().build(g4["tris"], accel.PREC_F64)
+pf = accel.make_path_frame(cam4[:16], cam4[16], bool(cam4[17]), 256, 256, spp=256, max_vertices=10, seed=11, kd=1.0, Le=1.0)
+a4.render_pathtrace(pf); rgb4, s4 = a4.render_pathtrace(pf)
+print(f"C4 pathtrace 256x256x256spp: {s4.ms_total:.2f} ms, {s4.nrays} rays -> {s4.nrays/s4.ms_total/1e3:.1f} Mrays/s mean {rgb4.mean():.4f}")
