@@ -69,7 +69,7 @@ struct ri_b200_accel {
     uint32_t *d_mt_polys = nullptr, *d_mt_states = nullptr;
     uint32_t  mt_states_cap = 0, mt_states_seed = 0;
     unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
-    unsigned work_slot = 0;
+    std::atomic<unsigned> work_slot{0};   // the _dev entry points may be called from several host threads / streams
     // single-ray path
     void *h_pin = nullptr, *d_one = nullptr;
     std::mutex mu;
@@ -208,7 +208,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             uint64_t want = ((uint64_t)m + chunk - 1) / chunk;             // one chunk per warp at least
             want = (want + (kBlock / 32) - 1) / (kBlock / 32);
             const unsigned blocks = (unsigned)(want < cap ? want : cap);
-            unsigned int *ctr = a->d_work + (a->work_slot++ & 63u);
+            unsigned int *ctr = a->d_work + (a->work_slot.fetch_add(1) & 63u);
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                            d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
