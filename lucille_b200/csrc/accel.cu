@@ -57,6 +57,7 @@ struct ri_b200_accel {
     cudaEvent_t  ev[8] = {};
     Node32 *d_nodes32 = nullptr; Tri32 *d_tris32 = nullptr;
     Node64 *d_nodes64 = nullptr; Tri64 *d_tris64 = nullptr;
+    Tri32 *d_tris32t = nullptr; Tri64 *d_tris64t = nullptr;   // leaf-transposed copies (pool.cuh)
     uint32_t *d_slot_of_prim = nullptr;
     double *d_nrm64 = nullptr; float *d_nrm32 = nullptr;     // optional vertex normals, [prim][9]
     uint64_t device_bytes = 0;
@@ -172,6 +173,10 @@ trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const
 }
 
 #include "persistent.cuh"
+#include "pool.cuh"
+
+static const char *pool_tris(const ri_b200_accel *a, float)  { return reinterpret_cast<const char *>(a->d_tris32t); }
+static const char *pool_tris(const ri_b200_accel *a, double) { return reinterpret_cast<const char *>(a->d_tris64t); }
 
 static int stack_capacity(const ri_b200_accel *a)
 {
@@ -191,10 +196,15 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
     if (!COUNT) {
         // production path: persistent warps with ray replacement; batches above 2^31 rays are split
         auto pk = trace_persistent_kernel<Real, ANYHIT>;
+        auto pool = occluded_pool_kernel<Real>;
+        static const bool use_pool = !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);   // A/B knob: 0 = vote-scheduled kernel
+        const bool pooled = ANYHIT && use_pool;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kBlock, smem));
+        if (pooled) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool, kBlock, smem));
+        else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kBlock, smem));
         if (per_sm < 1) return fail("persistent traversal kernel does not fit on an SM");
         const uint64_t kMax = 1ull << 31;
         for (uint64_t done = 0; done < n; done += kMax) {
@@ -210,9 +220,14 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             const unsigned blocks = (unsigned)(want < cap ? want : cap);
             unsigned int *ctr = a->d_work + (a->work_slot.fetch_add(1) & 63u);
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
-            pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
-                                           d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
-                                           d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, refill_at);
+            if (pooled)
+                pool<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
+                                                 d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,
+                                                 rays_per_count, ctr, refill_at);
+            else
+                pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
+                                               d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
+                                               d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, refill_at);
             LAUNCHED();
             CUDA_OK(cudaGetLastError());
         }
@@ -297,6 +312,8 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         if (upload(&a->d_tris32, a->flat.tris32, a->device_bytes)) return -1;
         if (upload(&a->d_nodes64, a->flat.nodes64, a->device_bytes)) return -1;
         if (upload(&a->d_tris64, a->flat.tris64, a->device_bytes)) return -1;
+        if (upload(&a->d_tris32t, a->flat.tris32t, a->device_bytes)) return -1;
+        if (upload(&a->d_tris64t, a->flat.tris64t, a->device_bytes)) return -1;
         if (upload(&a->d_slot_of_prim, a->flat.slot_of_prim, a->device_bytes)) return -1;
         CUDA_OK(cudaMalloc((void **)&a->d_counters, 8 * sizeof(unsigned long long)));
         CUDA_OK(cudaMalloc((void **)&a->d_work, 64 * sizeof(unsigned int)));
@@ -309,6 +326,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
     // flat host copies are no longer needed (keep the small header fields)
     std::vector<Node32>().swap(a->flat.nodes32); std::vector<Tri32>().swap(a->flat.tris32);
     std::vector<Node64>().swap(a->flat.nodes64); std::vector<Tri64>().swap(a->flat.tris64);
+    std::vector<Tri32>().swap(a->flat.tris32t); std::vector<Tri64>().swap(a->flat.tris64t);
     std::vector<uint32_t>().swap(a->flat.slot_of_prim);
     return a;
 }
@@ -319,7 +337,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
-    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32);
+    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     for (auto p : a->d_frame) cudaFree(p);
     cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work); cudaFree(a->d_mt_polys); cudaFree(a->d_mt_states);

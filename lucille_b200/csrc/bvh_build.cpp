@@ -503,6 +503,28 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
             if (want64) out.tris64[(size_t)slot].prim = 0xffffffffull;
         }
     }
+
+    // leaf-transposed copies for the pooled occlusion kernel
+    if (want32) out.tris32t.resize((size_t)nslots);
+    if (want64) out.tris64t.resize((size_t)nslots);
+    for (size_t c = 0; c < nn; ++c) {
+        const CanonNode &n = t.nodes[c];
+        if (!n.is_leaf) continue;
+        const uint64_t slot0 = slot_of[c], ns = (uint64_t)((n.ntris + 1) & ~1ll);
+        if (want32) {                                        // item = pair of slots = 3 chunks of 32 B
+            const uint64_t m = ns / 2;
+            const char *src = reinterpret_cast<const char *>(out.tris32.data() + slot0);
+            char *dst = reinterpret_cast<char *>(out.tris32t.data() + slot0);
+            for (uint64_t j = 0; j < m; ++j)
+                for (uint64_t k = 0; k < 3; ++k) std::memcpy(dst + (k * m + j) * 32, src + j * 96 + k * 32, 32);
+        }
+        if (want64) {                                        // item = one slot = 3 chunks of 32 B
+            const char *src = reinterpret_cast<const char *>(out.tris64.data() + slot0);
+            char *dst = reinterpret_cast<char *>(out.tris64t.data() + slot0);
+            for (uint64_t j = 0; j < ns; ++j)
+                for (uint64_t k = 0; k < 3; ++k) std::memcpy(dst + (k * ns + j) * 32, src + j * 96 + k * 32, 32);
+        }
+    }
 }
 
 }  // namespace b200

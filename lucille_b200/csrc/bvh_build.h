@@ -72,6 +72,11 @@ struct FlatTree {
     std::vector<Node64> nodes64;
     std::vector<Tri32>  tris32;      // nslots entries
     std::vector<Tri64>  tris64;
+    // the same slots, 32-byte chunks TRANSPOSED inside each leaf (pooled occlusion kernel, pool.cuh): a leaf at slot0
+    // with m items (fp32: m = pairs of slots, fp64: m = slots) keeps chunk k of item j at byte
+    // slot0 * sizeof(slot) + (k * m + j) * 32, so lanes testing consecutive items read consecutive 32-byte chunks
+    std::vector<Tri32>  tris32t;
+    std::vector<Tri64>  tris64t;
     uint64_t nslots = 0;
     std::vector<uint32_t> slot_of_prim;   // post-build triangle position -> slot
     float  smin32[3], smax32[3];

@@ -1,0 +1,214 @@
+// Pooled occlusion (any-hit) traverser: the production kernel for ri_b200_occluded_* and the AO transport.
+//
+// The persistent kernel of persistent.cuh gives every lane one ray and lets the warp vote between a node step and a leaf
+// step; with the reference's tree (leaves of up to 16 triangles) a ray spends as long inside leaves as between them, so
+// each step runs with about half of the lanes.  Here a lane still OWNS one ray and walks the inner nodes for it, but the
+// triangle tests of all the leaves the warp is standing in are POOLED: every leaf contributes its remaining test items
+// (fp32: a pair of triangle slots, fp64: one slot), a warp prefix sum numbers them, and a leaf round hands 32 consecutive
+// items to the 32 lanes -- lane g finds the owner of item g by binary search over the prefix sums (__shfl_sync), fetches
+// the owner's ray with shuffles, tests its item and the owners read the verdicts back from one __ballot_sync.  A leaf
+// round therefore runs with 32 lanes whenever 32 items are waiting, and node steps run with every lane that is not
+// waiting for a leaf.
+//
+// Why this is still the reference's answer, bit for bit: an occlusion query returns `bvh_traverse(...) != 0`
+// (bvh.c:1187), i.e. whether ANY visited leaf holds a triangle that triangle_isect accepts with t < 1e38.  Before the
+// first acceptance the closest-so-far values are their initial 1e38 (bvh.c:1114, 833), so every box test and every
+// triangle test of the query is evaluated against the same constants in whatever order it happens: the set of leaves
+// reached, each per-triangle verdict and hence the OR are order-independent.  Each lane performs its ray's node steps in
+// the reference's order with the reference's arithmetic (slab_mm / tri_test_bf of trace.cuh); only the triangle tests of
+// one leaf are spread over several lanes.  (A NaN t, the one value that makes `t > t_leaf` order-dependent inside a leaf,
+// can only turn a later rejection `t > 1e38` into an acceptance with t >= 1e38, which does not commit: bvh.c:850.)
+//
+// Memory: node records as in persistent.cuh (2 x LDG.256 per node).  Triangles come from the leaf-TRANSPOSED copy
+// (FlatTree::tris32t / tris64t): chunk k of item j of a leaf with m items sits at slot0*sizeof(slot) + (k*m + j)*32, so
+// the lanes that test consecutive items of one leaf read consecutive 32-byte chunks -- one L1 wavefront per 128-byte
+// line instead of one per lane.
+#pragma once
+
+namespace b200 {
+
+template <typename Real> struct PoolLeaf;
+
+template <> struct PoolLeaf<float> {                 // item = two triangle slots (96 B = 3 chunks)
+    static __device__ __forceinline__ uint32_t items(uint32_t ntris) { return (ntris + 1u) >> 1; }
+    static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
+                                                const float org[3], const float dir[3])
+    {
+        const uint32_t m = (ntris + 1u) >> 1;
+        const char *c = trisT + (size_t)slot0 * sizeof(Tri32) + (size_t)j * 32u;
+        const size_t stride = (size_t)m * 32u;
+        const F8 q0 = ldg256(c), q1 = ldg256(c + stride), q2 = ldg256(c + 2 * stride);
+        TriRegs<float> a, b;
+        a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = 0;
+        a.e1[0] = q0.v[4]; a.e1[1] = q0.v[5]; a.e1[2] = q0.v[6];
+        a.e2[0] = q1.v[0]; a.e2[1] = q1.v[1]; a.e2[2] = q1.v[2];
+        b.v0[0] = q1.v[4]; b.v0[1] = q1.v[5]; b.v0[2] = q1.v[6]; b.prim = 0;
+        b.e1[0] = q2.v[0]; b.e1[1] = q2.v[1]; b.e1[2] = q2.v[2];
+        b.e2[0] = q2.v[4]; b.e2[1] = q2.v[5]; b.e2[2] = q2.v[6];
+        float tl = Prec<float>::inf(), ul = 0.0f, vl = 0.0f;
+        uint32_t tprim = 0xffffffffu;
+        tri_test_bf<float>(a, org, dir, true, tl, ul, vl, tprim);
+        tri_test_bf<float>(b, org, dir, 2u * j + 1u < ntris, tl, ul, vl, tprim);
+        return tl < Prec<float>::inf();
+    }
+};
+
+template <> struct PoolLeaf<double> {                // item = one triangle slot (96 B = 3 chunks)
+    static __device__ __forceinline__ uint32_t items(uint32_t ntris) { return ntris; }
+    static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
+                                                const double org[3], const double dir[3])
+    {
+        const uint32_t m = (ntris + 1u) & ~1u;       // slots owned by the leaf
+        const char *c = trisT + (size_t)slot0 * sizeof(Tri64) + (size_t)j * 32u;
+        const size_t stride = (size_t)m * 32u;
+        const D4 q0 = ldg256d(c), q1 = ldg256d(c + stride), q2 = ldg256d(c + 2 * stride);
+        TriRegs<double> a;
+        a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = 0;
+        a.e1[0] = q1.v[0]; a.e1[1] = q1.v[1]; a.e1[2] = q1.v[2];
+        a.e2[0] = q2.v[0]; a.e2[1] = q2.v[1]; a.e2[2] = q2.v[2];
+        double tl = Prec<double>::inf(), ul = 0.0, vl = 0.0;
+        uint32_t tprim = 0xffffffffu;
+        tri_test_bf<double>(a, org, dir, true, tl, ul, vl, tprim);
+        return tl < Prec<double>::inf();
+    }
+};
+
+__device__ __forceinline__ float  shfl_real(float v, unsigned src)  { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_real(double v, unsigned src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <typename Real>
+__global__ void __launch_bounds__(kBlock, sizeof(Real) == 4 ? 4 : 3)
+occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
+                     const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
+                     unsigned int *__restrict__ work_counter, const uint32_t refill_at)
+{
+    using P = Prec<Real>;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ uint32_t s_stack[];
+    uint32_t *stk = s_stack + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
+    bool exhausted = false;                      // warp-uniform
+
+    // per-lane ray state.  cur: kIdle | inner-node index | leaf word; prog: items of that leaf already tested
+    uint32_t cur = kIdle, prog = 0, idx = 0, sp = 0;
+    Real org[3], dir[3], inv[3];
+    bool sx = false, sy = false, sz = false;
+    org[0] = org[1] = org[2] = dir[0] = dir[1] = dir[2] = inv[0] = inv[1] = inv[2] = Real(0);
+
+    auto retire = [&](const bool hit) {
+        if (counts) { if (hit) atomicAdd(&counts[idx / rays_per_count], 1u); }
+        else occ[idx] = hit ? 1 : 0;
+    };
+
+    for (;;) {
+        // ------------------------------------------------------------------ fetch (as in persistent.cuh)
+        unsigned idle = __ballot_sync(FULL, cur == kIdle);
+        while (idle && !exhausted) {
+            if (chunk_next >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; break; }
+                chunk_next = base;
+                chunk_end = (n - base < chunk) ? n : base + chunk;
+            }
+            const unsigned avail = chunk_end - chunk_next;
+            const unsigned n_idle = __popc(idle);
+            const unsigned take = n_idle < avail ? n_idle : avail;
+            const unsigned rank = __popc(idle & lt_mask);
+            if (cur == kIdle && rank < take) {
+                idx = chunk_next + rank;
+                RayIO<Real>::load(rays, idx, org, dir);
+                sx = dir[0] < Real(0); sy = dir[1] < Real(0); sz = dir[2] < Real(0);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)      // bvh.c:473-497
+                    inv[k] = (P::rabs(dir[k]) > P::eps()) ? Real(1) / dir[k] : ((dir[k] < Real(0)) ? -P::vmax() : P::vmax());
+                Real tmin;
+                const bool in_scene = (S.root_word != kDoneWord) &&
+                    slab<Real>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
+                sp = 0; prog = 0;
+                if (in_scene) cur = S.root_word;
+                else retire(false);              // bvh.c:446 / 522-526: miss without traversal
+            }
+            chunk_next += take;
+            idle = __ballot_sync(FULL, cur == kIdle);
+        }
+        if (idle == FULL) break;                 // nothing in flight and nothing left to fetch
+
+        // ------------------------------------------------------------------ traverse
+        for (;;) {
+            const bool in_leaf = (cur & kLeafFlag) != 0u;
+            const bool in_node = !in_leaf && (cur != kIdle);
+            const uint32_t ntris = ((cur >> kLeafShift) & 15u) + 1u;
+            const uint32_t nitems = PoolLeaf<Real>::items(ntris);
+            const uint32_t cnt = in_leaf ? nitems - prog : 0u;        // >= 1 for a lane standing in a leaf
+            const uint32_t total = __reduce_add_sync(FULL, cnt);
+            const unsigned n_node = __popc(__ballot_sync(FULL, in_node));
+            if (n_node == 0u && total == 0u) break;
+            if (!exhausted && (uint32_t)__popc(__ballot_sync(FULL, cur == kIdle)) >= refill_at) break;
+
+            if (total >= 32u || total > n_node) {
+                // ---- leaf round: items 0..31 of the pool, one per lane
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= (unsigned)o) incl += up;
+                }
+                const uint32_t excl = incl - cnt;
+                uint32_t own = 0;                                     // first lane whose inclusive sum exceeds my item number
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t v = __shfl_sync(FULL, incl, own + step - 1);
+                    if (v <= lane) own += step;
+                }
+                const bool have = lane < total;
+                own = have ? own : lane;
+                const uint32_t oword = __shfl_sync(FULL, cur, own);
+                const uint32_t ofirst = __shfl_sync(FULL, prog - excl, own);   // item number inside the leaf = lane + ofirst (mod 2^32)
+                Real oorg[3], odir[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { oorg[k] = shfl_real(org[k], own); odir[k] = shfl_real(dir[k], own); }
+                bool hit = false;
+                if (have)
+                    hit = PoolLeaf<Real>::test(trisT, oword & kSlotMask, ((oword >> kLeafShift) & 15u) + 1u, lane + ofirst, oorg, odir);
+                const unsigned hits = __ballot_sync(FULL, hit);
+                if (in_leaf && excl < 32u) {                          // my leaf had items in this round
+                    const uint32_t took = (cnt < 32u - excl) ? cnt : 32u - excl;
+                    const unsigned mine = ((took >= 32u) ? FULL : ((1u << took) - 1u)) << excl;
+                    if (hits & mine) { retire(true); cur = kIdle; }   // occluded: bvh.c:850 commits, the query is decided
+                    else {
+                        prog += took;
+                        if (prog == nitems) {                         // leaf exhausted without a hit: pop, or the ray escapes
+                            prog = 0;
+                            if (sp == 0u) { retire(false); cur = kIdle; }
+                            else { --sp; cur = stk[sp * kBlock]; }
+                        }
+                    }
+                }
+            } else if (in_node) {
+                // ---- node step: bvh.c:1153-1179 with best_t == 1e38 (no hit yet)
+                NodeRegs<Real> nd;
+                load_node_wide(S.nodes + cur, nd);
+                const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, P::inf());
+                const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, P::inf());
+                const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);     // near child = child[sign[axis0]]
+                const bool both = h0 && h1, none = !h0 && !h1;
+                const bool pop = none && (sp != 0u);
+                if (both) stk[sp * kBlock] = order ? nd.c0 : nd.c1;
+                const uint32_t popped = pop ? stk[(sp - 1u) * kBlock] : kIdle;
+                sp = sp + (both ? 1u : 0u) - (pop ? 1u : 0u);
+                const uint32_t one = h0 ? nd.c0 : nd.c1;
+                const uint32_t next = both ? (order ? nd.c1 : nd.c0) : (none ? popped : one);
+                if (next == kIdle) retire(false);                     // stack ran dry
+                prog = 0;
+                cur = next;
+            }
+        }
+    }
+}
+
+}  // namespace b200
