@@ -201,9 +201,10 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         const bool pooled = ANYHIT && use_pool;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t pool_smem = pool_smem_bytes<Real>(cap);
+        if (pool_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem));
         int per_sm = 0;
-        if (pooled) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool, kBlock, smem));
+        if (pooled) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool, kBlock, pool_smem));
         else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kBlock, smem));
         if (per_sm < 1) return fail("persistent traversal kernel does not fit on an SM");
         const uint64_t kMax = 1ull << 31;
@@ -221,9 +222,9 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             unsigned int *ctr = a->d_work + (a->work_slot.fetch_add(1) & 63u);
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             if (pooled)
-                pool<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
-                                                 d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,
-                                                 rays_per_count, ctr, refill_at);
+                pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
+                                                      d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,
+                                                      rays_per_count, ctr, refill_at, (uint32_t)stack_capacity(a));
             else
                 pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,

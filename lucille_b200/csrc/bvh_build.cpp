@@ -517,6 +517,12 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
             char *dst = reinterpret_cast<char *>(out.tris32t.data() + slot0);
             for (uint64_t j = 0; j < m; ++j)
                 for (uint64_t k = 0; k < 3; ++k) std::memcpy(dst + (k * m + j) * 32, src + j * 96 + k * 32, 32);
+            if (n.ntris & 1) {
+                // the filler slot is masked by its item's validity bit, never by its determinant: give it unit edges so
+                // that 1/det stays on the fast path of the reciprocal (a zero determinant takes the slow one)
+                float *e = reinterpret_cast<float *>(dst + (2 * m + (m - 1)) * 32);
+                e[0] = 1.0f; e[5] = 1.0f;                    // b.e1 = (1,0,0), b.e2 = (0,1,0)
+            }
         }
         if (want64) {                                        // item = one slot = 3 chunks of 32 B
             const char *src = reinterpret_cast<const char *>(out.tris64.data() + slot0);

@@ -30,6 +30,7 @@ namespace b200 {
 template <typename Real> struct PoolLeaf;
 
 template <> struct PoolLeaf<float> {                 // item = two triangle slots (96 B = 3 chunks)
+    static constexpr int kCntBits = 4;               // items per leaf <= 8
     static __device__ __forceinline__ uint32_t items(uint32_t ntris) { return (ntris + 1u) >> 1; }
     static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
                                                 const float org[3], const float dir[3])
@@ -54,6 +55,7 @@ template <> struct PoolLeaf<float> {                 // item = two triangle slot
 };
 
 template <> struct PoolLeaf<double> {                // item = one triangle slot (96 B = 3 chunks)
+    static constexpr int kCntBits = 5;               // items per leaf <= 16
     static __device__ __forceinline__ uint32_t items(uint32_t ntris) { return ntris; }
     static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
                                                 const double org[3], const double dir[3])
@@ -73,21 +75,54 @@ template <> struct PoolLeaf<double> {                // item = one triangle slot
     }
 };
 
-__device__ __forceinline__ float  shfl_real(float v, unsigned src)  { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ double shfl_real(double v, unsigned src) { return __shfl_sync(0xffffffffu, v, src); }
+// a lane's ray (org, dir) in shared memory, where the lanes that test its leaf items pick it up
+template <typename Real> struct RaySlot;
+template <> struct RaySlot<float> {
+    static constexpr uint32_t kBytes = 32;
+    static __device__ __forceinline__ void store(char *base, unsigned slot, const float org[3], const float dir[3])
+    {
+        float4 *p = reinterpret_cast<float4 *>(base + slot * kBytes);
+        p[0] = make_float4(org[0], org[1], org[2], 0.0f); p[1] = make_float4(dir[0], dir[1], dir[2], 0.0f);
+    }
+    static __device__ __forceinline__ void load(const char *base, unsigned slot, float org[3], float dir[3])
+    {
+        const float4 *p = reinterpret_cast<const float4 *>(base + slot * kBytes);
+        const float4 a = p[0], b = p[1];
+        org[0] = a.x; org[1] = a.y; org[2] = a.z; dir[0] = b.x; dir[1] = b.y; dir[2] = b.z;
+    }
+};
+template <> struct RaySlot<double> {
+    static constexpr uint32_t kBytes = 48;
+    static __device__ __forceinline__ void store(char *base, unsigned slot, const double org[3], const double dir[3])
+    {
+        double2 *p = reinterpret_cast<double2 *>(base + slot * kBytes);
+        p[0] = make_double2(org[0], org[1]); p[1] = make_double2(org[2], dir[0]); p[2] = make_double2(dir[1], dir[2]);
+    }
+    static __device__ __forceinline__ void load(const char *base, unsigned slot, double org[3], double dir[3])
+    {
+        const double2 *p = reinterpret_cast<const double2 *>(base + slot * kBytes);
+        const double2 a = p[0], b = p[1], c = p[2];
+        org[0] = a.x; org[1] = a.y; org[2] = b.x; dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
+    }
+};
+template <typename Real> constexpr size_t pool_smem_bytes(int stack_cap)
+{ return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2)); }
 
 template <typename Real>
 __global__ void __launch_bounds__(kBlock, sizeof(Real) == 4 ? 4 : 3)
 occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
                      const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
-                     unsigned int *__restrict__ work_counter, const uint32_t refill_at)
+                     unsigned int *__restrict__ work_counter, const uint32_t refill_at, const uint32_t stack_cap)
 {
     using P = Prec<Real>;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ uint32_t s_stack[];
+    extern __shared__ __align__(16) uint32_t s_stack[];          // [stack_cap][kBlock] words, then ray slots, then descriptors
     uint32_t *stk = s_stack + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
+    char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kBlock);
+    char *s_rays = s_tail + (size_t)(threadIdx.x & ~31u) * RaySlot<Real>::kBytes;              // this warp's 32 ray slots
+    uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<Real>::kBytes) + (threadIdx.x & ~31u);
 
     uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
     bool exhausted = false;                      // warp-uniform
@@ -122,6 +157,7 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             if (cur == kIdle && rank < take) {
                 idx = chunk_next + rank;
                 RayIO<Real>::load(rays, idx, org, dir);
+                RaySlot<Real>::store(s_rays, lane, org, dir);
                 sx = dir[0] < Real(0); sy = dir[1] < Real(0); sz = dir[2] < Real(0);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)      // bvh.c:473-497
@@ -141,42 +177,39 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
         // ------------------------------------------------------------------ traverse
         for (;;) {
             const bool in_leaf = (cur & kLeafFlag) != 0u;
-            const bool in_node = !in_leaf && (cur != kIdle);
             const uint32_t ntris = ((cur >> kLeafShift) & 15u) + 1u;
             const uint32_t nitems = PoolLeaf<Real>::items(ntris);
             const uint32_t cnt = in_leaf ? nitems - prog : 0u;        // >= 1 for a lane standing in a leaf
             const uint32_t total = __reduce_add_sync(FULL, cnt);
-            const unsigned n_node = __popc(__ballot_sync(FULL, in_node));
+            const unsigned n_node = __popc(__ballot_sync(FULL, !in_leaf && cur != kIdle));
             if (n_node == 0u && total == 0u) break;
             if (!exhausted && (uint32_t)__popc(__ballot_sync(FULL, cur == kIdle)) >= refill_at) break;
 
             if (total >= 32u || total > n_node) {
-                // ---- leaf round: items 0..31 of the pool, one per lane
-                uint32_t incl = cnt;
+                // ---- leaf round: items 0..31 of the pool, one per lane.
+                // exclusive prefix sum of cnt (<= 16) from bit-sliced ballots: no dependent shuffle chain
+                uint32_t excl = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t up = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= (unsigned)o) incl += up;
-                }
-                const uint32_t excl = incl - cnt;
-                uint32_t own = 0;                                     // first lane whose inclusive sum exceeds my item number
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const uint32_t v = __shfl_sync(FULL, incl, own + step - 1);
-                    if (v <= lane) own += step;
-                }
+                for (int b = 0; b < PoolLeaf<Real>::kCntBits; ++b)
+                    excl += (uint32_t)__popc(__ballot_sync(FULL, (cnt >> b) & 1u) & lt_mask) << b;
+                const bool owner = in_leaf && excl < 32u;             // my leaf has items in this round
+                // bit e of `starts` = an owner's first item is item e; owners publish a descriptor under their ordinal
+                const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);
+                const unsigned owners = __ballot_sync(FULL, in_leaf);
+                if (owner) s_desc[__popc(owners & lt_mask)] = make_uint2(cur, lane | ((prog - excl + 64u) << 8));
+                __syncwarp();
                 const bool have = lane < total;
-                own = have ? own : lane;
-                const uint32_t oword = __shfl_sync(FULL, cur, own);
-                const uint32_t ofirst = __shfl_sync(FULL, prog - excl, own);   // item number inside the leaf = lane + ofirst (mod 2^32)
-                Real oorg[3], odir[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { oorg[k] = shfl_real(org[k], own); odir[k] = shfl_real(dir[k], own); }
                 bool hit = false;
-                if (have)
-                    hit = PoolLeaf<Real>::test(trisT, oword & kSlotMask, ((oword >> kLeafShift) & 15u) + 1u, lane + ofirst, oorg, odir);
+                if (have) {
+                    const uint2 d = s_desc[__popc(starts & ((2u << lane) - 1u)) - 1u];
+                    const unsigned own = d.y & 31u;
+                    const uint32_t item = lane + (d.y >> 8) - 64u;    // item number inside the owner's leaf
+                    Real oorg[3], odir[3];
+                    RaySlot<Real>::load(s_rays, own, oorg, odir);
+                    hit = PoolLeaf<Real>::test(trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir);
+                }
                 const unsigned hits = __ballot_sync(FULL, hit);
-                if (in_leaf && excl < 32u) {                          // my leaf had items in this round
+                if (owner) {
                     const uint32_t took = (cnt < 32u - excl) ? cnt : 32u - excl;
                     const unsigned mine = ((took >= 32u) ? FULL : ((1u << took) - 1u)) << excl;
                     if (hits & mine) { retire(true); cur = kIdle; }   // occluded: bvh.c:850 commits, the query is decided
@@ -189,7 +222,8 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                         }
                     }
                 }
-            } else if (in_node) {
+            }
+            if (!(cur & kLeafFlag) && cur != kIdle) {
                 // ---- node step: bvh.c:1153-1179 with best_t == 1e38 (no hit yet)
                 NodeRegs<Real> nd;
                 load_node_wide(S.nodes + cur, nd);
