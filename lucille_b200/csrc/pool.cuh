@@ -36,9 +36,8 @@ template <> struct PoolLeaf<float> {                 // item = two triangle slot
                                                 const float org[3], const float dir[3])
     {
         const uint32_t m = (ntris + 1u) >> 1;
-        const char *c = trisT + (size_t)slot0 * sizeof(Tri32) + (size_t)j * 32u;
-        const size_t stride = (size_t)m * 32u;
-        const F8 q0 = ldg256(c), q1 = ldg256(c + stride), q2 = ldg256(c + 2 * stride);
+        const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = o1 + 2u * m;      // 16-byte units: < 2^29
+        const F8 q0 = ldg256(trisT + (size_t)o0 * 16u), q1 = ldg256(trisT + (size_t)o1 * 16u), q2 = ldg256(trisT + (size_t)o2 * 16u);
         TriRegs<float> a, b;
         a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = 0;
         a.e1[0] = q0.v[4]; a.e1[1] = q0.v[5]; a.e1[2] = q0.v[6];
@@ -61,9 +60,8 @@ template <> struct PoolLeaf<double> {                // item = one triangle slot
                                                 const double org[3], const double dir[3])
     {
         const uint32_t m = (ntris + 1u) & ~1u;       // slots owned by the leaf
-        const char *c = trisT + (size_t)slot0 * sizeof(Tri64) + (size_t)j * 32u;
-        const size_t stride = (size_t)m * 32u;
-        const D4 q0 = ldg256d(c), q1 = ldg256d(c + stride), q2 = ldg256d(c + 2 * stride);
+        const uint32_t o0 = slot0 * 3u + j, o1 = o0 + m, o2 = o1 + m;                       // 32-byte units: < 2^29
+        const D4 q0 = ldg256d(trisT + (size_t)o0 * 32u), q1 = ldg256d(trisT + (size_t)o1 * 32u), q2 = ldg256d(trisT + (size_t)o2 * 32u);
         TriRegs<double> a;
         a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = 0;
         a.e1[0] = q1.v[0]; a.e1[1] = q1.v[1]; a.e1[2] = q1.v[2];
@@ -119,7 +117,7 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
     extern __shared__ __align__(16) uint32_t s_stack[];          // [stack_cap][kBlock] words, then ray slots, then descriptors
     uint32_t *stk = s_stack + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
     char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kBlock);
     char *s_rays = s_tail + (size_t)(threadIdx.x & ~31u) * RaySlot<Real>::kBytes;              // this warp's 32 ray slots
     uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<Real>::kBytes) + (threadIdx.x & ~31u);
@@ -181,9 +179,10 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             const uint32_t nitems = PoolLeaf<Real>::items(ntris);
             const uint32_t cnt = in_leaf ? nitems - prog : 0u;        // >= 1 for a lane standing in a leaf
             const uint32_t total = __reduce_add_sync(FULL, cnt);
-            const unsigned n_node = __popc(__ballot_sync(FULL, !in_leaf && cur != kIdle));
+            const unsigned owners = __ballot_sync(FULL, in_leaf);
+            const unsigned n_node = __popc(__ballot_sync(FULL, cur < kIdle));     // inner-node indices are < kIdle, leaf words above
             if (n_node == 0u && total == 0u) break;
-            if (!exhausted && (uint32_t)__popc(__ballot_sync(FULL, cur == kIdle)) >= refill_at) break;
+            if (!exhausted && 32u - n_node - (uint32_t)__popc(owners) >= refill_at) break;
 
             if (total >= 32u || total > n_node) {
                 // ---- leaf round: items 0..31 of the pool, one per lane.
@@ -191,17 +190,16 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                 uint32_t excl = 0;
 #pragma unroll
                 for (int b = 0; b < PoolLeaf<Real>::kCntBits; ++b)
-                    excl += (uint32_t)__popc(__ballot_sync(FULL, (cnt >> b) & 1u) & lt_mask) << b;
+                    excl += (uint32_t)__popc(__ballot_sync(FULL, (cnt & (1u << b)) != 0u) & lt_mask) << b;
                 const bool owner = in_leaf && excl < 32u;             // my leaf has items in this round
                 // bit e of `starts` = an owner's first item is item e; owners publish a descriptor under their ordinal
                 const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);
-                const unsigned owners = __ballot_sync(FULL, in_leaf);
                 if (owner) s_desc[__popc(owners & lt_mask)] = make_uint2(cur, lane | ((prog - excl + 64u) << 8));
                 __syncwarp();
                 const bool have = lane < total;
                 bool hit = false;
                 if (have) {
-                    const uint2 d = s_desc[__popc(starts & ((2u << lane) - 1u)) - 1u];
+                    const uint2 d = s_desc[__popc(starts & le_mask) - 1u];
                     const unsigned own = d.y & 31u;
                     const uint32_t item = lane + (d.y >> 8) - 64u;    // item number inside the owner's leaf
                     Real oorg[3], odir[3];
@@ -223,7 +221,7 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                     }
                 }
             }
-            if (!(cur & kLeafFlag) && cur != kIdle) {
+            if (cur < kIdle) {
                 // ---- node step: bvh.c:1153-1179 with best_t == 1e38 (no hit yet)
                 NodeRegs<Real> nd;
                 load_node_wide(S.nodes + cur, nd);

@@ -6,5 +6,5 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py --impl reference --steps 3 --warmup 3 2> gpurun_out/bench_ref.err | tee gpurun_out/bench_ref.json
 python bench.py --steps 10 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:trace_persistent -s 2 -c 1 -o gpurun_out/prof_bench python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:occluded_pool -s 2 -c 1 -o gpurun_out/prof_bench python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
