@@ -103,6 +103,14 @@ template <> struct RaySlot<double> {
         org[0] = a.x; org[1] = a.y; org[2] = b.x; dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
     }
 };
+// __ballot_sync(full, (x & bit) != 0) pinned to LOP3-with-predicate + VOTE (the compiler's own form is shift, and, compare, vote)
+__device__ __forceinline__ unsigned ballot_bit(uint32_t x, uint32_t bit)
+{
+    unsigned r;
+    asm volatile("{ .reg .pred p; .reg .b32 t; and.b32 t, %1, %2; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; }"
+                 : "=r"(r) : "r"(x), "r"(bit));
+    return r;
+}
 template <typename Real> constexpr size_t pool_smem_bytes(int stack_cap)
 { return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2)); }
 
@@ -190,7 +198,7 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                 uint32_t excl = 0;
 #pragma unroll
                 for (int b = 0; b < PoolLeaf<Real>::kCntBits; ++b)
-                    excl += (uint32_t)__popc(__ballot_sync(FULL, (cnt & (1u << b)) != 0u) & lt_mask) << b;
+                    excl += (uint32_t)__popc(ballot_bit(cnt, 1u << b) & lt_mask) << b;
                 const bool owner = in_leaf && excl < 32u;             // my leaf has items in this round
                 // bit e of `starts` = an owner's first item is item e; owners publish a descriptor under their ordinal
                 const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);

@@ -708,6 +708,197 @@ void orc_render_ao(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ sun-sky gather (row a12) */
+
+/* sunsky.c:24-38.  All variables are float, the libm calls are the double ones: every `sin(x)` promotes its float argument
+ * and every assignment rounds the double expression once. */
+static float sky_angle_between(float v_theta, float v_phi, float s_theta, float s_phi)
+{
+    float cospi = sin(v_theta) * sin(s_theta) * cos(s_phi - v_phi) + cos(v_theta) * cos(s_theta);
+    if (cospi > 1.0) return 0.0;
+    if (cospi < -1.0) return M_PI;
+    return acos(cospi);
+}
+
+/* sunsky.c:136-152 */
+static float sky_perez(const float *lam, float theta, float gamma, float lvz, float sun_theta)
+{
+    float den, num;
+    den = ((1.0 + lam[0] * exp(lam[1])) *
+           (1.0 + lam[2] * exp(lam[3] * sun_theta) + lam[4] * cos(sun_theta) * cos(sun_theta)));
+    num = ((1.0 + lam[0] * exp(lam[1] / cos(theta))) *
+           (1.0 + lam[2] * exp(lam[3] * gamma) + lam[4] * cos(gamma) * cos(gamma)));
+    return lvz * num / den;
+}
+
+/* specrend.c:366-440 (the float* overload): 81 five-nanometre bins, each 10 nm sample used twice, float accumulation */
+static void sky_spectrum_to_xyz(const orc_sunsky_t *s, const float *spectrum, float *x, float *y, float *z)
+{
+    int i;
+    float lambda, X = 0, Y = 0, Z = 0;
+    for (i = 0, lambda = 380; lambda < 780.1; i++, lambda += 5) {
+        X += spectrum[i / 2] * s->cie[i][0];
+        Y += spectrum[i / 2] * s->cie[i][1];
+        Z += spectrum[i / 2] * s->cie[i][2];
+    }
+    *x = X; *y = Y; *z = Z;
+}
+
+/* specrend.c:127-172 */
+static void sky_xyz_to_rgb(const float *cs, float xc, float yc, float zc, float *r, float *g, float *b)
+{
+    float xr, yr, zr, xg, yg, zg, xb, yb, zb, xw, yw, zw;
+    float rx, ry, rz, gx, gy, gz, bx, by, bz, rw, gw, bw;
+    xr = cs[0]; yr = cs[1]; zr = 1 - (xr + yr);
+    xg = cs[2]; yg = cs[3]; zg = 1 - (xg + yg);
+    xb = cs[4]; yb = cs[5]; zb = 1 - (xb + yb);
+    xw = cs[6]; yw = cs[7]; zw = 1 - (xw + yw);
+    rx = (yg * zb) - (yb * zg); ry = (xb * zg) - (xg * zb); rz = (xg * yb) - (xb * yg);
+    gx = (yb * zr) - (yr * zb); gy = (xr * zb) - (xb * zr); gz = (xb * yr) - (xr * yb);
+    bx = (yr * zg) - (yg * zr); by = (xg * zr) - (xr * zg); bz = (xr * yg) - (xg * yr);
+    if (fabs(yw) > 1.0e-48) {
+        rw = ((rx * xw) + (ry * yw) + (rz * zw)) / yw;
+        gw = ((gx * xw) + (gy * yw) + (gz * zw)) / yw;
+        bw = ((bx * xw) + (by * yw) + (bz * zw)) / yw;
+    } else {
+        rw = 1.0; gw = 1.0; bw = 1.0;
+    }
+    rx = rx / rw; ry = ry / rw; rz = rz / rw;
+    gx = gx / gw; gy = gy / gw; gz = gz / gw;
+    bx = bx / bw; by = by / bw; bz = bz / bw;
+    *r = (rx * xc) + (ry * yc) + (rz * zc);
+    *g = (gx * xc) + (gy * yc) + (gz * zc);
+    *b = (bx * xc) + (by * yc) + (bz * zc);
+}
+
+/* sunsky.c:322-408: ri_sunsky_get_sky_spectrum + ri_sunsky_get_sky_rgb (y and z swapped on entry, :337-339) */
+static void sky_rgb(const orc_sunsky_t *s, const float v[3], float rgb[3])
+{
+    float spec[41];
+    float theta, phi, vlen, gamma, x, y, Y, lx, ly, lz, t[3], M1, M2, X, Yc, Z;
+    int i;
+    t[0] = v[0]; t[1] = v[2]; t[2] = v[1];
+    if (t[2] < 0.0) {                                         /* under the horizon: zero spectrum */
+        for (i = 0; i < 41; i++) spec[i] = 0.0f;
+    } else {
+        if (t[2] < 0.001) {
+            t[2] = 0.001;
+            vlen = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+            t[0] /= vlen; t[1] /= vlen; t[2] /= vlen;
+        }
+        theta = acos(t[2]);
+        if (fabs(theta) < 1.0e-6) phi = 0.0; else phi = atan2(t[1], t[0]);
+        gamma = sky_angle_between(theta, phi, s->sun_theta, s->sun_phi);
+        x = sky_perez(s->perez_x, theta, gamma, s->zenith_x, s->sun_theta);
+        y = sky_perez(s->perez_y, theta, gamma, s->zenith_y, s->sun_theta);
+        Y = sky_perez(s->perez_Y, theta, gamma, s->zenith_Y, s->sun_theta);
+        /* chromaticity_to_spectrum, sunsky.c:297-314 */
+        M1 = (-1.3515 - 1.7703 * x + 5.9114 * y) / (0.0241 + 0.2562 * x - 0.7341 * y);
+        M2 = (0.03 - 31.4424 * x + 30.0717 * y) / (0.0241 + 0.2562 * x - 0.7341 * y);
+        for (i = 0; i < 41; i++) spec[i] = s->S0[i] + M1 * s->S1[i] + M2 * s->S2[i];
+        sky_spectrum_to_xyz(s, spec, &lx, &ly, &lz);
+        if (fabs(ly) < 1.0e-48) ly = 1.0;
+        for (i = 0; i < 41; i++) spec[i] = Y * spec[i] / ly;
+    }
+    sky_spectrum_to_xyz(s, spec, &X, &Yc, &Z);
+    sky_xyz_to_rgb(s->cs, X, Yc, Z, &rgb[0], &rgb[1], &rgb[2]);
+}
+
+void orc_sunsky_sky_rgb(const orc_sunsky_t *s, const float *dirs, uint64_t n, float *rgb)
+{
+    uint64_t i;
+    for (i = 0; i < n; i++) sky_rgb(s, dirs + 3 * i, rgb + 3 * i);
+}
+
+/* ambientocclusion.c:206-324 gather_sunsky(8, 8) + 153-199 contribution_from_sunlight */
+static void sunsky_radiance(const orc_tree *T, const view_t_f64 *V, const orc_state_f64 *st, const orc_sunsky_t *s,
+                            mt_t *rng, uint64_t *nrays, double Lo[3])
+{
+    const uint32_t ntheta = 8, nphi = 8;
+    const double eps = 1.0e-5;
+    double basis[3][3], org[3], dirl[3], dir[3], col[3] = {0.0, 0.0, 0.0};
+    double t, u, v, nsamples, m;
+    uint32_t prim, i, j;
+    int k, l;
+
+    ortho_basis_f64(basis, st->Ns);
+    for (k = 0; k < 3; k++) org[k] = st->P[k];
+    for (k = 0; k < 3; k++) org[k] += st->Ns[k] * eps;
+    for (j = 0; j < nphi; j++) {
+        for (i = 0; i < ntheta; i++) {
+            double z0 = (i + mt_next(rng)) / (double)ntheta;
+            double z1 = (j + mt_next(rng)) / (double)nphi;
+            double cos_theta = sqrt(z0);
+            double phi = 2.0 * M_PI * z1;
+            dirl[0] = cos(phi) * cos_theta;
+            dirl[1] = sin(phi) * cos_theta;
+            dirl[2] = sqrt(1.0 - cos_theta * cos_theta);
+            for (k = 0; k < 3; k++)
+                dir[k] = dirl[0] * basis[0][k] + dirl[1] * basis[1][k] + dirl[2] * basis[2][k];
+            (*nrays)++;
+            if (!trace_f64(T, V, org, dir, 0, &t, &u, &v, &prim, NULL)) {
+                float vf[3], c[3];
+                vf[0] = dir[0]; vf[1] = dir[1]; vf[2] = dir[2];
+                sky_rgb(s, vf, c);
+                col[0] += c[0]; col[1] += c[1]; col[2] += c[2];
+            }
+        }
+    }
+    for (l = 0; l < s->nsun; l++) {                           /* one shadow ray per LIGHTTYPE_SUNLIGHT, same offset origin */
+        for (k = 0; k < 3; k++) dir[k] = s->sun_dir[l][k];
+        (*nrays)++;
+        if (!trace_f64(T, V, org, dir, 0, &t, &u, &v, &prim, NULL))
+            for (k = 0; k < 3; k++) col[k] += s->sun_col[l][k];
+    }
+    nsamples = ntheta * nphi;
+    m = (1.0 / M_PI);
+    for (k = 0; k < 3; k++) Lo[k] = m * col[k] / nsamples;
+}
+
+/* the pixel loop of orc_render_ao with the sun-sky transport (ambientocclusion.c:369-376) and three channels (render.c:805,820) */
+void orc_render_sunsky(const orc_tree *T, const orc_frame_t *f, const orc_sunsky_t *s, float *rgb, uint64_t *nrays_out)
+{
+    int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(f->width, f->height, f->bucket_size, buckets, nb_max);
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t nrays = 0;
+    int b, k;
+
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, 4357);
+    for (b = 0; b < nb; b++) {
+        int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        int u, v;
+        for (v = by; v < by + bh; v++) {
+            for (u = bx; u < bx + bw; u++) {
+                double accum[3] = {0.0, 0.0, 0.0};
+                int xs, ys;
+                float *dst = rgb + 3 * ((size_t)(f->height - v - 1) * f->width + u);
+                for (ys = 0; ys < f->ysamples; ys++) {
+                    for (xs = 0; xs < f->xsamples; xs++) {
+                        double jx, jy, org[3], dir[3], t, uu, vv, rad[3] = {0.0, 0.0, 0.0};
+                        uint32_t prim;
+                        orc_subpixel_jitter(xs, ys, f->xsamples, f->ysamples, &jx, &jy);
+                        orc_camera_ray(f, (double)(u + jx), (double)(v + jy), org, dir);
+                        nrays++;
+                        if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+                            orc_state_f64 st;
+                            state_build_uv(T, org, dir, t, uu, vv, prim, &st);
+                            sunsky_radiance(T, &V, &st, s, &rng, &nrays, rad);
+                        }
+                        for (k = 0; k < 3; k++) accum[k] = accum[k] + rad[k];
+                    }
+                }
+                for (k = 0; k < 3; k++) dst[k] = (float)(accum[k] * ((double)1.0 / (f->xsamples * f->ysamples)));
+            }
+        }
+    }
+    free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
 /* ------------------------------------------------------------------ beam visibility (row a10) */
 
 typedef struct {

@@ -144,6 +144,29 @@ typedef struct {
 void orc_render_pathtrace(const orc_tree *t, const orc_path_frame_t *f, float *rgb, uint64_t *nrays_out);
 void orc_det_sincos2pi(double r, double *s, double *c);
 
+/* ---- sun-sky gather (row a12): ambientocclusion.c:153-324 gather_sunsky + contribution_from_sunlight, with the sky lookup
+ * ri_sunsky_get_sky_rgb (render/sunsky.c:24-38 angle_between, 136-152 PerezFunction, 297-408; render/specrend.c:127-172
+ * xyz_to_rgb, 366-440 spectrum_to_xyz).  The block is what the host side owns after ri_sunsky_init(): Perez coefficients,
+ * zenith values and sun angles of ri_sunsky_t (sunsky.h:22-50), the S0/S1/S2 daylight tables of sunsky.dat, the CIE matching
+ * table of specrend.c:387-414, the chromaticities of specrend.h CIEsystem, and the LIGHTTYPE_SUNLIGHT lights of the scene
+ * (lightsource.c:152-170).  Same layout as ri_b200_sunsky_t (include/lucille_b200.h). */
+typedef struct {
+    float   sun_theta, sun_phi;
+    float   perez_x[5], perez_y[5], perez_Y[5];
+    float   zenith_x, zenith_y, zenith_Y;
+    float   S0[41], S1[41], S2[41];
+    float   cie[81][3];
+    float   cs[8];               /* xRed yRed xGreen yGreen xBlue yBlue xWhite yWhite */
+    int32_t nsun;                /* <= 4 */
+    int32_t pad;
+    double  sun_dir[4][3];       /* ri_light_t.direction */
+    double  sun_col[4][3];       /* ri_light_t.col */
+} orc_sunsky_t;
+/* sky colour for n directions (world space, the transport's ray.dir cast to float): rgb [n][3] */
+void orc_sunsky_sky_rgb(const orc_sunsky_t *s, const float *dirs, uint64_t n, float *rgb);
+/* whole frame with the sun-sky transport: 8x8 gather, eps 1e-5, Lo = (1/pi) * col / 64 (f->ntheta/nphi are ignored) */
+void orc_render_sunsky(const orc_tree *t, const orc_frame_t *f, const orc_sunsky_t *s, float *rgb, uint64_t *nrays_out);
+
 /* counter-based uniform for the synthetic configs (shared definition with the product) */
 uint64_t orc_splitmix64(uint64_t x);
 

@@ -6,9 +6,10 @@
  * Stands in for `lsh` (src/lsh/main.c), whose flex/bison front end cannot be generated here.
  *
  *   oracle_rib scene.rib [--nthreads N] [--width W --height H] [--pixelsamples P]
- *                        [--gather G] [--out frame.bin] [--scene scene.bin] [--accel bvh|b200]
+ *                        [--gather G] [--out frame.bin] [--scene scene.bin] [--sunsky sunsky.bin] [--accel bvh|b200]
  *
  * frame.bin : "LFRM" u32 w, u32 h, u32 0, f64 seconds("Render frame"), u64 nrays(stat.nrays), f32 rgb[h][w][3]
+ * sunsky.bin: f64[45] = lref_frame_sunsky() block (only written when the scene has an AreaLightSource "sunsky")
  * scene.bin : "LSCN" u32 0, u64 ntris, f64 cam[27], f64 tri[ntris][9], u32 geom[ntris], f64 normals[ntris][9] (zeros if none)
  */
 #include <stdio.h>
@@ -28,10 +29,11 @@ extern double  *lref_frame_tris(void);
 extern uint32_t*lref_frame_trigeom(void);
 extern double  *lref_frame_normals(void);
 extern void     lref_frame_camera(double *out27);
+extern int      lref_frame_sunsky(double *out45);
 
 int main(int argc, char **argv)
 {
-    const char *rib = NULL, *out = NULL, *scene = NULL;
+    const char *rib = NULL, *out = NULL, *scene = NULL, *sunsky = NULL;
     int nthreads = 1, width = 0, height = 0, ps = 0, gather = 0, i;
     for (i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--nthreads") && i + 1 < argc) nthreads = atoi(argv[++i]);
@@ -45,6 +47,7 @@ int main(int argc, char **argv)
         }
         else if (!strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
         else if (!strcmp(argv[i], "--scene") && i + 1 < argc) scene = argv[++i];
+        else if (!strcmp(argv[i], "--sunsky") && i + 1 < argc) sunsky = argv[++i];
         else rib = argv[i];
     }
     if (!rib) { fprintf(stderr, "usage: oracle_rib scene.rib [options]\n"); return 2; }
@@ -63,6 +66,16 @@ int main(int argc, char **argv)
             fwrite(&sec, 8, 1, fp); fwrite(&nrays, 8, 1, fp);
             fwrite(lref_frame_rgb(), sizeof(float), (size_t)w * h * 3, fp);
             fclose(fp);
+        }
+        if (sunsky) {
+            double blk[45];
+            memset(blk, 0, sizeof(blk));
+            if (lref_frame_sunsky(blk)) {
+                FILE *fp = fopen(sunsky, "wb");
+                if (!fp) return 1;
+                fwrite(blk, 8, 45, fp);
+                fclose(fp);
+            }
         }
         if (scene) {
             double cam[27];

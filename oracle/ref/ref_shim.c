@@ -35,6 +35,10 @@
 #include "log.h"
 #include "raytrace.h"
 #include "beam.h"
+#include "light.h"
+#include "sunsky.h"
+
+static void capture_sunsky(void);
 
 extern int lref_rib_parse_file(const char *path);
 
@@ -411,6 +415,7 @@ static int dd_open(const char *name, int width, int height, int bits, RtToken co
     g_frame.gather   = opt->gather_nsamples;
     g_frame.bucket_size  = r->bucket_size;
     g_frame.bucket_order = r->bucket_order;
+    capture_sunsky();
     return 1;
 }
 
@@ -474,6 +479,52 @@ uint64_t lref_frame_ntris(void)  { return g_frame.ntris; }
 double  *lref_frame_tris(void)   { return g_frame.tri_xyz; }
 uint32_t*lref_frame_trigeom(void){ return g_frame.tri_geom; }
 double  *lref_frame_normals(void){ return g_frame.tri_nrm; }
+/* ---- sun-sky (row a12) ---------------------------------------------------------------------------------------------
+ * block layout = orc_sunsky_t / ri_b200_sunsky_t minus the tables the reference keeps private:
+ * out[0..1] sun_theta, sun_phi; [2..6] perez_x; [7..11] perez_y; [12..16] perez_Y; [17..19] zenith x,y,Y;
+ * [20] nsun; then nsun x (direction[3], col[3]).  Returns 0 when the scene has no sun-sky light. */
+static double g_sunsky[21 + 6 * 4];
+static int    g_has_sunsky = 0;
+static void capture_sunsky(void)
+{
+    ri_scene_t *scene = ri_render_get()->scene;
+    ri_list_t *itr;
+    int i, n = 0;
+    g_has_sunsky = 0;
+    if (!scene->sunsky_light || !scene->sunsky_light->sunsky) return;
+    {
+        const ri_sunsky_t *s = scene->sunsky_light->sunsky;
+        g_sunsky[0] = s->sun_theta; g_sunsky[1] = s->sun_phi;
+        for (i = 0; i < 5; i++) { g_sunsky[2 + i] = s->perez_x[i]; g_sunsky[7 + i] = s->perez_y[i]; g_sunsky[12 + i] = s->perez_Y[i]; }
+        g_sunsky[17] = s->zenith_x; g_sunsky[18] = s->zenith_y; g_sunsky[19] = s->zenith_Y;
+    }
+    for (itr = ri_list_first(scene->light_list); itr; itr = ri_list_next(itr)) {
+        const ri_light_t *l = (const ri_light_t *)itr->data;
+        if (l->type != LIGHTTYPE_SUNLIGHT || n >= 4) continue;
+        for (i = 0; i < 3; i++) { g_sunsky[21 + 6 * n + i] = l->direction[i]; g_sunsky[21 + 6 * n + 3 + i] = l->col[i]; }
+        n++;
+    }
+    g_sunsky[20] = n;
+    g_has_sunsky = 1;
+}
+int lref_frame_sunsky(double *out45)
+{
+    if (g_has_sunsky) memcpy(out45, g_sunsky, sizeof(g_sunsky));
+    return g_has_sunsky;
+}
+/* ri_sunsky_init() + ri_sunsky_get_sky_rgb() without a scene: the sky colour of n directions, and the block above (no lights) */
+void lref_sunsky_eval(float latitude, float longitude, float sm, int jd, float tod, float turb,
+                      const float *dirs, uint64_t n, float *rgb, double *out21)
+{
+    ri_sunsky_t *s = ri_sunsky_new();
+    uint64_t k; int i;
+    ri_sunsky_init(s, latitude, longitude, sm, jd, tod, turb, 0);
+    for (k = 0; k < n; k++) ri_sunsky_get_sky_rgb(rgb + 3 * k, s, dirs + 3 * k);
+    out21[0] = s->sun_theta; out21[1] = s->sun_phi;
+    for (i = 0; i < 5; i++) { out21[2 + i] = s->perez_x[i]; out21[7 + i] = s->perez_y[i]; out21[12 + i] = s->perez_Y[i]; }
+    out21[17] = s->zenith_x; out21[18] = s->zenith_y; out21[19] = s->zenith_Y; out21[20] = 0;
+}
+
 /* out: c2w[16], flength, is_rh, ortho, fov, xsamples, ysamples, gather, bucket_size, bucket_order, has_normals, ngeoms */
 void lref_frame_camera(double *out27)
 {

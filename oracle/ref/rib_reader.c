@@ -233,6 +233,12 @@ int lref_rib_parse_file(const char *path)
             read_param_list(lx, &pl);
             RiAttributeV(strdup(s1), pl.n, pl.tokens, pl.args);
         }
+        else if (!strcmp(c, "AreaLightSource")) {          /* parserib.y:371-375: name, sequence number, parameters */
+            lex_next(lx); strcpy(s1, lx->text);
+            read_nums(lx, f, 1);
+            read_param_list(lx, &pl);
+            RiAreaLightSourceV(strdup(s1), pl.n, pl.tokens, pl.args);
+        }
         else if (!strcmp(c, "Surface")) {
             lex_next(lx); strcpy(s1, lx->text);
             read_param_list(lx, &pl);

@@ -44,12 +44,79 @@ class PathFrameParams(C.Structure):
                 ("rank", C.c_int32), ("world", C.c_int32), ("bucket_size", C.c_int32)]
 
 
+class SunskyBlock(C.Structure):
+    """orc_sunsky_t == ri_b200_sunsky_t (include/lucille_b200.h)."""
+    _fields_ = [("sun_theta", C.c_float), ("sun_phi", C.c_float),
+                ("perez_x", C.c_float * 5), ("perez_y", C.c_float * 5), ("perez_Y", C.c_float * 5),
+                ("zenith_x", C.c_float), ("zenith_y", C.c_float), ("zenith_Y", C.c_float),
+                ("S0", C.c_float * 41), ("S1", C.c_float * 41), ("S2", C.c_float * 41),
+                ("cie", C.c_float * 243), ("cs", C.c_float * 8),
+                ("nsun", C.c_int32), ("pad", C.c_int32),
+                ("sun_dir", C.c_double * 12), ("sun_col", C.c_double * 12)]
+
+
+def sky_dirs(n: int, seed: int) -> np.ndarray:
+    """Seeded unit directions for the sky-lookup tests, with grazing ones (the t[2] < 0.001 branch of sunsky.c:349-355),
+    below-horizon ones and the axes."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[: n // 8, 1] = np.abs(d[: n // 8, 1]) * 1e-3
+    d[n // 8: n // 8 + 4] = [[0, 1, 0], [1, 0, 0], [0, -1, 0], [0, 0, 1]]
+    return d.astype(np.float32)
+
+
+def sunsky_block(params45: np.ndarray, tables) -> SunskyBlock:
+    """params45: the lref_frame_sunsky()/lref_sunsky_eval() record; tables: mapping with S0 S1 S2 cie cs
+    (tests/golden/sunsky.npz, extracted from the reference by tests/golden/make_sunsky_golden.py)."""
+    b = SunskyBlock()
+    p = np.asarray(params45, dtype=np.float64)
+    b.sun_theta, b.sun_phi = float(p[0]), float(p[1])
+    for i in range(5):
+        b.perez_x[i], b.perez_y[i], b.perez_Y[i] = float(p[2 + i]), float(p[7 + i]), float(p[12 + i])
+    b.zenith_x, b.zenith_y, b.zenith_Y = float(p[17]), float(p[18]), float(p[19])
+    for name in ("S0", "S1", "S2"):
+        arr = np.asarray(tables[name], dtype=np.float32)
+        for i in range(41):
+            getattr(b, name)[i] = float(arr[i])
+    cie = np.asarray(tables["cie"], dtype=np.float32).reshape(243)
+    for i in range(243):
+        b.cie[i] = float(cie[i])
+    cs = np.asarray(tables["cs"], dtype=np.float32)
+    for i in range(8):
+        b.cs[i] = float(cs[i])
+    n = int(p[20]) if len(p) > 20 else 0
+    b.nsun = n
+    for l in range(n):
+        for k in range(3):
+            b.sun_dir[3 * l + k] = float(p[21 + 6 * l + k])
+            b.sun_col[3 * l + k] = float(p[21 + 6 * l + 3 + k])
+    return b
+
+
 def oracle_available() -> bool:
     return os.path.exists(ORACLE_SO)
 
 
 def reference_available() -> bool:
     return os.path.exists(REF_SO)
+
+
+class _quiet:
+    """The reference printf()s from its setup code: keep fd 1 clean while it runs."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        C.CDLL(None).fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
 
 
 def _ptr(a: np.ndarray):
@@ -150,6 +217,12 @@ class OracleTree:
         self.lib.orc_render_ao(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
         return rgb, nrays.value
 
+    def render_sunsky(self, frame: "FrameParams", block: "SunskyBlock"):
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_sunsky(self.h, C.byref(frame), C.byref(block), _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
 
 class Oracle:
     def __init__(self):
@@ -182,7 +255,15 @@ class Oracle:
         lib.orc_render_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_splitmix64.restype = C.c_uint64
         lib.orc_splitmix64.argtypes = [C.c_uint64]
+        lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_render_sunsky.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib = lib
+
+    def sunsky_sky_rgb(self, block: SunskyBlock, dirs: np.ndarray) -> np.ndarray:
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros_like(dirs)
+        self.lib.orc_sunsky_sky_rgb(C.byref(block), _ptr(dirs), C.c_uint64(len(dirs)), _ptr(out))
+        return out
 
     def build(self, tris: np.ndarray) -> OracleTree:
         tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 9)
@@ -286,8 +367,24 @@ class Reference:
         lib.lref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.lref_stats_get.argtypes = [C.c_void_p]
         lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_void_p]
+        lib.lref_sunsky_eval.restype = None
         self.lib = lib
         self.stats = stats
+
+    def sunsky_eval(self, dirs: np.ndarray, latitude=35.39, longitude=139.44, sm=9.0, jd=20, tod=10.5, turbidity=2.0):
+        """ri_sunsky_init + ri_sunsky_get_sky_rgb of the compiled reference: (rgb [n][3] float32, 21-double parameter record)."""
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        rgb = np.zeros_like(dirs)
+        rec = np.zeros(45, dtype=np.float64)
+        with _quiet():
+            self.lib.lref_sunsky_eval(latitude, longitude, sm, jd, tod, turbidity, _ptr(dirs), C.c_uint64(len(dirs)), _ptr(rgb), _ptr(rec))
+        return rgb, rec
+
+    def table(self, name: str, n: int) -> np.ndarray:
+        """A float table the reference exports as a data symbol (sunsky.dat: S0Amplitudes, S1Amplitudes, S2Amplitudes)."""
+        return np.array((C.c_float * n).in_dll(self.lib, name), dtype=np.float32)
 
     def build(self, tris: np.ndarray, geom_sizes=None) -> ReferenceScene:
         tris = np.ascontiguousarray(tris, dtype=np.float64).reshape(-1, 9)
@@ -331,7 +428,7 @@ def read_scene(path: str):
 
 
 def run_oracle_rib(rib: str, out: str, scene: str | None = None, nthreads: int = 1, width: int = 0, height: int = 0,
-                   pixelsamples: int = 0, gather: int = 0, timeout: int = 3600):
+                   pixelsamples: int = 0, gather: int = 0, timeout: int = 3600, sunsky: str | None = None):
     """Run the compiled reference renderer on a RIB in a subprocess (one frame per process)."""
     cmd = [ORACLE_RIB, rib, "--nthreads", str(nthreads), "--out", out]
     if scene:
@@ -342,6 +439,8 @@ def run_oracle_rib(rib: str, out: str, scene: str | None = None, nthreads: int =
         cmd += ["--pixelsamples", str(pixelsamples)]
     if gather:
         cmd += ["--gather", str(gather)]
+    if sunsky:
+        cmd += ["--sunsky", sunsky]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
     return read_frame(out)
 

@@ -72,3 +72,15 @@ def test_beam_visibility(oracle, ref):
         rs = ref.build(tris)
         want = np.array([rs.beam_visibility(b[:3], b[3:]) for b in beams], dtype=np.int32)
         assert np.array_equal(got, want)
+
+
+def test_sunsky_sky_lookup(oracle, ref, golden_dir):
+    """Row a12: the sky lookup against the compiled ri_sunsky_init + ri_sunsky_get_sky_rgb on a site/time the goldens do not hold."""
+    import os
+    tables = np.load(os.path.join(golden_dir, "sunsky.npz"))
+    for name, n in (("S0", 41), ("S1", 41), ("S2", 41)):
+        assert np.array_equal(ref.table(name + "Amplitudes", n), tables[name])
+    dirs = ol.sky_dirs(20000, 77)
+    want, rec = ref.sunsky_eval(dirs, latitude=60.17, longitude=24.94, sm=2.0, jd=200, tod=18.5, turbidity=3.3)
+    got = oracle.sunsky_sky_rgb(ol.sunsky_block(rec, tables), dirs)
+    assert np.array_equal(got, want)
