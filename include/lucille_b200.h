@@ -170,6 +170,37 @@ int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
                                     ri_b200_frame_stats_t *stats);
 int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
 
+/* ---- sun-sky variant of the same transport: gather_sunsky + contribution_from_sunlight (ambientocclusion.c:153-324), taken by
+ * ri_transport_ambientocclusion whenever the scene has an AreaLightSource "sunsky" (ambientocclusion.c:369-376): fixed 8 x 8
+ * gather (frame->ntheta/nphi are ignored), origin offset 1e-5, the sky colour ri_sunsky_get_sky_rgb(dir) (render/sunsky.c:322-408)
+ * summed over the MISSED rays, one shadow ray per LIGHTTYPE_SUNLIGHT light, Lo = (1/pi) * col / 64, three channels.
+ * The block is what the host owns after ri_sunsky_init() (sunsky.c:176-295) -- set-up stays on the reference side:
+ *   sun_theta .. zenith_Y   ri_sunsky_t fields of scene->sunsky_light->sunsky (sunsky.h:22-50)
+ *   S0 S1 S2                S0Amplitudes / S1Amplitudes / S2Amplitudes (render/sunsky.dat)
+ *   cie                     cie_colour_match (render/specrend.c:387-414)
+ *   cs                      CIEsystem: xRed yRed xGreen yGreen xBlue yBlue xWhite yWhite (render/specrend.h)
+ *   sun_dir / sun_col       ri_light_t.direction / .col of the scene's LIGHTTYPE_SUNLIGHT lights, light_list order (lightsource.c:152-170)
+ * The lookup is float arithmetic around double libm calls; the device's sin/cos/acos/atan2/exp differ from the host's in the
+ * last place, so parity with the reference is to float tolerance, not bit-exact (tests/test_gpu_parity.py states it). */
+typedef struct {
+    float   sun_theta, sun_phi;
+    float   perez_x[5], perez_y[5], perez_Y[5];
+    float   zenith_x, zenith_y, zenith_Y;
+    float   S0[41], S1[41], S2[41];
+    float   cie[81][3];
+    float   cs[8];
+    int32_t nsun;                 /* 0..4 */
+    int32_t pad;
+    double  sun_dir[4][3];
+    double  sun_col[4][3];
+} ri_b200_sunsky_t;
+int ri_b200_render_sunsky(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, const ri_b200_sunsky_t *sky, float *rgb_out,
+                          ri_b200_frame_stats_t *stats);
+int ri_b200_render_sunsky_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, const ri_b200_sunsky_t *sky, float *d_packed,
+                                    void *stream, ri_b200_frame_stats_t *stats);
+/* ri_sunsky_get_sky_rgb for a HOST batch of directions ([n][3] floats in, [n][3] floats out), computed on `device` */
+int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device);
+
 /* ---- replaces ri_beam_set + ri_bvh_intersect_beam_visibility (beam.c:332-466, bvh.c:612-667) for a batch of beams.
  * beams: HOST [n][15] doubles = org.xyz, dir0.xyz .. dir3.xyz (consecutive corners of the frustum).  out[i] = RI_BEAM_MISS_COMPLETELY 0 /
  * RI_BEAM_HIT_COMPLETELY 1 / RI_BEAM_HIT_PARTIALLY 2 (beam.h:27-29), or -1 where ri_beam_set would fail (corner directions

@@ -78,6 +78,17 @@ class PathFrame(C.Structure):
                 ("rank", C.c_int32), ("world", C.c_int32), ("bucket_size", C.c_int32)]
 
 
+class Sunsky(C.Structure):
+    """ri_b200_sunsky_t: what the host owns after ri_sunsky_init() (sunsky.c:176-295) plus the scene's sun lights."""
+    _fields_ = [("sun_theta", C.c_float), ("sun_phi", C.c_float),
+                ("perez_x", C.c_float * 5), ("perez_y", C.c_float * 5), ("perez_Y", C.c_float * 5),
+                ("zenith_x", C.c_float), ("zenith_y", C.c_float), ("zenith_Y", C.c_float),
+                ("S0", C.c_float * 41), ("S1", C.c_float * 41), ("S2", C.c_float * 41),
+                ("cie", C.c_float * 243), ("cs", C.c_float * 8),
+                ("nsun", C.c_int32), ("pad", C.c_int32),
+                ("sun_dir", C.c_double * 12), ("sun_col", C.c_double * 12)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("nrays_primary", C.c_uint64), ("nrays_ao", C.c_uint64), ("nhits_primary", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_primary", C.c_double), ("ms_rng", C.c_double), ("ms_ao", C.c_double),
@@ -118,6 +129,9 @@ ABI = [
     ("ri_b200_render_ao_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_ao_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
+    ("ri_b200_render_sunsky", _I, [_P, _P, _P, _P, _P]),
+    ("ri_b200_render_sunsky_tiles_dev", _I, [_P, _P, _P, _P, _P, _P]),
+    ("ri_b200_sunsky_rgb", _I, [_P, _P, _U64, _P, _I]),
     ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_pathtrace_tiles_dev", _I, [_P, _P, _P, _P, _P]),
@@ -341,6 +355,13 @@ class Accel:
         _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
         return rgb, stats
 
+    def render_sunsky(self, frame: Frame, sky: "Sunsky"):
+        """One frame with the sun-sky gather (ambientocclusion.c:206-324) -> (rgb [h,w,3] float32 on the host, FrameStats)."""
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_sunsky(self._h(), C.byref(frame), C.byref(sky), _ptr(rgb), C.byref(stats)))
+        return rgb, stats
+
     def beam_visibility(self, beams15: np.ndarray) -> np.ndarray:
         """``ri_bvh_intersect_beam_visibility`` for a batch: [n,15] float64 beams -> int32 codes (0 miss, 1 full hit, 2 partial, -1 invalid)."""
         beams15 = np.ascontiguousarray(beams15, dtype=np.float64).reshape(-1, 15)
@@ -367,6 +388,14 @@ class Accel:
         _check(self.lib.ri_b200_render_ao_dev(self._h(), C.byref(frame), _ptr(d_rgb),
                                               C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
         return stats
+
+
+def sunsky_rgb(sky: "Sunsky", dirs: np.ndarray, device: int = 0) -> np.ndarray:
+    """``ri_sunsky_get_sky_rgb`` (sunsky.c:387-408) for a batch of directions, computed on the device."""
+    dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros_like(dirs)
+    _check(load_library().ri_b200_sunsky_rgb(C.byref(sky), _ptr(dirs), len(dirs), _ptr(out), device))
+    return out
 
 
 def frame_pixels(frame: Frame) -> np.ndarray:

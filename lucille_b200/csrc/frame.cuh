@@ -25,6 +25,7 @@ struct FrameDev {
     int    width, height, xsamples, ysamples, ntheta, nphi, spp, nao;
     int    rng_mode;
     uint32_t seed;
+    double ao_eps;              // shading-point offset along Ns: 1e-6 (ambientocclusion.c:56), 1e-5 for the sun-sky gather (:222)
 };
 
 // camera.c:248-352 (perspective) + render.c:770-781 normalise -------------------------------------
@@ -133,11 +134,10 @@ template <typename Real> struct StateMath;      // hit state in the accelerator'
 
 template <> struct StateMath<double> {
     static __device__ __forceinline__ void frame(const SceneView<double> &S, const double org[3], const double dir[3], double t,
-                                                 double bu, double bv, uint32_t prim, double rec[12])
+                                                 double bu, double bv, uint32_t prim, const double eps, double rec[12])
     {
         ri_b200_state_f64 s;
-        state_from_hit(S.tris, S.slot_of_prim, org, dir, t, prim, s, S.normals, bu, bv);
-        const double eps = 1.0e-6;                                      // ambientocclusion.c:56,73-75
+        state_from_hit(S.tris, S.slot_of_prim, org, dir, t, prim, s, S.normals, bu, bv);                                                 // eps: ambientocclusion.c:56,73-75
         double b0[3], b1[3];
         ortho_basis(b0, b1, s.Ns);                                      // ambientocclusion.c:65
         for (int k = 0; k < 3; ++k) {
@@ -159,7 +159,7 @@ template <> struct StateMath<float> {
         d[0] = a[1] * b[2] - a[2] * b[1]; d[1] = a[2] * b[0] - a[0] * b[2]; d[2] = a[0] * b[1] - a[1] * b[0];
     }
     static __device__ __forceinline__ void frame(const SceneView<float> &S, const float org[3], const float dir[3], float t,
-                                                 float bu, float bv, uint32_t prim, float rec[12])
+                                                 float bu, float bv, uint32_t prim, const double eps, float rec[12])
     {
         TriRegs<float> tr;
         load_tri(S.tris + S.slot_of_prim[prim], tr);
@@ -183,7 +183,7 @@ template <> struct StateMath<float> {
         crs(b1, n, b0); nrm(b1);
         for (int k = 0; k < 3; ++k) {
             float o = org[k] + dir[k] * t;
-            o += n[k] * 1.0e-6f;
+            o += n[k] * (float)eps;
             rec[k] = o; rec[3 + k] = b0[k]; rec[6 + k] = b1[k]; rec[9 + k] = n[k];
         }
     }
@@ -217,7 +217,7 @@ compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__rest
         camera_ray(F, (int)(pix & 0xffffu), (int)(pix >> 16), jitter[2 * sub], jitter[2 * sub + 1], org, dir);
         Real o[3] = {(Real)org[0], (Real)org[1], (Real)org[2]}, d[3] = {(Real)dir[0], (Real)dir[1], (Real)dir[2]};
         Real rec[12];
-        StateMath<Real>::frame(S, o, d, hit_t[s], hit_uv ? hit_uv[2 * s] : Real(0), hit_uv ? hit_uv[2 * s + 1] : Real(0), hit_prim[s], rec);
+        StateMath<Real>::frame(S, o, d, hit_t[s], hit_uv ? hit_uv[2 * s] : Real(0), hit_uv ? hit_uv[2 * s + 1] : Real(0), hit_prim[s], F.ao_eps, rec);
         Real *dst = records + 12 * (uint64_t)rank;
 #pragma unroll
         for (int q = 0; q < 12; ++q) dst[q] = rec[q];
@@ -345,6 +345,53 @@ __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x)
     return x ^ (x >> 31);
 }
 
+// ---- occlusion-ray direction k = j*ntheta + i of hit sample `rank`: ambientocclusion.c:83-117 (stratified cosine sampling about
+// the shading frame in `rec`), uniforms from the MT19937 stream in the reference's consumption order or from the counter RNG
+template <typename Real>
+__device__ __forceinline__ void ao_direction(const FrameDev &F, const uint32_t rank, const uint32_t k, const Real *__restrict__ rec,
+                                             const uint32_t *__restrict__ rank_sample, const uint32_t *__restrict__ pixels,
+                                             const uint32_t *__restrict__ mt_stream, Real dir[3])
+{
+    const uint32_t N = (uint32_t)F.nao;
+    const uint32_t j = k / (uint32_t)F.ntheta, i = k - j * (uint32_t)F.ntheta;
+    double r0, r1;
+    if (F.rng_mode == 0) {
+        const uint64_t base = (uint64_t)2 * N * rank + 2 * k;               // draw order z0 then z1, ambientocclusion.c:91-92
+        r0 = (double)mt_stream[base] * 2.3283064365386963e-10;               // random.c:244
+        r1 = (double)mt_stream[base + 1] * 2.3283064365386963e-10;
+    } else {
+        const uint32_t s = rank_sample[rank];
+        const uint64_t p = s / (uint32_t)F.spp;
+        const uint32_t sub = s - (uint32_t)p * (uint32_t)F.spp;
+        const uint32_t pix = pixels[p];
+        const uint64_t sid = ((uint64_t)(pix >> 16) * (uint64_t)F.width + (pix & 0xffffu)) * (uint64_t)F.spp + sub;
+        const uint64_t idx = (sid * N + k) * 2;
+        r0 = (double)(splitmix64_dev((uint64_t)F.seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+        r1 = (double)(splitmix64_dev((uint64_t)F.seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+    }
+    if (sizeof(Real) == 8) {                                                 // ambientocclusion.c:91-117, double
+        const double z0 = ((double)i + r0) / (double)F.ntheta;
+        const double z1 = ((double)j + r1) / (double)F.nphi;
+        const double ct = sqrt(z0);
+        const double phi = 2.0 * 3.14159265358979323846 * z1;
+        const double lx = cos(phi) * ct, ly = sin(phi) * ct, lz = sqrt(1.0 - ct * ct);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            dir[q] = (Real)(lx * (double)rec[3 + q] + ly * (double)rec[6 + q] + lz * (double)rec[9 + q]);
+    } else {
+        const float z0 = ((float)i + (float)r0) / (float)F.ntheta;
+        const float z1 = ((float)j + (float)r1) / (float)F.nphi;
+        const float ct = sqrtf(z0);
+        const float phi = 6.28318530717958647692f * z1;
+        float sp, cp;
+        sincosf(phi, &sp, &cp);
+        const float lx = cp * ct, ly = sp * ct, lz = sqrtf(1.0f - ct * ct);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            dir[q] = (Real)(lx * (float)rec[3 + q] + ly * (float)rec[6 + q] + lz * (float)rec[9 + q]);
+    }
+}
+
 // ---- K4: occlusion rays ----------------------------------------------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(kBlock)
@@ -362,47 +409,9 @@ ao_kernel(const SceneView<Real> S, const FrameDev F, const uint64_t nrays, const
         const uint32_t N = (uint32_t)F.nao;
         rank = rank0 + (uint32_t)(gid / N);
         const uint32_t k = (uint32_t)(gid - (uint64_t)(rank - rank0) * N);
-        const uint32_t j = k / (uint32_t)F.ntheta, i = k - j * (uint32_t)F.ntheta;
         const Real *rec = records + 12 * (uint64_t)rank;
-
-        double r0, r1;
-        if (F.rng_mode == 0) {
-            const uint64_t base = (uint64_t)2 * N * rank + 2 * k;       // draw order z0 then z1, ambientocclusion.c:91-92
-            r0 = (double)mt_stream[base] * 2.3283064365386963e-10;       // random.c:244
-            r1 = (double)mt_stream[base + 1] * 2.3283064365386963e-10;
-        } else {
-            const uint32_t s = rank_sample[rank];
-            const uint64_t p = s / (uint32_t)F.spp;
-            const uint32_t sub = s - (uint32_t)p * (uint32_t)F.spp;
-            const uint32_t pix = pixels[p];
-            const uint64_t sid = ((uint64_t)(pix >> 16) * (uint64_t)F.width + (pix & 0xffffu)) * (uint64_t)F.spp + sub;
-            const uint64_t idx = (sid * N + k) * 2;
-            r0 = (double)(splitmix64_dev((uint64_t)F.seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
-            r1 = (double)(splitmix64_dev((uint64_t)F.seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
-        }
-
         Real org[3] = {rec[0], rec[1], rec[2]}, dir[3];
-        if (sizeof(Real) == 8) {                                         // ambientocclusion.c:91-117, double
-            const double z0 = ((double)i + r0) / (double)F.ntheta;
-            const double z1 = ((double)j + r1) / (double)F.nphi;
-            const double ct = sqrt(z0);
-            const double phi = 2.0 * 3.14159265358979323846 * z1;
-            const double lx = cos(phi) * ct, ly = sin(phi) * ct, lz = sqrt(1.0 - ct * ct);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                dir[q] = (Real)(lx * (double)rec[3 + q] + ly * (double)rec[6 + q] + lz * (double)rec[9 + q]);
-        } else {
-            const float z0 = ((float)i + (float)r0) / (float)F.ntheta;
-            const float z1 = ((float)j + (float)r1) / (float)F.nphi;
-            const float ct = sqrtf(z0);
-            const float phi = 6.28318530717958647692f * z1;
-            float sp, cp;
-            sincosf(phi, &sp, &cp);
-            const float lx = cp * ct, ly = sp * ct, lz = sqrtf(1.0f - ct * ct);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                dir[q] = (Real)(lx * (float)rec[3 + q] + ly * (float)rec[6 + q] + lz * (float)rec[9 + q]);
-        }
+        ao_direction<Real>(F, rank, k, rec, rank_sample, pixels, mt_stream, dir);
         if (dump_rays && gid < dump_count) {
             const int st = sizeof(Real) == 8 ? 6 : 8, off = sizeof(Real) == 8 ? 3 : 4;
             Real *d = dump_rays + gid * st;
@@ -435,45 +444,9 @@ ao_gen_kernel(const FrameDev F, const uint64_t nrays, const uint32_t rank0, cons
     const uint32_t N = (uint32_t)F.nao;
     const uint32_t rank = rank0 + (uint32_t)(gid / N);
     const uint32_t k = (uint32_t)(gid - (uint64_t)(rank - rank0) * N);
-    const uint32_t j = k / (uint32_t)F.ntheta, i = k - j * (uint32_t)F.ntheta;
     const Real *rec = records + 12 * (uint64_t)rank;
-    double r0, r1;
-    if (F.rng_mode == 0) {
-        const uint64_t base = (uint64_t)2 * N * rank + 2 * k;               // z0 then z1, ambientocclusion.c:91-92
-        r0 = (double)mt_stream[base] * 2.3283064365386963e-10;               // random.c:244
-        r1 = (double)mt_stream[base + 1] * 2.3283064365386963e-10;
-    } else {
-        const uint32_t s = rank_sample[rank];
-        const uint64_t p = s / (uint32_t)F.spp;
-        const uint32_t sub = s - (uint32_t)p * (uint32_t)F.spp;
-        const uint32_t pix = pixels[p];
-        const uint64_t sid = ((uint64_t)(pix >> 16) * (uint64_t)F.width + (pix & 0xffffu)) * (uint64_t)F.spp + sub;
-        const uint64_t idx = (sid * N + k) * 2;
-        r0 = (double)(splitmix64_dev((uint64_t)F.seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
-        r1 = (double)(splitmix64_dev((uint64_t)F.seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
-    }
     Real dir[3];
-    if (sizeof(Real) == 8) {                                                 // ambientocclusion.c:91-117, double
-        const double z0 = ((double)i + r0) / (double)F.ntheta;
-        const double z1 = ((double)j + r1) / (double)F.nphi;
-        const double ct = sqrt(z0);
-        const double phi = 2.0 * 3.14159265358979323846 * z1;
-        const double lx = cos(phi) * ct, ly = sin(phi) * ct, lz = sqrt(1.0 - ct * ct);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            dir[q] = (Real)(lx * (double)rec[3 + q] + ly * (double)rec[6 + q] + lz * (double)rec[9 + q]);
-    } else {
-        const float z0 = ((float)i + (float)r0) / (float)F.ntheta;
-        const float z1 = ((float)j + (float)r1) / (float)F.nphi;
-        const float ct = sqrtf(z0);
-        const float phi = 6.28318530717958647692f * z1;
-        float sp, cp;
-        sincosf(phi, &sp, &cp);
-        const float lx = cp * ct, ly = sp * ct, lz = sqrtf(1.0f - ct * ct);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            dir[q] = (Real)(lx * (float)rec[3 + q] + ly * (float)rec[6 + q] + lz * (float)rec[9 + q]);
-    }
+    ao_direction<Real>(F, rank, k, rec, rank_sample, pixels, mt_stream, dir);
     if (sizeof(Real) == 8) {
         double2 *o = reinterpret_cast<double2 *>(rays_out) + 3 * gid;
         o[0] = make_double2((double)rec[0], (double)rec[1]);
@@ -512,6 +485,10 @@ __global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pi
 
 // ---- host helpers ---------------------------------------------------------------------------------
 // spiral.c:97-140 NthBucketSpiral
+}  // namespace b200
+#include "sunsky.cuh"
+namespace b200 {
+
 static void nth_bucket_spiral(int n, int nxb, int nyb, int *bx, int *by)
 {
     const int minnb = nxb < nyb ? nxb : nyb;
@@ -631,14 +608,16 @@ static int mt_stream_launch(ri_b200_accel *a, uint32_t seed, uint32_t segments, 
 
 template <typename Real>
 static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_rgb, cudaStream_t st, ri_b200_frame_stats_t *stats,
-                          Real *d_dump, uint64_t dump_count, int packed = 0)
+                          Real *d_dump, uint64_t dump_count, int packed = 0, const ri_b200_sunsky_t *sky = nullptr)
 {
     std::vector<uint32_t> pix;
     std::vector<double> jit;
     pixel_order(f, pix);
     jitter_table(f.xsamples, f.ysamples, jit);
     const uint64_t npix = pix.size();
-    const int spp = f.xsamples * f.ysamples, N = f.ntheta * f.nphi;
+    // the sun-sky transport gathers with a fixed 8 x 8 pattern whatever Option "gather" says (ambientocclusion.c:371-374)
+    const int ntheta = sky ? 8 : f.ntheta, nphi = sky ? 8 : f.nphi;
+    const int spp = f.xsamples * f.ysamples, N = ntheta * nphi;
     const uint64_t nsamples = npix * (uint64_t)spp;
     if (nsamples >= 0xfffffff0ull) return fail("too many samples per rank for 32-bit sample ids");
 
@@ -647,8 +626,9 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     F.flength_signed = (double)(float)(f.is_rh ? -1.0 : 1.0) * f.flength;
     F.w = (double)f.width; F.h = (double)f.height;
     F.width = f.width; F.height = f.height; F.xsamples = f.xsamples; F.ysamples = f.ysamples;
-    F.ntheta = f.ntheta; F.nphi = f.nphi; F.spp = spp; F.nao = N;
+    F.ntheta = ntheta; F.nphi = nphi; F.spp = spp; F.nao = N;
     F.rng_mode = f.rng_mode; F.seed = f.seed;
+    F.ao_eps = sky ? 1.0e-5 : 1.0e-6;
 
     const int cap = stack_capacity(a);
     const size_t smem = (size_t)cap * kBlock * sizeof(uint32_t);
@@ -657,6 +637,8 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         CUDA_OK(cudaFuncSetAttribute(primary_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_OK(cudaFuncSetAttribute(ao_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    const size_t sky_smem = smem + 3 * kBlock * sizeof(float);
+    if (sky && sky_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(sunsky_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sky_smem));
 
     const uint32_t ntiles = (uint32_t)((nsamples + kScanTile - 1) / kScanTile);
     void *p = nullptr;
@@ -725,7 +707,21 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     // wins (C1: 11.5 ms vs 17.9 ms); everything else goes through the persistent traverser (1M-triangle soup: 167 ms vs 278 ms)
     const char *force = getenv("B200_FUSED_AO_TEST");         // test hook: exercise both paths on the same scene
     const bool fused_ao = force ? atoi(force) != 0 : (a->tree.ntris < 4096);
-    if (nao_rays && fused_ao) {                   // one lane per ray, generation fused with a one-ray-per-thread traversal
+    double *d_lo = nullptr;
+    if (sky) {                                    // sun-sky gather: one lane per ray, sky lookup on misses, per-sample sums in order
+        ri_b200_sunsky_t *d_sky = nullptr;
+        if (frame_buf(a, 8, sizeof(ri_b200_sunsky_t), &p)) return -1;
+        d_sky = (ri_b200_sunsky_t *)p;
+        if (frame_buf(a, 9, ((uint64_t)nhits + 1) * 3 * sizeof(double), &p)) return -1;
+        d_lo = (double *)p;
+        CUDA_OK(cudaMemcpyAsync(d_sky, sky, sizeof(ri_b200_sunsky_t), cudaMemcpyHostToDevice, st));
+        if (nao_rays) {
+            const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
+            if (blocks > 0x7fffffffull) return fail("too many gather rays in one frame pass");
+            sunsky_kernel<Real><<<(unsigned)blocks, kBlock, sky_smem, st>>>(S, F, d_sky, nao_rays, d_rec, d_ranks, d_pix, d_mt, d_lo, (uint32_t)cap);
+            LAUNCHED();
+        }
+    } else if (nao_rays && fused_ao) {                   // one lane per ray, generation fused with a one-ray-per-thread traversal
         const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
         if (blocks > 0x7fffffffull) return fail("too many occlusion rays in one frame pass");
         ao_kernel<Real><<<(unsigned)blocks, kBlock, smem, st>>>(S, F, nao_rays, 0u, d_rec, d_ranks, d_pix, d_mt, d_occ, d_dump, dump_count);
@@ -748,7 +744,8 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
     CUDA_OK(cudaEventRecord(a->ev[4], st));
     if (npix) {
-        resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed);
+        if (sky) resolve_rgb_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_lo, d_rgb, packed);
+        else resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed);
         LAUNCHED();
     }
     CUDA_OK(cudaGetLastError());
@@ -757,7 +754,8 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         CUDA_OK(cudaEventSynchronize(a->ev[5]));
         float ms;
         std::memset(stats, 0, sizeof(*stats));
-        stats->nrays_primary = nsamples; stats->nrays_ao = nao_rays; stats->nhits_primary = nhits;
+        stats->nrays_primary = nsamples; stats->nhits_primary = nhits;
+        stats->nrays_ao = nao_rays + (sky ? (uint64_t)nhits * (uint64_t)sky->nsun : 0);     // + one shadow ray per sun light and hit sample
         CUDA_OK(cudaEventElapsedTime(&ms, a->ev[0], a->ev[5])); stats->ms_total = ms;
         CUDA_OK(cudaEventElapsedTime(&ms, a->ev[0], a->ev[1])); stats->ms_primary = ms;
         CUDA_OK(cudaEventElapsedTime(&ms, a->ev[2], a->ev[3])); stats->ms_rng = ms;
@@ -834,6 +832,66 @@ extern "C" int ri_b200_render_ao(ri_b200_accel_t *a, const ri_b200_frame_t *f, f
     CUDA_OK(cudaMemcpyAsync(rgb_out, p, bytes, cudaMemcpyDeviceToHost, a->stream));
     CUDA_OK(cudaStreamSynchronize(a->stream));
     return 0;
+}
+
+extern "C" int ri_b200_render_sunsky(ri_b200_accel_t *a, const ri_b200_frame_t *f, const ri_b200_sunsky_t *sky, float *rgb_out,
+                                     ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!rgb_out || !sky) return fail("null argument");
+    if (sky->nsun < 0 || sky->nsun > 4) return fail("bad sun light count %d", sky->nsun);
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    const size_t bytes = (size_t)f->width * f->height * 3 * sizeof(float);
+    void *p = nullptr;
+    if (frame_buf(a, 6, bytes, &p)) return -1;
+    int rc;
+    if (f->precision == RI_B200_PREC_F64) rc = render_ao_impl<double>(a, *f, (float *)p, a->stream, stats, nullptr, 0, 0, sky);
+    else rc = render_ao_impl<float>(a, *f, (float *)p, a->stream, stats, nullptr, 0, 0, sky);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(rgb_out, p, bytes, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_OK(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
+extern "C" int ri_b200_render_sunsky_tiles_dev(ri_b200_accel_t *a, const ri_b200_frame_t *f, const ri_b200_sunsky_t *sky, float *d_packed,
+                                               void *stream, ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!d_packed || !sky) return fail("null argument");
+    if (sky->nsun < 0 || sky->nsun > 4) return fail("bad sun light count %d", sky->nsun);
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
+    if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_packed, st, stats, nullptr, 0, 1, sky);
+    return render_ao_impl<float>(a, *f, d_packed, st, stats, nullptr, 0, 1, sky);
+}
+
+extern "C" int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device)
+{
+    if (!sky || (n && (!dirs || !rgb_out))) return fail("null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: libb200accel has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail("bad device %d", device);
+    if (n == 0) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    ri_b200_sunsky_t *d_sky = nullptr;
+    float *d_dirs = nullptr, *d_rgb = nullptr;
+    auto body = [&]() -> int {
+        CUDA_OK(cudaMalloc((void **)&d_sky, sizeof(*sky)));
+        CUDA_OK(cudaMalloc((void **)&d_dirs, n * 3 * sizeof(float)));
+        CUDA_OK(cudaMalloc((void **)&d_rgb, n * 3 * sizeof(float)));
+        CUDA_OK(cudaMemcpy(d_sky, sky, sizeof(*sky), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_dirs, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+        sky_rgb_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d_sky, d_dirs, n, d_rgb);
+        LAUNCHED();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpy(rgb_out, d_rgb, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    const int rc = body();
+    cudaFree(d_sky); cudaFree(d_dirs); cudaFree(d_rgb);
+    return rc;
 }
 
 extern "C" int ri_b200_mt_stream(ri_b200_accel_t *a, uint32_t seed, uint64_t n, uint32_t *out_u32, int device)
