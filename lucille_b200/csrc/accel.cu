@@ -65,6 +65,8 @@ struct ri_b200_accel {
     // staging for host-buffer batches (double buffered)
     void    *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
     uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
+    void    *d_whole_in = nullptr, *d_whole_out = nullptr;     // whole-batch staging of the streamed occlusion path
+    uint64_t whole_in_bytes = 0, whole_out_bytes = 0;
     unsigned long long *d_counters = nullptr;
     // MT19937 jump-ahead: polynomial table and cached window states at segment starts (frame.cuh)
     uint32_t *d_mt_polys = nullptr, *d_mt_states = nullptr;
@@ -187,7 +189,8 @@ static int stack_capacity(const ri_b200_accel *a)
 
 template <typename Real, bool ANYHIT, bool COUNT>
 static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typename RayIO<Real>::Hit *d_hits, uint8_t *d_occ,
-                        unsigned long long *d_counters, cudaStream_t st, uint32_t *d_counts = nullptr, uint32_t rays_per_count = 1)
+                        unsigned long long *d_counters, cudaStream_t st, uint32_t *d_counts = nullptr, uint32_t rays_per_count = 1,
+                        const unsigned int *d_ready = nullptr, unsigned int *d_fault = nullptr)
 {
     if (n == 0) return 0;
     const int cap = stack_capacity(a);
@@ -196,7 +199,8 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
     if (!COUNT) {
         // production path: persistent warps with ray replacement; batches above 2^31 rays are split
         auto pk = trace_persistent_kernel<Real, ANYHIT>;
-        auto pool = occluded_pool_kernel<Real>;
+        // 4 CTAs x 256 threads per SM at 64 registers (fp32): measured 979 Mrays/s on C3 against 878 with 3 CTAs at 72 registers
+        auto pool = occluded_pool_kernel<Real, (sizeof(Real) == 4 ? 4 : 3)>;
         static const bool use_pool = !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);   // A/B knob: 0 = vote-scheduled kernel
         const bool pooled = ANYHIT && use_pool;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
@@ -224,7 +228,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             if (pooled)
                 pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                       d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,
-                                                      rays_per_count, ctr, refill_at, (uint32_t)stack_capacity(a));
+                                                      rays_per_count, ctr, refill_at, (uint32_t)stack_capacity(a), d_ready, d_fault);
             else
                 pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
@@ -317,7 +321,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         if (upload(&a->d_tris64t, a->flat.tris64t, a->device_bytes)) return -1;
         if (upload(&a->d_slot_of_prim, a->flat.slot_of_prim, a->device_bytes)) return -1;
         CUDA_OK(cudaMalloc((void **)&a->d_counters, 8 * sizeof(unsigned long long)));
-        CUDA_OK(cudaMalloc((void **)&a->d_work, 64 * sizeof(unsigned int)));
+        CUDA_OK(cudaMalloc((void **)&a->d_work, 66 * sizeof(unsigned int)));      // 64 work counters, then the upload cursor and fault flag of the streamed host-buffer path
         CUDA_OK(cudaMallocHost(&a->h_pin, 4096));
         CUDA_OK(cudaMalloc(&a->d_one, 4096));
         return 0;
@@ -340,6 +344,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->stream) cudaStreamSynchronize(a->stream);
     cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
+    cudaFree(a->d_whole_in); cudaFree(a->d_whole_out);
     for (auto p : a->d_frame) cudaFree(p);
     cudaFree(a->d_counters); cudaFree(a->d_one); cudaFree(a->d_work); cudaFree(a->d_mt_polys); cudaFree(a->d_mt_states);
     if (a->h_pin) cudaFreeHost(a->h_pin);
@@ -475,6 +480,12 @@ static uint64_t chunk_rays()
     return v < 1024 ? 1024 : v;
 }
 
+static uint64_t chunk_ramp()
+{
+    static const uint64_t v = getenv("B200_CHUNK0") ? (uint64_t)atoll(getenv("B200_CHUNK0")) : (1ull << 18);
+    return v < 1024 ? 1024 : v;
+}
+
 static int ensure_stage(ri_b200_accel *a, uint64_t in_bytes, uint64_t out_bytes)
 {
     if (a->stage_in_bytes < in_bytes) {
@@ -488,6 +499,57 @@ static int ensure_stage(ri_b200_accel *a, uint64_t in_bytes, uint64_t out_bytes)
     return 0;
 }
 
+// Occlusion batches from HOST buffers, streamed: ONE persistent launch consumes the batch while the copy engine is still
+// uploading it.  The upload goes piece by piece on a copy stream, each piece followed (in stream order) by a 4-byte write of
+// the number of rays that have landed; a warp that claims rays beyond that cursor waits for it (pool.cuh).  Against one launch
+// per piece this removes the ramp and the tail of every launch but one (2 Mi-ray pieces: 2.35 ms each instead of 2.14).
+template <typename Real>
+static int host_occluded_streamed(ri_b200_accel *a, const Real *rays, uint64_t n, uint8_t *out)
+{
+    const uint64_t ray_bytes = RayIO<Real>::kRayStride * sizeof(Real);
+    if (a->whole_in_bytes < n * ray_bytes) {
+        cudaFree(a->d_whole_in); a->d_whole_in = nullptr; a->whole_in_bytes = 0;
+        CUDA_OK(cudaMalloc(&a->d_whole_in, n * ray_bytes));
+        a->whole_in_bytes = n * ray_bytes;
+    }
+    if (a->whole_out_bytes < n) {
+        cudaFree(a->d_whole_out); a->d_whole_out = nullptr; a->whole_out_bytes = 0;
+        CUDA_OK(cudaMalloc(&a->d_whole_out, n));
+        a->whole_out_bytes = n;
+    }
+    unsigned int *d_ready = a->d_work + 64, *d_fault = a->d_work + 65;
+    uint32_t *cursor = (uint32_t *)a->h_pin;                       // pinned: one value per piece, <= 1024 pieces
+    cudaStream_t ks = a->stream, cs = a->copy_stream[0];
+    // piece size: measured on C3 (16 Mi rays, kernel alone 17.1 ms): 2 Mi 18.6 ms, 1 Mi 18.2, 512 Ki 18.0, 256 Ki 17.9, 128 Ki 17.95
+    static const uint64_t piece0 = getenv("B200_PIECE") ? (uint64_t)atoll(getenv("B200_PIECE")) : (1ull << 18);
+    uint64_t piece = piece0 < 1024 ? 1024 : piece0;
+    while ((n + piece - 1) / piece > 1000) piece *= 2;
+
+    CUDA_OK(cudaMemsetAsync(d_ready, 0, 2 * sizeof(unsigned int), ks));
+    CUDA_OK(cudaEventRecord(a->ev[6], ks));
+    CUDA_OK(cudaStreamWaitEvent(cs, a->ev[6], 0));
+    if (launch_trace<Real, true, false>(a, (const Real *)a->d_whole_in, n, nullptr, (uint8_t *)a->d_whole_out, nullptr, ks, nullptr, 1,
+                                        d_ready, d_fault)) return -1;
+    uint64_t done = 0;
+    int k = 0;
+    while (done < n) {
+        const uint64_t m = (n - done) < piece ? (n - done) : piece;
+        CUDA_OK(cudaMemcpyAsync((char *)a->d_whole_in + done * ray_bytes, (const char *)rays + done * ray_bytes, m * ray_bytes,
+                                cudaMemcpyHostToDevice, cs));
+        done += m;
+        cursor[k] = (uint32_t)done;
+        CUDA_OK(cudaMemcpyAsync(d_ready, &cursor[k], sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+        ++k;
+    }
+    CUDA_OK(cudaMemcpyAsync(out, a->d_whole_out, n, cudaMemcpyDeviceToHost, ks));
+    unsigned int *h_fault = (unsigned int *)((char *)a->h_pin + 4092);
+    CUDA_OK(cudaMemcpyAsync(h_fault, d_fault, sizeof(unsigned int), cudaMemcpyDeviceToHost, ks));
+    CUDA_OK(cudaStreamSynchronize(cs));
+    CUDA_OK(cudaStreamSynchronize(ks));
+    if (*h_fault) return fail("streamed upload never reached the traversal kernel");
+    return 0;
+}
+
 template <typename Real, bool ANYHIT>
 static int host_batch(ri_b200_accel *a, const Real *rays, uint64_t n, void *out)
 {
@@ -497,20 +559,35 @@ static int host_batch(ri_b200_accel *a, const Real *rays, uint64_t n, void *out)
     if (!rays || !out) return fail("null buffer");
     std::lock_guard<std::mutex> lock(a->mu);
     CUDA_OK(cudaSetDevice(a->device));
+    {
+        static const bool streamed = !(getenv("B200_STREAMED") && atoi(getenv("B200_STREAMED")) == 0) &&
+                                     !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);
+        if (ANYHIT && streamed && n < (1ull << 31)) return host_occluded_streamed<Real>(a, rays, n, (uint8_t *)out);
+    }
     const uint64_t ray_bytes = RayIO<Real>::kRayStride * sizeof(Real);
     const uint64_t out_bytes = ANYHIT ? 1 : sizeof(Hit);
     const uint64_t chunk = n < chunk_rays() ? n : chunk_rays();
     if (ensure_stage(a, chunk * ray_bytes, chunk * out_bytes)) return -1;
 
-    uint64_t done = 0;
+    // chunk sizes ramp up (256 Ki, 512 Ki, ... up to `chunk`): the first upload, which nothing can hide, stays short
+    uint64_t done = 0, m_next = chunk_ramp() < chunk ? chunk_ramp() : chunk;
     int slot = 0;
+    const bool trace = getenv("B200_E2E_TRACE") != nullptr;     // diagnostics: per-chunk device timeline on stderr
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); } };
     while (done < n) {
-        const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
+        const uint64_t m = (n - done) < m_next ? (n - done) : m_next;
+        m_next = (m_next * 2 < chunk) ? m_next * 2 : chunk;
         cudaStream_t st = a->copy_stream[slot];
-        CUDA_OK(cudaMemcpyAsync(a->d_in[slot], (const char *)rays + done * ray_bytes, m * ray_bytes, cudaMemcpyHostToDevice, st));
-        if (launch_trace<Real, ANYHIT, false>(a, (const Real *)a->d_in[slot], m, ANYHIT ? nullptr : (Hit *)a->d_out[slot],
+        const int dbg_skip = getenv("B200_E2E_SKIP") ? atoi(getenv("B200_E2E_SKIP")) : 0;    // diagnostics only: 1 = no upload, 2 = no kernel
+        mark(st);
+        if (dbg_skip != 1) CUDA_OK(cudaMemcpyAsync(a->d_in[slot], (const char *)rays + done * ray_bytes, m * ray_bytes, cudaMemcpyHostToDevice, st));
+        mark(st);
+        if (dbg_skip != 2 && launch_trace<Real, ANYHIT, false>(a, (const Real *)a->d_in[slot], m, ANYHIT ? nullptr : (Hit *)a->d_out[slot],
                                               ANYHIT ? (uint8_t *)a->d_out[slot] : nullptr, nullptr, st)) return -1;
+        mark(st);
         CUDA_OK(cudaMemcpyAsync((char *)out + done * out_bytes, a->d_out[slot], m * out_bytes, cudaMemcpyDeviceToHost, st));
+        mark(st);
         done += m;
         slot ^= 1;
         // the slot we are about to reuse must have drained (its stream runs copy->kernel->copy in order)
@@ -518,6 +595,12 @@ static int host_batch(ri_b200_accel *a, const Real *rays, uint64_t n, void *out)
     }
     CUDA_OK(cudaStreamSynchronize(a->copy_stream[0]));
     CUDA_OK(cudaStreamSynchronize(a->copy_stream[1]));
+    for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+        float t[4];
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[i + k]);
+        fprintf(stderr, "[e2e] chunk %zu: upload %.3f-%.3f kernel -%.3f download -%.3f ms\n", i / 4, t[0], t[1], t[2], t[3]);
+    }
+    for (auto e : tev) cudaEventDestroy(e);
     return 0;
 }
 

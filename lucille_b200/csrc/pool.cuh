@@ -114,11 +114,14 @@ __device__ __forceinline__ unsigned ballot_bit(uint32_t x, uint32_t bit)
 template <typename Real> constexpr size_t pool_smem_bytes(int stack_cap)
 { return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2)); }
 
-template <typename Real>
-__global__ void __launch_bounds__(kBlock, sizeof(Real) == 4 ? 4 : 3)
+constexpr unsigned kPoolSpinCap = 20u * 1000u * 1000u;        // x 200 ns: seconds, far beyond any upload
+
+template <typename Real, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
 occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
                      const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
-                     unsigned int *__restrict__ work_counter, const uint32_t refill_at, const uint32_t stack_cap)
+                     unsigned int *__restrict__ work_counter, const uint32_t refill_at, const uint32_t stack_cap,
+                     const unsigned int *__restrict__ ready, unsigned int *__restrict__ fault)
 {
     using P = Prec<Real>;
     constexpr unsigned FULL = 0xffffffffu;
@@ -155,6 +158,21 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                 if (base >= n) { exhausted = true; break; }
                 chunk_next = base;
                 chunk_end = (n - base < chunk) ? n : base + chunk;
+                if (ready) {
+                    // streamed upload (host-buffer entry points): the copy engine is still writing the batch while this kernel
+                    // runs; `*ready` = number of leading rays that have landed, bumped in stream order after every piece
+                    if (lane == 0) {
+                        unsigned spins = 0, have;
+                        for (;;) {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(ready) : "memory");
+                            if (have >= chunk_end) break;
+                            __nanosleep(200);
+                            if (++spins > kPoolSpinCap) { atomicExch(fault, 1u); break; }     // upload never arrived: give up loudly
+                        }
+                    }
+                    __syncwarp();
+                    if (*(volatile unsigned int *)fault) { exhausted = true; break; }
+                }
             }
             const unsigned avail = chunk_end - chunk_next;
             const unsigned n_idle = __popc(idle);
