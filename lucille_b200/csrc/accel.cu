@@ -286,6 +286,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         h->precisions = precisions;
         build_tree(tri_xyz, ntris, h->tree);
         flatten_tree(h->tree, 1024, (precisions & RI_B200_PREC_F32) != 0, (precisions & RI_B200_PREC_F64) != 0, h->flat);
+        if (h->flat.overflow) { fail("too many triangle slots for the 27-bit leaf word"); delete h; return nullptr; }
         return h;
     }
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -302,6 +303,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
 
     build_tree(tri_xyz, ntris, a->tree);
     flatten_tree(a->tree, 1024, (precisions & RI_B200_PREC_F32) != 0, (precisions & RI_B200_PREC_F64) != 0, a->flat);
+    if (a->flat.overflow) { fail("too many triangle slots for the 27-bit leaf word"); delete a; return nullptr; }
 
     auto t0 = std::chrono::steady_clock::now();
     auto body = [&]() -> int {

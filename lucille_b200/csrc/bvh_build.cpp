@@ -429,16 +429,19 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
     }
     out.ninner = (uint32_t)order.size();
 
-    // triangle slots: each leaf starts at an even slot (DFS order of leaves == post-build triangle order)
+    // triangle slots: each leaf starts at a slot that is a multiple of four and owns round_up(ntris, 4) slots (DFS order of
+    // leaves == post-build triangle order): fp32 pairs stay 32-byte aligned, and the rows of the leaf-transposed copies below
+    // start on 64-byte (fp32) / 128-byte (fp64) boundaries, which is what lets neighbouring lanes share L1 wavefronts
     std::vector<uint32_t> slot_of(nn, 0);
     uint64_t nslots = 0;
     for (size_t c = 0; c < nn; ++c) {
         const CanonNode &n = t.nodes[c];
         if (!n.is_leaf) continue;
         slot_of[c] = (uint32_t)nslots;
-        nslots += (uint64_t)((n.ntris + 1) & ~1ll);
+        nslots += (uint64_t)((n.ntris + 3) & ~3ll);
     }
     out.nslots = nslots;
+    if (nslots >= (1ull << kLeafShift)) { out = FlatTree(); out.overflow = true; return; }     // the leaf word holds a 27-bit slot
     out.slot_of_prim.assign((size_t)t.ntris, 0);
 
     auto word = [&](int64_t c) -> uint32_t {
@@ -497,8 +500,8 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
                 d.prim = p;
             }
         }
-        if (n.ntris & 1) {                                   // filler slot: zero-area triangle, prim = MISS
-            const uint64_t slot = (uint64_t)slot_of[c] + (uint64_t)n.ntris;
+        for (int64_t i = n.ntris; i < ((n.ntris + 3) & ~3ll); ++i) {      // filler slots: zero-area triangles, prim = MISS
+            const uint64_t slot = (uint64_t)slot_of[c] + (uint64_t)i;
             if (want32) out.tris32[(size_t)slot].prim = 0xffffffffu;
             if (want64) out.tris64[(size_t)slot].prim = 0xffffffffull;
         }
@@ -510,17 +513,17 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
     for (size_t c = 0; c < nn; ++c) {
         const CanonNode &n = t.nodes[c];
         if (!n.is_leaf) continue;
-        const uint64_t slot0 = slot_of[c], ns = (uint64_t)((n.ntris + 1) & ~1ll);
-        if (want32) {                                        // item = pair of slots = 3 chunks of 32 B
-            const uint64_t m = ns / 2;
+        const uint64_t slot0 = slot_of[c], ns = (uint64_t)((n.ntris + 3) & ~3ll);
+        if (want32) {                                        // item = pair of slots = 3 chunks of 32 B; row = ns/2 chunks
+            const uint64_t m = ns / 2, used = (uint64_t)((n.ntris + 1) / 2);
             const char *src = reinterpret_cast<const char *>(out.tris32.data() + slot0);
             char *dst = reinterpret_cast<char *>(out.tris32t.data() + slot0);
             for (uint64_t j = 0; j < m; ++j)
                 for (uint64_t k = 0; k < 3; ++k) std::memcpy(dst + (k * m + j) * 32, src + j * 96 + k * 32, 32);
             if (n.ntris & 1) {
-                // the filler slot is masked by its item's validity bit, never by its determinant: give it unit edges so
-                // that 1/det stays on the fast path of the reciprocal (a zero determinant takes the slow one)
-                float *e = reinterpret_cast<float *>(dst + (2 * m + (m - 1)) * 32);
+                // the filler slot of the last pair is masked by its validity bit, never by its determinant: give it unit edges
+                // so that 1/det stays on the fast path of the reciprocal (a zero determinant takes the slow one)
+                float *e = reinterpret_cast<float *>(dst + (2 * m + (used - 1)) * 32);
                 e[0] = 1.0f; e[5] = 1.0f;                    // b.e1 = (1,0,0), b.e2 = (0,1,0)
             }
         }

@@ -43,7 +43,7 @@ void build_tree(const double *tri_xyz, uint64_t ntris, HostTree &out, int nthrea
 constexpr uint32_t kLeafFlag  = 0x80000000u;
 constexpr uint32_t kDoneWord  = 0x7fffffffu;
 constexpr uint32_t kLeafShift = 27;                  // word = flag | (ntris-1)<<27 | first triangle SLOT (always even)
-constexpr uint64_t kMaxTris   = (1ull << 27) / 17 * 16 - 2;   // slots = sum over leaves of ntris rounded up to even
+constexpr uint64_t kMaxTris   = (1ull << 27) - 4;              // necessary only: flatten_tree checks the real slot count (sum of round_up(ntris, 4))
 
 struct Node32 {                 // 64 B, read as 4 x LDG.128
     float    x[4];              // lo0.x hi0.x lo1.x hi1.x   (slot 0 = left child, slot 1 = right child)
@@ -58,13 +58,14 @@ struct Node64 {                 // 128 B
     uint32_t c0, c1, axis, pad;
     uint32_t pad2[4];
 };
-// Triangle SLOTS.  Every leaf starts at an even slot and owns round_up(ntris, 2) slots, so a pair of fp32 slots is one
-// 32-byte-aligned 96-byte run = 3 x LDG.256; the odd leftover slot of a leaf holds a zero-area triangle (never hit:
-// |det| <= 1e-14 rejects it, bvh.c:759-763).  `prim` = position in the post-build triangle order (the hit id).
+// Triangle SLOTS.  Every leaf starts at a multiple-of-four slot and owns round_up(ntris, 4) slots, so a pair of fp32 slots is
+// one 32-byte-aligned 96-byte run = 3 x LDG.256; the leftover slots of a leaf hold zero-area triangles (never hit:
+// |det| <= 1e-14 rejects them, bvh.c:759-763).  `prim` = position in the post-build triangle order (the hit id).
 struct Tri32 { float v0[3]; uint32_t prim; float e1[3]; uint32_t pad1; float e2[3]; uint32_t pad2; };          // 48 B
 struct Tri64 { double v0[3]; uint64_t prim; double e1[3]; uint64_t pad1; double e2[3]; uint64_t pad2; };       // 96 B = 3 x LDG.256
 
 struct FlatTree {
+    bool     overflow = false;       // more triangle slots than the 27-bit field of a leaf word can address
     uint32_t root_word = kDoneWord;  // inner index, leaf word, or kDoneWord for an empty scene
     uint32_t ninner = 0;
     uint32_t top_count = 0;          // the first top_count inner nodes are in BFS order (SMEM-resident cluster)
@@ -73,7 +74,7 @@ struct FlatTree {
     std::vector<Tri32>  tris32;      // nslots entries
     std::vector<Tri64>  tris64;
     // the same slots, 32-byte chunks TRANSPOSED inside each leaf (pooled occlusion kernel, pool.cuh): a leaf at slot0
-    // with m items (fp32: m = pairs of slots, fp64: m = slots) keeps chunk k of item j at byte
+    // whose rows hold m items (fp32: m = slots/2 pairs, fp64: m = slots; slots = round_up(ntris, 4)) keeps chunk k of item j at byte
     // slot0 * sizeof(slot) + (k * m + j) * 32, so lanes testing consecutive items read consecutive 32-byte chunks
     std::vector<Tri32>  tris32t;
     std::vector<Tri64>  tris64t;

@@ -20,7 +20,8 @@
 // can only turn a later rejection `t > 1e38` into an acceptance with t >= 1e38, which does not commit: bvh.c:850.)
 //
 // Memory: node records as in persistent.cuh (2 x LDG.256 per node).  Triangles come from the leaf-TRANSPOSED copy
-// (FlatTree::tris32t / tris64t): chunk k of item j of a leaf with m items sits at slot0*sizeof(slot) + (k*m + j)*32, so
+// (FlatTree::tris32t / tris64t): chunk k of item j of a leaf whose rows hold m items sits at slot0*sizeof(slot) + (k*m + j)*32
+// (rows start on 64-byte boundaries for fp32, 128-byte ones for fp64), so
 // the lanes that test consecutive items of one leaf read consecutive 32-byte chunks -- one L1 wavefront per 128-byte
 // line instead of one per lane.
 #pragma once
@@ -35,7 +36,7 @@ template <> struct PoolLeaf<float> {                 // item = two triangle slot
     static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
                                                 const float org[3], const float dir[3])
     {
-        const uint32_t m = (ntris + 1u) >> 1;
+        const uint32_t m = ((ntris + 3u) >> 2) << 1;                                      // row length in pairs: the leaf owns round_up(ntris, 4) slots
         const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = o1 + 2u * m;      // 16-byte units: < 2^29
         const F8 q0 = ldg256(trisT + (size_t)o0 * 16u), q1 = ldg256(trisT + (size_t)o1 * 16u), q2 = ldg256(trisT + (size_t)o2 * 16u);
         TriRegs<float> a, b;
@@ -59,7 +60,7 @@ template <> struct PoolLeaf<double> {                // item = one triangle slot
     static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
                                                 const double org[3], const double dir[3])
     {
-        const uint32_t m = (ntris + 1u) & ~1u;       // slots owned by the leaf
+        const uint32_t m = (ntris + 3u) & ~3u;       // slots owned by the leaf = row length
         const uint32_t o0 = slot0 * 3u + j, o1 = o0 + m, o2 = o1 + m;                       // 32-byte units: < 2^29
         const D4 q0 = ldg256d(trisT + (size_t)o0 * 32u), q1 = ldg256d(trisT + (size_t)o1 * 32u), q2 = ldg256d(trisT + (size_t)o2 * 32u);
         TriRegs<double> a;

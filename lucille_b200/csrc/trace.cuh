@@ -132,7 +132,7 @@ __device__ __forceinline__ void load_node_wide(const Node64 *p, NodeRegs<double>
     r.c0 = w.x; r.c1 = w.y; r.axis = w.z;
 }
 
-// a PAIR of fp32 triangle slots (even slot first): 96 contiguous, 32-byte-aligned bytes = 3 x LDG.256
+// a PAIR of fp32 triangle slots (even slot first; leaves start at multiples of four): 96 contiguous, 32-byte-aligned bytes = 3 x LDG.256
 __device__ __forceinline__ void load_tri_pair(const Tri32 *p, TriRegs<float> &a, TriRegs<float> &b)
 {
     const char *c = reinterpret_cast<const char *>(p);

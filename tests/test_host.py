@@ -102,17 +102,17 @@ def test_flat_records_decode_to_canonical_tree(n):
                     for got, want in ((lb, c["lbox"]), (rb, c["rbox"])):
                         assert np.all(got[:3] <= want[:3]) and np.all(got[3:] >= want[3:])
                         assert np.all(np.abs(got - want) <= np.spacing(np.abs(want).astype(np.float32)).astype(np.float64))
-    # triangle slots: every leaf starts at an even slot, owns round_up(ntris, 2) slots, carries prim ids in post-build
-    # order; v0, e1 = v1 - v0, e2 = v2 - v0; the odd filler slot is a zero-area triangle with prim = MISS
+    # triangle slots: every leaf starts at a multiple-of-four slot, owns round_up(ntris, 4) slots, carries prim ids in post-build
+    # order; v0, e1 = v1 - v0, e2 = v2 - v0; the filler slots are zero-area triangles with prim = MISS
     order = a.triorder()
     src = tris[order]
     leaves = canon[canon["is_leaf"] == 1]
     t64, t32 = flat["tris64"], flat["tris32"]
-    assert flat["nslots"] == int(((leaves["ntris"] + 1) // 2 * 2).sum()) == len(t32) == len(t64)
+    assert flat["nslots"] == int(((leaves["ntris"] + 3) // 4 * 4).sum()) == len(t32) == len(t64)
     leaf_words = [d for d in _decode(flat, 32) if d["is_leaf"]]
     for d, c in zip(leaf_words, leaves):
         s0, cnt, p0 = d["tri_start"], int(c["ntris"]), int(c["tri_start"])
-        assert s0 % 2 == 0
+        assert s0 % 4 == 0
         assert np.array_equal(t32["prim"][s0:s0 + cnt], np.arange(p0, p0 + cnt))
         assert np.array_equal(t64["prim"][s0:s0 + cnt], np.arange(p0, p0 + cnt))
         assert np.array_equal(t64["v0"][s0:s0 + cnt], src[p0:p0 + cnt, 0])
@@ -121,8 +121,8 @@ def test_flat_records_decode_to_canonical_tree(n):
         s32 = src[p0:p0 + cnt].astype(np.float32)
         assert np.array_equal(t32["v0"][s0:s0 + cnt], s32[:, 0]) and np.array_equal(t32["e1"][s0:s0 + cnt], s32[:, 1] - s32[:, 0])
         assert np.array_equal(t32["e2"][s0:s0 + cnt], s32[:, 2] - s32[:, 0])
-        if cnt & 1:
-            assert t32["prim"][s0 + cnt] == 0xFFFFFFFF and not t32["e1"][s0 + cnt].any() and not t32["e2"][s0 + cnt].any()
+        for f in range(s0 + cnt, s0 + (cnt + 3) // 4 * 4):
+            assert t32["prim"][f] == 0xFFFFFFFF and not t32["e1"][f].any() and not t32["e2"][f].any()
     assert flat["top_count"] == min(1024, flat["ninner"])
 
 
