@@ -548,8 +548,7 @@ static int host_occluded_streamed(ri_b200_accel *a, const Real *rays, uint64_t n
     CUDA_OK(cudaMemcpyAsync(h_fault, d_fault, sizeof(unsigned int), cudaMemcpyDeviceToHost, ks));
     CUDA_OK(cudaStreamSynchronize(cs));
     CUDA_OK(cudaStreamSynchronize(ks));
-    if (*h_fault) return fail("streamed upload never reached the traversal kernel");
-    return 0;
+    return *h_fault ? 1 : 0;          // 1: the upload could not run beside the kernel -- the caller takes the launch-per-piece path
 }
 
 template <typename Real, bool ANYHIT>
@@ -564,7 +563,10 @@ static int host_batch(ri_b200_accel *a, const Real *rays, uint64_t n, void *out)
     {
         static const bool streamed = !(getenv("B200_STREAMED") && atoi(getenv("B200_STREAMED")) == 0) &&
                                      !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);
-        if (ANYHIT && streamed && n < (1ull << 31)) return host_occluded_streamed<Real>(a, rays, n, (uint8_t *)out);
+        if (ANYHIT && streamed && n < (1ull << 31)) {
+            const int rc = host_occluded_streamed<Real>(a, rays, n, (uint8_t *)out);
+            if (rc <= 0) return rc;
+        }
     }
     const uint64_t ray_bytes = RayIO<Real>::kRayStride * sizeof(Real);
     const uint64_t out_bytes = ANYHIT ? 1 : sizeof(Hit);

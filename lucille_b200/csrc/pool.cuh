@@ -115,7 +115,9 @@ __device__ __forceinline__ unsigned ballot_bit(uint32_t x, uint32_t bit)
 template <typename Real> constexpr size_t pool_smem_bytes(int stack_cap)
 { return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2)); }
 
-constexpr unsigned kPoolSpinCap = 20u * 1000u * 1000u;        // x 200 ns: seconds, far beyond any upload
+// x 200 ns ~ 0.1 s and more: a piece of the upload lands every 0.15 ms.  The cap is what ends the launch when the copies cannot
+// run beside the kernel at all (a profiler that serialises the two streams): the host then falls back to one launch per piece.
+constexpr unsigned kPoolSpinCap = 500u * 1000u;
 
 template <typename Real, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)

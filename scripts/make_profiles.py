@@ -28,8 +28,9 @@ with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
             "| kernel | grid | block | launches | avg ms | share of listed GPU time |\n|---|---|---|---:|---:|---:|\n")
     for (k, grid, block), v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"| `{k}` | {grid} | {block} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {sum(v) / tot * 100:.1f} % |\n")
-    f.write("\n`trace_persistent_kernel<float, 1>` = occlusion (any-hit) traverser: grid 592 = 4 CTAs x 148 SMs; the 16 Mi-ray launches are the\n"
-            "warm-up + timed steps, the 1 Mi-ray ones are the chunks of the host-buffer (e2e) path.\n"
+    f.write("\n`occluded_pool_kernel<float, 4>` = pooled occlusion (any-hit) traverser, the timed kernel: grid 592 = 4 CTAs x 148 SMs; every\n"
+            "launch traces the whole 16 Mi-ray batch (warm-up, timed steps, and the streamed host-buffer (e2e) calls, which are ONE launch each).\n"
+            "`trace_persistent_kernel<float, 0>` = closest-hit traverser (reported as closest_hit_mrays_s, and the primary rays of the set-up).\n"
             "`trace_batch_kernel<..., 1>` = one-ray-per-thread kernel with the reference's traversal counters (I, T of the roofline formula), run once, untimed.\n")
 
 # ---- full capture of the timed kernel ---------------------------------------------------------------------------------
@@ -62,9 +63,11 @@ with open(os.path.join(out_dir, f"{tag}_occluded_f32_c3.md"), "w") as f:
             f.write(f"| {k} | {m[k][0]} | {m[k][1]} |\n")
     f.write(f"\nDRAM traffic of the launch: {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written = {(rd + wr) / 1e6:.1f} MB "
             "(the 512 MiB ray batch + the 54 MB scene once + 16 MiB of occlusion bytes); algorithmic bytes of the same launch: "
-            "174 GB (10.39 KB/ray) -- the scene records are re-read from L2 (hit rate 98.8 %), not from HBM.\n\n"
-            "Reading: no tensor pipe (by design), DRAM idle, L2 at a third of its peak; the kernel is limited by warp-instruction issue and by L1 "
-            "wavefronts (one per lane-request for divergent loads), with ~14 of 32 lanes active per issued instruction.\n")
+            "174 GB (10.39 KB/ray) -- the scene records are re-read from L2, not from HBM.\n\n"
+            "Reading: no tensor pipe (by design), DRAM idle, L2 at a quarter of its peak; the kernel is limited by warp-instruction issue "
+            "(~77 % of the issue slots) with the L1 data pipe next (~75-80 % of its wavefronts: one per 32-byte sector of a lane's node record, "
+            "shared between neighbouring lanes for the leaf-transposed triangle rows); ~26 of 32 lanes are active per issued instruction "
+            "(15 in the vote-scheduled kernel this one replaced: profiles/r01_early_*).\n")
 with open(os.path.join(out_dir, "traffic.json"), "w") as f:
     json.dump({"occluded_f32_c3_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": f"profiles/{tag}_occluded_f32_c3.md"}, f)
 
@@ -84,7 +87,7 @@ with open(os.path.join(out_dir, f"{tag}_occluded_f32_c3_sass.md"), "w") as f:
             "| opcode | share of executed warp instructions |\n|---|---:|\n")
     for k, v in sorted(opc.items(), key=lambda kv: -kv[1])[:24]:
         f.write(f"| {k} | {v / total * 100:.1f} % |\n")
-    f.write("\n`LDG.E.ENL2.256` = the 256-bit node / triangle-pair loads; `FMNMX3` = 3-input min/max of the slab test; `VOTE`/`POPC` = the warp vote.\n\n"
+    f.write("\n`LDG.E.ENL2.256` = the 256-bit node / triangle-chunk loads; `FMNMX3` = 3-input min/max of the slab test; `VOTE`/`POPC`/`REDUX` = the pool bookkeeping (prefix sums from bit-sliced ballots, item totals).\n\n"
             "## lines with the most stall samples\n\n| samples | executed | avg threads | SASS |\n|---:|---:|---:|---|\n")
     for r in sorted(data, key=lambda r: -int(r[isamp]))[:25]:
         f.write(f"| {int(r[isamp]) / tots * 100:.2f} % | {int(r[ia]) / total * 100:.2f} % | {r[iavg]} | `{r[isrc].strip()[:90]}` |\n")
