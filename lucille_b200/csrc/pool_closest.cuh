@@ -1,0 +1,187 @@
+// Pooled closest-hit traverser (fp32 records): pool.cuh's scheme for ri_b200_intersect_*_f32.
+//
+// A closest-hit query is order-DEPENDENT: the best t so far culls boxes (bvh.c:1038-1044) and leaves commit in visiting order
+// (bvh.c:850).  That order is kept: a lane walks its ray's nodes in the reference's order, and when it reaches a leaf it WAITS
+// there until every triangle of the leaf has been tested and the leaf's result committed, exactly where bvh_intersect_leaf_node
+// would have returned.  Only the tests of one leaf are spread over lanes (and possibly two rounds).  Inside a leaf the reference
+// keeps a leaf-local closest t starting at 1e38 and accepts a triangle unless `t > t_leaf`, so the leaf's answer is the smallest
+// accepted t and, among equal ones, the LAST triangle in leaf order; a pair's own winner (tri_test_bf on its two triangles, from
+// 1e38) combined in leaf order by the same rule gives the same triangle (the case analysis is in DESIGN.md).  Across lanes the
+// combination is one 64-bit shared-memory atomicMin on (bits of |t|) << 32 | (31 - item number): smallest t first, latest item
+// on ties; -0.0 and +0.0 compare equal as they do in the reference's float comparisons, and the winner's (t, u, v, prim) are
+// then read back unchanged.  (A NaN t needs coordinates whose products overflow fp32; such scenes are outside this kernel's
+// contract -- B200_POOL_CLOSEST=0 selects the one-lane-per-ray kernel, which is exact for them too.)
+#pragma once
+
+namespace b200 {
+
+// pair-local winner of item j of a leaf, tested from t_leaf = 1e38 (bvh.c:833-848 restricted to the pair)
+__device__ __forceinline__ void pool_pair_closest(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const float org[3],
+                                                  const float dir[3], float &tl, float &ul, float &vl, uint32_t &tprim)
+{
+    const uint32_t m = ((ntris + 3u) >> 2) << 1;
+    const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = o1 + 2u * m;
+    const F8 q0 = ldg256(trisT + (size_t)o0 * 16u), q1 = ldg256(trisT + (size_t)o1 * 16u), q2 = ldg256(trisT + (size_t)o2 * 16u);
+    TriRegs<float> a, b;
+    a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = __float_as_uint(q0.v[3]);
+    a.e1[0] = q0.v[4]; a.e1[1] = q0.v[5]; a.e1[2] = q0.v[6];
+    a.e2[0] = q1.v[0]; a.e2[1] = q1.v[1]; a.e2[2] = q1.v[2];
+    b.v0[0] = q1.v[4]; b.v0[1] = q1.v[5]; b.v0[2] = q1.v[6]; b.prim = __float_as_uint(q1.v[7]);
+    b.e1[0] = q2.v[0]; b.e1[1] = q2.v[1]; b.e1[2] = q2.v[2];
+    b.e2[0] = q2.v[4]; b.e2[1] = q2.v[5]; b.e2[2] = q2.v[6];
+    tl = Prec<float>::inf(); ul = 0.0f; vl = 0.0f; tprim = 0xffffffffu;
+    tri_test_bf<float>(a, org, dir, true, tl, ul, vl, tprim);
+    tri_test_bf<float>(b, org, dir, 2u * j + 1u < ntris, tl, ul, vl, tprim);
+}
+
+constexpr size_t pool_closest_smem_bytes(int stack_cap)
+{ return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(float4)); }
+
+__global__ void __launch_bounds__(kBlock, 3)
+closest_pool_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
+                    const uint32_t chunk, ri_b200_hit_f32 *__restrict__ hits_out, unsigned int *__restrict__ work_counter,
+                    const uint32_t refill_at, const uint32_t stack_cap)
+{
+    using P = Prec<float>;
+    using L = PoolLeaf<float>;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint32_t s_stack[];  // [stack_cap][kBlock] words, ray slots, descriptors, keys, results
+    uint32_t *stk = s_stack + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
+    char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kBlock);
+    char *s_rays = s_tail + (size_t)wbase * RaySlot<float>::kBytes;
+    uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<float>::kBytes) + wbase;
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_tail + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2))) + wbase;
+    float4 *s_res = reinterpret_cast<float4 *>(s_tail + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2) + sizeof(unsigned long long))) + wbase;
+
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    uint32_t cur = kIdle, prog = 0, idx = 0, sp = 0, best_prim = 0xffffffffu, tprim = 0xffffffffu;
+    float org[3], dir[3], inv[3], best_t = P::inf(), best_u = 0.0f, best_v = 0.0f, tl = P::inf(), ul = 0.0f, vl = 0.0f;
+    bool sx = false, sy = false, sz = false;
+    org[0] = org[1] = org[2] = dir[0] = dir[1] = dir[2] = inv[0] = inv[1] = inv[2] = 0.0f;
+
+    auto retire = [&]() { RayIO<float>::store(hits_out, idx, best_t < P::inf(), best_t, best_u, best_v, best_prim); };   // bvh.c:1187
+    auto enter = [&](const uint32_t word) {      // step onto `word`; a leaf starts with a fresh leaf-local record (bvh.c:833-836)
+        cur = word; prog = 0;
+        tl = P::inf(); ul = 0.0f; vl = 0.0f; tprim = 0xffffffffu;
+    };
+
+    for (;;) {
+        // ------------------------------------------------------------------ fetch
+        unsigned idle = __ballot_sync(FULL, cur == kIdle);
+        while (idle && !exhausted) {
+            if (chunk_next >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; break; }
+                chunk_next = base;
+                chunk_end = (n - base < chunk) ? n : base + chunk;
+            }
+            const unsigned avail = chunk_end - chunk_next;
+            const unsigned n_idle = __popc(idle);
+            const unsigned take = n_idle < avail ? n_idle : avail;
+            const unsigned rank = __popc(idle & lt_mask);
+            if (cur == kIdle && rank < take) {
+                idx = chunk_next + rank;
+                RayIO<float>::load(rays, idx, org, dir);
+                RaySlot<float>::store(s_rays, lane, org, dir);
+                best_t = P::inf(); best_u = 0.0f; best_v = 0.0f; best_prim = 0xffffffffu;
+                sx = dir[0] < 0.0f; sy = dir[1] < 0.0f; sz = dir[2] < 0.0f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)      // bvh.c:473-497
+                    inv[k] = (P::rabs(dir[k]) > P::eps()) ? 1.0f / dir[k] : ((dir[k] < 0.0f) ? -P::vmax() : P::vmax());
+                float tmin;
+                const bool in_scene = (S.root_word != kDoneWord) &&
+                    slab<float>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
+                sp = 0;
+                if (in_scene) enter(S.root_word);
+                else retire();                   // bvh.c:446 / 522-526: miss without traversal
+            }
+            chunk_next += take;
+            idle = __ballot_sync(FULL, cur == kIdle);
+        }
+        if (idle == FULL) break;
+
+        // ------------------------------------------------------------------ traverse
+        for (;;) {
+            const bool in_leaf = (cur & kLeafFlag) != 0u;
+            const uint32_t ntris = ((cur >> kLeafShift) & 15u) + 1u;
+            const uint32_t nitems = L::items(ntris);
+            const uint32_t cnt = in_leaf ? nitems - prog : 0u;
+            const uint32_t total = __reduce_add_sync(FULL, cnt);
+            const unsigned owners = __ballot_sync(FULL, in_leaf);
+            const unsigned n_node = __popc(__ballot_sync(FULL, cur < kIdle));
+            if (n_node == 0u && total == 0u) break;
+            if (!exhausted && 32u - n_node - (uint32_t)__popc(owners) >= refill_at) break;
+
+            if (total >= 32u || total > n_node) {
+                // ---- leaf round (pool.cuh): items 0..31 of the pool, one per lane
+                uint32_t excl = 0;
+#pragma unroll
+                for (int b = 0; b < L::kCntBits; ++b)
+                    excl += (uint32_t)__popc(ballot_bit(cnt, 1u << b) & lt_mask) << b;
+                const bool owner = in_leaf && excl < 32u;
+                const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);
+                if (owner) {
+                    s_desc[__popc(owners & lt_mask)] = make_uint2(cur, lane | ((prog - excl + 64u) << 8));
+                    s_key[lane] = ~0ull;
+                }
+                __syncwarp();
+                if (lane < total) {
+                    const uint2 d = s_desc[__popc(starts & le_mask) - 1u];
+                    const unsigned own = d.y & 31u;
+                    const uint32_t item = lane + (d.y >> 8) - 64u;
+                    float oorg[3], odir[3], t, u, v;
+                    uint32_t prim;
+                    RaySlot<float>::load(s_rays, own, oorg, odir);
+                    pool_pair_closest(trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir, t, u, v, prim);
+                    if (prim != 0xffffffffu) {   // the pair accepted a triangle: offer it to the owner
+                        s_res[lane] = make_float4(t, u, v, __uint_as_float(prim));
+                        atomicMin(&s_key[own], ((unsigned long long)(__float_as_uint(t) & 0x7fffffffu) << 32) | (unsigned long long)(31u - lane));
+                    }
+                }
+                __syncwarp();
+                if (owner) {
+                    const uint32_t took = (cnt < 32u - excl) ? cnt : 32u - excl;
+                    const unsigned long long key = s_key[lane];
+                    if (key != ~0ull) {          // winner of this round's items of my leaf; accepted unless t > t_leaf (bvh.c:780)
+                        const float4 r = s_res[31u - (unsigned)(key & 31ull)];
+                        if (!(r.x > tl)) { tl = r.x; ul = r.y; vl = r.z; tprim = __float_as_uint(r.w); }
+                    }
+                    prog += took;
+                    if (prog == nitems) {        // leaf finished: commit (bvh.c:850), then pop or retire
+                        const bool commit = (tprim != 0xffffffffu) && (tl < best_t);
+                        best_t = commit ? tl : best_t; best_u = commit ? ul : best_u; best_v = commit ? vl : best_v;
+                        best_prim = commit ? tprim : best_prim;
+                        if (sp == 0u) { retire(); cur = kIdle; }
+                        else { --sp; enter(stk[sp * kBlock]); }
+                    }
+                }
+                __syncwarp();                    // s_key / s_res are rewritten by the next round
+            }
+            if (cur < kIdle) {
+                // ---- node step: bvh.c:1153-1179
+                NodeRegs<float> nd;
+                load_node_wide(S.nodes + cur, nd);
+                const bool h0 = slab_mm<float>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
+                const bool h1 = slab_mm<float>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
+                const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);
+                const bool both = h0 && h1, none = !h0 && !h1;
+                const bool pop = none && (sp != 0u);
+                if (both) stk[sp * kBlock] = order ? nd.c0 : nd.c1;
+                const uint32_t popped = pop ? stk[(sp - 1u) * kBlock] : kIdle;
+                sp = sp + (both ? 1u : 0u) - (pop ? 1u : 0u);
+                const uint32_t one = h0 ? nd.c0 : nd.c1;
+                const uint32_t next = both ? (order ? nd.c1 : nd.c0) : (none ? popped : one);
+                if (next == kIdle) { retire(); cur = kIdle; }
+                else enter(next);
+            }
+        }
+    }
+}
+
+}  // namespace b200
