@@ -37,6 +37,7 @@ __device__ __forceinline__ void pool_pair_closest(const char *trisT, uint32_t sl
 constexpr size_t pool_closest_smem_bytes(int stack_cap)
 { return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(float4)); }
 
+// 3 CTAs x 256 threads per SM at 79 registers: measured 909 Mrays/s on the C3 batch against 877 with 4 CTAs at 64 (spills)
 __global__ void __launch_bounds__(kBlock, 3)
 closest_pool_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
                     const uint32_t chunk, ri_b200_hit_f32 *__restrict__ hits_out, unsigned int *__restrict__ work_counter,
