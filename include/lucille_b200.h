@@ -32,6 +32,8 @@ extern "C" {
 #define RI_B200_PREC_F64       2u            /* double records: bit-identical to the CPU reference */
 #define RI_B200_HOST_ONLY      0x100u        /* build + flatten on the host, no device upload: every trace call on
                                                 such an accelerator fails loudly (used by the CPU-only tests) */
+#define RI_B200_BUILD_DEVICE   0x200u        /* build the tree on the device (level-by-level binned SAH, csrc/bvh_build_gpu.cuh): the same
+                                                 tree as the host builder and the reference, bit for bit */
 
 typedef struct ri_b200_accel ri_b200_accel_t;   /* opaque; stored in ri_accel_t.data (accel.h:73) */
 

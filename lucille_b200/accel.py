@@ -28,6 +28,7 @@ RI_ACCEL_B200 = 2       # the id this backend registers
 PREC_F32 = 1
 PREC_F64 = 2
 HOST_ONLY = 0x100
+BUILD_DEVICE = 0x200    # build the tree on the device (same tree, bit for bit)
 MISS_PRIM = 0xFFFFFFFF
 RI_INFINITY = 1.0e38
 

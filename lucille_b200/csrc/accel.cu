@@ -295,6 +295,8 @@ template <typename T> static int upload(T **dst, const std::vector<T> &src, uint
     return 0;
 }
 
+namespace b200 { static int build_tree_device(const double *tri_xyz, uint64_t ntris, HostTree &out, cudaStream_t st); }   // bvh_build_gpu.cuh
+
 extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris, uint32_t precisions, int device)
 {
     if (ntris > kMaxTris) { fail("too many triangles (%llu > %llu)", (unsigned long long)ntris, (unsigned long long)kMaxTris); return nullptr; }
@@ -324,7 +326,12 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
     a->device = device;
     a->precisions = precisions;
 
-    build_tree(tri_xyz, ntris, a->tree);
+    if (precisions & RI_B200_BUILD_DEVICE) {
+        if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); delete a; return nullptr; }
+        if (build_tree_device(tri_xyz, ntris, a->tree, nullptr) != 0) { delete a; return nullptr; }
+    } else {
+        build_tree(tri_xyz, ntris, a->tree);
+    }
     flatten_tree(a->tree, 1024, (precisions & RI_B200_PREC_F32) != 0, (precisions & RI_B200_PREC_F64) != 0, a->flat);
     if (a->flat.overflow) { fail("too many triangle slots for the 27-bit leaf word"); delete a; return nullptr; }
 
@@ -806,3 +813,4 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
 #include "frame.cuh"
 #include "pathtrace.cuh"
 #include "beam.cuh"
+#include "bvh_build_gpu.cuh"

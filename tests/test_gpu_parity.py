@@ -384,3 +384,33 @@ def test_sunsky_frame(oracle, golden_dir, prec):
     else:
         rmse = float(np.sqrt(np.mean((rgb - want) ** 2)))
         assert rmse / want.mean() < 2e-2, rmse / want.mean()
+
+
+@pytest.mark.parametrize("maker", [
+    lambda: scenes.triangle_soup(100000, scenes.SEED_C2),
+    lambda: scenes.triangle_soup(5000, 1),
+    lambda: scenes.triangle_soup(33, 3),
+    lambda: scenes.triangle_soup(17, 7),
+    lambda: scenes.triangle_soup(16, 7),
+    lambda: scenes.triangle_soup(1, 7),
+    lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0),                # identical boxes -> object-median fallback
+    lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0]),         # zero-extent axis
+], ids=["soup100k", "soup5k", "soup33", "soup17", "soup16", "soup1", "dup300", "flat500"])
+def test_device_builder_builds_the_same_tree(maker):
+    """the level-by-level device builder (csrc/bvh_build_gpu.cuh) against the host builder, which the CPU suite
+    pins to the reference's tree: identical nodes, boxes, split axes, leaf contents and triangle order."""
+    _need_gpu()
+    tris = maker()
+    host = accel.Accel.bind().build(tris, accel.PREC_F32)
+    dev = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.BUILD_DEVICE)
+    hn, dn = host.nodes(), dev.nodes()
+    assert len(hn) == len(dn)
+    for f in accel.NODE_DTYPE.names:
+        assert np.array_equal(hn[f], dn[f]), f
+    assert np.array_equal(host.triorder(), dev.triorder())
+    hi, di = host.info(), dev.info()
+    assert (hi.ninner, hi.nleaf, hi.max_depth) == (di.ninner, di.nleaf, di.max_depth)
+    assert list(hi.bmin) == list(di.bmin) and list(hi.bmax) == list(di.bmax)
+    rays = scenes.pinhole_rays(64, 64)
+    a, b = host.intersect(rays), dev.intersect(rays)
+    assert all(np.array_equal(a[f], b[f]) for f in ("t", "u", "v", "prim"))
