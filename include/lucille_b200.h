@@ -34,6 +34,7 @@ extern "C" {
                                                 such an accelerator fails loudly (used by the CPU-only tests) */
 #define RI_B200_BUILD_DEVICE   0x200u        /* build the tree on the device (level-by-level binned SAH, csrc/bvh_build_gpu.cuh): the same
                                                  tree as the host builder and the reference, bit for bit */
+#define RI_B200_BUILD_HOST     0x400u        /* build it with the threaded host builder.  Neither flag: device from 32 Ki triangles up */
 
 typedef struct ri_b200_accel ri_b200_accel_t;   /* opaque; stored in ri_accel_t.data (accel.h:73) */
 

@@ -29,6 +29,7 @@ PREC_F32 = 1
 PREC_F64 = 2
 HOST_ONLY = 0x100
 BUILD_DEVICE = 0x200    # build the tree on the device (same tree, bit for bit)
+BUILD_HOST = 0x400      # build it with the threaded host builder (neither flag: device from 32 Ki triangles up)
 MISS_PRIM = 0xFFFFFFFF
 RI_INFINITY = 1.0e38
 

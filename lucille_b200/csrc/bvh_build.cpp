@@ -387,7 +387,7 @@ void build_tree(const double *tri_xyz, uint64_t ntris, HostTree &out, int nthrea
 static float f32_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -INFINITY); return f; }
 static float f32_up(double x)   { float f = (float)x; if ((double)f < x) f = std::nextafterf(f,  INFINITY); return f; }
 
-void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want64, FlatTree &out)
+void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want64, FlatTree &out, bool fill_tris)
 {
     out = FlatTree();
     for (int k = 0; k < 3; ++k) { out.smin32[k] = f32_down(t.bmin[k]); out.smax32[k] = f32_up(t.bmax[k]); }
@@ -442,7 +442,8 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
     }
     out.nslots = nslots;
     if (nslots >= (1ull << kLeafShift)) { out = FlatTree(); out.overflow = true; return; }     // the leaf word holds a 27-bit slot
-    out.slot_of_prim.assign((size_t)t.ntris, 0);
+    out.leaf_slot = slot_of;
+    if (fill_tris) out.slot_of_prim.assign((size_t)t.ntris, 0);
 
     auto word = [&](int64_t c) -> uint32_t {
         const CanonNode &n = t.nodes[(size_t)c];
@@ -477,6 +478,7 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
         }
     }
 
+    if (!fill_tris) return;
     if (want32) { out.tris32.resize((size_t)nslots); std::memset(out.tris32.data(), 0, out.tris32.size() * sizeof(Tri32)); }
     if (want64) { out.tris64.resize((size_t)nslots); std::memset(out.tris64.data(), 0, out.tris64.size() * sizeof(Tri64)); }
     for (size_t c = 0; c < nn; ++c) {

@@ -80,11 +80,13 @@ struct FlatTree {
     std::vector<Tri64>  tris64t;
     uint64_t nslots = 0;
     std::vector<uint32_t> slot_of_prim;   // post-build triangle position -> slot
+    std::vector<uint32_t> leaf_slot;      // canonical node index -> first slot (leaves only)
     float  smin32[3], smax32[3];
 };
 
 // Lays the inner nodes out as [BFS top cluster | DFS-preorder remainder] and folds leaves into
 // their parent's child words.  fp32 boxes are rounded OUTWARD (min down, max up).
-void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want64, FlatTree &out);
+// fill_tris = false: node records, leaf words and leaf_slot only -- the device builder writes the triangle slots itself.
+void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want64, FlatTree &out, bool fill_tris = true);
 
 }  // namespace b200

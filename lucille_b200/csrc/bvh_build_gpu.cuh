@@ -296,10 +296,11 @@ struct GpuBuildScratch {
     }
 };
 
-static int64_t gb_emit(const std::vector<GNode> &g, uint32_t i, std::vector<CanonNode> &out, int depth, HostTree &t)
+static int64_t gb_emit(const std::vector<GNode> &g, uint32_t i, std::vector<CanonNode> &out, int depth, HostTree &t, std::vector<uint32_t> &canon_of)
 {
     const int64_t me = (int64_t)out.size();
     out.emplace_back();
+    canon_of[i] = (uint32_t)me;
     if (depth > t.max_depth) t.max_depth = depth;
     const GNode &n = g[i];
     {
@@ -317,16 +318,91 @@ static int64_t gb_emit(const std::vector<GNode> &g, uint32_t i, std::vector<Cano
         for (int k = 0; k < 3; ++k) { c.lbox[k] = l.lo[k]; c.lbox[3 + k] = l.hi[k]; c.rbox[k] = r.lo[k]; c.rbox[3 + k] = r.hi[k]; }
         t.ninner++;
     }
-    const int64_t c0 = gb_emit(g, n.child0, out, depth + 1, t);
+    const int64_t c0 = gb_emit(g, n.child0, out, depth + 1, t, canon_of);
     out[(size_t)me].child0 = c0;
-    const int64_t c1 = gb_emit(g, n.child1, out, depth + 1, t);
+    const int64_t c1 = gb_emit(g, n.child1, out, depth + 1, t, canon_of);
     out[(size_t)me].child1 = c1;
     return me;
 }
 
-// tri_xyz: HOST [ntris][9].  Fills `out` like build_tree(); build_seconds = device time incl. the triangle upload and the downloads.
-static int build_tree_device(const double *tri_xyz, uint64_t ntris64, HostTree &out, cudaStream_t st)
+struct DeviceBuild {                                   // what the slot-filling pass needs after the tree is final
+    GpuBuildScratch s;
+    int      cur = 0;
+    uint32_t n = 0, total = 0;
+    std::vector<uint32_t> canon_of;                    // breadth-first node -> canonical (depth-first) node
+};
+
+__global__ void gb_extract_idx(const GBox *__restrict__ boxes, uint32_t n, uint32_t *__restrict__ idx)
 {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) idx[p] = boxes[p].idx;
+}
+
+// Triangle slots straight from the device copy of the triangles: what flatten_tree()'s per-triangle loops write on the host
+// (bvh_build.cpp) -- the slot records of both precisions, their leaf-transposed copies, slot_of_prim, the filler slots.
+// One lane per triangle in its final position p (= prim id); buffers are zeroed beforehand.
+__global__ void gb_fill_slots(const double *__restrict__ tri, const GBox *__restrict__ boxes, uint32_t n, const GNode *__restrict__ nodes,
+                              const uint32_t *__restrict__ leaf_slot, Tri32 *__restrict__ t32, Tri64 *__restrict__ t64,
+                              char *__restrict__ t32t, char *__restrict__ t64t, uint32_t *__restrict__ slot_of_prim)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const GBox &b = boxes[p];
+    const GNode &nd = nodes[b.node];
+    const uint32_t i = p - nd.left, ntris = nd.n, slot0 = leaf_slot[b.node], slot = slot0 + i;
+    const uint32_t ns = (ntris + 3u) & ~3u, m = ns / 2u;             // slots / fp32 pairs per row
+    const double *v = tri + 9 * (size_t)b.idx;
+    slot_of_prim[p] = slot;
+    if (t64) {
+        Tri64 d;
+        for (int k = 0; k < 3; ++k) { d.v0[k] = v[k]; d.e1[k] = v[3 + k] - v[k]; d.e2[k] = v[6 + k] - v[k]; }
+        d.prim = p; d.pad1 = 0; d.pad2 = 0;
+        t64[slot] = d;
+        const uint4 *src = reinterpret_cast<const uint4 *>(&d);
+        for (uint32_t k = 0; k < 3; ++k) {
+            uint4 *dst = reinterpret_cast<uint4 *>(t64t + (size_t)slot0 * sizeof(Tri64) + ((size_t)k * ns + i) * 32u);
+            dst[0] = src[2 * k]; dst[1] = src[2 * k + 1];
+        }
+    }
+    if (t32) {
+        Tri32 d;
+        for (int k = 0; k < 3; ++k) {
+            const float v0 = (float)v[k], v1 = (float)v[3 + k], v2 = (float)v[6 + k];
+            d.v0[k] = v0; d.e1[k] = v1 - v0; d.e2[k] = v2 - v0;      // bvh.c:747-752, in fp32
+        }
+        d.prim = p; d.pad1 = 0; d.pad2 = 0;
+        t32[slot] = d;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&d);
+        const uint32_t j = i >> 1, h = i & 1u;
+        for (uint32_t q = 0; q < 12; ++q) {
+            const uint32_t off = h * 48u + q * 4u;
+            *reinterpret_cast<uint32_t *>(t32t + (size_t)slot0 * sizeof(Tri32) + ((size_t)(off >> 5) * m + j) * 32u + (off & 31u)) = w[q];
+        }
+    }
+    if (i == ntris - 1u) {                                               // filler slots: zero-area triangles, prim = MISS
+        for (uint32_t f = ntris; f < ns; ++f) {
+            if (t64) {
+                t64[slot0 + f].prim = 0xffffffffull;
+                *reinterpret_cast<unsigned long long *>(t64t + (size_t)slot0 * sizeof(Tri64) + (size_t)f * 32u + 24u) = 0xffffffffull;
+            }
+            if (t32) {
+                t32[slot0 + f].prim = 0xffffffffu;
+                const uint32_t off = (f & 1u) * 48u + 12u;
+                *reinterpret_cast<uint32_t *>(t32t + (size_t)slot0 * sizeof(Tri32) + ((size_t)(off >> 5) * m + (f >> 1)) * 32u + (off & 31u)) = 0xffffffffu;
+            }
+        }
+        if (t32 && (ntris & 1u)) {                                       // unit edges for the masked half of the last pair (bvh_build.cpp)
+            float *e = reinterpret_cast<float *>(t32t + (size_t)slot0 * sizeof(Tri32) + ((size_t)2 * m + ((ntris + 1u) / 2u - 1u)) * 32u);
+            e[0] = 1.0f; e[5] = 1.0f;
+        }
+    }
+}
+
+// tri_xyz: HOST [ntris][9].  Fills `out` like build_tree() except for out.tri (the triangles stay on the device: db);
+// build_seconds = wall time incl. the triangle upload and the node download.
+static int build_tree_device(const double *tri_xyz, uint64_t ntris64, HostTree &out, cudaStream_t st, DeviceBuild &db)
+{
+    GpuBuildScratch &s = db.s;
     const auto t0 = std::chrono::steady_clock::now();
     out = HostTree();
     out.ntris = ntris64;
@@ -336,7 +412,6 @@ static int build_tree_device(const double *tri_xyz, uint64_t ntris64, HostTree &
     const uint32_t n = (uint32_t)ntris64;
     const uint32_t max_nodes = 2u * n + 2u, max_level_inner = n / (uint32_t)(kGbLeaf + 1) + 2u;
     const uint32_t ntiles = (n + 1 + kScanTile - 1) / kScanTile;
-    GpuBuildScratch s;
     CUDA_OK(cudaMalloc((void **)&s.d_tri, (size_t)n * 9 * sizeof(double)));
     CUDA_OK(cudaMalloc((void **)&s.d_box[0], (size_t)n * sizeof(GBox)));
     CUDA_OK(cudaMalloc((void **)&s.d_box[1], (size_t)n * sizeof(GBox)));
@@ -359,8 +434,16 @@ static int build_tree_device(const double *tri_xyz, uint64_t ntris64, HostTree &
         LAUNCHED();
     }
     uint32_t first = 0, count = 1, inner = (n > (uint32_t)kGbLeaf) ? 1u : 0u;
-    int cur = 0;
+    int cur = 0, levels = 0;
+    const bool trace = getenv("B200_BUILD_TRACE") != nullptr;
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[device build] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
+    lap("alloc+upload+boxes");
     while (inner > 0) {
+        ++levels;
         if (count > max_level_inner * 2u + 8u) return fail("device builder: level overflow");
         const uint32_t next_first = first + count;
         uint32_t h_counters[2] = {next_first, 0u};
@@ -393,23 +476,23 @@ static int build_tree_device(const double *tri_xyz, uint64_t ntris64, HostTree &
         cur ^= 1;
     }
     CUDA_OK(cudaGetLastError());
+    lap("levels");
     const uint32_t total = first + count;
     std::vector<GNode> g(total);
-    std::vector<GBox> boxes(n);
-    CUDA_OK(cudaMemcpyAsync(g.data(), s.d_nodes, (size_t)total * sizeof(GNode), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(boxes.data(), s.d_box[cur], (size_t)n * sizeof(GBox), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-
-    for (int k = 0; k < 3; ++k) { out.bmin[k] = g[0].lo[k]; out.bmax[k] = g[0].hi[k]; }
-    out.tri.resize(9 * (size_t)n);
     out.orig.resize(n);
-    for (uint32_t i = 0; i < n; ++i) {                                  // gather_triangles, bvh.c:1897-1917
-        const uint32_t src = boxes[i].idx;
-        std::memcpy(out.tri.data() + 9 * (size_t)i, tri_xyz + 9 * (size_t)src, 9 * sizeof(double));
-        out.orig[i] = src;
-    }
+    gb_extract_idx<<<nb, 256, 0, st>>>(s.d_box[cur], n, s.d_S);
+    LAUNCHED();
+    CUDA_OK(cudaMemcpyAsync(g.data(), s.d_nodes, (size_t)total * sizeof(GNode), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(out.orig.data(), s.d_S, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    lap("download");
+    for (int k = 0; k < 3; ++k) { out.bmin[k] = g[0].lo[k]; out.bmax[k] = g[0].hi[k]; }
     out.nodes.reserve(total);
-    gb_emit(g, 0, out.nodes, 0, out);
+    db.canon_of.assign(total, 0u);
+    gb_emit(g, 0, out.nodes, 0, out, db.canon_of);
+    lap("host renumber");
+    if (trace) fprintf(stderr, "[device build] %d levels, %u nodes\n", levels, total);
+    db.cur = cur; db.n = n; db.total = total;
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }

@@ -401,8 +401,8 @@ def test_device_builder_builds_the_same_tree(maker):
     pins to the reference's tree: identical nodes, boxes, split axes, leaf contents and triangle order."""
     _need_gpu()
     tris = maker()
-    host = accel.Accel.bind().build(tris, accel.PREC_F32)
-    dev = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.BUILD_DEVICE)
+    host = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64 | accel.BUILD_HOST)
+    dev = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64 | accel.BUILD_DEVICE)
     hn, dn = host.nodes(), dev.nodes()
     assert len(hn) == len(dn)
     for f in accel.NODE_DTYPE.names:
@@ -411,6 +411,15 @@ def test_device_builder_builds_the_same_tree(maker):
     hi, di = host.info(), dev.info()
     assert (hi.ninner, hi.nleaf, hi.max_depth) == (di.ninner, di.nleaf, di.max_depth)
     assert list(hi.bmin) == list(di.bmin) and list(hi.bmax) == list(di.bmax)
-    rays = scenes.pinhole_rays(64, 64)
-    a, b = host.intersect(rays), dev.intersect(rays)
+    # every device buffer the device path fills itself (slots of both precisions, their leaf-transposed copies, slot_of_prim)
+    # is read by one of these: closest hit and occlusion in both precisions, and the hit state
+    rays8 = np.concatenate([scenes.pinhole_rays(64, 64), _mixed_rays(4096, 5)])
+    rays6 = scenes.rays_f32_to_f64(rays8)
+    a, b = host.intersect(rays8), dev.intersect(rays8)
     assert all(np.array_equal(a[f], b[f]) for f in ("t", "u", "v", "prim"))
+    a6, b6 = host.intersect(rays6), dev.intersect(rays6)
+    assert all(np.array_equal(a6[f], b6[f]) for f in ("t", "u", "v", "prim", "hit"))
+    assert np.array_equal(host.occluded(rays8), dev.occluded(rays8)) and np.array_equal(host.occluded(rays6), dev.occluded(rays6))
+    sa, sb = host.state(rays6, a6), dev.state(rays6, b6)
+    m = a6["hit"] == 1
+    assert all(np.array_equal(sa[f][m], sb[f][m]) for f in ("P", "Ng", "Ns", "tangent", "binormal"))
