@@ -204,6 +204,13 @@ int ri_b200_render_sunsky_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
 /* ri_sunsky_get_sky_rgb for a HOST batch of directions ([n][3] floats in, [n][3] floats out), computed on `device` */
 int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device);
 
+/* ---- the output step right after the path: lucille's Radiance .hdr display driver (display/hdrdrv.c:62-102 hdr_dd_write clamp +
+ * accumulate, hdr_dd_close; imageio/rgbe.c:78-96 float2rgbe, 117-139 RGBE_WriteHeader, 244-340 RGBE_WritePixels_RLE) computed on the
+ * device.  rgb: [height][width][3] floats in display order -- a DEVICE pointer when rgb_on_device != 0 (e.g. the buffer
+ * ri_b200_render_ao_dev filled), else a HOST pointer.  Returns the size of the file image in bytes (or -1) and writes it to `out`
+ * (HOST) when cap is large enough; byte-identical to the file the reference writes. */
+int64_t ri_b200_hdr_encode(const float *rgb, int width, int height, uint8_t *out, uint64_t cap, int device, int rgb_on_device);
+
 /* ---- replaces ri_beam_set + ri_bvh_intersect_beam_visibility (beam.c:332-466, bvh.c:612-667) for a batch of beams.
  * beams: HOST [n][15] doubles = org.xyz, dir0.xyz .. dir3.xyz (consecutive corners of the frustum).  out[i] = RI_BEAM_MISS_COMPLETELY 0 /
  * RI_BEAM_HIT_COMPLETELY 1 / RI_BEAM_HIT_PARTIALLY 2 (beam.h:27-29), or -1 where ri_beam_set would fail (corner directions

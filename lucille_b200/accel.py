@@ -134,6 +134,7 @@ ABI = [
     ("ri_b200_render_sunsky", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_sunsky_tiles_dev", _I, [_P, _P, _P, _P, _P, _P]),
     ("ri_b200_sunsky_rgb", _I, [_P, _P, _U64, _P, _I]),
+    ("ri_b200_hdr_encode", C.c_int64, [_P, _I, _I, _P, _U64, _I, _I]),
     ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_pathtrace_tiles_dev", _I, [_P, _P, _P, _P, _P]),
@@ -398,6 +399,24 @@ def sunsky_rgb(sky: "Sunsky", dirs: np.ndarray, device: int = 0) -> np.ndarray:
     out = np.zeros_like(dirs)
     _check(load_library().ri_b200_sunsky_rgb(C.byref(sky), _ptr(dirs), len(dirs), _ptr(out), device))
     return out
+
+
+def hdr_encode(rgb, width: int = 0, height: int = 0, device: int = 0) -> bytes:
+    """The Radiance .hdr file lucille's display driver writes for a float framebuffer (hdrdrv.c / rgbe.c), encoded on the device.
+    ``rgb``: a [h,w,3] float32 numpy array on the host, or a device pointer / CUDA tensor with ``width`` and ``height`` given."""
+    lib = load_library()
+    if isinstance(rgb, np.ndarray):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        height, width = rgb.shape[:2]
+        src, on_dev = _ptr(rgb), 0
+    else:
+        src, on_dev = _ptr(rgb), 1
+    cap = 64 + 4 * height + width * height * 4 + (width // 64 + 8) * 4 * height + 128
+    out = np.zeros(cap, dtype=np.uint8)
+    n = lib.ri_b200_hdr_encode(src, width, height, _ptr(out), cap, device, on_dev)
+    if n < 0 or n > cap:
+        raise B200Error(last_error() if n < 0 else "hdr buffer too small")
+    return out[:n].tobytes()
 
 
 def frame_pixels(frame: Frame) -> np.ndarray:

@@ -833,6 +833,7 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
 #include "pathtrace.cuh"
 #include "beam.cuh"
 #include "bvh_build_gpu.cuh"
+#include "hdr.cuh"
 
 // Device build path of ri_b200_build: tree on the device, topology numbering + node records on the host (a few hundred
 // thousand records), triangle slots on the device again.  The triangles cross PCIe once and are never gathered on the host.

@@ -1,0 +1,189 @@
+// The output step right after the path: lucille's Radiance .hdr display driver on the device, so that a frame
+// rendered into device memory leaves the GPU as the finished file image instead of a float framebuffer.
+//   hdr_dd_write   display/hdrdrv.c:62-88    clamp negative components to 0, add onto the zeroed buffer
+//   float2rgbe     imageio/rgbe.c:78-96       v = frexp(max) * 256 / max in double rounded to float; bytes by truncation
+//   RGBE_WritePixels_RLE / RGBE_WriteBytes_RLE  rgbe.c:296-340, 244-294   per scanline: 2 2 hi lo, then the four channel planes
+//                                               run-length coded one after the other; flat pixels for widths < 8 or > 0x7fff
+//   RGBE_WriteHeader  rgbe.c:117-139
+// hdr_rgbe_kernel: one lane per pixel.  hdr_rle_kernel: one lane per (scanline, channel) row runs the reference's sequential coder
+// on its row (rows are independent; 4 x height lanes).  hdr_offsets_kernel: one block scans the row lengths.  hdr_pack_kernel:
+// one CTA per row copies it to its place.  Byte-identical to the file the reference writes (tests/test_gpu_parity.py).
+#pragma once
+
+namespace b200 {
+
+__device__ __forceinline__ void hdr_float2rgbe(unsigned char rgbe[4], float red, float green, float blue)
+{
+    float v = red;
+    if (green > v) v = green;
+    if (blue > v) v = blue;
+    if ((double)v < 1e-32) {
+        rgbe[0] = rgbe[1] = rgbe[2] = rgbe[3] = 0;
+    } else {
+        int e;
+        v = (float)(frexp((double)v, &e) * 256.0 / (double)v);
+        rgbe[0] = (unsigned char)(red * v);
+        rgbe[1] = (unsigned char)(green * v);
+        rgbe[2] = (unsigned char)(blue * v);
+        rgbe[3] = (unsigned char)(e + 128);
+    }
+}
+
+// planes: [height][4][width] bytes (flat == 0) or the pixel-interleaved rgbe stream itself (flat == 1)
+__global__ void hdr_rgbe_kernel(const float *__restrict__ rgb, int width, int height, unsigned char *__restrict__ planes, int flat)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)width * height) return;
+    const int y = (int)(i / width), x = (int)(i - (size_t)y * width);
+    float acc[3];
+    for (int k = 0; k < 3; ++k) {                                    // hdr_dd_write
+        float c = rgb[3 * i + k];
+        if ((double)c < 0.0) c = 0.0f;
+        acc[k] = 0.0f;
+        acc[k] += c;
+    }
+    unsigned char q[4];
+    hdr_float2rgbe(q, acc[0], acc[1], acc[2]);
+    if (flat) {
+        for (int k = 0; k < 4; ++k) planes[4 * i + k] = q[k];
+    } else {
+        unsigned char *row = planes + (size_t)y * 4 * width;
+        for (int k = 0; k < 4; ++k) row[(size_t)k * width + x] = q[k];
+    }
+}
+
+// rgbe.c:244-294, one row per lane; out has row_cap bytes per row
+__global__ void hdr_rle_kernel(const unsigned char *__restrict__ planes, int width, int nrows, unsigned char *__restrict__ tmp, uint32_t row_cap,
+                               uint32_t *__restrict__ row_len)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const unsigned char *data = planes + (size_t)r * width;
+    unsigned char *out = tmp + (size_t)r * row_cap;
+    const int numbytes = width, MINRUNLENGTH = 4;
+    uint32_t n = 0;
+    int cur = 0;
+    while (cur < numbytes) {
+        int beg_run = cur, run_count = 0, old_run_count = 0;
+        while ((run_count < MINRUNLENGTH) && (beg_run < numbytes)) {
+            beg_run += run_count;
+            old_run_count = run_count;
+            run_count = 1;
+            while ((beg_run + run_count < numbytes) && (run_count < 127) && (data[beg_run] == data[beg_run + run_count])) run_count++;
+        }
+        if ((old_run_count > 1) && (old_run_count == beg_run - cur)) {
+            out[n++] = (unsigned char)(128 + old_run_count);
+            out[n++] = data[cur];
+            cur = beg_run;
+        }
+        while (cur < beg_run) {
+            int nonrun_count = beg_run - cur;
+            if (nonrun_count > 128) nonrun_count = 128;
+            out[n++] = (unsigned char)nonrun_count;
+            for (int k = 0; k < nonrun_count; ++k) out[n++] = data[cur + k];
+            cur += nonrun_count;
+        }
+        if (run_count >= MINRUNLENGTH) {
+            out[n++] = (unsigned char)(128 + run_count);
+            out[n++] = data[beg_run];
+            cur += run_count;
+        }
+    }
+    row_len[r] = n;
+}
+
+// row_off[r] = offset of row r in the body (each scanline = 4 header bytes + its four rows); total body size in *body_bytes
+__global__ void __launch_bounds__(kScanBlock)
+hdr_offsets_kernel(const uint32_t *__restrict__ row_len, int nrows, unsigned long long *__restrict__ row_off, unsigned long long *__restrict__ body_bytes)
+{
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nrows; base += kScanBlock) {
+        const int r = base + (int)threadIdx.x;
+        const uint32_t x = (r < nrows) ? row_len[r] + (((r & 3) == 0) ? 4u : 0u) : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(x, &total);
+        if (r < nrows) row_off[r] = carry + ex + (((r & 3) == 0) ? 4u : 0u);      // the row's bytes start after its scanline's header
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *body_bytes = carry;
+}
+
+__global__ void hdr_pack_kernel(const unsigned char *__restrict__ tmp, uint32_t row_cap, const uint32_t *__restrict__ row_len,
+                                const unsigned long long *__restrict__ row_off, int width, unsigned char *__restrict__ body)
+{
+    const int r = blockIdx.x;
+    const uint32_t n = row_len[r];
+    unsigned char *dst = body + row_off[r];
+    const unsigned char *src = tmp + (size_t)r * row_cap;
+    if ((r & 3) == 0 && threadIdx.x == 0) {                              // rgbe.c:311-314
+        dst[-4] = 2; dst[-3] = 2; dst[-2] = (unsigned char)(width >> 8); dst[-1] = (unsigned char)(width & 0xFF);
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace b200
+
+// rgb: [height][width][3] floats in display order, in DEVICE memory when rgb_on_device != 0, else on the host.
+// Returns the file size in bytes (header included) or -1; the file image is written to `out` (HOST) when it fits in cap.
+extern "C" int64_t ri_b200_hdr_encode(const float *rgb, int width, int height, uint8_t *out, uint64_t cap, int device, int rgb_on_device)
+{
+    if (!rgb || width < 1 || height < 1) return fail("bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: libb200accel has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail("bad device %d", device);
+    CUDA_OK(cudaSetDevice(device));
+    char hdr[128];
+    const int hlen = snprintf(hdr, sizeof(hdr), "#?%s\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", "RGBE", height, width);   // rgbe.c:117-139
+    const size_t npix = (size_t)width * height;
+    const int flat = (width < 8) || (width > 0x7fff);                    // rgbe.c:303-305
+    const int nrows = 4 * height;
+    const uint32_t row_cap = (uint32_t)width + (uint32_t)width / 64u + 8u;
+    float *d_rgb = nullptr;
+    unsigned char *d_planes = nullptr, *d_tmp = nullptr, *d_body = nullptr;
+    uint32_t *d_len = nullptr;
+    unsigned long long *d_off = nullptr;
+    int64_t result = -1;
+    auto body = [&]() -> int {
+        const float *src = rgb;
+        if (!rgb_on_device) {
+            CUDA_OK(cudaMalloc((void **)&d_rgb, npix * 3 * sizeof(float)));
+            CUDA_OK(cudaMemcpy(d_rgb, rgb, npix * 3 * sizeof(float), cudaMemcpyHostToDevice));
+            src = d_rgb;
+        }
+        CUDA_OK(cudaMalloc((void **)&d_planes, npix * 4));
+        hdr_rgbe_kernel<<<(unsigned)((npix + 255) / 256), 256>>>(src, width, height, d_planes, flat);
+        LAUNCHED();
+        unsigned long long body_bytes = 0;
+        const unsigned char *d_src = d_planes;
+        if (flat) {
+            body_bytes = npix * 4;
+        } else {
+            CUDA_OK(cudaMalloc((void **)&d_tmp, (size_t)nrows * row_cap));
+            CUDA_OK(cudaMalloc((void **)&d_len, (size_t)nrows * sizeof(uint32_t)));
+            CUDA_OK(cudaMalloc((void **)&d_off, ((size_t)nrows + 1) * sizeof(unsigned long long)));
+            hdr_rle_kernel<<<(nrows + 63) / 64, 64>>>(d_planes, width, nrows, d_tmp, row_cap, d_len);
+            LAUNCHED();
+            hdr_offsets_kernel<<<1, kScanBlock>>>(d_len, nrows, d_off, d_off + nrows);
+            LAUNCHED();
+            CUDA_OK(cudaMemcpy(&body_bytes, d_off + nrows, sizeof(body_bytes), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMalloc((void **)&d_body, body_bytes ? body_bytes : 1));
+            hdr_pack_kernel<<<nrows, 128>>>(d_tmp, row_cap, d_len, d_off, width, d_body);
+            LAUNCHED();
+            d_src = d_body;
+        }
+        CUDA_OK(cudaGetLastError());
+        result = (int64_t)hlen + (int64_t)body_bytes;
+        if (out && cap >= (uint64_t)result) {
+            std::memcpy(out, hdr, (size_t)hlen);
+            CUDA_OK(cudaMemcpy(out + hlen, d_src, body_bytes, cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    };
+    const int rc = body();
+    cudaFree(d_rgb); cudaFree(d_planes); cudaFree(d_tmp); cudaFree(d_len); cudaFree(d_off); cudaFree(d_body);
+    return rc ? -1 : result;
+}

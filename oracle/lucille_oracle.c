@@ -899,6 +899,110 @@ void orc_render_sunsky(const orc_tree *T, const orc_frame_t *f, const orc_sunsky
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ .hdr output */
+
+typedef struct { uint8_t *out; uint64_t cap, n; } sink_t;
+static void sink_put(sink_t *s, const void *p, uint64_t len)
+{
+    if (s->out && s->n + len <= s->cap) memcpy(s->out + s->n, p, (size_t)len);
+    s->n += len;
+}
+
+/* rgbe.c:78-96 */
+static void hdr_float2rgbe(unsigned char rgbe[4], float red, float green, float blue)
+{
+    float v;
+    int e;
+    v = red;
+    if (green > v) v = green;
+    if (blue > v) v = blue;
+    if (v < 1e-32) {
+        rgbe[0] = rgbe[1] = rgbe[2] = rgbe[3] = 0;
+    } else {
+        v = frexp(v, &e) * 256.0 / v;
+        rgbe[0] = (unsigned char)(red * v);
+        rgbe[1] = (unsigned char)(green * v);
+        rgbe[2] = (unsigned char)(blue * v);
+        rgbe[3] = (unsigned char)(e + 128);
+    }
+}
+
+/* rgbe.c:244-294 */
+static void hdr_rle(sink_t *s, const unsigned char *data, int numbytes)
+{
+    const int MINRUNLENGTH = 4;
+    int cur, beg_run, run_count, old_run_count, nonrun_count;
+    unsigned char buf[2];
+    cur = 0;
+    while (cur < numbytes) {
+        beg_run = cur;
+        run_count = old_run_count = 0;
+        while ((run_count < MINRUNLENGTH) && (beg_run < numbytes)) {
+            beg_run += run_count;
+            old_run_count = run_count;
+            run_count = 1;
+            while ((beg_run + run_count < numbytes) && (run_count < 127) && (data[beg_run] == data[beg_run + run_count]))
+                run_count++;
+        }
+        if ((old_run_count > 1) && (old_run_count == beg_run - cur)) {
+            buf[0] = 128 + old_run_count;
+            buf[1] = data[cur];
+            sink_put(s, buf, 2);
+            cur = beg_run;
+        }
+        while (cur < beg_run) {
+            nonrun_count = beg_run - cur;
+            if (nonrun_count > 128) nonrun_count = 128;
+            buf[0] = nonrun_count;
+            sink_put(s, buf, 1);
+            sink_put(s, &data[cur], (uint64_t)nonrun_count);
+            cur += nonrun_count;
+        }
+        if (run_count >= MINRUNLENGTH) {
+            buf[0] = 128 + run_count;
+            buf[1] = data[beg_run];
+            sink_put(s, buf, 2);
+            cur += run_count;
+        }
+    }
+}
+
+uint64_t orc_hdr_encode(const float *rgb, int width, int height, uint8_t *out, uint64_t cap)
+{
+    sink_t s = { out, cap, 0 };
+    char hdr[128];
+    unsigned char rgbe[4], *buffer;
+    int x, y, i, len;
+    /* RGBE_WriteHeader(fp, width, height, NULL), rgbe.c:117-139 */
+    len = snprintf(hdr, sizeof(hdr), "#?%s\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", "RGBE", height, width);
+    sink_put(&s, hdr, (uint64_t)len);
+    buffer = (unsigned char *)malloc((size_t)4 * (size_t)(width > 0 ? width : 1));
+    for (y = 0; y < height; y++) {
+        const float *row = rgb + 3 * (size_t)y * (size_t)width;
+        const int flat = (width < 8) || (width > 0x7fff);                      /* rgbe.c:303-305 */
+        if (!flat) {
+            rgbe[0] = 2; rgbe[1] = 2; rgbe[2] = width >> 8; rgbe[3] = width & 0xFF;
+            sink_put(&s, rgbe, 4);
+        }
+        for (x = 0; x < width; x++) {
+            float col[3], acc[3];
+            for (i = 0; i < 3; i++) {                                          /* hdr_dd_write, hdrdrv.c:72-85 */
+                col[i] = row[3 * x + i];
+                if (col[i] < 0.0) col[i] = 0.0;
+                acc[i] = 0.0f;
+                acc[i] += col[i];
+            }
+            hdr_float2rgbe(rgbe, acc[0], acc[1], acc[2]);
+            if (flat) sink_put(&s, rgbe, 4);                                   /* RGBE_WritePixels, rgbe.c:206-222 */
+            else { buffer[x] = rgbe[0]; buffer[x + width] = rgbe[1]; buffer[x + 2 * width] = rgbe[2]; buffer[x + 3 * width] = rgbe[3]; }
+        }
+        if (!flat)
+            for (i = 0; i < 4; i++) hdr_rle(&s, &buffer[i * width], width);
+    }
+    free(buffer);
+    return s.n;
+}
+
 /* ------------------------------------------------------------------ beam visibility (row a10) */
 
 typedef struct {

@@ -167,6 +167,13 @@ void orc_sunsky_sky_rgb(const orc_sunsky_t *s, const float *dirs, uint64_t n, fl
 /* whole frame with the sun-sky transport: 8x8 gather, eps 1e-5, Lo = (1/pi) * col / 64 (f->ntheta/nphi are ignored) */
 void orc_render_sunsky(const orc_tree *t, const orc_frame_t *f, const orc_sunsky_t *s, float *rgb, uint64_t *nrays_out);
 
+/* ---- the output step right after the path: the Radiance .hdr display driver.  hdr_dd_write clamps negative
+ * components to 0 and adds onto a zeroed float buffer (display/hdrdrv.c:62-88); hdr_dd_close writes RGBE_WriteHeader +
+ * RGBE_WritePixels_RLE (hdrdrv.c:90-102; imageio/rgbe.c:78-96 float2rgbe, 117-139 header, 244-294 run-length coder, 296-340
+ * scanline framing, flat pixels when the width is < 8 or > 0x7fff).  rgb: [h][w][3] floats in display order.  Returns the file
+ * size (the bytes are written when cap is large enough; call with out == NULL to size). */
+uint64_t orc_hdr_encode(const float *rgb, int width, int height, uint8_t *out, uint64_t cap);
+
 /* counter-based uniform for the synthetic configs (shared definition with the product) */
 uint64_t orc_splitmix64(uint64_t x);
 

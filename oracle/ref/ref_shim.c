@@ -525,6 +525,20 @@ void lref_sunsky_eval(float latitude, float longitude, float sm, int jd, float t
     out21[17] = s->zenith_x; out21[18] = s->zenith_y; out21[19] = s->zenith_Y; out21[20] = 0;
 }
 
+/* ---- .hdr display driver (display/hdrdrv.c) driven exactly like bucket_write() drives it: open, one write per pixel, close */
+extern int hdr_dd_open(const char *name, int width, int height, int bits, RtToken component, const char *format);
+extern int hdr_dd_write(int x, int y, const void *pixel);
+extern int hdr_dd_close(void);
+int lref_hdr_file(const float *rgb, int width, int height, const char *path)
+{
+    int x, y;
+    if (!hdr_dd_open(path, width, height, 32, RI_RGB, "float")) return -1;
+    for (y = 0; y < height; y++)
+        for (x = 0; x < width; x++) hdr_dd_write(x, y, rgb + 3 * ((size_t)y * width + x));
+    hdr_dd_close();
+    return 0;
+}
+
 /* out: c2w[16], flength, is_rh, ortho, fov, xsamples, ysamples, gather, bucket_size, bucket_order, has_normals, ngeoms */
 void lref_frame_camera(double *out27)
 {

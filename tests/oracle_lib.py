@@ -55,6 +55,18 @@ class SunskyBlock(C.Structure):
                 ("sun_dir", C.c_double * 12), ("sun_col", C.c_double * 12)]
 
 
+def hdr_cases():
+    """Float framebuffers for the .hdr output tests: noise with negative components, long runs, a width below 8 (flat pixels),
+    values under the 1e-32 cut-off, exactly 8 columns, a constant image."""
+    rng = np.random.default_rng(1)
+    return {"noise": rng.uniform(-0.2, 3, (37, 53, 3)).astype(np.float32),
+            "runs": np.repeat(rng.uniform(0, 1, (16, 9, 3)), 17, axis=1).astype(np.float32),
+            "narrow": rng.uniform(0, 1, (5, 7, 3)).astype(np.float32),
+            "tiny": (rng.uniform(0, 1, (9, 40, 3)) * 1e-30).astype(np.float32),
+            "w8": rng.uniform(0, 1e4, (3, 8, 3)).astype(np.float32),
+            "const": np.full((10, 300, 3), 0.25, np.float32)}
+
+
 def sky_dirs(n: int, seed: int) -> np.ndarray:
     """Seeded unit directions for the sky-lookup tests, with grazing ones (the t[2] < 0.001 branch of sunsky.c:349-355),
     below-horizon ones and the axes."""
@@ -255,9 +267,20 @@ class Oracle:
         lib.orc_render_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_splitmix64.restype = C.c_uint64
         lib.orc_splitmix64.argtypes = [C.c_uint64]
+        lib.orc_hdr_encode.restype = C.c_uint64
+        lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_sunsky.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib = lib
+
+    def hdr_encode(self, rgb: np.ndarray) -> bytes:
+        """The .hdr file the reference's display driver writes for this float framebuffer ([h][w][3], display order)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        h, w = rgb.shape[:2]
+        n = self.lib.orc_hdr_encode(_ptr(rgb), w, h, None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        assert self.lib.orc_hdr_encode(_ptr(rgb), w, h, _ptr(out), n) == n
+        return out.tobytes()
 
     def sunsky_sky_rgb(self, block: SunskyBlock, dirs: np.ndarray) -> np.ndarray:
         dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
@@ -370,6 +393,7 @@ class Reference:
         lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_void_p]
         lib.lref_sunsky_eval.restype = None
+        lib.lref_hdr_file.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         self.lib = lib
         self.stats = stats
 
@@ -381,6 +405,16 @@ class Reference:
         with _quiet():
             self.lib.lref_sunsky_eval(latitude, longitude, sm, jd, tod, turbidity, _ptr(dirs), C.c_uint64(len(dirs)), _ptr(rgb), _ptr(rec))
         return rgb, rec
+
+    def hdr_file(self, rgb: np.ndarray, path: str) -> bytes:
+        """hdr_dd_open / hdr_dd_write per pixel / hdr_dd_close of the compiled reference (display/hdrdrv.c): the file's bytes."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        h, w = rgb.shape[:2]
+        with _quiet():
+            rc = self.lib.lref_hdr_file(_ptr(rgb), w, h, path.encode())
+        assert rc == 0
+        with open(path, "rb") as f:
+            return f.read()
 
     def table(self, name: str, n: int) -> np.ndarray:
         """A float table the reference exports as a data symbol (sunsky.dat: S0Amplitudes, S1Amplitudes, S2Amplitudes)."""

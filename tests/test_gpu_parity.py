@@ -423,3 +423,24 @@ def test_device_builder_builds_the_same_tree(maker):
     sa, sb = host.state(rays6, a6), dev.state(rays6, b6)
     m = a6["hit"] == 1
     assert all(np.array_equal(sa[f][m], sb[f][m]) for f in ("P", "Ng", "Ns", "tangent", "binormal"))
+
+
+def test_hdr_output_step_on_device(oracle, golden_dir):
+    """ri_b200_hdr_encode (device float2rgbe + run-length coder) writes the file the reference's .hdr driver
+    writes, byte for byte -- from host framebuffers and from a framebuffer the AO frame left in device memory."""
+    import torch
+    _need_gpu()
+    frames = dict(ol.hdr_cases())
+    frames["c1"] = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
+    frames["sunsky"] = np.load(os.path.join(golden_dir, "sunsky.npz"))["frame_rgb"]
+    for name, rgb in frames.items():
+        assert accel.hdr_encode(rgb) == oracle.hdr_encode(rgb), name
+    g = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    cam = g["cam"]
+    a = accel.Accel.bind().build(g["tris"], accel.PREC_F64)
+    fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 3, 3, gather_nsamples=64)
+    d_rgb = torch.zeros((120, 160, 3), dtype=torch.float32, device="cuda")
+    a.render_ao_dev(fr, d_rgb)
+    torch.cuda.synchronize()
+    want = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
+    assert accel.hdr_encode(d_rgb, 160, 120) == oracle.hdr_encode(want)

@@ -150,3 +150,16 @@ def test_sunsky_frame_golden(oracle, golden_dir):
     assert nrays == int(g["frame_nrays"])
     assert np.array_equal(rgb, g["frame_rgb"])
     assert rgb.max() > 1000.0 and (rgb[..., 2] > rgb[..., 0]).mean() > 0.3      # a blue-ish sky lit the scene
+
+
+def test_hdr_output_golden(oracle, golden_dir):
+    """The .hdr files of the reference's display driver for the committed frames (sha256 + size in hdr.npz, written by
+    tests/golden/make_hdr_golden.py from the compiled reference)."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "hdr.npz"))
+    frames = dict(ol.hdr_cases())
+    frames["c1"] = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
+    frames["sunsky"] = np.load(os.path.join(golden_dir, "sunsky.npz"))["frame_rgb"]
+    for name, rgb in frames.items():
+        data = oracle.hdr_encode(rgb)
+        assert len(data) == int(g[name + "_size"]) and hashlib.sha256(data).hexdigest() == str(g[name + "_sha256"]), name

@@ -84,3 +84,14 @@ def test_sunsky_sky_lookup(oracle, ref, golden_dir):
     want, rec = ref.sunsky_eval(dirs, latitude=60.17, longitude=24.94, sm=2.0, jd=200, tod=18.5, turbidity=3.3)
     got = oracle.sunsky_sky_rgb(ol.sunsky_block(rec, tables), dirs)
     assert np.array_equal(got, want)
+
+
+def test_hdr_output_step(oracle, ref, golden_dir, tmp_path):
+    """the .hdr display driver (hdr_dd_open/write/close -> RGBE_WriteHeader + RGBE_WritePixels_RLE):
+    the restatement writes the reference's file byte for byte."""
+    import os
+    cases = dict(ol.hdr_cases())
+    cases["c1"] = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
+    cases["sunsky"] = np.load(os.path.join(golden_dir, "sunsky.npz"))["frame_rgb"]
+    for name, rgb in cases.items():
+        assert oracle.hdr_encode(rgb) == ref.hdr_file(rgb, str(tmp_path / (name + ".hdr"))), name
