@@ -558,14 +558,16 @@ template <typename Real>
 static int host_occluded_streamed(ri_b200_accel *a, const Real *rays, uint64_t n, uint8_t *out)
 {
     const uint64_t ray_bytes = RayIO<Real>::kRayStride * sizeof(Real);
+    // whole-batch staging; a batch that does not fit (or more than 8 GiB of rays) takes the launch-per-piece path instead
+    if (n * ray_bytes > (8ull << 30)) return 1;
     if (a->whole_in_bytes < n * ray_bytes) {
         cudaFree(a->d_whole_in); a->d_whole_in = nullptr; a->whole_in_bytes = 0;
-        CUDA_OK(cudaMalloc(&a->d_whole_in, n * ray_bytes));
+        if (cudaMalloc(&a->d_whole_in, n * ray_bytes) != cudaSuccess) { cudaGetLastError(); a->d_whole_in = nullptr; return 1; }
         a->whole_in_bytes = n * ray_bytes;
     }
     if (a->whole_out_bytes < n) {
         cudaFree(a->d_whole_out); a->d_whole_out = nullptr; a->whole_out_bytes = 0;
-        CUDA_OK(cudaMalloc(&a->d_whole_out, n));
+        if (cudaMalloc(&a->d_whole_out, n) != cudaSuccess) { cudaGetLastError(); a->d_whole_out = nullptr; return 1; }
         a->whole_out_bytes = n;
     }
     unsigned int *d_ready = a->d_work + 64, *d_fault = a->d_work + 65;
