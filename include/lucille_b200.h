@@ -139,6 +139,17 @@ int ri_b200_occluded_batch_f64 (ri_b200_accel_t *accel, const double *rays, uint
 int ri_b200_state_batch_f64(ri_b200_accel_t *accel, const double *rays, const ri_b200_hit_f64 *hits, uint64_t n,
                             ri_b200_state_f64 *out);
 
+/* the rest of ri_intersection_state_build (intersection_state.c:123-133, 192-246): E, I = normalize(dir), vertex-colour lerp or
+ * (1,1,1), st lerp or 0, the two-sided back-side flag.  Attributes are per INPUT triangle, what ri_geom_t holds behind the index
+ * list: tri_colors [ntris][3][3] (geom->colors) with has_color[ntris] (0: the triangle's geom has no Cs), tri_st [ntris][3][2]
+ * (geom->texcoords or texcoords_unshared) with has_st[ntris], tri_inside[ntris] (1: geom->two_side && index >= nindices/2,
+ * polygon.c:595-612).  Any pointer may be NULL (absent everywhere). */
+typedef struct { double E[3], I[3], color[3], st[2], t; int32_t inside, hit; } ri_b200_state_ext_f64;
+int ri_b200_set_attributes(ri_b200_accel_t *accel, const double *tri_colors, const uint8_t *has_color, const double *tri_st,
+                           const uint8_t *has_st, const uint8_t *tri_inside);
+int ri_b200_state_ext_batch_f64(ri_b200_accel_t *accel, const double *rays, const ri_b200_hit_f64 *hits, uint64_t n,
+                                ri_b200_state_ext_f64 *out);
+
 /* DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the accelerator's own stream) */
 int ri_b200_intersect_dev_f32(ri_b200_accel_t *accel, const float  *d_rays, uint64_t n, ri_b200_hit_f32 *d_out, void *stream);
 int ri_b200_occluded_dev_f32 (ri_b200_accel_t *accel, const float  *d_rays, uint64_t n, uint8_t *d_out, void *stream);

@@ -37,6 +37,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200acce
 
 HIT32_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
 HIT64_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim", "<u4"), ("hit", "<u4")])
+STATE_EXT_DTYPE = np.dtype([("E", "<f8", 3), ("I", "<f8", 3), ("color", "<f8", 3), ("st", "<f8", 2), ("t", "<f8"), ("inside", "<i4"), ("hit", "<i4")])
 STATE_DTYPE = np.dtype([("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
 NODE_DTYPE = np.dtype([("is_leaf", "<i4"), ("axis", "<i4"), ("child0", "<i8"), ("child1", "<i8"),
                        ("tri_start", "<i8"), ("ntris", "<i8"), ("lbox", "<f8", 6), ("rbox", "<f8", 6)])
@@ -119,6 +120,8 @@ ABI = [
     ("ri_b200_intersect_batch_f64", _I, [_P, _P, _U64, _P]),
     ("ri_b200_occluded_batch_f64", _I, [_P, _P, _U64, _P]),
     ("ri_b200_state_batch_f64", _I, [_P, _P, _P, _U64, _P]),
+    ("ri_b200_set_attributes", _I, [_P, _P, _P, _P, _P, _P]),
+    ("ri_b200_state_ext_batch_f64", _I, [_P, _P, _P, _U64, _P]),
     ("ri_b200_intersect_dev_f32", _I, [_P, _P, _U64, _P, _P]),
     ("ri_b200_occluded_dev_f32", _I, [_P, _P, _U64, _P, _P]),
     ("ri_b200_intersect_dev_f64", _I, [_P, _P, _U64, _P, _P]),
@@ -331,6 +334,24 @@ class Accel:
         assert hits.dtype == HIT64_DTYPE
         out = np.zeros(len(rays6), dtype=STATE_DTYPE)
         _check(self.lib.ri_b200_state_batch_f64(self._h(), _ptr(rays6), _ptr(hits), len(rays6), _ptr(out)))
+        return out
+
+    def set_attributes(self, colors=None, has_color=None, st=None, has_st=None, inside=None) -> "Accel":
+        """Per-corner vertex colours [n,3,3] / texture coordinates [n,3,2] with per-triangle presence flags, and the back-side flag
+        of two-sided geometry (intersection_state.c:192-246)."""
+        def arr(x, dt, shape):
+            return None if x is None else np.ascontiguousarray(x, dtype=dt).reshape(shape)
+        args = [arr(colors, np.float64, (-1, 9)), arr(has_color, np.uint8, -1), arr(st, np.float64, (-1, 6)), arr(has_st, np.uint8, -1),
+                arr(inside, np.uint8, -1)]
+        _check(self.lib.ri_b200_set_attributes(self._h(), *[_ptr(x) for x in args]))
+        return self
+
+    def state_ext(self, rays6: np.ndarray, hits: np.ndarray) -> np.ndarray:
+        """E, I, colour, st, t, inside of ``ri_intersection_state_build`` for a batch of fp64 hits."""
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
+        hits = np.ascontiguousarray(hits)
+        out = np.zeros(len(rays6), dtype=STATE_EXT_DTYPE)
+        _check(self.lib.ri_b200_state_ext_batch_f64(self._h(), _ptr(rays6), _ptr(hits), len(rays6), _ptr(out)))
         return out
 
     def count(self, rays: np.ndarray, anyhit: bool = False) -> dict:

@@ -60,6 +60,7 @@ struct ri_b200_accel {
     Tri32 *d_tris32t = nullptr; Tri64 *d_tris64t = nullptr;   // leaf-transposed copies (pool.cuh)
     uint32_t *d_slot_of_prim = nullptr;
     double *d_nrm64 = nullptr; float *d_nrm32 = nullptr;     // optional vertex normals, [prim][9]
+    double *d_col = nullptr, *d_st = nullptr; uint8_t *d_attr_flags = nullptr;   // optional vertex colours [prim][9], st [prim][6], flags (1 colour, 2 st, 4 inside)
     uint64_t device_bytes = 0;
     double   upload_seconds = 0.0;
     // staging for host-buffer batches (double buffered)
@@ -393,7 +394,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
-    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32);
+    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     cudaFree(a->d_whole_in); cudaFree(a->d_whole_out);
     for (auto p : a->d_frame) cudaFree(p);
@@ -796,6 +797,97 @@ extern "C" int ri_b200_state_batch_f64(ri_b200_accel_t *a, const double *rays, c
         LAUNCHED();
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaMemcpyAsync(out, d_out, n * sizeof(ri_b200_state_f64), cudaMemcpyDeviceToHost, a->stream));
+        CUDA_OK(cudaStreamSynchronize(a->stream));
+        return 0;
+    };
+    const int rc = body();
+    cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_out);
+    return rc;
+}
+
+// ---- the rest of ri_intersection_state_build: E, I, colour, st, inside (intersection_state.c:123-133, 192-246) ----------------
+extern "C" int ri_b200_set_attributes(ri_b200_accel_t *a, const double *tri_colors, const uint8_t *has_color, const double *tri_st,
+                                      const uint8_t *has_st, const uint8_t *tri_inside)
+{
+    if (!a) return fail("null argument");
+    if (a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags);
+    a->d_col = a->d_st = nullptr; a->d_attr_flags = nullptr;
+    if (a->tree.empty) return 0;
+    const size_t n = (size_t)a->tree.ntris;
+    std::vector<double> col(9 * n, 0.0), st(6 * n, 0.0);
+    std::vector<uint8_t> fl(n, 0);
+    for (size_t p = 0; p < n; ++p) {                         // post-build order, like the normals
+        const size_t o = (size_t)a->tree.orig[p];
+        if (tri_colors && has_color && has_color[o]) { std::memcpy(&col[9 * p], tri_colors + 9 * o, 9 * sizeof(double)); fl[p] |= 1; }
+        if (tri_st && has_st && has_st[o]) { std::memcpy(&st[6 * p], tri_st + 6 * o, 6 * sizeof(double)); fl[p] |= 2; }
+        if (tri_inside && tri_inside[o]) fl[p] |= 4;
+    }
+    CUDA_OK(cudaMalloc((void **)&a->d_col, col.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&a->d_st, st.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&a->d_attr_flags, n));
+    CUDA_OK(cudaMemcpy(a->d_col, col.data(), col.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(a->d_st, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(a->d_attr_flags, fl.data(), n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+__global__ void state_ext_kernel(const double *__restrict__ col, const double *__restrict__ st, const uint8_t *__restrict__ flags,
+                                 const double *__restrict__ rays, const ri_b200_hit_f64 *__restrict__ hits, uint64_t n,
+                                 ri_b200_state_ext_f64 *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ri_b200_state_ext_f64 s;
+    memset(&s, 0, sizeof(s));
+    const ri_b200_hit_f64 h = hits[i];
+    s.hit = (int32_t)h.hit;
+    if (h.hit) {
+        double org[3], dir[3];
+        RayIO<double>::load(rays, i, org, dir);
+        const uint8_t fl = flags ? flags[h.prim] : 0;
+        for (int k = 0; k < 3; ++k) s.E[k] = org[k];                       // intersection_state.c:133
+        normalize3(dir);                                                   // :130-131
+        for (int k = 0; k < 3; ++k) s.I[k] = dir[k];
+        if (fl & 1) {                                                      // ri_lerp_vector, geometric.c:40-62
+            const double *c = col + 9 * (size_t)h.prim;
+            const double w0 = 1.0 - h.u - h.v;
+            for (int k = 0; k < 3; ++k) { const double x = c[k] * w0, y = c[3 + k] * h.u, z = c[6 + k] * h.v; s.color[k] = (x + y) + z; }
+        } else {
+            for (int k = 0; k < 3; ++k) s.color[k] = 1.0;                  // :204-207
+        }
+        if (fl & 2) {                                                      // lerp_uv, :266-280
+            const double *t = st + 6 * (size_t)h.prim;
+            s.st[0] = (1 - h.u - h.v) * t[0] + h.u * t[2] + h.v * t[4];
+            s.st[1] = (1 - h.u - h.v) * t[1] + h.u * t[3] + h.v * t[5];
+        }
+        s.t = h.t;
+        s.inside = (fl & 4) ? 1 : 0;                                       // :233-246
+    }
+    out[i] = s;
+}
+
+extern "C" int ri_b200_state_ext_batch_f64(ri_b200_accel_t *a, const double *rays, const ri_b200_hit_f64 *hits, uint64_t n,
+                                           ri_b200_state_ext_f64 *out)
+{
+    if (need(a, RI_B200_PREC_F64)) return -1;
+    if (n == 0) return 0;
+    if (!rays || !hits || !out) return fail("null buffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    double *d_rays = nullptr; ri_b200_hit_f64 *d_hits = nullptr; ri_b200_state_ext_f64 *d_out = nullptr;
+    auto body = [&]() -> int {
+        CUDA_OK(cudaMalloc((void **)&d_rays, n * 48));
+        CUDA_OK(cudaMalloc((void **)&d_hits, n * sizeof(ri_b200_hit_f64)));
+        CUDA_OK(cudaMalloc((void **)&d_out, n * sizeof(ri_b200_state_ext_f64)));
+        CUDA_OK(cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, a->stream));
+        CUDA_OK(cudaMemcpyAsync(d_hits, hits, n * sizeof(ri_b200_hit_f64), cudaMemcpyHostToDevice, a->stream));
+        state_ext_kernel<<<(unsigned)((n + 255) / 256), 256, 0, a->stream>>>(a->d_col, a->d_st, a->d_attr_flags, d_rays, d_hits, n, d_out);
+        LAUNCHED();
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync(out, d_out, n * sizeof(ri_b200_state_ext_f64), cudaMemcpyDeviceToHost, a->stream));
         CUDA_OK(cudaStreamSynchronize(a->stream));
         return 0;
     };

@@ -30,6 +30,9 @@ struct orc_tree {
     int         max_depth;
     double     *tri_xyz;       /* post-build order, [ntris][9] v0 v1 v2 */
     double     *tri_nrm;       /* post-build order, [ntris][9] n0 n1 n2, or NULL */
+    double     *tri_col;       /* post-build order, [ntris][9] c0 c1 c2, or NULL */
+    double     *tri_st;        /* post-build order, [ntris][6] st0 st1 st2, or NULL */
+    uint8_t    *tri_flags;     /* post-build order: bit0 has colour, bit1 has st, bit2 inside; or NULL */
     uint32_t   *orig;          /* post-build position -> input triangle */
     /* per-precision views, built once after construction */
     double     *lbox64, *rbox64, *tri64;
@@ -303,7 +306,7 @@ orc_tree *orc_build(const double *tri_xyz, uint64_t ntris)
 void orc_free(orc_tree *T)
 {
     if (!T) return;
-    free(T->nodes); free(T->tri_xyz); free(T->orig); free(T->tri_nrm);
+    free(T->nodes); free(T->tri_xyz); free(T->orig); free(T->tri_nrm); free(T->tri_col); free(T->tri_st); free(T->tri_flags);
     free(T->lbox64); free(T->rbox64); free(T->tri64);
     free(T->lbox32); free(T->rbox32); free(T->tri32);
     free(T);
@@ -460,6 +463,60 @@ static void state_build(const orc_tree *T, const double org[3], const double dir
     ((orc_tree *)T)->tri_nrm = NULL;
     state_build_uv(T, org, dir, t, 0.0, 0.0, prim, s);
     ((orc_tree *)T)->tri_nrm = saved;
+}
+
+void orc_set_attributes(orc_tree *T, const double *colors, const uint8_t *has_color, const double *st, const uint8_t *has_st,
+                        const uint8_t *inside)
+{
+    uint64_t p;
+    free(T->tri_col); free(T->tri_st); free(T->tri_flags);
+    T->tri_col = NULL; T->tri_st = NULL; T->tri_flags = NULL;
+    if (T->empty) return;
+    T->tri_col = (double *)calloc(9 * T->ntris, sizeof(double));
+    T->tri_st = (double *)calloc(6 * T->ntris, sizeof(double));
+    T->tri_flags = (uint8_t *)calloc(T->ntris, 1);
+    for (p = 0; p < T->ntris; p++) {
+        const size_t o = (size_t)T->orig[p];
+        if (colors && has_color && has_color[o]) { memcpy(T->tri_col + 9 * p, colors + 9 * o, sizeof(double) * 9); T->tri_flags[p] |= 1; }
+        if (st && has_st && has_st[o]) { memcpy(T->tri_st + 6 * p, st + 6 * o, sizeof(double) * 6); T->tri_flags[p] |= 2; }
+        if (inside && inside[o]) T->tri_flags[p] |= 4;
+    }
+}
+
+void orc_state_ext_build_f64(const orc_tree *T, const double *rays, const orc_hit_f64 *hits, uint64_t n, orc_state_ext_f64 *out)
+{
+    uint64_t i;
+    int k;
+    for (i = 0; i < n; i++) {
+        const double *r = rays + 6 * i;
+        orc_state_ext_f64 *o = &out[i];
+        memset(o, 0, sizeof(*o));
+        o->hit = (int32_t)hits[i].hit;
+        if (!hits[i].hit) continue;
+        {
+            const uint32_t p = hits[i].prim;
+            const double u = hits[i].u, v = hits[i].v;
+            const uint8_t fl = T->tri_flags ? T->tri_flags[p] : 0;
+            double d[3] = { r[3], r[4], r[5] };
+            for (k = 0; k < 3; k++) o->E[k] = r[k];                          /* intersection_state.c:133 */
+            normalize_f64(d);                                                /* :130-131 */
+            for (k = 0; k < 3; k++) o->I[k] = d[k];
+            if (fl & 1) {                                                    /* ri_lerp_vector, geometric.c:40-62 */
+                const double *c = T->tri_col + 9 * (size_t)p;
+                const double w0 = 1.0 - u - v;
+                for (k = 0; k < 3; k++) { const double a = c[k] * w0, b = c[3 + k] * u, cc = c[6 + k] * v; o->color[k] = (a + b) + cc; }
+            } else {
+                for (k = 0; k < 3; k++) o->color[k] = 1.0;                   /* :204-207 */
+            }
+            if (fl & 2) {                                                    /* lerp_uv, :266-280 */
+                const double *t = T->tri_st + 6 * (size_t)p;
+                o->st[0] = (1 - u - v) * t[0] + u * t[2] + v * t[4];
+                o->st[1] = (1 - u - v) * t[1] + u * t[3] + v * t[5];
+            }
+            o->t = hits[i].t;
+            o->inside = (fl & 4) ? 1 : 0;                                    /* :233-246 */
+        }
+    }
 }
 
 void orc_state_build_f64(const orc_tree *T, const double *rays, const orc_hit_f64 *hits, uint64_t n, orc_state_f64 *out)

@@ -79,6 +79,16 @@ int       orc_max_depth(const orc_tree *t);
  * (its geom's `normals` is NULL) and keeps Ns = Ng.  NULL removes them all. */
 void orc_set_normals(orc_tree *t, const double *tri_normals);
 
+/* vertex colours / texture coordinates / back-side flag of the hit state (intersection_state.c:192-246), per INPUT triangle:
+ * colors [ntris][3][3] with has_color[ntris] (0: the triangle's geom has no Cs -> colour (1,1,1), :204-207), st [ntris][3][2] with
+ * has_st[ntris] (0: no texture coordinates -> st = 0, :228-231), inside[ntris] (1: second half of a two-sided geom, :233-244).
+ * Any pointer may be NULL (= absent everywhere). */
+void orc_set_attributes(orc_tree *t, const double *colors, const uint8_t *has_color, const double *st, const uint8_t *has_st,
+                        const uint8_t *inside);
+typedef struct { double E[3], I[3], color[3], st[2], t; int32_t inside, hit; } orc_state_ext_f64;
+/* the rest of ri_intersection_state_build (intersection_state.c:123-133, 192-246): E, I = normalize(dir), colour, st, inside */
+void orc_state_ext_build_f64(const orc_tree *t, const double *rays, const orc_hit_f64 *hits, uint64_t n, orc_state_ext_f64 *out);
+
 /* closest hit, reference order (bvh.c:430-542, 1092-1188). rays f64: [n][6] org,dir. f32: [n][8] ox,oy,oz,tmin,dx,dy,dz,tmax
  * (tmin/tmax are carried but never read, exactly like ri_ray_t.min_t/max_t). counters may be NULL. */
 void orc_intersect_f64(const orc_tree *t, const double *rays, uint64_t n, orc_hit_f64 *out, orc_counters_t *c);

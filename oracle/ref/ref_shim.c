@@ -290,6 +290,60 @@ double lref_intersect(void *h, const double *rays, uint64_t n, int nthreads, lre
     return now_sec() - t0;
 }
 
+/* ---- vertex colours, texture coordinates, two-sided flag (intersection_state.c:192-246) ------------------------------------
+ * colors: [ntris][3][3], st: [ntris][3][2] per corner, in the input triangle order (the shim's geoms have unshared vertices,
+ * 3 per triangle, so a corner IS a vertex).  geom_flags[g]: bit0 the geom has Cs, bit1 shared texcoords, bit2 unshared texcoords,
+ * bit3 two_side (polygon.c:595-612 doubles the faces; here the second half of the geom's triangles counts as the back side). */
+void lref_scene_set_attr(void *h, const double *colors, const double *st, const uint8_t *geom_flags)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    uint64_t off = 0;
+    int g;
+    for (g = 0; g < s->ngeoms; g++) {
+        ri_geom_t *geom = s->geoms[g];
+        const uint64_t n = geom->nindices / 3;
+        uint64_t i;
+        if (n && colors && (geom_flags[g] & 1)) {
+            ri_vector_t *c = (ri_vector_t *)malloc(sizeof(ri_vector_t) * 3 * n);
+            for (i = 0; i < 3 * n; i++) { c[i][0] = colors[3 * (3 * off + i)]; c[i][1] = colors[3 * (3 * off + i) + 1]; c[i][2] = colors[3 * (3 * off + i) + 2]; c[i][3] = 1.0; }
+            ri_geom_add_colors(geom, (unsigned int)(3 * n), (const ri_vector_t *)c);
+            free(c);
+        }
+        if (n && st && (geom_flags[g] & 6)) {
+            ri_float_t *t = (ri_float_t *)malloc(sizeof(ri_float_t) * 2 * 3 * n);
+            for (i = 0; i < 2 * 3 * n; i++) t[i] = st[2 * 3 * off + i];
+            if (geom_flags[g] & 2) ri_geom_add_texcoords(geom, (unsigned int)(3 * n), t);
+            else ri_geom_add_texcoords_unshared(geom, (unsigned int)(3 * n), t);
+            free(t);
+        }
+        geom->two_side = (geom_flags[g] & 8) ? 1 : 0;
+        off += n;
+    }
+}
+
+typedef struct { double E[3], I[3], color[3], st[2], t; int32_t inside, hit; } lref_ext_t;
+void lref_intersect_ext(void *h, const double *rays, uint64_t n, lref_ext_t *out)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_ray_t ray;
+    ri_intersection_state_t state;
+    uint64_t i;
+    int k;
+    memset(&ray, 0, sizeof(ray));
+    for (i = 0; i < n; i++) {
+        const double *r = rays + 6 * i;
+        lref_ext_t *o = &out[i];
+        ray.org[0] = r[0]; ray.org[1] = r[1]; ray.org[2] = r[2]; ray.org[3] = 1.0;
+        ray.dir[0] = r[3]; ray.dir[1] = r[4]; ray.dir[2] = r[5]; ray.dir[3] = 0.0;
+        memset(o, 0, sizeof(*o));
+        o->hit = ri_bvh_intersect(s->bvh, &ray, &state, NULL);
+        if (!o->hit) continue;
+        for (k = 0; k < 3; k++) { o->E[k] = state.E[k]; o->I[k] = state.I[k]; o->color[k] = state.color[k]; }
+        o->st[0] = state.stqr[0]; o->st[1] = state.stqr[1];
+        o->t = state.t; o->inside = state.inside;
+    }
+}
+
 /* reference traversal counters (only meaningful in libluciref_stat.so; bvh.c:146,686-688) */
 extern ri_bvh_stat_traversal_t g_stattrav;
 void lref_stats_reset(void) { memset(&g_stattrav, 0, sizeof(g_stattrav)); }

@@ -29,6 +29,7 @@ COUNTERS_DTYPE = np.dtype([("nrays", "<u8"), ("ninner", "<u8"), ("nleaf", "<u8")
 REFHIT_DTYPE = np.dtype([("hit", "<i4"), ("index", "<u4"), ("geom_id", "<u4"), ("pad", "<u4"),
                          ("t", "<f8"), ("u", "<f8"), ("v", "<f8"),
                          ("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
+STATE_EXT_DTYPE = np.dtype([("E", "<f8", 3), ("I", "<f8", 3), ("color", "<f8", 3), ("st", "<f8", 2), ("t", "<f8"), ("inside", "<i4"), ("hit", "<i4")])
 MISS_PRIM = 0xFFFFFFFF
 
 
@@ -53,6 +54,24 @@ class SunskyBlock(C.Structure):
                 ("cie", C.c_float * 243), ("cs", C.c_float * 8),
                 ("nsun", C.c_int32), ("pad", C.c_int32),
                 ("sun_dir", C.c_double * 12), ("sun_col", C.c_double * 12)]
+
+
+def attribute_case(ntris: int, geom_sizes, seed: int):
+    """Seeded per-corner colours / st and per-geom flags (1 Cs, 2 shared st, 4 unshared st, 8 two-sided) for the hit-state tests,
+    with the per-triangle presence / back-side arrays the oracle and the product take."""
+    rng = np.random.default_rng(seed)
+    colors = rng.uniform(0.0, 1.0, (ntris, 3, 3))
+    st = rng.uniform(-2.0, 3.0, (ntris, 3, 2))
+    flags = np.array([(1 | 2), 0, (4 | 8), (1 | 8), 2][: len(geom_sizes)], dtype=np.uint8)
+    has_color, has_st, inside = np.zeros(ntris, np.uint8), np.zeros(ntris, np.uint8), np.zeros(ntris, np.uint8)
+    off = 0
+    for n, f in zip(geom_sizes, flags):
+        has_color[off:off + n] = 1 if f & 1 else 0
+        has_st[off:off + n] = 1 if f & 6 else 0
+        if f & 8:
+            inside[off + (3 * n // 2 + 2) // 3: off + n] = 1        # index >= nindices / 2, index = 3 * triangle
+        off += n
+    return colors, st, flags, has_color, has_st, inside
 
 
 def hdr_cases():
@@ -211,6 +230,20 @@ class OracleTree:
         self.lib.orc_state_build_f64(self.h, _ptr(rays6), _ptr(hits), C.c_uint64(len(rays6)), _ptr(out))
         return out
 
+    def set_attributes(self, colors=None, has_color=None, st=None, has_st=None, inside=None):
+        """Per-corner colours [n,3,3] / texture coordinates [n,3,2] with per-triangle presence flags, and the back-side flag."""
+        def arr(a, dt, shape):
+            return None if a is None else np.ascontiguousarray(a, dtype=dt).reshape(shape)
+        self._attr = [arr(colors, np.float64, (-1, 9)), arr(has_color, np.uint8, -1), arr(st, np.float64, (-1, 6)), arr(has_st, np.uint8, -1),
+                      arr(inside, np.uint8, -1)]
+        self.lib.orc_set_attributes(self.h, *[None if a is None else _ptr(a) for a in self._attr])
+
+    def state_ext(self, rays6: np.ndarray, hits: np.ndarray) -> np.ndarray:
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(len(rays6), dtype=STATE_EXT_DTYPE)
+        self.lib.orc_state_ext_build_f64(self.h, _ptr(rays6), _ptr(np.ascontiguousarray(hits)), C.c_uint64(len(rays6)), _ptr(out))
+        return out
+
     def beam_visibility(self, beams15: np.ndarray) -> np.ndarray:
         beams15 = np.ascontiguousarray(beams15, dtype=np.float64).reshape(-1, 15)
         out = np.zeros(len(beams15), dtype=np.int32)
@@ -267,6 +300,8 @@ class Oracle:
         lib.orc_render_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_splitmix64.restype = C.c_uint64
         lib.orc_splitmix64.argtypes = [C.c_uint64]
+        lib.orc_set_attributes.argtypes = [C.c_void_p] * 6
+        lib.orc_state_ext_build_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_hdr_encode.restype = C.c_uint64
         lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -362,6 +397,19 @@ class ReferenceScene:
                                       _ptr(out) if want_hits else None)
         return out, sec
 
+    def set_attributes(self, colors, st, geom_flags):
+        """colors [n,3,3], st [n,3,2] (either may be None); geom_flags per geom: 1 Cs, 2 shared st, 4 unshared st, 8 two-sided."""
+        c = None if colors is None else np.ascontiguousarray(colors, dtype=np.float64)
+        t = None if st is None else np.ascontiguousarray(st, dtype=np.float64)
+        f = np.ascontiguousarray(geom_flags, dtype=np.uint8)
+        self.lib.lref_scene_set_attr(self.h, None if c is None else _ptr(c), None if t is None else _ptr(t), _ptr(f))
+
+    def intersect_ext(self, rays6: np.ndarray) -> np.ndarray:
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(len(rays6), dtype=STATE_EXT_DTYPE)
+        self.lib.lref_intersect_ext(self.h, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out))
+        return out
+
     def beam_visibility(self, org, dirs) -> int:
         org = np.ascontiguousarray(org, dtype=np.float64)
         dirs = np.ascontiguousarray(dirs, dtype=np.float64)
@@ -390,6 +438,8 @@ class Reference:
         lib.lref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.lref_stats_get.argtypes = [C.c_void_p]
         lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_scene_set_attr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_intersect_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_void_p]
         lib.lref_sunsky_eval.restype = None

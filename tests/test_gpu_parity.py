@@ -444,3 +444,26 @@ def test_hdr_output_step_on_device(oracle, golden_dir):
     torch.cuda.synchronize()
     want = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
     assert accel.hdr_encode(d_rgb, 160, 120) == oracle.hdr_encode(want)
+
+
+def test_hit_state_colours_texcoords_inside(oracle):
+    """Row a8 completed: E, I, vertex colours, st and the back-side flag of ri_intersection_state_build on the device, bit-identical
+    to the oracle (which tests/test_oracle_vs_reference.py pins to the compiled reference on the same kind of scene)."""
+    _need_gpu()
+    sizes = [300, 200, 250, 150, 100]
+    tris = scenes.triangle_soup(sum(sizes), 21)
+    colors, st, flags, has_color, has_st, inside = ol.attribute_case(len(tris), sizes, 4)
+    ot = oracle.build(tris)
+    ot.set_attributes(colors, has_color, st, has_st, inside)
+    a = accel.Accel.bind().build(tris, accel.PREC_F64).set_attributes(colors, has_color, st, has_st, inside)
+    rng = np.random.default_rng(8)
+    org = rng.uniform(-0.5, 1.5, (30000, 3))
+    rays6 = np.concatenate([org, rng.uniform(0.0, 1.0, (30000, 3)) - org], axis=1)
+    hits = a.intersect(rays6)
+    oh = ot.intersect_f64(rays6)
+    assert all(np.array_equal(hits[f], oh[f]) for f in ("t", "u", "v", "prim", "hit"))
+    got, want = a.state_ext(rays6, hits), ot.state_ext(rays6, oh)
+    for f in ("E", "I", "color", "st", "t", "inside", "hit"):
+        assert np.array_equal(got[f], want[f]), f
+    m = got["hit"] != 0
+    assert (got["color"][m] != 1.0).any() and (got["st"][m] != 0.0).any() and set(np.unique(got["inside"][m])) == {0, 1}

@@ -95,3 +95,28 @@ def test_hdr_output_step(oracle, ref, golden_dir, tmp_path):
     cases["sunsky"] = np.load(os.path.join(golden_dir, "sunsky.npz"))["frame_rgb"]
     for name, rgb in cases.items():
         assert oracle.hdr_encode(rgb) == ref.hdr_file(rgb, str(tmp_path / (name + ".hdr"))), name
+
+
+def test_hit_state_colours_texcoords_inside(oracle, ref):
+    """Row a8, the rest of ri_intersection_state_build (intersection_state.c:123-133, 192-246): E, I, vertex-colour lerp or (1,1,1),
+    st lerp (shared and unshared texture coordinates) or 0, the two-sided back-side flag -- bit-identical to the reference."""
+    sizes = [300, 200, 250, 150, 100]
+    tris = scenes.triangle_soup(sum(sizes), 21)
+    colors, st, flags, has_color, has_st, inside = ol.attribute_case(len(tris), sizes, 4)
+    rs = ref.build(tris, geom_sizes=sizes)
+    rs.set_attributes(colors, st, flags)
+    ot = oracle.build(tris)
+    ot.set_attributes(colors, has_color, st, has_st, inside)
+    rng = np.random.default_rng(8)
+    org = rng.uniform(-0.5, 1.5, (30000, 3))
+    rays6 = np.concatenate([org, rng.uniform(0.0, 1.0, (30000, 3)) - org], axis=1)
+    want = rs.intersect_ext(rays6)
+    hits = ot.intersect_f64(rays6)
+    got = ot.state_ext(rays6, hits)
+    m = want["hit"] != 0
+    assert m.sum() > 3000 and np.array_equal(got["hit"] != 0, m)
+    for f in ("E", "I", "color", "st", "t", "inside"):
+        assert np.array_equal(got[f][m], want[f][m]), f
+    # every class occurs: coloured and default colour, st and none, both sides
+    assert (got["color"][m] != 1.0).any() and (got["color"][m] == 1.0).all(axis=1).any()
+    assert (got["st"][m] != 0.0).any() and (got["st"][m] == 0.0).all(axis=1).any() and set(np.unique(got["inside"][m])) == {0, 1}
