@@ -122,6 +122,7 @@ ABI = [
     ("ri_b200_state_batch_f64", _I, [_P, _P, _P, _U64, _P]),
     ("ri_b200_set_attributes", _I, [_P, _P, _P, _P, _P, _P]),
     ("ri_b200_state_ext_batch_f64", _I, [_P, _P, _P, _U64, _P]),
+    ("ri_b200_set_texture", _I, [_P, _P, _I, _I, _P]),
     ("ri_b200_intersect_dev_f32", _I, [_P, _P, _U64, _P, _P]),
     ("ri_b200_occluded_dev_f32", _I, [_P, _P, _U64, _P, _P]),
     ("ri_b200_intersect_dev_f64", _I, [_P, _P, _U64, _P, _P]),
@@ -344,6 +345,16 @@ class Accel:
         args = [arr(colors, np.float64, (-1, 9)), arr(has_color, np.uint8, -1), arr(st, np.float64, (-1, 6)), arr(has_st, np.uint8, -1),
                 arr(inside, np.uint8, -1)]
         _check(self.lib.ri_b200_set_attributes(self._h(), *[_ptr(x) for x in args]))
+        return self
+
+    def set_texture(self, rgba, tri_textured=None) -> "Accel":
+        """Material texture of the AO transport ([h,w,4] float32; None removes it); call after set_attributes."""
+        if rgba is None:
+            _check(self.lib.ri_b200_set_texture(self._h(), None, 0, 0, None))
+            return self
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        mask = None if tri_textured is None else np.ascontiguousarray(tri_textured, dtype=np.uint8)
+        _check(self.lib.ri_b200_set_texture(self._h(), _ptr(rgba), rgba.shape[1], rgba.shape[0], _ptr(mask)))
         return self
 
     def state_ext(self, rays6: np.ndarray, hits: np.ndarray) -> np.ndarray:

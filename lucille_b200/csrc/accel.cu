@@ -60,6 +60,7 @@ struct ri_b200_accel {
     Tri32 *d_tris32t = nullptr; Tri64 *d_tris64t = nullptr;   // leaf-transposed copies (pool.cuh)
     uint32_t *d_slot_of_prim = nullptr;
     double *d_nrm64 = nullptr; float *d_nrm32 = nullptr;     // optional vertex normals, [prim][9]
+    float *d_tex = nullptr; int tex_w = 0, tex_h = 0;          // optional material texture, [h][w][4] floats
     double *d_col = nullptr, *d_st = nullptr; uint8_t *d_attr_flags = nullptr;   // optional vertex colours [prim][9], st [prim][6], flags (1 colour, 2 st, 4 inside)
     uint64_t device_bytes = 0;
     double   upload_seconds = 0.0;
@@ -394,7 +395,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
-    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags);
+    cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags); cudaFree(a->d_tex);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     cudaFree(a->d_whole_in); cudaFree(a->d_whole_out);
     for (auto p : a->d_frame) cudaFree(p);
@@ -831,6 +832,43 @@ extern "C" int ri_b200_set_attributes(ri_b200_accel_t *a, const double *tri_colo
     CUDA_OK(cudaMemcpy(a->d_col, col.data(), col.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(a->d_st, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(a->d_attr_flags, fl.data(), n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Material texture of the AO transport (ambientocclusion.c:393-401; what Surface "..." "texture" [...] loads, ri/attribute.c:309-327):
+// rgba [h][w][4] floats = ri_texture_t.data after ri_texture_scale; tri_textured[ntris] marks the triangles whose geom carries it
+// (NULL: all).  The st come from ri_b200_set_attributes (call it first); a textured triangle without st fetches at (0,0).
+__global__ void mark_textured_kernel(uint8_t *flags, const uint8_t *textured, uint32_t n)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) flags[p] = (uint8_t)((flags[p] & ~8u) | (textured[p] ? 8u : 0u));
+}
+
+extern "C" int ri_b200_set_texture(ri_b200_accel_t *a, const float *rgba, int width, int height, const uint8_t *tri_textured)
+{
+    if (!a) return fail("null argument");
+    if (a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaFree(a->d_tex); a->d_tex = nullptr; a->tex_w = a->tex_h = 0;
+    if (!rgba || a->tree.empty) return 0;
+    if (width < 1 || height < 1) return fail("bad texture size");
+    const size_t n = (size_t)a->tree.ntris;
+    std::vector<uint8_t> mark(n, 1);
+    if (tri_textured) for (size_t p = 0; p < n; ++p) mark[p] = tri_textured[(size_t)a->tree.orig[p]] ? 1 : 0;
+    if (!a->d_attr_flags) {
+        CUDA_OK(cudaMalloc((void **)&a->d_attr_flags, n));
+        CUDA_OK(cudaMemset(a->d_attr_flags, 0, n));
+    }
+    uint8_t *d_mark = nullptr;
+    CUDA_OK(cudaMalloc((void **)&d_mark, n));
+    cudaError_t e = cudaMemcpy(d_mark, mark.data(), n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { mark_textured_kernel<<<(unsigned)((n + 255) / 256), 256>>>(a->d_attr_flags, d_mark, (uint32_t)n); LAUNCHED(); e = cudaDeviceSynchronize(); }
+    cudaFree(d_mark);
+    if (e != cudaSuccess) return fail("texture mask upload failed: %s", cudaGetErrorString(e));
+    CUDA_OK(cudaMalloc((void **)&a->d_tex, sizeof(float) * 4 * (size_t)width * height));
+    CUDA_OK(cudaMemcpy(a->d_tex, rgba, sizeof(float) * 4 * (size_t)width * height, cudaMemcpyHostToDevice));
+    a->tex_w = width; a->tex_h = height;
     return 0;
 }
 

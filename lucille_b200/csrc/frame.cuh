@@ -189,12 +189,47 @@ template <> struct StateMath<float> {
     }
 };
 
+// ---- material texture of the AO transport (ambientocclusion.c:393-401): radiance *= ri_texture_fetch(texture, st) per channel ----
+struct TexDev {
+    const float   *data;      // [h][w][4] floats (ri_texture_t.data, USE_ZORDER 0), NULL: no texture
+    int            width, height;
+    const double  *st;        // [prim][6] corner texture coordinates (may be NULL)
+    const uint8_t *flags;     // [prim]: 2 = has st, 8 = the triangle's geom carries the texture (may be NULL: no triangle does)
+    double        *texcol;    // out: [rank][3]; (1,1,1) where the hit triangle is not textured
+};
+
+// render/texture.c:86-236: wrap by floor, clamp, bilinear over the 2x2 texels at (u (w-1), v (h-1)), ZERO texels beyond the last
+// row / column
+__device__ __forceinline__ void texture_fetch_dev(const TexDev &T, double u, double v, double out[3])
+{
+    const double sx = floor(u), sy = floor(v);
+    u = u - sx; v = v - sy;
+    if (u < 0.0) u = 0.0;
+    if (u >= 1.0) u = 1.0;
+    if (v < 0.0) v = 0.0;
+    if (v >= 1.0) v = 1.0;
+    const double px = u * (double)(T.width - 1), py = v * (double)(T.height - 1);
+    const int x = (int)px, y = (int)py;
+    const double dx = px - (double)x, dy = py - (double)y;
+    const double w0 = (1.0 - dx) * (1.0 - dy), w1 = (1.0 - dx) * dy, w2 = dx * (1.0 - dy), w3 = dx * dy;
+    const bool my = y < T.height - 1, mx = x < T.width - 1;
+    const float *t0 = T.data + 4 * ((size_t)y * T.width + x);
+    const float *t1 = t0 + 4 * (size_t)T.width, *t2 = t0 + 4, *t3 = t1 + 4;
+    for (int i = 0; i < 3; ++i) {
+        const double a = (double)t0[i];
+        const double b = my ? (double)t1[i] : 0.0;                      // texel (x, y+1)
+        const double c = mx ? (double)t2[i] : 0.0;                      // texel (x+1, y)
+        const double d = (my && mx) ? (double)t3[i] : 0.0;              // texel (x+1, y+1)
+        out[i] = w0 * a + w1 * b + w2 * c + w3 * d;
+    }
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(kScanBlock)
 compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter,
                const uint64_t nsamples, const Real *__restrict__ hit_t, const uint32_t *__restrict__ hit_prim,
                const Real *__restrict__ hit_uv, const uint32_t *__restrict__ tile_offsets, uint32_t *__restrict__ sample_rank, uint32_t *__restrict__ rank_sample,
-               Real *__restrict__ records)
+               Real *__restrict__ records, const TexDev tex)
 {
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     uint32_t flags = 0, c = 0;
@@ -221,6 +256,23 @@ compact_kernel(const SceneView<Real> S, const FrameDev F, const uint32_t *__rest
         Real *dst = records + 12 * (uint64_t)rank;
 #pragma unroll
         for (int q = 0; q < 12; ++q) dst[q] = rec[q];
+        if (tex.data) {                                                  // ambientocclusion.c:393-401
+            double col[3] = {1.0, 1.0, 1.0};
+            const uint32_t prim = hit_prim[s];
+            const uint8_t fl = tex.flags ? tex.flags[prim] : 0;
+            if (fl & 8) {
+                double s0 = 0.0, s1 = 0.0;
+                if ((fl & 2) && tex.st) {                                // lerp_uv, intersection_state.c:266-280
+                    const double u = (double)hit_uv[2 * s], v = (double)hit_uv[2 * s + 1];
+                    const double *c = tex.st + 6 * (size_t)prim;
+                    s0 = (1 - u - v) * c[0] + u * c[2] + v * c[4];
+                    s1 = (1 - u - v) * c[1] + u * c[3] + v * c[5];
+                }
+                texture_fetch_dev(tex, s0, s1, col);
+            }
+            double *o = tex.texcol + 3 * (uint64_t)rank;
+            o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+        }
         ++rank;
     }
 }
@@ -459,6 +511,29 @@ ao_gen_kernel(const FrameDev F, const uint64_t nrays, const uint32_t rank0, cons
     }
 }
 
+// ---- resolve with a material texture: radiance[k] = Lo * texcol[k] (ambientocclusion.c:398-400), three channels
+__global__ void resolve_tex_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
+                                   const uint32_t *__restrict__ sample_rank, const uint32_t *__restrict__ occ, const double *__restrict__ texcol,
+                                   float *__restrict__ rgb, const int packed)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npixels) return;
+    const uint32_t pix = pixels[p];
+    const int x = (int)(pix & 0xffffu), y = (int)(pix >> 16);
+    const double ns = (double)F.nao;
+    double accum[3] = {0.0, 0.0, 0.0};
+    for (int sub = 0; sub < F.spp; ++sub) {
+        const uint32_t r = sample_rank[p * (uint64_t)F.spp + sub];
+        for (int q = 0; q < 3; ++q) {
+            double rad = 0.0;
+            if (r != 0xffffffffu) { rad = 1.0 * (ns - (double)occ[r]) / ns; rad *= texcol[3 * (uint64_t)r + q]; }
+            accum[q] = accum[q] + rad;
+        }
+    }
+    float *dst = packed ? rgb + 3 * p : rgb + 3 * ((uint64_t)(F.height - y - 1) * F.width + x);
+    for (int q = 0; q < 3; ++q) dst[q] = (float)(accum[q] * (1.0 / (double)(F.xsamples * F.ysamples)));
+}
+
 // ---- resolve: Lo = (N - occluded)/N per hit sample, mean over sub-samples, float at row H-1-y ---------
 __global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
                                const uint32_t *__restrict__ sample_rank, const uint32_t *__restrict__ occ, float *__restrict__ rgb,
@@ -647,10 +722,11 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     Real *d_t;
     if (frame_buf(a, 0, (npix + 1) * 4 + jit.size() * 8 + 64, &p)) return -1;
     d_jit = (double *)p; d_pix = (uint32_t *)(d_jit + jit.size());
-    const bool with_normals = make_view<Real>(a).normals != nullptr;
-    if (frame_buf(a, 1, (nsamples + 1) * sizeof(Real) * (with_normals ? 3 : 1), &p)) return -1;
+    const bool textured = a->d_tex != nullptr && !sky;                   // the sun-sky branch does not look at the texture (ambientocclusion.c:369-376)
+    const bool with_normals = make_view<Real>(a).normals != nullptr, with_uv = with_normals || textured;
+    if (frame_buf(a, 1, (nsamples + 1) * sizeof(Real) * (with_uv ? 3 : 1), &p)) return -1;
     d_t = (Real *)p;
-    Real *d_uv = with_normals ? d_t + nsamples : nullptr;
+    Real *d_uv = with_uv ? d_t + nsamples : nullptr;
     if (frame_buf(a, 2, (nsamples + 1) * 4 * 3 + ((uint64_t)ntiles + 4) * 4, &p)) return -1;
     d_prim = (uint32_t *)p; d_srank = d_prim + nsamples; d_ranks = d_srank + nsamples; d_tiles = d_ranks + nsamples;
     uint32_t *d_total = d_tiles + ntiles;
@@ -680,6 +756,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
 
     const uint64_t nao_rays = (uint64_t)nhits * (uint64_t)N;
+    double *d_texcol = nullptr;
     Real *d_rec = nullptr;
     uint32_t *d_occ = nullptr, *d_mt = nullptr;
     if (frame_buf(a, 3, ((uint64_t)nhits + 1) * 12 * sizeof(Real), &p)) return -1;
@@ -692,7 +769,15 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     const uint32_t mt_segments = (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks);
 
     if (nhits) {
-        compact_kernel<Real><<<ntiles, kScanBlock, 0, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_uv, d_tiles, d_srank, d_ranks, d_rec);
+        TexDev tex;
+        tex.data = textured ? a->d_tex : nullptr; tex.width = a->tex_w; tex.height = a->tex_h; tex.st = a->d_st; tex.flags = a->d_attr_flags;
+        tex.texcol = nullptr;
+        if (textured) {
+            if (frame_buf(a, 9, ((uint64_t)nhits + 1) * 3 * sizeof(double), &p)) return -1;
+            tex.texcol = (double *)p;
+        }
+        d_texcol = tex.texcol;
+        compact_kernel<Real><<<ntiles, kScanBlock, 0, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_uv, d_tiles, d_srank, d_ranks, d_rec, tex);
         LAUNCHED();
         CUDA_OK(cudaMemsetAsync(d_occ, 0, (uint64_t)nhits * 4, st));
     } else if (nsamples) {
@@ -745,6 +830,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     CUDA_OK(cudaEventRecord(a->ev[4], st));
     if (npix) {
         if (sky) resolve_rgb_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_lo, d_rgb, packed);
+        else if (textured && d_texcol) resolve_tex_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_texcol, d_rgb, packed);
         else resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed);
         LAUNCHED();
     }

@@ -765,6 +765,100 @@ void orc_render_ao(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ material texture (row a11, ambientocclusion.c:393-401) */
+
+/* render/texture.c:86-236 with USE_ZORDER 0 */
+static void tex_fetch(const float *data, int width, int height, double u, double v, double color_out[4])
+{
+    int i, idx, x, y;
+    double sx, sy, w[4], texel[4][4], px, py, dx, dy;
+    sx = floor(u); sy = floor(v);
+    u = u - sx; v = v - sy;
+    if (u < 0.0) u = 0.0;
+    if (u >= 1.0) u = 1.0;
+    if (v < 0.0) v = 0.0;
+    if (v >= 1.0) v = 1.0;
+    px = u * (width - 1);
+    py = v * (height - 1);
+    x = (int)px; y = (int)py;
+    dx = px - x; dy = py - y;
+    w[0] = (1.0 - dx) * (1.0 - dy);
+    w[1] = (1.0 - dx) * dy;
+    w[2] = dx * (1.0 - dy);
+    w[3] = dx * dy;
+    idx = y * width + x;
+    for (i = 0; i < 4; i++) texel[0][i] = data[4 * idx + i];
+    for (i = 0; i < 4; i++) { texel[1][i] = 0.0; texel[2][i] = 0.0; texel[3][i] = 0.0; }
+    if (y < height - 1 && x < width - 1) {
+        idx = (y + 1) * width + x;     for (i = 0; i < 4; i++) texel[1][i] = data[4 * idx + i];
+        idx = y * width + x + 1;       for (i = 0; i < 4; i++) texel[2][i] = data[4 * idx + i];
+        idx = (y + 1) * width + x + 1; for (i = 0; i < 4; i++) texel[3][i] = data[4 * idx + i];
+    } else if (y < height - 1) {
+        idx = (y + 1) * width + x;     for (i = 0; i < 4; i++) texel[1][i] = data[4 * idx + i];
+    } else if (x < width - 1) {
+        idx = y * width + x + 1;       for (i = 0; i < 4; i++) texel[2][i] = data[4 * idx + i];
+    }
+    for (i = 0; i < 4; i++)
+        color_out[i] = (double)(w[0] * texel[0][i] + w[1] * texel[1][i] + w[2] * texel[2][i] + w[3] * texel[3][i]);
+}
+
+void orc_texture_fetch(const float *rgba, int width, int height, const double *uv, uint64_t n, double *out4)
+{
+    uint64_t i;
+    for (i = 0; i < n; i++) tex_fetch(rgba, width, height, uv[2 * i], uv[2 * i + 1], out4 + 4 * i);
+}
+
+void orc_render_ao_textured(const orc_tree *T, const orc_frame_t *f, const float *rgba, int tw, int th, float *rgb, uint64_t *nrays_out)
+{
+    int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(f->width, f->height, f->bucket_size, buckets, nb_max);
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t nrays = 0;
+    int b, k;
+
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, 4357);
+    for (b = 0; b < nb; b++) {
+        int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        int u, v;
+        for (v = by; v < by + bh; v++) {
+            for (u = bx; u < bx + bw; u++) {
+                double accum[3] = {0.0, 0.0, 0.0};
+                int xs, ys;
+                float *dst = rgb + 3 * ((size_t)(f->height - v - 1) * f->width + u);
+                for (ys = 0; ys < f->ysamples; ys++) {
+                    for (xs = 0; xs < f->xsamples; xs++) {
+                        double jx, jy, org[3], dir[3], t, uu, vv, rad[3] = {0.0, 0.0, 0.0};
+                        uint32_t prim;
+                        orc_subpixel_jitter(xs, ys, f->xsamples, f->ysamples, &jx, &jy);
+                        orc_camera_ray(f, (double)(u + jx), (double)(v + jy), org, dir);
+                        nrays++;
+                        if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+                            orc_state_f64 st;
+                            double lo, s0 = 0.0, s1 = 0.0, texcol[4];
+                            state_build_uv(T, org, dir, t, uu, vv, prim, &st);
+                            lo = ao_radiance(T, &V, &st, f->ntheta, f->nphi, &rng, &nrays);
+                            if (T->tri_flags && (T->tri_flags[prim] & 2)) {                  /* lerp_uv, intersection_state.c:266-280 */
+                                const double *c = T->tri_st + 6 * (size_t)prim;
+                                s0 = (1 - uu - vv) * c[0] + uu * c[2] + vv * c[4];
+                                s1 = (1 - uu - vv) * c[1] + uu * c[3] + vv * c[5];
+                            }
+                            tex_fetch(rgba, tw, th, s0, s1, texcol);
+                            for (k = 0; k < 3; k++) { rad[k] = lo; rad[k] *= texcol[k]; }     /* ambientocclusion.c:398-400 */
+                        }
+                        for (k = 0; k < 3; k++) accum[k] = accum[k] + rad[k];
+                    }
+                }
+                for (k = 0; k < 3; k++) dst[k] = (float)(accum[k] * ((double)1.0 / (f->xsamples * f->ysamples)));
+            }
+        }
+    }
+    free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
 /* ------------------------------------------------------------------ sun-sky gather (row a12) */
 
 /* sunsky.c:24-38.  All variables are float, the libm calls are the double ones: every `sin(x)` promotes its float argument

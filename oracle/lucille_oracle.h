@@ -154,6 +154,14 @@ typedef struct {
 void orc_render_pathtrace(const orc_tree *t, const orc_path_frame_t *f, float *rgb, uint64_t *nrays_out);
 void orc_det_sincos2pi(double r, double *s, double *c);
 
+/* ---- material texture of the AO transport (ambientocclusion.c:393-401): radiance *= ri_texture_fetch(texture, st) per channel.
+ * ri_texture_fetch (render/texture.c:86-236, USE_ZORDER 0): wrap by floor, clamp, bilinear over the 2x2 texels at
+ * (u (w-1), v (h-1)) with ZERO texels beyond the last row / column.  rgba: [h][w][4] floats (ri_texture_t.data). */
+void orc_texture_fetch(const float *rgba, int width, int height, const double *uv, uint64_t n, double *out4);
+/* orc_render_ao with every geom carrying this material texture; st per triangle from orc_set_attributes (0 where absent) */
+void orc_render_ao_textured(const orc_tree *t, const orc_frame_t *f, const float *rgba, int tex_width, int tex_height,
+                            float *rgb, uint64_t *nrays_out);
+
 /* ---- sun-sky gather (row a12): ambientocclusion.c:153-324 gather_sunsky + contribution_from_sunlight, with the sky lookup
  * ri_sunsky_get_sky_rgb (render/sunsky.c:24-38 angle_between, 136-152 PerezFunction, 297-408; render/specrend.c:127-172
  * xyz_to_rgb, 366-440 spectrum_to_xyz).  The block is what the host side owns after ri_sunsky_init(): Perez coefficients,

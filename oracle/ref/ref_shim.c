@@ -40,6 +40,43 @@
 
 static void capture_sunsky(void);
 
+/* ---- material texture (ambientocclusion.c:393-401): a float RGBA image handed over by the test driver becomes the
+ * material->texture of every geom of the frame, exactly the object Surface "..." "texture" [...] would have loaded
+ * (ri/attribute.c:309-327), without going through the image readers. */
+#include "texture.h"
+#include "material.h"
+static ri_texture_t g_frame_tex;
+static int          g_have_frame_tex = 0;
+void lref_set_frame_texture(const float *rgba, int width, int height)
+{
+    g_have_frame_tex = 0;
+    if (!rgba || width < 1 || height < 1) return;
+    memset(&g_frame_tex, 0, sizeof(g_frame_tex));
+    g_frame_tex.data = (float *)malloc(sizeof(float) * 4 * (size_t)width * height);
+    memcpy(g_frame_tex.data, rgba, sizeof(float) * 4 * (size_t)width * height);
+    g_frame_tex.width = width; g_frame_tex.height = height;
+    g_have_frame_tex = 1;
+}
+static void attach_frame_texture(ri_geom_t *geom)
+{
+    if (!g_have_frame_tex) return;
+    if (!geom->material) geom->material = ri_material_new();
+    geom->material->texture = &g_frame_tex;
+}
+/* ri_texture_fetch (render/texture.c:86-236) on a caller-supplied image: uv [n][2] doubles -> out [n][4] doubles */
+void lref_texture_fetch(const float *rgba, int width, int height, const double *uv, uint64_t n, double *out)
+{
+    ri_texture_t t;
+    uint64_t i;
+    memset(&t, 0, sizeof(t));
+    t.data = (float *)rgba; t.width = width; t.height = height;
+    for (i = 0; i < n; i++) {
+        ri_vector_t c;
+        ri_texture_fetch(c, &t, uv[2 * i], uv[2 * i + 1]);
+        out[4 * i] = c[0]; out[4 * i + 1] = c[1]; out[4 * i + 2] = c[2]; out[4 * i + 3] = c[3];
+    }
+}
+
 extern int lref_rib_parse_file(const char *path);
 
 /* ------------------------------------------------------------------ ray level */
@@ -391,6 +428,8 @@ typedef struct {
     /* scene capture (taken in the display-open callback, before the build) */
     double  *tri_xyz; uint64_t ntris; uint32_t *tri_geom; int ngeoms;
     double  *tri_nrm;        /* [ntris][3][3] vertex normals per corner (zeros where the geom has none) */
+    double  *tri_st;         /* [ntris][3][2] texture coordinates per corner (zeros where the geom has none) */
+    uint8_t *tri_has_st;     /* [ntris] */
     double   c2w[16]; double flength; int is_rh; int ortho; double fov;
     int      xsamples, ysamples, gather, bucket_size, bucket_order;
     int      has_normals;
@@ -439,19 +478,25 @@ static int dd_open(const char *name, int width, int height, int bits, RtToken co
     g_frame.tri_xyz  = (double *)malloc(sizeof(double) * 9 * (n ? n : 1));
     g_frame.tri_geom = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
     g_frame.tri_nrm  = (double *)calloc(9 * (n ? n : 1), sizeof(double));
+    g_frame.tri_st   = (double *)calloc(6 * (n ? n : 1), sizeof(double));
+    g_frame.tri_has_st = (uint8_t *)calloc(n ? n : 1, 1);
     g = 0;
     for (itr = ri_list_first(r->scene->geom_list); itr; itr = ri_list_next(itr)) {
         ri_geom_t *geom = (ri_geom_t *)itr->data;
         unsigned int t;
         if (geom->normals) g_frame.has_normals = 1;
+        attach_frame_texture(geom);
         for (t = 0; t < geom->nindices / 3; t++) {
             for (i = 0; i < 3; i++)
                 for (j = 0; j < 3; j++)
                 {
                     g_frame.tri_xyz[9 * idx + 3 * i + j] = geom->positions[geom->indices[3 * t + i]][j];
                     if (geom->normals) g_frame.tri_nrm[9 * idx + 3 * i + j] = geom->normals[geom->indices[3 * t + i]][j];
+                    if (j < 2 && geom->texcoords) g_frame.tri_st[6 * idx + 2 * i + j] = geom->texcoords[2 * geom->indices[3 * t + i] + j];
+                    else if (j < 2 && geom->texcoords_unshared) g_frame.tri_st[6 * idx + 2 * i + j] = geom->texcoords_unshared[2 * (3 * t + i) + j];
                 }
             g_frame.tri_geom[idx] = (uint32_t)g;
+            g_frame.tri_has_st[idx] = (geom->texcoords || geom->texcoords_unshared) ? 1 : 0;
             idx++;
         }
         g++;
@@ -533,6 +578,8 @@ uint64_t lref_frame_ntris(void)  { return g_frame.ntris; }
 double  *lref_frame_tris(void)   { return g_frame.tri_xyz; }
 uint32_t*lref_frame_trigeom(void){ return g_frame.tri_geom; }
 double  *lref_frame_normals(void){ return g_frame.tri_nrm; }
+double  *lref_frame_st(void)     { return g_frame.tri_st; }
+uint8_t *lref_frame_has_st(void) { return g_frame.tri_has_st; }
 /* ---- sun-sky (row a12) ---------------------------------------------------------------------------------------------
  * block layout = orc_sunsky_t / ri_b200_sunsky_t minus the tables the reference keeps private:
  * out[0..1] sun_theta, sun_phi; [2..6] perez_x; [7..11] perez_y; [12..16] perez_Y; [17..19] zenith x,y,Y;

@@ -74,6 +74,22 @@ def attribute_case(ntris: int, geom_sizes, seed: int):
     return colors, st, flags, has_color, has_st, inside
 
 
+def test_texture(w: int = 23, h: int = 17, seed: int = 3) -> np.ndarray:
+    """A seeded float RGBA image (not a power of two, not square) for the material-texture tests."""
+    rng = np.random.default_rng(seed)
+    return rng.uniform(0.0, 2.0, (h, w, 4)).astype(np.float32)
+
+
+test_texture.__test__ = False
+
+
+def read_attr(path: str, ntris: int):
+    raw = np.fromfile(path, dtype=np.uint8)
+    st = raw[: 48 * ntris].view("<f8").reshape(ntris, 3, 2).copy()
+    has_st = raw[48 * ntris: 49 * ntris].copy()
+    return st, has_st
+
+
 def hdr_cases():
     """Float framebuffers for the .hdr output tests: noise with negative components, long runs, a width below 8 (flat pixels),
     values under the 1e-32 cut-off, exactly 8 columns, a constant image."""
@@ -262,6 +278,13 @@ class OracleTree:
         self.lib.orc_render_ao(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
         return rgb, nrays.value
 
+    def render_ao_textured(self, frame: "FrameParams", rgba: np.ndarray):
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_ao_textured(self.h, C.byref(frame), _ptr(rgba), rgba.shape[1], rgba.shape[0], _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
     def render_sunsky(self, frame: "FrameParams", block: "SunskyBlock"):
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         nrays = C.c_uint64(0)
@@ -302,11 +325,20 @@ class Oracle:
         lib.orc_splitmix64.argtypes = [C.c_uint64]
         lib.orc_set_attributes.argtypes = [C.c_void_p] * 6
         lib.orc_state_ext_build_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_texture_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_render_ao_textured.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_hdr_encode.restype = C.c_uint64
         lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_sunsky.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib = lib
+
+    def texture_fetch(self, rgba: np.ndarray, uv: np.ndarray) -> np.ndarray:
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((len(uv), 4), dtype=np.float64)
+        self.lib.orc_texture_fetch(_ptr(rgba), rgba.shape[1], rgba.shape[0], _ptr(uv), C.c_uint64(len(uv)), _ptr(out))
+        return out
 
     def hdr_encode(self, rgb: np.ndarray) -> bytes:
         """The .hdr file the reference's display driver writes for this float framebuffer ([h][w][3], display order)."""
@@ -444,6 +476,7 @@ class Reference:
                                          C.c_void_p, C.c_void_p]
         lib.lref_sunsky_eval.restype = None
         lib.lref_hdr_file.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        lib.lref_texture_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         self.lib = lib
         self.stats = stats
 
@@ -455,6 +488,14 @@ class Reference:
         with _quiet():
             self.lib.lref_sunsky_eval(latitude, longitude, sm, jd, tod, turbidity, _ptr(dirs), C.c_uint64(len(dirs)), _ptr(rgb), _ptr(rec))
         return rgb, rec
+
+    def texture_fetch(self, rgba: np.ndarray, uv: np.ndarray) -> np.ndarray:
+        """ri_texture_fetch of the compiled reference on a caller-supplied float RGBA image."""
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((len(uv), 4), dtype=np.float64)
+        self.lib.lref_texture_fetch(_ptr(rgba), rgba.shape[1], rgba.shape[0], _ptr(uv), C.c_uint64(len(uv)), _ptr(out))
+        return out
 
     def hdr_file(self, rgb: np.ndarray, path: str) -> bytes:
         """hdr_dd_open / hdr_dd_write per pixel / hdr_dd_close of the compiled reference (display/hdrdrv.c): the file's bytes."""
@@ -512,7 +553,8 @@ def read_scene(path: str):
 
 
 def run_oracle_rib(rib: str, out: str, scene: str | None = None, nthreads: int = 1, width: int = 0, height: int = 0,
-                   pixelsamples: int = 0, gather: int = 0, timeout: int = 3600, sunsky: str | None = None):
+                   pixelsamples: int = 0, gather: int = 0, timeout: int = 3600, sunsky: str | None = None,
+                   texture: np.ndarray | None = None, attr: str | None = None):
     """Run the compiled reference renderer on a RIB in a subprocess (one frame per process)."""
     cmd = [ORACLE_RIB, rib, "--nthreads", str(nthreads), "--out", out]
     if scene:
@@ -525,6 +567,16 @@ def run_oracle_rib(rib: str, out: str, scene: str | None = None, nthreads: int =
         cmd += ["--gather", str(gather)]
     if sunsky:
         cmd += ["--sunsky", sunsky]
+    if texture is not None:
+        tex = np.ascontiguousarray(texture, dtype=np.float32)
+        tpath = out + ".tex"
+        with open(tpath, "wb") as f:
+            f.write(b"LTEX")
+            f.write(np.array([tex.shape[1], tex.shape[0]], dtype="<u4").tobytes())
+            f.write(tex.tobytes())
+        cmd += ["--texture", tpath]
+    if attr:
+        cmd += ["--attr", attr]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
     return read_frame(out)
 

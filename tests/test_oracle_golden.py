@@ -163,3 +163,15 @@ def test_hdr_output_golden(oracle, golden_dir):
     for name, rgb in frames.items():
         data = oracle.hdr_encode(rgb)
         assert len(data) == int(g[name + "_size"]) and hashlib.sha256(data).hexdigest() == str(g[name + "_sha256"]), name
+
+
+def test_textured_ao_frame_golden(oracle, golden_dir):
+    """Row a11, the material-texture clause (ambientocclusion.c:393-401): st lerp + ri_texture_fetch + per-channel multiply through the
+    pixel loop -- the reference's framebuffer of tests/scenes/textured_quads.rib, bit for bit (st spanning several periods, negative
+    st, a quad without texture coordinates)."""
+    g = np.load(os.path.join(golden_dir, "textured_quads.npz"))
+    t = oracle.build(g["tris"])
+    t.set_attributes(None, None, g["st"], g["has_st"], None)
+    rgb, nrays = t.render_ao_textured(ol.frame_params(g["cam"], 120, 90, gather=16), g["tex"])
+    assert nrays == int(g["nrays"]) and np.array_equal(rgb, g["rgb"])
+    assert (np.ptp(rgb, axis=2) > 1e-3).mean() > 0.2          # the texture coloured the image

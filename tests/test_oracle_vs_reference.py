@@ -120,3 +120,13 @@ def test_hit_state_colours_texcoords_inside(oracle, ref):
     # every class occurs: coloured and default colour, st and none, both sides
     assert (got["color"][m] != 1.0).any() and (got["color"][m] == 1.0).all(axis=1).any()
     assert (got["st"][m] != 0.0).any() and (got["st"][m] == 0.0).all(axis=1).any() and set(np.unique(got["inside"][m])) == {0, 1}
+
+
+def test_texture_fetch(oracle, ref):
+    """ri_texture_fetch (render/texture.c:86-236) on 50 000 coordinates incl. integers and values just below them."""
+    tex = ol.test_texture()
+    rng = np.random.default_rng(5)
+    uv = rng.uniform(-3, 4, (50000, 2))
+    uv[:100] = np.round(uv[:100])
+    uv[100:200, 0] = np.nextafter(np.round(uv[100:200, 0]), -np.inf)
+    assert np.array_equal(oracle.texture_fetch(tex, uv), ref.texture_fetch(tex, uv))
