@@ -219,6 +219,12 @@ int ri_b200_render_sunsky(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, 
                           ri_b200_frame_stats_t *stats);
 int ri_b200_render_sunsky_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, const ri_b200_sunsky_t *sky, float *d_packed,
                                     void *stream, ri_b200_frame_stats_t *stats);
+/* ---- dirt-map transport: ri_transport_dirtmap + calculate_dirt (transport/dirtmap.c:84-293), compiled into
+ * lucille but not wired into its pixel loop (render.c:800-804).  Same frame description; fixed 4 x 4 gather (frame->ntheta/nphi are
+ * ignored), origin offset 1e-5, CLOSEST hits: black within 0.1, white beyond 0.5 or on a miss, linear mix in between; times the
+ * material texture when one is set. */
+int ri_b200_render_dirtmap(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *rgb_out, ri_b200_frame_stats_t *stats);
+
 /* ri_sunsky_get_sky_rgb for a HOST batch of directions ([n][3] floats in, [n][3] floats out), computed on `device` */
 int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device);
 

@@ -138,6 +138,7 @@ ABI = [
     ("ri_b200_render_sunsky", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_sunsky_tiles_dev", _I, [_P, _P, _P, _P, _P, _P]),
     ("ri_b200_sunsky_rgb", _I, [_P, _P, _U64, _P, _I]),
+    ("ri_b200_render_dirtmap", _I, [_P, _P, _P, _P]),
     ("ri_b200_hdr_encode", C.c_int64, [_P, _I, _I, _P, _U64, _I, _I]),
     ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
@@ -388,6 +389,13 @@ class Accel:
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         stats = FrameStats()
         _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
+        return rgb, stats
+
+    def render_dirtmap(self, frame: Frame):
+        """One frame with the dirt-map transport (transport/dirtmap.c) -> (rgb [h,w,3] float32 on the host, FrameStats)."""
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_dirtmap(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
         return rgb, stats
 
     def render_sunsky(self, frame: Frame, sky: "Sunsky"):

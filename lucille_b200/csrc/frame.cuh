@@ -683,7 +683,7 @@ static int mt_stream_launch(ri_b200_accel *a, uint32_t seed, uint32_t segments, 
 
 template <typename Real>
 static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_rgb, cudaStream_t st, ri_b200_frame_stats_t *stats,
-                          Real *d_dump, uint64_t dump_count, int packed = 0, const ri_b200_sunsky_t *sky = nullptr)
+                          Real *d_dump, uint64_t dump_count, int packed = 0, const ri_b200_sunsky_t *sky = nullptr, const bool dirtmap = false)
 {
     std::vector<uint32_t> pix;
     std::vector<double> jit;
@@ -691,7 +691,8 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     jitter_table(f.xsamples, f.ysamples, jit);
     const uint64_t npix = pix.size();
     // the sun-sky transport gathers with a fixed 8 x 8 pattern whatever Option "gather" says (ambientocclusion.c:371-374)
-    const int ntheta = sky ? 8 : f.ntheta, nphi = sky ? 8 : f.nphi;
+    // ... and the dirt-map transport with a fixed 4 x 4 one (dirtmap.c:261-265)
+    const int ntheta = sky ? 8 : (dirtmap ? 4 : f.ntheta), nphi = sky ? 8 : (dirtmap ? 4 : f.nphi);
     const int spp = f.xsamples * f.ysamples, N = ntheta * nphi;
     const uint64_t nsamples = npix * (uint64_t)spp;
     if (nsamples >= 0xfffffff0ull) return fail("too many samples per rank for 32-bit sample ids");
@@ -703,7 +704,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     F.width = f.width; F.height = f.height; F.xsamples = f.xsamples; F.ysamples = f.ysamples;
     F.ntheta = ntheta; F.nphi = nphi; F.spp = spp; F.nao = N;
     F.rng_mode = f.rng_mode; F.seed = f.seed;
-    F.ao_eps = sky ? 1.0e-5 : 1.0e-6;
+    F.ao_eps = (sky || dirtmap) ? 1.0e-5 : 1.0e-6;                       // dirtmap.c:96
 
     const int cap = stack_capacity(a);
     const size_t smem = (size_t)cap * kBlock * sizeof(uint32_t);
@@ -714,6 +715,8 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
     const size_t sky_smem = smem + 3 * kBlock * sizeof(float);
     if (sky && sky_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(sunsky_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sky_smem));
+    const size_t dirt_smem = smem + kBlock * sizeof(double);
+    if (dirtmap && dirt_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(dirtmap_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dirt_smem));
 
     const uint32_t ntiles = (uint32_t)((nsamples + kScanTile - 1) / kScanTile);
     void *p = nullptr;
@@ -806,6 +809,15 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
             sunsky_kernel<Real><<<(unsigned)blocks, kBlock, sky_smem, st>>>(S, F, d_sky, nao_rays, d_rec, d_ranks, d_pix, d_mt, d_lo, (uint32_t)cap);
             LAUNCHED();
         }
+    } else if (dirtmap) {                         // dirt map: one lane per ray, closest hit, colour by distance, per-sample sums in order
+        if (frame_buf(a, 8, ((uint64_t)nhits + 1) * 3 * sizeof(double), &p)) return -1;
+        d_lo = (double *)p;
+        if (nao_rays) {
+            const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
+            if (blocks > 0x7fffffffull) return fail("too many gather rays in one frame pass");
+            dirtmap_kernel<Real><<<(unsigned)blocks, kBlock, dirt_smem, st>>>(S, F, nao_rays, d_rec, d_ranks, d_pix, d_mt, d_texcol, d_lo, (uint32_t)cap);
+            LAUNCHED();
+        }
     } else if (nao_rays && fused_ao) {                   // one lane per ray, generation fused with a one-ray-per-thread traversal
         const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
         if (blocks > 0x7fffffffull) return fail("too many occlusion rays in one frame pass");
@@ -829,7 +841,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
     CUDA_OK(cudaEventRecord(a->ev[4], st));
     if (npix) {
-        if (sky) resolve_rgb_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_lo, d_rgb, packed);
+        if (sky || dirtmap) resolve_rgb_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_lo, d_rgb, packed);
         else if (textured && d_texcol) resolve_tex_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_texcol, d_rgb, packed);
         else resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed);
         LAUNCHED();
@@ -951,6 +963,24 @@ extern "C" int ri_b200_render_sunsky_tiles_dev(ri_b200_accel_t *a, const ri_b200
     cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
     if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_packed, st, stats, nullptr, 0, 1, sky);
     return render_ao_impl<float>(a, *f, d_packed, st, stats, nullptr, 0, 1, sky);
+}
+
+extern "C" int ri_b200_render_dirtmap(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *rgb_out, ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!rgb_out) return fail("null framebuffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    const size_t bytes = (size_t)f->width * f->height * 3 * sizeof(float);
+    void *p = nullptr;
+    if (frame_buf(a, 6, bytes, &p)) return -1;
+    int rc;
+    if (f->precision == RI_B200_PREC_F64) rc = render_ao_impl<double>(a, *f, (float *)p, a->stream, stats, nullptr, 0, 0, nullptr, true);
+    else rc = render_ao_impl<float>(a, *f, (float *)p, a->stream, stats, nullptr, 0, 0, nullptr, true);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(rgb_out, p, bytes, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_OK(cudaStreamSynchronize(a->stream));
+    return 0;
 }
 
 extern "C" int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device)

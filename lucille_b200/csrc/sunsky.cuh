@@ -160,6 +160,59 @@ sunsky_kernel(const SceneView<Real> S, const FrameDev F, const ri_b200_sunsky_t 
     }
 }
 
+// ---- dirt-map transport (transport/dirtmap.c:84-221 calculate_dirt(4, 4), 223-293 ri_transport_dirtmap) ----
+// One lane per gather ray (4 x 4 per hit sample, sixteen samples per CTA): CLOSEST hit, colour by distance -- black within
+// near_clip 0.1, white beyond far_clip 0.5 or on a miss, mix_color in between (white * (1-p) - black * p, p = clamp(1 - (t-0.1)/0.4);
+// the reference raises it to the power 1.0f / dirt_gain = 1, which is the identity).  The first lane of each sample adds the 16
+// values in loop order and writes Lo = sum / 16 on three channels, times the material-texture colour when there is one
+// (dirtmap.c:272-281).
+template <typename Real>
+__global__ void __launch_bounds__(kBlock)
+dirtmap_kernel(const SceneView<Real> S, const FrameDev F, const uint64_t nrays, const Real *__restrict__ records,
+               const uint32_t *__restrict__ rank_sample, const uint32_t *__restrict__ pixels, const uint32_t *__restrict__ mt_stream,
+               const double *__restrict__ texcol, double *__restrict__ lo_out, const uint32_t stack_cap)
+{
+    extern __shared__ uint32_t s_stack[];
+    double *s_col = reinterpret_cast<double *>(s_stack + (size_t)stack_cap * kBlock);     // [kBlock]
+    const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t N = 16u;
+    const uint32_t rank = (uint32_t)(gid / N), k = (uint32_t)(gid % N);
+    const bool active = gid < nrays;
+    double c = 0.0;
+    if (active) {
+        const Real *rec = records + 12 * (uint64_t)rank;
+        Real org[3] = {rec[0], rec[1], rec[2]}, dir[3], t, u, v;
+        uint32_t prim;
+        ao_direction<Real>(F, rank, k, rec, rank_sample, pixels, mt_stream, dir);
+        const double near_clip = 0.1, far_clip = 0.5, dirt_color = 0.0, base_color = 1.0;
+        if (trace_ray<Real, false, false>(S, org, dir, s_stack + threadIdx.x, kBlock, t, u, v, prim, nullptr)) {
+            const double td = (double)t;
+            if (td <= near_clip) c = dirt_color;
+            else if (td >= far_clip) c = base_color;
+            else {
+                double p = 1.0 - ((td - near_clip) / (far_clip - near_clip));
+                if (p < 0.0) p = 0.0;
+                if (p > 1.0) p = 1.0;
+                c = (1.0 - p) * base_color - p * dirt_color;
+            }
+        } else {
+            c = base_color;
+        }
+    }
+    s_col[threadIdx.x] = c;
+    __syncthreads();
+    if (active && k == 0) {
+        double sum = 0.0;
+        for (uint32_t q = 0; q < N; ++q) sum = sum + s_col[threadIdx.x + q];
+        const double lo = sum / (double)N;
+        for (int q = 0; q < 3; ++q) {
+            double r = lo;
+            if (texcol) r *= texcol[3 * (uint64_t)rank + q];
+            lo_out[3 * (uint64_t)rank + q] = r;
+        }
+    }
+}
+
 // render.c:805,820 + bucket_write: three-channel box average of the sub-sample radiances, float RGB at row H-1-y
 __global__ void resolve_rgb_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
                                    const uint32_t *__restrict__ sample_rank, const double *__restrict__ lo, float *__restrict__ rgb, const int packed)

@@ -859,6 +859,121 @@ void orc_render_ao_textured(const orc_tree *T, const orc_frame_t *f, const float
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ dirt-map transport */
+
+/* dirtmap.c:84-221 calculate_dirt(4, 4) */
+static double dirt_radiance(const orc_tree *T, const view_t_f64 *V, const orc_state_f64 *s, mt_t *rng, uint64_t *nrays)
+{
+    const uint32_t ntheta = 4, nphi = 4;
+    const double eps = 1.0e-5, dirt_gain = 1.0f, near_clip = 0.1, far_clip = 0.5;
+    const double dirt_color = 0.0, base_color = 1.0;           /* black / white on all three channels */
+    double basis[3][3], org[3], dirl[3], dir[3], sum_color = 0.0, nsamples;
+    uint32_t i, j; int k;
+
+    ortho_basis_f64(basis, s->Ns);
+    for (k = 0; k < 3; k++) org[k] = s->P[k];
+    for (k = 0; k < 3; k++) org[k] += s->Ns[k] * eps;
+    for (j = 0; j < nphi; j++) {
+        for (i = 0; i < ntheta; i++) {
+            double z0 = (i + mt_next(rng)) / (double)ntheta;
+            double z1 = (j + mt_next(rng)) / (double)nphi;
+            double cos_theta = sqrt(z0);
+            double phi = 2.0 * M_PI * z1;
+            double t, u, v; uint32_t prim;
+            dirl[0] = cos(phi) * cos_theta;
+            dirl[1] = sin(phi) * cos_theta;
+            dirl[2] = sqrt(1.0 - cos_theta * cos_theta);
+            for (k = 0; k < 3; k++)
+                dir[k] = dirl[0] * basis[0][k] + dirl[1] * basis[1][k] + dirl[2] * basis[2][k];
+            (*nrays)++;
+            if (trace_f64(T, V, org, dir, 0, &t, &u, &v, &prim, NULL)) {
+                if (t <= near_clip) {
+                    sum_color = sum_color + dirt_color;
+                } else if (t >= far_clip) {
+                    sum_color = sum_color + base_color;
+                } else {                                       /* mix_color, dirtmap.c:70-82 */
+                    double p = pow(1.0 - ((t - near_clip) / (far_clip - near_clip)), 1.0f / dirt_gain);
+                    double col;
+                    if (p < 0.0) p = 0.0;
+                    if (p > 1.0) p = 1.0;
+                    col = (1.0 - p) * base_color - p * dirt_color;
+                    sum_color = sum_color + col;
+                }
+            } else {
+                sum_color = sum_color + base_color;
+            }
+        }
+    }
+    nsamples = ntheta * nphi;
+    return sum_color / nsamples;
+}
+
+void orc_transport_batch(const orc_tree *T, int which, int ntheta, int nphi, const double *rays, uint64_t n, double *radiance3)
+{
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t i, nrays = 0;
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, 4357);
+    for (i = 0; i < n; i++) {
+        const double *r = rays + 6 * i;
+        double org[3] = { r[0], r[1], r[2] }, dir[3] = { r[3], r[4], r[5] }, t, uu, vv, rad = 0.0;
+        uint32_t prim;
+        if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+            orc_state_f64 st;
+            state_build_uv(T, org, dir, t, uu, vv, prim, &st);
+            rad = which == 1 ? dirt_radiance(T, &V, &st, &rng, &nrays) : ao_radiance(T, &V, &st, ntheta, nphi, &rng, &nrays);
+        }
+        radiance3[3 * i] = radiance3[3 * i + 1] = radiance3[3 * i + 2] = rad;
+    }
+}
+
+void orc_render_dirtmap(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t *nrays_out)
+{
+    int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(f->width, f->height, f->bucket_size, buckets, nb_max);
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t nrays = 0;
+    int b;
+
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, 4357);
+    for (b = 0; b < nb; b++) {
+        int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        int u, v;
+        for (v = by; v < by + bh; v++) {
+            for (u = bx; u < bx + bw; u++) {
+                double accum = 0.0, px;
+                int xs, ys;
+                for (ys = 0; ys < f->ysamples; ys++) {
+                    for (xs = 0; xs < f->xsamples; xs++) {
+                        double jx, jy, org[3], dir[3], t, uu, vv, rad = 0.0;
+                        uint32_t prim;
+                        orc_subpixel_jitter(xs, ys, f->xsamples, f->ysamples, &jx, &jy);
+                        orc_camera_ray(f, (double)(u + jx), (double)(v + jy), org, dir);
+                        nrays++;
+                        if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+                            orc_state_f64 st;
+                            state_build_uv(T, org, dir, t, uu, vv, prim, &st);
+                            rad = dirt_radiance(T, &V, &st, &rng, &nrays);
+                        }
+                        accum = accum + rad;
+                    }
+                }
+                px = accum * ((double)1.0 / (f->xsamples * f->ysamples));
+                {
+                    float *dst = rgb + 3 * ((size_t)(f->height - v - 1) * f->width + u);
+                    dst[0] = dst[1] = dst[2] = (float)px;
+                }
+            }
+        }
+    }
+    free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
 /* ------------------------------------------------------------------ sun-sky gather (row a12) */
 
 /* sunsky.c:24-38.  All variables are float, the libm calls are the double ones: every `sin(x)` promotes its float argument

@@ -162,6 +162,15 @@ void orc_texture_fetch(const float *rgba, int width, int height, const double *u
 void orc_render_ao_textured(const orc_tree *t, const orc_frame_t *f, const float *rgba, int tex_width, int tex_height,
                             float *rgb, uint64_t *nrays_out);
 
+/* ---- dirt-map transport (transport/dirtmap.c:84-221 calculate_dirt, 223-293 ri_transport_dirtmap): the AO
+ * hemisphere loop with a fixed 4 x 4 pattern, origin offset 1e-5 and CLOSEST hits: a gather ray adds black when it hits within 0.1,
+ * white beyond 0.5 or on a miss, and (1-p) white - p black with p = clamp(pow(1 - (t-0.1)/0.4, 1)) in between (mix_color, :70-82);
+ * Lo = sum / 16 on three channels.  orc_transport_batch: one radiance per eye ray ([n][6] org,dir), the thread's MT19937 stream
+ * re-seeded with 4357 and consumed ray after ray (which: 0 ambient occlusion with ntheta x nphi, 1 dirt map).
+ * orc_render_dirtmap: the pixel loop of orc_render_ao around the same transport. */
+void orc_transport_batch(const orc_tree *t, int which, int ntheta, int nphi, const double *rays, uint64_t n, double *radiance3);
+void orc_render_dirtmap(const orc_tree *t, const orc_frame_t *f, float *rgb, uint64_t *nrays_out);
+
 /* ---- sun-sky gather (row a12): ambientocclusion.c:153-324 gather_sunsky + contribution_from_sunlight, with the sky lookup
  * ri_sunsky_get_sky_rgb (render/sunsky.c:24-38 angle_between, 136-152 PerezFunction, 297-408; render/specrend.c:127-172
  * xyz_to_rgb, 366-440 spectrum_to_xyz).  The block is what the host side owns after ri_sunsky_init(): Perez coefficients,

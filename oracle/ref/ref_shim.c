@@ -381,6 +381,37 @@ void lref_intersect_ext(void *h, const double *rays, uint64_t n, lref_ext_t *out
     }
 }
 
+/* ---- the other transports: compiled into the reference but never called by its pixel loop (render.c:800-804).
+ * Called here per eye ray exactly as subsample() would call them: render = ri_render_get() with this scene installed, thread 0,
+ * the thread's MT19937 stream re-seeded with 4357 (random.c:98-112) before the batch.  which: 0 ambient occlusion, 1 dirt map. */
+#include "transport.h"
+extern int ri_transport_dirtmap(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
+extern int ri_transport_ambientocclusion(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
+extern void seedMT2();
+void lref_transport_batch(void *h, int which, const double *rays, uint64_t n, double *radiance3)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_render_t *render = ri_render_get();
+    ri_scene_t *saved = render->scene;
+    ri_ray_t ray;
+    ri_transport_info_t result;
+    uint64_t i;
+    render->scene = s->scene;
+    seedMT2((unsigned long)4357, 0);
+    memset(&ray, 0, sizeof(ray));
+    for (i = 0; i < n; i++) {
+        const double *r = rays + 6 * i;
+        ray.org[0] = r[0]; ray.org[1] = r[1]; ray.org[2] = r[2]; ray.org[3] = 1.0;
+        ray.dir[0] = r[3]; ray.dir[1] = r[4]; ray.dir[2] = r[5]; ray.dir[3] = 0.0;
+        ray.thread_num = 0;
+        memset(&result, 0, sizeof(result));
+        if (which == 1) ri_transport_dirtmap(render, &ray, &result);
+        else ri_transport_ambientocclusion(render, &ray, &result);
+        radiance3[3 * i] = result.radiance[0]; radiance3[3 * i + 1] = result.radiance[1]; radiance3[3 * i + 2] = result.radiance[2];
+    }
+    render->scene = saved;
+}
+
 /* reference traversal counters (only meaningful in libluciref_stat.so; bvh.c:146,686-688) */
 extern ri_bvh_stat_traversal_t g_stattrav;
 void lref_stats_reset(void) { memset(&g_stattrav, 0, sizeof(g_stattrav)); }

@@ -278,6 +278,19 @@ class OracleTree:
         self.lib.orc_render_ao(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
         return rgb, nrays.value
 
+    def transport_batch(self, which: int, rays6: np.ndarray, ntheta: int = 8, nphi: int = 8) -> np.ndarray:
+        """Radiance per eye ray of a transport (0 ambient occlusion, 1 dirt map), MT19937 stream seeded 4357 and consumed in ray order."""
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros((len(rays6), 3), dtype=np.float64)
+        self.lib.orc_transport_batch(self.h, which, ntheta, nphi, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out))
+        return out
+
+    def render_dirtmap(self, frame: "FrameParams"):
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_dirtmap(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
     def render_ao_textured(self, frame: "FrameParams", rgba: np.ndarray):
         rgba = np.ascontiguousarray(rgba, dtype=np.float32)
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
@@ -327,6 +340,8 @@ class Oracle:
         lib.orc_state_ext_build_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_texture_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_ao_textured.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.orc_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_hdr_encode.restype = C.c_uint64
         lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -429,6 +444,14 @@ class ReferenceScene:
                                       _ptr(out) if want_hits else None)
         return out, sec
 
+    def transport_batch(self, which: int, rays6: np.ndarray) -> np.ndarray:
+        """ri_transport_ambientocclusion (0) / ri_transport_dirtmap (1) of the compiled reference, one call per eye ray."""
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros((len(rays6), 3), dtype=np.float64)
+        with _quiet():
+            self.lib.lref_transport_batch(self.h, which, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out))
+        return out
+
     def set_attributes(self, colors, st, geom_flags):
         """colors [n,3,3], st [n,3,2] (either may be None); geom_flags per geom: 1 Cs, 2 shared st, 4 unshared st, 8 two-sided."""
         c = None if colors is None else np.ascontiguousarray(colors, dtype=np.float64)
@@ -470,6 +493,7 @@ class Reference:
         lib.lref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.lref_stats_get.argtypes = [C.c_void_p]
         lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_scene_set_attr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_intersect_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,

@@ -492,3 +492,25 @@ def test_textured_ao_frame(golden_dir, prec):
     a.set_texture(None)                                   # without the texture the frame is grey again
     grey, _ = a.render_ao(fr)
     assert np.array_equal(grey[..., 0], grey[..., 1]) and np.array_equal(grey[..., 1], grey[..., 2])
+
+
+def test_dirtmap_frame(oracle):
+    """SURVEY 8f rank 2, dirt-map transport: device frame against the oracle's (whose transport tests/test_oracle_vs_reference.py pins
+    to the compiled ri_transport_dirtmap ray by ray, and whose pixel loop the AO frames pin): fp64 records, identical image and ray
+    count.  Soup scaled by 3 so that gather distances fall on both sides of the 0.1 / 0.5 window."""
+    _need_gpu()
+    import math
+    tris = scenes.triangle_soup(3000, 9) * 3.0
+    c2w = np.eye(4)
+    c2w[3, :3] = (1.5, 1.5, -6.0)
+    flen = 1.0 / math.tan(math.radians(40.0) / 2)
+    a = accel.Accel.bind().build(tris, accel.PREC_F64)
+    fr = accel.make_frame(c2w.reshape(16), flen, False, 96, 72, 2, 2, gather_nsamples=64, precision=accel.PREC_F64)
+    rgb, stats = a.render_dirtmap(fr)
+    cam = np.zeros(27)
+    cam[:16] = c2w.reshape(16)
+    cam[16], cam[17], cam[20], cam[21], cam[22], cam[23] = flen, 0, 2, 2, 64, 32
+    want, nrays = oracle.build(tris).render_dirtmap(ol.frame_params(cam, 96, 72))
+    assert stats.nrays == nrays
+    assert np.array_equal(rgb, want)
+    assert np.unique(rgb).size > 50 and rgb.max() <= 1.0

@@ -130,3 +130,19 @@ def test_texture_fetch(oracle, ref):
     uv[:100] = np.round(uv[:100])
     uv[100:200, 0] = np.nextafter(np.round(uv[100:200, 0]), -np.inf)
     assert np.array_equal(oracle.texture_fetch(tex, uv), ref.texture_fetch(tex, uv))
+
+
+def test_transports_called_directly(oracle, ref):
+    """ri_transport_dirtmap (compiled into the reference, never called by its pixel loop) and, for symmetry,
+    ri_transport_ambientocclusion, called per eye ray with the thread's MT19937 stream re-seeded: the restatement returns the same
+    radiance bit for bit.  The soup is scaled by 3 so that the dirt map's 0.1 / 0.5 distance window is exercised on both sides."""
+    tris = scenes.triangle_soup(3000, 9) * 3.0
+    rs, ot = ref.build(tris), oracle.build(tris)
+    rng = np.random.default_rng(2)
+    org = rng.uniform(-1, 4, (3000, 3))
+    rays6 = np.concatenate([org, rng.uniform(0, 3, (3000, 3)) - org], axis=1)
+    for which in (1, 0):
+        want, got = rs.transport_batch(which, rays6), ot.transport_batch(which, rays6)
+        assert np.array_equal(got, want) and (want[:, 0] > 0).sum() > 1000
+    dirt = ot.transport_batch(1, rays6)[:, 0]
+    assert np.unique(np.round(dirt * 16, 6)).size > 100          # distances inside the window: more than the 17 AO levels
