@@ -23,14 +23,20 @@ for r in rows:
 tot = sum(sum(v) for v in d.values())
 with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
     f.write(f"# {tag}: kernel launch list of `bench.py --steps 3 --warmup 3 --no-cpu-baseline`\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 80` (cold-cache, serialised: compare shares, not absolutes).\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 600` (cold-cache, serialised: compare shares, not absolutes).\n"
             "Setup launches (primary rays, statistics counters) and the chunked end-to-end launches are part of the list.\n\n"
             "| kernel | grid | block | launches | avg ms | share of listed GPU time |\n|---|---|---|---:|---:|---:|\n")
     for (k, grid, block), v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"| `{k}` | {grid} | {block} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {sum(v) / tot * 100:.1f} % |\n")
-    f.write("\n`occluded_pool_kernel<float, 4>` = pooled occlusion (any-hit) traverser, the timed kernel: grid 592 = 4 CTAs x 148 SMs; every\n"
-            "launch traces the whole 16 Mi-ray batch (warm-up, timed steps, and the streamed host-buffer (e2e) calls, which are ONE launch each).\n"
-            "`trace_persistent_kernel<float, 0>` = closest-hit traverser (reported as closest_hit_mrays_s, and the primary rays of the set-up).\n"
+    f.write("\nThe timed region of bench.py is `steps` launches of `occluded_pool_kernel<float, 4>` and nothing else (one launch = one step = the\n"
+            "whole 16 Mi-ray batch; `gpu_launches` = steps), so the kernel's share of a step is 100 %; everything else in this list is set-up\n"
+            "(tree build, primary rays, statistics counters), the closest-hit side measurement and the end-to-end calls.\n"
+            "\n`occluded_pool_kernel<float, 4>` = pooled occlusion (any-hit) traverser, the timed kernel: grid 592 = 4 CTAs x 148 SMs; every\n"
+            "16 Mi-ray launches are the warm-up and timed steps; the 2 Mi-ray (and ramp-up) ones are the host-buffer (e2e) calls in their\n"
+            "launch-per-piece form -- this pass runs with B200_STREAMED=0 because ncu serialises the copy stream behind the kernel; outside\n"
+            "the profiler an e2e call is ONE streamed launch.\n"
+            "`closest_pool_kernel` = pooled closest-hit traverser (reported as closest_hit_mrays_s, and the primary rays of the set-up).\n"
+            "`gb_*` = the device BVH builder (set-up, untimed: ~10 launches per tree level, 19 levels) and `gb_fill_slots`.\n"
             "`trace_batch_kernel<..., 1>` = one-ray-per-thread kernel with the reference's traversal counters (I, T of the roofline formula), run once, untimed.\n")
 
 # ---- full capture of the timed kernel ---------------------------------------------------------------------------------
