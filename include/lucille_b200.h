@@ -225,6 +225,13 @@ int ri_b200_render_sunsky_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
  * material texture when one is set. */
 int ri_b200_render_dirtmap(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *rgb_out, ri_b200_frame_stats_t *stats);
 
+/* ---- Whitted transport: ri_transport_whitted + trace_whitted (transport/whitted.c:31-151): chains of refracted
+ * rays (eta 1.33, at most 8 bounces) from every eye hit, radiance = the angular-map environment along the direction that leaves the
+ * scene (ri_texture_ibl_fetch, render/texture.c:238-277), zero when the chain is cut.  env_rgba: HOST [h][w][4] floats =
+ * scene->envmap_light->texture->data, or NULL (no environment).  fp64 records; whole frames (world == 1). */
+int ri_b200_render_whitted(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, const float *env_rgba, int env_width, int env_height,
+                           float *rgb_out, ri_b200_frame_stats_t *stats);
+
 /* ri_sunsky_get_sky_rgb for a HOST batch of directions ([n][3] floats in, [n][3] floats out), computed on `device` */
 int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device);
 

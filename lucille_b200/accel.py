@@ -139,6 +139,7 @@ ABI = [
     ("ri_b200_render_sunsky_tiles_dev", _I, [_P, _P, _P, _P, _P, _P]),
     ("ri_b200_sunsky_rgb", _I, [_P, _P, _U64, _P, _I]),
     ("ri_b200_render_dirtmap", _I, [_P, _P, _P, _P]),
+    ("ri_b200_render_whitted", _I, [_P, _P, _P, _I, _I, _P, _P]),
     ("ri_b200_hdr_encode", C.c_int64, [_P, _I, _I, _P, _U64, _I, _I]),
     ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
@@ -389,6 +390,16 @@ class Accel:
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         stats = FrameStats()
         _check(self.lib.ri_b200_render_ao(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
+        return rgb, stats
+
+    def render_whitted(self, frame: Frame, env=None):
+        """One frame with the Whitted refraction tracer (transport/whitted.c) and the angular-map environment ``env`` ([h,w,4] float32
+        or None) -> (rgb [h,w,3] float32 on the host, FrameStats)."""
+        env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_whitted(self._h(), C.byref(frame), _ptr(env), 0 if env is None else env.shape[1],
+                                               0 if env is None else env.shape[0], _ptr(rgb), C.byref(stats)))
         return rgb, stats
 
     def render_dirtmap(self, frame: Frame):

@@ -974,6 +974,132 @@ void orc_render_dirtmap(const orc_tree *T, const orc_frame_t *f, float *rgb, uin
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ Whitted transport */
+
+/* reflection.c:25-49: the dot product is stored in a float */
+static void reflect_f64(double out[3], const double in[3], const double n[3])
+{
+    float dot = in[0] * n[0] + in[1] * n[1] + in[2] * n[2];
+    int k;
+    for (k = 0; k < 3; k++) { const double nd = n[k] * (2 * dot); out[k] = in[k] - nd; }
+}
+
+/* reflection.c:69-127 */
+static void refract_f64(double out[3], const double in[3], const double n[3], double eta)
+{
+    double cos1, coeff, N[3], e = 1.0 / eta;
+    cos1 = in[0] * n[0] + in[1] * n[1] + in[2] * n[2];
+    if (cos1 < 0.0) {
+        cos1 = -cos1;
+        N[0] = n[0]; N[1] = n[1]; N[2] = n[2];
+    } else {
+        e = eta;
+        N[0] = -(n[0]); N[1] = -(n[1]); N[2] = -(n[2]);
+    }
+    coeff = 1.0 - (e * e) * (1.0 - cos1 * cos1);
+    if (coeff <= 0.0) {                                       /* total internal reflection */
+        reflect_f64(out, in, n);
+        normalize_f64(out);
+        return;
+    }
+    coeff = e * cos1 - sqrt(coeff);
+    out[0] = coeff * N[0] + e * in[0];
+    out[1] = coeff * N[1] + e * in[1];
+    out[2] = coeff * N[2] + e * in[2];
+    normalize_f64(out);
+}
+
+/* texture.c:238-277 */
+static void ibl_fetch(const float *env, int w, int h, const double dir[3], double out[4])
+{
+    const double pi = 3.1415926535;
+    double u, v, r, norm2, ndir[3] = { dir[0], dir[1], dir[2] };
+    normalize_f64(ndir);
+    if (ndir[2] >= -1.0 && ndir[2] < 1.0) r = (1.0 / pi) * acos(ndir[2]);
+    else r = 0.0;
+    norm2 = ndir[0] * ndir[0] + ndir[1] * ndir[1];
+    if (norm2 > 1.0e-6) r /= sqrt(norm2);
+    u = ndir[0] * r;
+    v = ndir[1] * r;
+    u = 0.5 * u + 0.5;
+    v = 0.5 - 0.5 * v;
+    tex_fetch(env, w, h, u, v, out);
+}
+
+/* whitted.c:92-151 with trace_whitted (:31-83) unrolled into a loop: the recursion only passes the newest hit down */
+static void whitted_radiance(const orc_tree *T, const view_t_f64 *V, const float *env, int ew, int eh, const double eye_org[3],
+                             const double eye_dir[3], double rad[3], uint64_t *nrays)
+{
+    const double eps = 1.0e-7, eta = 1.33;
+    double org[3] = { eye_org[0], eye_org[1], eye_org[2] }, dir[3] = { eye_dir[0], eye_dir[1], eye_dir[2] };
+    double t, uu, vv, texel[4];
+    uint32_t prim;
+    int depth, k;
+    rad[0] = rad[1] = rad[2] = 0.0;
+    (*nrays)++;
+    if (!trace_f64(T, V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+        if (env) { ibl_fetch(env, ew, eh, dir, texel); for (k = 0; k < 3; k++) rad[k] = texel[k]; }
+        return;
+    }
+    for (depth = 1; depth <= 8; depth++) {                    /* MAX_TRACE_DEPTH 8, whitted.c:24,48 */
+        orc_state_f64 st;
+        double I[3] = { dir[0], dir[1], dir[2] }, Rd[3];
+        state_build_uv(T, org, dir, t, uu, vv, prim, &st);
+        normalize_f64(I);                                     /* intersection_state.c:130-131 */
+        refract_f64(Rd, I, st.Ns, eta);
+        for (k = 0; k < 3; k++) { org[k] = st.P[k] + eps * Rd[k]; dir[k] = Rd[k]; }
+        (*nrays)++;
+        if (!trace_f64(T, V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
+            if (env) { ibl_fetch(env, ew, eh, Rd, texel); for (k = 0; k < 3; k++) rad[k] = texel[k]; }
+            return;
+        }
+    }
+}
+
+void orc_transport_whitted(const orc_tree *T, const float *env, int ew, int eh, const double *rays, uint64_t n, double *radiance3,
+                           uint64_t *nrays_out)
+{
+    view_t_f64 V = {0};
+    uint64_t i, nrays = 0;
+    if (!T->empty) view64(T, &V);
+    for (i = 0; i < n; i++) whitted_radiance(T, &V, env, ew, eh, rays + 6 * i, rays + 6 * i + 3, radiance3 + 3 * i, &nrays);
+    if (nrays_out) *nrays_out = nrays;
+}
+
+void orc_render_whitted(const orc_tree *T, const orc_frame_t *f, const float *env, int ew, int eh, float *rgb, uint64_t *nrays_out)
+{
+    int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(f->width, f->height, f->bucket_size, buckets, nb_max);
+    view_t_f64 V = {0};
+    uint64_t nrays = 0;
+    int b, k;
+    if (!T->empty) view64(T, &V);
+    for (b = 0; b < nb; b++) {
+        int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        int u, v;
+        for (v = by; v < by + bh; v++) {
+            for (u = bx; u < bx + bw; u++) {
+                double accum[3] = {0.0, 0.0, 0.0};
+                int xs, ys;
+                float *dst = rgb + 3 * ((size_t)(f->height - v - 1) * f->width + u);
+                for (ys = 0; ys < f->ysamples; ys++) {
+                    for (xs = 0; xs < f->xsamples; xs++) {
+                        double jx, jy, org[3], dir[3], rad[3];
+                        orc_subpixel_jitter(xs, ys, f->xsamples, f->ysamples, &jx, &jy);
+                        orc_camera_ray(f, (double)(u + jx), (double)(v + jy), org, dir);
+                        whitted_radiance(T, &V, env, ew, eh, org, dir, rad, &nrays);
+                        for (k = 0; k < 3; k++) accum[k] = accum[k] + rad[k];
+                    }
+                }
+                for (k = 0; k < 3; k++) dst[k] = (float)(accum[k] * ((double)1.0 / (f->xsamples * f->ysamples)));
+            }
+        }
+    }
+    free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
 /* ------------------------------------------------------------------ sun-sky gather (row a12) */
 
 /* sunsky.c:24-38.  All variables are float, the libm calls are the double ones: every `sin(x)` promotes its float argument

@@ -171,6 +171,15 @@ void orc_render_ao_textured(const orc_tree *t, const orc_frame_t *f, const float
 void orc_transport_batch(const orc_tree *t, int which, int ntheta, int nphi, const double *rays, uint64_t n, double *radiance3);
 void orc_render_dirtmap(const orc_tree *t, const orc_frame_t *f, float *rgb, uint64_t *nrays_out);
 
+/* ---- Whitted transport (transport/whitted.c:31-83 trace_whitted, 92-151 ri_transport_whitted): from the eye hit
+ * a chain of REFRACTED rays (ri_refract with eta 1.33, render/reflection.c:69-127; total internal reflection falls back to ri_reflect,
+ * :25-49, whose dot product is a float), origin P + 1e-7 Rd, at most 8 bounces; the radiance is the environment map looked up along
+ * the direction that leaves the scene (ri_texture_ibl_fetch, render/texture.c:238-277, angular map) and zero when the chain is cut.
+ * env: [h][w][4] floats or NULL (no environment: radiance 0).  One radiance per eye ray; nrays counts ri_raytrace calls. */
+void orc_transport_whitted(const orc_tree *t, const float *env, int env_w, int env_h, const double *rays, uint64_t n, double *radiance3,
+                           uint64_t *nrays_out);
+void orc_render_whitted(const orc_tree *t, const orc_frame_t *f, const float *env, int env_w, int env_h, float *rgb, uint64_t *nrays_out);
+
 /* ---- sun-sky gather (row a12): ambientocclusion.c:153-324 gather_sunsky + contribution_from_sunlight, with the sky lookup
  * ri_sunsky_get_sky_rgb (render/sunsky.c:24-38 angle_between, 136-152 PerezFunction, 297-408; render/specrend.c:127-172
  * xyz_to_rgb, 366-440 spectrum_to_xyz).  The block is what the host side owns after ri_sunsky_init(): Perez coefficients,

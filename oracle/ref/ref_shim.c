@@ -383,11 +383,24 @@ void lref_intersect_ext(void *h, const double *rays, uint64_t n, lref_ext_t *out
 
 /* ---- the other transports: compiled into the reference but never called by its pixel loop (render.c:800-804).
  * Called here per eye ray exactly as subsample() would call them: render = ri_render_get() with this scene installed, thread 0,
- * the thread's MT19937 stream re-seeded with 4357 (random.c:98-112) before the batch.  which: 0 ambient occlusion, 1 dirt map. */
+ * the thread's MT19937 stream re-seeded with 4357 (random.c:98-112) before the batch.  which: 0 ambient occlusion, 1 dirt map, 2 Whitted refraction tracer. */
 #include "transport.h"
 extern int ri_transport_dirtmap(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
 extern int ri_transport_ambientocclusion(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
 extern void seedMT2();
+extern int ri_transport_whitted(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
+/* environment map of the scene (scene->envmap_light->texture, read by whitted.c:72-77,135-140 through ri_texture_ibl_fetch) */
+void lref_set_envmap(void *h, const float *rgba, int width, int height)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_light_t *l = ri_light_new();
+    ri_texture_t *t = (ri_texture_t *)calloc(1, sizeof(ri_texture_t));
+    t->data = (float *)malloc(sizeof(float) * 4 * (size_t)width * height);
+    memcpy(t->data, rgba, sizeof(float) * 4 * (size_t)width * height);
+    t->width = width; t->height = height;
+    l->texture = t;
+    s->scene->envmap_light = l;
+}
 void lref_transport_batch(void *h, int which, const double *rays, uint64_t n, double *radiance3)
 {
     lref_scene_t *s = (lref_scene_t *)h;
@@ -405,7 +418,8 @@ void lref_transport_batch(void *h, int which, const double *rays, uint64_t n, do
         ray.dir[0] = r[3]; ray.dir[1] = r[4]; ray.dir[2] = r[5]; ray.dir[3] = 0.0;
         ray.thread_num = 0;
         memset(&result, 0, sizeof(result));
-        if (which == 1) ri_transport_dirtmap(render, &ray, &result);
+        if (which == 2) ri_transport_whitted(render, &ray, &result);
+        else if (which == 1) ri_transport_dirtmap(render, &ray, &result);
         else ri_transport_ambientocclusion(render, &ray, &result);
         radiance3[3 * i] = result.radiance[0]; radiance3[3 * i + 1] = result.radiance[1]; radiance3[3 * i + 2] = result.radiance[2];
     }

@@ -285,6 +285,24 @@ class OracleTree:
         self.lib.orc_transport_batch(self.h, which, ntheta, nphi, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out))
         return out
 
+    def transport_whitted(self, rays6: np.ndarray, env):
+        """Radiance per eye ray of the Whitted refraction tracer with the angular-map environment ``env`` ([h,w,4] float32 or None)."""
+        rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
+        env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        out = np.zeros((len(rays6), 3), dtype=np.float64)
+        nrays = C.c_uint64(0)
+        self.lib.orc_transport_whitted(self.h, None if env is None else _ptr(env), 0 if env is None else env.shape[1],
+                                       0 if env is None else env.shape[0], _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out), C.byref(nrays))
+        return out, nrays.value
+
+    def render_whitted(self, frame: "FrameParams", env):
+        env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_whitted(self.h, C.byref(frame), None if env is None else _ptr(env), 0 if env is None else env.shape[1],
+                                    0 if env is None else env.shape[0], _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
     def render_dirtmap(self, frame: "FrameParams"):
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         nrays = C.c_uint64(0)
@@ -342,6 +360,8 @@ class Oracle:
         lib.orc_render_ao_textured.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_hdr_encode.restype = C.c_uint64
         lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -444,8 +464,14 @@ class ReferenceScene:
                                       _ptr(out) if want_hits else None)
         return out, sec
 
+    def set_envmap(self, rgba: np.ndarray):
+        """scene->envmap_light with this angular-map texture ([h,w,4] float32)."""
+        rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+        self.lib.lref_set_envmap(self.h, _ptr(rgba), rgba.shape[1], rgba.shape[0])
+
     def transport_batch(self, which: int, rays6: np.ndarray) -> np.ndarray:
-        """ri_transport_ambientocclusion (0) / ri_transport_dirtmap (1) of the compiled reference, one call per eye ray."""
+        """ri_transport_ambientocclusion (0) / ri_transport_dirtmap (1) / ri_transport_whitted (2) of the compiled reference, one call
+        per eye ray."""
         rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
         out = np.zeros((len(rays6), 3), dtype=np.float64)
         with _quiet():
@@ -493,6 +519,7 @@ class Reference:
         lib.lref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         lib.lref_stats_get.argtypes = [C.c_void_p]
         lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lref_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.lref_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_scene_set_attr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_intersect_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]

@@ -514,3 +514,28 @@ def test_dirtmap_frame(oracle):
     assert stats.nrays == nrays
     assert np.array_equal(rgb, want)
     assert np.unique(rgb).size > 50 and rgb.max() <= 1.0
+
+
+def test_whitted_frame(oracle):
+    """SURVEY 8f rank 2, Whitted refraction tracer: device frame against the oracle's (transport pinned ray by ray to the compiled
+    ri_transport_whitted on CPU).  fp64 records; the environment lookup's acos is the one libm call, so the comparison allows 1e-9
+    relative -- and demands the oracle's exact ray count (every chain has the same length)."""
+    _need_gpu()
+    import math
+    env = ol.test_texture(31, 29, 7)
+    tris = np.concatenate([scenes.triangle_soup(4000, 9), scenes.triangle_soup(6, 3) * 0.2 + 0.4])
+    c2w = np.eye(4)
+    c2w[3, :3] = (0.5, 0.5, -2.0)
+    flen = 1.0 / math.tan(math.radians(40.0) / 2)
+    a = accel.Accel.bind().build(tris, accel.PREC_F64)
+    fr = accel.make_frame(c2w.reshape(16), flen, False, 96, 72, 2, 2, gather_nsamples=64, precision=accel.PREC_F64)
+    cam = np.zeros(27)
+    cam[:16] = c2w.reshape(16)
+    cam[16], cam[17], cam[20], cam[21], cam[22], cam[23] = flen, 0, 2, 2, 64, 32
+    ot = oracle.build(tris)
+    for e in (env, None):
+        rgb, stats = a.render_whitted(fr, e)
+        want, nrays = ot.render_whitted(ol.frame_params(cam, 96, 72), e)
+        assert stats.nrays == nrays
+        assert np.allclose(rgb, want, rtol=1e-9, atol=0.0)
+    assert not rgb.any()                                   # no environment: the transport returns black

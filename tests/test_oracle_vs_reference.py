@@ -146,3 +146,31 @@ def test_transports_called_directly(oracle, ref):
         assert np.array_equal(got, want) and (want[:, 0] > 0).sum() > 1000
     dirt = ot.transport_batch(1, rays6)[:, 0]
     assert np.unique(np.round(dirt * 16, 6)).size > 100          # distances inside the window: more than the 17 AO levels
+
+
+def _glass_stack(n=12):
+    """n parallel quads (two triangles each) one behind the other: a chain of refractions that outlives MAX_TRACE_DEPTH."""
+    tris = []
+    for i in range(n):
+        z = 0.2 * i
+        tris += [[[-1, -1, z], [1, -1, z], [1, 1, z]], [[-1, -1, z], [1, 1, z], [-1, 1, z]]]
+    return np.array(tris, dtype=np.float64)
+
+
+def test_whitted_transport_called_directly(oracle, ref):
+    """ri_transport_whitted of the compiled reference per eye ray (refraction chains, total internal reflection,
+    angular-map environment lookup) against the restatement: bit-identical radiance; the glass stack cuts chains at depth 8."""
+    env = ol.test_texture(31, 29, 7)
+    rng = np.random.default_rng(2)
+    for tris, lo, hi in ((scenes.triangle_soup(20000, 9), 0.0, 1.0), (_glass_stack(), -0.6, 0.6)):
+        rs, ot = ref.build(tris), oracle.build(tris)
+        rs.set_envmap(env)
+        org = rng.uniform(-0.3, 1.3, (4000, 3))
+        org[:, 2] = -1.0 - rng.uniform(0, 1, 4000)
+        tgt = np.concatenate([rng.uniform(lo, hi, (4000, 2)), rng.uniform(0.0, 1.0, (4000, 1))], axis=1)
+        rays6 = np.concatenate([org, tgt - org], axis=1)
+        want = rs.transport_batch(2, rays6)
+        got, nrays = ot.transport_whitted(rays6, env)
+        assert np.array_equal(got, want)
+        assert nrays > 1.5 * len(rays6)
+    assert (got.sum(axis=1) == 0).sum() > 100          # chains cut at MAX_TRACE_DEPTH leave zero radiance
