@@ -153,7 +153,7 @@ int ri_b200_state_ext_batch_f64(ri_b200_accel_t *accel, const double *rays, cons
 /* material texture of the AO transport: ri_transport_ambientocclusion multiplies the radiance by ri_texture_fetch(texture, st) when
  * the hit geom's material has one (ambientocclusion.c:393-401; render/texture.c:86-236 bilinear fetch, wrap by floor, zero texels
  * beyond the last row/column).  rgba: [height][width][4] floats = ri_texture_t.data; tri_textured[ntris] marks the INPUT triangles
- * whose geom carries the texture (NULL: all).  Call after ri_b200_set_attributes (which supplies st); ri_b200_render_ao then writes
+ * whose geom carries the texture (NULL: all); the st come from ri_b200_set_attributes (either order).  ri_b200_render_ao then writes
  * three channels.  NULL rgba removes the texture. */
 int ri_b200_set_texture(ri_b200_accel_t *accel, const float *rgba, int width, int height, const uint8_t *tri_textured);
 

@@ -814,12 +814,16 @@ extern "C" int ri_b200_set_attributes(ri_b200_accel_t *a, const double *tri_colo
     if (a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
     std::lock_guard<std::mutex> lock(a->mu);
     CUDA_OK(cudaSetDevice(a->device));
+    const size_t n = (size_t)a->tree.ntris;
+    std::vector<uint8_t> fl(n, 0);
+    if (a->d_attr_flags && n) {                              // keep the "carries the material texture" marks of ri_b200_set_texture
+        CUDA_OK(cudaMemcpy(fl.data(), a->d_attr_flags, n, cudaMemcpyDeviceToHost));
+        for (auto &f : fl) f &= 8u;
+    }
     cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags);
     a->d_col = a->d_st = nullptr; a->d_attr_flags = nullptr;
     if (a->tree.empty) return 0;
-    const size_t n = (size_t)a->tree.ntris;
     std::vector<double> col(9 * n, 0.0), st(6 * n, 0.0);
-    std::vector<uint8_t> fl(n, 0);
     for (size_t p = 0; p < n; ++p) {                         // post-build order, like the normals
         const size_t o = (size_t)a->tree.orig[p];
         if (tri_colors && has_color && has_color[o]) { std::memcpy(&col[9 * p], tri_colors + 9 * o, 9 * sizeof(double)); fl[p] |= 1; }
