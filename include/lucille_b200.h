@@ -122,6 +122,9 @@ int     ri_b200_triorder(const ri_b200_accel_t *accel, uint32_t *orig_out);   /*
 int64_t ri_b200_export_flat(const ri_b200_accel_t *accel, void *nodes32, void *nodes64, void *tris32, void *tris64,
                             uint32_t *header_out);
 
+/* the leaf-transposed copies of the triangle slots (same sizes as tris32 / tris64; layout: lucille_b200/csrc/bvh_build.h) */
+int     ri_b200_export_flat_transposed(const ri_b200_accel_t *accel, void *tris32t, void *tris64t);
+
 /* ---- replaces accel_intersect_func / ri_bvh_intersect for ONE ray (accel.h:30-34, bvh.c:430-542),
  * double precision, returns 1 on hit / 0 on miss / <0 on error.  state may be NULL. */
 int ri_b200_intersect1(ri_b200_accel_t *accel, const double org[3], const double dir[3],

@@ -114,6 +114,7 @@ ABI = [
     ("ri_b200_export_nodes", C.c_int64, [_P, _P, C.c_int64]),
     ("ri_b200_triorder", _I, [_P, _P]),
     ("ri_b200_export_flat", C.c_int64, [_P, _P, _P, _P, _P, _P]),
+    ("ri_b200_export_flat_transposed", _I, [_P, _P, _P]),
     ("ri_b200_intersect1", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_intersect_batch_f32", _I, [_P, _P, _U64, _P]),
     ("ri_b200_occluded_batch_f32", _I, [_P, _P, _U64, _P]),
@@ -288,8 +289,11 @@ class Accel:
         t64 = np.zeros(nslots if info.precisions & PREC_F64 else 0, dtype=TRI64_DTYPE)
         _check(self.lib.ri_b200_export_flat(self._h(), _ptr(n32) if len(n32) else None, _ptr(n64) if len(n64) else None,
                                             _ptr(t32) if len(t32) else None, _ptr(t64) if len(t64) else None, _ptr(hdr)))
-        return dict(nodes32=n32, nodes64=n64, tris32=t32, tris64=t64, root_word=int(hdr[0]), ninner=int(hdr[1]),
-                    top_count=int(hdr[2]), nslots=nslots)
+        t32t = np.zeros(len(t32) * 48, dtype=np.uint8)       # leaf-transposed copies, raw bytes (layout: csrc/bvh_build.h)
+        t64t = np.zeros(len(t64) * 96, dtype=np.uint8)
+        _check(self.lib.ri_b200_export_flat_transposed(self._h(), _ptr(t32t) if len(t32t) else None, _ptr(t64t) if len(t64t) else None))
+        return dict(nodes32=n32, nodes64=n64, tris32=t32, tris64=t64, tris32t=t32t, tris64t=t64t, root_word=int(hdr[0]),
+                    ninner=int(hdr[1]), top_count=int(hdr[2]), nslots=nslots)
 
     # -- accel->intersect, batched (host buffers) ---------------------------------------------------
     def intersect(self, rays: np.ndarray) -> np.ndarray:

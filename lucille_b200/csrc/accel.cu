@@ -453,6 +453,16 @@ extern "C" int64_t ri_b200_export_flat(const ri_b200_accel_t *a, void *nodes32, 
     return (int64_t)f.ninner;
 }
 
+extern "C" int ri_b200_export_flat_transposed(const ri_b200_accel_t *a, void *tris32t, void *tris64t)
+{
+    if (!a) return fail("null argument");
+    if (a->device >= 0) return fail("flat records are only kept on RI_B200_HOST_ONLY accelerators");
+    const FlatTree &f = a->flat;
+    if (tris32t && !f.tris32t.empty()) std::memcpy(tris32t, f.tris32t.data(), f.tris32t.size() * sizeof(Tri32));
+    if (tris64t && !f.tris64t.empty()) std::memcpy(tris64t, f.tris64t.data(), f.tris64t.size() * sizeof(Tri64));
+    return 0;
+}
+
 extern "C" int ri_b200_set_normals(ri_b200_accel_t *a, const double *tri_normals)
 {
     if (!a) return fail("null argument");

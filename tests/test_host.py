@@ -126,6 +126,42 @@ def test_flat_records_decode_to_canonical_tree(n):
     assert flat["top_count"] == min(1024, flat["ninner"])
 
 
+def test_leaf_transposed_copies_are_a_permutation_of_the_slots():
+    """The pooled kernels read the leaf-TRANSPOSED copies: chunk k (32 bytes) of item j of a leaf whose rows hold m items sits at
+    slot0 * sizeof(slot) + (k * m + j) * 32 (fp32: item = pair of slots, m = slots/2; fp64: item = slot, m = slots; slots =
+    round_up(ntris, 4)).  Same bytes as the plain slots, except the unit edges given to the masked half of an odd last pair."""
+    tris = scenes.triangle_soup(3000, 3)
+    a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64 | accel.HOST_ONLY)
+    flat = a.flat()
+    t32 = flat["tris32"].view(np.uint8).reshape(-1, 48)
+    t64 = flat["tris64"].view(np.uint8).reshape(-1, 96)
+    t32t, t64t = flat["tris32t"], flat["tris64t"]
+    leaves = [n for n in a.nodes() if n["is_leaf"]]
+    slot0, odd_leaves = 0, 0
+    for leaf in leaves:
+        ntris = int(leaf["ntris"])
+        ns = (ntris + 3) // 4 * 4
+        assert np.array_equal(flat["tris32"]["prim"][slot0:slot0 + ntris], np.arange(leaf["tri_start"], leaf["tri_start"] + ntris))
+        pairs = t32[slot0:slot0 + ns].reshape(ns // 2, 96)
+        m = ns // 2
+        for j in range(m):
+            for k in range(3):
+                got = t32t[slot0 * 48 + (k * m + j) * 32: slot0 * 48 + (k * m + j) * 32 + 32]
+                want = pairs[j, 32 * k: 32 * k + 32].copy()
+                if (ntris & 1) and j == (ntris + 1) // 2 - 1 and k == 2:          # masked half of the last used pair: unit edges
+                    w = want.view(np.float32).copy()
+                    w[0], w[5] = 1.0, 1.0
+                    want = w.view(np.uint8)
+                    odd_leaves += 1
+                assert np.array_equal(got, want)
+        for j in range(ns):
+            for k in range(3):
+                got = t64t[slot0 * 96 + (k * ns + j) * 32: slot0 * 96 + (k * ns + j) * 32 + 32]
+                assert np.array_equal(got, t64[slot0 + j, 32 * k: 32 * k + 32])
+        slot0 += ns
+    assert slot0 == flat["nslots"] and odd_leaves > 10
+
+
 def test_empty_scene_builds_valid_accelerator():
     a = accel.Accel.bind().build(np.zeros((0, 3, 3)), accel.PREC_F32 | accel.HOST_ONLY)
     info = a.info()
