@@ -190,21 +190,22 @@ static int stack_capacity(const ri_b200_accel *a)
     return cap;
 }
 
-static void launch_closest_pool(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits,
+template <typename Real>
+static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m, uint32_t chunk, typename RayIO<Real>::Hit *d_hits,
                                 unsigned int *ctr, uint32_t refill_at, cudaStream_t st)
 {
     const int cap = stack_capacity(a);
-    const size_t smem = pool_closest_smem_bytes(cap);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(closest_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = pool_closest_smem_bytes<Real>(cap);
+    auto kern = closest_pool_kernel<Real>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, closest_pool_kernel, kBlock, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem);
     if (per_sm < 1) per_sm = 1;
     const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
     uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
     want = (want + (kBlock / 32) - 1) / (kBlock / 32);
     const unsigned blocks = (unsigned)(want < capb ? want : capb);
-    closest_pool_kernel<<<blocks, kBlock, smem, st>>>(make_view<float>(a), reinterpret_cast<const char *>(a->d_tris32t), d_rays, m, chunk,
-                                                     d_hits, ctr, refill_at, (uint32_t)cap);
+    kern<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays, m, chunk, d_hits, ctr, refill_at, (uint32_t)cap);
 }
 
 template <typename Real, bool ANYHIT, bool COUNT>
@@ -224,7 +225,8 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         static const bool use_pool = !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);   // A/B knob: 0 = vote-scheduled kernel
         const bool pooled = ANYHIT && use_pool;
         static const bool use_pool_closest = !(getenv("B200_POOL_CLOSEST") && atoi(getenv("B200_POOL_CLOSEST")) == 0);
-        const bool pooled_closest = !ANYHIT && sizeof(Real) == 4 && use_pool_closest && d_hits != nullptr;
+        static const bool use_pool_closest64 = !(getenv("B200_POOL_CLOSEST64") && atoi(getenv("B200_POOL_CLOSEST64")) == 0);
+        const bool pooled_closest = !ANYHIT && use_pool_closest && (sizeof(Real) == 4 || use_pool_closest64) && d_hits != nullptr;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const size_t pool_smem = pool_smem_bytes<Real>(cap);
@@ -248,8 +250,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             unsigned int *ctr = a->d_work + (a->work_slot.fetch_add(1) & 63u);
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             if (pooled_closest)
-                launch_closest_pool(a, (const float *)(const void *)(d_rays + done * RayIO<Real>::kRayStride), m, chunk,
-                                    (ri_b200_hit_f32 *)(void *)(d_hits + done), ctr, refill_at, st);
+                launch_closest_pool<Real>(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_hits + done, ctr, refill_at, st);
             else if (pooled)
                 pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                       d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,

@@ -1,4 +1,6 @@
-// Pooled closest-hit traverser (fp32 records): pool.cuh's scheme for ri_b200_intersect_*_f32.
+// Pooled closest-hit traverser: pool.cuh's scheme for ri_b200_intersect_* (fp32 records: items are slot pairs, one 64-bit key;
+// fp64 records: items are single slots and the winner is found in two steps -- atomicMin on the bits of |t|, then atomicMax on the
+// item number among the lanes that hold that t).
 //
 // A closest-hit query is order-DEPENDENT: the best t so far culls boxes (bvh.c:1038-1044) and leaves commit in visiting order
 // (bvh.c:850).  That order is kept: a lane walks its ray's nodes in the reference's order, and when it reaches a leaf it WAITS
@@ -34,40 +36,67 @@ __device__ __forceinline__ void pool_pair_closest(const char *trisT, uint32_t sl
     tri_test_bf<float>(b, org, dir, 2u * j + 1u < ntris, tl, ul, vl, tprim);
 }
 
-constexpr size_t pool_closest_smem_bytes(int stack_cap)
-{ return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(float4)); }
+__device__ __forceinline__ void pool_item_closest(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const float org[3],
+                                                  const float dir[3], float &tl, float &ul, float &vl, uint32_t &tprim)
+{ pool_pair_closest(trisT, slot0, ntris, j, org, dir, tl, ul, vl, tprim); }
 
-// 3 CTAs x 256 threads per SM at 79 registers: measured 909 Mrays/s on the C3 batch against 877 with 4 CTAs at 64 (spills)
-__global__ void __launch_bounds__(kBlock, 3)
-closest_pool_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
-                    const uint32_t chunk, ri_b200_hit_f32 *__restrict__ hits_out, unsigned int *__restrict__ work_counter,
+// fp64: one triangle slot per item, tested from t_leaf = 1e38
+__device__ __forceinline__ void pool_item_closest(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const double org[3],
+                                                  const double dir[3], double &tl, double &ul, double &vl, uint32_t &tprim)
+{
+    const uint32_t m = (ntris + 3u) & ~3u;
+    const uint32_t o0 = slot0 * 3u + j, o1 = o0 + m, o2 = o1 + m;
+    const D4 q0 = ldg256d(trisT + (size_t)o0 * 32u), q1 = ldg256d(trisT + (size_t)o1 * 32u), q2 = ldg256d(trisT + (size_t)o2 * 32u);
+    TriRegs<double> a;
+    a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = (uint32_t)__double_as_longlong(q0.v[3]);
+    a.e1[0] = q1.v[0]; a.e1[1] = q1.v[1]; a.e1[2] = q1.v[2];
+    a.e2[0] = q2.v[0]; a.e2[1] = q2.v[1]; a.e2[2] = q2.v[2];
+    tl = Prec<double>::inf(); ul = 0.0; vl = 0.0; tprim = 0xffffffffu;
+    tri_test_bf<double>(a, org, dir, true, tl, ul, vl, tprim);
+}
+
+template <typename Real> struct PoolRes;                      // an item's offer to its owner: (t, u, v, prim)
+template <> struct PoolRes<float>  { float  t, u, v; uint32_t prim; };
+template <> struct PoolRes<double> { double t, u, v; uint32_t prim, pad; };
+__device__ __forceinline__ unsigned long long abs_bits(float t)  { return (unsigned long long)(__float_as_uint(t) & 0x7fffffffu); }
+__device__ __forceinline__ unsigned long long abs_bits(double t) { return (unsigned long long)__double_as_longlong(t) & 0x7fffffffffffffffull; }
+
+template <typename Real> constexpr size_t pool_closest_smem_bytes(int stack_cap)
+{ return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(PoolRes<Real>) + sizeof(uint32_t)); }
+
+// fp32: 3 CTAs x 256 threads per SM at 79 registers: measured 909 Mrays/s on the C3 batch against 877 with 4 CTAs at 64 (spills)
+template <typename Real>
+__global__ void __launch_bounds__(kBlock, sizeof(Real) == 4 ? 3 : 2)
+closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
+                    const uint32_t chunk, typename RayIO<Real>::Hit *__restrict__ hits_out, unsigned int *__restrict__ work_counter,
                     const uint32_t refill_at, const uint32_t stack_cap)
 {
-    using P = Prec<float>;
-    using L = PoolLeaf<float>;
+    using P = Prec<Real>;
+    using L = PoolLeaf<Real>;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t s_stack[];  // [stack_cap][kBlock] words, ray slots, descriptors, keys, results
     uint32_t *stk = s_stack + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
     char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kBlock);
-    char *s_rays = s_tail + (size_t)wbase * RaySlot<float>::kBytes;
-    uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<float>::kBytes) + wbase;
-    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_tail + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2))) + wbase;
-    float4 *s_res = reinterpret_cast<float4 *>(s_tail + (size_t)kBlock * (RaySlot<float>::kBytes + sizeof(uint2) + sizeof(unsigned long long))) + wbase;
+    char *s_rays = s_tail + (size_t)wbase * RaySlot<Real>::kBytes;
+    uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<Real>::kBytes) + wbase;
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2))) + wbase;
+    PoolRes<Real> *s_res = reinterpret_cast<PoolRes<Real> *>(s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long))) + wbase;
+    uint32_t *s_win = reinterpret_cast<uint32_t *>(s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(PoolRes<Real>))) + wbase;
 
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = false;
 
     uint32_t cur = kIdle, prog = 0, idx = 0, sp = 0, best_prim = 0xffffffffu, tprim = 0xffffffffu;
-    float org[3], dir[3], inv[3], best_t = P::inf(), best_u = 0.0f, best_v = 0.0f, tl = P::inf(), ul = 0.0f, vl = 0.0f;
+    Real org[3], dir[3], inv[3], best_t = P::inf(), best_u = Real(0), best_v = Real(0), tl = P::inf(), ul = Real(0), vl = Real(0);
     bool sx = false, sy = false, sz = false;
-    org[0] = org[1] = org[2] = dir[0] = dir[1] = dir[2] = inv[0] = inv[1] = inv[2] = 0.0f;
+    org[0] = org[1] = org[2] = dir[0] = dir[1] = dir[2] = inv[0] = inv[1] = inv[2] = Real(0);
 
-    auto retire = [&]() { RayIO<float>::store(hits_out, idx, best_t < P::inf(), best_t, best_u, best_v, best_prim); };   // bvh.c:1187
+    auto retire = [&]() { RayIO<Real>::store(hits_out, idx, best_t < P::inf(), best_t, best_u, best_v, best_prim); };   // bvh.c:1187
     auto enter = [&](const uint32_t word) {      // step onto `word`; a leaf starts with a fresh leaf-local record (bvh.c:833-836)
         cur = word; prog = 0;
-        tl = P::inf(); ul = 0.0f; vl = 0.0f; tprim = 0xffffffffu;
+        tl = P::inf(); ul = Real(0); vl = Real(0); tprim = 0xffffffffu;
     };
 
     for (;;) {
@@ -88,16 +117,16 @@ closest_pool_kernel(const SceneView<float> S, const char *__restrict__ trisT, co
             const unsigned rank = __popc(idle & lt_mask);
             if (cur == kIdle && rank < take) {
                 idx = chunk_next + rank;
-                RayIO<float>::load(rays, idx, org, dir);
-                RaySlot<float>::store(s_rays, lane, org, dir);
-                best_t = P::inf(); best_u = 0.0f; best_v = 0.0f; best_prim = 0xffffffffu;
-                sx = dir[0] < 0.0f; sy = dir[1] < 0.0f; sz = dir[2] < 0.0f;
+                RayIO<Real>::load(rays, idx, org, dir);
+                RaySlot<Real>::store(s_rays, lane, org, dir);
+                best_t = P::inf(); best_u = Real(0); best_v = Real(0); best_prim = 0xffffffffu;
+                sx = dir[0] < Real(0); sy = dir[1] < Real(0); sz = dir[2] < Real(0);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)      // bvh.c:473-497
-                    inv[k] = (P::rabs(dir[k]) > P::eps()) ? 1.0f / dir[k] : ((dir[k] < 0.0f) ? -P::vmax() : P::vmax());
-                float tmin;
+                    inv[k] = (P::rabs(dir[k]) > P::eps()) ? Real(1) / dir[k] : ((dir[k] < Real(0)) ? -P::vmax() : P::vmax());
+                Real tmin;
                 const bool in_scene = (S.root_word != kDoneWord) &&
-                    slab<float>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
+                    slab<Real>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
                 sp = 0;
                 if (in_scene) enter(S.root_word);
                 else retire();                   // bvh.c:446 / 522-526: miss without traversal
@@ -130,28 +159,40 @@ closest_pool_kernel(const SceneView<float> S, const char *__restrict__ trisT, co
                 if (owner) {
                     s_desc[__popc(owners & lt_mask)] = make_uint2(cur, lane | ((prog - excl + 64u) << 8));
                     s_key[lane] = ~0ull;
+                    if (sizeof(Real) == 8) s_win[lane] = 0u;
                 }
                 __syncwarp();
+                unsigned own = 0;
+                unsigned long long my_bits = ~0ull;
                 if (lane < total) {
                     const uint2 d = s_desc[__popc(starts & le_mask) - 1u];
-                    const unsigned own = d.y & 31u;
+                    own = d.y & 31u;
                     const uint32_t item = lane + (d.y >> 8) - 64u;
-                    float oorg[3], odir[3], t, u, v;
+                    Real oorg[3], odir[3], t, u, v;
                     uint32_t prim;
-                    RaySlot<float>::load(s_rays, own, oorg, odir);
-                    pool_pair_closest(trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir, t, u, v, prim);
-                    if (prim != 0xffffffffu) {   // the pair accepted a triangle: offer it to the owner
-                        s_res[lane] = make_float4(t, u, v, __uint_as_float(prim));
-                        atomicMin(&s_key[own], ((unsigned long long)(__float_as_uint(t) & 0x7fffffffu) << 32) | (unsigned long long)(31u - lane));
+                    RaySlot<Real>::load(s_rays, own, oorg, odir);
+                    pool_item_closest(trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir, t, u, v, prim);
+                    if (prim != 0xffffffffu) {   // the item accepted a triangle: offer it to the owner
+                        PoolRes<Real> r;
+                        r.t = t; r.u = u; r.v = v; r.prim = prim;
+                        s_res[lane] = r;
+                        my_bits = abs_bits(t);
+                        if (sizeof(Real) == 4) atomicMin(&s_key[own], (my_bits << 32) | (unsigned long long)(31u - lane));
+                        else atomicMin(&s_key[own], my_bits);
                     }
                 }
                 __syncwarp();
+                if (sizeof(Real) == 8) {         // fp64: among the items that hold the smallest t, the latest one
+                    if (my_bits != ~0ull && s_key[own] == my_bits) atomicMax(&s_win[own], lane + 1u);
+                    __syncwarp();
+                }
                 if (owner) {
                     const uint32_t took = (cnt < 32u - excl) ? cnt : 32u - excl;
                     const unsigned long long key = s_key[lane];
                     if (key != ~0ull) {          // winner of this round's items of my leaf; accepted unless t > t_leaf (bvh.c:780)
-                        const float4 r = s_res[31u - (unsigned)(key & 31ull)];
-                        if (!(r.x > tl)) { tl = r.x; ul = r.y; vl = r.z; tprim = __float_as_uint(r.w); }
+                        const unsigned w = (sizeof(Real) == 4) ? 31u - (unsigned)(key & 31ull) : s_win[lane] - 1u;
+                        const PoolRes<Real> r = s_res[w];
+                        if (!(r.t > tl)) { tl = r.t; ul = r.u; vl = r.v; tprim = r.prim; }
                     }
                     prog += took;
                     if (prog == nitems) {        // leaf finished: commit (bvh.c:850), then pop or retire
@@ -166,10 +207,10 @@ closest_pool_kernel(const SceneView<float> S, const char *__restrict__ trisT, co
             }
             if (cur < kIdle) {
                 // ---- node step: bvh.c:1153-1179
-                NodeRegs<float> nd;
+                NodeRegs<Real> nd;
                 load_node_wide(S.nodes + cur, nd);
-                const bool h0 = slab_mm<float>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
-                const bool h1 = slab_mm<float>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
+                const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
+                const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
                 const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);
                 const bool both = h0 && h1, none = !h0 && !h1;
                 const bool pop = none && (sp != 0u);
