@@ -235,6 +235,9 @@ int ri_b200_render_dirtmap(ri_b200_accel_t *accel, const ri_b200_frame_t *frame,
 int ri_b200_render_whitted(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, const float *env_rgba, int env_width, int env_height,
                            float *rgb_out, ri_b200_frame_stats_t *stats);
 
+/* ri_transport_sample / trace_path (transport/transport.c:50-173): white where the eye ray hits, black elsewhere.  fp64 records. */
+int ri_b200_render_sample(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *rgb_out, ri_b200_frame_stats_t *stats);
+
 /* ri_sunsky_get_sky_rgb for a HOST batch of directions ([n][3] floats in, [n][3] floats out), computed on `device` */
 int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t n, float *rgb_out, int device);
 

@@ -141,6 +141,7 @@ ABI = [
     ("ri_b200_sunsky_rgb", _I, [_P, _P, _U64, _P, _I]),
     ("ri_b200_render_dirtmap", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_whitted", _I, [_P, _P, _P, _I, _I, _P, _P]),
+    ("ri_b200_render_sample", _I, [_P, _P, _P, _P]),
     ("ri_b200_hdr_encode", C.c_int64, [_P, _I, _I, _P, _U64, _I, _I]),
     ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
@@ -404,6 +405,13 @@ class Accel:
         stats = FrameStats()
         _check(self.lib.ri_b200_render_whitted(self._h(), C.byref(frame), _ptr(env), 0 if env is None else env.shape[1],
                                                0 if env is None else env.shape[0], _ptr(rgb), C.byref(stats)))
+        return rgb, stats
+
+    def render_sample(self, frame: Frame):
+        """One frame with ``ri_transport_sample`` (transport/transport.c): white where the eye ray hits."""
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_sample(self._h(), C.byref(frame), _ptr(rgb), C.byref(stats)))
         return rgb, stats
 
     def render_dirtmap(self, frame: Frame):

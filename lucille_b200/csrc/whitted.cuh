@@ -43,7 +43,8 @@ __device__ __forceinline__ void ibl_fetch_dev(const TexDev &env, const double di
 
 __global__ void __launch_bounds__(kBlock)
 whitted_kernel(const SceneView<double> S, const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter,
-               const uint64_t nsamples, const TexDev env, double *__restrict__ rad_out, unsigned long long *__restrict__ nrays_out)
+               const uint64_t nsamples, const TexDev env, double *__restrict__ rad_out, unsigned long long *__restrict__ nrays_out,
+               const int hitmask_only)
 {
     extern __shared__ uint32_t s_stack[];
     const uint64_t s = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -57,7 +58,9 @@ whitted_kernel(const SceneView<double> S, const FrameDev F, const uint32_t *__re
         camera_ray(F, (int)(pix & 0xffffu), (int)(pix >> 16), jitter[2 * sub], jitter[2 * sub + 1], org, dir);
         ++traced;
         bool hit = trace_ray<double, false, false>(S, org, dir, s_stack + threadIdx.x, kBlock, t, u, v, prim, nullptr);
-        if (!hit) {
+        if (hitmask_only) {                                               // ri_transport_sample, transport.c:135-160: white on a hit
+            if (hit) rad[0] = rad[1] = rad[2] = 1.0;
+        } else if (!hit) {
             if (env.data) ibl_fetch_dev(env, dir, rad);
         } else {
             for (int depth = 1; depth <= 8 && hit; ++depth) {             // MAX_TRACE_DEPTH, whitted.c:24,48
@@ -95,8 +98,21 @@ __global__ void resolve_samples_kernel(const FrameDev F, const uint32_t *__restr
 
 }  // namespace b200
 
+static int render_eye_transport(ri_b200_accel_t *a, const ri_b200_frame_t *f, const float *env_rgba, int env_width, int env_height,
+                                float *rgb_out, ri_b200_frame_stats_t *stats, int hitmask_only);
+
 extern "C" int ri_b200_render_whitted(ri_b200_accel_t *a, const ri_b200_frame_t *f, const float *env_rgba, int env_width, int env_height,
                                       float *rgb_out, ri_b200_frame_stats_t *stats)
+{ return render_eye_transport(a, f, env_rgba, env_width, env_height, rgb_out, stats, 0); }
+
+// ri_transport_sample (transport/transport.c:50-173), the integrator Option "renderer" "method" would select if render.c did not
+// hard-wire ambient occlusion: white where the eye ray hits, black elsewhere (area-light geometry, which returns the light's colour,
+// is not part of the triangle soup this library receives).
+extern "C" int ri_b200_render_sample(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *rgb_out, ri_b200_frame_stats_t *stats)
+{ return render_eye_transport(a, f, nullptr, 0, 0, rgb_out, stats, 1); }
+
+static int render_eye_transport(ri_b200_accel_t *a, const ri_b200_frame_t *f, const float *env_rgba, int env_width, int env_height,
+                                float *rgb_out, ri_b200_frame_stats_t *stats, int hitmask_only)
 {
     if (!a || !f || !rgb_out) return fail("null argument");
     if (f->width < 1 || f->height < 1 || f->width > 65535 || f->height > 65535) return fail("bad frame size");
@@ -146,7 +162,7 @@ extern "C" int ri_b200_render_whitted(ri_b200_accel_t *a, const ri_b200_frame_t 
     CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(d_nrays, 0, 16, st));
     CUDA_OK(cudaMemsetAsync(d_rgb, 0, fb_bytes, st));
-    whitted_kernel<<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(make_view<double>(a), F, d_pix, d_jit, nsamples, env, d_rad, d_nrays);
+    whitted_kernel<<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(make_view<double>(a), F, d_pix, d_jit, nsamples, env, d_rad, d_nrays, hitmask_only);
     LAUNCHED();
     resolve_samples_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_rad, d_rgb);
     LAUNCHED();

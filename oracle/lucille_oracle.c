@@ -922,7 +922,8 @@ void orc_transport_batch(const orc_tree *T, int which, int ntheta, int nphi, con
         if (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) {
             orc_state_f64 st;
             state_build_uv(T, org, dir, t, uu, vv, prim, &st);
-            rad = which == 1 ? dirt_radiance(T, &V, &st, &rng, &nrays) : ao_radiance(T, &V, &st, ntheta, nphi, &rng, &nrays);
+            if (which == 3) rad = 1.0;                                       /* transport.c:150: white */
+            else rad = which == 1 ? dirt_radiance(T, &V, &st, &rng, &nrays) : ao_radiance(T, &V, &st, ntheta, nphi, &rng, &nrays);
         }
         radiance3[3 * i] = radiance3[3 * i + 1] = radiance3[3 * i + 2] = rad;
     }
@@ -1093,6 +1094,43 @@ void orc_render_whitted(const orc_tree *T, const orc_frame_t *f, const float *en
                     }
                 }
                 for (k = 0; k < 3; k++) dst[k] = (float)(accum[k] * ((double)1.0 / (f->xsamples * f->ysamples)));
+            }
+        }
+    }
+    free(buckets);
+    if (nrays_out) *nrays_out = nrays;
+}
+
+/* transport.c:50-173 ri_transport_sample -> trace_path: radiance = white on a hit (light geometry aside), black on a miss */
+void orc_render_hitmask(const orc_tree *T, const orc_frame_t *f, float *rgb, uint64_t *nrays_out)
+{
+    int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(f->width, f->height, f->bucket_size, buckets, nb_max);
+    view_t_f64 V = {0};
+    uint64_t nrays = 0;
+    int b;
+    if (!T->empty) view64(T, &V);
+    for (b = 0; b < nb; b++) {
+        int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        int u, v;
+        for (v = by; v < by + bh; v++) {
+            for (u = bx; u < bx + bw; u++) {
+                double accum = 0.0, px;
+                int xs, ys;
+                float *dst = rgb + 3 * ((size_t)(f->height - v - 1) * f->width + u);
+                for (ys = 0; ys < f->ysamples; ys++) {
+                    for (xs = 0; xs < f->xsamples; xs++) {
+                        double jx, jy, org[3], dir[3], t, uu, vv;
+                        uint32_t prim;
+                        orc_subpixel_jitter(xs, ys, f->xsamples, f->ysamples, &jx, &jy);
+                        orc_camera_ray(f, (double)(u + jx), (double)(v + jy), org, dir);
+                        nrays++;
+                        accum = accum + (trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL) ? 1.0 : 0.0);
+                    }
+                }
+                px = accum * ((double)1.0 / (f->xsamples * f->ysamples));
+                dst[0] = dst[1] = dst[2] = (float)px;
             }
         }
     }

@@ -178,6 +178,8 @@ void orc_render_dirtmap(const orc_tree *t, const orc_frame_t *f, float *rgb, uin
  * env: [h][w][4] floats or NULL (no environment: radiance 0).  One radiance per eye ray; nrays counts ri_raytrace calls. */
 void orc_transport_whitted(const orc_tree *t, const float *env, int env_w, int env_h, const double *rays, uint64_t n, double *radiance3,
                            uint64_t *nrays_out);
+/* ri_transport_sample / trace_path (transport/transport.c:50-173): white where the eye ray hits (no light geometry), black elsewhere */
+void orc_render_hitmask(const orc_tree *t, const orc_frame_t *f, float *rgb, uint64_t *nrays_out);
 void orc_render_whitted(const orc_tree *t, const orc_frame_t *f, const float *env, int env_w, int env_h, float *rgb, uint64_t *nrays_out);
 
 /* ---- sun-sky gather (row a12): ambientocclusion.c:153-324 gather_sunsky + contribution_from_sunlight, with the sky lookup

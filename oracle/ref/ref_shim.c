@@ -383,7 +383,7 @@ void lref_intersect_ext(void *h, const double *rays, uint64_t n, lref_ext_t *out
 
 /* ---- the other transports: compiled into the reference but never called by its pixel loop (render.c:800-804).
  * Called here per eye ray exactly as subsample() would call them: render = ri_render_get() with this scene installed, thread 0,
- * the thread's MT19937 stream re-seeded with 4357 (random.c:98-112) before the batch.  which: 0 ambient occlusion, 1 dirt map, 2 Whitted refraction tracer. */
+ * the thread's MT19937 stream re-seeded with 4357 (random.c:98-112) before the batch.  which: 0 ambient occlusion, 1 dirt map, 2 Whitted refraction tracer, 3 ri_transport_sample (transport.c:50-173: white on a hit). */
 #include "transport.h"
 extern int ri_transport_dirtmap(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
 extern int ri_transport_ambientocclusion(ri_render_t *render, const ri_ray_t *ray, ri_transport_info_t *result);
@@ -418,7 +418,8 @@ void lref_transport_batch(void *h, int which, const double *rays, uint64_t n, do
         ray.dir[0] = r[3]; ray.dir[1] = r[4]; ray.dir[2] = r[5]; ray.dir[3] = 0.0;
         ray.thread_num = 0;
         memset(&result, 0, sizeof(result));
-        if (which == 2) ri_transport_whitted(render, &ray, &result);
+        if (which == 3) ri_transport_sample(render, &ray, &result);
+        else if (which == 2) ri_transport_whitted(render, &ray, &result);
         else if (which == 1) ri_transport_dirtmap(render, &ray, &result);
         else ri_transport_ambientocclusion(render, &ray, &result);
         radiance3[3 * i] = result.radiance[0]; radiance3[3 * i + 1] = result.radiance[1]; radiance3[3 * i + 2] = result.radiance[2];

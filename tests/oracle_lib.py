@@ -303,6 +303,12 @@ class OracleTree:
                                     0 if env is None else env.shape[0], _ptr(rgb), C.byref(nrays))
         return rgb, nrays.value
 
+    def render_hitmask(self, frame: "FrameParams"):
+        rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        nrays = C.c_uint64(0)
+        self.lib.orc_render_hitmask(self.h, C.byref(frame), _ptr(rgb), C.byref(nrays))
+        return rgb, nrays.value
+
     def render_dirtmap(self, frame: "FrameParams"):
         rgb = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
         nrays = C.c_uint64(0)
@@ -362,6 +368,7 @@ class Oracle:
         lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.orc_render_hitmask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_hdr_encode.restype = C.c_uint64
         lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]

@@ -539,3 +539,6 @@ def test_whitted_frame(oracle):
         assert stats.nrays == nrays
         assert np.allclose(rgb, want, rtol=1e-9, atol=0.0)
     assert not rgb.any()                                   # no environment: the transport returns black
+    mask, stats = a.render_sample(fr)                      # ri_transport_sample: white where the eye ray hits
+    want, nrays = ot.render_hitmask(ol.frame_params(cam, 96, 72))
+    assert stats.nrays == nrays and np.array_equal(mask, want) and 0.05 < mask.mean() < 0.95

@@ -141,7 +141,7 @@ def test_transports_called_directly(oracle, ref):
     rng = np.random.default_rng(2)
     org = rng.uniform(-1, 4, (3000, 3))
     rays6 = np.concatenate([org, rng.uniform(0, 3, (3000, 3)) - org], axis=1)
-    for which in (1, 0):
+    for which in (1, 0, 3):                                  # 3 = ri_transport_sample (transport.c:50-173): white on a hit
         want, got = rs.transport_batch(which, rays6), ot.transport_batch(which, rays6)
         assert np.array_equal(got, want) and (want[:, 0] > 0).sum() > 1000
     dirt = ot.transport_batch(1, rays6)[:, 0]
