@@ -221,7 +221,9 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         // production path: persistent warps with ray replacement; batches above 2^31 rays are split
         auto pk = trace_persistent_kernel<Real, ANYHIT>;
         // 4 CTAs x 256 threads per SM at 64 registers (fp32): measured 979 Mrays/s on C3 against 878 with 3 CTAs at 72 registers
-        auto pool = occluded_pool_kernel<Real, (sizeof(Real) == 4 ? 4 : 3)>;
+        static const bool top_smem = getenv("B200_POOL_TOPSMEM") && atoi(getenv("B200_POOL_TOPSMEM")) != 0;      // experiment, fp32 only (pool.cuh)
+        const bool use_top = top_smem && sizeof(Real) == 4;
+        auto pool = use_top ? occluded_pool_kernel<Real, (sizeof(Real) == 4 ? 4 : 3), (sizeof(Real) == 4)> : occluded_pool_kernel<Real, (sizeof(Real) == 4 ? 4 : 3)>;
         static const bool use_pool = !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);   // A/B knob: 0 = vote-scheduled kernel
         const bool pooled = ANYHIT && use_pool;
         static const bool use_pool_closest = !(getenv("B200_POOL_CLOSEST") && atoi(getenv("B200_POOL_CLOSEST")) == 0);
@@ -229,7 +231,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         const bool pooled_closest = !ANYHIT && use_pool_closest && (sizeof(Real) == 4 || use_pool_closest64) && d_hits != nullptr;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const size_t pool_smem = pool_smem_bytes<Real>(cap);
+        const size_t pool_smem = pool_smem_bytes<Real>(cap) + (use_top ? kTopNodes * sizeof(Node32) + 16 : 0);
         if (pool_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem));
         int per_sm = 0;
         if (pooled) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool, kBlock, pool_smem));

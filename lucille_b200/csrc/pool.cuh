@@ -119,7 +119,24 @@ template <typename Real> constexpr size_t pool_smem_bytes(int stack_cap)
 // run beside the kernel at all (a profiler that serialises the two streams): the host then falls back to one launch per piece.
 constexpr unsigned kPoolSpinCap = 500u * 1000u;
 
-template <typename Real, int kMinBlocks>
+// EXPERIMENT (B200_POOL_TOPSMEM=1, fp32): the first kTopNodes inner nodes (breadth-first: the top levels of the tree, which every ray
+// walks) staged once per CTA into shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier, the TMA engine), node
+// steps on them served by LDS.128 instead of LDG.256.  Measured slower than the plain kernel -- see DESIGN.md -- and kept as evidence.
+constexpr uint32_t kTopNodes = 256;
+
+__device__ __forceinline__ void load_node_shared(const char *p, NodeRegs<float> &r)
+{
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 16),
+                 c = *reinterpret_cast<const float4 *>(p + 32);
+    const uint4 d = *reinterpret_cast<const uint4 *>(p + 48);
+    r.x[0] = a.x; r.x[1] = a.y; r.x[2] = a.z; r.x[3] = a.w;
+    r.y[0] = b.x; r.y[1] = b.y; r.y[2] = b.z; r.y[3] = b.w;
+    r.z[0] = c.x; r.z[1] = c.y; r.z[2] = c.z; r.z[3] = c.w;
+    r.c0 = d.x; r.c1 = d.y; r.axis = d.z;
+}
+__device__ __forceinline__ void load_node_shared(const char *, NodeRegs<double> &) {}
+
+template <typename Real, int kMinBlocks, bool kTopSmem = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
 occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
                      const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
@@ -135,6 +152,26 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
     char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kBlock);
     char *s_rays = s_tail + (size_t)(threadIdx.x & ~31u) * RaySlot<Real>::kBytes;              // this warp's 32 ray slots
     uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<Real>::kBytes) + (threadIdx.x & ~31u);
+    char *s_top = s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2));            // kTopSmem: [kTopNodes] node records, then the mbarrier
+    const uint32_t ntop = kTopSmem ? (S.top_count < kTopNodes ? S.top_count : kTopNodes) : 0u;
+    if (kTopSmem && ntop) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_top + kTopNodes * sizeof(Node32));
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_top);
+        const uint32_t bytes = ntop * (uint32_t)sizeof(Node32);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(S.nodes), "r"(bytes), "r"(bar) : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
 
     uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
     bool exhausted = false;                      // warp-uniform
@@ -253,7 +290,8 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             if (cur < kIdle) {
                 // ---- node step: bvh.c:1153-1179 with best_t == 1e38 (no hit yet)
                 NodeRegs<Real> nd;
-                load_node_wide(S.nodes + cur, nd);
+                if (kTopSmem && cur < ntop) load_node_shared(s_top + (size_t)cur * sizeof(Node32), nd);
+                else load_node_wide(S.nodes + cur, nd);
                 const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, P::inf());
                 const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, P::inf());
                 const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);     // near child = child[sign[axis0]]
