@@ -194,6 +194,20 @@ int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
                                     ri_b200_frame_stats_t *stats);
 int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
 
+/* fused multi-GPU resolve (one process per GPU of ONE node): rank 0 allocates the framebuffer with ri_b200_peer_alloc ([h][w][3]
+ * floats, zeroed) and hands the 64-byte CUDA IPC handle to the other ranks (any transport: torch.distributed, MPI, a pipe); they
+ * map it with ri_b200_peer_open.  ri_b200_render_ao_peer_dev renders the buckets of frame->rank and its resolve kernel stores them
+ * at their framebuffer positions in that shared buffer -- over NVLink / NVSwitch peer memory for ranks > 0 -- without clearing
+ * it: the gather that would follow the frame is done by the stores.  After every rank's stream has drained (and a barrier), rank 0
+ * reads the frame with ri_b200_peer_read.  ri_b200_peer_close (ranks > 0) / ri_b200_peer_free (rank 0) release it. */
+void *ri_b200_peer_alloc(uint64_t bytes, int device, uint8_t handle_out[64]);
+void *ri_b200_peer_open(const uint8_t handle[64], int device);
+int   ri_b200_peer_close(void *p, int device);
+int   ri_b200_peer_free(void *p, int device);
+int   ri_b200_peer_read(const void *p, void *host, uint64_t bytes, int device);
+int   ri_b200_render_ao_peer_dev(ri_b200_accel_t *accel, const ri_b200_frame_t *frame, float *d_rgb_shared, void *stream,
+                                 ri_b200_frame_stats_t *stats);
+
 /* ---- sun-sky variant of the same transport: gather_sunsky + contribution_from_sunlight (ambientocclusion.c:153-324), taken by
  * ri_transport_ambientocclusion whenever the scene has an AreaLightSource "sunsky" (ambientocclusion.c:369-376): fixed 8 x 8
  * gather (frame->ntheta/nphi are ignored), origin offset 1e-5, the sky colour ri_sunsky_get_sky_rgb(dir) (render/sunsky.c:322-408)

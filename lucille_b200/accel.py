@@ -136,6 +136,12 @@ ABI = [
     ("ri_b200_render_ao_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_ao_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
+    ("ri_b200_render_ao_peer_dev", _I, [_P, _P, _P, _P, _P]),
+    ("ri_b200_peer_alloc", _P, [_U64, _I, _P]),
+    ("ri_b200_peer_open", _P, [_P, _I]),
+    ("ri_b200_peer_close", _I, [_P, _I]),
+    ("ri_b200_peer_free", _I, [_P, _I]),
+    ("ri_b200_peer_read", _I, [_P, _P, _U64, _I]),
     ("ri_b200_render_sunsky", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_render_sunsky_tiles_dev", _I, [_P, _P, _P, _P, _P, _P]),
     ("ri_b200_sunsky_rgb", _I, [_P, _P, _U64, _P, _I]),
@@ -449,6 +455,13 @@ class Accel:
                                                     C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
         return stats
 
+    def render_ao_peer_dev(self, frame: Frame, d_rgb_shared: int, stream: Optional[int] = None, want_stats: bool = True):
+        """This rank's buckets stored at their framebuffer positions in a buffer shared by the ranks of the node (peer memory)."""
+        stats = FrameStats()
+        _check(self.lib.ri_b200_render_ao_peer_dev(self._h(), C.byref(frame), C.c_void_p(d_rgb_shared),
+                                                   C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
+        return stats
+
     def render_ao_dev(self, frame: Frame, d_rgb, stream: Optional[int] = None, want_stats: bool = True):
         stats = FrameStats()
         _check(self.lib.ri_b200_render_ao_dev(self._h(), C.byref(frame), _ptr(d_rgb),
@@ -480,6 +493,37 @@ def hdr_encode(rgb, width: int = 0, height: int = 0, device: int = 0) -> bytes:
     if n < 0 or n > cap:
         raise B200Error(last_error() if n < 0 else "hdr buffer too small")
     return out[:n].tobytes()
+
+
+def peer_alloc(nbytes: int, device: int = 0):
+    """(device pointer, 64-byte IPC handle) of a zeroed buffer other processes of the node can map (ri_b200_peer_alloc)."""
+    handle = np.zeros(64, dtype=np.uint8)
+    p = load_library().ri_b200_peer_alloc(nbytes, device, _ptr(handle))
+    if not p:
+        raise B200Error(last_error())
+    return int(p), handle.tobytes()
+
+
+def peer_open(handle: bytes, device: int = 0) -> int:
+    h = np.frombuffer(handle, dtype=np.uint8).copy()
+    p = load_library().ri_b200_peer_open(_ptr(h), device)
+    if not p:
+        raise B200Error(last_error())
+    return int(p)
+
+
+def peer_close(p: int, device: int = 0):
+    _check(load_library().ri_b200_peer_close(C.c_void_p(p), device))
+
+
+def peer_free(p: int, device: int = 0):
+    _check(load_library().ri_b200_peer_free(C.c_void_p(p), device))
+
+
+def peer_read(p: int, shape, device: int = 0) -> np.ndarray:
+    out = np.zeros(shape, dtype=np.float32)
+    _check(load_library().ri_b200_peer_read(C.c_void_p(p), _ptr(out), out.nbytes, device))
+    return out
 
 
 def frame_pixels(frame: Frame) -> np.ndarray:

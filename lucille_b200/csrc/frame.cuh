@@ -740,7 +740,9 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         CUDA_OK(cudaMemcpyAsync(d_jit, jit.data(), jit.size() * 8, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
     }
-    if (!packed) CUDA_OK(cudaMemsetAsync(d_rgb, 0, (size_t)f.width * f.height * 3 * sizeof(float), st));
+    // packed: 0 = full framebuffer, cleared first; 1 = this rank's pixels packed in visiting order; 2 = full framebuffer addressing
+    // WITHOUT clearing -- the buffer is shared by the ranks of a node (peer memory), each storing its own tiles into it
+    if (packed == 0) CUDA_OK(cudaMemsetAsync(d_rgb, 0, (size_t)f.width * f.height * 3 * sizeof(float), st));
     uint32_t nhits = 0;
     if (nsamples) {
         primary_kernel<Real><<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(S, F, d_pix, d_jit, nsamples, d_t, d_prim, d_uv);
@@ -841,9 +843,9 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     }
     CUDA_OK(cudaEventRecord(a->ev[4], st));
     if (npix) {
-        if (sky || dirtmap) resolve_rgb_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_lo, d_rgb, packed);
-        else if (textured && d_texcol) resolve_tex_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_texcol, d_rgb, packed);
-        else resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed);
+        if (sky || dirtmap) resolve_rgb_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_lo, d_rgb, packed == 1);
+        else if (textured && d_texcol) resolve_tex_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_texcol, d_rgb, packed == 1);
+        else resolve_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_srank, d_occ, d_rgb, packed == 1);
         LAUNCHED();
     }
     CUDA_OK(cudaGetLastError());
@@ -899,6 +901,66 @@ extern "C" int ri_b200_render_ao_tiles_dev(ri_b200_accel_t *a, const ri_b200_fra
     cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
     if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_packed, st, stats, nullptr, 0, 1);
     return render_ao_impl<float>(a, *f, d_packed, st, stats, nullptr, 0, 1);
+}
+
+// ---- fused multi-GPU resolve: every rank's resolve kernel stores its tiles straight into ONE framebuffer that lives on rank 0's GPU
+// and is mapped into the other ranks' address spaces (CUDA IPC over NVLink / NVSwitch peer memory) -- the gather that would follow
+// the frame is done by the stores themselves, no packed slab, no NCCL call.
+extern "C" int ri_b200_render_ao_peer_dev(ri_b200_accel_t *a, const ri_b200_frame_t *f, float *d_rgb_shared, void *stream,
+                                          ri_b200_frame_stats_t *stats)
+{
+    if (check_frame(a, f)) return -1;
+    if (!d_rgb_shared) return fail("null framebuffer");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
+    if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_rgb_shared, st, stats, nullptr, 0, 2);
+    return render_ao_impl<float>(a, *f, d_rgb_shared, st, stats, nullptr, 0, 2);
+}
+
+extern "C" void *ri_b200_peer_alloc(uint64_t bytes, int device, uint8_t handle_out[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    cudaIpcMemHandle_t h;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); fail("peer_alloc: cudaMalloc(%llu) failed", (unsigned long long)bytes); return nullptr; }
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); fail("peer_alloc: cudaIpcGetMemHandle failed"); return nullptr; }
+    if (handle_out) std::memcpy(handle_out, &h, 64);
+    return p;
+}
+extern "C" void *ri_b200_peer_open(const uint8_t handle[64], int device)
+{
+    void *p = nullptr;
+    cudaIpcMemHandle_t h;
+    if (!handle) { fail("null handle"); return nullptr; }
+    std::memcpy(&h, handle, 64);
+    if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        fail("peer_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" int ri_b200_peer_close(void *p, int device)
+{
+    if (!p) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+extern "C" int ri_b200_peer_free(void *p, int device)
+{
+    if (!p) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaFree(p));
+    return 0;
+}
+extern "C" int ri_b200_peer_read(const void *p, void *host, uint64_t bytes, int device)
+{
+    if (!p || !host) return fail("null argument");
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host, p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 extern "C" int64_t ri_b200_frame_pixels(const ri_b200_frame_t *f, uint32_t *out, int64_t capacity)

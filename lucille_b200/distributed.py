@@ -62,6 +62,53 @@ def gather_frame(local_slab, frame: "_accel.Frame", rank: int, world: int, group
     return scatter_tiles(frame.width, frame.height, lists, [b.cpu().numpy() for b in bufs])
 
 
+class PeerFramebuffer:
+    """One framebuffer on rank 0's GPU, mapped by every rank of the node (CUDA IPC, NVLink / NVSwitch peer memory).  Made once and
+    reused frame after frame: mapping a handle costs far more than a frame.  torch.distributed carries the 64-byte handle."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, device: int, group=None):
+        import torch.distributed as dist
+
+        self.shape, self.rank, self.world, self.device, self.group = (height, width, 3), rank, world, device, group
+        box = [None]
+        if rank == 0:
+            self.ptr, box[0] = _accel.peer_alloc(width * height * 3 * 4, device)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            self.ptr = _accel.peer_open(box[0], device)
+
+    def close(self):
+        import torch.distributed as dist
+
+        if self.ptr is None:
+            return
+        if self.world > 1:
+            dist.barrier(group=self.group)             # nobody frees or unmaps while another rank may still store
+        (_accel.peer_free if self.rank == 0 else _accel.peer_close)(self.ptr, self.device)
+        self.ptr = None
+
+
+def render_ao_distributed_peer(acc: "_accel.Accel", frame: "_accel.Frame", fb: PeerFramebuffer, stream=None):
+    """The same frame with the gather FUSED into the resolve kernels: every rank's resolve kernel stores its tiles straight into
+    rank 0's framebuffer (ri_b200_render_ao_peer_dev); one barrier says the stores have landed, then rank 0 reads the frame.
+    Returns (framebuffer on rank 0 or None, FrameStats of this rank)."""
+    import torch
+    import torch.distributed as dist
+
+    assert (frame.height, frame.width, 3) == fb.shape
+    f = copy.copy(frame)
+    f.rank, f.world = fb.rank, fb.world
+    if fb.world > 1:
+        dist.barrier(group=fb.group)                   # rank 0 has read the previous frame out of the buffer
+    stats = acc.render_ao_peer_dev(f, fb.ptr, stream)
+    torch.cuda.synchronize()
+    if fb.world > 1:
+        dist.barrier(group=fb.group)
+    rgb = _accel.peer_read(fb.ptr, fb.shape, fb.device) if fb.rank == 0 else None
+    return rgb, stats
+
+
 def render_ao_distributed(acc: "_accel.Accel", frame: "_accel.Frame", rank: int, world: int, group=None, stream=None):
     """Render this rank's tiles on its GPU, gather on rank 0.  Returns (framebuffer or None, FrameStats of this rank)."""
     import torch

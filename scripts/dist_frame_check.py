@@ -30,6 +30,18 @@ for it in range(2):
         rays = sum(float(x[2]) for x in allt); wall = max(float(x[0]) for x in allt)
         print(f"iter {it}: {world} GPU(s) {res}x{res} 16 spp x 64 AO rays on {ntris} tris: {rays/1e6:.1f} Mrays in {wall*1e3:.1f} ms wall "
               f"(device max {max(float(x[1]) for x in allt)*1e3:.1f} ms) -> {rays/wall/1e6:.1f} Mrays/s incl. gather", flush=True)
+# the same frame with the gather fused into the resolve kernels (peer memory)
+fb = distributed.PeerFramebuffer(res, res, rank, world, local)
+for it in range(3):
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    rgb_p, stats_p = distributed.render_ao_distributed_peer(a, fr, fb)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"peer iter {it}: {float(t.item())*1e3:.1f} ms wall, equal to the NCCL-gathered frame: {bool(np.array_equal(rgb_p, rgb))}", flush=True)
+fb.close()
 if rank == 0 and world > 1:
     full, _ = a.render_ao(fr)
     print("equal to single-GPU frame:", bool(np.array_equal(full, rgb)), "mean", float(rgb.mean()), flush=True)

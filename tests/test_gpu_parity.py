@@ -542,3 +542,25 @@ def test_whitted_frame(oracle):
     mask, stats = a.render_sample(fr)                      # ri_transport_sample: white where the eye ray hits
     want, nrays = ot.render_hitmask(ol.frame_params(cam, 96, 72))
     assert stats.nrays == nrays and np.array_equal(mask, want) and 0.05 < mask.mean() < 0.95
+
+
+def test_peer_framebuffer_path_single_rank(golden_dir):
+    """The fused multi-GPU resolve (tiles stored straight into a framebuffer shared over peer memory) with one rank: allocate, render
+    two interleaved half-frames into the SAME buffer as ranks 0 and 1 of a world of two would, read back -- equal to render_ao.
+    (scripts/dist_frame_check.py runs it across real GPUs and processes.)"""
+    _need_gpu()
+    g = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    cam = g["cam"]
+    a = accel.Accel.bind().build(g["tris"], accel.PREC_F32)
+    fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 2, 2, gather_nsamples=16, rng_mode=1, seed=7, precision=accel.PREC_F32)
+    want, _ = a.render_ao(fr)
+    ptr, handle = accel.peer_alloc(160 * 120 * 3 * 4, 0)
+    assert len(handle) == 64
+    import copy
+    for r in (0, 1):
+        f = copy.copy(fr)
+        f.rank, f.world = r, 2
+        a.render_ao_peer_dev(f, ptr)
+    got = accel.peer_read(ptr, (120, 160, 3), 0)
+    accel.peer_free(ptr, 0)
+    assert np.array_equal(got, want)
