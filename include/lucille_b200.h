@@ -194,6 +194,18 @@ int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
                                     ri_b200_frame_stats_t *stats);
 int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
 
+/* rng_mode 0 (the reference's single MT19937 stream, random.c:211-247) on world > 1.  The stream position of a gather ray depends
+ * on how many eye samples hit something in every bucket the reference renders EARLIER (render.c:1131-1146 in spiral order), and
+ * those buckets belong to other ranks: between the eye pass and the gather pass the frame call hands the host this rank's
+ * hit-sample count per bucket (buckets rank, rank + world, ... of the spiral order, in that order) and wants back, for each of
+ * them, the number of hit samples in all buckets of the frame that precede it, plus the frame's total.  The host implements it with
+ * whatever it has between ranks (an all-gather of a few hundred integers: lucille_b200/distributed.py uses torch.distributed;
+ * lucille itself would use ri_parallel_gather + ri_parallel_bcast, parallel.c:102-196).  Return 0, or non-zero to fail the frame.
+ * With it the multi-GPU frame equals the reference's single-thread frame bit for bit, like the one-GPU frame. */
+typedef int (*ri_b200_hit_exchange_fn)(void *user, const uint32_t *bucket_hits, uint32_t nbuckets, uint64_t *bucket_base_out,
+                                       uint64_t *frame_hits_out);
+int ri_b200_set_hit_exchange(ri_b200_accel_t *accel, ri_b200_hit_exchange_fn fn, void *user);
+
 /* fused multi-GPU resolve (one process per GPU of ONE node): rank 0 allocates the framebuffer with ri_b200_peer_alloc ([h][w][3]
  * floats, zeroed) and hands the 64-byte CUDA IPC handle to the other ranks (any transport: torch.distributed, MPI, a pipe); they
  * map it with ri_b200_peer_open.  ri_b200_render_ao_peer_dev renders the buckets of frame->rank and its resolve kernel stores them

@@ -137,6 +137,7 @@ ABI = [
     ("ri_b200_render_ao_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
     ("ri_b200_render_ao_peer_dev", _I, [_P, _P, _P, _P, _P]),
+    ("ri_b200_set_hit_exchange", _I, [_P, _P, _P]),
     ("ri_b200_peer_alloc", _P, [_U64, _I, _P]),
     ("ri_b200_peer_open", _P, [_P, _I]),
     ("ri_b200_peer_close", _I, [_P, _I]),
@@ -455,6 +456,33 @@ class Accel:
                                                     C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
         return stats
 
+    def set_hit_exchange(self, fn):
+        """rng_mode 0 on world > 1 (ri_b200_set_hit_exchange): fn(bucket_hits: np.ndarray[u32]) -> (bucket_base: array of u64, same
+        length; frame_hits: int).  None removes it."""
+        if fn is None:
+            self._hit_cb = None
+            _check(self.lib.ri_b200_set_hit_exchange(self._h(), None, None))
+            return
+
+        def tramp(_user, hits_p, n, base_p, total_p):
+            try:
+                hits = np.ctypeslib.as_array(hits_p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+                base, total = fn(hits)
+                base = np.asarray(base, dtype=np.uint64)
+                if len(base) != n:
+                    return 2
+                for i in range(n):
+                    base_p[i] = int(base[i])
+                total_p[0] = int(total)
+                return 0
+            except Exception:                     # an exception must not unwind through the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._hit_cb = HIT_EXCHANGE_FN(tramp)     # keep the trampoline alive as long as the accelerator uses it
+        _check(self.lib.ri_b200_set_hit_exchange(self._h(), C.cast(self._hit_cb, C.c_void_p), None))
+
     def render_ao_peer_dev(self, frame: Frame, d_rgb_shared: int, stream: Optional[int] = None, want_stats: bool = True):
         """This rank's buckets stored at their framebuffer positions in a buffer shared by the ranks of the node (peer memory)."""
         stats = FrameStats()
@@ -493,6 +521,9 @@ def hdr_encode(rgb, width: int = 0, height: int = 0, device: int = 0) -> bytes:
     if n < 0 or n > cap:
         raise B200Error(last_error() if n < 0 else "hdr buffer too small")
     return out[:n].tobytes()
+
+
+HIT_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
 
 
 def peer_alloc(nbytes: int, device: int = 0):

@@ -73,6 +73,8 @@ struct ri_b200_accel {
     // MT19937 jump-ahead: polynomial table and cached window states at segment starts (frame.cuh)
     uint32_t *d_mt_polys = nullptr, *d_mt_states = nullptr;
     uint32_t  mt_states_cap = 0, mt_states_seed = 0;
+    ri_b200_hit_exchange_fn hit_exchange = nullptr;      // rng_mode 0 over several ranks (frame.cuh)
+    void     *hit_exchange_user = nullptr;
     unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
     std::atomic<unsigned> work_slot{0};   // the _dev entry points may be called from several host threads / streams
     // single-ray path

@@ -26,6 +26,11 @@ struct FrameDev {
     int    rng_mode;
     uint32_t seed;
     double ao_eps;              // shading-point offset along Ns: 1e-6 (ambientocclusion.c:56), 1e-5 for the sun-sky gather (:222)
+    // rng_mode 0 on more than one rank: the frame's hit samples are numbered over ALL ranks' buckets in spiral order, so that every
+    // gather ray draws the same two words of the single MT19937 stream as in the reference.  delta = (hit samples of the whole
+    // frame before bucket b) - (hit samples of this rank before bucket b); both null when world == 1.
+    const uint32_t  *pix_bucket = nullptr;       // [pixel of this rank] -> index among this rank's buckets
+    const long long *bucket_delta = nullptr;     // [bucket of this rank]
 };
 
 // camera.c:248-352 (perspective) + render.c:770-781 normalise -------------------------------------
@@ -408,7 +413,9 @@ __device__ __forceinline__ void ao_direction(const FrameDev &F, const uint32_t r
     const uint32_t j = k / (uint32_t)F.ntheta, i = k - j * (uint32_t)F.ntheta;
     double r0, r1;
     if (F.rng_mode == 0) {
-        const uint64_t base = (uint64_t)2 * N * rank + 2 * k;               // draw order z0 then z1, ambientocclusion.c:91-92
+        uint64_t grank = rank;
+        if (F.bucket_delta) grank = (uint64_t)((long long)rank + F.bucket_delta[F.pix_bucket[rank_sample[rank] / (uint32_t)F.spp]]);
+        const uint64_t base = (uint64_t)2 * N * grank + 2 * k;              // draw order z0 then z1, ambientocclusion.c:91-92
         r0 = (double)mt_stream[base] * 2.3283064365386963e-10;               // random.c:244
         r1 = (double)mt_stream[base + 1] * 2.3283064365386963e-10;
     } else {
@@ -558,6 +565,23 @@ __global__ void resolve_kernel(const FrameDev F, const uint32_t *__restrict__ pi
     dst[0] = f; dst[1] = f; dst[2] = f;
 }
 
+// hit samples per bucket of this rank (one CTA per bucket; samples of a bucket are contiguous in visiting order)
+__global__ void __launch_bounds__(256)
+bucket_hits_kernel(const uint32_t *__restrict__ hit_prim, const uint32_t *__restrict__ bucket_first_pixel, uint32_t spp,
+                   uint32_t *__restrict__ bucket_hits)
+{
+    __shared__ uint32_t total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    const uint64_t lo = (uint64_t)bucket_first_pixel[blockIdx.x] * spp, hi = (uint64_t)bucket_first_pixel[blockIdx.x + 1] * spp;
+    uint32_t c = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += 256) c += hit_prim[i] != 0xffffffffu;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+    __syncthreads();
+    if (threadIdx.x == 0) bucket_hits[blockIdx.x] = total;
+}
+
 // ---- host helpers ---------------------------------------------------------------------------------
 // spiral.c:97-140 NthBucketSpiral
 }  // namespace b200
@@ -583,14 +607,16 @@ static void nth_bucket_spiral(int n, int nxb, int nyb, int *bx, int *by)
 }
 
 // pixel visiting order of the reference for this rank's buckets: render.c:582-710 + 1131-1146
-static void pixel_order(const ri_b200_frame_t &f, std::vector<uint32_t> &pix)
+static void pixel_order(const ri_b200_frame_t &f, std::vector<uint32_t> &pix, std::vector<uint32_t> *bucket_first = nullptr)
 {
     const int bs = f.bucket_size > 0 ? f.bucket_size : 32;
     const int nxb = (f.width + bs - 1) / bs, nyb = (f.height + bs - 1) / bs;
     const int world = f.world > 0 ? f.world : 1;
     pix.clear();
+    if (bucket_first) bucket_first->clear();
     for (int n = 0; n < nxb * nyb; ++n) {
         if (n % world != f.rank) continue;
+        if (bucket_first) bucket_first->push_back((uint32_t)pix.size());
         int bx, by;
         nth_bucket_spiral(n, nxb, nyb, &bx, &by);
         const int x0 = bx * bs, y0 = by * bs;
@@ -599,6 +625,7 @@ static void pixel_order(const ri_b200_frame_t &f, std::vector<uint32_t> &pix)
         for (int v = y0; v < y0 + h; ++v)
             for (int u = x0; u < x0 + w; ++u) pix.push_back((uint32_t)u | ((uint32_t)v << 16));
     }
+    if (bucket_first) bucket_first->push_back((uint32_t)pix.size());
 }
 
 // render.c:830-917 sample_subpixel / init_sigma (periodx masks both indices -- reproduced)
@@ -687,9 +714,13 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
 {
     std::vector<uint32_t> pix;
     std::vector<double> jit;
-    pixel_order(f, pix);
+    // one MT19937 stream over several ranks: the per-bucket hit counts are exchanged through the host's callback (below)
+    const bool shared_stream = f.rng_mode == 0 && f.world > 1;
+    std::vector<uint32_t> bfirst;
+    pixel_order(f, pix, shared_stream ? &bfirst : nullptr);
     jitter_table(f.xsamples, f.ysamples, jit);
     const uint64_t npix = pix.size();
+    const uint32_t nbuckets = shared_stream ? (uint32_t)bfirst.size() - 1 : 0;
     // the sun-sky transport gathers with a fixed 8 x 8 pattern whatever Option "gather" says (ambientocclusion.c:371-374)
     // ... and the dirt-map transport with a fixed 4 x 4 one (dirtmap.c:261-265)
     const int ntheta = sky ? 8 : (dirtmap ? 4 : f.ntheta), nphi = sky ? 8 : (dirtmap ? 4 : f.nphi);
@@ -723,8 +754,12 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     uint32_t *d_pix, *d_prim, *d_tiles, *d_srank, *d_ranks;
     double *d_jit;
     Real *d_t;
-    if (frame_buf(a, 0, (npix + 1) * 4 + jit.size() * 8 + 64, &p)) return -1;
-    d_jit = (double *)p; d_pix = (uint32_t *)(d_jit + jit.size());
+    if (frame_buf(a, 0, (npix + 1) * 4 + jit.size() * 8 + 64 + (shared_stream ? npix * 4 + ((uint64_t)nbuckets + 1) * 16 : 0), &p)) return -1;
+    d_jit = (double *)p;
+    long long *d_bdelta = (long long *)(d_jit + jit.size());                 // shared_stream only: [nbuckets]
+    d_pix = (uint32_t *)(d_bdelta + nbuckets);
+    uint32_t *d_pixb = d_pix + npix + 1, *d_bfirst = d_pixb + (shared_stream ? npix : 0), *d_bhits = d_bfirst + nbuckets + 1;
+    F.pix_bucket = nullptr; F.bucket_delta = nullptr;
     const bool textured = a->d_tex != nullptr && !sky;                   // the sun-sky branch does not look at the texture (ambientocclusion.c:369-376)
     const bool with_normals = make_view<Real>(a).normals != nullptr, with_uv = with_normals || textured;
     if (frame_buf(a, 1, (nsamples + 1) * sizeof(Real) * (with_uv ? 3 : 1), &p)) return -1;
@@ -739,6 +774,14 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     if (npix) {
         CUDA_OK(cudaMemcpyAsync(d_jit, jit.data(), jit.size() * 8, cudaMemcpyHostToDevice, st));
         CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<uint32_t> pixb;
+    if (shared_stream && npix) {
+        pixb.resize(npix);
+        for (uint32_t b = 0; b < nbuckets; ++b)
+            for (uint32_t q = bfirst[b]; q < bfirst[b + 1]; ++q) pixb[q] = b;
+        CUDA_OK(cudaMemcpyAsync(d_pixb, pixb.data(), npix * 4, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_bfirst, bfirst.data(), ((size_t)nbuckets + 1) * 4, cudaMemcpyHostToDevice, st));
     }
     // packed: 0 = full framebuffer, cleared first; 1 = this rank's pixels packed in visiting order; 2 = full framebuffer addressing
     // WITHOUT clearing -- the buffer is shared by the ranks of a node (peer memory), each storing its own tiles into it
@@ -760,6 +803,34 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         CUDA_OK(cudaEventRecord(a->ev[1], st));
     }
 
+    uint64_t frame_hits = nhits;                 // hit samples of the whole frame (== nhits on one rank)
+    if (shared_stream) {
+        // ri_b200_set_hit_exchange: this rank's hit samples per bucket go out, the frame-wide count before each of them comes back
+        std::vector<uint32_t> bhits(nbuckets, 0u);
+        std::vector<uint64_t> bbase(nbuckets, 0ull);
+        if (nbuckets && nsamples) {
+            bucket_hits_kernel<<<nbuckets, 256, 0, st>>>(d_prim, d_bfirst, (uint32_t)spp, d_bhits);
+            LAUNCHED();
+            CUDA_OK(cudaMemcpyAsync(bhits.data(), d_bhits, (size_t)nbuckets * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaStreamSynchronize(st));
+        }
+        if (a->hit_exchange(a->hit_exchange_user, bhits.data(), nbuckets, bbase.data(), &frame_hits) != 0)
+            return fail("the hit-count exchange callback failed");
+        std::vector<long long> delta(nbuckets);
+        uint64_t before = 0;
+        for (uint32_t b = 0; b < nbuckets; ++b) {
+            if (bbase[b] + bhits[b] > frame_hits) return fail("hit-count exchange: bucket %u ends beyond the frame's hit samples", b);
+            delta[b] = (long long)bbase[b] - (long long)before;
+            before += bhits[b];
+        }
+        if (before != nhits) return fail("hit-count exchange: bucket sums disagree with the scan");
+        if (nbuckets) {
+            CUDA_OK(cudaMemcpyAsync(d_bdelta, delta.data(), (size_t)nbuckets * 8, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaStreamSynchronize(st));                                    // delta is a local
+            F.pix_bucket = d_pixb; F.bucket_delta = d_bdelta;
+        }
+    }
+
     const uint64_t nao_rays = (uint64_t)nhits * (uint64_t)N;
     double *d_texcol = nullptr;
     Real *d_rec = nullptr;
@@ -768,7 +839,8 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     d_rec = (Real *)p;
     if (frame_buf(a, 4, ((uint64_t)nhits + 1) * 4, &p)) return -1;
     d_occ = (uint32_t *)p;
-    const uint64_t mt_blocks = f.rng_mode == 0 ? (2 * nao_rays + kMtN - 1) / kMtN : 0;
+    // on several ranks every rank generates the stream of the whole frame (interleaved buckets touch nearly every segment anyway)
+    const uint64_t mt_blocks = f.rng_mode == 0 && nhits ? (2 * frame_hits * (uint64_t)N + kMtN - 1) / kMtN : 0;
     if (frame_buf(a, 5, (mt_blocks * kMtN + 4) * 4, &p)) return -1;
     d_mt = (uint32_t *)p;
     const uint32_t mt_segments = (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks);
@@ -871,8 +943,8 @@ static int check_frame(const ri_b200_accel *a, const ri_b200_frame_t *f)
     if (f->width < 1 || f->height < 1 || f->width > 65535 || f->height > 65535) return fail("bad frame size");
     if (f->xsamples < 1 || f->ysamples < 1 || f->ntheta < 1 || f->nphi < 1) return fail("bad sample counts");
     if (f->world < 1 || f->rank < 0 || f->rank >= f->world) return fail("bad rank/world");
-    if (f->rng_mode == 0 && f->world != 1)
-        return fail("rng_mode 0 (single MT19937 stream in reference order) is defined for world == 1 only");
+    if (f->rng_mode == 0 && f->world != 1 && !a->hit_exchange)
+        return fail("rng_mode 0 (single MT19937 stream in reference order) on world > 1 needs ri_b200_set_hit_exchange()");
     if (f->precision != RI_B200_PREC_F32 && f->precision != RI_B200_PREC_F64) return fail("bad precision");
     return need(a, (uint32_t)f->precision);
 }
@@ -916,6 +988,14 @@ extern "C" int ri_b200_render_ao_peer_dev(ri_b200_accel_t *a, const ri_b200_fram
     cudaStream_t st = stream ? (cudaStream_t)stream : a->stream;
     if (f->precision == RI_B200_PREC_F64) return render_ao_impl<double>(a, *f, d_rgb_shared, st, stats, nullptr, 0, 2);
     return render_ao_impl<float>(a, *f, d_rgb_shared, st, stats, nullptr, 0, 2);
+}
+
+extern "C" int ri_b200_set_hit_exchange(ri_b200_accel_t *a, ri_b200_hit_exchange_fn fn, void *user)
+{
+    if (!a) return fail("null accelerator");
+    std::lock_guard<std::mutex> lock(a->mu);
+    a->hit_exchange = fn; a->hit_exchange_user = user;
+    return 0;
 }
 
 extern "C" void *ri_b200_peer_alloc(uint64_t bytes, int device, uint8_t handle_out[64])

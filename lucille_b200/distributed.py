@@ -5,7 +5,9 @@ workers (src/render/render.c:582-710, 1043-1105), and its compiled-out MPI layer
 (src/base/parallel.c:45-232, render.c:468-514).  Here bucket ``b`` of the spiral order belongs to rank ``b % world``;
 every rank renders its pixels with no inter-GPU traffic and writes them PACKED, in visiting order, straight into its NCCL
 send buffer (the resolve kernel does it: no staging copy); rank 0 gathers the slabs over NVLink and scatters them into the
-framebuffer.  torch.distributed is plumbing only (process group + the collective).
+framebuffer -- or, fused (PeerFramebuffer / render_ao_distributed_peer), every rank's resolve kernel stores its tiles straight into
+rank 0's framebuffer over NVLink peer memory and no data collective runs at all.  torch.distributed is plumbing only (process
+group, the 64-byte IPC handle, barriers, and the per-bucket hit counts of the shared MT19937 stream mode).
 """
 from __future__ import annotations
 
@@ -62,6 +64,32 @@ def gather_frame(local_slab, frame: "_accel.Frame", rank: int, world: int, group
     return scatter_tiles(frame.width, frame.height, lists, [b.cpu().numpy() for b in bufs])
 
 
+def bucket_bases(all_hits, world: int):
+    """all_hits[r][i] = hit samples of bucket r + i*world (rank r's i-th bucket; ranks with one bucket fewer are padded with 0).
+    Returns bases[r][i] = hit samples in all buckets that precede bucket r + i*world in spiral order, and the frame's total."""
+    all_hits = np.asarray(all_hits, dtype=np.int64)              # [world][per_rank]
+    order = all_hits.T.reshape(-1)                               # bucket b = i*world + r
+    ex = np.cumsum(order) - order
+    return ex.reshape(-1, world).T.astype(np.uint64), int(order.sum())
+
+
+def hit_exchange(rank: int, world: int, group=None, device=None):
+    """The ri_b200_set_hit_exchange callback over torch.distributed: one all-gather of the per-bucket hit counts."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(hits):
+        n = torch.tensor([len(hits)], dtype=torch.int64, device=device)
+        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
+        mine = torch.zeros(int(n.item()), dtype=torch.int64, device=device)
+        mine[:len(hits)] = torch.from_numpy(hits.astype(np.int64))
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        bases, total = bucket_bases(torch.stack(parts).cpu().numpy(), world)
+        return bases[rank][:len(hits)], total
+    return fn
+
+
 class PeerFramebuffer:
     """One framebuffer on rank 0's GPU, mapped by every rank of the node (CUDA IPC, NVLink / NVSwitch peer memory).  Made once and
     reused frame after frame: mapping a handle costs far more than a frame.  torch.distributed carries the 64-byte handle."""
@@ -99,6 +127,8 @@ def render_ao_distributed_peer(acc: "_accel.Accel", frame: "_accel.Frame", fb: P
     assert (frame.height, frame.width, 3) == fb.shape
     f = copy.copy(frame)
     f.rank, f.world = fb.rank, fb.world
+    if f.rng_mode == 0 and fb.world > 1:
+        acc.set_hit_exchange(hit_exchange(fb.rank, fb.world, fb.group, device="cuda"))
     if fb.world > 1:
         dist.barrier(group=fb.group)                   # rank 0 has read the previous frame out of the buffer
     stats = acc.render_ao_peer_dev(f, fb.ptr, stream)
@@ -115,6 +145,8 @@ def render_ao_distributed(acc: "_accel.Accel", frame: "_accel.Frame", rank: int,
 
     f = copy.copy(frame)
     f.rank, f.world = rank, world
+    if f.rng_mode == 0 and world > 1:              # the reference's single MT19937 stream, shared by the ranks (bit-exact frames)
+        acc.set_hit_exchange(hit_exchange(rank, world, group, device="cuda"))
     npix = len(_accel.frame_pixels(f))
     slab = torch.empty((max(npix, 1), 3), dtype=torch.float32, device="cuda")
     stats = acc.render_ao_tiles_dev(f, slab, stream)

@@ -41,6 +41,15 @@ for it in range(3):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"peer iter {it}: {float(t.item())*1e3:.1f} ms wall, equal to the NCCL-gathered frame: {bool(np.array_equal(rgb_p, rgb))}", flush=True)
+# the reference's single MT19937 stream shared by the ranks (hit counts all-gathered between the eye pass and the gather pass)
+fr0 = accel.make_frame(c2w.reshape(16), 1.0 / math.tan(math.radians(40.0) / 2), False, res, res, 2, 2, 64, rng_mode=0, seed=4357, precision=accel.PREC_F32)
+if world > 1: dist.barrier()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+rgb0, _ = distributed.render_ao_distributed_peer(a, fr0, fb)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+if rank == 0:
+    one0, _ = a.render_ao(fr0)
+    print(f"MT19937 stream over {world} rank(s): {dt*1e3:.1f} ms wall, equal to the single-GPU rng_mode-0 frame: {bool(np.array_equal(rgb0, one0))}", flush=True)
 fb.close()
 if rank == 0 and world > 1:
     full, _ = a.render_ao(fr)

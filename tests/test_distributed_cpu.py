@@ -77,3 +77,53 @@ def test_gather_over_gloo_world2():
     ys, xs = np.mgrid[0:h, 0:w]
     want = np.stack([xs, ys, xs * 1000 + ys], axis=-1).astype(np.float32)[::-1]   # row H-1-y
     assert np.array_equal(rgb, want)
+
+
+def test_bucket_bases_is_the_spiral_prefix():
+    """distributed.bucket_bases: with buckets dealt round-robin (b % world == rank), the base of a bucket is the number of hit
+    samples in all buckets before it in spiral order -- the position of its first gather ray in the single MT19937 stream."""
+    rng = np.random.default_rng(3)
+    for world, nb in ((1, 7), (2, 7), (3, 300), (8, 300)):
+        hits = rng.integers(0, 9217, size=nb)
+        per = (nb + world - 1) // world
+        padded = np.zeros((world, per), dtype=np.int64)
+        for b in range(nb):
+            padded[b % world, b // world] = hits[b]
+        bases, total = distributed.bucket_bases(padded, world)
+        want = np.cumsum(hits) - hits
+        assert total == hits.sum()
+        for b in range(nb):
+            assert int(bases[b % world, b // world]) == int(want[b])
+
+
+def _exchange_worker(rank, world, port, nb, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hits = (np.arange(nb, dtype=np.uint32) * 37 + 5) % 1000            # the frame's per-bucket counts, known to the test
+    mine = hits[rank::world]
+    base, total = distributed.hit_exchange(rank, world)(mine)
+    q.put((rank, np.asarray(base), total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_hit_exchange_over_gloo_world2():
+    """The callback a multi-rank rng_mode-0 frame calls between its eye pass and its gather pass: ranks with different bucket
+    counts (7 buckets over 2 ranks) get the frame-wide prefix of their own buckets."""
+    nb, world = 7, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, nb, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((r, (b, t)) for r, b, t in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    hits = (np.arange(nb, dtype=np.int64) * 37 + 5) % 1000
+    want = np.cumsum(hits) - hits
+    for r in range(world):
+        assert got[r][1] == hits.sum()
+        assert np.array_equal(got[r][0].astype(np.int64), want[r::world])

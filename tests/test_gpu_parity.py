@@ -564,3 +564,64 @@ def test_peer_framebuffer_path_single_rank(golden_dir):
     got = accel.peer_read(ptr, (120, 160, 3), 0)
     accel.peer_free(ptr, 0)
     assert np.array_equal(got, want)
+
+
+def test_mt_stream_frame_over_three_ranks(golden_dir):
+    """rng_mode 0 on world > 1 (RNG-stream parity across GPUs): three ranks -- here three accelerators driven by three
+    threads on one GPU, exchanging their per-bucket hit counts through ri_b200_set_hit_exchange -- each render their buckets of
+    ambient_occlusion.rib; the assembled frame is the reference's single-thread framebuffer (and the one-rank frame, bit for bit)."""
+    _need_gpu()
+    import threading
+    from lucille_b200 import distributed
+    sc = np.load(os.path.join(golden_dir, "c1_scene.npz"))
+    g = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))
+    cam = sc["cam"]
+    world = 3
+    one = accel.Accel.bind().build(sc["tris"], accel.PREC_F64)
+    full, st1 = one.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 3, 3, gather_nsamples=64))
+    with pytest.raises(accel.B200Error):                       # without the exchange the frame refuses, it does not guess
+        one.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 3, 3, gather_nsamples=64, rank=0, world=world))
+
+    barrier = threading.Barrier(world)
+    posted, parts, errors = {}, {}, []
+
+    def exchange(rank):
+        def fn(hits):
+            posted[rank] = hits.astype(np.int64)
+            barrier.wait(timeout=60)
+            per = max(len(v) for v in posted.values())
+            table = np.zeros((world, per), dtype=np.int64)
+            for r, v in posted.items():
+                table[r, :len(v)] = v
+            bases, total = distributed.bucket_bases(table, world)
+            barrier.wait(timeout=60)
+            return bases[rank][:len(hits)], total
+        return fn
+
+    def run(rank):
+        try:
+            a = accel.Accel.bind().build(sc["tris"], accel.PREC_F64)
+            a.set_hit_exchange(exchange(rank))
+            fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 160, 120, 3, 3, gather_nsamples=64, rank=rank, world=world)
+            parts[rank] = a.render_ao(fr)
+        except Exception as e:                                  # noqa: BLE001 -- reported below
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    acc = np.zeros_like(full)
+    nrays = 0
+    for r in range(world):
+        rgb, st = parts[r]
+        assert np.all((rgb == 0) | (acc == 0))
+        acc += rgb
+        nrays += st.nrays
+    assert nrays == st1.nrays == int(g["nrays"])
+    assert np.array_equal(acc, full)
+    rmse = float(np.sqrt(np.mean((acc.astype(np.float64) - g["rgb"].astype(np.float64)) ** 2)))
+    assert rmse <= RMSE_TOL, rmse
