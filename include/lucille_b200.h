@@ -194,6 +194,32 @@ int     ri_b200_render_ao_tiles_dev(ri_b200_accel_t *accel, const ri_b200_frame_
                                     ri_b200_frame_stats_t *stats);
 int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_t capacity);
 
+/* ---- hemisphere gathers at shading points: the per-point loops of three more ri_raytrace callers, batched.
+ * points = [n][6] doubles (P, N); out3 = [n][3] doubles; results equal one reference call per point, in order, with the
+ * generator seeded `seed` (4357 is the reference's) and `stream_offset` words already drawn before point 0:
+ *   RI_B200_GATHER_OCCLUSION  float occlusion(status, P, N, nsamples)                      shader.c:680-768 (all three channels)
+ *   RI_B200_GATHER_IBL        ri_ibl_sample_cosweight(power, N, nsamples, ray, P, eye, l)  ibl.c:53-228, l->texture = env_rgba
+ *   RI_B200_GATHER_DOME       ri_domelight_sample(power, hemi, nsamples, ray, P, eye, l)   ibl.c:231-389, l->col, l->intensity
+ * (Monte Carlo branches: Option "use_qmc" is 0 by default, option.c:139.)  nrays_out (may be NULL) = rays traced.
+ * trace() (shader.c:895-976) needs no entry of its own: it is one closest-hit query + hit state + environment lookup on a miss --
+ * ri_b200_intersect_batch_f64 / ri_b200_state_ext_batch_f64 -- followed by the hit geometry's shader procedure, which stays on the host. */
+#define RI_B200_GATHER_OCCLUSION 0
+#define RI_B200_GATHER_IBL       1
+#define RI_B200_GATHER_DOME      2
+typedef struct {
+    int32_t  kind;
+    int32_t  nsamples;
+    uint32_t seed;
+    uint32_t pad_;
+    uint64_t stream_offset;
+    const float *env_rgba;        /* IBL: angular map [env_height][env_width][4] (ri_texture_t.data), host memory */
+    int32_t  env_width, env_height;
+    double   col[3];              /* DOME: ri_light_t.col */
+    double   intensity;           /* DOME: ri_light_t.intensity */
+} ri_b200_gather_t;
+int ri_b200_gather_points_f64(ri_b200_accel_t *accel, const ri_b200_gather_t *gather, const double *points, uint64_t n, double *out3,
+                              uint64_t *nrays_out);
+
 /* rng_mode 0 (the reference's single MT19937 stream, random.c:211-247) on world > 1.  The stream position of a gather ray depends
  * on how many eye samples hit something in every bucket the reference renders EARLIER (render.c:1131-1146 in spiral order), and
  * those buckets belong to other ranks: between the eye pass and the gather pass the frame call hands the host this rank's

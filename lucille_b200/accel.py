@@ -138,6 +138,7 @@ ABI = [
     ("ri_b200_frame_pixels", C.c_int64, [_P, _P, C.c_int64]),
     ("ri_b200_render_ao_peer_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_set_hit_exchange", _I, [_P, _P, _P]),
+    ("ri_b200_gather_points_f64", _I, [_P, _P, _P, _U64, _P, _P]),
     ("ri_b200_peer_alloc", _P, [_U64, _I, _P]),
     ("ri_b200_peer_open", _P, [_P, _I]),
     ("ri_b200_peer_close", _I, [_P, _I]),
@@ -456,6 +457,25 @@ class Accel:
                                                     C.c_void_p(stream) if stream else None, C.byref(stats) if want_stats else None))
         return stats
 
+    def gather_points(self, kind: int, nsamples: int, points6, env=None, col=(1.0, 1.0, 1.0), intensity: float = 1.0,
+                      seed: int = 4357, stream_offset: int = 0):
+        """Hemisphere gathers at shading points (P, N) (ri_b200_gather_points_f64): GATHER_OCCLUSION = the occlusion() shadeop,
+        GATHER_IBL = ri_ibl_sample_cosweight with the angular map ``env`` [h,w,4], GATHER_DOME = ri_domelight_sample.
+        Returns ([n,3] float64, rays traced)."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        g = Gather()
+        g.kind, g.nsamples, g.seed, g.stream_offset = int(kind), int(nsamples), int(seed), int(stream_offset)
+        if env is not None:
+            env = np.ascontiguousarray(env, dtype=np.float32)
+            g.env_rgba, g.env_width, g.env_height = env.ctypes.data, env.shape[1], env.shape[0]
+        for i in range(3):
+            g.col[i] = float(col[i])
+        g.intensity = float(intensity)
+        out = np.zeros((len(pts), 3), dtype=np.float64)
+        nrays = C.c_uint64(0)
+        _check(self.lib.ri_b200_gather_points_f64(self._h(), C.byref(g), _ptr(pts), len(pts), _ptr(out), C.byref(nrays)))
+        return out, nrays.value
+
     def set_hit_exchange(self, fn):
         """rng_mode 0 on world > 1 (ri_b200_set_hit_exchange): fn(bucket_hits: np.ndarray[u32]) -> (bucket_base: array of u64, same
         length; frame_hits: int).  None removes it."""
@@ -521,6 +541,16 @@ def hdr_encode(rgb, width: int = 0, height: int = 0, device: int = 0) -> bytes:
     if n < 0 or n > cap:
         raise B200Error(last_error() if n < 0 else "hdr buffer too small")
     return out[:n].tobytes()
+
+
+GATHER_OCCLUSION, GATHER_IBL, GATHER_DOME = 0, 1, 2
+
+
+class Gather(C.Structure):
+    """ri_b200_gather_t"""
+    _fields_ = [("kind", C.c_int32), ("nsamples", C.c_int32), ("seed", C.c_uint32), ("pad_", C.c_uint32), ("stream_offset", C.c_uint64),
+                ("env_rgba", C.c_void_p), ("env_width", C.c_int32), ("env_height", C.c_int32), ("col", C.c_double * 3),
+                ("intensity", C.c_double)]
 
 
 HIT_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))

@@ -1067,6 +1067,72 @@ void orc_transport_whitted(const orc_tree *T, const float *env, int ew, int eh, 
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ hemisphere gathers at shading points
+ * The per-point loops of three more ri_raytrace callers, Monte Carlo branches (Option use_qmc defaults to 0, option.c:139):
+ *   kind 0  occlusion() shadeop            shader.c:680-768   coverage / nsamples (float)
+ *   kind 1  ri_ibl_sample_cosweight        ibl.c:53-228       pi * sum(Le / pi) / (ntheta * nphi), Le = angular-map lookup on a miss
+ *   kind 2  ri_domelight_sample            ibl.c:231-389      pi * sum(col * intensity / pi) / nsamples on misses
+ * points = [n][6] (P, N); one MT19937 stream (randomMT / randomMT2, same generator and seed, random.c:163-247) over the points in
+ * order, 2 draws per ray whether it hits or not. */
+void orc_point_gather(const orc_tree *T, int kind, int nsamples, uint32_t seed, const double *points, uint64_t n,
+                      const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out)
+{
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t p, nrays = 0;
+    int ntheta, nphi, i, j, k;
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, seed);
+    if (kind == 0) ntheta = (int)((float)nsamples / 3.0);      /* shader.c:710 (nsamples is a float there) */
+    else ntheta = (int)(nsamples / 3.0);                       /* ibl.c:160, 326 */
+    ntheta = (int)sqrt((double)ntheta);
+    if (ntheta < 1) ntheta = 1;
+    if (kind != 0 && ntheta > 128) ntheta = 128;               /* MAX_HEMISAMPLE, ibl.h:20 */
+    nphi = 3 * ntheta;
+    for (p = 0; p < n; p++) {
+        const double *P = points + 6 * p, *N = P + 3;
+        double basis[3][3], dpower[3] = { 0.0, 0.0, 0.0 }, org[3], dirl[3], dir[3], theta, phi, t, uu, vv;
+        uint32_t prim;
+        int coverage = 0, hit;
+        ortho_basis_f64(basis, N);
+        for (j = 0; j < nphi; j++) {
+            for (i = 0; i < ntheta; i++) {
+                if (kind == 0) theta = sqrt((double)i + mt_next(&rng)) / (double)ntheta;           /* shader.c:731 */
+                else theta = sqrt(((double)i + mt_next(&rng)) / ntheta);                           /* ibl.c:174, 337 */
+                phi = 2.0 * M_PI * ((double)j + mt_next(&rng)) / (double)nphi;
+                dirl[0] = cos(phi) * theta;
+                dirl[1] = sin(phi) * theta;
+                dirl[2] = sqrt(1.0 - theta * theta);
+                for (k = 0; k < 3; k++)
+                    dir[k] = dirl[0] * basis[0][k] + dirl[1] * basis[1][k] + dirl[2] * basis[2][k];
+                normalize_f64(dir);
+                for (k = 0; k < 3; k++) org[k] = P[k];
+                if (kind == 0) for (k = 0; k < 3; k++) org[k] += 0.0001 * dir[k];                 /* shader.c:750-752 */
+                if (kind == 1) for (k = 0; k < 3; k++) org[k] += N[k] * 0.0001;                   /* ibl.c:92-94 */
+                nrays++;
+                hit = T->empty ? 0 : trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL);
+                if (kind == 0) {
+                    if (hit) coverage++;
+                } else if (!hit) {
+                    double rad[4], brdf = 1.0 / M_PI;
+                    if (kind == 1) ibl_fetch(env, ew, eh, dir, rad);
+                    else for (k = 0; k < 3; k++) rad[k] = col3[k] * intensity;
+                    for (k = 0; k < 3; k++) dpower[k] += rad[k] * brdf;
+                }
+            }
+        }
+        if (kind == 0) {
+            if (coverage > nsamples) coverage = nsamples;
+            out3[3 * p] = out3[3 * p + 1] = out3[3 * p + 2] = (double)(float)((double)coverage / (double)(float)nsamples);
+        } else if (kind == 1) {
+            for (k = 0; k < 3; k++) out3[3 * p + k] = M_PI * dpower[k] / (double)(ntheta * nphi);
+        } else {
+            for (k = 0; k < 3; k++) out3[3 * p + k] = M_PI * dpower[k] / (double)nsamples;
+        }
+    }
+    if (nrays_out) *nrays_out = nrays;
+}
+
 void orc_render_whitted(const orc_tree *T, const orc_frame_t *f, const float *env, int ew, int eh, float *rgb, uint64_t *nrays_out)
 {
     int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);

@@ -218,4 +218,8 @@ uint64_t orc_splitmix64(uint64_t x);
 #ifdef __cplusplus
 }
 #endif
+/* hemisphere gathers at shading points: shader.c occlusion() (kind 0), ri_ibl_sample_cosweight (1), ri_domelight_sample (2) */
+void orc_point_gather(const orc_tree *T, int kind, int nsamples, uint32_t seed, const double *points, uint64_t n,
+                      const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out);
+
 #endif

@@ -427,6 +427,48 @@ void lref_transport_batch(void *h, int which, const double *rays, uint64_t n, do
     render->scene = saved;
 }
 
+/* The reference's own per-point gathers: occlusion() shadeop (shader.c:680-768), ri_ibl_sample_cosweight (ibl.c:53-228, needs
+ * lref_set_envmap first), ri_domelight_sample (ibl.c:231-389).  points = [n][6] (P, N). */
+#include "shader.h"
+#include "ibl.h"
+extern void seedMT(unsigned long seed);
+void lref_point_gather(void *h, int kind, int nsamples, const double *points, uint64_t n, const double *col3, double intensity,
+                       double *out3)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_render_t *render = ri_render_get();
+    ri_scene_t *saved = render->scene;
+    static ri_hemisphere_t hemi;
+    ri_status_t status;
+    ri_ray_t inray;
+    ri_light_t *dome = ri_light_new();
+    ri_vector_t P, N, eye, power;
+    uint64_t i;
+    int k;
+    render->scene = s->scene;
+    seedMT((unsigned long)4357);
+    seedMT2((unsigned long)4357, 0);
+    memset(&status, 0, sizeof(status));
+    memset(&inray, 0, sizeof(inray));
+    memset(eye, 0, sizeof(eye));
+    if (col3) { for (k = 0; k < 3; k++) dome->col[k] = col3[k]; dome->col[3] = 1.0; }
+    dome->intensity = intensity;
+    for (i = 0; i < n; i++) {
+        for (k = 0; k < 3; k++) { P[k] = points[6 * i + k]; N[k] = points[6 * i + 3 + k]; }
+        P[3] = 1.0; N[3] = 0.0;
+        if (kind == 0) {
+            power[0] = power[1] = power[2] = (double)occlusion(&status, P, N, (float)nsamples);
+        } else if (kind == 1) {
+            ri_ibl_sample_cosweight(power, N, nsamples, &inray, P, eye, s->scene->envmap_light);
+        } else {
+            for (k = 0; k < 4; k++) hemi.basis[2][k] = N[k];
+            ri_domelight_sample(power, &hemi, nsamples, &inray, P, eye, dome);
+        }
+        for (k = 0; k < 3; k++) out3[3 * i + k] = power[k];
+    }
+    render->scene = saved;
+}
+
 /* reference traversal counters (only meaningful in libluciref_stat.so; bvh.c:146,686-688) */
 extern ri_bvh_stat_traversal_t g_stattrav;
 void lref_stats_reset(void) { memset(&g_stattrav, 0, sizeof(g_stattrav)); }

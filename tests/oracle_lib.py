@@ -285,6 +285,18 @@ class OracleTree:
         self.lib.orc_transport_batch(self.h, which, ntheta, nphi, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out))
         return out
 
+    def point_gather(self, kind: int, nsamples: int, points6: np.ndarray, env=None, col=(1.0, 1.0, 1.0), intensity=1.0, seed=4357):
+        """Hemisphere gather at shading points (P, N): 0 occlusion() shadeop, 1 ri_ibl_sample_cosweight, 2 ri_domelight_sample."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        c = np.ascontiguousarray(col, dtype=np.float64)
+        out = np.zeros((len(pts), 3), dtype=np.float64)
+        nrays = C.c_uint64(0)
+        self.lib.orc_point_gather(self.h, kind, nsamples, seed, _ptr(pts), C.c_uint64(len(pts)), None if env is None else _ptr(env),
+                                  0 if env is None else env.shape[1], 0 if env is None else env.shape[0], _ptr(c), C.c_double(intensity),
+                                  _ptr(out), C.byref(nrays))
+        return out, nrays.value
+
     def transport_whitted(self, rays6: np.ndarray, env):
         """Radiance per eye ray of the Whitted refraction tracer with the angular-map environment ``env`` ([h,w,4] float32 or None)."""
         rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
@@ -365,6 +377,8 @@ class Oracle:
         lib.orc_texture_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_ao_textured.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_point_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -485,6 +499,16 @@ class ReferenceScene:
             self.lib.lref_transport_batch(self.h, which, _ptr(rays6), C.c_uint64(len(rays6)), _ptr(out))
         return out
 
+    def point_gather(self, kind: int, nsamples: int, points6: np.ndarray, col=(1.0, 1.0, 1.0), intensity=1.0) -> np.ndarray:
+        """The compiled reference's occlusion() shadeop (0), ri_ibl_sample_cosweight (1, after set_envmap) or ri_domelight_sample (2),
+        one call per shading point (P, N), generators reseeded to 4357 first."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        c = np.ascontiguousarray(col, dtype=np.float64)
+        out = np.zeros((len(pts), 3), dtype=np.float64)
+        with _quiet():
+            self.lib.lref_point_gather(self.h, kind, nsamples, _ptr(pts), C.c_uint64(len(pts)), _ptr(c), C.c_double(intensity), _ptr(out))
+        return out
+
     def set_attributes(self, colors, st, geom_flags):
         """colors [n,3,3], st [n,3,2] (either may be None); geom_flags per geom: 1 Cs, 2 shared st, 4 unshared st, 8 two-sided."""
         c = None if colors is None else np.ascontiguousarray(colors, dtype=np.float64)
@@ -528,6 +552,7 @@ class Reference:
         lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.lref_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.lref_point_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_void_p]
         lib.lref_scene_set_attr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_intersect_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,

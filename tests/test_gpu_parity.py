@@ -625,3 +625,45 @@ def test_mt_stream_frame_over_three_ranks(golden_dir):
     assert np.array_equal(acc, full)
     rmse = float(np.sqrt(np.mean((acc.astype(np.float64) - g["rgb"].astype(np.float64)) ** 2)))
     assert rmse <= RMSE_TOL, rmse
+
+
+def test_point_gathers(oracle, golden_dir):
+    """SURVEY 8f rank 2, per-point hemisphere gathers through ri_b200_gather_points_f64 against the compiled reference's golden
+    vectors and the oracle: the occlusion() shadeop is a ray count -> exact; the dome light adds one constant per miss in ray order
+    -> exact; the IBL gather looks the angular map up with acos -> 1e-9 relative.  A stream offset continues the reference's stream
+    where an earlier batch stopped."""
+    _need_gpu()
+    g = np.load(os.path.join(golden_dir, "point_gathers.npz"))
+    tris = scenes.triangle_soup(int(g["ntris"]), int(g["seed"]))
+    a = accel.Accel.bind().build(tris, accel.PREC_F64)
+    pts, env, col, inten = g["points"], g["env"], g["col"], float(g["intensity"])
+    for kind, ns in g["cases"]:
+        kind, ns = int(kind), int(ns)
+        got, nrays = a.gather_points(kind, ns, pts, env if kind == accel.GATHER_IBL else None, col, inten)
+        want = g[f"k{kind}_n{ns}"]
+        nth = max(1, int(np.sqrt(int(ns / 3.0))))
+        assert nrays == len(pts) * 3 * nth * nth
+        if kind == accel.GATHER_IBL:
+            assert np.allclose(got, want, rtol=1e-9, atol=0.0)
+        else:
+            assert np.array_equal(got, want), (kind, ns)
+    # second half of the points as a batch of its own: same numbers as in the whole batch when the stream continues
+    half = len(pts) // 2
+    whole, _ = a.gather_points(accel.GATHER_DOME, 27, pts, None, col, inten)
+    tail, _ = a.gather_points(accel.GATHER_DOME, 27, pts[half:], None, col, inten, stream_offset=2 * 27 * half)
+    assert np.array_equal(tail, whole[half:])
+    # a bigger, different case against the oracle directly
+    ot = oracle.build(tris)
+    rng = np.random.default_rng(4)
+    n = rng.normal(size=(3000, 3))
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    big = np.concatenate([rng.uniform(0.0, 1.0, (3000, 3)), n], axis=1)
+    for kind, ns in ((accel.GATHER_OCCLUSION, 108), (accel.GATHER_IBL, 12)):
+        got, _ = a.gather_points(kind, ns, big, env, col, inten)
+        want, _ = ot.point_gather(kind, ns, big, env, col, inten)
+        if kind == accel.GATHER_IBL:
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-300)
+        else:
+            assert np.array_equal(got, want)
+    with pytest.raises(accel.B200Error):
+        a.gather_points(accel.GATHER_IBL, 12, big, None)

@@ -175,3 +175,13 @@ def test_textured_ao_frame_golden(oracle, golden_dir):
     rgb, nrays = t.render_ao_textured(ol.frame_params(g["cam"], 120, 90, gather=16), g["tex"])
     assert nrays == int(g["nrays"]) and np.array_equal(rgb, g["rgb"])
     assert (np.ptp(rgb, axis=2) > 1e-3).mean() > 0.2          # the texture coloured the image
+
+
+def test_point_gathers_golden(oracle, golden_dir):
+    """SURVEY 8f rank 2, per-point hemisphere gathers: the compiled reference's occlusion() shadeop, ri_ibl_sample_cosweight and
+    ri_domelight_sample at 800 shading points (tests/golden/make_gather_golden.py) -- the restatement reproduces them bit for bit."""
+    g = np.load(os.path.join(golden_dir, "point_gathers.npz"))
+    t = oracle.build(scenes.triangle_soup(int(g["ntris"]), int(g["seed"])))
+    for kind, ns in g["cases"]:
+        got, _ = t.point_gather(int(kind), int(ns), g["points"], g["env"] if kind == 1 else None, g["col"], float(g["intensity"]))
+        assert np.array_equal(got, g[f"k{kind}_n{ns}"]), (kind, ns)

@@ -174,3 +174,32 @@ def test_whitted_transport_called_directly(oracle, ref):
         assert np.array_equal(got, want)
         assert nrays > 1.5 * len(rays6)
     assert (got.sum(axis=1) == 0).sum() > 100          # chains cut at MAX_TRACE_DEPTH leave zero radiance
+
+
+def _shading_points(oracle_tree, n_side=64):
+    """(P, N) of the primary hits of a small camera on the tree's scene: realistic shading points for the per-point gathers."""
+    rays = scenes.rays_f32_to_f64(scenes.pinhole_rays(n_side, n_side))
+    hits = oracle_tree.intersect_f64(rays)
+    st = oracle_tree.state_build(rays, hits)
+    m = hits["hit"] == 1
+    return np.concatenate([st["P"][m][:, :3], st["Ns"][m][:, :3]], axis=1)
+
+
+@pytest.mark.parametrize("kind,nsamples", [(0, 48), (0, 16), (0, 2), (1, 48), (1, 30), (2, 27), (2, 100)])
+def test_point_gathers_called_directly(oracle, ref, kind, nsamples):
+    """SURVEY 8f rank 2, the per-point hemisphere gathers: the occlusion() shadeop (shader.c:680-768), ri_ibl_sample_cosweight
+    (ibl.c:53-228) and ri_domelight_sample (ibl.c:231-389) of the compiled reference, called once per shading point, against the
+    restatement: bit-identical results (sample counts that are and are not 3 * ntheta^2)."""
+    tris = scenes.triangle_soup(20000, 9)
+    rs, ot = ref.build(tris), oracle.build(tris)
+    env = ol.test_texture(32, 32, 5)
+    rs.set_envmap(env)
+    pts = _shading_points(ot)[:1500]
+    assert len(pts) > 500
+    col, inten = (0.9, 0.5, 0.25), 2.5
+    want = rs.point_gather(kind, nsamples, pts, col, inten)
+    got, nrays = ot.point_gather(kind, nsamples, pts, env if kind == 1 else None, col, inten)
+    nth = max(1, int(np.sqrt(int(nsamples / 3.0))))
+    assert nrays == len(pts) * 3 * nth * nth
+    assert np.array_equal(got, want)
+    assert np.ptp(got[:, 0]) > 0.05                     # neither all open nor all blocked
