@@ -21,4 +21,40 @@ for prec in (accel.PREC_F64, accel.PREC_F32):
         fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 32, 24, 2, 2, gather_nsamples=16, precision=prec)
         rgb, s = c1.render_ao(fr)
         print("frame", prec, env, float(rgb.mean()), s.nrays)
+os.environ.pop("B200_FUSED_AO_TEST", None)
+# dirt map / whitted / hit mask / sun-sky-free transports, .hdr encoder, point gathers, peer framebuffer, shared MT stream over 2 ranks
+import oracle_lib as ol
+fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 40, 30, 2, 2, gather_nsamples=16, precision=accel.PREC_F64)
+rgb, _ = c1.render_dirtmap(fr); print("dirtmap", float(rgb.mean()))
+env = ol.test_texture(16, 16, 2)
+rgb, _ = c1.render_whitted(fr, env); print("whitted", float(rgb.mean()))
+rgb, _ = c1.render_sample(fr); print("sample", float(rgb.mean()))
+print("hdr", len(accel.hdr_encode(rgb)))
+pts = np.concatenate([np.random.default_rng(1).uniform(0, 1, (200, 3)), np.tile([0.0, 0.0, 1.0], (200, 1))], axis=1)
+for kind in (accel.GATHER_OCCLUSION, accel.GATHER_IBL, accel.GATHER_DOME):
+    out, n = a.gather_points(kind, 27, pts, env); print("gather", kind, float(out.mean()), n)
+ptr, _ = accel.peer_alloc(40 * 30 * 12, 0)
+import copy, threading
+for r in (0, 1):
+    f = copy.copy(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 40, 30, 2, 2, gather_nsamples=16, rng_mode=1, precision=accel.PREC_F32))
+    f.rank, f.world = r, 2
+    c1.render_ao_peer_dev(f, ptr)
+print("peer", float(accel.peer_read(ptr, (30, 40, 3), 0).mean())); accel.peer_free(ptr, 0)
+from lucille_b200 import distributed
+bar, posted, res = threading.Barrier(2), {}, {}
+def exch(rank):
+    def fn(hits):
+        posted[rank] = hits.astype(np.int64); bar.wait(timeout=300)
+        per = max(len(v) for v in posted.values()); tab = np.zeros((2, per), dtype=np.int64)
+        for r, v in posted.items(): tab[r, :len(v)] = v
+        b, t = distributed.bucket_bases(tab, 2); bar.wait(timeout=300)
+        return b[rank][:len(hits)], t
+    return fn
+def run(rank):
+    acc = accel.Accel.bind().build(g["tris"], accel.PREC_F64); acc.set_hit_exchange(exch(rank))
+    res[rank] = acc.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 70, 40, 2, 2, gather_nsamples=16, rank=rank, world=2))[0]
+th = [threading.Thread(target=run, args=(r,)) for r in (0, 1)]
+[t.start() for t in th]; [t.join() for t in th]
+one, _ = c1.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 70, 40, 2, 2, gather_nsamples=16))
+print("shared stream equal:", bool(np.array_equal(res[0] + res[1], one)))
 print("done")
