@@ -81,8 +81,8 @@ struct ri_b200_accel {
     void *h_pin = nullptr, *d_one = nullptr;
     std::mutex mu;
     // frame scratch (grown on demand)
-    void *d_frame[10] = {};
-    uint64_t frame_bytes[10] = {};
+    void *d_frame[12] = {};
+    uint64_t frame_bytes[12] = {};
 };
 
 template <typename Real> static SceneView<Real> make_view(const ri_b200_accel *a);

@@ -877,20 +877,63 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         if (frame_buf(a, 9, ((uint64_t)nhits + 1) * 3 * sizeof(double), &p)) return -1;
         d_lo = (double *)p;
         CUDA_OK(cudaMemcpyAsync(d_sky, sky, sizeof(ri_b200_sunsky_t), cudaMemcpyHostToDevice, st));
-        if (nao_rays) {
+        if (nao_rays && fused_ao) {
             const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
             if (blocks > 0x7fffffffull) return fail("too many gather rays in one frame pass");
             sunsky_kernel<Real><<<(unsigned)blocks, kBlock, sky_smem, st>>>(S, F, d_sky, nao_rays, d_rec, d_ranks, d_pix, d_mt, d_lo, (uint32_t)cap);
             LAUNCHED();
+        } else if (nao_rays) {                    // wavefront: gather rays and sun shadow rays through the pooled occlusion traverser
+            const uint32_t chunk_samples = (1u << 24) / 64u, nsun = (uint32_t)(sky->nsun > 0 ? sky->nsun : 0);
+            const uint64_t ray_words = sizeof(Real) == 8 ? 6 : 8;
+            const uint64_t buf_samples = nhits < chunk_samples ? nhits : chunk_samples;
+            if (frame_buf(a, 7, buf_samples * 64 * ray_words * sizeof(Real), &p)) return -1;
+            Real *d_rays = (Real *)p;
+            if (frame_buf(a, 10, buf_samples * 64 + buf_samples * (nsun + 1) + 64, &p)) return -1;
+            uint8_t *d_occ8 = (uint8_t *)p, *d_sunocc = d_occ8 + buf_samples * 64;
+            if (frame_buf(a, 11, (buf_samples * (nsun + 1) + 1) * ray_words * sizeof(Real), &p)) return -1;
+            Real *d_sunrays = (Real *)p;
+            for (uint32_t r0 = 0; r0 < nhits; r0 += chunk_samples) {
+                const uint32_t ns = (nhits - r0) < chunk_samples ? (nhits - r0) : chunk_samples;
+                const uint64_t nr = (uint64_t)ns * 64;
+                ao_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(F, nr, r0, d_rec, d_ranks, d_pix, d_mt, d_rays);
+                LAUNCHED();
+                if (launch_trace<Real, true, false>(a, d_rays, nr, nullptr, d_occ8, nullptr, st)) return -1;
+                if (nsun) {
+                    const uint64_t nsr = (uint64_t)ns * nsun;
+                    sun_rays_kernel<Real><<<(unsigned)((nsr + 255) / 256), 256, 0, st>>>(d_sky, d_rec, r0, ns, d_sunrays);
+                    LAUNCHED();
+                    if (launch_trace<Real, true, false>(a, d_sunrays, nsr, nullptr, d_sunocc, nullptr, st)) return -1;
+                }
+                sky_accum_kernel<Real><<<(ns + kBlock / 32 - 1) / (kBlock / 32), kBlock, 0, st>>>(d_sky, d_rays, d_occ8, d_sunocc, r0, ns, d_lo);
+                LAUNCHED();
+            }
         }
-    } else if (dirtmap) {                         // dirt map: one lane per ray, closest hit, colour by distance, per-sample sums in order
+    } else if (dirtmap) {                         // dirt map: closest hit per gather ray, colour by distance, per-sample sums in order
         if (frame_buf(a, 8, ((uint64_t)nhits + 1) * 3 * sizeof(double), &p)) return -1;
         d_lo = (double *)p;
-        if (nao_rays) {
+        if (nao_rays && fused_ao) {               // one lane per ray
             const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;
             if (blocks > 0x7fffffffull) return fail("too many gather rays in one frame pass");
             dirtmap_kernel<Real><<<(unsigned)blocks, kBlock, dirt_smem, st>>>(S, F, nao_rays, d_rec, d_ranks, d_pix, d_mt, d_texcol, d_lo, (uint32_t)cap);
             LAUNCHED();
+        } else if (nao_rays) {                    // wavefront through the pooled closest-hit traverser
+            using Hit = typename RayIO<Real>::Hit;
+            const uint32_t chunk_samples = (1u << 24) / 16u;
+            const uint64_t ray_words = sizeof(Real) == 8 ? 6 : 8;
+            const uint64_t buf_samples = nhits < chunk_samples ? nhits : chunk_samples;
+            if (frame_buf(a, 7, buf_samples * 16 * ray_words * sizeof(Real), &p)) return -1;
+            Real *d_rays = (Real *)p;
+            if (frame_buf(a, 10, (buf_samples * 16 + 1) * sizeof(Hit), &p)) return -1;
+            Hit *d_hits = (Hit *)p;
+            for (uint32_t r0 = 0; r0 < nhits; r0 += chunk_samples) {
+                const uint32_t ns = (nhits - r0) < chunk_samples ? (nhits - r0) : chunk_samples;
+                const uint64_t nr = (uint64_t)ns * 16;
+                ao_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(F, nr, r0, d_rec, d_ranks, d_pix, d_mt, d_rays);
+                LAUNCHED();
+                if (launch_trace<Real, false, false>(a, d_rays, nr, d_hits, nullptr, nullptr, st)) return -1;
+                dirt_accum_kernel<Real><<<(ns + 255) / 256, 256, 0, st>>>(d_hits, d_texcol, r0, ns, d_lo);
+                LAUNCHED();
+            }
         }
     } else if (nao_rays && fused_ao) {                   // one lane per ray, generation fused with a one-ray-per-thread traversal
         const uint64_t blocks = (nao_rays + kBlock - 1) / kBlock;

@@ -213,6 +213,105 @@ dirtmap_kernel(const SceneView<Real> S, const FrameDev F, const uint64_t nrays, 
     }
 }
 
+// ---- wavefront forms of the two gathers for scenes past a few thousand triangles: rays written by ao_gen_kernel go through the
+// pooled traversers (pool.cuh / pool_closest.cuh) and these kernels do the per-sample arithmetic afterwards, in the same order.
+
+// shadow ray of sun light l for every hit sample of the chunk, from the offset origin in the record (ambientocclusion.c:176-187)
+template <typename Real>
+__global__ void sun_rays_kernel(const ri_b200_sunsky_t *__restrict__ K, const Real *__restrict__ records, const uint32_t rank0,
+                                const uint32_t nsamples, Real *__restrict__ rays_out)
+{
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nsun = (uint32_t)K->nsun;
+    if (gid >= (uint64_t)nsamples * nsun) return;
+    const uint32_t s = (uint32_t)(gid / nsun), l = (uint32_t)(gid - (uint64_t)s * nsun);
+    const Real *rec = records + 12 * (uint64_t)(rank0 + s);
+    if (sizeof(Real) == 8) {
+        double2 *o = reinterpret_cast<double2 *>(rays_out) + 3 * gid;
+        o[0] = make_double2((double)rec[0], (double)rec[1]);
+        o[1] = make_double2((double)rec[2], (double)K->sun_dir[l][0]);
+        o[2] = make_double2((double)K->sun_dir[l][1], (double)K->sun_dir[l][2]);
+    } else {
+        float4 *o = reinterpret_cast<float4 *>(rays_out) + 2 * gid;
+        o[0] = make_float4((float)rec[0], (float)rec[1], (float)rec[2], 0.0f);
+        o[1] = make_float4((float)(Real)K->sun_dir[l][0], (float)(Real)K->sun_dir[l][1], (float)(Real)K->sun_dir[l][2], 1.0e38f);
+    }
+}
+
+// One warp per hit sample: the 64 occlusion flags of its gather rays are read two per lane, the MISSED rays are dealt densely to the
+// lanes (the sky lookup is ~1500 instructions; a third of the rays need it), their colours parked in shared memory by ray number,
+// then lanes 0..2 add one channel each in ray order (double += float, occluded rays hold +0.0f), add the unshadowed suns and write Lo.
+template <typename Real>
+__global__ void __launch_bounds__(kBlock)
+sky_accum_kernel(const ri_b200_sunsky_t *__restrict__ K, const Real *__restrict__ rays, const uint8_t *__restrict__ occ,
+                 const uint8_t *__restrict__ sun_occ, const uint32_t rank0, const uint32_t nsamples, double *__restrict__ lo_out)
+{
+    __shared__ float s_col[kBlock / 32][3][64];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t s = blockIdx.x * (kBlock / 32) + warp;
+    if (s >= nsamples) return;
+    const uint64_t r0 = (uint64_t)s * 64;
+    const uint32_t m0 = __ballot_sync(0xffffffffu, occ[r0 + lane] == 0), m1 = __ballot_sync(0xffffffffu, occ[r0 + 32 + lane] == 0);
+    for (int q = 0; q < 3; ++q) { s_col[warp][q][lane] = 0.0f; s_col[warp][q][32 + lane] = 0.0f; }
+    __syncwarp();
+    const uint32_t nmiss = (uint32_t)(__popc(m0) + __popc(m1));
+    for (uint32_t i = lane; i < nmiss; i += 32) {
+        // i-th missed ray of the sample: i-th set bit of (m1:m0)
+        uint32_t k;
+        const uint32_t c0 = (uint32_t)__popc(m0);
+        if (i < c0) k = (uint32_t)__fns(m0, 0, (int)i + 1);
+        else k = 32u + (uint32_t)__fns(m1, 0, (int)(i - c0) + 1);
+        float v[3], c[3];
+        if (sizeof(Real) == 8) {
+            const double *r = reinterpret_cast<const double *>(rays) + 6 * (r0 + k);
+            v[0] = (float)r[3]; v[1] = (float)r[4]; v[2] = (float)r[5];                        // ambientocclusion.c:294-296
+        } else {
+            const float *r = reinterpret_cast<const float *>(rays) + 8 * (r0 + k);
+            v[0] = r[4]; v[1] = r[5]; v[2] = r[6];
+        }
+        sky_rgb_dev(K, v, c);
+        s_col[warp][0][k] = c[0]; s_col[warp][1][k] = c[1]; s_col[warp][2][k] = c[2];
+    }
+    __syncwarp();
+    if (lane < 3) {
+        double col = 0.0;
+        for (int q = 0; q < 64; ++q) col += (double)s_col[warp][lane][q];
+        for (int l = 0; l < K->nsun; ++l)                                                     // contribution_from_sunlight
+            if (!sun_occ[(uint64_t)s * (uint32_t)K->nsun + l]) col += K->sun_col[l][lane];
+        lo_out[3 * (uint64_t)(rank0 + s) + lane] = (1.0 / 3.14159265358979323846) * col / 64.0;
+    }
+}
+
+// dirt map: one lane per hit sample adds the 16 colours of its gather rays (closest-hit records from the pooled traverser) in order
+template <typename Real>
+__global__ void dirt_accum_kernel(const typename RayIO<Real>::Hit *__restrict__ hits, const double *__restrict__ texcol, const uint32_t rank0,
+                                  const uint32_t nsamples, double *__restrict__ lo_out)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsamples) return;
+    const double near_clip = 0.1, far_clip = 0.5, dirt_color = 0.0, base_color = 1.0;
+    double sum = 0.0;
+    for (uint32_t q = 0; q < 16u; ++q) {
+        const typename RayIO<Real>::Hit h = hits[(uint64_t)s * 16 + q];
+        double c = base_color;
+        if (h.prim != 0xffffffffu) {
+            const double td = (double)h.t;
+            if (td <= near_clip) c = dirt_color;
+            else if (td >= far_clip) c = base_color;
+            else {
+                double p = 1.0 - ((td - near_clip) / (far_clip - near_clip));
+                if (p < 0.0) p = 0.0;
+                if (p > 1.0) p = 1.0;
+                c = (1.0 - p) * base_color - p * dirt_color;
+            }
+        }
+        sum = sum + c;
+    }
+    const double lo = sum / 16.0;
+    const uint64_t rank = (uint64_t)rank0 + s;
+    for (int q = 0; q < 3; ++q) lo_out[3 * rank + q] = texcol ? lo * texcol[3 * rank + q] : lo;
+}
+
 // render.c:805,820 + bucket_write: three-channel box average of the sub-sample radiances, float RGB at row H-1-y
 __global__ void resolve_rgb_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels,
                                    const uint32_t *__restrict__ sample_rank, const double *__restrict__ lo, float *__restrict__ rgb, const int packed)

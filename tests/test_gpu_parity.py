@@ -374,16 +374,22 @@ def test_sunsky_frame(oracle, golden_dir, prec):
     cam = g["frame_cam"]
     a = accel.Accel.bind().build(g["frame_tris"], prec)
     fr = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 120, 90, 2, 2, gather_nsamples=int(cam[22]), precision=prec)
-    rgb, stats = a.render_sunsky(fr, _device_sunsky(blk))
     want = g["frame_rgb"].astype(np.float64)
-    if prec == accel.PREC_F64:
-        assert stats.nrays == int(g["frame_nrays"])
-        rel = np.abs(rgb - want) / (np.abs(want) + 1.0)
-        assert rel.max() < 1e-5, rel.max()
-        assert np.array_equal(rgb == 0, want == 0)
-    else:
-        rmse = float(np.sqrt(np.mean((rgb - want) ** 2)))
-        assert rmse / want.mean() < 2e-2, rmse / want.mean()
+    frames = []
+    for fused in ("1", "0"):                       # one-lane-per-ray kernel, and the wavefront through the pooled traverser
+        os.environ["B200_FUSED_AO_TEST"] = fused
+        rgb, stats = a.render_sunsky(fr, _device_sunsky(blk))
+        frames.append(rgb)
+        if prec == accel.PREC_F64:
+            assert stats.nrays == int(g["frame_nrays"])
+            rel = np.abs(rgb - want) / (np.abs(want) + 1.0)
+            assert rel.max() < 1e-5, rel.max()
+            assert np.array_equal(rgb == 0, want == 0)
+        else:
+            rmse = float(np.sqrt(np.mean((rgb - want) ** 2)))
+            assert rmse / want.mean() < 2e-2, rmse / want.mean()
+    os.environ.pop("B200_FUSED_AO_TEST", None)
+    assert np.array_equal(frames[0], frames[1])    # same rays, same lookups, same order of additions
 
 
 @pytest.mark.parametrize("maker", [
@@ -506,14 +512,25 @@ def test_dirtmap_frame(oracle):
     flen = 1.0 / math.tan(math.radians(40.0) / 2)
     a = accel.Accel.bind().build(tris, accel.PREC_F64)
     fr = accel.make_frame(c2w.reshape(16), flen, False, 96, 72, 2, 2, gather_nsamples=64, precision=accel.PREC_F64)
-    rgb, stats = a.render_dirtmap(fr)
     cam = np.zeros(27)
     cam[:16] = c2w.reshape(16)
     cam[16], cam[17], cam[20], cam[21], cam[22], cam[23] = flen, 0, 2, 2, 64, 32
     want, nrays = oracle.build(tris).render_dirtmap(ol.frame_params(cam, 96, 72))
-    assert stats.nrays == nrays
-    assert np.array_equal(rgb, want)
+    for fused in ("1", "0"):                       # one-lane-per-ray kernel, and the wavefront through the pooled closest-hit traverser
+        os.environ["B200_FUSED_AO_TEST"] = fused
+        rgb, stats = a.render_dirtmap(fr)
+        assert stats.nrays == nrays
+        assert np.array_equal(rgb, want)
+    os.environ.pop("B200_FUSED_AO_TEST", None)
     assert np.unique(rgb).size > 50 and rgb.max() <= 1.0
+    a32 = accel.Accel.bind().build(tris, accel.PREC_F32)       # fp32 records: both paths give one image
+    f32 = accel.make_frame(c2w.reshape(16), flen, False, 96, 72, 2, 2, gather_nsamples=64, precision=accel.PREC_F32)
+    both = []
+    for fused in ("1", "0"):
+        os.environ["B200_FUSED_AO_TEST"] = fused
+        both.append(a32.render_dirtmap(f32)[0])
+    os.environ.pop("B200_FUSED_AO_TEST", None)
+    assert np.array_equal(both[0], both[1]) and abs(float(both[0].mean()) - float(want.mean())) < 5e-3
 
 
 def test_whitted_frame(oracle):
