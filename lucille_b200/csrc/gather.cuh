@@ -7,7 +7,7 @@
 // (randomMT / randomMT2: same generator, same seed, random.c:163-247), so point p starts at stream word 2*N*p: the stream comes
 // from the jump-ahead generator of frame.cuh and every ray is independent.
 //
-// One warp per point: lane l takes rays l, l+32, ...; after each group of 32 the contributions are added in ray order (every lane
+// Small scenes: one warp per point, lane l takes rays l, l+32, ...; after each group of 32 the contributions are added in ray order (every lane
 // runs the same 32-step shuffle sum, adding +0.0 for rays that hit), which is the reference's accumulation order exactly.
 // ri_ibl_sample_bruteforce (ibl.c:395-518) is not built: it overwrites the ray origin with the direction before measuring their
 // distance (ibl.c:497-505), so every term is multiplied by invdist = 0 and the function returns zero power for any input.
@@ -22,6 +22,34 @@ struct GatherDev {
     TexDev   env;                   // IBL
 };
 
+// ray k = j*ntheta + i of point p: stratified cosine fan about N (reflection.c:312-333 basis), normalised, origin per caller
+__device__ __forceinline__ void gather_ray(const GatherDev &G, const double *__restrict__ points, const uint32_t *__restrict__ mt_stream,
+                                           const uint64_t p, const uint32_t k, double org[3], double dir[3])
+{
+    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    const double P[3] = {points[6 * p], points[6 * p + 1], points[6 * p + 2]};
+    const double Nn[3] = {points[6 * p + 3], points[6 * p + 4], points[6 * p + 5]};
+    double b0[3], b1[3];
+    ortho_basis(b0, b1, Nn);
+    const uint32_t j = k / (uint32_t)G.ntheta, i = k - j * (uint32_t)G.ntheta;
+    const uint64_t w = G.stream_offset + 2 * ((uint64_t)N * p + k);
+    const double r0 = (double)mt_stream[w] * 2.3283064365386963e-10;        // random.c:196,244
+    const double r1 = (double)mt_stream[w + 1] * 2.3283064365386963e-10;
+    const double theta = (G.kind == RI_B200_GATHER_OCCLUSION) ? sqrt((double)i + r0) / (double)G.ntheta     // shader.c:731
+                                                              : sqrt(((double)i + r0) / (double)G.ntheta);  // ibl.c:174,337
+    const double phi = 2.0 * 3.14159265358979323846 * ((double)j + r1) / (double)G.nphi;
+    const double lx = cos(phi) * theta, ly = sin(phi) * theta, lz = sqrt(1.0 - theta * theta);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dir[q] = lx * b0[q] + ly * b1[q] + lz * Nn[q];
+    normalize3(dir);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        org[q] = P[q];
+        if (G.kind == RI_B200_GATHER_OCCLUSION) org[q] += 0.0001 * dir[q];  // shader.c:750-752
+        if (G.kind == RI_B200_GATHER_IBL) org[q] += Nn[q] * 0.0001;          // ibl.c:92-94
+    }
+}
+
 __global__ void __launch_bounds__(kBlock)
 point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *__restrict__ points, const uint64_t npoints,
                     const uint32_t *__restrict__ mt_stream, double *__restrict__ out3, const uint32_t stack_cap)
@@ -31,10 +59,6 @@ point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *
     const uint32_t lane = threadIdx.x & 31u;
     if (p >= npoints) return;                                               // whole warps leave together
     const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
-    const double P[3] = {points[6 * p], points[6 * p + 1], points[6 * p + 2]};
-    const double Nn[3] = {points[6 * p + 3], points[6 * p + 4], points[6 * p + 5]};
-    double b0[3], b1[3];
-    ortho_basis(b0, b1, Nn);                                                // reflection.c:312-333: basis = (b0, b1, N)
     double sum[3] = {0.0, 0.0, 0.0};
     uint32_t coverage = 0;
     for (uint32_t base = 0; base < N; base += 32) {
@@ -42,25 +66,9 @@ point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *
         double c[3] = {0.0, 0.0, 0.0};
         bool hit = false;
         if (k < N) {
-            const uint32_t j = k / (uint32_t)G.ntheta, i = k - j * (uint32_t)G.ntheta;
-            const uint64_t w = G.stream_offset + 2 * ((uint64_t)N * p + k);
-            const double r0 = (double)mt_stream[w] * 2.3283064365386963e-10;        // random.c:196,244
-            const double r1 = (double)mt_stream[w + 1] * 2.3283064365386963e-10;
-            const double theta = (G.kind == RI_B200_GATHER_OCCLUSION) ? sqrt((double)i + r0) / (double)G.ntheta     // shader.c:731
-                                                                      : sqrt(((double)i + r0) / (double)G.ntheta);  // ibl.c:174,337
-            const double phi = 2.0 * 3.14159265358979323846 * ((double)j + r1) / (double)G.nphi;
-            const double lx = cos(phi) * theta, ly = sin(phi) * theta, lz = sqrt(1.0 - theta * theta);
             double dir[3], org[3], t, u, v;
             uint32_t prim;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) dir[q] = lx * b0[q] + ly * b1[q] + lz * Nn[q];
-            normalize3(dir);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                org[q] = P[q];
-                if (G.kind == RI_B200_GATHER_OCCLUSION) org[q] += 0.0001 * dir[q];  // shader.c:750-752
-                if (G.kind == RI_B200_GATHER_IBL) org[q] += Nn[q] * 0.0001;          // ibl.c:92-94
-            }
+            gather_ray(G, points, mt_stream, p, k, org, dir);
             hit = trace_ray<double, true, false>(S, org, dir, s_stack + threadIdx.x, kBlock, t, u, v, prim, nullptr);
             if (!hit && G.kind != RI_B200_GATHER_OCCLUSION) {
                 double rad[3] = {G.rad[0], G.rad[1], G.rad[2]};
@@ -81,6 +89,75 @@ point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *
     }
     if (lane == 0) {
         double *o = out3 + 3 * p;
+        if (G.kind == RI_B200_GATHER_OCCLUSION) {
+            if (coverage > (uint32_t)G.nsamples) coverage = (uint32_t)G.nsamples;
+            o[0] = o[1] = o[2] = (double)(float)((double)coverage / (double)(float)G.nsamples);
+        } else if (G.kind == RI_B200_GATHER_IBL) {
+            for (int q = 0; q < 3; ++q) o[q] = 3.14159265358979323846 * sum[q] / (double)(G.ntheta * G.nphi);
+        } else {
+            for (int q = 0; q < 3; ++q) o[q] = 3.14159265358979323846 * sum[q] / (double)G.nsamples;
+        }
+    }
+}
+
+// ---- wavefront form (scenes past a few thousand triangles): the same rays written out, traced by the pooled occlusion traverser
+// (pool.cuh, fp64 records), and accumulated per point in ray order.
+__global__ void __launch_bounds__(kBlock)
+gather_gen_kernel(const GatherDev G, const double *__restrict__ points, const uint64_t p0, const uint64_t nrays,
+                  const uint32_t *__restrict__ mt_stream, double *__restrict__ rays_out)
+{
+    const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (gid >= nrays) return;
+    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    const uint64_t p = p0 + gid / N;
+    const uint32_t k = (uint32_t)(gid % N);
+    double org[3], dir[3];
+    gather_ray(G, points, mt_stream, p, k, org, dir);
+    double2 *o = reinterpret_cast<double2 *>(rays_out) + 3 * gid;
+    o[0] = make_double2(org[0], org[1]);
+    o[1] = make_double2(org[2], dir[0]);
+    o[2] = make_double2(dir[1], dir[2]);
+}
+
+__global__ void __launch_bounds__(kBlock)
+gather_accum_kernel(const GatherDev G, const double *__restrict__ rays, const uint8_t *__restrict__ occ, const uint64_t p0,
+                    const uint64_t npoints, double *__restrict__ out3)
+{
+    const uint64_t lp = ((uint64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;          // point within the chunk
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lp >= npoints) return;
+    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    double sum[3] = {0.0, 0.0, 0.0};
+    uint32_t coverage = 0;
+    for (uint32_t base = 0; base < N; base += 32) {
+        const uint32_t k = base + lane;
+        double c[3] = {0.0, 0.0, 0.0};
+        bool hit = false;
+        if (k < N) {
+            const uint64_t r = lp * N + k;
+            hit = occ[r] != 0;
+            if (!hit && G.kind != RI_B200_GATHER_OCCLUSION) {
+                double rad[3] = {G.rad[0], G.rad[1], G.rad[2]};
+                if (G.kind == RI_B200_GATHER_IBL) {
+                    const double dir[3] = {rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]};
+                    ibl_fetch_dev(G.env, dir, rad);
+                }
+                const double brdf = 1.0 / 3.14159265358979323846;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) c[q] = rad[q] * brdf;
+            }
+        }
+        if (G.kind == RI_B200_GATHER_OCCLUSION) {
+            coverage += (uint32_t)__popc(__ballot_sync(0xffffffffu, hit));
+        } else {
+            for (int l = 0; l < 32; ++l) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) sum[q] = sum[q] + __shfl_sync(0xffffffffu, c[q], l);
+            }
+        }
+    }
+    if (lane == 0) {
+        double *o = out3 + 3 * (p0 + lp);
         if (G.kind == RI_B200_GATHER_OCCLUSION) {
             if (coverage > (uint32_t)G.nsamples) coverage = (uint32_t)G.nsamples;
             o[0] = o[1] = o[2] = (double)(float)((double)coverage / (double)(float)G.nsamples);
@@ -143,10 +220,29 @@ extern "C" int ri_b200_gather_points_f64(ri_b200_accel_t *a, const ri_b200_gathe
     }
     CUDA_OK(cudaMemcpyAsync(d_points, points, n * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (mt_stream_launch(a, g->seed, (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks), mt_blocks, d_mt, st)) return -1;
-    const uint64_t blocks = (n * 32 + kBlock - 1) / kBlock;
-    if (blocks > 0x7fffffffull) return fail("too many shading points in one gather");
-    point_gather_kernel<<<(unsigned)blocks, kBlock, smem, st>>>(make_view<double>(a), G, d_points, n, d_mt, d_out, (uint32_t)cap);
-    LAUNCHED();
+    const char *force = getenv("B200_FUSED_AO_TEST");         // test hook: exercise both paths on the same scene
+    const bool fused = force ? atoi(force) != 0 : (a->tree.ntris < 4096);
+    if (fused) {                                              // one warp per point, one-ray-per-lane traversal
+        const uint64_t blocks = (n * 32 + kBlock - 1) / kBlock;
+        if (blocks > 0x7fffffffull) return fail("too many shading points in one gather");
+        point_gather_kernel<<<(unsigned)blocks, kBlock, smem, st>>>(make_view<double>(a), G, d_points, n, d_mt, d_out, (uint32_t)cap);
+        LAUNCHED();
+    } else {                                                  // wavefront: <= 2^24 rays at a time through the pooled traverser
+        const uint64_t chunk_points = ((1ull << 24) / N) ? (1ull << 24) / N : 1;
+        const uint64_t buf_points = n < chunk_points ? n : chunk_points;
+        if (frame_buf(a, 10, buf_points * N * 6 * sizeof(double), &p)) return -1;
+        double *d_rays = (double *)p;
+        if (frame_buf(a, 11, buf_points * N + 64, &p)) return -1;
+        uint8_t *d_occ8 = (uint8_t *)p;
+        for (uint64_t p0 = 0; p0 < n; p0 += chunk_points) {
+            const uint64_t np = (n - p0) < chunk_points ? (n - p0) : chunk_points, nr = np * N;
+            gather_gen_kernel<<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_points, p0, nr, d_mt, d_rays);
+            LAUNCHED();
+            if (launch_trace<double, true, false>(a, d_rays, nr, nullptr, d_occ8, nullptr, st)) return -1;
+            gather_accum_kernel<<<(unsigned)((np * 32 + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_rays, d_occ8, p0, np, d_out);
+            LAUNCHED();
+        }
+    }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(out3, d_out, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));

@@ -656,14 +656,20 @@ def test_point_gathers(oracle, golden_dir):
     pts, env, col, inten = g["points"], g["env"], g["col"], float(g["intensity"])
     for kind, ns in g["cases"]:
         kind, ns = int(kind), int(ns)
-        got, nrays = a.gather_points(kind, ns, pts, env if kind == accel.GATHER_IBL else None, col, inten)
         want = g[f"k{kind}_n{ns}"]
         nth = max(1, int(np.sqrt(int(ns / 3.0))))
-        assert nrays == len(pts) * 3 * nth * nth
-        if kind == accel.GATHER_IBL:
-            assert np.allclose(got, want, rtol=1e-9, atol=0.0)
-        else:
-            assert np.array_equal(got, want), (kind, ns)
+        paths = []
+        for fused in ("1", "0"):                   # one-ray-per-lane kernel, and the wavefront through the pooled traverser
+            os.environ["B200_FUSED_AO_TEST"] = fused
+            got, nrays = a.gather_points(kind, ns, pts, env if kind == accel.GATHER_IBL else None, col, inten)
+            paths.append(got)
+            assert nrays == len(pts) * 3 * nth * nth
+            if kind == accel.GATHER_IBL:
+                assert np.allclose(got, want, rtol=1e-9, atol=0.0)
+            else:
+                assert np.array_equal(got, want), (kind, ns)
+        os.environ.pop("B200_FUSED_AO_TEST", None)
+        assert np.array_equal(paths[0], paths[1])
     # second half of the points as a batch of its own: same numbers as in the whole batch when the stream continues
     half = len(pts) // 2
     whole, _ = a.gather_points(accel.GATHER_DOME, 27, pts, None, col, inten)
