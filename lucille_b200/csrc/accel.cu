@@ -347,7 +347,8 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", device); delete a; return nullptr; }
         if (build_on_device(a, tri_xyz, ntris) != 0) {
             if (precisions & RI_B200_BUILD_DEVICE) { ri_b200_free(a); return nullptr; }       // asked for explicitly: report it
-            cudaGetLastError();                                                                 // automatic choice: fall back to the host builder
+            cudaGetLastError();                                                                 // automatic choice: the host builder makes the same tree --
+            fprintf(stderr, "[b200] device BVH build failed (%s); building the same tree on the host\n", g_err);   // said out loud, never silent
             cudaFree(a->d_tris32); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim);
             a->d_tris32 = a->d_tris32t = nullptr; a->d_tris64 = a->d_tris64t = nullptr; a->d_slot_of_prim = nullptr; a->device_bytes = 0;
             on_device = false;

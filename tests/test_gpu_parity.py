@@ -690,3 +690,16 @@ def test_point_gathers(oracle, golden_dir):
             assert np.array_equal(got, want)
     with pytest.raises(accel.B200Error):
         a.gather_points(accel.GATHER_IBL, 12, big, None)
+    # edge cases: no points; an empty scene (every ray escapes: occlusion 0, the dome's full radiance); ragged batch sizes
+    out, n = a.gather_points(accel.GATHER_DOME, 27, np.zeros((0, 6)), None, col, inten)
+    assert out.shape == (0, 3) and n == 0
+    empty, oe = accel.Accel.bind().build(np.zeros((0, 3, 3)), accel.PREC_F64), oracle.build(np.zeros((0, 3, 3)))
+    for kind in (accel.GATHER_OCCLUSION, accel.GATHER_DOME):
+        got, _ = empty.gather_points(kind, 30, big[:33], None, col, inten)
+        want, _ = oe.point_gather(kind, 30, big[:33], None, col, inten)
+        assert np.array_equal(got, want)
+    assert not empty.gather_points(accel.GATHER_OCCLUSION, 30, big[:33])[0].any()
+    for m in (1, 31, 1001):
+        got, _ = a.gather_points(accel.GATHER_OCCLUSION, 3, big[:m])
+        want, _ = ot.point_gather(accel.GATHER_OCCLUSION, 3, big[:m])
+        assert np.array_equal(got, want)
