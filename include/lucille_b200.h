@@ -200,7 +200,7 @@ int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_
  *   RI_B200_GATHER_OCCLUSION  float occlusion(status, P, N, nsamples)                      shader.c:680-768 (all three channels)
  *   RI_B200_GATHER_IBL        ri_ibl_sample_cosweight(power, N, nsamples, ray, P, eye, l)  ibl.c:53-228, l->texture = env_rgba
  *   RI_B200_GATHER_DOME       ri_domelight_sample(power, hemi, nsamples, ray, P, eye, l)   ibl.c:231-389, l->col, l->intensity
- * (Monte Carlo branches: Option "use_qmc" is 0 by default, option.c:139.)  nrays_out (may be NULL) = rays traced.
+ * (Monte Carlo branches by default; use_qmc selects the quasi-Monte Carlo ones.)  nrays_out (may be NULL) = rays traced.
  * trace() (shader.c:895-976) needs no entry of its own: it is one closest-hit query + hit state + environment lookup on a miss --
  * ri_b200_intersect_batch_f64 / ri_b200_state_ext_batch_f64 -- followed by the hit geometry's shader procedure, which stays on the host. */
 #define RI_B200_GATHER_OCCLUSION 0
@@ -216,6 +216,14 @@ typedef struct {
     int32_t  env_width, env_height;
     double   col[3];              /* DOME: ri_light_t.col */
     double   intensity;           /* DOME: ri_light_t.intensity */
+    /* Option "use_qmc" (option.c:139, 520; off by default): the quasi-Monte Carlo branches of the IBL and dome gathers (ibl.c:107-151,
+     * 266-320) -- nsamples rays per point from scrambled Halton / Hammersley points over lucille's Faure permutation table
+     * (qmc.c:182-260, 329-396), no random numbers: seed and stream_offset are not used.  qmc_instance[p] = inray->i of point p (NULL:
+     * all 0), qmc_dim = inray->d (values < 1 count as 1; primes[qmc_dim] must be below 100, i.e. qmc_dim <= 24).  The occlusion()
+     * shadeop has no such branch. */
+    int32_t  use_qmc;
+    int32_t  qmc_dim;
+    const int32_t *qmc_instance;
 } ri_b200_gather_t;
 int ri_b200_gather_points_f64(ri_b200_accel_t *accel, const ri_b200_gather_t *gather, const double *points, uint64_t n, double *out3,
                               uint64_t *nrays_out);

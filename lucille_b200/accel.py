@@ -458,7 +458,7 @@ class Accel:
         return stats
 
     def gather_points(self, kind: int, nsamples: int, points6, env=None, col=(1.0, 1.0, 1.0), intensity: float = 1.0,
-                      seed: int = 4357, stream_offset: int = 0):
+                      seed: int = 4357, stream_offset: int = 0, qmc: bool = False, qmc_instance=None, qmc_dim: int = 0):
         """Hemisphere gathers at shading points (P, N) (ri_b200_gather_points_f64): GATHER_OCCLUSION = the occlusion() shadeop,
         GATHER_IBL = ri_ibl_sample_cosweight with the angular map ``env`` [h,w,4], GATHER_DOME = ri_domelight_sample.
         Returns ([n,3] float64, rays traced)."""
@@ -471,6 +471,11 @@ class Accel:
         for i in range(3):
             g.col[i] = float(col[i])
         g.intensity = float(intensity)
+        g.use_qmc, g.qmc_dim = int(bool(qmc)), int(qmc_dim)       # Option "use_qmc": quasi-Monte Carlo branches, inray->i / inray->d
+        if qmc_instance is not None:
+            inst = np.ascontiguousarray(qmc_instance, dtype=np.int32)
+            assert len(inst) == len(pts)
+            g.qmc_instance = inst.ctypes.data
         out = np.zeros((len(pts), 3), dtype=np.float64)
         nrays = C.c_uint64(0)
         _check(self.lib.ri_b200_gather_points_f64(self._h(), C.byref(g), _ptr(pts), len(pts), _ptr(out), C.byref(nrays)))
@@ -550,7 +555,7 @@ class Gather(C.Structure):
     """ri_b200_gather_t"""
     _fields_ = [("kind", C.c_int32), ("nsamples", C.c_int32), ("seed", C.c_uint32), ("pad_", C.c_uint32), ("stream_offset", C.c_uint64),
                 ("env_rgba", C.c_void_p), ("env_width", C.c_int32), ("env_height", C.c_int32), ("col", C.c_double * 3),
-                ("intensity", C.c_double)]
+                ("intensity", C.c_double), ("use_qmc", C.c_int32), ("qmc_dim", C.c_int32), ("qmc_instance", C.c_void_p)]
 
 
 HIT_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))

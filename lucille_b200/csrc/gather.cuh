@@ -1,5 +1,6 @@
-// Hemisphere gathers at shading points: the per-point loops of three more ri_raytrace callers, Monte Carlo
-// branches (Option "use_qmc" defaults to 0, option.c:139), as ONE batched query over n points (P, N):
+// Hemisphere gathers at shading points: the per-point loops of three more ri_raytrace callers as ONE batched query
+// over n points (P, N) -- the Monte Carlo branches (Option "use_qmc" defaults to 0, option.c:139) and, for the IBL and dome gathers,
+// the quasi-Monte Carlo ones (scrambled Halton / Hammersley points over Faure permutations, qmc.c; nsamples rays per point):
 //   RI_B200_GATHER_OCCLUSION  occlusion() shadeop        shader.c:680-768   coverage / nsamples
 //   RI_B200_GATHER_IBL        ri_ibl_sample_cosweight    ibl.c:53-228       pi * sum(Le/pi) / (ntheta*nphi), Le from the angular map on a miss
 //   RI_B200_GATHER_DOME       ri_domelight_sample        ibl.c:231-389      pi * sum(col*intensity/pi) / nsamples on misses
@@ -17,27 +18,62 @@ namespace b200 {
 
 struct GatherDev {
     int      kind, nsamples, ntheta, nphi;
+    int      nper;                  // rays per point: ntheta * nphi, or nsamples in the quasi-Monte Carlo branches
+    int      qmc, qmc_base;         // use_qmc; primes[inray->d] of the dome light's shift
+    const int32_t *instance;        // inray->i per point, or null
+    int      perm3[3], perm5[5], permd[97];   // Faure permutations of bases 3, 5 and qmc_base (qmc.c:182-260)
     uint64_t stream_offset;         // stream words consumed before point 0
     double   rad[3];                // DOME: col * intensity
     TexDev   env;                   // IBL
 };
 
+// qmc.c:329-349 generalized_vdC
+__device__ __forceinline__ double generalized_vdc_dev(int i, const int base, const int *perm)
+{
+    double h = 0.0;
+    const double f = 1.0 / (double)base;
+    double factor = f;
+    while (i > 0) {
+        h += (double)perm[i % base] * factor;
+        i /= base;
+        factor *= f;
+    }
+    return h;
+}
+
 // ray k = j*ntheta + i of point p: stratified cosine fan about N (reflection.c:312-333 basis), normalised, origin per caller
 __device__ __forceinline__ void gather_ray(const GatherDev &G, const double *__restrict__ points, const uint32_t *__restrict__ mt_stream,
                                            const uint64_t p, const uint32_t k, double org[3], double dir[3])
 {
-    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    const uint32_t N = (uint32_t)G.nper;
     const double P[3] = {points[6 * p], points[6 * p + 1], points[6 * p + 2]};
     const double Nn[3] = {points[6 * p + 3], points[6 * p + 4], points[6 * p + 5]};
     double b0[3], b1[3];
     ortho_basis(b0, b1, Nn);
-    const uint32_t j = k / (uint32_t)G.ntheta, i = k - j * (uint32_t)G.ntheta;
-    const uint64_t w = G.stream_offset + 2 * ((uint64_t)N * p + k);
-    const double r0 = (double)mt_stream[w] * 2.3283064365386963e-10;        // random.c:196,244
-    const double r1 = (double)mt_stream[w + 1] * 2.3283064365386963e-10;
-    const double theta = (G.kind == RI_B200_GATHER_OCCLUSION) ? sqrt((double)i + r0) / (double)G.ntheta     // shader.c:731
-                                                              : sqrt(((double)i + r0) / (double)G.ntheta);  // ibl.c:174,337
-    const double phi = 2.0 * 3.14159265358979323846 * ((double)j + r1) / (double)G.nphi;
+    double theta, phi;
+    if (G.qmc) {                                                            // ibl.c:107-151 + 540-581, 266-320
+        const int inst = G.instance ? G.instance[p] : 0;
+        double s0, s1;
+        if (G.kind == RI_B200_GATHER_IBL) {                                 // scrambled Halton, bases 3 and 5, index i + inray->i
+            s0 = 0.0 + generalized_vdc_dev((int)k + inst, 3, G.perm3);
+            s1 = 0.0 + generalized_vdc_dev((int)k + inst, 5, G.perm5);
+        } else {                                                            // Hammersley (i/n, base 3), both shifted by u
+            const double u = generalized_vdc_dev(inst, G.qmc_base, G.permd);
+            s0 = u + (double)k / (double)G.nsamples;
+            s1 = u + generalized_vdc_dev((int)k, 3, G.perm3);
+        }
+        s0 = s0 - floor(s0); s1 = s1 - floor(s1);                           // mod_1, qmc.c:523-532
+        theta = sqrt(s0);
+        phi = 2.0 * 3.14159265358979323846 * s1;
+    } else {
+        const uint32_t j = k / (uint32_t)G.ntheta, i = k - j * (uint32_t)G.ntheta;
+        const uint64_t w = G.stream_offset + 2 * ((uint64_t)N * p + k);
+        const double r0 = (double)mt_stream[w] * 2.3283064365386963e-10;    // random.c:196,244
+        const double r1 = (double)mt_stream[w + 1] * 2.3283064365386963e-10;
+        theta = (G.kind == RI_B200_GATHER_OCCLUSION) ? sqrt((double)i + r0) / (double)G.ntheta     // shader.c:731
+                                                     : sqrt(((double)i + r0) / (double)G.ntheta);  // ibl.c:174,337
+        phi = 2.0 * 3.14159265358979323846 * ((double)j + r1) / (double)G.nphi;
+    }
     const double lx = cos(phi) * theta, ly = sin(phi) * theta, lz = sqrt(1.0 - theta * theta);
 #pragma unroll
     for (int q = 0; q < 3; ++q) dir[q] = lx * b0[q] + ly * b1[q] + lz * Nn[q];
@@ -58,7 +94,7 @@ point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *
     const uint64_t p = ((uint64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (p >= npoints) return;                                               // whole warps leave together
-    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    const uint32_t N = (uint32_t)G.nper;
     double sum[3] = {0.0, 0.0, 0.0};
     uint32_t coverage = 0;
     for (uint32_t base = 0; base < N; base += 32) {
@@ -73,7 +109,7 @@ point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *
             if (!hit && G.kind != RI_B200_GATHER_OCCLUSION) {
                 double rad[3] = {G.rad[0], G.rad[1], G.rad[2]};
                 if (G.kind == RI_B200_GATHER_IBL) ibl_fetch_dev(G.env, dir, rad);
-                const double brdf = 1.0 / 3.14159265358979323846;
+                const double brdf = (G.qmc && G.kind == RI_B200_GATHER_IBL) ? (double)0.31831f : 1.0 / 3.14159265358979323846;   // ibl.c:139
 #pragma unroll
                 for (int q = 0; q < 3; ++q) c[q] = rad[q] * brdf;
             }
@@ -93,7 +129,7 @@ point_gather_kernel(const SceneView<double> S, const GatherDev G, const double *
             if (coverage > (uint32_t)G.nsamples) coverage = (uint32_t)G.nsamples;
             o[0] = o[1] = o[2] = (double)(float)((double)coverage / (double)(float)G.nsamples);
         } else if (G.kind == RI_B200_GATHER_IBL) {
-            for (int q = 0; q < 3; ++q) o[q] = 3.14159265358979323846 * sum[q] / (double)(G.ntheta * G.nphi);
+            for (int q = 0; q < 3; ++q) o[q] = G.qmc ? sum[q] / (double)G.nsamples : 3.14159265358979323846 * sum[q] / (double)(G.ntheta * G.nphi);
         } else {
             for (int q = 0; q < 3; ++q) o[q] = 3.14159265358979323846 * sum[q] / (double)G.nsamples;
         }
@@ -108,7 +144,7 @@ gather_gen_kernel(const GatherDev G, const double *__restrict__ points, const ui
 {
     const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
     if (gid >= nrays) return;
-    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    const uint32_t N = (uint32_t)G.nper;
     const uint64_t p = p0 + gid / N;
     const uint32_t k = (uint32_t)(gid % N);
     double org[3], dir[3];
@@ -126,7 +162,7 @@ gather_accum_kernel(const GatherDev G, const double *__restrict__ rays, const ui
     const uint64_t lp = ((uint64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;          // point within the chunk
     const uint32_t lane = threadIdx.x & 31u;
     if (lp >= npoints) return;
-    const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
+    const uint32_t N = (uint32_t)G.nper;
     double sum[3] = {0.0, 0.0, 0.0};
     uint32_t coverage = 0;
     for (uint32_t base = 0; base < N; base += 32) {
@@ -142,7 +178,7 @@ gather_accum_kernel(const GatherDev G, const double *__restrict__ rays, const ui
                     const double dir[3] = {rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]};
                     ibl_fetch_dev(G.env, dir, rad);
                 }
-                const double brdf = 1.0 / 3.14159265358979323846;
+                const double brdf = (G.qmc && G.kind == RI_B200_GATHER_IBL) ? (double)0.31831f : 1.0 / 3.14159265358979323846;   // ibl.c:139
 #pragma unroll
                 for (int q = 0; q < 3; ++q) c[q] = rad[q] * brdf;
             }
@@ -162,7 +198,7 @@ gather_accum_kernel(const GatherDev G, const double *__restrict__ rays, const ui
             if (coverage > (uint32_t)G.nsamples) coverage = (uint32_t)G.nsamples;
             o[0] = o[1] = o[2] = (double)(float)((double)coverage / (double)(float)G.nsamples);
         } else if (G.kind == RI_B200_GATHER_IBL) {
-            for (int q = 0; q < 3; ++q) o[q] = 3.14159265358979323846 * sum[q] / (double)(G.ntheta * G.nphi);
+            for (int q = 0; q < 3; ++q) o[q] = G.qmc ? sum[q] / (double)G.nsamples : 3.14159265358979323846 * sum[q] / (double)(G.ntheta * G.nphi);
         } else {
             for (int q = 0; q < 3; ++q) o[q] = 3.14159265358979323846 * sum[q] / (double)G.nsamples;
         }
@@ -170,6 +206,25 @@ gather_accum_kernel(const GatherDev G, const double *__restrict__ rays, const ui
 }
 
 }  // namespace b200
+
+// qmc.c:182-260 faure_permutation, one base (host): p_2 = (0,1); odd b: p_{b-1} with the values >= (b-1)/2 raised by one and (b-1)/2
+// put in the middle; even b: (2 p_{b/2}, 2 p_{b/2} + 1)
+static void faure_perm(int base, int *out)
+{
+    int tmp[128];
+    if (base == 2) { out[0] = 0; out[1] = 1; return; }
+    if (base % 2 != 0) {
+        const int c = (base - 1) / 2;
+        faure_perm(base - 1, tmp);
+        for (int j = 0; j < c; ++j) out[j] = (2 * tmp[j] >= base - 1) ? tmp[j] + 1 : tmp[j];
+        out[c] = c;
+        for (int j = c + 1; j < base; ++j) out[j] = (2 * tmp[j - 1] >= base - 1) ? tmp[j - 1] + 1 : tmp[j - 1];
+    } else {
+        faure_perm(base / 2, tmp);
+        for (int j = 0; j < base / 2; ++j) out[j] = 2 * tmp[j];
+        for (int j = base / 2; j < base; ++j) out[j] = out[j - base / 2] + 1;
+    }
+}
 
 extern "C" int ri_b200_gather_points_f64(ri_b200_accel_t *a, const ri_b200_gather_t *g, const double *points, uint64_t n, double *out3,
                                          uint64_t *nrays_out)
@@ -194,7 +249,17 @@ extern "C" int ri_b200_gather_points_f64(ri_b200_accel_t *a, const ri_b200_gathe
     G.stream_offset = g->stream_offset;
     for (int q = 0; q < 3; ++q) G.rad[q] = g->col[q] * g->intensity;
     G.env.data = nullptr; G.env.width = g->env_width; G.env.height = g->env_height; G.env.st = nullptr; G.env.flags = nullptr; G.env.texcol = nullptr;
-    const uint64_t N = (uint64_t)G.ntheta * G.nphi;
+    G.qmc = g->use_qmc ? 1 : 0; G.qmc_base = 3; G.instance = nullptr;
+    if (G.qmc) {
+        if (g->kind == RI_B200_GATHER_OCCLUSION) return fail("the occlusion() shadeop has no quasi-Monte Carlo branch");
+        static const int primes[25] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97};   // qmc.c:20-31
+        const int dim = g->qmc_dim < 1 ? 1 : g->qmc_dim;
+        if (dim > 24) return fail("qmc_dim %d: primes[dim] is beyond lucille's 100-entry permutation table", g->qmc_dim);
+        G.qmc_base = primes[dim];
+        faure_perm(3, G.perm3); faure_perm(5, G.perm5); faure_perm(G.qmc_base, G.permd);
+    }
+    G.nper = G.qmc ? g->nsamples : G.ntheta * G.nphi;
+    const uint64_t N = (uint64_t)G.nper;
     if (nrays_out) *nrays_out = N * n;
     if (!n) return 0;
 
@@ -208,7 +273,12 @@ extern "C" int ri_b200_gather_points_f64(ri_b200_accel_t *a, const ri_b200_gathe
     double *d_points = (double *)p;
     if (frame_buf(a, 1, n * 3 * sizeof(double), &p)) return -1;
     double *d_out = (double *)p;
-    const uint64_t words = g->stream_offset + 2 * N * n;
+    if (G.qmc && g->qmc_instance) {
+        if (frame_buf(a, 2, n * sizeof(int32_t), &p)) return -1;
+        CUDA_OK(cudaMemcpyAsync(p, g->qmc_instance, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        G.instance = (const int32_t *)p;
+    }
+    const uint64_t words = G.qmc ? 1 : g->stream_offset + 2 * N * n;
     const uint64_t mt_blocks = (words + kMtN - 1) / kMtN;
     if (frame_buf(a, 5, (mt_blocks * kMtN + 4) * 4, &p)) return -1;
     uint32_t *d_mt = (uint32_t *)p;
@@ -219,7 +289,7 @@ extern "C" int ri_b200_gather_points_f64(ri_b200_accel_t *a, const ri_b200_gathe
         G.env.data = (const float *)p;
     }
     CUDA_OK(cudaMemcpyAsync(d_points, points, n * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (mt_stream_launch(a, g->seed, (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks), mt_blocks, d_mt, st)) return -1;
+    if (!G.qmc && mt_stream_launch(a, g->seed, (uint32_t)((mt_blocks + kMtSegBlocks - 1) / kMtSegBlocks), mt_blocks, d_mt, st)) return -1;
     const char *force = getenv("B200_FUSED_AO_TEST");         // test hook: exercise both paths on the same scene
     const bool fused = force ? atoi(force) != 0 : (a->tree.ntris < 4096);
     if (fused) {                                              // one warp per point, one-ray-per-lane traversal

@@ -1074,6 +1074,98 @@ void orc_transport_whitted(const orc_tree *T, const float *env, int ew, int eh, 
  *   kind 2  ri_domelight_sample            ibl.c:231-389      pi * sum(col * intensity / pi) / nsamples on misses
  * points = [n][6] (P, N); one MT19937 stream (randomMT / randomMT2, same generator and seed, random.c:163-247) over the points in
  * order, 2 draws per ray whether it hits or not. */
+/* qmc.c:182-260 faure_permutation, one base: p_2 = (0,1); odd b: p_{b-1} with values >= (b-1)/2 raised by one and (b-1)/2 put in
+ * the middle; even b: (2 p_{b/2}, 2 p_{b/2} + 1). */
+static void faure_perm(int base, int *out)
+{
+    int tmp[128], j;
+    if (base == 2) { out[0] = 0; out[1] = 1; return; }
+    if (base % 2 != 0) {
+        const int c = (base - 1) / 2;
+        faure_perm(base - 1, tmp);
+        for (j = 0; j < c; j++) out[j] = (2 * tmp[j] >= base - 1) ? tmp[j] + 1 : tmp[j];
+        out[c] = c;
+        for (j = c + 1; j < base; j++) out[j] = (2 * tmp[j - 1] >= base - 1) ? tmp[j - 1] + 1 : tmp[j - 1];
+    } else {
+        faure_perm(base / 2, tmp);
+        for (j = 0; j < base / 2; j++) out[j] = 2 * tmp[j];
+        for (j = base / 2; j < base; j++) out[j] = out[j - base / 2] + 1;
+    }
+}
+
+static const int qmc_primes[25] = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97 };
+
+/* qmc.c:329-349 generalized_vdC */
+static double generalized_vdc(int i, int base, const int *perm)
+{
+    double h = 0.0, f, factor;
+    f = factor = 1.0 / (double)base;
+    while (i > 0) {
+        h += (double)perm[i % base] * factor;
+        i /= base;
+        factor *= f;
+    }
+    return h;
+}
+
+static double mod_1(double x) { return x - floor(x); }         /* qmc.c:523-532 */
+
+/* The quasi-Monte Carlo branches (Option "use_qmc"): ri_ibl_sample_cosweight (ibl.c:107-151, gen_qmc_samples :540-581: scrambled
+ * Halton in bases 3 and 5 at index i + inray->i; brdf is the float constant 0.31831f and there is no pi in the result) and
+ * ri_domelight_sample (ibl.c:266-320: Hammersley (i/n, base 3) shifted by ONE scrambled-Halton value u of (inray->i, inray->d) --
+ * both coordinates by u, the v it also computes is never used).  nsamples rays per point, no random numbers.  instance = inray->i
+ * per point (NULL: 0), dim = inray->d (< 1 counts as 1; primes[dim] must stay below 100, the size of lucille's permutation table). */
+void orc_point_gather_qmc(const orc_tree *T, int kind, int nsamples, const double *points, uint64_t n, const int32_t *instance, int dim,
+                          const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out)
+{
+    view_t_f64 V = {0};
+    uint64_t p, nrays = 0;
+    int perm3[3], perm5[5], permd[128], primd, i, k;
+    if (!T->empty) view64(T, &V);
+    if (dim < 1) dim = 1;
+    if (dim > 24) dim = 24;
+    primd = qmc_primes[dim];
+    faure_perm(3, perm3); faure_perm(5, perm5); faure_perm(primd, permd);
+    for (p = 0; p < n; p++) {
+        const double *P = points + 6 * p, *N = P + 3;
+        const int inst = instance ? instance[p] : 0;
+        double basis[3][3], dpower[3] = { 0.0, 0.0, 0.0 }, org[3], dirl[3], dir[3], theta, phi, t, uu, vv, s0, s1, u = 0.0;
+        uint32_t prim;
+        ortho_basis_f64(basis, N);
+        if (kind == 2) u = generalized_vdc(inst, primd, permd);                 /* ibl.c:286-289 */
+        for (i = 0; i < nsamples; i++) {
+            if (kind == 1) {
+                s0 = mod_1(0.0 + generalized_vdc(i + inst, 3, perm3));          /* ibl.c:560-575: dims 1 and 2 */
+                s1 = mod_1(0.0 + generalized_vdc(i + inst, 5, perm5));
+            } else {
+                const int j = (i > nsamples) ? i % nsamples : i;                /* qmc.c:439-442 */
+                s0 = mod_1(u + (double)i / (double)nsamples);                   /* hammersley dim 1 */
+                s1 = mod_1(u + generalized_vdc(j, 3, perm3));                   /* hammersley dim 2: primes[1] */
+            }
+            theta = sqrt(s0);
+            phi = 2.0 * M_PI * s1;
+            dirl[0] = cos(phi) * theta;
+            dirl[1] = sin(phi) * theta;
+            dirl[2] = sqrt(1.0 - theta * theta);
+            for (k = 0; k < 3; k++)
+                dir[k] = dirl[0] * basis[0][k] + dirl[1] * basis[1][k] + dirl[2] * basis[2][k];
+            normalize_f64(dir);
+            for (k = 0; k < 3; k++) org[k] = P[k];
+            if (kind == 1) for (k = 0; k < 3; k++) org[k] += N[k] * 0.0001;
+            nrays++;
+            if (!(T->empty ? 0 : trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL))) {
+                double rad[4], brdf = (kind == 1) ? (double)0.31831f : (double)1.0 / M_PI;
+                if (kind == 1) ibl_fetch(env, ew, eh, dir, rad);
+                else for (k = 0; k < 3; k++) rad[k] = col3[k] * (double)intensity;
+                for (k = 0; k < 3; k++) dpower[k] += rad[k] * brdf;
+            }
+        }
+        for (k = 0; k < 3; k++)
+            out3[3 * p + k] = (kind == 1) ? dpower[k] / (double)nsamples : M_PI * dpower[k] / (double)nsamples;
+    }
+    if (nrays_out) *nrays_out = nrays;
+}
+
 void orc_point_gather(const orc_tree *T, int kind, int nsamples, uint32_t seed, const double *points, uint64_t n,
                       const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out)
 {

@@ -222,4 +222,8 @@ uint64_t orc_splitmix64(uint64_t x);
 void orc_point_gather(const orc_tree *T, int kind, int nsamples, uint32_t seed, const double *points, uint64_t n,
                       const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out);
 
+/* the quasi-Monte Carlo branches of the IBL (kind 1) and dome-light (kind 2) gathers (Option "use_qmc") */
+void orc_point_gather_qmc(const orc_tree *T, int kind, int nsamples, const double *points, uint64_t n, const int32_t *instance, int dim,
+                          const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out);
+
 #endif

@@ -432,8 +432,14 @@ void lref_transport_batch(void *h, int which, const double *rays, uint64_t n, do
 #include "shader.h"
 #include "ibl.h"
 extern void seedMT(unsigned long seed);
+void lref_point_gather_ex(void *h, int kind, int nsamples, const double *points, uint64_t n, const double *col3, double intensity,
+                          int use_qmc, const int32_t *instance, int dim, double *out3);
 void lref_point_gather(void *h, int kind, int nsamples, const double *points, uint64_t n, const double *col3, double intensity,
                        double *out3)
+{ lref_point_gather_ex(h, kind, nsamples, points, n, col3, intensity, 0, NULL, 0, out3); }
+/* use_qmc: Option "use_qmc" for the duration of the call; instance[p] -> inray->i, dim -> inray->d */
+void lref_point_gather_ex(void *h, int kind, int nsamples, const double *points, uint64_t n, const double *col3, double intensity,
+                          int use_qmc, const int32_t *instance, int dim, double *out3)
 {
     lref_scene_t *s = (lref_scene_t *)h;
     ri_render_t *render = ri_render_get();
@@ -445,6 +451,9 @@ void lref_point_gather(void *h, int kind, int nsamples, const double *points, ui
     ri_vector_t P, N, eye, power;
     uint64_t i;
     int k;
+    ri_option_t *opt = render->context->option;
+    const int saved_qmc = opt->use_qmc;
+    opt->use_qmc = use_qmc;
     render->scene = s->scene;
     seedMT((unsigned long)4357);
     seedMT2((unsigned long)4357, 0);
@@ -456,6 +465,7 @@ void lref_point_gather(void *h, int kind, int nsamples, const double *points, ui
     for (i = 0; i < n; i++) {
         for (k = 0; k < 3; k++) { P[k] = points[6 * i + k]; N[k] = points[6 * i + 3 + k]; }
         P[3] = 1.0; N[3] = 0.0;
+        inray.i = instance ? instance[i] : 0; inray.d = dim;
         if (kind == 0) {
             power[0] = power[1] = power[2] = (double)occlusion(&status, P, N, (float)nsamples);
         } else if (kind == 1) {
@@ -466,6 +476,7 @@ void lref_point_gather(void *h, int kind, int nsamples, const double *points, ui
         }
         for (k = 0; k < 3; k++) out3[3 * i + k] = power[k];
     }
+    opt->use_qmc = saved_qmc;
     render->scene = saved;
 }
 

@@ -30,5 +30,11 @@ pts = np.concatenate([st["P"][m][:, :3], st["Ns"][m][:, :3]], axis=1)[:NPOINTS]
 out = dict(ntris=NTRIS, seed=SEED, points=pts, env=env, col=np.array(COL), intensity=INTENSITY, cases=np.array(CASES))
 for kind, ns in CASES:
     out[f"k{kind}_n{ns}"] = rs.point_gather(kind, ns, pts, COL, INTENSITY)
+# the quasi-Monte Carlo branches (Option "use_qmc"): per-point instance numbers (inray->i), dimension inray->d
+QMC_CASES = ((1, 48, 0), (2, 31, 3))                          # (kind, nsamples, dim)
+inst = (np.arange(len(pts)) * 7919 % 5000).astype(np.int32)
+out["qmc_cases"], out["qmc_instance"] = np.array(QMC_CASES), inst
+for kind, ns, dim in QMC_CASES:
+    out[f"q{kind}_n{ns}_d{dim}"] = rs.point_gather_qmc(kind, ns, pts, inst, dim, COL, INTENSITY)
 np.savez_compressed(os.path.join(HERE, "point_gathers.npz"), **out)
 print("point_gathers.npz", len(pts), {k: float(v.mean()) for k, v in out.items() if k.startswith("k")})

@@ -297,6 +297,20 @@ class OracleTree:
                                   _ptr(out), C.byref(nrays))
         return out, nrays.value
 
+    def point_gather_qmc(self, kind: int, nsamples: int, points6: np.ndarray, instance=None, dim: int = 0, env=None,
+                         col=(1.0, 1.0, 1.0), intensity=1.0):
+        """The quasi-Monte Carlo branches (Option "use_qmc") of the IBL (1) and dome-light (2) gathers; instance = inray->i per point."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        inst = None if instance is None else np.ascontiguousarray(instance, dtype=np.int32)
+        c = np.ascontiguousarray(col, dtype=np.float64)
+        out = np.zeros((len(pts), 3), dtype=np.float64)
+        nrays = C.c_uint64(0)
+        self.lib.orc_point_gather_qmc(self.h, kind, nsamples, _ptr(pts), C.c_uint64(len(pts)), None if inst is None else _ptr(inst), dim,
+                                      None if env is None else _ptr(env), 0 if env is None else env.shape[1],
+                                      0 if env is None else env.shape[0], _ptr(c), C.c_double(intensity), _ptr(out), C.byref(nrays))
+        return out, nrays.value
+
     def transport_whitted(self, rays6: np.ndarray, env):
         """Radiance per eye ray of the Whitted refraction tracer with the angular-map environment ``env`` ([h,w,4] float32 or None)."""
         rays6 = np.ascontiguousarray(rays6, dtype=np.float64).reshape(-1, 6)
@@ -379,6 +393,8 @@ class Oracle:
         lib.orc_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_point_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        lib.orc_point_gather_qmc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -509,6 +525,18 @@ class ReferenceScene:
             self.lib.lref_point_gather(self.h, kind, nsamples, _ptr(pts), C.c_uint64(len(pts)), _ptr(c), C.c_double(intensity), _ptr(out))
         return out
 
+    def point_gather_qmc(self, kind: int, nsamples: int, points6: np.ndarray, instance=None, dim: int = 0, col=(1.0, 1.0, 1.0),
+                         intensity=1.0) -> np.ndarray:
+        """The same reference functions with Option "use_qmc" on (ibl.c:107-151, 266-320); instance[p] -> inray->i, dim -> inray->d."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        inst = None if instance is None else np.ascontiguousarray(instance, dtype=np.int32)
+        c = np.ascontiguousarray(col, dtype=np.float64)
+        out = np.zeros((len(pts), 3), dtype=np.float64)
+        with _quiet():
+            self.lib.lref_point_gather_ex(self.h, kind, nsamples, _ptr(pts), C.c_uint64(len(pts)), _ptr(c), C.c_double(intensity), 1,
+                                          None if inst is None else _ptr(inst), dim, _ptr(out))
+        return out
+
     def set_attributes(self, colors, st, geom_flags):
         """colors [n,3,3], st [n,3,2] (either may be None); geom_flags per geom: 1 Cs, 2 shared st, 4 unshared st, 8 two-sided."""
         c = None if colors is None else np.ascontiguousarray(colors, dtype=np.float64)
@@ -553,6 +581,8 @@ class Reference:
         lib.lref_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.lref_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_point_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_void_p]
+        lib.lref_point_gather_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int,
+                                             C.c_void_p, C.c_int, C.c_void_p]
         lib.lref_scene_set_attr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_intersect_ext.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,

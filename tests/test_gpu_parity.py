@@ -670,6 +670,21 @@ def test_point_gathers(oracle, golden_dir):
                 assert np.array_equal(got, want), (kind, ns)
         os.environ.pop("B200_FUSED_AO_TEST", None)
         assert np.array_equal(paths[0], paths[1])
+    for kind, ns, dim in g["qmc_cases"]:           # Option "use_qmc": the quasi-Monte Carlo branches, both device forms
+        kind, ns, dim = int(kind), int(ns), int(dim)
+        want = g[f"q{kind}_n{ns}_d{dim}"]
+        paths = []
+        for fused in ("1", "0"):
+            os.environ["B200_FUSED_AO_TEST"] = fused
+            got, nrays = a.gather_points(kind, ns, pts, env if kind == accel.GATHER_IBL else None, col, inten, qmc=True,
+                                         qmc_instance=g["qmc_instance"], qmc_dim=dim)
+            paths.append(got)
+            assert nrays == len(pts) * ns
+            assert np.allclose(got, want, rtol=1e-9, atol=0.0) if kind == accel.GATHER_IBL else np.array_equal(got, want)
+        os.environ.pop("B200_FUSED_AO_TEST", None)
+        assert np.array_equal(paths[0], paths[1])
+    with pytest.raises(accel.B200Error):
+        a.gather_points(accel.GATHER_OCCLUSION, 12, pts, qmc=True)
     # second half of the points as a batch of its own: same numbers as in the whole batch when the stream continues
     half = len(pts) // 2
     whole, _ = a.gather_points(accel.GATHER_DOME, 27, pts, None, col, inten)

@@ -185,3 +185,7 @@ def test_point_gathers_golden(oracle, golden_dir):
     for kind, ns in g["cases"]:
         got, _ = t.point_gather(int(kind), int(ns), g["points"], g["env"] if kind == 1 else None, g["col"], float(g["intensity"]))
         assert np.array_equal(got, g[f"k{kind}_n{ns}"]), (kind, ns)
+    for kind, ns, dim in g["qmc_cases"]:                       # Option "use_qmc" branches
+        got, _ = t.point_gather_qmc(int(kind), int(ns), g["points"], g["qmc_instance"], int(dim), g["env"] if kind == 1 else None,
+                                    g["col"], float(g["intensity"]))
+        assert np.array_equal(got, g[f"q{kind}_n{ns}_d{dim}"]), (kind, ns, dim)

@@ -203,3 +203,23 @@ def test_point_gathers_called_directly(oracle, ref, kind, nsamples):
     assert nrays == len(pts) * 3 * nth * nth
     assert np.array_equal(got, want)
     assert np.ptp(got[:, 0]) > 0.05                     # neither all open nor all blocked
+
+
+@pytest.mark.parametrize("kind,nsamples,dim", [(1, 48, 0), (1, 7, 0), (2, 48, 0), (2, 31, 3), (2, 16, 24)])
+def test_point_gathers_qmc_called_directly(oracle, ref, kind, nsamples, dim):
+    """The quasi-Monte Carlo branches of the same gathers (Option "use_qmc"): scrambled Halton / Hammersley points from lucille's
+    Faure permutation table, per-point instance numbers (inray->i) and dimension (inray->d) -- bit-identical to the compiled
+    reference."""
+    tris = scenes.triangle_soup(20000, 9)
+    rs, ot = ref.build(tris), oracle.build(tris)
+    env = ol.test_texture(32, 32, 5)
+    rs.set_envmap(env)
+    pts = _shading_points(ot)[:1200]
+    inst = (np.arange(len(pts)) * 7919 % 5000).astype(np.int32)
+    col, inten = (0.9, 0.5, 0.25), 2.5
+    for instance in (None, inst):
+        want = rs.point_gather_qmc(kind, nsamples, pts, instance, dim, col, inten)
+        got, nrays = ot.point_gather_qmc(kind, nsamples, pts, instance, dim, env if kind == 1 else None, col, inten)
+        assert nrays == len(pts) * nsamples
+        assert np.array_equal(got, want)
+    assert np.ptp(got[:, 0]) > 0.05
