@@ -81,6 +81,78 @@ whitted_kernel(const SceneView<double> S, const FrameDev F, const uint32_t *__re
     if ((threadIdx.x & 31) == 0 && traced) atomicAdd(nrays_out, traced);
 }
 
+// ---- wavefront form (scenes past a few thousand triangles): the chains advance one refraction at a time, every generation of rays
+// goes through the pooled closest-hit traverser (pool_closest.cuh, fp64 records) and the chains that go on are compacted.
+__global__ void __launch_bounds__(kBlock)
+eye_rays_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, const double *__restrict__ jitter, const uint64_t nsamples,
+                double *__restrict__ rays_out, uint32_t *__restrict__ ids_out, double *__restrict__ rad_out)
+{
+    const uint64_t s = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (s >= nsamples) return;
+    const uint64_t p = s / (uint64_t)F.spp;
+    const int sub = (int)(s - p * (uint64_t)F.spp);
+    const uint32_t pix = pixels[p];
+    double org[3], dir[3];
+    camera_ray(F, (int)(pix & 0xffffu), (int)(pix >> 16), jitter[2 * sub], jitter[2 * sub + 1], org, dir);
+    double2 *o = reinterpret_cast<double2 *>(rays_out) + 3 * s;
+    o[0] = make_double2(org[0], org[1]);
+    o[1] = make_double2(org[2], dir[0]);
+    o[2] = make_double2(dir[1], dir[2]);
+    ids_out[s] = (uint32_t)s;
+    rad_out[3 * s] = 0.0; rad_out[3 * s + 1] = 0.0; rad_out[3 * s + 2] = 0.0;
+}
+
+// generation `depth` has been traced: a chain that left the scene takes the environment's radiance along its ray; a chain that hit
+// something refracts (whitted.c:31-83) and joins generation depth + 1, unless it already is the eighth bounce (MAX_TRACE_DEPTH)
+__global__ void __launch_bounds__(kBlock)
+whitted_step_kernel(const SceneView<double> S, const TexDev env, const int depth, const int hitmask_only, const uint32_t n,
+                    const double *__restrict__ rays, const uint32_t *__restrict__ ids, const ri_b200_hit_f64 *__restrict__ hits,
+                    double *__restrict__ rays_next, uint32_t *__restrict__ ids_next, unsigned int *__restrict__ n_next,
+                    double *__restrict__ rad_out)
+{
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    bool go_on = false;
+    double org[3], dir[3];
+    uint32_t s = 0;
+    if (i < n) {
+        s = ids[i];
+        RayIO<double>::load(rays, i, org, dir);
+        const ri_b200_hit_f64 h = hits[i];
+        if (!h.hit) {
+            if (!hitmask_only && env.data) {
+                double rad[3] = {0.0, 0.0, 0.0};
+                ibl_fetch_dev(env, dir, rad);
+                rad_out[3 * (uint64_t)s] = rad[0]; rad_out[3 * (uint64_t)s + 1] = rad[1]; rad_out[3 * (uint64_t)s + 2] = rad[2];
+            }
+        } else if (hitmask_only) {
+            rad_out[3 * (uint64_t)s] = 1.0; rad_out[3 * (uint64_t)s + 1] = 1.0; rad_out[3 * (uint64_t)s + 2] = 1.0;
+        } else if (depth < 8) {
+            ri_b200_state_f64 st;
+            state_from_hit(S.tris, S.slot_of_prim, org, dir, h.t, h.prim, st, S.normals, h.u, h.v);
+            double I[3] = {dir[0], dir[1], dir[2]}, Rd[3];
+            normalize3(I);
+            refract_dev(Rd, I, st.Ns, 1.33);
+            for (int k = 0; k < 3; ++k) { org[k] = st.P[k] + 1.0e-7 * Rd[k]; dir[k] = Rd[k]; }
+            go_on = true;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, go_on);
+    if (m) {
+        const unsigned lane = threadIdx.x & 31u;
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(n_next, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (go_on) {
+            const uint64_t pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+            double2 *o = reinterpret_cast<double2 *>(rays_next) + 3 * pos;
+            o[0] = make_double2(org[0], org[1]);
+            o[1] = make_double2(org[2], dir[0]);
+            o[2] = make_double2(dir[1], dir[2]);
+            ids_next[pos] = s;
+        }
+    }
+}
+
 // render.c:805,820 + bucket_write: box average of the sub-sample radiances, float RGB at row H-1-y
 __global__ void resolve_samples_kernel(const FrameDev F, const uint32_t *__restrict__ pixels, uint64_t npixels, const double *__restrict__ rad,
                                        float *__restrict__ rgb)
@@ -162,8 +234,39 @@ static int render_eye_transport(ri_b200_accel_t *a, const ri_b200_frame_t *f, co
     CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(d_nrays, 0, 16, st));
     CUDA_OK(cudaMemsetAsync(d_rgb, 0, fb_bytes, st));
-    whitted_kernel<<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(make_view<double>(a), F, d_pix, d_jit, nsamples, env, d_rad, d_nrays, hitmask_only);
-    LAUNCHED();
+    const char *force = getenv("B200_FUSED_AO_TEST");         // test hook: exercise both paths on the same scene
+    const bool fused = force ? atoi(force) != 0 : (a->tree.ntris < 4096);
+    uint64_t wave_rays = 0;
+    if (fused || nsamples == 0) {                             // one lane per chain
+        whitted_kernel<<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, smem, st>>>(make_view<double>(a), F, d_pix, d_jit, nsamples, env, d_rad, d_nrays, hitmask_only);
+        LAUNCHED();
+    } else {                                                  // one generation of rays at a time through the pooled traverser
+        if (nsamples >= 0xfffffff0ull) return fail("too many samples for 32-bit chain ids");
+        if (frame_buf(a, 8, 2 * nsamples * 6 * sizeof(double), &p)) return -1;
+        double *d_rays[2] = {(double *)p, (double *)p + nsamples * 6};
+        if (frame_buf(a, 9, 2 * nsamples * sizeof(uint32_t) + 64, &p)) return -1;
+        uint32_t *d_ids[2] = {(uint32_t *)p, (uint32_t *)p + nsamples};
+        unsigned int *d_cnt = (unsigned int *)((uint32_t *)p + 2 * nsamples);            // [16] live chains per generation
+        if (frame_buf(a, 10, nsamples * sizeof(ri_b200_hit_f64), &p)) return -1;
+        ri_b200_hit_f64 *d_hits = (ri_b200_hit_f64 *)p;
+        CUDA_OK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned int), st));
+        eye_rays_kernel<<<(unsigned)((nsamples + kBlock - 1) / kBlock), kBlock, 0, st>>>(F, d_pix, d_jit, nsamples, d_rays[0], d_ids[0], d_rad);
+        LAUNCHED();
+        uint32_t live = (uint32_t)nsamples;
+        const SceneView<double> S = make_view<double>(a);
+        for (int depth = 0, cur = 0; depth <= 8 && live; ++depth, cur ^= 1) {
+            wave_rays += live;
+            if (launch_trace<double, false, false>(a, d_rays[cur], live, d_hits, nullptr, nullptr, st)) return -1;
+            whitted_step_kernel<<<(live + kBlock - 1) / kBlock, kBlock, 0, st>>>(S, env, depth, hitmask_only, live, d_rays[cur], d_ids[cur], d_hits,
+                                                                               d_rays[cur ^ 1], d_ids[cur ^ 1], d_cnt + depth + 1, d_rad);
+            LAUNCHED();
+            CUDA_OK(cudaMemcpyAsync(a->h_pin, d_cnt + depth + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaStreamSynchronize(st));
+            live = *(unsigned int *)a->h_pin;
+        }
+        CUDA_OK(cudaMemcpyAsync(d_nrays, &wave_rays, 8, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaStreamSynchronize(st));                   // wave_rays is a local
+    }
     resolve_samples_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(F, d_pix, npix, d_rad, d_rgb);
     LAUNCHED();
     CUDA_OK(cudaGetLastError());

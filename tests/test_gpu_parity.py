@@ -550,15 +550,18 @@ def test_whitted_frame(oracle):
     cam[:16] = c2w.reshape(16)
     cam[16], cam[17], cam[20], cam[21], cam[22], cam[23] = flen, 0, 2, 2, 64, 32
     ot = oracle.build(tris)
-    for e in (env, None):
-        rgb, stats = a.render_whitted(fr, e)
-        want, nrays = ot.render_whitted(ol.frame_params(cam, 96, 72), e)
-        assert stats.nrays == nrays
-        assert np.allclose(rgb, want, rtol=1e-9, atol=0.0)
-    assert not rgb.any()                                   # no environment: the transport returns black
-    mask, stats = a.render_sample(fr)                      # ri_transport_sample: white where the eye ray hits
-    want, nrays = ot.render_hitmask(ol.frame_params(cam, 96, 72))
-    assert stats.nrays == nrays and np.array_equal(mask, want) and 0.05 < mask.mean() < 0.95
+    for fused in ("1", "0"):                               # one lane per chain, and generation by generation through the pooled traverser
+        os.environ["B200_FUSED_AO_TEST"] = fused
+        for e in (env, None):
+            rgb, stats = a.render_whitted(fr, e)
+            want, nrays = ot.render_whitted(ol.frame_params(cam, 96, 72), e)
+            assert stats.nrays == nrays
+            assert np.allclose(rgb, want, rtol=1e-9, atol=0.0)
+        assert not rgb.any()                               # no environment: the transport returns black
+        mask, stats = a.render_sample(fr)                  # ri_transport_sample: white where the eye ray hits
+        want, nrays = ot.render_hitmask(ol.frame_params(cam, 96, 72))
+        assert stats.nrays == nrays and np.array_equal(mask, want) and 0.05 < mask.mean() < 0.95
+    os.environ.pop("B200_FUSED_AO_TEST", None)
 
 
 def test_peer_framebuffer_path_single_rank(golden_dir):
