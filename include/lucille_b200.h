@@ -308,6 +308,14 @@ int ri_b200_sunsky_rgb(const ri_b200_sunsky_t *sky, const float *dirs, uint64_t 
  * (HOST) when cap is large enough; byte-identical to the file the reference writes. */
 int64_t ri_b200_hdr_encode(const float *rgb, int width, int height, uint8_t *out, uint64_t cap, int device, int rgb_on_device);
 
+/* The other float display driver: the byte stream lucille's socket driver sends to its viewer for a finished frame
+ * (display/sockdrv.c:118-262 sock_dd_open / sock_dd_write / sock_dd_close, sockdrv_defs.h), packed on the device -- header, one
+ * message per 1024 pixels in bucket_write's order (render.c:919-979; frame->bucket_size), finish command; the remainder below 1024
+ * pixels is never sent by the reference and is not here either.  The stream only: connect() and send() stay with the host.  rgb as
+ * for ri_b200_hdr_encode; frame gives width, height and bucket_size.  Returns the stream's size (writes it when cap suffices), -1 on
+ * failure. */
+int64_t ri_b200_sockdrv_encode(const float *rgb, const ri_b200_frame_t *frame, uint8_t *out, uint64_t cap, int device, int rgb_on_device);
+
 /* ---- replaces ri_beam_set + ri_bvh_intersect_beam_visibility (beam.c:332-466, bvh.c:612-667) for a batch of beams.
  * beams: HOST [n][15] doubles = org.xyz, dir0.xyz .. dir3.xyz (consecutive corners of the frustum).  out[i] = RI_BEAM_MISS_COMPLETELY 0 /
  * RI_BEAM_HIT_COMPLETELY 1 / RI_BEAM_HIT_PARTIALLY 2 (beam.h:27-29), or -1 where ri_beam_set would fail (corner directions

@@ -151,6 +151,7 @@ ABI = [
     ("ri_b200_render_whitted", _I, [_P, _P, _P, _I, _I, _P, _P]),
     ("ri_b200_render_sample", _I, [_P, _P, _P, _P]),
     ("ri_b200_hdr_encode", C.c_int64, [_P, _I, _I, _P, _U64, _I, _I]),
+    ("ri_b200_sockdrv_encode", C.c_int64, [_P, _P, _P, _U64, _I, _I]),
     ("ri_b200_beam_visibility_batch", _I, [_P, _P, _U64, _P]),
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_pathtrace_tiles_dev", _I, [_P, _P, _P, _P, _P]),
@@ -559,6 +560,20 @@ class Gather(C.Structure):
 
 
 HIT_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+
+
+def sockdrv_encode(rgb, frame: Frame, device: int = 0) -> bytes:
+    """Byte stream of lucille's socket display driver for the finished frame ``rgb`` [h,w,3] (ri_b200_sockdrv_encode)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+    lib = load_library()
+    need = lib.ri_b200_sockdrv_encode(_ptr(rgb), C.byref(frame), None, 0, device, 0)
+    if need < 0:
+        raise B200Error(last_error())
+    out = np.zeros(need, dtype=np.uint8)
+    n = lib.ri_b200_sockdrv_encode(_ptr(rgb), C.byref(frame), _ptr(out), need, device, 0)
+    if n < 0:
+        raise B200Error(last_error())
+    return out[:n].tobytes()
 
 
 def peer_alloc(nbytes: int, device: int = 0):

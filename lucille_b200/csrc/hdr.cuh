@@ -187,3 +187,70 @@ extern "C" int64_t ri_b200_hdr_encode(const float *rgb, int width, int height, u
     cudaFree(d_rgb); cudaFree(d_planes); cudaFree(d_tmp); cudaFree(d_len); cudaFree(d_off); cudaFree(d_body);
     return rc ? -1 : result;
 }
+
+// ---- the other display driver of the reference that takes float pixels: the socket driver's wire format (display/sockdrv.c:118-262,
+// sockdrv_defs.h).  [COMMAND_NEW=0][8][width][height], one [COMMAND_PIXEL=2][24*1024] message per MAXPACKETS = 1024
+// pixels {int x, int y, float r, g, b, 1.0f} in the order bucket_write hands them to the driver (render.c:919-979), [COMMAND_FINISH=1].
+// The pixels left over when the frame is not a multiple of 1024 are never sent by the reference (sock_dd_close does not flush its
+// packet array) -- reproduced.  This is the stream only; opening the socket and send() stay with the host.
+namespace b200 {
+__global__ void sock_pack_kernel(const float *__restrict__ rgb, const uint32_t *__restrict__ pixels, const uint64_t nsent, const int width,
+                                 const int height, unsigned char *__restrict__ out)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nsent) return;
+    const uint32_t pix = pixels[q];
+    const int x = (int)(pix & 0xffffu), y = height - (int)(pix >> 16) - 1;
+    const uint64_t g = q >> 10, k = q & 1023u;
+    unsigned char *msg = out + 16 + g * (8 + 24 * 1024);
+    if (k == 0) { int32_t *h = reinterpret_cast<int32_t *>(msg); h[0] = 2; h[1] = 24 * 1024; }
+    int32_t *o = reinterpret_cast<int32_t *>(msg + 8 + k * 24);
+    const float *px = rgb + 3 * ((uint64_t)y * width + x);
+    o[0] = x; o[1] = y;
+    o[2] = __float_as_int(px[0]); o[3] = __float_as_int(px[1]); o[4] = __float_as_int(px[2]); o[5] = __float_as_int(1.0f);
+}
+}  // namespace b200
+
+extern "C" int64_t ri_b200_sockdrv_encode(const float *rgb, const ri_b200_frame_t *f, uint8_t *out, uint64_t cap, int device, int rgb_on_device)
+{
+    using namespace b200;
+    if (!rgb || !f || f->width < 1 || f->height < 1 || f->width > 65535 || f->height > 65535) return fail("bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: libb200accel has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail("bad device %d", device);
+    CUDA_OK(cudaSetDevice(device));
+    ri_b200_frame_t whole = *f;
+    whole.rank = 0; whole.world = 1;                             // the display sees the whole frame
+    std::vector<uint32_t> pix;
+    pixel_order(whole, pix);
+    const uint64_t npix = pix.size(), ngroups = npix / 1024, nsent = ngroups * 1024;
+    const int64_t total = 16 + (int64_t)ngroups * (8 + 24 * 1024) + 4;
+    if (!out || cap < (uint64_t)total) return total;
+    float *d_rgb = nullptr;
+    uint32_t *d_pix = nullptr;
+    unsigned char *d_out = nullptr;
+    auto body = [&]() -> int {
+        const float *src = rgb;
+        if (!rgb_on_device) {
+            CUDA_OK(cudaMalloc((void **)&d_rgb, npix * 3 * sizeof(float)));
+            CUDA_OK(cudaMemcpy(d_rgb, rgb, npix * 3 * sizeof(float), cudaMemcpyHostToDevice));
+            src = d_rgb;
+        }
+        CUDA_OK(cudaMalloc((void **)&d_pix, (nsent + 1) * sizeof(uint32_t)));
+        CUDA_OK(cudaMalloc((void **)&d_out, (size_t)total));
+        if (nsent) {
+            CUDA_OK(cudaMemcpy(d_pix, pix.data(), nsent * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            sock_pack_kernel<<<(unsigned)((nsent + 255) / 256), 256>>>(src, d_pix, nsent, f->width, f->height, d_out);
+            LAUNCHED();
+            CUDA_OK(cudaGetLastError());
+        }
+        CUDA_OK(cudaMemcpy(out, d_out, (size_t)total, cudaMemcpyDeviceToHost));
+        const int32_t head[4] = {0, 8, f->width, f->height}, fin = 1;
+        std::memcpy(out, head, 16);
+        std::memcpy(out + total - 4, &fin, 4);
+        return 0;
+    };
+    const int rc = body();
+    cudaFree(d_rgb); cudaFree(d_pix); cudaFree(d_out);
+    return rc ? -1 : total;
+}

@@ -1067,6 +1067,42 @@ void orc_transport_whitted(const orc_tree *T, const float *env, int ew, int eh, 
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ socket display driver stream
+ * display/sockdrv.c:118-262 + sockdrv_defs.h: [COMMAND_NEW=0][8][width][height], then one [COMMAND_PIXEL=2][24*1024] message per
+ * MAXPACKETS = 1024 pixels {int x, int y, float r, g, b, 1.0f} in the order bucket_write hands them over (render.c:919-979: buckets in
+ * spiral order, rows inside a bucket, y = H-1-row), then [COMMAND_FINISH=1].  Pixels left over when the frame is not a multiple of
+ * 1024 are never sent (sock_dd_close does not flush gpackets) -- reproduced.  rgb = [height][width][3] floats in display order. */
+uint64_t orc_sockdrv_encode(const float *rgb, int width, int height, int bucket_size, unsigned char *out, uint64_t cap)
+{
+    int nb_max = (width / bucket_size + 1) * (height / bucket_size + 1);
+    int32_t *buckets = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)nb_max);
+    int nb = orc_bucket_list(width, height, bucket_size, buckets, nb_max), b, sx, sy;
+    const uint64_t npix = (uint64_t)width * height, ngroups = npix / 1024;
+    const uint64_t need = 16 + ngroups * (8 + 24 * 1024) + 4;
+    uint64_t count = 0;
+    unsigned char *w = out;
+    if (!out || cap < need) { free(buckets); return need; }
+    { int32_t h[4] = { 0, 8, width, height }; memcpy(w, h, 16); w += 16; }
+    for (b = 0; b < nb; b++) {
+        const int bx = buckets[4 * b], by = buckets[4 * b + 1], bw = buckets[4 * b + 2], bh = buckets[4 * b + 3];
+        for (sy = 0; sy < bh; sy++) {
+            for (sx = 0; sx < bw; sx++) {
+                const int x = sx + bx, y = height - (sy + by) - 1;
+                const float *px = rgb + 3 * ((size_t)y * width + x);
+                int32_t xy[2] = { x, y };
+                float col[4] = { px[0], px[1], px[2], 1.0f };
+                if (count / 1024 >= ngroups) continue;                         /* the unsent remainder */
+                if (count % 1024 == 0) { int32_t h[2] = { 2, 24 * 1024 }; memcpy(w, h, 8); w += 8; }
+                memcpy(w, xy, 8); memcpy(w + 8, col, 16); w += 24;
+                count++;
+            }
+        }
+    }
+    { int32_t fin = 1; memcpy(w, &fin, 4); w += 4; }
+    free(buckets);
+    return (uint64_t)(w - out);
+}
+
 /* ------------------------------------------------------------------ hemisphere gathers at shading points
  * The per-point loops of three more ri_raytrace callers, Monte Carlo branches (Option use_qmc defaults to 0, option.c:139):
  *   kind 0  occlusion() shadeop            shader.c:680-768   coverage / nsamples (float)

@@ -226,4 +226,7 @@ void orc_point_gather(const orc_tree *T, int kind, int nsamples, uint32_t seed, 
 void orc_point_gather_qmc(const orc_tree *T, int kind, int nsamples, const double *points, uint64_t n, const int32_t *instance, int dim,
                           const float *env, int ew, int eh, const double *col3, double intensity, double *out3, uint64_t *nrays_out);
 
+/* byte stream of the socket display driver (display/sockdrv.c) for a finished frame; returns the size (writes when cap suffices) */
+uint64_t orc_sockdrv_encode(const float *rgb, int width, int height, int bucket_size, unsigned char *out, uint64_t cap);
+
 #endif

@@ -480,6 +480,60 @@ void lref_point_gather_ex(void *h, int kind, int nsamples, const double *points,
     render->scene = saved;
 }
 
+/* The byte stream the reference's socket display driver (display/sockdrv.c) sends for a frame: a listener on 127.0.0.1:DEFAULT_PORT in
+ * this process stands in for the viewer, sock_dd_open/write/close are called the way bucket_write does (render.c:919-979: pixels in
+ * `pixels` order, (x, y) = display coordinates), everything received is returned.  Returns the number of bytes, -1 on failure. */
+#include <sys/socket.h>
+#include <netinet/in.h>
+#include <arpa/inet.h>
+#include "sockdrv.h"
+#include "sockdrv_defs.h"
+typedef struct { int lfd; unsigned char *buf; size_t cap, len; } sock_capture_t;
+static void *sock_capture_main(void *arg)
+{
+    sock_capture_t *c = (sock_capture_t *)arg;
+    int fd = accept(c->lfd, NULL, NULL);
+    if (fd < 0) return NULL;
+    for (;;) {
+        ssize_t r;
+        if (c->len == c->cap) break;
+        r = recv(fd, c->buf + c->len, c->cap - c->len, 0);
+        if (r <= 0) break;
+        c->len += (size_t)r;
+    }
+    close(fd);
+    return NULL;
+}
+int64_t lref_sockdrv_stream(const float *rgb_display, int width, int height, const uint32_t *pixels_xy, uint64_t npixels,
+                            unsigned char *out, uint64_t cap)
+{
+    struct sockaddr_in addr;
+    sock_capture_t c;
+    pthread_t th;
+    uint64_t i;
+    int one = 1;
+    c.lfd = socket(AF_INET, SOCK_STREAM, 0);
+    if (c.lfd < 0) return -1;
+    setsockopt(c.lfd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    memset(&addr, 0, sizeof(addr));
+    addr.sin_family = AF_INET; addr.sin_port = htons(DEFAULT_PORT); addr.sin_addr.s_addr = inet_addr(LOCALADDR);
+    if (bind(c.lfd, (struct sockaddr *)&addr, sizeof(addr)) != 0 || listen(c.lfd, 1) != 0) { close(c.lfd); return -1; }
+    c.buf = out; c.cap = cap; c.len = 0;
+    pthread_create(&th, NULL, sock_capture_main, &c);
+    if (!sock_dd_open("capture", width, height, 32, "rgb", "float")) { close(c.lfd); pthread_cancel(th); pthread_join(th, NULL); return -1; }
+    for (i = 0; i < npixels; i++) {                       /* pixels_xy: x | y << 16, y already the display row */
+        const int x = (int)(pixels_xy[i] & 0xffffu), y = (int)(pixels_xy[i] >> 16);
+        sock_dd_write(x, y, rgb_display + 3 * ((size_t)y * width + x));
+    }
+    sock_dd_close();
+    pthread_join(th, NULL);
+    close(c.lfd);
+    /* the driver's packet counter is a static that outlives the frame (a lucille process renders one frame): bring it back to zero
+     * so that the next capture starts like a fresh process.  The descriptor is closed, the one send() this triggers fails with EBADF. */
+    { const float zero[3] = { 0.0f, 0.0f, 0.0f }; for (i = npixels % (MAXPACKETS); i % (MAXPACKETS) != 0; i++) sock_dd_write(0, 0, zero);   /* MAXPACKETS is an unparenthesised 32*32 */ }
+    return (int64_t)c.len;
+}
+
 /* reference traversal counters (only meaningful in libluciref_stat.so; bvh.c:146,686-688) */
 extern ri_bvh_stat_traversal_t g_stattrav;
 void lref_stats_reset(void) { memset(&g_stattrav, 0, sizeof(g_stattrav)); }

@@ -399,11 +399,22 @@ class Oracle:
         lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_render_hitmask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.orc_sockdrv_encode.restype = C.c_uint64
+        lib.orc_sockdrv_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_hdr_encode.restype = C.c_uint64
         lib.orc_hdr_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_sunsky.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib = lib
+
+    def sockdrv_encode(self, rgb: np.ndarray, bucket_size: int = 32) -> bytes:
+        """Byte stream of the reference's socket display driver for the finished frame ``rgb`` [h,w,3] (display order)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        h, w = rgb.shape[:2]
+        need = self.lib.orc_sockdrv_encode(_ptr(rgb), w, h, bucket_size, None, 0)
+        out = np.zeros(need, dtype=np.uint8)
+        n = self.lib.orc_sockdrv_encode(_ptr(rgb), w, h, bucket_size, _ptr(out), need)
+        return out[:n].tobytes()
 
     def texture_fetch(self, rgba: np.ndarray, uv: np.ndarray) -> np.ndarray:
         rgba = np.ascontiguousarray(rgba, dtype=np.float32)
@@ -588,10 +599,25 @@ class Reference:
         lib.lref_sunsky_eval.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_void_p]
         lib.lref_sunsky_eval.restype = None
+        lib.lref_sockdrv_stream.restype = C.c_int64
+        lib.lref_sockdrv_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         lib.lref_hdr_file.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         lib.lref_texture_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         self.lib = lib
         self.stats = stats
+
+    def sockdrv_stream(self, rgb: np.ndarray, pixels_xy: np.ndarray) -> bytes:
+        """What sock_dd_open / sock_dd_write / sock_dd_close of the compiled reference put on the wire for this frame: a listener in
+        this process plays the viewer.  pixels_xy = display coordinates (x | y << 16) in the order bucket_write writes them."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        pix = np.ascontiguousarray(pixels_xy, dtype=np.uint32)
+        h, w = rgb.shape[:2]
+        out = np.zeros(64 + len(pix) * 25, dtype=np.uint8)
+        with _quiet():
+            n = self.lib.lref_sockdrv_stream(_ptr(rgb), w, h, _ptr(pix), C.c_uint64(len(pix)), _ptr(out), C.c_uint64(len(out)))
+        if n < 0:
+            raise RuntimeError("socket capture failed (port 12346 busy?)")
+        return out[:n].tobytes()
 
     def sunsky_eval(self, dirs: np.ndarray, latitude=35.39, longitude=139.44, sm=9.0, jd=20, tod=10.5, turbidity=2.0):
         """ri_sunsky_init + ri_sunsky_get_sky_rgb of the compiled reference: (rgb [n][3] float32, 21-double parameter record)."""

@@ -452,6 +452,25 @@ def test_hdr_output_step_on_device(oracle, golden_dir):
     assert accel.hdr_encode(d_rgb, 160, 120) == oracle.hdr_encode(want)
 
 
+def test_socket_display_stream_on_device(oracle, golden_dir):
+    """SURVEY 8f rank 4, second half: ri_b200_sockdrv_encode packs the byte stream lucille's socket display driver sends -- equal to the
+    oracle's (pinned on CPU to the compiled driver talking to a listener) and to the committed digests of the reference's own stream:
+    frames that are a multiple of 1024 pixels, frames with an unsent remainder, frames smaller than one message."""
+    import hashlib
+    _need_gpu()
+    g = np.load(os.path.join(golden_dir, "sockdrv.npz"))
+    frames = dict(ol.hdr_cases())
+    frames["c1"] = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
+    frames["sunsky"] = np.load(os.path.join(golden_dir, "sunsky.npz"))["frame_rgb"]
+    frames["exact"] = np.random.default_rng(5).uniform(0, 1, (64, 96, 3)).astype(np.float32)          # 6 messages, nothing left over
+    for name, rgb in frames.items():
+        h, w = rgb.shape[:2]
+        data = accel.sockdrv_encode(rgb, accel.make_frame(np.eye(4).reshape(16), 1.0, False, w, h, 1, 1))
+        assert data == oracle.sockdrv_encode(rgb), name
+        if name + "_size" in g:
+            assert len(data) == int(g[name + "_size"]) and hashlib.sha256(data).hexdigest() == str(g[name + "_sha256"]), name
+
+
 def test_hit_state_colours_texcoords_inside(oracle):
     """Row a8 completed: E, I, vertex colours, st and the back-side flag of ri_intersection_state_build on the device, bit-identical
     to the oracle (which tests/test_oracle_vs_reference.py pins to the compiled reference on the same kind of scene)."""

@@ -189,3 +189,16 @@ def test_point_gathers_golden(oracle, golden_dir):
         got, _ = t.point_gather_qmc(int(kind), int(ns), g["points"], g["qmc_instance"], int(dim), g["env"] if kind == 1 else None,
                                     g["col"], float(g["intensity"]))
         assert np.array_equal(got, g[f"q{kind}_n{ns}_d{dim}"]), (kind, ns, dim)
+
+
+def test_socket_display_stream_golden(oracle, golden_dir):
+    """The socket display driver's byte stream for the committed frames (sha256 + size in sockdrv.npz, captured from the compiled
+    reference by tests/golden/make_sockdrv_golden.py)."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "sockdrv.npz"))
+    frames = dict(ol.hdr_cases())
+    frames["c1"] = np.load(os.path.join(golden_dir, "c1_frame_160x120.npz"))["rgb"]
+    frames["sunsky"] = np.load(os.path.join(golden_dir, "sunsky.npz"))["frame_rgb"]
+    for name, rgb in frames.items():
+        data = oracle.sockdrv_encode(rgb)
+        assert len(data) == int(g[name + "_size"]) and hashlib.sha256(data).hexdigest() == str(g[name + "_sha256"]), name

@@ -223,3 +223,22 @@ def test_point_gathers_qmc_called_directly(oracle, ref, kind, nsamples, dim):
         assert nrays == len(pts) * nsamples
         assert np.array_equal(got, want)
     assert np.ptp(got[:, 0]) > 0.05
+
+
+@pytest.mark.parametrize("w,h", [(64, 64), (160, 120), (97, 61), (33, 31)])
+def test_socket_display_stream(oracle, ref, w, h):
+    """SURVEY 8f rank 4, second half: what the reference's socket display driver (display/sockdrv.c) puts on the wire for a frame --
+    captured from sock_dd_open/write/close talking to a listener in this process -- against the restatement, byte for byte: header,
+    one message per 1024 pixels in bucket order, the finish command, and the remainder below 1024 pixels that is never sent."""
+    from lucille_b200 import accel
+    rgb = np.random.default_rng(w * h).uniform(-1, 5, (h, w, 3)).astype(np.float32)
+    fr = accel.make_frame(np.eye(4).reshape(16), 1.0, False, w, h, 1, 1)
+    pix = accel.frame_pixels(fr)                                     # visiting order (x | y << 16), y counted from the bucket origin
+    disp = (pix & 0xFFFF) | ((np.uint32(h - 1) - (pix >> 16)) << 16)  # bucket_write: row H-1-y
+    try:
+        want = ref.sockdrv_stream(rgb, disp)
+    except RuntimeError as e:                                         # the driver's fixed port 12346 is taken on this machine
+        pytest.skip(str(e))
+    got = oracle.sockdrv_encode(rgb)
+    assert len(want) == 16 + (w * h // 1024) * (8 + 24 * 1024) + 4
+    assert got == want
