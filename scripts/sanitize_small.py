@@ -33,6 +33,21 @@ print("hdr", len(accel.hdr_encode(rgb)))
 pts = np.concatenate([np.random.default_rng(1).uniform(0, 1, (200, 3)), np.tile([0.0, 0.0, 1.0], (200, 1))], axis=1)
 for kind in (accel.GATHER_OCCLUSION, accel.GATHER_IBL, accel.GATHER_DOME):
     out, n = a.gather_points(kind, 27, pts, env); print("gather", kind, float(out.mean()), n)
+for kind in (accel.GATHER_IBL, accel.GATHER_DOME):
+    out, n = a.gather_points(kind, 13, pts, env, qmc=True, qmc_instance=np.arange(200, dtype=np.int32), qmc_dim=2); print("gather qmc", kind, float(out.mean()), n)
+# the wavefront forms (the scenes above are small enough for the one-lane-per-ray kernels): forced through the test hook
+os.environ["B200_FUSED_AO_TEST"] = "0"
+import ctypes
+gs = np.load(os.path.join("tests", "golden", "sunsky.npz")); blk = ol.sunsky_block(gs["frame_block"], gs)
+sky = accel.Sunsky(); ctypes.memmove(ctypes.byref(sky), ctypes.byref(blk), ctypes.sizeof(blk))
+for prec in (accel.PREC_F64, accel.PREC_F32):
+    f2 = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 40, 30, 2, 2, gather_nsamples=16, precision=prec)
+    print("wavefront sunsky", prec, float(c1.render_sunsky(f2, sky)[0].mean()), "dirtmap", float(c1.render_dirtmap(f2)[0].mean()))
+print("wavefront whitted", float(c1.render_whitted(fr, env)[0].mean()), "sample", float(c1.render_sample(fr)[0].mean()))
+for kind in (accel.GATHER_OCCLUSION, accel.GATHER_IBL, accel.GATHER_DOME):
+    out, n = a.gather_points(kind, 27, pts, env); print("wavefront gather", kind, float(out.mean()), n)
+os.environ.pop("B200_FUSED_AO_TEST", None)
+print("sockdrv", len(accel.sockdrv_encode(rgb, accel.make_frame(np.eye(4).reshape(16), 1.0, False, 40, 30, 1, 1))))
 ptr, _ = accel.peer_alloc(40 * 30 * 12, 0)
 import copy, threading
 for r in (0, 1):
