@@ -470,6 +470,10 @@ void lref_point_gather_ex(void *h, int kind, int nsamples, const double *points,
             power[0] = power[1] = power[2] = (double)occlusion(&status, P, N, (float)nsamples);
         } else if (kind == 1) {
             ri_ibl_sample_cosweight(power, N, nsamples, &inray, P, eye, s->scene->envmap_light);
+        } else if (kind == 3) {                 /* ri_ibl_sample_bruteforce (ibl.c:395-518): needs a square angular map */
+            for (k = 0; k < 4; k++) hemi.basis[2][k] = N[k];
+            s->scene->envmap_light->type = LIGHTTYPE_IBL;
+            ri_ibl_sample_bruteforce(power, &hemi, nsamples, P, eye, s->scene->envmap_light);
         } else {
             for (k = 0; k < 4; k++) hemi.basis[2][k] = N[k];
             ri_domelight_sample(power, &hemi, nsamples, &inray, P, eye, dome);

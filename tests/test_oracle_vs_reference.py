@@ -242,3 +242,16 @@ def test_socket_display_stream(oracle, ref, w, h):
     got = oracle.sockdrv_encode(rgb)
     assert len(want) == 16 + (w * h // 1024) * (8 + 24 * 1024) + 4
     assert got == want
+
+
+def test_ibl_bruteforce_returns_zero_power(oracle, ref):
+    """Why ri_ibl_sample_bruteforce (ibl.c:395-518) has no device form: after the first ray that escapes, the function overwrites the
+    ray ORIGIN with the direction and measures the distance between the two (ibl.c:497-505) -- zero -- so every term of its sum is
+    multiplied by invdist = 0.  The compiled reference agrees: exactly zero power at every shading point, bright environment or not."""
+    tris = scenes.triangle_soup(2000, 9)
+    rs, ot = ref.build(tris), oracle.build(tris)
+    rs.set_envmap(ol.test_texture(16, 16, 5) + 3.0)
+    pts = _shading_points(ot, 24)[:40]
+    assert len(pts) >= 20
+    out = rs.point_gather(3, 1, pts)
+    assert not out.any()
