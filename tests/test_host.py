@@ -205,3 +205,47 @@ def test_ao_ray_generator_is_cosine_hemisphere():
     assert np.all(d[:, 2] >= 0.0) and np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-6)
     assert abs(d[:, 2].mean() - 2.0 / 3.0) < 0.02                                # E[cos] under a cosine-weighted pdf
     assert np.allclose(rays[:, 2], 0.5 + 1e-6, atol=1e-7)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes / numpy mirrors in lucille_b200/accel.py against the C header: a probe compiled from include/lucille_b200.h prints
+    sizeof (and the offset of the last member) of every struct that crosses the boundary."""
+    import ctypes
+    import subprocess
+    from lucille_b200 import accel
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = tmp_path / "probe.c"
+    probe.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "lucille_b200.h"
+#define S(t, last) printf(#t " %zu %zu\\n", sizeof(t), offsetof(t, last))
+int main(void) {
+    S(ri_b200_hit_f32, prim); S(ri_b200_hit_f64, hit); S(ri_b200_state_f64, binormal); S(ri_b200_state_ext_f64, hit);
+    S(ri_b200_info_t, build_seconds); S(ri_b200_counters_t, nhit_tris); S(ri_b200_frame_t, precision);
+    S(ri_b200_frame_stats_t, ms_resolve); S(ri_b200_gather_t, qmc_instance); S(ri_b200_sunsky_t, nsun); S(ri_b200_path_frame_t, bucket_size);
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(probe), "-o", str(exe)])
+    got = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        name, size, off = line.split()
+        got[name] = (int(size), int(off))
+
+    def ct(cls, last):
+        return ctypes.sizeof(cls), getattr(cls, last).offset
+
+    def nd(dt, last):
+        return dt.itemsize, dt.fields[last][1]
+
+    want = {
+        "ri_b200_hit_f32": nd(accel.HIT32_DTYPE, "prim"), "ri_b200_hit_f64": nd(accel.HIT64_DTYPE, "hit"),
+        "ri_b200_state_f64": nd(accel.STATE_DTYPE, "binormal"), "ri_b200_state_ext_f64": nd(accel.STATE_EXT_DTYPE, "hit"),
+        "ri_b200_info_t": ct(accel.Info, "build_seconds"), "ri_b200_counters_t": ct(accel.Counters, "nhit_tris"),
+        "ri_b200_frame_t": ct(accel.Frame, "precision"), "ri_b200_frame_stats_t": ct(accel.FrameStats, "ms_resolve"),
+        "ri_b200_gather_t": ct(accel.Gather, "qmc_instance"), "ri_b200_sunsky_t": ct(accel.Sunsky, "nsun"),
+        "ri_b200_path_frame_t": ct(accel.PathFrame, "bucket_size"),
+    }
+    assert got == want
