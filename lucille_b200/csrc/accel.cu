@@ -232,6 +232,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         static const bool use_pool_closest64 = !(getenv("B200_POOL_CLOSEST64") && atoi(getenv("B200_POOL_CLOSEST64")) == 0);
         const bool pooled_closest = !ANYHIT && use_pool_closest && (sizeof(Real) == 4 || use_pool_closest64) && d_hits != nullptr;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
+        static const uint32_t leaf_at = getenv("B200_LEAF_AT") ? (uint32_t)atoi(getenv("B200_LEAF_AT")) : 32u;  // items waiting before a leaf round runs
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const size_t pool_smem = pool_smem_bytes<Real>(cap) + (use_top ? kTopNodes * sizeof(Node32) + 16 : 0);
         if (pool_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem));
@@ -258,7 +259,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             else if (pooled)
                 pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                       d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,
-                                                      rays_per_count, ctr, refill_at, (uint32_t)stack_capacity(a), d_ready, d_fault);
+                                                      rays_per_count, ctr, refill_at | (leaf_at << 8), (uint32_t)stack_capacity(a), d_ready, d_fault);
             else
                 pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,

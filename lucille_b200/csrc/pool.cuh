@@ -250,9 +250,9 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             const unsigned owners = __ballot_sync(FULL, in_leaf);
             const unsigned n_node = __popc(__ballot_sync(FULL, cur < kIdle));     // inner-node indices are < kIdle, leaf words above
             if (n_node == 0u && total == 0u) break;
-            if (!exhausted && 32u - n_node - (uint32_t)__popc(owners) >= refill_at) break;
+            if (!exhausted && 32u - n_node - (uint32_t)__popc(owners) >= (refill_at & 255u)) break;
 
-            if (total >= 32u || total > n_node) {
+            if (total >= (refill_at >> 8) || total > n_node) {           // leaf-round threshold rides in the upper bits (B200_LEAF_AT, default 32)
                 // ---- leaf round: items 0..31 of the pool, one per lane.
                 // exclusive prefix sum of cnt (<= 16) from bit-sliced ballots: no dependent shuffle chain
                 uint32_t excl = 0;
