@@ -152,12 +152,17 @@ def run_reference(args, rank, world):
     total = sum(secs)
     value = len(rays6) * args.steps / total / 1e6
     sample = f"{len(rays6)} of the {NRAYS} rays per step (first {sample_pts} points), closest-hit ri_bvh_intersect incl. state build"
+    single = None
+    if kind == "reference":                       # the one-thread figure beside the all-threads one (best of 3, bounded sample)
+        one = rays6[: max(50_000, len(rays6) // (4 * cores))]
+        sec1 = min(scene.intersect(one, nthreads=1, want_hits=False)[1] for _ in range(3))
+        single = {"value": len(one) / sec1 / 1e6, "unit": "Mrays/s", "cores": 1, "sample": f"first {len(one)} rays of the same sample, best of 3"}
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sampled": True},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample, "single_thread": single},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
