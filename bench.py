@@ -167,7 +167,25 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
-def cpu_baseline(tris, rays8_sample):
+def parity_sample(tris, rays8, gpu_occ, ref_scene=None):
+    """Part of the cpu_baseline leg (rank 0, N=1, outside every timed region): the occlusion bytes the GPU produced for the first rays
+    of the batch against the oracle's fp32 instantiation (the bit-exact contract of the fp32 records) and against the compiled
+    reference's double closest-hit flags (the fraction of rays where fp32 records and the double reference disagree)."""
+    try:
+        import oracle_lib as ol
+        n = min(len(rays8), 200_000)
+        want = ol.Oracle().build(tris).occluded_f32(rays8[:n])
+        got = np.asarray(gpu_occ[:n])
+        res = {"rays": int(n), "mismatches_vs_oracle_f32": int(np.count_nonzero((got != 0) != (want != 0)))}
+        if ref_scene is not None:
+            hits, _ = ref_scene.intersect(scenes.rays_f32_to_f64(rays8[:n]), nthreads=os.cpu_count() or 1, want_hits=True)
+            res["disagree_with_reference_f64"] = float(np.mean((got != 0) != (hits["hit"] == 1)))
+        return res
+    except Exception as e:      # pragma: no cover -- the bench line must survive a broken checker
+        return {"error": repr(e)}
+
+
+def cpu_baseline(tris, rays8_sample, gpu_occ=None):
     """Reported baseline (rank 0, N=1): the compiled reference on the box's host cores, bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     try:
@@ -182,13 +200,18 @@ def cpu_baseline(tris, rays8_sample):
         scene.intersect(rays6[:20000], nthreads=cores, want_hits=False)
         sec = min(scene.intersect(rays6, nthreads=cores, want_hits=False)[1] for _ in range(2))
         kind, threads = "reference", cores
+        ref_scene = scene
     else:
+        ref_scene = None
         t = ol.Oracle().build(tris)
         t0 = time.perf_counter()
         t.occluded_f64(rays6[:200000])
         sec, kind, threads = (time.perf_counter() - t0) * len(rays6) / 200000, "port", 1
-    return {"value": len(rays6) / sec / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind,
-            "sample": f"first {len(rays6)} rays of the batch, closest-hit ri_bvh_intersect incl. state build, {threads} threads"}
+    out = {"value": len(rays6) / sec / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind,
+           "sample": f"first {len(rays6)} rays of the batch, closest-hit ri_bvh_intersect incl. state build, {threads} threads"}
+    if gpu_occ is not None:
+        out["parity"] = parity_sample(tris, rays8_sample, gpu_occ, ref_scene)
+    return out
 
 
 def main():
@@ -346,7 +369,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             n_sample = min(nrays, 150_000 * (os.cpu_count() or 1))
-            out["cpu_baseline"] = cpu_baseline(tris, rays_np[:n_sample])
+            out["cpu_baseline"] = cpu_baseline(tris, rays_np[:n_sample], occ_host[:n_sample])
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), flush=True)
