@@ -54,6 +54,34 @@ def triangle_soup(ntris: int, seed: int, chunk: int = 1 << 20) -> np.ndarray:
     return out.astype(np.float32).astype(np.float64)
 
 
+def box_city(nx: int, nz: int, seed: int) -> np.ndarray:
+    """An architectural test scene in the unit cube, [ntris, 3, 3] float64 (fp32-representable): an nx x nz grid of axis-aligned boxes
+    on a ground of axis-aligned quads, coordinates snapped to a 1/64 lattice.  Unlike the soup it is full of what real meshes have:
+    shared vertices, coplanar faces, triangles whose boxes have zero extent on one axis, many triangles with EQUAL box bounds
+    (so the builder's bins, SAH costs and partition predicate see exact ties everywhere) and rays that graze edges."""
+    u = uniform01(seed, 0, 4 * nx * nz).reshape(nx * nz, 4)
+    tris = []
+
+    def quad(a, b, c, d):
+        tris.append((a, b, c))
+        tris.append((a, c, d))
+
+    for i in range(nx):
+        for k in range(nz):
+            x0, x1, z0, z1 = i / nx, (i + 1) / nx, k / nz, (k + 1) / nz
+            quad((x0, 0, z0), (x1, 0, z0), (x1, 0, z1), (x0, 0, z1))                       # ground tile
+            r = u[i * nz + k]
+            w = np.floor(r[0] * 24 + 8) / 64.0 / max(nx, nz) * 2.0                         # footprint, lattice-snapped
+            h = np.floor(r[1] * 40 + 4) / 64.0                                              # height
+            cx = np.floor((x0 + (x1 - x0) * (0.25 + 0.5 * r[2])) * 64) / 64.0
+            cz = np.floor((z0 + (z1 - z0) * (0.25 + 0.5 * r[3])) * 64) / 64.0
+            a, b, c, d = (cx, 0, cz), (cx + w, 0, cz), (cx + w, 0, cz + w), (cx, 0, cz + w)
+            e, f, g, hh = (cx, h, cz), (cx + w, h, cz), (cx + w, h, cz + w), (cx, h, cz + w)
+            quad(e, f, g, hh)                                                              # roof
+            quad(a, b, f, e); quad(b, c, g, f); quad(c, d, hh, g); quad(d, a, e, hh)       # walls
+    return np.asarray(tris, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
 def pinhole_rays(width: int, height: int, eye=(0.5, 0.5, -2.0), fov_deg: float = 40.0) -> np.ndarray:
     """Row-major pixel-centre rays looking down +z, shape [h*w, 8] float32: ox,oy,oz,tmin,dx,dy,dz,tmax.
 

@@ -141,6 +141,27 @@ def sunsky_block(params45: np.ndarray, tables) -> SunskyBlock:
     return b
 
 
+REFERENCE_MESH_DIR = "/root/reference/src/testbed"           # read where it lies; never copied (absent on the GPU box -> tests skip)
+
+
+def load_obj_triangles(path: str) -> np.ndarray:
+    """Triangles [n,3,3] (float64) of a Wavefront OBJ: `v x y z` and `f a b c ...` with a/b/c, a//c or a forms, polygons fanned
+    from their first corner.  For the real-mesh parity tests (the reference's testbed meshes: shared vertices, axis-aligned walls,
+    degenerate faces)."""
+    verts, faces = [], []
+    with open(path, "r", errors="replace") as f:
+        for line in f:
+            if line.startswith("v "):
+                verts.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith("f "):
+                idx = [int(tok.split("/")[0]) for tok in line.split()[1:]]
+                idx = [i - 1 if i > 0 else len(verts) + i for i in idx]
+                for k in range(1, len(idx) - 1):
+                    faces.append((idx[0], idx[k], idx[k + 1]))
+    v = np.asarray(verts, dtype=np.float64)
+    return v[np.asarray(faces, dtype=np.int64)]
+
+
 def oracle_available() -> bool:
     return os.path.exists(ORACLE_SO)
 

@@ -104,6 +104,7 @@ def test_hit_state_and_single_ray(soup20k):
     lambda: scenes.triangle_soup(17, 7),
     lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0),            # exact ties: later triangle in a leaf wins
     lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0]) + np.array([0, 0, 0.5]),   # coplanar, zero-extent boxes
+    lambda: scenes.box_city(40, 40, 3),                                     # axis-aligned architecture: exact ties, grazing rays
 ])
 def test_edge_case_scenes(maker):
     _need_gpu()
@@ -401,7 +402,8 @@ def test_sunsky_frame(oracle, golden_dir, prec):
     lambda: scenes.triangle_soup(1, 7),
     lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0),                # identical boxes -> object-median fallback
     lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0]),         # zero-extent axis
-], ids=["soup100k", "soup5k", "soup33", "soup17", "soup16", "soup1", "dup300", "flat500"])
+    lambda: scenes.box_city(150, 120, 5),                                      # 216 K axis-aligned triangles: equal bounds and costs everywhere
+], ids=["soup100k", "soup5k", "soup33", "soup17", "soup16", "soup1", "dup300", "flat500", "city216k"])
 def test_device_builder_builds_the_same_tree(maker):
     """the level-by-level device builder (csrc/bvh_build_gpu.cuh) against the host builder, which the CPU suite
     pins to the reference's tree: identical nodes, boxes, split axes, leaf contents and triangle order."""

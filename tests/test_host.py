@@ -40,6 +40,8 @@ def test_bind_rejects_other_methods():
     lambda: scenes.triangle_soup(1, 7),
     lambda: np.repeat(scenes.triangle_soup(3, 9), 100, axis=0),
     lambda: scenes.triangle_soup(500, 11) * np.array([1.0, 1.0, 0.0]),
+    lambda: scenes.box_city(40, 40, 3),                 # axis-aligned architecture: shared vertices, coplanar faces, exact ties everywhere
+    lambda: scenes.box_city(150, 120, 5),               # 216 K triangles of the same, above the parallel threshold
 ])
 def test_host_builder_matches_oracle_tree(oracle, maker):
     tris = maker()

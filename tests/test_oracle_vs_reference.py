@@ -1,5 +1,7 @@
 """CPU, build container only: the oracle restatement against the compiled, unmodified reference (oracle/_ref).
 Skipped where oracle/_ref has not been built (it needs /root/reference); the golden-vector tests cover that case."""
+import os
+
 import numpy as np
 import pytest
 
@@ -255,3 +257,72 @@ def test_ibl_bruteforce_returns_zero_power(oracle, ref):
     assert len(pts) >= 20
     out = rs.point_gather(3, 1, pts)
     assert not out.any()
+
+
+@pytest.mark.parametrize("mesh", ["bunny.obj", "sponza_cooked.obj", "sphere.obj", "cornellbox.obj"])
+def test_real_meshes_against_the_reference(oracle, ref, mesh):
+    """the reference's own testbed meshes, read where they lie (skipped where /root/reference is absent): shared
+    vertices, thousands of axis-aligned walls and zero-extent boxes (sponza, cornell box), sliver triangles.  Restatement against the
+    compiled reference: same tree (every node, box and the triangle order), same closest hits bit for bit for camera rays from three
+    sides and for rays between random points inside the bounding box, same traversal counters."""
+    path = os.path.join(ol.REFERENCE_MESH_DIR, mesh)
+    if not os.path.exists(path):
+        pytest.skip("reference testbed meshes not present")
+    tris = ol.load_obj_triangles(path)
+    assert len(tris) > 10
+    rs, ot = ref.build(tris), oracle.build(tris)
+    rn, on = rs.nodes(), ot.nodes()
+    assert len(rn) == len(on)
+    for f in ol.NODE_DTYPE.names:
+        assert np.array_equal(rn[f], on[f]), f
+    assert np.array_equal(rs.triorder(), ot.triorder())
+    lo, hi = tris.reshape(-1, 3).min(axis=0), tris.reshape(-1, 3).max(axis=0)
+    c, ext = 0.5 * (lo + hi), float((hi - lo).max())
+    rng = np.random.default_rng(len(tris))
+    rays = []
+    for axis in range(3):                                            # a camera on each side, looking at the centre
+        eye = c.copy()
+        eye[axis] += 1.7 * ext
+        tgt = c + rng.uniform(-0.55, 0.55, (4000, 3)) * ext
+        rays.append(np.concatenate([np.tile(eye, (4000, 1)), tgt - eye], axis=1))
+    a, b = rng.uniform(lo, hi, (6000, 3)), rng.uniform(lo, hi, (6000, 3))
+    rays.append(np.concatenate([a, b - a], axis=1))                  # incoherent rays that start inside the scene
+    rays6 = np.concatenate(rays)
+    want, _ = rs.intersect(rays6, nthreads=1, want_hits=True)
+    got, cnt = ot.intersect_f64(rays6, counters=True)
+    m = want["hit"] == 1
+    assert np.array_equal(got["hit"] == 1, m) and m.sum() > 1000
+    for f in ("t", "u", "v"):
+        assert np.array_equal(got[f][m], want[f][m]), f
+    assert np.array_equal(ot.triorder()[got["prim"][m]], want["index"][m] // 3)        # state.index = 3 * triangle number (bvh.c:1813)
+
+
+def test_box_city_against_the_reference(oracle, ref):
+    """The procedural stand-in for the real meshes that CAN travel to the GPU box (scenes.box_city: axis-aligned boxes on a tiled
+    ground, lattice coordinates -- equal box bounds, zero-extent boxes, coplanar faces, rays grazing edges): restatement against the
+    compiled reference, tree and closest hits bit for bit."""
+    tris = scenes.box_city(40, 40, 3)
+    rs, ot = ref.build(tris), oracle.build(tris)
+    rn, on = rs.nodes(), ot.nodes()
+    assert len(rn) == len(on)
+    for f in ol.NODE_DTYPE.names:
+        assert np.array_equal(rn[f], on[f]), f
+    assert np.array_equal(rs.triorder(), ot.triorder())
+    rays6 = scenes.rays_f32_to_f64(np.concatenate([scenes.pinhole_rays(96, 96, eye=(0.5, 0.9, -1.2)), _city_rays(6000, 2)]))
+    want, _ = rs.intersect(rays6, nthreads=1, want_hits=True)
+    got = ot.intersect_f64(rays6)
+    m = want["hit"] == 1
+    assert np.array_equal(got["hit"] == 1, m) and 2000 < m.sum() < len(m)
+    for f in ("t", "u", "v"):
+        assert np.array_equal(got[f][m], want[f][m]), f
+    assert np.array_equal(ot.triorder()[got["prim"][m]], want["index"][m] // 3)
+
+
+def _city_rays(n, seed):
+    """Rays between random points above the city: many run along walls and roofs."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0, 1, (n, 3)) * np.array([1.0, 0.7, 1.0])
+    b = rng.uniform(0, 1, (n, 3)) * np.array([1.0, 0.7, 1.0])
+    r = np.zeros((n, 8), dtype=np.float32)
+    r[:, 0:3], r[:, 4:7], r[:, 7] = a, b - a, 1.0e38
+    return r
