@@ -228,6 +228,29 @@ typedef struct {
 int ri_b200_gather_points_f64(ri_b200_accel_t *accel, const ri_b200_gather_t *gather, const double *points, uint64_t n, double *out3,
                               uint64_t *nrays_out);
 
+/* ---- calculate_occlusion (transport/ambientocclusion.c:42-151) as one batched call: n shading points (P, Ns) in, the number of
+ * OCCLUDED gather rays per point out (the reference's `occlusion` counter; Lo = (N - occluded) / N, N = ntheta * nphi,
+ * ambientocclusion.c:143-147).  The N rays of a point are set up on the device exactly as the reference does -- origin P + eps * Ns
+ * (eps = 1e-6 in ri_transport_ambientocclusion), basis = ri_ortho_basis(Ns), stratified cosine-weighted directions, outer loop over
+ * phi, inner loop over theta -- in double, rounded once to fp32 ray records, and traced by the fp32 occlusion traverser; the host
+ * moves 48 bytes per point in and 4 bytes per point out.  Two stated substitutions keep a batch order-free and bit-reproducible
+ * (SURVEY 8d, C3): the uniforms are counter-based, u(point, j, i, k) = scenes.uniform01(seed)[((point * N) + j * ntheta + i) * 2 + k],
+ * not the next words of the one sequential randomMT2 stream (the frame entry points keep that stream), and sin / cos of 2 pi z are
+ * evaluated by a fixed sequence of IEEE multiplies and adds (|error| < 1e-15) instead of libm.
+ *   points         [n][6] doubles: P.xyz, Ns.xyz (host memory; the _dev form takes device memory and is asynchronous on `stream`)
+ *   occluded_out   [n] uint32
+ * ri_b200_ao_point_rays_f32 returns the generated batch itself, [n * N][8] fp32 ray records in the order they are traced. */
+typedef struct {
+    int32_t  ntheta, nphi;        /* (int)sqrt(gather_nsamples) each, ambientocclusion.c:378-387 */
+    uint64_t seed;
+    double   eps;                 /* origin offset along Ns */
+} ri_b200_ao_points_t;
+int ri_b200_occlusion_points_f32(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *points, uint64_t n,
+                                 uint32_t *occluded_out);
+int ri_b200_occlusion_points_dev_f32(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *d_points, uint64_t n,
+                                     uint32_t *d_occluded, void *stream);
+int ri_b200_ao_point_rays_f32(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *points, uint64_t n, float *rays_out);
+
 /* rng_mode 0 (the reference's single MT19937 stream, random.c:211-247) on world > 1.  The stream position of a gather ray depends
  * on how many eye samples hit something in every bucket the reference renders EARLIER (render.c:1131-1146 in spiral order), and
  * those buckets belong to other ranks: between the eye pass and the gather pass the frame call hands the host this rank's

@@ -139,6 +139,9 @@ ABI = [
     ("ri_b200_render_ao_peer_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_set_hit_exchange", _I, [_P, _P, _P]),
     ("ri_b200_gather_points_f64", _I, [_P, _P, _P, _U64, _P, _P]),
+    ("ri_b200_occlusion_points_f32", _I, [_P, _P, _P, _U64, _P]),
+    ("ri_b200_occlusion_points_dev_f32", _I, [_P, _P, _P, _U64, _P, _P]),
+    ("ri_b200_ao_point_rays_f32", _I, [_P, _P, _P, _U64, _P]),
     ("ri_b200_peer_alloc", _P, [_U64, _I, _P]),
     ("ri_b200_peer_open", _P, [_P, _I]),
     ("ri_b200_peer_close", _I, [_P, _I]),
@@ -398,6 +401,28 @@ class Accel:
         fn = self.lib.ri_b200_occluded_dev_f64 if f64 else self.lib.ri_b200_occluded_dev_f32
         _check(fn(self._h(), _ptr(d_rays), n, _ptr(d_out), C.c_void_p(stream) if stream else None))
 
+    # -- calculate_occlusion as a batch: shading points in, occluded-ray counts out (rays generated on the device) ------
+    def occlusion_points(self, points6: np.ndarray, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6) -> np.ndarray:
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(len(pts), dtype=np.uint32)
+        par = AoPoints(ntheta, nphi, seed, eps)
+        _check(self.lib.ri_b200_occlusion_points_f32(self._h(), C.byref(par), _ptr(pts), len(pts), _ptr(out)))
+        return out
+
+    def occlusion_points_dev(self, d_points, n: int, d_out, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6,
+                             stream: Optional[int] = None):
+        par = AoPoints(ntheta, nphi, seed, eps)
+        _check(self.lib.ri_b200_occlusion_points_dev_f32(self._h(), C.byref(par), _ptr(d_points), n, _ptr(d_out),
+                                                          C.c_void_p(stream) if stream else None))
+
+    def ao_point_rays(self, points6: np.ndarray, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6) -> np.ndarray:
+        """The ray batch ri_b200_occlusion_points_f32 traces, [n*ntheta*nphi, 8] float32."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros((len(pts) * ntheta * nphi, 8), dtype=np.float32)
+        par = AoPoints(ntheta, nphi, seed, eps)
+        _check(self.lib.ri_b200_ao_point_rays_f32(self._h(), C.byref(par), _ptr(pts), len(pts), _ptr(out)))
+        return out
+
     # -- the frame-level transport ------------------------------------------------------------------
     def render_ao(self, frame: Frame):
         """One ambient-occlusion frame -> (rgb [h,w,3] float32 on the host, FrameStats)."""
@@ -557,6 +582,11 @@ class Gather(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nsamples", C.c_int32), ("seed", C.c_uint32), ("pad_", C.c_uint32), ("stream_offset", C.c_uint64),
                 ("env_rgba", C.c_void_p), ("env_width", C.c_int32), ("env_height", C.c_int32), ("col", C.c_double * 3),
                 ("intensity", C.c_double), ("use_qmc", C.c_int32), ("qmc_dim", C.c_int32), ("qmc_instance", C.c_void_p)]
+
+
+class AoPoints(C.Structure):
+    """ri_b200_ao_points_t"""
+    _fields_ = [("ntheta", C.c_int32), ("nphi", C.c_int32), ("seed", C.c_uint64), ("eps", C.c_double)]
 
 
 HIT_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))

@@ -179,6 +179,7 @@ trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const
 }
 
 #include "persistent.cuh"
+#include "packed.cuh"
 #include "pool.cuh"
 #include "pool_closest.cuh"
 
@@ -207,7 +208,7 @@ static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m
     uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
     want = (want + (kBlock / 32) - 1) / (kBlock / 32);
     const unsigned blocks = (unsigned)(want < capb ? want : capb);
-    kern<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays, m, chunk, d_hits, ctr, refill_at, (uint32_t)cap);
+    kern<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays, m, chunk, d_hits, ctr, refill_at, (uint32_t)cap, make_pack_k());
 }
 
 template <typename Real, bool ANYHIT, bool COUNT>
@@ -233,6 +234,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
         const bool pooled_closest = !ANYHIT && use_pool_closest && (sizeof(Real) == 4 || use_pool_closest64) && d_hits != nullptr;
         static const uint32_t refill_at = getenv("B200_REFILL") ? (uint32_t)atoi(getenv("B200_REFILL")) : 4u;   // measured best of 1,4,8,16,24 on C3
         static const uint32_t leaf_at = getenv("B200_LEAF_AT") ? (uint32_t)atoi(getenv("B200_LEAF_AT")) : 32u;  // items waiting before a leaf round runs
+        static const uint32_t quad_fetch = (getenv("B200_QUADFETCH") && atoi(getenv("B200_QUADFETCH")) != 0) ? 1u : 0u;   // pool.cuh: refill whole lane quads
         if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const size_t pool_smem = pool_smem_bytes<Real>(cap) + (use_top ? kTopNodes * sizeof(Node32) + 16 : 0);
         if (pool_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem));
@@ -259,7 +261,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             else if (pooled)
                 pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                       d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,
-                                                      rays_per_count, ctr, refill_at | (leaf_at << 8), (uint32_t)stack_capacity(a), d_ready, d_fault);
+                                                      rays_per_count, ctr, refill_at | (leaf_at << 8) | (quad_fetch << 16), (uint32_t)stack_capacity(a), d_ready, d_fault, make_pack_k());
             else
                 pk<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                d_hits ? d_hits + done : nullptr, d_occ ? d_occ + done : nullptr,
@@ -984,6 +986,7 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
 
 #include "frame.cuh"
 #include "pathtrace.cuh"
+#include "points.cuh"
 #include "beam.cuh"
 #include "whitted.cuh"
 #include "gather.cuh"

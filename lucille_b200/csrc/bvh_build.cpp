@@ -517,16 +517,33 @@ void flatten_tree(const HostTree &t, uint32_t top_nodes, bool want32, bool want6
         if (!n.is_leaf) continue;
         const uint64_t slot0 = slot_of[c], ns = (uint64_t)((n.ntris + 3) & ~3ll);
         if (want32) {                                        // item = pair of slots = 3 chunks of 32 B; row = ns/2 chunks
+            // Inside an item the two triangles A (even slot) and B (odd slot) are INTERLEAVED word by word so that every field
+            // arrives as an aligned (A, B) register pair for the packed fp32 arithmetic of the pooled kernels (FFMA2, packed.cuh):
+            // words (2f, 2f+1) = field f of (A, B), f = v0.xyz e1.xyz e2.xyz; words 18, 19 = prim of (A, B).  Rows 0 and 1 hold words
+            // 0..7 / 8..15 of every item (32 B per item), row 2 holds words 16..19 (16 B per item, at byte 64 m of the leaf's block):
+            // a leaf's third row fits one 128-byte line and is read with LDG.128 (8 lanes per L1 pass instead of 4).
             const uint64_t m = ns / 2, used = (uint64_t)((n.ntris + 1) / 2);
-            const char *src = reinterpret_cast<const char *>(out.tris32.data() + slot0);
+            const Tri32 *src = out.tris32.data() + slot0;
             char *dst = reinterpret_cast<char *>(out.tris32t.data() + slot0);
-            for (uint64_t j = 0; j < m; ++j)
-                for (uint64_t k = 0; k < 3; ++k) std::memcpy(dst + (k * m + j) * 32, src + j * 96 + k * 32, 32);
-            if (n.ntris & 1) {
-                // the filler slot of the last pair is masked by its validity bit, never by its determinant: give it unit edges
-                // so that 1/det stays on the fast path of the reciprocal (a zero determinant takes the slow one)
-                float *e = reinterpret_cast<float *>(dst + (2 * m + (used - 1)) * 32);
-                e[0] = 1.0f; e[5] = 1.0f;                    // b.e1 = (1,0,0), b.e2 = (0,1,0)
+            for (uint64_t j = 0; j < m; ++j) {
+                uint32_t w[24];
+                std::memset(w, 0, sizeof(w));
+                for (int h = 0; h < 2; ++h) {
+                    const Tri32 &s = src[2 * j + (uint64_t)h];
+                    const float f[9] = {s.v0[0], s.v0[1], s.v0[2], s.e1[0], s.e1[1], s.e1[2], s.e2[0], s.e2[1], s.e2[2]};
+                    for (int q = 0; q < 9; ++q) std::memcpy(&w[2 * q + h], &f[q], 4);
+                    w[18 + h] = s.prim;
+                }
+                if ((n.ntris & 1) && j == used - 1) {
+                    // the filler half of the last pair is masked by its validity bit, never by its determinant: give it unit edges
+                    // so that 1/det stays on the fast path of the reciprocal (a zero determinant takes the slow one)
+                    const float one = 1.0f;
+                    std::memcpy(&w[2 * 3 + 1], &one, 4);     // B.e1 = (1,0,0)
+                    std::memcpy(&w[2 * 7 + 1], &one, 4);     // B.e2 = (0,1,0)
+                }
+                std::memcpy(dst + j * 32, w, 32);
+                std::memcpy(dst + (m + j) * 32, w + 8, 32);
+                std::memcpy(dst + 2 * m * 32 + j * 16, w + 16, 16);
             }
         }
         if (want64) {                                        // item = one slot = 3 chunks of 32 B

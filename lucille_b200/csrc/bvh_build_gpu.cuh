@@ -372,12 +372,17 @@ __global__ void gb_fill_slots(const double *__restrict__ tri, const GBox *__rest
         }
         d.prim = p; d.pad1 = 0; d.pad2 = 0;
         t32[slot] = d;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(&d);
+        // leaf-transposed copy: the pair's two triangles interleaved word by word (bvh_build.cpp): word 2f+h = field f of half h
         const uint32_t j = i >> 1, h = i & 1u;
-        for (uint32_t q = 0; q < 12; ++q) {
-            const uint32_t off = h * 48u + q * 4u;
-            *reinterpret_cast<uint32_t *>(t32t + (size_t)slot0 * sizeof(Tri32) + ((size_t)(off >> 5) * m + j) * 32u + (off & 31u)) = w[q];
+        const float f[9] = {d.v0[0], d.v0[1], d.v0[2], d.e1[0], d.e1[1], d.e1[2], d.e2[0], d.e2[1], d.e2[2]};
+        // rows 0 / 1: words 0..7 / 8..15 of the item (32 B per item); row 2: words 16..19 (16 B per item) at byte 64 m of the block
+        char *blk = t32t + (size_t)slot0 * sizeof(Tri32);
+        for (uint32_t q = 0; q < 8; ++q) {
+            const uint32_t wi = 2u * q + h;
+            *reinterpret_cast<float *>(blk + ((size_t)(wi >> 3) * m + j) * 32u + (wi & 7u) * 4u) = f[q];
         }
+        *reinterpret_cast<float *>(blk + (size_t)m * 64u + (size_t)j * 16u + h * 4u) = f[8];       // word 16 + h
+        *reinterpret_cast<uint32_t *>(blk + (size_t)m * 64u + (size_t)j * 16u + (2u + h) * 4u) = p;   // word 18 + h
     }
     if (i == ntris - 1u) {                                               // filler slots: zero-area triangles, prim = MISS
         for (uint32_t f = ntris; f < ns; ++f) {
@@ -387,13 +392,13 @@ __global__ void gb_fill_slots(const double *__restrict__ tri, const GBox *__rest
             }
             if (t32) {
                 t32[slot0 + f].prim = 0xffffffffu;
-                const uint32_t off = (f & 1u) * 48u + 12u;
-                *reinterpret_cast<uint32_t *>(t32t + (size_t)slot0 * sizeof(Tri32) + ((size_t)(off >> 5) * m + (f >> 1)) * 32u + (off & 31u)) = 0xffffffffu;
+                *reinterpret_cast<uint32_t *>(t32t + (size_t)slot0 * sizeof(Tri32) + (size_t)m * 64u + (size_t)(f >> 1) * 16u + (2u + (f & 1u)) * 4u) = 0xffffffffu;
             }
         }
         if (t32 && (ntris & 1u)) {                                       // unit edges for the masked half of the last pair (bvh_build.cpp)
-            float *e = reinterpret_cast<float *>(t32t + (size_t)slot0 * sizeof(Tri32) + ((size_t)2 * m + ((ntris + 1u) / 2u - 1u)) * 32u);
-            e[0] = 1.0f; e[5] = 1.0f;
+            char *item = t32t + (size_t)slot0 * sizeof(Tri32) + (size_t)((ntris + 1u) / 2u - 1u) * 32u;
+            *reinterpret_cast<float *>(item + 7u * 4u) = 1.0f;                                   // word 7  = B.e1.x (chunk 0)
+            *reinterpret_cast<float *>(item + (size_t)m * 32u + 7u * 4u) = 1.0f;                 // word 15 = B.e2.y (chunk 1)
         }
     }
 }

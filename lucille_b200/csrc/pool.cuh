@@ -35,31 +35,19 @@ template <typename Real> struct PoolLeaf;
 template <> struct PoolLeaf<float> {                 // item = two triangle slots (96 B = 3 chunks)
     static constexpr int kCntBits = 4;               // items per leaf <= 8
     static __device__ __forceinline__ uint32_t items(uint32_t ntris) { return (ntris + 1u) >> 1; }
-    static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
+    static __device__ __forceinline__ bool test(const PackK &K, const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
                                                 const float org[3], const float dir[3])
     {
         const uint32_t m = ((ntris + 3u) >> 2) << 1;                                      // row length in pairs: the leaf owns round_up(ntris, 4) slots
-        const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = o1 + 2u * m;      // 16-byte units: < 2^29
-        const F8 q0 = ldg256(trisT + (size_t)o0 * 16u), q1 = ldg256(trisT + (size_t)o1 * 16u), q2 = ldg256(trisT + (size_t)o2 * 16u);
-        TriRegs<float> a, b;
-        a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = 0;
-        a.e1[0] = q0.v[4]; a.e1[1] = q0.v[5]; a.e1[2] = q0.v[6];
-        a.e2[0] = q1.v[0]; a.e2[1] = q1.v[1]; a.e2[2] = q1.v[2];
-        b.v0[0] = q1.v[4]; b.v0[1] = q1.v[5]; b.v0[2] = q1.v[6]; b.prim = 0;
-        b.e1[0] = q2.v[0]; b.e1[1] = q2.v[1]; b.e1[2] = q2.v[2];
-        b.e2[0] = q2.v[4]; b.e2[1] = q2.v[5]; b.e2[2] = q2.v[6];
-        float tl = Prec<float>::inf(), ul = 0.0f, vl = 0.0f;
-        uint32_t tprim = 0xffffffffu;
-        tri_test_bf<float>(a, org, dir, true, tl, ul, vl, tprim);
-        tri_test_bf<float>(b, org, dir, 2u * j + 1u < ntris, tl, ul, vl, tprim);
-        return tl < Prec<float>::inf();
+        const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = slot0 * 3u + 4u * m + j;     // 16-byte units: < 2^29; row 2 holds 16 B per item
+        return pair_occluded(K, trisT + (size_t)o0 * 16u, trisT + (size_t)o1 * 16u, trisT + (size_t)o2 * 16u, 2u * j + 1u < ntris, org, dir);
     }
 };
 
 template <> struct PoolLeaf<double> {                // item = one triangle slot (96 B = 3 chunks)
     static constexpr int kCntBits = 5;               // items per leaf <= 16
     static __device__ __forceinline__ uint32_t items(uint32_t ntris) { return ntris; }
-    static __device__ __forceinline__ bool test(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
+    static __device__ __forceinline__ bool test(const PackK &, const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j,
                                                 const double org[3], const double dir[3])
     {
         const uint32_t m = (ntris + 3u) & ~3u;       // slots owned by the leaf = row length
@@ -138,12 +126,26 @@ __device__ __forceinline__ void load_node_shared(const char *p, NodeRegs<float> 
 }
 __device__ __forceinline__ void load_node_shared(const char *, NodeRegs<double> &) {}
 
+// one node step on packed pairs: two LDG.256 bring (lo, hi) of both child boxes per axis as aligned register pairs
+__device__ __forceinline__ void node_step_pk(const PackK &K, const Node32 *p, const float org[3], const float inv[3], bool sx, bool sy, bool sz,
+                                             float best_t, bool &h0, bool &h1, uint32_t &c0, uint32_t &c1, uint32_t &axis)
+{
+    const P4 a = ldg256p(p), b = ldg256p(reinterpret_cast<const char *>(p) + 32);
+    const pk_t ox = pkb(org[0]), oy = pkb(org[1]), oz = pkb(org[2]);
+    const pk_t ix = pkb(inv[0]), iy = pkb(inv[1]), iz = pkb(inv[2]);
+    h0 = slab_pk(K, a.v[0], a.v[2], b.v[0], ox, oy, oz, ix, iy, iz, sx, sy, sz, best_t);
+    h1 = slab_pk(K, a.v[1], a.v[3], b.v[1], ox, oy, oz, ix, iy, iz, sx, sy, sz, best_t);
+    c0 = (uint32_t)b.v[2]; c1 = (uint32_t)(b.v[2] >> 32); axis = (uint32_t)b.v[3];
+}
+__device__ __forceinline__ void node_step_pk(const PackK &, const Node64 *, const double *, const double *, bool, bool, bool, double,
+                                             bool &, bool &, uint32_t &, uint32_t &, uint32_t &) {}
+
 template <typename Real, int kMinBlocks, bool kTopSmem = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
 occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
                      const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
                      unsigned int *__restrict__ work_counter, const uint32_t refill_at, const uint32_t stack_cap,
-                     const unsigned int *__restrict__ ready, unsigned int *__restrict__ fault)
+                     const unsigned int *__restrict__ ready, unsigned int *__restrict__ fault, const PackK K)
 {
     using P = Prec<Real>;
     constexpr unsigned FULL = 0xffffffffu;
@@ -191,7 +193,17 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
 
     for (;;) {
         // ------------------------------------------------------------------ fetch (as in persistent.cuh)
-        unsigned idle = __ballot_sync(FULL, cur == kIdle);
+        // quad mode (refill_at bit 16): new rays go only to ALIGNED LANE QUADS that are idle as a whole, four consecutive rays each.
+        // An LDG.256 is served four lanes per L1 pass, and four rays of one AO point that start at the root together walk the
+        // same nodes until their paths part -- one wavefront per node record instead of four while they do.
+        const bool quad_mode = ((refill_at >> 16) & 1u) != 0u;
+        auto fetchable = [&](unsigned m) -> unsigned {
+            if (!quad_mode) return m;
+            const unsigned q = m & (m >> 1) & (m >> 2) & (m >> 3) & 0x11111111u;
+            return q * 15u;
+        };
+        unsigned idle_all = __ballot_sync(FULL, cur == kIdle);
+        unsigned idle = fetchable(idle_all);
         while (idle && !exhausted) {
             if (chunk_next >= chunk_end) {
                 uint32_t base = 0;
@@ -220,7 +232,7 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             const unsigned n_idle = __popc(idle);
             const unsigned take = n_idle < avail ? n_idle : avail;
             const unsigned rank = __popc(idle & lt_mask);
-            if (cur == kIdle && rank < take) {
+            if (((idle >> lane) & 1u) && rank < take) {
                 idx = chunk_next + rank;
                 RayIO<Real>::load(rays, idx, org, dir);
                 RaySlot<Real>::store(s_rays, lane, org, dir);
@@ -236,9 +248,10 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                 else retire(false);              // bvh.c:446 / 522-526: miss without traversal
             }
             chunk_next += take;
-            idle = __ballot_sync(FULL, cur == kIdle);
+            idle_all = __ballot_sync(FULL, cur == kIdle);
+            idle = fetchable(idle_all);
         }
-        if (idle == FULL) break;                 // nothing in flight and nothing left to fetch
+        if (idle_all == FULL) break;             // nothing in flight and nothing left to fetch
 
         // ------------------------------------------------------------------ traverse
         for (;;) {
@@ -248,11 +261,12 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             const uint32_t cnt = in_leaf ? nitems - prog : 0u;        // >= 1 for a lane standing in a leaf
             const uint32_t total = __reduce_add_sync(FULL, cnt);
             const unsigned owners = __ballot_sync(FULL, in_leaf);
-            const unsigned n_node = __popc(__ballot_sync(FULL, cur < kIdle));     // inner-node indices are < kIdle, leaf words above
+            const unsigned in_node = __ballot_sync(FULL, cur < kIdle);            // inner-node indices are < kIdle, leaf words above
+            const unsigned n_node = __popc(in_node);
             if (n_node == 0u && total == 0u) break;
-            if (!exhausted && 32u - n_node - (uint32_t)__popc(owners) >= (refill_at & 255u)) break;
+            if (!exhausted && (uint32_t)__popc(fetchable(~(in_node | owners))) >= (refill_at & 255u)) break;
 
-            if (total >= (refill_at >> 8) || total > n_node) {           // leaf-round threshold rides in the upper bits (B200_LEAF_AT, default 32)
+            if (total >= ((refill_at >> 8) & 255u) || total > n_node) {           // leaf-round threshold rides in the upper bits (B200_LEAF_AT, default 32)
                 // ---- leaf round: items 0..31 of the pool, one per lane.
                 // exclusive prefix sum of cnt (<= 16) from bit-sliced ballots: no dependent shuffle chain
                 uint32_t excl = 0;
@@ -272,7 +286,7 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
                     const uint32_t item = lane + (d.y >> 8) - 64u;    // item number inside the owner's leaf
                     Real oorg[3], odir[3];
                     RaySlot<Real>::load(s_rays, own, oorg, odir);
-                    hit = PoolLeaf<Real>::test(trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir);
+                    hit = PoolLeaf<Real>::test(K, trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir);
                 }
                 const unsigned hits = __ballot_sync(FULL, hit);
                 if (owner) {
@@ -291,19 +305,26 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             }
             if (cur < kIdle) {
                 // ---- node step: bvh.c:1153-1179 with best_t == 1e38 (no hit yet)
-                NodeRegs<Real> nd;
-                if (kTopSmem && cur < ntop) load_node_shared(s_top + (size_t)cur * sizeof(Node32), nd);
-                else load_node_wide(S.nodes + cur, nd);
-                const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, P::inf());
-                const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, P::inf());
-                const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);     // near child = child[sign[axis0]]
+                bool h0, h1;
+                uint32_t c0, c1, axis;
+                if (sizeof(Real) == 4 && !kTopSmem) {                 // packed fp32: (lo, hi) of each child box as a register pair (packed.cuh)
+                    node_step_pk(K, S.nodes + cur, org, inv, sx, sy, sz, P::inf(), h0, h1, c0, c1, axis);
+                } else {
+                    NodeRegs<Real> nd;
+                    if (kTopSmem && cur < ntop) load_node_shared(s_top + (size_t)cur * sizeof(Node32), nd);
+                    else load_node_wide(S.nodes + cur, nd);
+                    h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, P::inf());
+                    h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, P::inf());
+                    c0 = nd.c0; c1 = nd.c1; axis = nd.axis;
+                }
+                const bool order = (axis == 0) ? sx : ((axis == 1) ? sy : sz);           // near child = child[sign[axis0]]
                 const bool both = h0 && h1, none = !h0 && !h1;
                 const bool pop = none && (sp != 0u);
-                if (both) stk[sp * kBlock] = order ? nd.c0 : nd.c1;
+                if (both) stk[sp * kBlock] = order ? c0 : c1;
                 const uint32_t popped = pop ? stk[(sp - 1u) * kBlock] : kIdle;
                 sp = sp + (both ? 1u : 0u) - (pop ? 1u : 0u);
-                const uint32_t one = h0 ? nd.c0 : nd.c1;
-                const uint32_t next = both ? (order ? nd.c1 : nd.c0) : (none ? popped : one);
+                const uint32_t one = h0 ? c0 : c1;
+                const uint32_t next = both ? (order ? c1 : c0) : (none ? popped : one);
                 if (next == kIdle) retire(false);                     // stack ran dry
                 prog = 0;
                 cur = next;

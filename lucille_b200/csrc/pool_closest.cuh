@@ -18,30 +18,20 @@
 namespace b200 {
 
 // pair-local winner of item j of a leaf, tested from t_leaf = 1e38 (bvh.c:833-848 restricted to the pair)
-__device__ __forceinline__ void pool_pair_closest(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const float org[3],
+__device__ __forceinline__ void pool_pair_closest(const PackK &K, const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const float org[3],
                                                   const float dir[3], float &tl, float &ul, float &vl, uint32_t &tprim)
 {
     const uint32_t m = ((ntris + 3u) >> 2) << 1;
-    const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = o1 + 2u * m;
-    const F8 q0 = ldg256(trisT + (size_t)o0 * 16u), q1 = ldg256(trisT + (size_t)o1 * 16u), q2 = ldg256(trisT + (size_t)o2 * 16u);
-    TriRegs<float> a, b;
-    a.v0[0] = q0.v[0]; a.v0[1] = q0.v[1]; a.v0[2] = q0.v[2]; a.prim = __float_as_uint(q0.v[3]);
-    a.e1[0] = q0.v[4]; a.e1[1] = q0.v[5]; a.e1[2] = q0.v[6];
-    a.e2[0] = q1.v[0]; a.e2[1] = q1.v[1]; a.e2[2] = q1.v[2];
-    b.v0[0] = q1.v[4]; b.v0[1] = q1.v[5]; b.v0[2] = q1.v[6]; b.prim = __float_as_uint(q1.v[7]);
-    b.e1[0] = q2.v[0]; b.e1[1] = q2.v[1]; b.e1[2] = q2.v[2];
-    b.e2[0] = q2.v[4]; b.e2[1] = q2.v[5]; b.e2[2] = q2.v[6];
-    tl = Prec<float>::inf(); ul = 0.0f; vl = 0.0f; tprim = 0xffffffffu;
-    tri_test_bf<float>(a, org, dir, true, tl, ul, vl, tprim);
-    tri_test_bf<float>(b, org, dir, 2u * j + 1u < ntris, tl, ul, vl, tprim);
+    const uint32_t o0 = slot0 * 3u + j * 2u, o1 = o0 + 2u * m, o2 = slot0 * 3u + 4u * m + j;     // row 2 holds 16 B per item
+    pair_closest(K, trisT + (size_t)o0 * 16u, trisT + (size_t)o1 * 16u, trisT + (size_t)o2 * 16u, 2u * j + 1u < ntris, org, dir, tl, ul, vl, tprim);
 }
 
-__device__ __forceinline__ void pool_item_closest(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const float org[3],
+__device__ __forceinline__ void pool_item_closest(const PackK &K, const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const float org[3],
                                                   const float dir[3], float &tl, float &ul, float &vl, uint32_t &tprim)
-{ pool_pair_closest(trisT, slot0, ntris, j, org, dir, tl, ul, vl, tprim); }
+{ pool_pair_closest(K, trisT, slot0, ntris, j, org, dir, tl, ul, vl, tprim); }
 
 // fp64: one triangle slot per item, tested from t_leaf = 1e38
-__device__ __forceinline__ void pool_item_closest(const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const double org[3],
+__device__ __forceinline__ void pool_item_closest(const PackK &, const char *trisT, uint32_t slot0, uint32_t ntris, uint32_t j, const double org[3],
                                                   const double dir[3], double &tl, double &ul, double &vl, uint32_t &tprim)
 {
     const uint32_t m = (ntris + 3u) & ~3u;
@@ -69,7 +59,7 @@ template <typename Real>
 __global__ void __launch_bounds__(kBlock, sizeof(Real) == 4 ? 3 : 2)
 closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
                     const uint32_t chunk, typename RayIO<Real>::Hit *__restrict__ hits_out, unsigned int *__restrict__ work_counter,
-                    const uint32_t refill_at, const uint32_t stack_cap)
+                    const uint32_t refill_at, const uint32_t stack_cap, const PackK K)
 {
     using P = Prec<Real>;
     using L = PoolLeaf<Real>;
@@ -171,7 +161,7 @@ closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, con
                     Real oorg[3], odir[3], t, u, v;
                     uint32_t prim;
                     RaySlot<Real>::load(s_rays, own, oorg, odir);
-                    pool_item_closest(trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir, t, u, v, prim);
+                    pool_item_closest(K, trisT, d.x & kSlotMask, ((d.x >> kLeafShift) & 15u) + 1u, item, oorg, odir, t, u, v, prim);
                     if (prim != 0xffffffffu) {   // the item accepted a triangle: offer it to the owner
                         PoolRes<Real> r;
                         r.t = t; r.u = u; r.v = v; r.prim = prim;
@@ -207,18 +197,25 @@ closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, con
             }
             if (cur < kIdle) {
                 // ---- node step: bvh.c:1153-1179
-                NodeRegs<Real> nd;
-                load_node_wide(S.nodes + cur, nd);
-                const bool h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
-                const bool h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
-                const bool order = (nd.axis == 0) ? sx : ((nd.axis == 1) ? sy : sz);
+                bool h0, h1;
+                uint32_t c0, c1, axis;
+                if (sizeof(Real) == 4) {
+                    node_step_pk(K, S.nodes + cur, org, inv, sx, sy, sz, best_t, h0, h1, c0, c1, axis);
+                } else {
+                    NodeRegs<Real> nd;
+                    load_node_wide(S.nodes + cur, nd);
+                    h0 = slab_mm<Real>(nd.x[0], nd.x[1], nd.y[0], nd.y[1], nd.z[0], nd.z[1], org, inv, sx, sy, sz, best_t);
+                    h1 = slab_mm<Real>(nd.x[2], nd.x[3], nd.y[2], nd.y[3], nd.z[2], nd.z[3], org, inv, sx, sy, sz, best_t);
+                    c0 = nd.c0; c1 = nd.c1; axis = nd.axis;
+                }
+                const bool order = (axis == 0) ? sx : ((axis == 1) ? sy : sz);
                 const bool both = h0 && h1, none = !h0 && !h1;
                 const bool pop = none && (sp != 0u);
-                if (both) stk[sp * kBlock] = order ? nd.c0 : nd.c1;
+                if (both) stk[sp * kBlock] = order ? c0 : c1;
                 const uint32_t popped = pop ? stk[(sp - 1u) * kBlock] : kIdle;
                 sp = sp + (both ? 1u : 0u) - (pop ? 1u : 0u);
-                const uint32_t one = h0 ? nd.c0 : nd.c1;
-                const uint32_t next = both ? (order ? nd.c1 : nd.c0) : (none ? popped : one);
+                const uint32_t one = h0 ? c0 : c1;
+                const uint32_t next = both ? (order ? c1 : c0) : (none ? popped : one);
                 if (next == kIdle) { retire(); cur = kIdle; }
                 else enter(next);
             }

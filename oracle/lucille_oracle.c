@@ -1899,3 +1899,42 @@ uint64_t orc_splitmix64(uint64_t x)
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
+
+/* ------------------------------------------------------------------ point-based AO batch (ri_b200_occlusion_points_f32)
+ * The ray set-up of calculate_occlusion (transport/ambientocclusion.c:56-117) for a batch of shading points (P, Ns): origin
+ * P + eps * Ns, basis = ri_ortho_basis(Ns), outer loop j over phi, inner loop i over theta, z0 = (i + u0) / ntheta,
+ * z1 = (j + u1) / nphi, cos(theta) = sqrt(z0), local = (cos(phi) cos(theta), sin(phi) cos(theta), sqrt(1 - cos^2(theta))),
+ * dir = sum local[k] * basis[k] -- in double, rounded once to the fp32 ray record [ox oy oz 0 dx dy dz 1e38].  Builder-stated
+ * substitutions, shared with the device: u0, u1 = the counter-based uniforms of scenes.uniform01 keyed by
+ * (seed, point, j, i) in place of the sequential randomMT2 stream, and sin / cos by orc_det_sincos2pi in place of libm. */
+void orc_ao_point_rays_f32(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, float *rays_out)
+{
+    const uint64_t N = (uint64_t)ntheta * (uint64_t)nphi;
+    uint64_t p;
+    for (p = 0; p < n; p++) {
+        const double *pt = points + 6 * p;
+        double basis[3][3], nrm[3];
+        uint32_t i, j; int k;
+        for (k = 0; k < 3; k++) nrm[k] = pt[3 + k];
+        ortho_basis_f64(basis, nrm);
+        for (j = 0; j < (uint32_t)nphi; j++) {
+            for (i = 0; i < (uint32_t)ntheta; i++) {
+                const uint64_t kk = (uint64_t)j * (uint64_t)ntheta + i, idx = ((first_point + p) * N + kk) * 2;      /* keyed by the point's position in the whole batch */
+                const double u0 = (double)(orc_splitmix64(seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+                const double u1 = (double)(orc_splitmix64(seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+                const double z0 = ((double)i + u0) / (double)ntheta;
+                const double z1 = ((double)j + u1) / (double)nphi;
+                const double ct = sqrt(z0);
+                double sn, cs, lx, ly, lz;
+                float *o = rays_out + 8 * (p * N + kk);
+                orc_det_sincos2pi(z1, &sn, &cs);
+                lx = cs * ct; ly = sn * ct; lz = sqrt(1.0 - ct * ct);
+                for (k = 0; k < 3; k++) {
+                    o[k] = (float)(pt[k] + nrm[k] * eps);
+                    o[4 + k] = (float)(lx * basis[0][k] + ly * basis[1][k] + lz * basis[2][k]);
+                }
+                o[3] = 0.0f; o[7] = 1.0e38f;
+            }
+        }
+    }
+}

@@ -153,6 +153,8 @@ typedef struct {
 } orc_path_frame_t;
 void orc_render_pathtrace(const orc_tree *t, const orc_path_frame_t *f, float *rgb, uint64_t *nrays_out);
 void orc_det_sincos2pi(double r, double *s, double *c);
+/* ray batch of the point-based AO call (calculate_occlusion's ray set-up, ambientocclusion.c:56-117): [n*ntheta*nphi][8] floats */
+void orc_ao_point_rays_f32(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, float *rays_out);
 
 /* ---- material texture of the AO transport (ambientocclusion.c:393-401): radiance *= ri_texture_fetch(texture, st) per channel.
  * ri_texture_fetch (render/texture.c:86-236, USE_ZORDER 0): wrap by floor, clamp, bilinear over the 2x2 texels at

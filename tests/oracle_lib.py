@@ -416,6 +416,7 @@ class Oracle:
                                          C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_point_gather_qmc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                              C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        lib.orc_ao_point_rays_f32.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_void_p]
         lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -427,6 +428,15 @@ class Oracle:
         lib.orc_sunsky_sky_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_render_sunsky.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib = lib
+
+    def ao_point_rays(self, points6: np.ndarray, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6, first_point: int = 0) -> np.ndarray:
+        """Ray batch of the point-based AO call (calculate_occlusion's ray set-up, counter RNG + deterministic sin/cos), [n*N, 8] f32.
+        ``first_point``: position of points6[0] in the whole batch (the counter RNG is keyed by it)."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros((len(pts) * ntheta * nphi, 8), dtype=np.float32)
+        self.lib.orc_ao_point_rays_f32(_ptr(pts), C.c_uint64(len(pts)), C.c_uint64(first_point), ntheta, nphi, C.c_uint64(seed),
+                                       C.c_double(eps), _ptr(out))
+        return out
 
     def sockdrv_encode(self, rgb: np.ndarray, bucket_size: int = 32) -> bytes:
         """Byte stream of the reference's socket display driver for the finished frame ``rgb`` [h,w,3] (display order)."""

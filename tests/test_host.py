@@ -131,11 +131,14 @@ def test_flat_records_decode_to_canonical_tree(n):
 def test_leaf_transposed_copies_are_a_permutation_of_the_slots():
     """The pooled kernels read the leaf-TRANSPOSED copies: chunk k (32 bytes) of item j of a leaf whose rows hold m items sits at
     slot0 * sizeof(slot) + (k * m + j) * 32 (fp32: item = pair of slots, m = slots/2; fp64: item = slot, m = slots; slots =
-    round_up(ntris, 4)).  Same bytes as the plain slots, except the unit edges given to the masked half of an odd last pair."""
+    round_up(ntris, 4)).  An fp32 item holds its two triangles (A, B) INTERLEAVED word by word -- word 2f+h = field f of half h,
+    f = v0.xyz e1.xyz e2.xyz, words 18/19 = prim of A/B -- so that every field arrives as an aligned register pair for the packed
+    FFMA2 arithmetic (csrc/packed.cuh); rows 0 and 1 hold words 0..7 / 8..15 (32 B per item), row 2 words 16..19 (16 B per item, at
+    byte 64 m of the leaf's block); the masked half of an odd last pair gets unit edges."""
     tris = scenes.triangle_soup(3000, 3)
     a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64 | accel.HOST_ONLY)
     flat = a.flat()
-    t32 = flat["tris32"].view(np.uint8).reshape(-1, 48)
+    t32 = flat["tris32"]
     t64 = flat["tris64"].view(np.uint8).reshape(-1, 96)
     t32t, t64t = flat["tris32t"], flat["tris64t"]
     leaves = [n for n in a.nodes() if n["is_leaf"]]
@@ -143,19 +146,24 @@ def test_leaf_transposed_copies_are_a_permutation_of_the_slots():
     for leaf in leaves:
         ntris = int(leaf["ntris"])
         ns = (ntris + 3) // 4 * 4
-        assert np.array_equal(flat["tris32"]["prim"][slot0:slot0 + ntris], np.arange(leaf["tri_start"], leaf["tri_start"] + ntris))
-        pairs = t32[slot0:slot0 + ns].reshape(ns // 2, 96)
+        assert np.array_equal(t32["prim"][slot0:slot0 + ntris], np.arange(leaf["tri_start"], leaf["tri_start"] + ntris))
         m = ns // 2
         for j in range(m):
-            for k in range(3):
+            want = np.zeros(24, dtype=np.uint32)
+            for h in range(2):
+                s = t32[slot0 + 2 * j + h]
+                f = np.concatenate([s["v0"], s["e1"], s["e2"]]).astype(np.float32)
+                want[h:18:2] = f.view(np.uint32)
+                want[18 + h] = s["prim"]
+            if (ntris & 1) and j == (ntris + 1) // 2 - 1:          # masked half of the last used pair: unit edges
+                one = np.float32(1.0).view(np.uint32)
+                want[2 * 3 + 1], want[2 * 7 + 1] = one, one
+                odd_leaves += 1
+            for k in range(2):                                      # rows 0 and 1: 32 bytes per item
                 got = t32t[slot0 * 48 + (k * m + j) * 32: slot0 * 48 + (k * m + j) * 32 + 32]
-                want = pairs[j, 32 * k: 32 * k + 32].copy()
-                if (ntris & 1) and j == (ntris + 1) // 2 - 1 and k == 2:          # masked half of the last used pair: unit edges
-                    w = want.view(np.float32).copy()
-                    w[0], w[5] = 1.0, 1.0
-                    want = w.view(np.uint8)
-                    odd_leaves += 1
-                assert np.array_equal(got, want)
+                assert np.array_equal(got.view(np.uint32), want[8 * k: 8 * k + 8])
+            got = t32t[slot0 * 48 + m * 64 + j * 16: slot0 * 48 + m * 64 + j * 16 + 16]      # row 2: 16 bytes per item
+            assert np.array_equal(got.view(np.uint32), want[16:20])
         for j in range(ns):
             for k in range(3):
                 got = t64t[slot0 * 96 + (k * ns + j) * 32: slot0 * 96 + (k * ns + j) * 32 + 32]

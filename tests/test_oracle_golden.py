@@ -202,3 +202,24 @@ def test_socket_display_stream_golden(oracle, golden_dir):
     for name, rgb in frames.items():
         data = oracle.sockdrv_encode(rgb)
         assert len(data) == int(g[name + "_size"]) and hashlib.sha256(data).hexdigest() == str(g[name + "_sha256"]), name
+
+
+def test_point_ao_ray_setup_matches_the_numpy_generator():
+    """orc_ao_point_rays_f32 (calculate_occlusion's ray set-up, ambientocclusion.c:56-117, with the counter RNG and the deterministic
+    sin/cos) against the independent numpy statement of the same loop (scenes.ao_rays: libm sin/cos): identical fp32 records except
+    where the last place of sin/cos moves a float rounding, never by more than one ulp; windows of a batch are position-keyed."""
+    rng = np.random.default_rng(3)
+    P = rng.random((2000, 3))
+    n = rng.normal(size=(2000, 3))
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    n[:3] = [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, -1.0]]
+    pts = np.concatenate([P, n], axis=1)
+    for ntheta, nphi in ((8, 8), (3, 5)):
+        got = ol.Oracle().ao_point_rays(pts, ntheta, nphi, scenes.SEED_C3)
+        want = scenes.ao_rays(P, n, ntheta, nphi, scenes.SEED_C3)
+        assert got.shape == want.shape
+        same = got.view(np.uint32) == want.view(np.uint32)
+        assert same.mean() > 0.9999
+        assert np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max() <= 1
+        tail = ol.Oracle().ao_point_rays(pts[1500:], ntheta, nphi, scenes.SEED_C3, first_point=1500)
+        assert np.array_equal(tail.view(np.uint32), got[1500 * ntheta * nphi:].view(np.uint32))
