@@ -33,7 +33,8 @@ BUILD_HOST = 0x400      # build it with the threaded host builder (neither flag:
 MISS_PRIM = 0xFFFFFFFF
 RI_INFINITY = 1.0e38
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200accel.so")
+# B200_LIB: an alternative build of the same library (A/B experiments: scripts/build_variants.sh); default = the in-tree product
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200accel.so")
 
 HIT32_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
 HIT64_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim", "<u4"), ("hit", "<u4")])

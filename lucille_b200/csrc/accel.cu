@@ -120,6 +120,15 @@ template <> struct RayIO<float> {
         org[0] = a.x; org[1] = a.y; org[2] = a.z;
         dir[0] = b.x; dir[1] = b.y; dir[2] = b.z;
     }
+    // a buffer the copy engine is still writing while the kernel runs (streamed host batches): ld.global.cg, never the
+    // non-coherent path -- ld.global.nc requires the data to be read-only for the kernel's lifetime
+    static __device__ __forceinline__ void load_coherent(const float *rays, uint64_t i, float org[3], float dir[3])
+    {
+        const float4 *p = reinterpret_cast<const float4 *>(rays) + 2 * i;
+        const float4 a = __ldcg(p), b = __ldcg(p + 1);
+        org[0] = a.x; org[1] = a.y; org[2] = a.z;
+        dir[0] = b.x; dir[1] = b.y; dir[2] = b.z;
+    }
     static __device__ __forceinline__ void store(Hit *out, uint64_t i, bool hit, float t, float u, float v, uint32_t prim)
     {
         float4 r;
@@ -135,6 +144,13 @@ template <> struct RayIO<double> {
     {
         const double2 *p = reinterpret_cast<const double2 *>(rays) + 3 * i;
         const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        org[0] = a.x; org[1] = a.y; org[2] = b.x;
+        dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
+    }
+    static __device__ __forceinline__ void load_coherent(const double *rays, uint64_t i, double org[3], double dir[3])
+    {
+        const double2 *p = reinterpret_cast<const double2 *>(rays) + 3 * i;
+        const double2 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
         org[0] = a.x; org[1] = a.y; org[2] = b.x;
         dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
     }
@@ -181,6 +197,7 @@ trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const
 #include "persistent.cuh"
 #include "packed.cuh"
 #include "pool.cuh"
+#include "pool32.cuh"
 #include "pool_closest.cuh"
 
 static const char *pool_tris(const ri_b200_accel *a, float)  { return reinterpret_cast<const char *>(a->d_tris32t); }
@@ -210,6 +227,34 @@ static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m
     const unsigned blocks = (unsigned)(want < capb ? want : capb);
     kern<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays, m, chunk, d_hits, ctr, refill_at, (uint32_t)cap, make_pack_k());
 }
+
+// pool32.cuh: fp32 occlusion with static shared memory.  Returns false when it does not apply (fp64 records, a tree deeper than
+// the largest instantiated stack, B200_POOL32=0 or one of pool.cuh's experiment knobs) and the generic pooled kernel should run.
+template <int kCap>
+static void launch_pool32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
+                              uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+{
+    if (d_counts)
+        occluded_pool32_kernel<kCap, true><<<blocks, kBlock, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, nullptr, d_counts,
+                                                                     rays_per_count, ctr, d_ready, d_fault, make_pack_k());
+    else
+        occluded_pool32_kernel<kCap, false><<<blocks, kBlock, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_occ, nullptr,
+                                                                      rays_per_count, ctr, d_ready, d_fault, make_pack_k());
+}
+static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
+                          uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+{
+    static const bool off = (getenv("B200_POOL32") && atoi(getenv("B200_POOL32")) == 0) || getenv("B200_POOL_TOPSMEM") || getenv("B200_REFILL") ||
+                            getenv("B200_LEAF_AT") || getenv("B200_QUADFETCH");
+    const int cap = stack_capacity(a);
+    if (off || cap > 36) return false;
+    if (cap <= 20) launch_pool32_cap<20>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st);
+    else if (cap <= 28) launch_pool32_cap<28>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st);
+    else launch_pool32_cap<36>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st);
+    return true;
+}
+static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, uint8_t *, uint32_t *, uint32_t, unsigned int *,
+                          const unsigned int *, unsigned int *, unsigned, cudaStream_t) { return false; }
 
 template <typename Real, bool ANYHIT, bool COUNT>
 static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typename RayIO<Real>::Hit *d_hits, uint8_t *d_occ,
@@ -258,6 +303,9 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             if (pooled_closest)
                 launch_closest_pool<Real>(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_hits + done, ctr, refill_at, st);
+            else if (pooled && launch_pool32(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_occ ? d_occ + done : nullptr,
+                                             d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, d_ready, d_fault, blocks, st))
+                ;                                // fp32 occlusion on a tree that fits a static stack: the specialised kernel (pool32.cuh)
             else if (pooled)
                 pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
                                                       d_occ ? d_occ + done : nullptr, d_counts ? d_counts + done / rays_per_count : nullptr,

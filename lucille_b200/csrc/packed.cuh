@@ -66,6 +66,27 @@ __device__ __forceinline__ P4 ldg256p(const void *p)          // LDG.E.256 into 
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
     return r;
 }
+// the same load with an L1 eviction hint: node records are re-used by every ray (keep), triangle chunks stream through (do not allocate)
+__device__ __forceinline__ P4 ldg256p_keep(const void *p)
+{
+#ifdef B200_L1_HINTS
+    P4 r;
+    asm volatile("ld.global.nc.L1::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
+    return r;
+#else
+    return ldg256p(p);
+#endif
+}
+__device__ __forceinline__ P4 ldg256p_stream(const void *p)
+{
+#ifdef B200_L1_HINTS
+    P4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
+    return r;
+#else
+    return ldg256p(p);
+#endif
+}
 
 struct __align__(16) P2 { pk_t v[2]; };
 __device__ __forceinline__ P2 ldg128p(const void *p)          // LDG.E.128 into two aligned register pairs
@@ -116,7 +137,7 @@ __device__ __forceinline__ bool mt_accept(float a, float u, float v, float uv, f
 __device__ __forceinline__ void pair_closest(const PackK &K, const char *p0, const char *p1, const char *p2, const bool valid_b,
                                              const float org[3], const float dir[3], float &tl, float &ul, float &vl, uint32_t &tprim)
 {
-    const P4 c0 = ldg256p(p0), c1 = ldg256p(p1);
+    const P4 c0 = ldg256p_stream(p0), c1 = ldg256p_stream(p1);
     const P2 c2 = ldg128p(p2);
     const PairMT r = pair_mt(K, c0, c1, c2, org, dir);
     float aA, aB, uA, uB, vA, vB, tA, tB, wA, wB, primA, primB;
@@ -132,7 +153,7 @@ __device__ __forceinline__ void pair_closest(const PackK &K, const char *p0, con
 __device__ __forceinline__ bool pair_occluded(const PackK &K, const char *p0, const char *p1, const char *p2, const bool valid_b,
                                               const float org[3], const float dir[3])
 {
-    const P4 c0 = ldg256p(p0), c1 = ldg256p(p1);
+    const P4 c0 = ldg256p_stream(p0), c1 = ldg256p_stream(p1);
     const P2 c2 = ldg128p(p2);
     const PairMT r = pair_mt(K, c0, c1, c2, org, dir);
     float aA, aB, uA, uB, vA, vB, tA, tB, wA, wB;

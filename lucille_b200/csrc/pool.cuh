@@ -130,7 +130,7 @@ __device__ __forceinline__ void load_node_shared(const char *, NodeRegs<double> 
 __device__ __forceinline__ void node_step_pk(const PackK &K, const Node32 *p, const float org[3], const float inv[3], bool sx, bool sy, bool sz,
                                              float best_t, bool &h0, bool &h1, uint32_t &c0, uint32_t &c1, uint32_t &axis)
 {
-    const P4 a = ldg256p(p), b = ldg256p(reinterpret_cast<const char *>(p) + 32);
+    const P4 a = ldg256p_keep(p), b = ldg256p_keep(reinterpret_cast<const char *>(p) + 32);
     const pk_t ox = pkb(org[0]), oy = pkb(org[1]), oz = pkb(org[2]);
     const pk_t ix = pkb(inv[0]), iy = pkb(inv[1]), iz = pkb(inv[2]);
     h0 = slab_pk(K, a.v[0], a.v[2], b.v[0], ox, oy, oz, ix, iy, iz, sx, sy, sz, best_t);
@@ -196,7 +196,11 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
         // quad mode (refill_at bit 16): new rays go only to ALIGNED LANE QUADS that are idle as a whole, four consecutive rays each.
         // An LDG.256 is served four lanes per L1 pass, and four rays of one AO point that start at the root together walk the
         // same nodes until their paths part -- one wavefront per node record instead of four while they do.
+#ifdef B200_NO_QUAD
+        const bool quad_mode = false;
+#else
         const bool quad_mode = ((refill_at >> 16) & 1u) != 0u;
+#endif
         auto fetchable = [&](unsigned m) -> unsigned {
             if (!quad_mode) return m;
             const unsigned q = m & (m >> 1) & (m >> 2) & (m >> 3) & 0x11111111u;
@@ -234,7 +238,8 @@ occluded_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, co
             const unsigned rank = __popc(idle & lt_mask);
             if (((idle >> lane) & 1u) && rank < take) {
                 idx = chunk_next + rank;
-                RayIO<Real>::load(rays, idx, org, dir);
+                if (ready) RayIO<Real>::load_coherent(rays, idx, org, dir);      // the copy engine is still writing this buffer: no ld.global.nc
+                else RayIO<Real>::load(rays, idx, org, dir);
                 RaySlot<Real>::store(s_rays, lane, org, dir);
                 sx = dir[0] < Real(0); sy = dir[1] < Real(0); sz = dir[2] < Real(0);
 #pragma unroll

@@ -1,0 +1,227 @@
+// The fp32 occlusion traverser the AO rays run through: pool.cuh's pooled scheme (same answers, same argument for exactness),
+// specialised and put on an instruction diet.
+//
+// Why: profiles/r02_* show the pooled kernel limited by warp-instruction ISSUE (an A/B with ~10 dead bookkeeping instructions per
+// loop iteration added cost 3 % of the rays/s; ray order, L1 hints and the L1 wavefront count did not move it), so every instruction
+// that is not arithmetic of the reference is overhead to remove:
+//   * STATIC shared memory, templated on the stack capacity: every shared-memory address is lane offset + compile-time constant.
+//     With the dynamic array of pool.cuh the compiler re-derived the shared window base (S2UR SR_CgaCtaId, UMOV, ULEA, LDCU) at
+//     each use because it cannot spare registers for the pointers at 64 registers / 4 CTAs per SM.
+//   * the per-lane stack pointer is kept as a BYTE OFFSET that already contains the lane's column (push / pop = one add);
+//   * the ray's three sign bits live in one mask: near child = (mask >> axis) & 1 instead of two selects and a compare;
+//   * leaf-round / refill thresholds and the result kind (occlusion bytes or per-point counters) are template constants;
+//   * the acceptance window of triangle_isect is a chain of predicated SETPs (one instruction per comparison).
+// Arithmetic: packed.cuh (FFMA2 on (A, B) triangle pairs and (lo, hi) box planes, each result rounded like the scalar operation).
+// Trees deeper than the largest instantiated stack, fp64 records and the experiments stay with pool.cuh.
+#pragma once
+
+namespace b200 {
+
+// acceptance of both triangles of an item in leaf order from t_leaf = 1e38 (bvh.c:833-848; NEGATED comparisons like tri_test_bf):
+// returns tl < 1e38 after the pair.
+__device__ __forceinline__ bool pair_accept_occluded(const PairMT &r, const bool valid_b)
+{
+    float aA, aB, uA, uB, vA, vB, tA, tB, wA, wB;
+    upk2(r.a, aA, aB); upk2(r.u, uA, uB); upk2(r.v, vA, vB); upk2(r.t, tA, tB); upk2(r.uv, wA, wB);
+    uint32_t res;
+    asm("{\n\t.reg .pred p, q;\n\t.reg .f32 x, tl;\n\t"
+        "abs.f32 x, %1;\n\t"
+        "setp.gt.f32 p, x, 0f283424DC;\n\t"             // |a| > 1e-14f
+        "setp.geu.and.f32 p, %2, 0f00000000, p;\n\t"    // !(u < 0)
+        "setp.leu.and.f32 p, %2, 0f3F800000, p;\n\t"    // !(u > 1)
+        "setp.geu.and.f32 p, %3, 0f00000000, p;\n\t"    // !(v < 0)
+        "setp.leu.and.f32 p, %4, 0f3F800000, p;\n\t"    // !(u + v > 1)
+        "setp.geu.and.f32 p, %5, 0f00000000, p;\n\t"    // !(t < 0)
+        "setp.leu.and.f32 p, %5, 0f7E967699, p;\n\t"    // !(t > 1e38)
+        "selp.f32 tl, %5, 0f7E967699, p;\n\t"           // t_leaf after A
+        "abs.f32 x, %6;\n\t"
+        "setp.ne.u32 q, %11, 0;\n\t"                    // B is a real triangle
+        "setp.gt.and.f32 q, x, 0f283424DC, q;\n\t"
+        "setp.geu.and.f32 q, %7, 0f00000000, q;\n\t"
+        "setp.leu.and.f32 q, %7, 0f3F800000, q;\n\t"
+        "setp.geu.and.f32 q, %8, 0f00000000, q;\n\t"
+        "setp.leu.and.f32 q, %9, 0f3F800000, q;\n\t"
+        "setp.geu.and.f32 q, %10, 0f00000000, q;\n\t"
+        "setp.leu.and.f32 q, %10, tl, q;\n\t"           // !(t > t_leaf)
+        "selp.f32 tl, %10, tl, q;\n\t"
+        "setp.lt.f32 p, tl, 0f7E967699;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(res)
+        : "f"(aA), "f"(uA), "f"(vA), "f"(wA), "f"(tA), "f"(aB), "f"(uB), "f"(vB), "f"(wB), "f"(tB), "r"((uint32_t)valid_b));
+    return res != 0u;
+}
+
+template <int kCap> struct Pool32Smem {
+    uint32_t stack[kCap * kBlock];       // [depth][thread]: conflict-free columns
+    float4   rays[kBlock * 2];           // a lane's (org, dir): 32 bytes, read by the lanes that test its leaf items
+    uint2    desc[kBlock];               // leaf-round descriptors, one run per warp
+};
+
+template <int kCap, bool kCounts>
+__global__ void __launch_bounds__(kBlock, 4)
+occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
+                       const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
+                       unsigned int *__restrict__ work_counter, const unsigned int *__restrict__ ready, unsigned int *__restrict__ fault,
+                       const PackK K)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t kRefillAt = 4u, kLeafAt = 32u;                  // measured best on C3 (B200_REFILL / B200_LEAF_AT sweeps of pool.cuh)
+    constexpr uint32_t kRow = kBlock * 4u;                             // bytes between two stack levels of a lane
+    __shared__ __align__(16) Pool32Smem<kCap> sm;
+    const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
+    char *const stack_bytes = reinterpret_cast<char *>(sm.stack);
+    const float4 *const w_rays = sm.rays + 2u * wbase;                 // this warp's 32 ray slots
+    uint2 *const w_desc = sm.desc + wbase;
+
+    uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
+    bool exhausted = false;                      // warp-uniform
+
+    // per-lane ray state.  cur: kIdle | inner-node index | leaf word; prog: items of that leaf already tested;
+    // spa: byte offset of the lane's next free stack entry (level * kRow + 4 * thread); sgn: bit k = dir[k] < 0
+    uint32_t cur = kIdle, prog = 0, idx = 0, spa = threadIdx.x * 4u, sgn = 0;
+    float org[3] = {0.0f, 0.0f, 0.0f}, inv[3] = {0.0f, 0.0f, 0.0f};
+
+    auto retire = [&](const bool hit) {
+        if (kCounts) { if (hit) atomicAdd(&counts[idx / rays_per_count], 1u); }
+        else occ[idx] = hit ? 1 : 0;
+    };
+
+    for (;;) {
+        // ------------------------------------------------------------------ fetch (pool.cuh)
+        unsigned idle = __ballot_sync(FULL, cur == kIdle);
+        while (idle && !exhausted) {
+            if (chunk_next >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; break; }
+                chunk_next = base;
+                chunk_end = (n - base < chunk) ? n : base + chunk;
+                if (ready) {                     // streamed upload: wait until the copy engine has delivered this chunk
+                    if (lane == 0) {
+                        unsigned spins = 0, have;
+                        for (;;) {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(ready) : "memory");
+                            if (have >= chunk_end) break;
+                            __nanosleep(200);
+                            if (++spins > kPoolSpinCap) { atomicExch(fault, 1u); break; }
+                        }
+                    }
+                    __syncwarp();
+                    if (*(volatile unsigned int *)fault) { exhausted = true; break; }
+                }
+            }
+            const unsigned avail = chunk_end - chunk_next;
+            const unsigned n_idle = __popc(idle);
+            const unsigned take = n_idle < avail ? n_idle : avail;
+            const unsigned rank = __popc(idle & lt_mask);
+            if (cur == kIdle && rank < take) {
+                idx = chunk_next + rank;
+                float dir[3];
+                if (ready) RayIO<float>::load_coherent(rays, idx, org, dir);      // the copy engine is still writing this buffer: no ld.global.nc
+                else RayIO<float>::load(rays, idx, org, dir);
+                float4 *slot = sm.rays + 2u * threadIdx.x;
+                slot[0] = make_float4(org[0], org[1], org[2], 0.0f); slot[1] = make_float4(dir[0], dir[1], dir[2], 0.0f);
+                const bool sx = dir[0] < 0.0f, sy = dir[1] < 0.0f, sz = dir[2] < 0.0f;
+                sgn = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)      // bvh.c:473-497
+                    inv[k] = (fabsf(dir[k]) > 1.0e-14f) ? 1.0f / dir[k] : ((dir[k] < 0.0f) ? -FLT_MAX : FLT_MAX);
+                float tmin;
+                const bool in_scene = (S.root_word != kDoneWord) &&
+                    slab<float>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
+                spa = threadIdx.x * 4u; prog = 0;
+                if (in_scene) cur = S.root_word;
+                else retire(false);              // bvh.c:446 / 522-526: miss without traversal
+            }
+            chunk_next += take;
+            idle = __ballot_sync(FULL, cur == kIdle);
+        }
+        if (idle == FULL) break;                 // nothing in flight and nothing left to fetch
+
+        // ------------------------------------------------------------------ traverse
+        for (;;) {
+            const bool in_leaf = (int32_t)cur < 0;
+            const uint32_t nitems = (((cur >> kLeafShift) & 15u) + 2u) >> 1;      // (ntris + 1) / 2 pairs
+            const uint32_t cnt = in_leaf ? nitems - prog : 0u;                    // >= 1 for a lane standing in a leaf
+            const uint32_t total = __reduce_add_sync(FULL, cnt);
+            const unsigned owners = __ballot_sync(FULL, in_leaf);
+            const unsigned in_node = __ballot_sync(FULL, cur < kIdle);            // inner-node indices are < kIdle, leaf words above
+            const unsigned n_node = __popc(in_node);
+            if ((in_node | owners) == 0u) break;
+            if (!exhausted && (uint32_t)__popc(~(in_node | owners)) >= kRefillAt) break;
+
+            if (total >= kLeafAt || total > n_node) {
+                // ---- leaf round: items 0..31 of the pool, one per lane (pool.cuh)
+                uint32_t excl = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    excl += (uint32_t)__popc(ballot_bit(cnt, 1u << b) & lt_mask) << b;
+                const bool owner = in_leaf && excl < 32u;
+                const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);
+                if (owner) w_desc[__popc(owners & lt_mask)] = make_uint2(cur, lane | ((prog - excl + 64u) << 8));
+                __syncwarp();
+                bool hit = false;
+                if (lane < total) {
+                    const uint2 d = w_desc[__popc(starts & le_mask) - 1u];
+                    const unsigned own = d.y & 31u;
+                    const uint32_t item = lane + (d.y >> 8) - 64u;                // item number inside the owner's leaf
+                    const uint32_t ntris = ((d.x >> kLeafShift) & 15u) + 1u, slot0 = d.x & kSlotMask;
+                    const uint32_t m = ((ntris + 3u) >> 2) << 1;                  // row length in pairs
+                    const uint32_t o0 = slot0 * 3u + item * 2u, o1 = o0 + 2u * m, o2 = slot0 * 3u + 4u * m + item;    // 16-byte units
+                    const P4 c0 = ldg256p(trisT + (size_t)o0 * 16u), c1 = ldg256p(trisT + (size_t)o1 * 16u);
+                    const P2 c2 = ldg128p(trisT + (size_t)o2 * 16u);
+                    const float4 ro = w_rays[2u * own], rd = w_rays[2u * own + 1u];
+                    const float oorg[3] = {ro.x, ro.y, ro.z}, odir[3] = {rd.x, rd.y, rd.z};
+                    hit = pair_accept_occluded(pair_mt(K, c0, c1, c2, oorg, odir), 2u * item + 1u < ntris);
+                }
+                const unsigned hits = __ballot_sync(FULL, hit);
+                if (owner) {
+                    const uint32_t room = 32u - excl, took = cnt < room ? cnt : room;
+                    const unsigned mine = (FULL >> (32u - took)) << excl;         // took >= 1
+                    if (hits & mine) { retire(true); cur = kIdle; }               // occluded: bvh.c:850 commits, the query is decided
+                    else {
+                        prog += took;
+                        if (prog == nitems) {                                     // leaf exhausted without a hit: pop, or the ray escapes
+                            prog = 0;
+                            if (spa < kRow) { retire(false); cur = kIdle; }
+                            else { spa -= kRow; cur = *reinterpret_cast<const uint32_t *>(stack_bytes + spa); }
+                        }
+                    }
+                }
+            }
+            if (cur < kIdle) {
+                // ---- node step: bvh.c:1153-1179 with best_t == 1e38 (no hit yet)
+                const Node32 *p = S.nodes + cur;
+                const P4 a = ldg256p(p), b = ldg256p(reinterpret_cast<const char *>(p) + 32);
+                const pk_t ox = pkb(org[0]), oy = pkb(org[1]), oz = pkb(org[2]);
+                const pk_t ix = pkb(inv[0]), iy = pkb(inv[1]), iz = pkb(inv[2]);
+                const bool sx = (sgn & 1u) != 0u, sy = (sgn & 2u) != 0u, sz = (sgn & 4u) != 0u;
+                const bool h0 = slab_pk(K, a.v[0], a.v[2], b.v[0], ox, oy, oz, ix, iy, iz, sx, sy, sz, 1.0e38f);
+                const bool h1 = slab_pk(K, a.v[1], a.v[3], b.v[1], ox, oy, oz, ix, iy, iz, sx, sy, sz, 1.0e38f);
+                const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
+                const bool order = ((sgn >> axis) & 1u) != 0u;                    // near child = child[sign[axis0]]
+                const uint32_t near = order ? c1 : c0, far = order ? c0 : c1;
+                uint32_t next;
+                if (h0 && h1) {
+                    *reinterpret_cast<uint32_t *>(stack_bytes + spa) = far;
+                    spa += kRow;
+                    next = near;
+                } else if (h0 || h1) {
+                    next = h0 ? c0 : c1;
+                } else if (spa >= kRow) {
+                    spa -= kRow;
+                    next = *reinterpret_cast<const uint32_t *>(stack_bytes + spa);
+                } else {
+                    next = kIdle;
+                    retire(false);                                                // stack ran dry
+                }
+                prog = 0;
+                cur = next;
+            }
+        }
+    }
+}
+
+}  // namespace b200

@@ -55,6 +55,8 @@ def main():
         "morton_oct": np.argsort((morton << np.uint64(35)) | (octant << np.uint64(32)) | point, kind="stable"),
         "random": rng.permutation(nr),
     }
+    if os.environ.get("ORDERS"):
+        orders = {k: v for k, v in orders.items() if k in os.environ["ORDERS"].split(",")}
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     d_occ = torch.empty((nr,), dtype=torch.uint8, device="cuda")
