@@ -210,10 +210,16 @@ static int stack_capacity(const ri_b200_accel *a)
     return cap;
 }
 
+template <int kCap>
+static void launch_closest32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st);
+static bool launch_closest32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st);
+static bool launch_closest32(ri_b200_accel *, const double *, uint32_t, uint32_t, ri_b200_hit_f64 *, unsigned int *, cudaStream_t) { return false; }
+
 template <typename Real>
 static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m, uint32_t chunk, typename RayIO<Real>::Hit *d_hits,
                                 unsigned int *ctr, uint32_t refill_at, cudaStream_t st)
 {
+    if (launch_closest32(a, d_rays, m, chunk, d_hits, ctr, st)) return;       // fp32 on a tree that fits a static stack: pool32.cuh
     const int cap = stack_capacity(a);
     const size_t smem = pool_closest_smem_bytes<Real>(cap);
     auto kern = closest_pool_kernel<Real>;
@@ -255,6 +261,29 @@ static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uin
 }
 static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, uint8_t *, uint32_t *, uint32_t, unsigned int *,
                           const unsigned int *, unsigned int *, unsigned, cudaStream_t) { return false; }
+
+template <int kCap>
+static void launch_closest32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st)
+{
+    auto kern = closest_pool32_kernel<kCap>;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0);
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
+    uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
+    want = (want + (kBlock / 32) - 1) / (kBlock / 32);
+    const unsigned blocks = (unsigned)(want < capb ? want : capb);
+    kern<<<blocks, kBlock, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_hits, ctr, make_pack_k());
+}
+static bool launch_closest32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st)
+{
+    static const bool off = (getenv("B200_POOL32") && atoi(getenv("B200_POOL32")) == 0) || getenv("B200_REFILL");
+    const int cap = stack_capacity(a);
+    if (off || cap > 24) return false;
+    if (cap <= 20) launch_closest32_cap<20>(a, d_rays, m, chunk, d_hits, ctr, st);
+    else launch_closest32_cap<24>(a, d_rays, m, chunk, d_hits, ctr, st);
+    return true;
+}
 
 template <typename Real, bool ANYHIT, bool COUNT>
 static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typename RayIO<Real>::Hit *d_hits, uint8_t *d_occ,

@@ -51,10 +51,28 @@ __device__ __forceinline__ bool pair_accept_occluded(const PairMT &r, const bool
     return res != 0u;
 }
 
+// shared-memory accesses by 32-bit shared-window address: [lane offset + link-time constant] in SASS.  Through generic pointers the
+// compiler re-derives the shared window base (S2UR SR_CgaCtaId, UMOV, ULEA) at every use when it has no register to keep it in.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v)
+{ asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
+
+struct Pool32Warp {
+    float4 rays[64];                     // a lane's (org, dir): 32 bytes, read by the lanes that test its leaf items
+    uint2  desc[32];                     // leaf-round descriptors of this warp (one address register serves both areas)
+};
 template <int kCap> struct Pool32Smem {
-    uint32_t stack[kCap * kBlock];       // [depth][thread]: conflict-free columns
-    float4   rays[kBlock * 2];           // a lane's (org, dir): 32 bytes, read by the lanes that test its leaf items
-    uint2    desc[kBlock];               // leaf-round descriptors, one run per warp
+    uint32_t   stack[kCap * kBlock];     // [depth][thread]: conflict-free columns
+    Pool32Warp warp[kBlock / 32];
 };
 
 template <int kCap, bool kCounts>
@@ -70,9 +88,13 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
     __shared__ __align__(16) Pool32Smem<kCap> sm;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
-    char *const stack_bytes = reinterpret_cast<char *>(sm.stack);
-    const float4 *const w_rays = sm.rays + 2u * wbase;                 // this warp's 32 ray slots
-    uint2 *const w_desc = sm.desc + wbase;
+    // shared-window address of the block's record, taken ONCE through an opaque asm so that it is kept (the compiler's own
+    // conversion is rematerialised at every use); everything else is a compile-time offset from it
+    uint32_t sm_a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sm_a) : "l"(&sm));
+    const uint32_t stack_a = sm_a + (uint32_t)offsetof(Pool32Smem<kCap>, stack);
+    const uint32_t rays_a = sm_a + (uint32_t)offsetof(Pool32Smem<kCap>, warp) + (wbase >> 5) * (uint32_t)sizeof(Pool32Warp);   // this warp's 32 ray slots
+    const uint32_t desc_a = rays_a + (uint32_t)offsetof(Pool32Warp, desc);                                                        // and its descriptor run
 
     uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform
     bool exhausted = false;                      // warp-uniform
@@ -121,8 +143,8 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                 float dir[3];
                 if (ready) RayIO<float>::load_coherent(rays, idx, org, dir);      // the copy engine is still writing this buffer: no ld.global.nc
                 else RayIO<float>::load(rays, idx, org, dir);
-                float4 *slot = sm.rays + 2u * threadIdx.x;
-                slot[0] = make_float4(org[0], org[1], org[2], 0.0f); slot[1] = make_float4(dir[0], dir[1], dir[2], 0.0f);
+                sts128(rays_a + lane * 32u, make_float4(org[0], org[1], org[2], 0.0f));
+                sts128(rays_a + lane * 32u + 16u, make_float4(dir[0], dir[1], dir[2], 0.0f));
                 const bool sx = dir[0] < 0.0f, sy = dir[1] < 0.0f, sz = dir[2] < 0.0f;
                 sgn = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
 #pragma unroll
@@ -160,11 +182,11 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                     excl += (uint32_t)__popc(ballot_bit(cnt, 1u << b) & lt_mask) << b;
                 const bool owner = in_leaf && excl < 32u;
                 const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);
-                if (owner) w_desc[__popc(owners & lt_mask)] = make_uint2(cur, lane | ((prog - excl + 64u) << 8));
+                if (owner) sts64(desc_a + (uint32_t)__popc(owners & lt_mask) * 8u, make_uint2(cur, lane | ((prog - excl + 64u) << 8)));
                 __syncwarp();
                 bool hit = false;
                 if (lane < total) {
-                    const uint2 d = w_desc[__popc(starts & le_mask) - 1u];
+                    const uint2 d = lds64(desc_a + (uint32_t)__popc(starts & le_mask) * 8u - 8u);
                     const unsigned own = d.y & 31u;
                     const uint32_t item = lane + (d.y >> 8) - 64u;                // item number inside the owner's leaf
                     const uint32_t ntris = ((d.x >> kLeafShift) & 15u) + 1u, slot0 = d.x & kSlotMask;
@@ -172,7 +194,7 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                     const uint32_t o0 = slot0 * 3u + item * 2u, o1 = o0 + 2u * m, o2 = slot0 * 3u + 4u * m + item;    // 16-byte units
                     const P4 c0 = ldg256p(trisT + (size_t)o0 * 16u), c1 = ldg256p(trisT + (size_t)o1 * 16u);
                     const P2 c2 = ldg128p(trisT + (size_t)o2 * 16u);
-                    const float4 ro = w_rays[2u * own], rd = w_rays[2u * own + 1u];
+                    const float4 ro = lds128(rays_a + own * 32u), rd = lds128(rays_a + own * 32u + 16u);
                     const float oorg[3] = {ro.x, ro.y, ro.z}, odir[3] = {rd.x, rd.y, rd.z};
                     hit = pair_accept_occluded(pair_mt(K, c0, c1, c2, oorg, odir), 2u * item + 1u < ntris);
                 }
@@ -186,7 +208,7 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                         if (prog == nitems) {                                     // leaf exhausted without a hit: pop, or the ray escapes
                             prog = 0;
                             if (spa < kRow) { retire(false); cur = kIdle; }
-                            else { spa -= kRow; cur = *reinterpret_cast<const uint32_t *>(stack_bytes + spa); }
+                            else { spa -= kRow; cur = lds32(stack_a + spa); }
                         }
                     }
                 }
@@ -204,21 +226,200 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                 const bool order = ((sgn >> axis) & 1u) != 0u;                    // near child = child[sign[axis0]]
                 const uint32_t near = order ? c1 : c0, far = order ? c0 : c1;
                 uint32_t next;
-                if (h0 && h1) {
-                    *reinterpret_cast<uint32_t *>(stack_bytes + spa) = far;
-                    spa += kRow;
-                    next = near;
-                } else if (h0 || h1) {
-                    next = h0 ? c0 : c1;
-                } else if (spa >= kRow) {
-                    spa -= kRow;
-                    next = *reinterpret_cast<const uint32_t *>(stack_bytes + spa);
-                } else {
-                    next = kIdle;
-                    retire(false);                                                // stack ran dry
-                }
+                const bool both = h0 && h1, none = !h0 && !h1;                   // predicated: measured 1080 vs 1072 Mrays/s for the branchy form
+                const bool pop = none && (spa >= kRow);
+                if (both) sts32(stack_a + spa, far);
+                const uint32_t popped = pop ? lds32(stack_a + spa - kRow) : kIdle;
+                spa = spa + (both ? kRow : 0u) - (pop ? kRow : 0u);
+                next = both ? near : (none ? popped : (h0 ? c0 : c1));
+                if (next == kIdle) retire(false);                                 // stack ran dry
                 prog = 0;
                 cur = next;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// closest hit, fp32 records: pool_closest.cuh's scheme (a lane waits in its leaf until the leaf is committed; the leaf's winner is one
+// shared-memory atomicMin on (bits of |t|) << 32 | (31 - lane); exactness argument there) with the same diet as the kernel above.
+struct Close32Warp {
+    float4 rays[64];                     // ray slots
+    uint2  desc[32];                     // leaf-round descriptors
+    unsigned long long key[32];          // per owner: smallest (|t| bits, 31 - lane) offered this round
+    float4 res[32];                      // per item lane: (t, u, v, prim bits) of its accepted triangle
+    float4 leaf[32];                     // per lane: the leaf-local winner so far (t, u, v, prim bits); its t is also in a register
+    float4 best[32];                     // per lane: the committed closest hit so far; its t is also in a register
+};
+template <int kCap> struct Close32Smem {
+    uint32_t    stack[kCap * kBlock];
+    Close32Warp warp[kBlock / 32];
+};
+__device__ __forceinline__ void atom_min_shared_u64(uint32_t a, unsigned long long v)
+{ asm volatile("red.shared.min.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a)
+{ unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+
+// 3 CTAs per SM at 80 registers: measured 892 Mrays/s on the C3 batch against 838 with 4 CTAs at 64 registers (spills)
+#ifndef B200_CLOSE_CTAS
+#define B200_CLOSE_CTAS 3
+#endif
+template <int kCap>
+__global__ void __launch_bounds__(kBlock, B200_CLOSE_CTAS)
+closest_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
+                      const uint32_t chunk, ri_b200_hit_f32 *__restrict__ hits_out, unsigned int *__restrict__ work_counter, const PackK K)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t kRefillAt = 4u;
+    constexpr uint32_t kRow = kBlock * 4u;
+    __shared__ __align__(16) Close32Smem<kCap> sm;
+    const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
+    uint32_t sm_a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sm_a) : "l"(&sm));
+    const uint32_t stack_a = sm_a + (uint32_t)offsetof(Close32Smem<kCap>, stack);
+    const uint32_t rays_a = sm_a + (uint32_t)offsetof(Close32Smem<kCap>, warp) + (wbase >> 5) * (uint32_t)sizeof(Close32Warp);
+    const uint32_t desc_a = rays_a + (uint32_t)offsetof(Close32Warp, desc);
+    const uint32_t key_a = rays_a + (uint32_t)offsetof(Close32Warp, key);
+    const uint32_t res_a = rays_a + (uint32_t)offsetof(Close32Warp, res);
+    const uint32_t leaf_a = rays_a + (uint32_t)offsetof(Close32Warp, leaf) + lane * 16u;      // (u, v, prim) of the two records live in
+    const uint32_t best_a = rays_a + (uint32_t)offsetof(Close32Warp, best) + lane * 16u;      // shared memory, their t in registers
+
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    uint32_t cur = kIdle, prog = 0, idx = 0, spa = threadIdx.x * 4u, sgn = 0;
+    float org[3] = {0.0f, 0.0f, 0.0f}, inv[3] = {0.0f, 0.0f, 0.0f};
+    float best_t = 1.0e38f, tl = 1.0e38f;        // tl == 1e38 <=> the leaf has no accepted triangle yet (a t of exactly 1e38 never commits: bvh.c:850)
+
+    auto retire = [&]() {                        // bvh.c:1187
+        const float4 b = lds128(best_a);
+        RayIO<float>::store(hits_out, idx, best_t < 1.0e38f, best_t, b.y, b.z, __float_as_uint(b.w));
+    };
+    auto enter = [&](const uint32_t word) {      // step onto `word`; a leaf starts with a fresh leaf-local record (bvh.c:833-836)
+        cur = word; prog = 0;
+        tl = 1.0e38f;
+    };
+
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, cur == kIdle);
+        while (idle && !exhausted) {
+            if (chunk_next >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; break; }
+                chunk_next = base;
+                chunk_end = (n - base < chunk) ? n : base + chunk;
+            }
+            const unsigned avail = chunk_end - chunk_next;
+            const unsigned n_idle = __popc(idle);
+            const unsigned take = n_idle < avail ? n_idle : avail;
+            const unsigned rank = __popc(idle & lt_mask);
+            if (cur == kIdle && rank < take) {
+                idx = chunk_next + rank;
+                float dir[3];
+                RayIO<float>::load(rays, idx, org, dir);
+                sts128(rays_a + lane * 32u, make_float4(org[0], org[1], org[2], 0.0f));
+                sts128(rays_a + lane * 32u + 16u, make_float4(dir[0], dir[1], dir[2], 0.0f));
+                best_t = 1.0e38f;
+                const bool sx = dir[0] < 0.0f, sy = dir[1] < 0.0f, sz = dir[2] < 0.0f;
+                sgn = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)      // bvh.c:473-497
+                    inv[k] = (fabsf(dir[k]) > 1.0e-14f) ? 1.0f / dir[k] : ((dir[k] < 0.0f) ? -FLT_MAX : FLT_MAX);
+                float tmin;
+                const bool in_scene = (S.root_word != kDoneWord) &&
+                    slab<float>(S.smin[0], S.smax[0], S.smin[1], S.smax[1], S.smin[2], S.smax[2], org, inv, sx, sy, sz, tmin);
+                spa = threadIdx.x * 4u;
+                if (in_scene) enter(S.root_word);
+                else retire();                   // bvh.c:446 / 522-526: miss without traversal
+            }
+            chunk_next += take;
+            idle = __ballot_sync(FULL, cur == kIdle);
+        }
+        if (idle == FULL) break;
+
+        for (;;) {
+            const bool in_leaf = (int32_t)cur < 0;
+            const uint32_t nitems = (((cur >> kLeafShift) & 15u) + 2u) >> 1;
+            const uint32_t cnt = in_leaf ? nitems - prog : 0u;
+            const uint32_t total = __reduce_add_sync(FULL, cnt);
+            const unsigned owners = __ballot_sync(FULL, in_leaf);
+            const unsigned in_node = __ballot_sync(FULL, cur < kIdle);
+            const unsigned n_node = __popc(in_node);
+            if ((in_node | owners) == 0u) break;
+            if (!exhausted && (uint32_t)__popc(~(in_node | owners)) >= kRefillAt) break;
+
+            if (total >= 32u || total > n_node) {
+                // ---- leaf round: items 0..31 of the pool, one per lane
+                uint32_t excl = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    excl += (uint32_t)__popc(ballot_bit(cnt, 1u << b) & lt_mask) << b;
+                const bool owner = in_leaf && excl < 32u;
+                const unsigned starts = __reduce_or_sync(FULL, owner ? (1u << excl) : 0u);
+                if (owner) {
+                    sts64(desc_a + (uint32_t)__popc(owners & lt_mask) * 8u, make_uint2(cur, lane | ((prog - excl + 64u) << 8)));
+                    sts_u64(key_a + lane * 8u, ~0ull);
+                }
+                __syncwarp();
+                if (lane < total) {
+                    const uint2 d = lds64(desc_a + (uint32_t)__popc(starts & le_mask) * 8u - 8u);
+                    const unsigned own = d.y & 31u;
+                    const uint32_t item = lane + (d.y >> 8) - 64u;
+                    const uint32_t ntris = ((d.x >> kLeafShift) & 15u) + 1u, slot0 = d.x & kSlotMask;
+                    const uint32_t m = ((ntris + 3u) >> 2) << 1;
+                    const uint32_t o0 = slot0 * 3u + item * 2u, o1 = o0 + 2u * m, o2 = slot0 * 3u + 4u * m + item;
+                    const float4 ro = lds128(rays_a + own * 32u), rd = lds128(rays_a + own * 32u + 16u);
+                    const float oorg[3] = {ro.x, ro.y, ro.z}, odir[3] = {rd.x, rd.y, rd.z};
+                    float t, u, v;
+                    uint32_t prim;
+                    pair_closest(K, trisT + (size_t)o0 * 16u, trisT + (size_t)o1 * 16u, trisT + (size_t)o2 * 16u, 2u * item + 1u < ntris, oorg, odir,
+                                 t, u, v, prim);
+                    if (prim != 0xffffffffu) {   // the item accepted a triangle: offer it to the owner
+                        sts128(res_a + lane * 16u, make_float4(t, u, v, __uint_as_float(prim)));
+                        atom_min_shared_u64(key_a + own * 8u, ((unsigned long long)(__float_as_uint(t) & 0x7fffffffu) << 32) | (unsigned long long)(31u - lane));
+                    }
+                }
+                __syncwarp();
+                if (owner) {
+                    const uint32_t room = 32u - excl, took = cnt < room ? cnt : room;
+                    const unsigned long long key = lds_u64(key_a + lane * 8u);
+                    if (key != ~0ull) {          // winner of this round's items of my leaf; accepted unless t > t_leaf (bvh.c:780)
+                        const float4 r = lds128(res_a + (31u - (unsigned)(key & 31ull)) * 16u);
+                        if (!(r.x > tl)) { tl = r.x; sts128(leaf_a, r); }
+                    }
+                    prog += took;
+                    if (prog == nitems) {        // leaf finished: commit (bvh.c:850), then pop or retire
+                        if (tl < best_t) { best_t = tl; sts128(best_a, lds128(leaf_a)); }      // tl < best_t <= 1e38: the leaf accepted a triangle
+                        if (spa < kRow) { retire(); cur = kIdle; }
+                        else { spa -= kRow; enter(lds32(stack_a + spa)); }
+                    }
+                }
+                __syncwarp();                    // key / res are rewritten by the next round
+            }
+            if (cur < kIdle) {
+                // ---- node step: bvh.c:1153-1179
+                const Node32 *p = S.nodes + cur;
+                const P4 a = ldg256p(p), b = ldg256p(reinterpret_cast<const char *>(p) + 32);
+                const pk_t ox = pkb(org[0]), oy = pkb(org[1]), oz = pkb(org[2]);
+                const pk_t ix = pkb(inv[0]), iy = pkb(inv[1]), iz = pkb(inv[2]);
+                const bool sx = (sgn & 1u) != 0u, sy = (sgn & 2u) != 0u, sz = (sgn & 4u) != 0u;
+                const bool h0 = slab_pk(K, a.v[0], a.v[2], b.v[0], ox, oy, oz, ix, iy, iz, sx, sy, sz, best_t);
+                const bool h1 = slab_pk(K, a.v[1], a.v[3], b.v[1], ox, oy, oz, ix, iy, iz, sx, sy, sz, best_t);
+                const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
+                const bool order = ((sgn >> axis) & 1u) != 0u;
+                const uint32_t near = order ? c1 : c0, far = order ? c0 : c1;
+                const bool both = h0 && h1, none = !h0 && !h1;
+                const bool pop = none && (spa >= kRow);
+                if (both) sts32(stack_a + spa, far);
+                const uint32_t popped = pop ? lds32(stack_a + spa - kRow) : kIdle;
+                spa = spa + (both ? kRow : 0u) - (pop ? kRow : 0u);
+                const uint32_t next = both ? near : (none ? popped : (h0 ? c0 : c1));
+                if (next == kIdle) { retire(); cur = kIdle; }
+                else enter(next);
             }
         }
     }
