@@ -7,9 +7,18 @@ synthetic 1 M-triangle soup, 16 M incoherent ambient-occlusion hemisphere rays, 
 
 A "step" is one pass of the hot path over one batch: one occlusion (any-hit) traversal of the whole 16 Mi-ray batch
 on the reference-identical BVH.  `value` is whole-job Mrays/s with rays resident in HBM; `e2e` is the same metric
-through the C-ABI call with pinned HOST buffers (H2D of the rays and D2H of the occlusion bytes inside the timed
-region).  Multi-GPU: the scene is replicated, every rank traces its own 16 Mi-ray batch (weak scaling), no data-path
-collective (rays never interact); timing is barrier + CUDA events, max over ranks.
+through the reference-facing C-ABI call with HOST buffers: ri_b200_occlusion_points_f32 = calculate_occlusion
+(ambientocclusion.c:42-151) for the batch's 262 144 shading points -- pinned host points in (H2D), rays generated and
+traced on the device, occluded-ray counts out (D2H), all inside the timed region; the older per-ray host path
+(ri_b200_occluded_batch_f32: 32 B per ray up, 1 B per ray down) is reported beside it.  Multi-GPU: the scene is
+replicated, every rank traces its own 16 Mi-ray batch (weak scaling), no data-path collective (rays never interact);
+timing is barrier + CUDA events, max over ranks.
+
+`config.frames` is the other multi-GPU shape BASELINE.json names (configs[4] and configs[0]): ONE frame strong-scaled over
+the N ranks -- 32x32 buckets of the spiral order dealt round-robin to the ranks, scene replicated, the framebuffer gathered
+on rank 0 either by the resolve kernels themselves storing into rank 0's buffer over NVLink peer memory (fused) or by one
+NCCL gather of packed slabs.  Reported per frame: device time per rank, wall time until rank 0 holds the host framebuffer,
+and the frame's sha256 (equal to the single-rank frame; for ambient_occlusion.rib equal to the reference's own framebuffer).
 """
 from __future__ import annotations
 
@@ -214,6 +223,110 @@ def cpu_baseline(tris, rays8_sample, gpu_occ=None):
     return out
 
 
+def _wall_max(fn, world, dist, torch):
+    """barrier | fn() | barrier, wall seconds, max over ranks; returns (seconds, fn's result)."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return dt, out
+
+
+def frame_leg(args, rank, world, local_rank, torch, dist):
+    """config.frames: the tiled multi-GPU frames of BASELINE configs[4] (10 M-triangle soup) and configs[0] (ambient_occlusion.rib)."""
+    import hashlib
+    import math
+    from lucille_b200 import accel, distributed
+
+    def gather_stats(stats):
+        t = torch.tensor([stats.ms_total, float(stats.nrays)], device="cuda", dtype=torch.float64)
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(parts, t)
+        else:
+            parts = [t]
+        return [float(x[0]) for x in parts], sum(float(x[1]) for x in parts)
+
+    out = {}
+    # ---- configs[4]: synthetic 10 M-triangle soup, 4096 x 4096, AO; strong scaling over the ranks ------------------------------
+    ntris, res = args.frame_tris, args.frame_res
+    t0 = time.time()
+    tris = scenes.triangle_soup(ntris, scenes.SEED_C5)
+    a = accel.Accel.bind(accel.RI_ACCEL_B200).build(tris, accel.PREC_F32, device=local_rank)
+    info = a.info()
+    del tris
+    log(f"[rank {rank}] frame leg: {ntris} triangles built in {info.build_seconds:.2f}s (setup {time.time() - t0:.1f}s), "
+        f"{info.device_bytes / 1e6:.0f} MB of records")
+    c2w = np.eye(4)
+    c2w[3, :3] = (0.5, 0.5, -2.0)
+    fr = accel.make_frame(c2w.reshape(16), 1.0 / math.tan(math.radians(40.0) / 2), False, res, res, 1, 1, 64, rng_mode=1, seed=5,
+                          precision=accel.PREC_F32)
+    fb = distributed.PeerFramebuffer(res, res, rank, world, local_rank)
+    distributed.render_ao_distributed_peer(a, fr, fb)                                           # warm-up (allocations, first launches)
+    wall_p, (rgb_p, st_p) = _wall_max(lambda: distributed.render_ao_distributed_peer(a, fr, fb), world, dist, torch)
+    dev_p, nrays = gather_stats(st_p)
+    wall_n, (rgb_n, st_n) = _wall_max(lambda: distributed.render_ao_distributed(a, fr, rank, world), world, dist, torch)
+    dev_n, _ = gather_stats(st_n)
+    fb.close()
+    c5 = {"scene": f"synthetic {ntris}-triangle soup (seed C5), {info.device_bytes / 1e6:.0f} MB of records per GPU (beyond L2)",
+          "frame": f"{res}x{res}, 1x1 pixel samples, 8x8 AO rays per hit, fp32 records, counter RNG; 32x32 buckets b % {world} == rank",
+          "rays": nrays, "scaling": "strong"}
+    if rank == 0:
+        sha_p = hashlib.sha256(np.ascontiguousarray(rgb_p).tobytes()).hexdigest()
+        c5["fused_peer_store"] = {"wall_ms_to_rank0_host_framebuffer": wall_p * 1e3, "device_ms_per_rank": dev_p,
+                                  "mrays_s": nrays / wall_p / 1e6, "sha256": sha_p}
+        c5["nccl_gather"] = {"wall_ms_to_rank0_host_framebuffer": wall_n * 1e3, "device_ms_per_rank": dev_n,
+                             "mrays_s": nrays / wall_n / 1e6, "sha256": hashlib.sha256(np.ascontiguousarray(rgb_n).tobytes()).hexdigest()}
+        if world > 1:                                                                           # the same frame rendered by rank 0 alone
+            one, _ = a.render_ao(fr)
+            c5["equals_one_rank_frame"] = bool(np.array_equal(one, rgb_p) and np.array_equal(one, rgb_n))
+        else:
+            c5["equals_one_rank_frame"] = bool(np.array_equal(rgb_p, rgb_n))
+        c5["mean"] = float(rgb_p.mean())
+    out["configs[4]"] = c5
+    a.free()
+
+    # ---- configs[0]: examples/ambient_occlusion/ambient_occlusion.rib, 640 x 480, 3 x 3, 64 AO rays, the reference's MT19937 stream --
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_scene.npz"))
+    dig = np.load(os.path.join(ROOT, "tests", "golden", "c1_frame_640x480_digest.npz"))
+    cam = g["cam"]
+    c1a = accel.Accel.bind(accel.RI_ACCEL_B200).build(g["tris"], accel.PREC_F64, device=local_rank)
+    fr1 = accel.make_frame(cam[:16], cam[16], bool(cam[17]), 640, 480, 3, 3, gather_nsamples=64)
+    fb1 = distributed.PeerFramebuffer(640, 480, rank, world, local_rank)
+    distributed.render_ao_distributed_peer(c1a, fr1, fb1)
+    wall_1, (rgb_1, st_1) = _wall_max(lambda: distributed.render_ao_distributed_peer(c1a, fr1, fb1), world, dist, torch)
+    dev_1, nrays_1 = gather_stats(st_1)
+    fb1.close()
+    c1 = {"scene": "ambient_occlusion.rib (322 triangles), 640x480, PixelSamples 3 3, 64 AO rays per hit, fp64 records, the reference's "
+                   "one MT19937 stream shared by the ranks (per-bucket hit counts all-gathered between eye pass and gather pass)",
+          "rays": nrays_1, "scaling": "strong"}
+    if rank == 0:
+        sha = hashlib.sha256(np.ascontiguousarray(rgb_1, dtype=np.float32).tobytes()).hexdigest()
+        c1.update({"wall_ms_to_rank0_host_framebuffer": wall_1 * 1e3, "device_ms_per_rank": dev_1, "mrays_s": nrays_1 / wall_1 / 1e6,
+                   "sha256": sha, "equals_reference_framebuffer": bool(sha == str(dig["sha256"])),
+                   "reference_rays": int(dig["nrays"]), "reference_seconds_1thread": float(dig["seconds_1thread"])})
+    out["configs[0]"] = c1
+    c1a.free()
+    return out
+
+
+def kernel_metrics():
+    """ncu counters of ONE launch of the timed kernel on this batch (profiles/r02_kernel_metrics.json, written by
+    scripts/make_profiles.py from a committed `ncu --set full` capture): what physically limits the kernel."""
+    p = os.path.join(ROOT, "profiles", "r02_kernel_metrics.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +334,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frames", action="store_true", help="skip config.frames (the tiled multi-GPU frame leg)")
+    ap.add_argument("--frame-tris", type=int, default=10_000_000)
+    ap.add_argument("--frame-res", type=int, default=4096)
     ap.add_argument("--points", type=int, default=NPOINTS, help="debug: fewer AO points (invalidates the number)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -251,14 +367,21 @@ def main():
     info = a.info()
     order = a.triorder()
     P, n = primary_points(a.intersect, tris[order])
-    # every rank traces its own batch: same points, its own hemisphere samples (weak scaling)
-    rays_np = scenes.ao_rays(P[:npoints], n[:npoints], NTHETA, NPHI, scenes.SEED_C3 + 1000 * rank)
+    # every rank traces its own batch: same points, its own hemisphere samples (weak scaling).  The batch is the one the point entry
+    # generates on the device (calculate_occlusion's ray set-up; oracle restatement orc_ao_point_rays_f32, tests/test_gpu_fullsize.py)
+    seed = scenes.SEED_C3 + 1000 * rank
+    pts_np = np.ascontiguousarray(np.concatenate([P[:npoints], n[:npoints]], axis=1))
+    h_rays = torch.empty((nrays, 8), dtype=torch.float32, pin_memory=True)
+    accel._check(a.lib.ri_b200_ao_point_rays_f32(a.data, accel.C.byref(accel.AoPoints(NTHETA, NPHI, seed, 1.0e-6)), accel._ptr(pts_np), npoints,
+                                                  accel._ptr(h_rays.numpy())))
+    rays_np = h_rays.numpy()
     log(f"[rank {rank}] setup {time.time() - t0:.1f}s: build {info.build_seconds:.2f}s, {info.ninner} inner nodes, depth {info.max_depth}, "
         f"{info.device_bytes / 1e6:.1f} MB on device")
 
-    h_rays = torch.empty((nrays, 8), dtype=torch.float32, pin_memory=True)
-    h_rays.numpy()[:] = rays_np
     h_occ = torch.empty((nrays,), dtype=torch.uint8, pin_memory=True)
+    h_pts = torch.empty((npoints, 6), dtype=torch.float64, pin_memory=True)
+    h_pts.numpy()[:] = pts_np
+    h_cnt = torch.empty((npoints,), dtype=torch.int32, pin_memory=True)
     d_rays = h_rays.cuda(non_blocking=True)
     d_occ = torch.empty((nrays,), dtype=torch.uint8, device="cuda")
     d_hits = torch.empty((nrays, 4), dtype=torch.float32, device="cuda")
@@ -298,6 +421,19 @@ def main():
             ms = float(t.item())
         return ms
 
+    def wall(fn, steps):
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        ms = (time.perf_counter() - t1) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     step_any = lambda: a.occluded_dev(d_rays, nrays, d_occ, stream)      # noqa: E731
     step_closest = lambda: a.intersect_dev(d_rays, nrays, d_hits, stream)  # noqa: E731
 
@@ -313,32 +449,45 @@ def main():
     value = world * nrays * args.steps / (ms * 1e-3) / 1e6
 
     # closest-hit on the same batch (reported, not the headline)
+    csteps = max(3, args.steps // 2)
     for _ in range(2):
         step_closest()
-    ms_c = timed(step_closest, max(3, args.steps // 2))
-    closest = world * nrays * max(3, args.steps // 2) / (ms_c * 1e-3) / 1e6
+    ms_c = timed(step_closest, csteps)
+    closest = world * nrays * csteps / (ms_c * 1e-3) / 1e6
 
-    # end to end through the host-buffer C-ABI call: pinned host rays in, occlusion bytes out
-    rays_host, occ_host = h_rays.numpy(), h_occ.numpy()
+    # end to end through the reference-facing host call: calculate_occlusion for the batch's shading points.  Pinned host points in,
+    # occluded-ray counts out; the rays are generated and traced on the device inside the call.
+    par = accel.AoPoints(NTHETA, NPHI, seed, 1.0e-6)
+    pts_host, cnt_host = h_pts.numpy(), h_cnt.numpy()
 
     def e2e_step():
+        accel._check(a.lib.ri_b200_occlusion_points_f32(a.data, accel.C.byref(par), accel._ptr(pts_host), npoints, accel._ptr(cnt_host)))
+
+    esteps = max(3, args.steps // 2)
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = wall(e2e_step, esteps)
+    e2e_value = world * nrays * esteps / (e2e_ms * 1e-3) / 1e6
+
+    # the per-ray host path (rays up, occlusion bytes down), as in round 1
+    rays_host, occ_host = h_rays.numpy(), h_occ.numpy()
+
+    def e2e_rays_step():
         accel._check(a.lib.ri_b200_occluded_batch_f32(a.data, accel._ptr(rays_host), nrays, accel._ptr(occ_host)))
 
     for _ in range(2):
-        e2e_step()
-    barrier()
-    t1 = time.perf_counter()
-    esteps = max(3, args.steps // 2)
-    for _ in range(esteps):
-        e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t1) * 1e3
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * nrays * esteps / (e2e_ms * 1e-3) / 1e6
+        e2e_rays_step()
+    e2e_rays_ms = wall(e2e_rays_step, esteps)
+    e2e_rays_value = world * nrays * esteps / (e2e_rays_ms * 1e-3) / 1e6
     assert np.array_equal(occ_host, d_occ.cpu().numpy()), "host-buffer path and device path disagree"
+    assert np.array_equal(cnt_host.astype(np.int64), occ_host.reshape(npoints, NTHETA * NPHI).sum(axis=1, dtype=np.int64)), \
+        "point entry's counts and the per-ray occlusion bytes disagree"
+
+    frames = None
+    if not args.no_frames:
+        a_keep = a                      # the C3 accelerator stays alive for the cpu_baseline parity sample below
+        frames = frame_leg(args, rank, world, local_rank, torch, dist)
+        a = a_keep
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -349,6 +498,18 @@ def main():
                 traffic = json.load(f).get("occluded_f32_c3_bytes_per_launch")
         per_gpu_rays_s = nrays * args.steps / (ms * 1e-3)
         achieved = per_gpu_rays_s * b_ray / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "bytes_per_ray": b_ray, "inner_visits_per_ray": I, "tri_tests_per_ray": T,
+                "note": "contract roofline: ALGORITHMIC bytes of the reference traversal (SURVEY 8d) over the measured HBM copy bandwidth; the "
+                        "records are L2-resident, so the physical limiter is NOT HBM -- see `limiter` (ncu, one launch of this kernel)",
+                "closest_hit": {"bytes_per_ray": b_ray_c, "inner_visits_per_ray": Ic, "tri_tests_per_ray": Tc,
+                                "achieved": nrays * csteps / (ms_c * 1e-3) * b_ray_c / 1e9,
+                                "frac": nrays * csteps / (ms_c * 1e-3) * b_ray_c / 1e9 / peak}}
+        km = kernel_metrics()
+        if km and traffic:
+            roof["dram_frac"] = traffic / (ms / args.steps * 1e-3) / 1e9 / peak
+        if km:
+            roof["limiter"] = km
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -356,16 +517,17 @@ def main():
             "config": {"workload": WORKLOAD, "kernel": "occlusion (any-hit) traversal, reference-identical binary BVH, leaf<=16",
                        "rays_per_gpu_per_step": nrays, "ntris": NTRIS, "inner_nodes": int(info.ninner), "depth": int(info.max_depth),
                        "l2": "ray batch (512 MiB) exceeds L2 every step; scene records (54 MB) are L2-resident by nature of the workload",
-                       "closest_hit_mrays_s": closest, "occluded_fraction": float(occ_host.mean())},
+                       "closest_hit_mrays_s": closest, "occluded_fraction": float(occ_host.mean()), "frames": frames},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": world * nrays * 32, "d2h_bytes_per_step": world * nrays,
-                    "ms_per_step": e2e_ms / esteps, "api": "ri_b200_occluded_batch_f32 (pinned host buffers)"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": world * npoints * 48, "d2h_bytes_per_step": world * npoints * 4,
+                    "ms_per_step": e2e_ms / esteps,
+                    "api": "ri_b200_occlusion_points_f32 (calculate_occlusion for 262144 shading points: pinned host points in, rays generated + "
+                           "traced on the device, occluded-ray counts out)",
+                    "ray_batch": {"value": e2e_rays_value, "unit": "Mrays/s", "h2d_bytes_per_step": world * nrays * 32,
+                                  "d2h_bytes_per_step": world * nrays, "ms_per_step": e2e_rays_ms / esteps,
+                                  "api": "ri_b200_occluded_batch_f32 (pinned host ray records in, occlusion bytes out)"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "bytes_per_ray": b_ray, "inner_visits_per_ray": I, "tri_tests_per_ray": T,
-                         "closest_hit": {"bytes_per_ray": b_ray_c, "inner_visits_per_ray": Ic, "tri_tests_per_ray": Tc,
-                                         "achieved": nrays * max(3, args.steps // 2) / (ms_c * 1e-3) * b_ray_c / 1e9,
-                                         "frac": nrays * max(3, args.steps // 2) / (ms_c * 1e-3) * b_ray_c / 1e9 / peak}},
+            "roofline": roof,
         }
         if world == 1 and not args.no_cpu_baseline:
             n_sample = min(nrays, 150_000 * (os.cpu_count() or 1))

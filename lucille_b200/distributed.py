@@ -19,13 +19,20 @@ from . import accel as _accel
 
 
 def shard_counts(frame: "_accel.Frame", world: int):
-    """Pixels per rank for ``world`` ranks (host logic; every rank computes the same table)."""
-    out = []
-    for r in range(world):
-        f = copy.copy(frame)
-        f.rank, f.world = r, world
-        out.append(len(_accel.frame_pixels(f)))
-    return out
+    """Pixels per rank for ``world`` ranks (host logic; every rank computes the same table; cached per frame geometry)."""
+    key = (frame.width, frame.height, frame.bucket_size, world)
+    if key not in _COUNTS_CACHE:
+        out = []
+        for r in range(world):
+            f = copy.copy(frame)
+            f.rank, f.world = r, world
+            out.append(len(_accel.frame_pixels(f)))
+        _COUNTS_CACHE.clear()
+        _COUNTS_CACHE[key] = out
+    return list(_COUNTS_CACHE[key])
+
+
+_COUNTS_CACHE = {}
 
 
 def scatter_tiles(width: int, height: int, pixel_lists, slabs) -> np.ndarray:
@@ -56,12 +63,33 @@ def gather_frame(local_slab, frame: "_accel.Frame", rank: int, world: int, group
         dist.gather(send, bufs, dst=0, group=group)
     if rank != 0:
         return None
+    if bufs[0].is_cuda:
+        # assemble on rank 0's GPU (one indexed store per slab, plumbing), then ONE device-to-host copy of the framebuffer
+        key = (frame.width, frame.height, frame.bucket_size, world)
+        idx = _SCATTER_CACHE.get(key)
+        if idx is None:
+            idx = []
+            for r in range(world):
+                f = copy.copy(frame)
+                f.rank, f.world = r, world
+                pix = _accel.frame_pixels(f).astype(np.int64)
+                lin = (frame.height - 1 - (pix >> 16)) * frame.width + (pix & 0xFFFF)          # row H-1-y, render.c:962-964
+                idx.append(torch.from_numpy(lin).to(bufs[0].device))
+            _SCATTER_CACHE.clear()
+            _SCATTER_CACHE[key] = idx
+        fbuf = torch.zeros((frame.height * frame.width, 3), dtype=torch.float32, device=bufs[0].device)
+        for r in range(world):
+            fbuf[idx[r]] = bufs[r][: counts[r]]
+        return fbuf.reshape(frame.height, frame.width, 3).cpu().numpy()
     lists = []
     for r in range(world):
         f = copy.copy(frame)
         f.rank, f.world = r, world
         lists.append(_accel.frame_pixels(f))
     return scatter_tiles(frame.width, frame.height, lists, [b.cpu().numpy() for b in bufs])
+
+
+_SCATTER_CACHE = {}
 
 
 def bucket_bases(all_hits, world: int):
