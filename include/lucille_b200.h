@@ -160,7 +160,15 @@ int ri_b200_state_ext_batch_f64(ri_b200_accel_t *accel, const double *rays, cons
  * three channels.  NULL rgba removes the texture. */
 int ri_b200_set_texture(ri_b200_accel_t *accel, const float *rgba, int width, int height, const uint8_t *tri_textured);
 
-/* DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the accelerator's own stream) */
+/* DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the accelerator's own stream).  These entry
+ * points take no lock and may be called from several host threads / streams; each launch takes its work counter from a ring of
+ * 1024, so at most 1024 launches of one accelerator may be IN FLIGHT at a time (a counter is re-zeroed when its slot comes round).
+ *
+ * Ray set-up contract (all query entry points): sign[k] = dir[k] < 0 and inv[k] = |dir[k]| > 1e-14 ? 1 / dir[k] : +-REAL_MAX for ALL
+ * three axes -- the rule bvh.c:473-497 intends.  The reference itself leaves invdir[1] UNSET when |dir[1]| <= 1e-14 (it assigns
+ * invdir[2] a second time, bvh.c:483-487: stale stack contents decide), so for rays whose y component is exactly 0 (or denormal-small)
+ * the reference's answer is undefined and cannot be compared; x- and z-parallel rays are well defined there and equal here
+ * (tests/test_gpu_parity.py::test_axis_parallel_rays). */
 int ri_b200_intersect_dev_f32(ri_b200_accel_t *accel, const float  *d_rays, uint64_t n, ri_b200_hit_f32 *d_out, void *stream);
 int ri_b200_occluded_dev_f32 (ri_b200_accel_t *accel, const float  *d_rays, uint64_t n, uint8_t *d_out, void *stream);
 int ri_b200_intersect_dev_f64(ri_b200_accel_t *accel, const double *d_rays, uint64_t n, ri_b200_hit_f64 *d_out, void *stream);

@@ -75,6 +75,7 @@ struct ri_b200_accel {
     uint32_t  mt_states_cap = 0, mt_states_seed = 0;
     ri_b200_hit_exchange_fn hit_exchange = nullptr;      // rng_mode 0 over several ranks (frame.cuh)
     void     *hit_exchange_user = nullptr;
+    bool streamed_faulted = false;        // host_batch: the streamed upload timed out once -> launch-per-piece from then on
     unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
     std::atomic<unsigned> work_slot{0};   // the _dev entry points may be called from several host threads / streams
     // single-ray path
@@ -108,6 +109,7 @@ template <> SceneView<double> make_view<double>(const ri_b200_accel *a)
 // ray-batch kernels
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlock = 256;
+constexpr unsigned kWorkRing = 1024;     // work counters of the persistent kernels: one per launch, reused round-robin
 
 template <typename Real> struct RayIO;
 template <> struct RayIO<float> {
@@ -328,7 +330,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             uint64_t want = ((uint64_t)m + chunk - 1) / chunk;             // one chunk per warp at least
             want = (want + (kBlock / 32) - 1) / (kBlock / 32);
             const unsigned blocks = (unsigned)(want < cap ? want : cap);
-            unsigned int *ctr = a->d_work + (a->work_slot.fetch_add(1) & 63u);
+            unsigned int *ctr = a->d_work + (a->work_slot.fetch_add(1) & (kWorkRing - 1u));      // documented limit: kWorkRing launches in flight (lucille_b200.h)
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             if (pooled_closest)
                 launch_closest_pool<Real>(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_hits + done, ctr, refill_at, st);
@@ -460,7 +462,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
             if (upload(&a->d_slot_of_prim, a->flat.slot_of_prim, a->device_bytes)) return -1;
         }
         CUDA_OK(cudaMalloc((void **)&a->d_counters, 8 * sizeof(unsigned long long)));
-        CUDA_OK(cudaMalloc((void **)&a->d_work, 66 * sizeof(unsigned int)));      // 64 work counters, then the upload cursor and fault flag of the streamed host-buffer path
+        CUDA_OK(cudaMalloc((void **)&a->d_work, (kWorkRing + 2) * sizeof(unsigned int)));      // work counters, then the upload cursor and fault flag of the streamed host-buffer path
         CUDA_OK(cudaMallocHost(&a->h_pin, 4096));
         CUDA_OK(cudaMalloc(&a->d_one, 4096));
         return 0;
@@ -668,7 +670,7 @@ static int host_occluded_streamed(ri_b200_accel *a, const Real *rays, uint64_t n
         if (cudaMalloc(&a->d_whole_out, n) != cudaSuccess) { cudaGetLastError(); a->d_whole_out = nullptr; return 1; }
         a->whole_out_bytes = n;
     }
-    unsigned int *d_ready = a->d_work + 64, *d_fault = a->d_work + 65;
+    unsigned int *d_ready = a->d_work + kWorkRing, *d_fault = a->d_work + kWorkRing + 1;
     uint32_t *cursor = (uint32_t *)a->h_pin;                       // pinned: one value per piece, <= 1024 pieces
     cudaStream_t ks = a->stream, cs = a->copy_stream[0];
     // piece size: measured on C3 (16 Mi rays, kernel alone 17.1 ms): 2 Mi 18.6 ms, 1 Mi 18.2, 512 Ki 18.0, 256 Ki 17.9, 128 Ki 17.95
@@ -712,9 +714,13 @@ static int host_batch(ri_b200_accel *a, const Real *rays, uint64_t n, void *out)
     {
         static const bool streamed = !(getenv("B200_STREAMED") && atoi(getenv("B200_STREAMED")) == 0) &&
                                      !(getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0);
-        if (ANYHIT && streamed && n < (1ull << 31)) {
+        if (ANYHIT && streamed && !a->streamed_faulted && n < (1ull << 31)) {
             const int rc = host_occluded_streamed<Real>(a, rays, n, (uint8_t *)out);
             if (rc <= 0) return rc;
+            // the upload could not run beside the kernel (a profiler or CUDA_LAUNCH_BLOCKING serialises the two streams): LATCH the
+            // launch-per-piece path for this accelerator, so that only this one call pays the spin cap (~0.1 s), and say so once
+            a->streamed_faulted = true;
+            fprintf(stderr, "[b200] streamed host-buffer upload cannot overlap the kernel here; using one launch per piece from now on\n");
         }
     }
     const uint64_t ray_bytes = RayIO<Real>::kRayStride * sizeof(Real);

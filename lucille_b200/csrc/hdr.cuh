@@ -5,8 +5,8 @@
 //   RGBE_WritePixels_RLE / RGBE_WriteBytes_RLE  rgbe.c:296-340, 244-294   per scanline: 2 2 hi lo, then the four channel planes
 //                                               run-length coded one after the other; flat pixels for widths < 8 or > 0x7fff
 //   RGBE_WriteHeader  rgbe.c:117-139
-// hdr_rgbe_kernel: one lane per pixel.  hdr_rle_kernel: one lane per (scanline, channel) row runs the reference's sequential coder
-// on its row (rows are independent; 4 x height lanes).  hdr_offsets_kernel: one block scans the row lengths.  hdr_pack_kernel:
+// hdr_rgbe_kernel: one lane per pixel.  hdr_rle_kernel: one WARP per (scanline, channel) row, a parallel run detector (three warp
+// scans per 32 bytes) that emits what the reference's sequential coder emits.  hdr_offsets_kernel: one block scans the row lengths.  hdr_pack_kernel:
 // one CTA per row copies it to its place.  Byte-identical to the file the reference writes (tests/test_gpu_parity.py).
 #pragma once
 
@@ -52,44 +52,82 @@ __global__ void hdr_rgbe_kernel(const float *__restrict__ rgb, int width, int he
     }
 }
 
-// rgbe.c:244-294, one row per lane; out has row_cap bytes per row
+// The run-length code of one channel row (what RGBE_WriteBytes_RLE, rgbe.c:244-294, produces) as a PARALLEL run detector: one warp
+// per row, 32 bytes per step, three warp scans per step and no sequential coder.  The reference's output is a function of the row's
+// PIECES -- maximal runs of equal bytes cut every 127 bytes from the run's start -- which are LONG (>= 4 bytes) or short:
+//   * a long piece of l bytes becomes [128 + l, value];
+//   * a maximal stretch of short pieces between long pieces (or the row's ends) becomes literal packets [count <= 128, bytes...],
+//     except that a stretch made of exactly ONE piece of 2 or 3 bytes becomes [128 + l, value] (rgbe.c:268-273).
+// Every byte decides what it emits from left context carried by scans (start of its run, end of the last long piece, bytes
+// emitted so far) and at most six bytes of lookahead: a long piece is written by its LAST byte (which knows l), a literal packet's
+// count by the packet's last byte, at the offset it derives from its own.
+__device__ __forceinline__ bool hdr_piece_is_long(const unsigned char *d, int n, int ps)      // the piece starting at ps has >= 4 bytes
+{ return ps + 3 < n && d[ps + 1] == d[ps] && d[ps + 2] == d[ps] && d[ps + 3] == d[ps]; }
+
 __global__ void hdr_rle_kernel(const unsigned char *__restrict__ planes, int width, int nrows, unsigned char *__restrict__ tmp, uint32_t row_cap,
                                uint32_t *__restrict__ row_len)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrows) return;
-    const unsigned char *data = planes + (size_t)r * width;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
+    if (r >= nrows) return;                                                      // whole warps leave together
+    const unsigned char *d = planes + (size_t)r * width;
     unsigned char *out = tmp + (size_t)r * row_cap;
-    const int numbytes = width, MINRUNLENGTH = 4;
-    uint32_t n = 0;
-    int cur = 0;
-    while (cur < numbytes) {
-        int beg_run = cur, run_count = 0, old_run_count = 0;
-        while ((run_count < MINRUNLENGTH) && (beg_run < numbytes)) {
-            beg_run += run_count;
-            old_run_count = run_count;
-            run_count = 1;
-            while ((beg_run + run_count < numbytes) && (run_count < 127) && (data[beg_run] == data[beg_run + run_count])) run_count++;
+    const int n = width;
+    int carry_s = 0, carry_a = 0;                                                // run start / end of the last long piece, so far
+    uint32_t carry_off = 0;                                                      // bytes emitted so far
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool in = i < n;
+        const unsigned char v = in ? d[i] : 0;
+        // (1) start of my maximal run: inclusive max-scan of head positions
+        const bool head = in && (i == 0 || d[i - 1] != v);
+        int s = head ? i : carry_s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, s, o); if (lane >= o && t > s) s = t; }
+        const int k = (i - s) % 127, ps = i - k;                                 // my place in my piece, my piece's start
+        const bool last_of_piece = in && (k == 126 || i + 1 == n || d[i + 1] != v);
+        const bool lng = in && hdr_piece_is_long(d, n, ps);
+        // (2) end of the last long piece before me: exclusive max-scan of (j + 1) over last bytes j of long pieces
+        int a_inc = (lng && last_of_piece) ? i + 1 : carry_a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, a_inc, o); if (lane >= o && t > a_inc) a_inc = t; }
+        int a = __shfl_up_sync(FULL, a_inc, 1);
+        if (lane == 0) a = carry_a;
+        // (3) what I emit
+        uint32_t c = 0;
+        bool single = false;
+        int la = 0;
+        const int rr = i - a;                                                    // my place in the stretch of short pieces
+        if (in && !lng) {
+            la = 1;                                                              // length of the (short) piece that opens the stretch
+            while (la < 3 && a + la < n && d[a + la] == d[a]) ++la;
+            single = la >= 2 && (a + la == n || hdr_piece_is_long(d, n, a + la));
+            c = single ? (i == a ? 2u : 0u) : (1u + ((rr & 127) == 0 ? 1u : 0u));
+        } else if (lng && last_of_piece) {
+            c = 2u;
         }
-        if ((old_run_count > 1) && (old_run_count == beg_run - cur)) {
-            out[n++] = (unsigned char)(128 + old_run_count);
-            out[n++] = data[cur];
-            cur = beg_run;
+        uint32_t e = c;                                                          // inclusive prefix sum of c
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, e, o); if (lane >= o) e += t; }
+        const uint32_t off = carry_off + e - c;
+        if (lng && last_of_piece) {
+            out[off] = (unsigned char)(128 + k + 1); out[off + 1] = v;
+        } else if (in && !lng) {
+            if (single) {
+                if (i == a) { out[off] = (unsigned char)(128 + la); out[off + 1] = v; }
+            } else {
+                const int kk = rr & 127;
+                const uint32_t pos = off + (kk == 0 ? 1u : 0u);                  // my data byte
+                out[pos] = v;
+                const bool stretch_ends = i + 1 == n || (last_of_piece && hdr_piece_is_long(d, n, i + 1));
+                if (kk == 127 || stretch_ends) out[pos - (uint32_t)kk - 1u] = (unsigned char)(kk + 1);      // the packet's count byte
+            }
         }
-        while (cur < beg_run) {
-            int nonrun_count = beg_run - cur;
-            if (nonrun_count > 128) nonrun_count = 128;
-            out[n++] = (unsigned char)nonrun_count;
-            for (int k = 0; k < nonrun_count; ++k) out[n++] = data[cur + k];
-            cur += nonrun_count;
-        }
-        if (run_count >= MINRUNLENGTH) {
-            out[n++] = (unsigned char)(128 + run_count);
-            out[n++] = data[beg_run];
-            cur += run_count;
-        }
+        carry_s = __shfl_sync(FULL, s, 31);
+        carry_a = __shfl_sync(FULL, a_inc, 31);
+        carry_off += __shfl_sync(FULL, e, 31);
     }
-    row_len[r] = n;
+    if (lane == 0) row_len[r] = carry_off;
 }
 
 // row_off[r] = offset of row r in the body (each scanline = 4 header bytes + its four rows); total body size in *body_bytes
@@ -165,7 +203,7 @@ extern "C" int64_t ri_b200_hdr_encode(const float *rgb, int width, int height, u
             CUDA_OK(cudaMalloc((void **)&d_tmp, (size_t)nrows * row_cap));
             CUDA_OK(cudaMalloc((void **)&d_len, (size_t)nrows * sizeof(uint32_t)));
             CUDA_OK(cudaMalloc((void **)&d_off, ((size_t)nrows + 1) * sizeof(unsigned long long)));
-            hdr_rle_kernel<<<(nrows + 63) / 64, 64>>>(d_planes, width, nrows, d_tmp, row_cap, d_len);
+            hdr_rle_kernel<<<(nrows + 3) / 4, 128>>>(d_planes, width, nrows, d_tmp, row_cap, d_len);      // one warp per (scanline, channel) row
             LAUNCHED();
             hdr_offsets_kernel<<<1, kScanBlock>>>(d_len, nrows, d_off, d_off + nrows);
             LAUNCHED();

@@ -22,16 +22,27 @@ struct AoPointsDev { int ntheta, nphi; uint64_t seed; double eps; };
 __global__ void __launch_bounds__(kBlock)
 ao_points_gen_kernel(const AoPointsDev G, const double *__restrict__ points, const uint64_t point0, const uint64_t nrays, float *__restrict__ rays_out)
 {
+    // the shading frame of a point is shared by its N rays: the first thread of the block that touches a point computes
+    // ri_ortho_basis once and parks it in shared memory (a block of 256 rays covers at most 256 points)
+    __shared__ double s_b0[kBlock][3], s_b1[kBlock][3];
     const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (gid >= nrays) return;
     const uint32_t N = (uint32_t)(G.ntheta * G.nphi);
-    const uint64_t p = point0 + gid / N;
-    const uint32_t k = (uint32_t)(gid % N);
-    const uint32_t j = k / (uint32_t)G.ntheta, i = k - j * (uint32_t)G.ntheta;     // outer loop j (phi), inner loop i (theta)
+    const uint64_t pb = point0 + ((uint64_t)blockIdx.x * kBlock) / N;             // first point of this block
+    const bool active = gid < nrays;
+    const uint64_t p = point0 + (active ? gid : nrays - 1) / N;
+    const uint32_t k = (uint32_t)((active ? gid : nrays - 1) % N);
     const double *pt = points + 6 * p;
     const double n[3] = {pt[3], pt[4], pt[5]};
-    double b0[3], b1[3];
-    ortho_basis(b0, b1, n);                                                       // ambientocclusion.c:65
+    const uint32_t local = (uint32_t)(p - pb);
+    if (active && (k == 0u || threadIdx.x == 0u)) {
+        double b0[3], b1[3];
+        ortho_basis(b0, b1, n);                                                   // ambientocclusion.c:65
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { s_b0[local][q] = b0[q]; s_b1[local][q] = b1[q]; }
+    }
+    __syncthreads();
+    if (!active) return;
+    const uint32_t j = k / (uint32_t)G.ntheta, i = k - j * (uint32_t)G.ntheta;     // outer loop j (phi), inner loop i (theta)
     const uint64_t idx = (p * N + k) * 2;
     const double u0 = (double)(splitmix64_dev(G.seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
     const double u1 = (double)(splitmix64_dev(G.seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
@@ -46,7 +57,7 @@ ao_points_gen_kernel(const AoPointsDev G, const double *__restrict__ points, con
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         org[q] = (float)(pt[q] + n[q] * G.eps);                                   // ambientocclusion.c:73-75
-        dir[q] = (float)(lx * b0[q] + ly * b1[q] + lz * n[q]);                    // ambientocclusion.c:106-111
+        dir[q] = (float)(lx * s_b0[local][q] + ly * s_b1[local][q] + lz * n[q]);  // ambientocclusion.c:106-111
     }
     o[0] = make_float4(org[0], org[1], org[2], 0.0f);
     o[1] = make_float4(dir[0], dir[1], dir[2], 1.0e38f);

@@ -68,6 +68,31 @@ def test_occlusion_matches_closest_hit_flag(soup20k):
     assert np.array_equal(a.occluded(rays8) == 1, a.intersect(rays8)["prim"] != accel.MISS_PRIM)
 
 
+def test_axis_parallel_rays(soup20k):
+    """Direction components that are EXACTLY zero: the safe-reciprocal rule |d| > 1e-14 ? 1/d : +-REAL_MAX on every axis
+    (bvh.c:473-497 as intended; the reference leaves invdir[1] unset for dir.y == 0, bvh.c:483-487, so y-parallel rays can only be
+    pinned to the restatement).  Device == oracle bit for bit, both precisions, closest hit and occlusion, -0.0 included."""
+    tris, a, orc = soup20k
+    rng = np.random.default_rng(17)
+    n = 6000
+    r = _mixed_rays(n, 17)
+    zero = rng.integers(1, 7, n)                                   # which components are zeroed (bit mask 1..6: never all three)
+    for k in range(3):
+        r[(zero >> k) & 1 == 1, 4 + k] = 0.0
+    r[::7, 4:7] *= np.float32(-1.0)                               # some -0.0
+    r[1::50, 0:3] = rng.uniform(0.2, 0.8, (len(r[1::50]), 3))     # origins inside the scene
+    h32, o32 = a.intersect(r), orc.intersect_f32(r)
+    for f in ("t", "u", "v", "prim"):
+        assert np.array_equal(h32[f], o32[f]), f
+    assert np.array_equal(a.occluded(r), orc.occluded_f32(r))
+    r6 = scenes.rays_f32_to_f64(r)
+    h64, o64 = a.intersect(r6), orc.intersect_f64(r6)
+    for f in ("t", "u", "v", "prim", "hit"):
+        assert np.array_equal(h64[f], o64[f]), f
+    assert np.array_equal(a.occluded(r6), orc.occluded_f64(r6))
+    assert (h32["prim"] != accel.MISS_PRIM).sum() > 50
+
+
 def test_traversal_counters_equal_reference_statistics(soup20k):
     """ninner / nleaf / ntris per batch are the I and T of the roofline formula: they must be the
     reference's own RI_BVH_TRACE_STATISTICS numbers, here via the oracle (pinned to them on CPU)."""
