@@ -22,6 +22,7 @@
 #include "scene.h"
 #include "geom.h"
 #include "accel.h"
+#include "bvh.h"
 #include "ray.h"
 #include "intersection_state.h"
 #include "list.h"
@@ -30,13 +31,7 @@
 
 #include "lucille_b200.h"
 
-typedef struct {
-    ri_b200_accel_t *dev;
-    uint64_t         ntris;
-    uint32_t        *orig;          /* post-build position -> flattened input triangle (ri_b200_triorder) */
-    ri_geom_t      **tri_geom;      /* flattened input triangle -> owning geom   (ri_triangle_t.geom,  bvh.c:1812) */
-    uint32_t        *tri_index;     /* flattened input triangle -> 3 * i         (ri_triangle_t.index, bvh.c:1813) */
-} b200_binding_t;
+#include "ri_b200_binding.h"
 
 /* accel_build_func: `data` is the ri_scene_t (scene.c:96,164).  Flattens the geoms exactly like create_triangle_list()
  * (bvh.c:1736-1826): geoms in list order, triangles in index order, positions already in world space. */
@@ -104,7 +99,21 @@ int ri_b200_accel_intersect(void *accel, ri_ray_t *ray, ri_intersection_state_t 
     b200_binding_t *b = (b200_binding_t *)accel;
     ri_b200_hit_f64 hit;
     int rc;
-    (void)user;
+    if (user) {
+        /* `user` is an ri_bvh_diag_t* from the testbed (simplerender.cpp:202).  ri_bvh_intersect zeroes it (bvh.c:451-456) and, in a
+         * build with RI_BVH_ENABLE_DIAGNOSTICS (bvh.h:38, off by default), counts inner-node visits, leaf visits and leaf calls
+         * (bvh.c:826-828, 1126-1147).  The accelerator has those counters in the reference's own traversal order, so it fills them. */
+        ri_bvh_diag_t *diag = (ri_bvh_diag_t *)user;
+        ri_b200_counters_t cnt;
+        double r6[6];
+        memset(diag, 0, sizeof(*diag));
+        for (rc = 0; rc < 3; rc++) { r6[rc] = ray->org[rc]; r6[3 + rc] = ray->dir[rc]; }
+        if (ri_b200_count_batch(b->dev, r6, 1, RI_B200_PREC_F64, 0, &cnt) == 0) {
+            diag->ninner_node_traversals = (uint32_t)cnt.ninner;
+            diag->nleaf_node_traversals  = (uint32_t)cnt.nleaf;
+            diag->ntriangle_isects       = (uint32_t)cnt.nleaf;      /* incremented once per bvh_intersect_leaf_node call, bvh.c:826-828 */
+        }
+    }
     rc = ri_b200_intersect1(b->dev, ray->org, ray->dir, &hit, NULL);
     if (rc < 0) { ri_log(LOG_FATAL, "(B200  ) %s", ri_b200_last_error()); abort(); }
     if (rc == 0) return 0;

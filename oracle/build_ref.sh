@@ -68,12 +68,14 @@ gcc -O2 -g -std=gnu99 -fPIC -w -D__64bit__ -D__x86__ -DLINUX -DWITH_PTHREAD -DWI
 gcc -O2 -g -std=gnu99 -w "$DRV/oracle_rib_main.c" -L"$OUT" -Wl,-rpath,'$ORIGIN' -lluciref -lm -ldl -lpthread -o "$OUT/oracle_rib"
 
 # drop-in proof: the same front end + the UNMODIFIED reference renderer, with ri_accel_bind() interposed so that accel
-# method 2 selects the GPU accelerator (integration/ri_b200_binding.c -> lucille_b200/libb200accel.so).  Needs the product
-# library to exist; skipped otherwise.
+# method 2 selects the GPU accelerator (integration/ri_b200_binding.c -> lucille_b200/libb200accel.so) and with the batched frame
+# hook (integration/ri_b200_frame_hook.c) spliced in at ri_render_frame / ri_thread_create: `--accel b200` renders the frame in ONE
+# ri_b200_render_ao call, `RI_B200_FRAME=0 ... --accel b200` through the per-ray vtable slot.  Needs the product library to exist.
 if [ -f "$HERE/../lucille_b200/libb200accel.so" ]; then
     gcc -O2 -g -std=gnu99 -w -D__64bit__ -D__x86__ -DLINUX -DWITH_PTHREAD -DWITH_SSE -DLREF_WITH_B200 $INC -I"$HERE/../include" \
         "$DRV/oracle_rib_main.c" "$DRV/ref_shim.c" "$DRV/rib_reader.c" "$HERE/../integration/ri_b200_binding.c" \
-        -Wl,--wrap=ri_accel_bind -Wl,--whole-archive "$OUT/libluciref_core.a" -Wl,--no-whole-archive \
+        "$HERE/../integration/ri_b200_frame_hook.c" -I"$HERE/../integration" \
+        -Wl,--wrap=ri_accel_bind -Wl,--wrap=ri_render_frame -Wl,--wrap=ri_thread_create -Wl,--whole-archive "$OUT/libluciref_core.a" -Wl,--no-whole-archive \
         -L"$HERE/../lucille_b200" -lb200accel -Wl,-rpath,'$ORIGIN/../../lucille_b200' -lm -ldl -lpthread -o "$OUT/lsh_b200"
 fi
 

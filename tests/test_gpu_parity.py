@@ -268,26 +268,73 @@ def test_full_size_config2_properties():
         assert np.array_equal(hits[f][rows], want[f]), f
 
 
+def _run_lsh(lsh, rib, out, accel_name, args, env_extra=None, timeout=900):
+    import subprocess
+    import time
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    t0 = time.perf_counter()
+    r = subprocess.run([lsh, rib, "--accel", accel_name, "--out", out] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=timeout, env=env, text=True)
+    return time.perf_counter() - t0, r.stdout
+
+
 def test_drop_in_through_the_reference_renderer(tmp_path):
-    """The real boundary: the UNMODIFIED reference renderer (Ri layer, pixel loop, AO transport, MT19937) with accel
+    """The real boundary, per-ray slot: the UNMODIFIED reference renderer (Ri layer, pixel loop, AO transport, MT19937) with accel
     method RI_ACCEL_B200 bound by integration/ri_b200_binding.c -- every ri_raytrace() is answered by the GPU through
-    ri_b200_intersect1() -- produces the same float framebuffer, bit for bit, as the reference's own CPU BVH."""
+    ri_b200_intersect1() (RI_B200_FRAME=0 keeps the batched hook out) -- produces the same float framebuffer, bit for bit, as the
+    reference's own CPU BVH."""
     _need_gpu()
     lsh_b200 = os.path.join(ol.REF_DIR, "lsh_b200")
     rib = os.path.join(ol.REF_DIR, "scenes", "ambient_occlusion.rib")
     if not (os.path.exists(lsh_b200) and os.path.exists(rib)):
         pytest.skip("oracle/_ref/lsh_b200 not built (needs /root/reference at build time)")
-    import subprocess
     args = ["--nthreads", "1", "--width", "64", "--height", "48", "--pixelsamples", "2", "--gather", "16"]
     out_gpu, out_cpu = str(tmp_path / "gpu.bin"), str(tmp_path / "cpu.bin")
-    subprocess.run([lsh_b200, rib, "--accel", "b200", "--out", out_gpu] + args, check=True, stdout=subprocess.DEVNULL,
-                   stderr=subprocess.DEVNULL, timeout=600)
-    subprocess.run([lsh_b200, rib, "--accel", "bvh", "--out", out_cpu] + args, check=True, stdout=subprocess.DEVNULL,
-                   stderr=subprocess.DEVNULL, timeout=600)
+    _, log_gpu = _run_lsh(lsh_b200, rib, out_gpu, "b200", args, {"RI_B200_FRAME": "0"})
+    _run_lsh(lsh_b200, rib, out_cpu, "bvh", args)
+    assert "one batched call" not in log_gpu
     g, _, ng = ol.read_frame(out_gpu)
     c, _, nc = ol.read_frame(out_cpu)
     assert ng == nc and ng > 50000
     assert np.array_equal(g, c) and g.max() > 0.5
+
+
+def test_batched_frame_hook_in_the_reference_renderer(tmp_path, golden_dir):
+    """the BATCHED frame hook compiled into the reference renderer (integration/ri_b200_frame_hook.c spliced in at
+    ri_render_frame / ri_thread_create).  The unmodified front end parses the unmodified ambient_occlusion.rib at its own 640x480,
+    PixelSamples 3 3, 64 gather rays; the frame is ONE ri_b200_render_ao call; the display driver receives the reference's float
+    framebuffer bit for bit (sha256 committed from the compiled reference at one thread), the renderer's own statistics count the
+    same 75 873 408 rays, and a small frame equals the CPU BVH run of the same binary."""
+    _need_gpu()
+    import hashlib
+    lsh_b200 = os.path.join(ol.REF_DIR, "lsh_b200")
+    rib = os.path.join(ol.REF_DIR, "scenes", "ambient_occlusion.rib")
+    if not (os.path.exists(lsh_b200) and os.path.exists(rib)):
+        pytest.skip("oracle/_ref/lsh_b200 not built (needs /root/reference at build time)")
+    dig = np.load(os.path.join(golden_dir, "c1_frame_640x480_digest.npz"))
+    out = str(tmp_path / "full.bin")
+    secs, log = _run_lsh(lsh_b200, rib, out, "b200", ["--nthreads", "1"])
+    assert "one batched call" in log
+    rgb, _, nrays = ol.read_frame(out)
+    assert rgb.shape == (480, 640, 3)
+    assert nrays == int(dig["nrays"]) == 75873408                      # render->stat.nrays, what "M Rays/sec" is printed from
+    assert hashlib.sha256(np.ascontiguousarray(rgb, dtype=np.float32).tobytes()).hexdigest() == str(dig["sha256"])
+    # more than one worker thread requested: the hook still renders the frame once and the image is the one-thread image
+    out8 = str(tmp_path / "full8.bin")
+    _run_lsh(lsh_b200, rib, out8, "b200", ["--nthreads", "8"])
+    rgb8, _, nrays8 = ol.read_frame(out8)
+    assert nrays8 == nrays and np.array_equal(rgb8, rgb)
+    # a small odd-sized frame against the CPU BVH of the same binary
+    args = ["--nthreads", "1", "--width", "97", "--height", "61", "--pixelsamples", "2", "--gather", "16"]
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    _run_lsh(lsh_b200, rib, a, "b200", args)
+    _run_lsh(lsh_b200, rib, b, "bvh", args)
+    fa, _, na = ol.read_frame(a)
+    fb, _, nb = ol.read_frame(b)
+    assert na == nb and np.array_equal(fa, fb)
+    print(f"lsh_b200 --accel b200 (batched hook), 640x480 3x3 x 64 rays: {secs:.2f} s wall for the whole process "
+          f"(reference, one thread: {float(dig['seconds_1thread']):.1f} s for the frame alone)")
 
 
 def _c4_scene(golden_dir):
