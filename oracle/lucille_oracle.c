@@ -1261,6 +1261,102 @@ void orc_point_gather(const orc_tree *T, int kind, int nsamples, uint32_t seed, 
     if (nrays_out) *nrays_out = nrays;
 }
 
+/* ------------------------------------------------------------------ shading-language callers of ri_raytrace
+ *
+ * trace() shadeop (render/shader.c:895-976) up to the call of the hit geometry's shader procedure, for n (P, R) pairs:
+ * ray.org = P + 0.0001 * R component by component, ray.dir = R (not normalised); on a miss dst = ri_texture_ibl_fetch(light->texture,
+ * ray.dir) when the scene's first light is an IBL / sun-sky light (use_env), else zero; on a hit the shader's input block is the hit
+ * state: Cs = state.color, P, N = Ns, Ng, dPdu = tangent, dPdv = binormal, I = normalize(state.P - P), s = u, t = v (shader.c:951-968).
+ * rays_out [n][6] receives the rays that were traced (the offset origins). */
+void orc_shade_trace(const orc_tree *T, const double *pr, uint64_t n, const float *env, int ew, int eh, int use_env,
+                     double *rays_out, orc_hit_f64 *hits, orc_state_f64 *states, orc_state_ext_f64 *exts, double *eye3, double *miss_rgb3)
+{
+    uint64_t i;
+    int k;
+    for (i = 0; i < n; i++) {
+        const double *P = pr + 6 * i, *R = P + 3;
+        double *r = rays_out + 6 * i;
+        for (k = 0; k < 3; k++) { r[3 + k] = R[k]; r[k] = P[k]; r[k] += 0.0001 * r[3 + k]; }
+    }
+    orc_intersect_f64(T, rays_out, n, hits, NULL);
+    orc_state_build_f64(T, rays_out, hits, n, states);
+    orc_state_ext_build_f64(T, rays_out, hits, n, exts);
+    for (i = 0; i < n; i++) {
+        const double *P = pr + 6 * i;
+        double *e = eye3 + 3 * i, *m = miss_rgb3 + 3 * i;
+        e[0] = e[1] = e[2] = 0.0; m[0] = m[1] = m[2] = 0.0;
+        if (hits[i].hit) {
+            for (k = 0; k < 3; k++) e[k] = states[i].P[k] - P[k];
+            normalize_f64(e);
+        } else if (use_env && env) {
+            double texel[4];
+            ibl_fetch(env, ew, eh, rays_out + 6 * i + 3, texel);
+            for (k = 0; k < 3; k++) m[k] = texel[k];
+        }
+    }
+}
+
+/* next_lightsource() + init_lightsource() (render/shader.c:1116-1186, 1236-1310): the light samples an illuminance loop visits at
+ * each of n shading points (P, N).  Per point: m = ntheta * 3 ntheta stratified cosine directions about N from the randomMT stream
+ * (two words per sample, all drawn up front), L = normalize(direction), Cl = ri_texture_ibl_fetch(env, L) * (1 / m); the loop then
+ * returns, in order, every sample with dot(L, N) > 0, acos(dot) < angle and no occluder along normalize(L) from P + 0.0001 * N --
+ * except the LAST sample of the set, which the reference can never return (after the break `sample_index >= nsamples` is true and
+ * the function returns NULL, shader.c:1170-1177).  visible[p][j] = 1 for the samples the loop returns.  Returns m. */
+int orc_light_samples(const orc_tree *T, int nsamples, double angle, uint32_t seed, const double *points, uint64_t n,
+                      const float *env, int ew, int eh, double *L_out, double *Cl_out, uint8_t *visible, uint64_t *nrays_out)
+{
+    view_t_f64 V = {0};
+    mt_t rng;
+    uint64_t p, nrays = 0;
+    int ntheta, nphi, m, i, j, k;
+    if (!T->empty) view64(T, &V);
+    mt_seed(&rng, seed);
+    ntheta = (int)(nsamples / 3.0);                            /* shader.c:1263-1266 */
+    ntheta = (int)sqrt((double)ntheta);
+    if (ntheta < 1) ntheta = 1;
+    nphi = 3 * ntheta;
+    m = ntheta * nphi;
+    for (p = 0; p < n; p++) {
+        const double *P = points + 6 * p, *N = P + 3;
+        double basis[3][3];
+        double *L = L_out + 3 * (size_t)m * p, *Cl = Cl_out + 3 * (size_t)m * p;
+        uint8_t *vis = visible + (size_t)m * p;
+        int count = 0;
+        ortho_basis_f64(basis, N);
+        for (j = 0; j < nphi; j++) {
+            for (i = 0; i < ntheta; i++) {
+                double dirl[3], ldir[3], texel[4] = {0.0, 0.0, 0.0, 0.0};
+                const double theta = sqrt(((double)i + mt_next(&rng)) / (double)ntheta);
+                const double phi = 2.0 * M_PI * ((double)j + mt_next(&rng)) / (double)nphi;
+                dirl[0] = cos(phi) * theta;
+                dirl[1] = sin(phi) * theta;
+                dirl[2] = sqrt(1.0 - theta * theta);
+                for (k = 0; k < 3; k++) ldir[k] = dirl[0] * basis[0][k] + dirl[1] * basis[1][k] + dirl[2] * basis[2][k];
+                normalize_f64(ldir);
+                if (env) ibl_fetch(env, ew, eh, ldir, texel);
+                for (k = 0; k < 3; k++) { L[3 * count + k] = ldir[k]; Cl[3 * count + k] = texel[k] * (double)(1.0f / (double)m); }
+                count++;
+            }
+        }
+        for (j = 0; j < m; j++) {
+            const double *l = L + 3 * j;
+            const double ndotl = l[0] * N[0] + l[1] * N[1] + l[2] * N[2];
+            double org[3], dir[3], t, uu, vv;
+            uint32_t prim;
+            vis[j] = 0;
+            if (ndotl <= 0.0) continue;
+            if (acos(ndotl) >= angle) continue;
+            for (k = 0; k < 3; k++) { org[k] = P[k]; org[k] += N[k] * 0.0001; dir[k] = l[k]; }
+            normalize_f64(dir);
+            nrays++;
+            if (!T->empty && trace_f64(T, &V, org, dir, 0, &t, &uu, &vv, &prim, NULL)) continue;
+            if (j + 1 < m) vis[j] = 1;                         /* the last sample is dropped: shader.c:1170-1177 */
+        }
+    }
+    if (nrays_out) *nrays_out = nrays;
+    return m;
+}
+
 void orc_render_whitted(const orc_tree *T, const orc_frame_t *f, const float *env, int ew, int eh, float *rgb, uint64_t *nrays_out)
 {
     int nb_max = (f->width / f->bucket_size + 1) * (f->height / f->bucket_size + 1);

@@ -152,6 +152,11 @@ typedef struct {
     int32_t bucket_size;
 } orc_path_frame_t;
 void orc_render_pathtrace(const orc_tree *t, const orc_path_frame_t *f, float *rgb, uint64_t *nrays_out);
+/* trace() shadeop up to the shader call (render/shader.c:895-976) and the light samples of next_lightsource() (shader.c:1116-1310) */
+void orc_shade_trace(const orc_tree *T, const double *pr, uint64_t n, const float *env, int ew, int eh, int use_env,
+                     double *rays_out, orc_hit_f64 *hits, orc_state_f64 *states, orc_state_ext_f64 *exts, double *eye3, double *miss_rgb3);
+int orc_light_samples(const orc_tree *T, int nsamples, double angle, uint32_t seed, const double *points, uint64_t n,
+                      const float *env, int ew, int eh, double *L_out, double *Cl_out, uint8_t *visible, uint64_t *nrays_out);
 void orc_det_sincos2pi(double r, double *s, double *c);
 /* ray batch of the point-based AO call (calculate_occlusion's ray set-up, ambientocclusion.c:56-117): [n*ntheta*nphi][8] floats */
 void orc_ao_point_rays_f32(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, float *rays_out);

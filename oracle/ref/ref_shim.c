@@ -484,6 +484,101 @@ void lref_point_gather_ex(void *h, int kind, int nsamples, const double *points,
     render->scene = saved;
 }
 
+/* ---- the two shading-language callers of ri_raytrace: trace() (shader.c:895-976) and next_lightsource()
+ * (shader.c:1116-1186).  trace() ends in the hit geometry's shader procedure; a capturing procedure installed on every geom records
+ * the input block the reference hands it.  Both need the scene's first light (get_light, shader.c:1219-1234): an IBL light carrying
+ * the environment map set with lref_set_envmap. */
+typedef struct { double Cs[3], P[3], N[3], Ng[3], dPdu[3], dPdv[3], I[3], dst[3]; float s, t; int32_t called, ray_depth; } lref_trace_rec_t;
+static lref_trace_rec_t *g_trace_rec = NULL;
+static void capture_shaderproc(ri_output_t *output, ri_status_t *status, ri_parameter_t *param)
+{
+    int k;
+    (void)param;
+    if (g_trace_rec) {
+        for (k = 0; k < 3; k++) {
+            g_trace_rec->Cs[k] = status->input.Cs[k]; g_trace_rec->P[k] = status->input.P[k]; g_trace_rec->N[k] = status->input.N[k];
+            g_trace_rec->Ng[k] = status->input.Ng[k]; g_trace_rec->dPdu[k] = status->input.dPdu[k]; g_trace_rec->dPdv[k] = status->input.dPdv[k];
+            g_trace_rec->I[k] = status->input.I[k];
+        }
+        g_trace_rec->s = status->input.s; g_trace_rec->t = status->input.t;
+        g_trace_rec->called = 1; g_trace_rec->ray_depth = status->ray_depth;
+    }
+    output->Ci[0] = 0.25; output->Ci[1] = 0.5; output->Ci[2] = 0.75; output->Ci[3] = 1.0;
+}
+static ri_shader_t g_capture_shader = { NULL, capture_shaderproc, NULL };
+
+static void ensure_ibl_light(lref_scene_t *s)
+{
+    if (ri_list_first(s->scene->light_list)) return;
+    if (s->scene->envmap_light) {
+        ri_light_t *l = ri_light_new();
+        l->type = LIGHTTYPE_IBL;
+        l->texture = s->scene->envmap_light->texture;
+        ri_list_append(s->scene->light_list, (void *)l);
+    }
+}
+
+void lref_shade_trace(void *h, const double *pr, uint64_t n, lref_trace_rec_t *out)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_render_t *render = ri_render_get();
+    ri_scene_t *saved = render->scene;
+    ri_status_t status;
+    uint64_t i;
+    int g, k;
+    render->scene = s->scene;
+    ensure_ibl_light(s);
+    for (g = 0; g < s->ngeoms; g++) s->geoms[g]->shader = &g_capture_shader;
+    memset(&status, 0, sizeof(status));
+    for (i = 0; i < n; i++) {
+        ri_vector_t P, R, dst;
+        for (k = 0; k < 3; k++) { P[k] = pr[6 * i + k]; R[k] = pr[6 * i + 3 + k]; }
+        P[3] = 1.0; R[3] = 0.0;
+        memset(&out[i], 0, sizeof(out[i]));
+        g_trace_rec = &out[i];
+        trace(&status, dst, P, R);
+        for (k = 0; k < 3; k++) out[i].dst[k] = dst[k];
+    }
+    g_trace_rec = NULL;
+    render->scene = saved;
+}
+
+/* the samples an `illuminance` loop receives from next_lightsource() at each point, in order: L and Cl of every returned sample.
+ * count_out[p] = number returned at point p (at most maxm are stored). */
+void lref_light_samples(void *h, int nsamples, double angle, const double *points, uint64_t n, int maxm,
+                        double *L_out, double *Cl_out, int32_t *count_out)
+{
+    lref_scene_t *s = (lref_scene_t *)h;
+    ri_render_t *render = ri_render_get();
+    ri_scene_t *saved = render->scene;
+    ri_option_t *opt = render->context->option;
+    const unsigned int saved_rays = opt->narealight_rays;
+    ri_status_t status;
+    uint64_t i;
+    int k;
+    render->scene = s->scene;
+    ensure_ibl_light(s);
+    opt->narealight_rays = (unsigned int)nsamples;
+    seedMT((unsigned long)4357);
+    seedMT2((unsigned long)4357, 0);
+    memset(&status, 0, sizeof(status));
+    for (i = 0; i < n; i++) {
+        ri_vector_t P, N;
+        ri_lightsource_t *l;
+        int c = 0;
+        for (k = 0; k < 3; k++) { P[k] = points[6 * i + k]; N[k] = points[6 * i + 3 + k]; }
+        P[3] = 1.0; N[3] = 0.0;
+        while ((l = next_lightsource(&status, P, N, (ri_float_t)angle)) != NULL) {
+            if (c < maxm)
+                for (k = 0; k < 3; k++) { L_out[3 * ((size_t)maxm * i + c) + k] = l->L[k]; Cl_out[3 * ((size_t)maxm * i + c) + k] = l->Cl[k]; }
+            c++;
+        }
+        count_out[i] = c;
+    }
+    opt->narealight_rays = saved_rays;
+    render->scene = saved;
+}
+
 /* The byte stream the reference's socket display driver (display/sockdrv.c) sends for a frame: a listener on 127.0.0.1:DEFAULT_PORT in
  * this process stands in for the viewer, sock_dd_open/write/close are called the way bucket_write does (render.c:919-979: pixels in
  * `pixels` order, (x, y) = display coordinates), everything received is returned.  Returns the number of bytes, -1 on failure. */

@@ -8,6 +8,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 
@@ -29,6 +30,8 @@ COUNTERS_DTYPE = np.dtype([("nrays", "<u8"), ("ninner", "<u8"), ("nleaf", "<u8")
 REFHIT_DTYPE = np.dtype([("hit", "<i4"), ("index", "<u4"), ("geom_id", "<u4"), ("pad", "<u4"),
                          ("t", "<f8"), ("u", "<f8"), ("v", "<f8"),
                          ("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
+TRACE_REC_DTYPE = np.dtype([("Cs", "<f8", 3), ("P", "<f8", 3), ("N", "<f8", 3), ("Ng", "<f8", 3), ("dPdu", "<f8", 3), ("dPdv", "<f8", 3),
+                            ("I", "<f8", 3), ("dst", "<f8", 3), ("s", "<f4"), ("t", "<f4"), ("called", "<i4"), ("ray_depth", "<i4")])
 STATE_EXT_DTYPE = np.dtype([("E", "<f8", 3), ("I", "<f8", 3), ("color", "<f8", 3), ("st", "<f8", 2), ("t", "<f8"), ("inside", "<i4"), ("hit", "<i4")])
 MISS_PRIM = 0xFFFFFFFF
 
@@ -318,6 +321,31 @@ class OracleTree:
                                   _ptr(out), C.byref(nrays))
         return out, nrays.value
 
+    def shade_trace(self, pr6: np.ndarray, env=None, use_env: bool = True):
+        """trace() shadeop up to the shader call (shader.c:895-976) for (P, R) pairs: dict(rays, hits, states, exts, eye, miss_rgb)."""
+        pr = np.ascontiguousarray(pr6, dtype=np.float64).reshape(-1, 6)
+        env = None if env is None else np.ascontiguousarray(env, dtype=np.float32)
+        n = len(pr)
+        rays = np.zeros((n, 6)); hits = np.zeros(n, dtype=HIT64_DTYPE); states = np.zeros(n, dtype=STATE_DTYPE)
+        exts = np.zeros(n, dtype=STATE_EXT_DTYPE); eye = np.zeros((n, 3)); miss = np.zeros((n, 3))
+        self.lib.orc_shade_trace(self.h, _ptr(pr), C.c_uint64(n), None if env is None else _ptr(env), 0 if env is None else env.shape[1],
+                                 0 if env is None else env.shape[0], int(use_env), _ptr(rays), _ptr(hits), _ptr(states), _ptr(exts),
+                                 _ptr(eye), _ptr(miss))
+        return dict(rays=rays, hits=hits, states=states, exts=exts, eye=eye, miss_rgb=miss)
+
+    def light_samples(self, nsamples: int, angle: float, points6: np.ndarray, env, seed: int = 4357):
+        """Light samples of next_lightsource() (shader.c:1116-1310) at points (P, N): (L [n,m,3], Cl [n,m,3], visible [n,m] u8, rays)."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        env = np.ascontiguousarray(env, dtype=np.float32)
+        nt = max(1, int(math.sqrt(int(nsamples / 3.0))))
+        m = nt * 3 * nt
+        L = np.zeros((len(pts), m, 3)); Cl = np.zeros((len(pts), m, 3)); vis = np.zeros((len(pts), m), dtype=np.uint8)
+        nrays = C.c_uint64(0)
+        got = self.lib.orc_light_samples(self.h, nsamples, C.c_double(angle), seed, _ptr(pts), C.c_uint64(len(pts)), _ptr(env),
+                                         env.shape[1], env.shape[0], _ptr(L), _ptr(Cl), _ptr(vis), C.byref(nrays))
+        assert got == m
+        return L, Cl, vis, nrays.value
+
     def point_gather_qmc(self, kind: int, nsamples: int, points6: np.ndarray, instance=None, dim: int = 0, env=None,
                          col=(1.0, 1.0, 1.0), intensity=1.0):
         """The quasi-Monte Carlo branches (Option "use_qmc") of the IBL (1) and dome-light (2) gathers; instance = inray->i per point."""
@@ -417,6 +445,10 @@ class Oracle:
         lib.orc_point_gather_qmc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                              C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_ao_point_rays_f32.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_void_p]
+        lib.orc_shade_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+        lib.orc_light_samples.restype = C.c_int
+        lib.orc_light_samples.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_render_dirtmap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_transport_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.orc_render_whitted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -567,6 +599,24 @@ class ReferenceScene:
             self.lib.lref_point_gather(self.h, kind, nsamples, _ptr(pts), C.c_uint64(len(pts)), _ptr(c), C.c_double(intensity), _ptr(out))
         return out
 
+    def shade_trace(self, pr6: np.ndarray) -> np.ndarray:
+        """The compiled reference's trace() shadeop (shader.c:895-976) per (P, R) pair with a capturing shader procedure on every geom:
+        records of the input block it hands the shader (called = 1) and of dst (the environment colour or zero on a miss)."""
+        pr = np.ascontiguousarray(pr6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(len(pr), dtype=TRACE_REC_DTYPE)
+        with _quiet():
+            self.lib.lref_shade_trace(self.h, _ptr(pr), C.c_uint64(len(pr)), _ptr(out))
+        return out
+
+    def light_samples(self, nsamples: int, angle: float, points6: np.ndarray, maxm: int = 1024):
+        """What an illuminance loop receives from the compiled next_lightsource() (shader.c:1116-1186) at each point (P, N):
+        (L [n,maxm,3], Cl [n,maxm,3], count [n]), generators reseeded to 4357 first; needs set_envmap."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        L = np.zeros((len(pts), maxm, 3)); Cl = np.zeros((len(pts), maxm, 3)); cnt = np.zeros(len(pts), dtype=np.int32)
+        with _quiet():
+            self.lib.lref_light_samples(self.h, nsamples, C.c_double(angle), _ptr(pts), C.c_uint64(len(pts)), maxm, _ptr(L), _ptr(Cl), _ptr(cnt))
+        return L, Cl, cnt
+
     def point_gather_qmc(self, kind: int, nsamples: int, points6: np.ndarray, instance=None, dim: int = 0, col=(1.0, 1.0, 1.0),
                          intensity=1.0) -> np.ndarray:
         """The same reference functions with Option "use_qmc" on (ibl.c:107-151, 266-320); instance[p] -> inray->i, dim -> inray->d."""
@@ -622,6 +672,8 @@ class Reference:
         lib.lref_beam_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.lref_transport_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.lref_shade_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.lref_light_samples.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.lref_point_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_void_p]
         lib.lref_point_gather_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_int,
                                              C.c_void_p, C.c_int, C.c_void_p]

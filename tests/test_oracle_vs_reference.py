@@ -227,6 +227,61 @@ def test_point_gathers_qmc_called_directly(oracle, ref, kind, nsamples, dim):
     assert np.ptp(got[:, 0]) > 0.05
 
 
+def test_trace_shadeop_called_directly(oracle, ref):
+    """SURVEY 8f rank 2, the trace() shadeop (shader.c:895-976): the compiled function called per (P, R) pair, a capturing shader
+    procedure on every geom of a five-geom scene with colours / texture coordinates / two-sided geometry, an IBL light carrying the
+    environment map.  The restatement reproduces, bit for bit, what the reference hands the hit surface's shader (Cs, P, N, Ng, dPdu,
+    dPdv, I, s, t) and what it returns on a miss (the environment colour along the UNnormalised direction)."""
+    sizes = [1500, 900, 1300, 1100, 1200]
+    tris = scenes.triangle_soup(sum(sizes), 21)
+    col, st, geom_flags, has_col, has_st, inside = ol.attribute_case(len(tris), sizes, 4)
+    rs = ref.build(tris, geom_sizes=sizes)
+    rs.set_attributes(col, st, geom_flags)
+    ot = oracle.build(tris)
+    ot.set_attributes(col, has_col, st, has_st, inside)
+    env = ol.test_texture(32, 32, 5)
+    rs.set_envmap(env)
+    rng = np.random.default_rng(4)
+    n = 4000
+    P = rng.uniform(-0.3, 1.3, (n, 3))
+    R = rng.uniform(0.0, 1.0, (n, 3)) - P
+    R *= rng.uniform(0.3, 2.5, (n, 1))                   # trace() does not normalise R
+    pr = np.concatenate([P, R], axis=1)
+    want = rs.shade_trace(pr)
+    got = ot.shade_trace(pr, env)
+    hit = got["hits"]["hit"] == 1
+    assert 0.2 < hit.mean() < 0.9
+    assert np.array_equal(want["called"] == 1, hit)
+    assert np.array_equal(want["dst"][~hit], got["miss_rgb"][~hit]) and np.ptp(got["miss_rgb"][~hit]) > 0.1
+    assert np.all(want["dst"][hit] == [0.25, 0.5, 0.75])         # the capturing shader's Ci
+    for name, field in (("Cs", got["exts"]["color"]), ("P", got["states"]["P"]), ("N", got["states"]["Ns"]), ("Ng", got["states"]["Ng"]),
+                        ("dPdu", got["states"]["tangent"]), ("dPdv", got["states"]["binormal"]), ("I", got["eye"])):
+        assert np.array_equal(want[name][hit], field[hit]), name
+    assert np.array_equal(want["s"][hit], got["hits"]["u"][hit].astype(np.float32))
+    assert np.array_equal(want["t"][hit], got["hits"]["v"][hit].astype(np.float32))
+    assert np.all(want["ray_depth"][hit] == 1)
+
+
+@pytest.mark.parametrize("nsamples,angle", [(48, 1.2), (27, 1.5707963267948966), (5, 0.6)])
+def test_next_lightsource_called_directly(oracle, ref, nsamples, angle):
+    """The illuminance loop's light samples (next_lightsource + init_lightsource, shader.c:1116-1186, 1236-1310): per shading point the
+    compiled reference returns, in order, the environment-map samples inside the cone that no triangle occludes -- never the last
+    sample of the set (shader.c:1170-1177).  The restatement's visible samples are the same list: L and Cl bit for bit."""
+    tris = scenes.triangle_soup(20000, 9)
+    rs, ot = ref.build(tris), oracle.build(tris)
+    env = ol.test_texture(32, 32, 5)
+    rs.set_envmap(env)
+    pts = _shading_points(ot)[:800]
+    Lw, Clw, cw = rs.light_samples(nsamples, angle, pts)
+    L, Cl, vis, nrays = ot.light_samples(nsamples, angle, pts, env)
+    assert np.array_equal(vis.sum(axis=1), cw)
+    assert 0 < vis.sum() < vis.size and nrays > vis.sum()
+    assert not vis[:, -1].any()
+    for p in range(len(pts)):
+        k = int(cw[p])
+        assert np.array_equal(L[p][vis[p] == 1], Lw[p, :k]) and np.array_equal(Cl[p][vis[p] == 1], Clw[p, :k]), p
+
+
 @pytest.mark.parametrize("w,h", [(64, 64), (160, 120), (97, 61), (33, 31)])
 def test_socket_display_stream(oracle, ref, w, h):
     """SURVEY 8f rank 4, second half: what the reference's socket display driver (display/sockdrv.c) puts on the wire for a frame --
