@@ -171,9 +171,20 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sampled": True},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample, "single_thread": single},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample, "single_thread": single,
+                         "baseline_kernel": BASELINE_KERNEL[kind]},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+# what the CPU arm runs per ray, next to what the GPU arm runs (the reference's AO loop calls the closest-hit query and builds the
+# hit state for every occlusion ray, ambientocclusion.c:123; the GPU answers the same question with an any-hit query)
+BASELINE_KERNEL = {
+    "reference": {"function": "ri_bvh_intersect (bvh.c:430-542) via ri_raytrace", "query": "closest hit + ri_intersection_state_build",
+                  "precision": "f64", "gpu_query": "any-hit (occlusion), fp32 records"},
+    "port": {"function": "orc_occluded_f64 (oracle/lucille_oracle.c, restatement of bvh_traverse)", "query": "any-hit",
+             "precision": "f64", "gpu_query": "any-hit (occlusion), fp32 records"},
+}
 
 
 def parity_sample(tris, rays8, gpu_occ, ref_scene=None):
@@ -217,7 +228,8 @@ def cpu_baseline(tris, rays8_sample, gpu_occ=None):
         t.occluded_f64(rays6[:200000])
         sec, kind, threads = (time.perf_counter() - t0) * len(rays6) / 200000, "port", 1
     out = {"value": len(rays6) / sec / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind,
-           "sample": f"first {len(rays6)} rays of the batch, closest-hit ri_bvh_intersect incl. state build, {threads} threads"}
+           "sample": f"first {len(rays6)} rays of the batch, closest-hit ri_bvh_intersect incl. state build, {threads} threads",
+           "baseline_kernel": BASELINE_KERNEL[kind]}
     if gpu_occ is not None:
         out["parity"] = parity_sample(tris, rays8_sample, gpu_occ, ref_scene)
     return out
@@ -499,7 +511,9 @@ def main():
         per_gpu_rays_s = nrays * args.steps / (ms * 1e-3)
         achieved = per_gpu_rays_s * b_ray / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "bytes_per_ray": b_ray, "inner_visits_per_ray": I, "tri_tests_per_ray": T,
+                "peak_source": peak_src, "achieved_kind": "modelled: measured rays/s x ALGORITHMIC bytes per ray (counters of the reference "
+                "traversal order on this batch); the measured DRAM bytes are `traffic`, their rate over the peak is `dram_frac`",
+                "bytes_per_ray": b_ray, "inner_visits_per_ray": I, "tri_tests_per_ray": T,
                 "note": "contract roofline: ALGORITHMIC bytes of the reference traversal (SURVEY 8d) over the measured HBM copy bandwidth; the "
                         "records are L2-resident, so the physical limiter is NOT HBM -- see `limiter` (ncu, one launch of this kernel)",
                 "closest_hit": {"bytes_per_ray": b_ray_c, "inner_visits_per_ray": Ic, "tri_tests_per_ray": Tc,

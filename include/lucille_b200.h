@@ -208,9 +208,7 @@ int64_t ri_b200_frame_pixels(const ri_b200_frame_t *frame, uint32_t *out, int64_
  *   RI_B200_GATHER_OCCLUSION  float occlusion(status, P, N, nsamples)                      shader.c:680-768 (all three channels)
  *   RI_B200_GATHER_IBL        ri_ibl_sample_cosweight(power, N, nsamples, ray, P, eye, l)  ibl.c:53-228, l->texture = env_rgba
  *   RI_B200_GATHER_DOME       ri_domelight_sample(power, hemi, nsamples, ray, P, eye, l)   ibl.c:231-389, l->col, l->intensity
- * (Monte Carlo branches by default; use_qmc selects the quasi-Monte Carlo ones.)  nrays_out (may be NULL) = rays traced.
- * trace() (shader.c:895-976) needs no entry of its own: it is one closest-hit query + hit state + environment lookup on a miss --
- * ri_b200_intersect_batch_f64 / ri_b200_state_ext_batch_f64 -- followed by the hit geometry's shader procedure, which stays on the host. */
+ * (Monte Carlo branches by default; use_qmc selects the quasi-Monte Carlo ones.)  nrays_out (may be NULL) = rays traced. */
 #define RI_B200_GATHER_OCCLUSION 0
 #define RI_B200_GATHER_IBL       1
 #define RI_B200_GATHER_DOME      2
@@ -235,6 +233,44 @@ typedef struct {
 } ri_b200_gather_t;
 int ri_b200_gather_points_f64(ri_b200_accel_t *accel, const ri_b200_gather_t *gather, const double *points, uint64_t n, double *out3,
                               uint64_t *nrays_out);
+
+/* ---- the two shading-language callers of ri_raytrace, batched over shading points.
+ *
+ * trace(status, dst, P, R) (render/shader.c:895-976) for n (P, R) pairs ([n][6] doubles, R NOT normalised): the ray (P + 0.0001 R, R),
+ * closest hit, and per pair what the shadeop does with the answer up to the call of the hit geometry's shader procedure (a host
+ * function pointer, which stays with the host).  On a hit: the procedure's input block -- Cs (vertex colours of ri_b200_set_attributes,
+ * else 1), P, N (the shading normal Ns), Ng, dPdu / dPdv (tangent / binormal), I = normalize(P_hit - P), s = u, t = v
+ * (shader.c:951-968) -- and Ci = 0.  On a miss: Ci = ri_texture_ibl_fetch(env, R) when env_rgba is given (the scene's first light is
+ * an IBL / sun-sky light, shader.c:927-940; [env_height][env_width][4] floats, host memory), else zero. */
+typedef struct {
+    double   Cs[3], P[3], N[3], Ng[3], dPdu[3], dPdv[3], I[3], Ci[3];
+    double   t;
+    float    s, tt;               /* the shader's s and t */
+    uint32_t prim;                /* post-build triangle number, RI_B200_MISS_PRIM on a miss */
+    int32_t  hit;
+} ri_b200_trace_rec_f64;
+int ri_b200_shade_trace_f64(ri_b200_accel_t *accel, const double *pr, uint64_t n, const float *env_rgba, int env_width, int env_height,
+                            ri_b200_trace_rec_f64 *out);
+
+/* next_lightsource(status, P, N, angle) + init_lightsource (render/shader.c:1116-1186, 1236-1310): the light samples an
+ * `illuminance` loop visits at each of n shading points ([n][6] doubles: P, N).  m = ri_b200_light_samples_count(nsamples) =
+ * ntheta * 3 ntheta samples per point, ntheta = (int)sqrt((int)(nsamples / 3.0)) (nsamples = Option narealight_rays); two words of
+ * the randomMT stream per sample (seed 4357 in the reference; `stream_offset` words drawn before point 0), L = normalize(direction),
+ * Cl = ri_texture_ibl_fetch(env, L) / m.  L_out / Cl_out: [n][m][3] doubles, all m samples in drawing order; visible_out [n][m]:
+ * 1 for the samples the reference's loop RETURNS, in that order -- inside the cone (dot(L, N) > 0 and acos(dot) < angle), not
+ * occluded along normalize(L) from P + 0.0001 N, and not the last sample of the set, which the reference can never return
+ * (shader.c:1170-1177).  nrays_out (may be NULL) = shadow rays traced.  Returns m, < 0 on failure. */
+typedef struct {
+    int32_t  nsamples;
+    uint32_t seed;
+    uint64_t stream_offset;
+    double   angle;
+    const float *env_rgba;        /* [env_height][env_width][4] floats (the IBL light's ri_texture_t.data), host memory; NULL: Cl = 0 */
+    int32_t  env_width, env_height;
+} ri_b200_light_t;
+int ri_b200_light_samples_count(int nsamples);
+int ri_b200_light_samples_f64(ri_b200_accel_t *accel, const ri_b200_light_t *light, const double *points, uint64_t n, double *L_out,
+                              double *Cl_out, uint8_t *visible_out, uint64_t *nrays_out);
 
 /* ---- calculate_occlusion (transport/ambientocclusion.c:42-151) as one batched call: n shading points (P, Ns) in, the number of
  * OCCLUDED gather rays per point out (the reference's `occlusion` counter; Lo = (N - occluded) / N, N = ntheta * nphi,
@@ -266,6 +302,11 @@ int ri_b200_ao_point_rays_f32(ri_b200_accel_t *accel, const ri_b200_ao_points_t 
  * them, the number of hit samples in all buckets of the frame that precede it, plus the frame's total.  The host implements it with
  * whatever it has between ranks (an all-gather of a few hundred integers: lucille_b200/distributed.py uses torch.distributed;
  * lucille itself would use ri_parallel_gather + ri_parallel_bcast, parallel.c:102-196).  Return 0, or non-zero to fail the frame.
+ * The call is a collective of the host's: every rank of the frame makes it exactly once per frame.  A rank whose frame call fails
+ * BEFORE it has counts still makes it, with bucket_hits == NULL and both output pointers NULL ("this rank has failed"): the host's
+ * exchange must then fail on every rank (distributed.hit_exchange carries a failure flag through its all-reduce), so that nobody
+ * waits for a rank that has gone.  The callback runs on the calling thread while the accelerator's lock is held: it must not call
+ * back into this accelerator.
  * With it the multi-GPU frame equals the reference's single-thread frame bit for bit, like the one-GPU frame. */
 typedef int (*ri_b200_hit_exchange_fn)(void *user, const uint32_t *bucket_hits, uint32_t nbuckets, uint64_t *bucket_base_out,
                                        uint64_t *frame_hits_out);

@@ -39,6 +39,8 @@ LIB_PATH = os.environ.get("B200_LIB") or os.path.join(os.path.dirname(os.path.ab
 HIT32_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4")])
 HIT64_DTYPE = np.dtype([("t", "<f8"), ("u", "<f8"), ("v", "<f8"), ("prim", "<u4"), ("hit", "<u4")])
 STATE_EXT_DTYPE = np.dtype([("E", "<f8", 3), ("I", "<f8", 3), ("color", "<f8", 3), ("st", "<f8", 2), ("t", "<f8"), ("inside", "<i4"), ("hit", "<i4")])
+TRACE_REC_DTYPE = np.dtype([("Cs", "<f8", 3), ("P", "<f8", 3), ("N", "<f8", 3), ("Ng", "<f8", 3), ("dPdu", "<f8", 3), ("dPdv", "<f8", 3),
+                            ("I", "<f8", 3), ("Ci", "<f8", 3), ("t", "<f8"), ("s", "<f4"), ("tt", "<f4"), ("prim", "<u4"), ("hit", "<i4")])
 STATE_DTYPE = np.dtype([("P", "<f8", 3), ("Ng", "<f8", 3), ("Ns", "<f8", 3), ("tangent", "<f8", 3), ("binormal", "<f8", 3)])
 NODE_DTYPE = np.dtype([("is_leaf", "<i4"), ("axis", "<i4"), ("child0", "<i8"), ("child1", "<i8"),
                        ("tri_start", "<i8"), ("ntris", "<i8"), ("lbox", "<f8", 6), ("rbox", "<f8", 6)])
@@ -93,6 +95,12 @@ class Sunsky(C.Structure):
                 ("sun_dir", C.c_double * 12), ("sun_col", C.c_double * 12)]
 
 
+class Light(C.Structure):
+    """ri_b200_light_t: the importance-sampled environment light of next_lightsource() (shader.c:1236-1310)."""
+    _fields_ = [("nsamples", C.c_int32), ("seed", C.c_uint32), ("stream_offset", C.c_uint64), ("angle", C.c_double),
+                ("env_rgba", C.c_void_p), ("env_width", C.c_int32), ("env_height", C.c_int32)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("nrays_primary", C.c_uint64), ("nrays_ao", C.c_uint64), ("nhits_primary", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_primary", C.c_double), ("ms_rng", C.c_double), ("ms_ao", C.c_double),
@@ -140,6 +148,9 @@ ABI = [
     ("ri_b200_render_ao_peer_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_set_hit_exchange", _I, [_P, _P, _P]),
     ("ri_b200_gather_points_f64", _I, [_P, _P, _P, _U64, _P, _P]),
+    ("ri_b200_shade_trace_f64", _I, [_P, _P, _U64, _P, _I, _I, _P]),
+    ("ri_b200_light_samples_count", _I, [_I]),
+    ("ri_b200_light_samples_f64", _I, [_P, _P, _P, _U64, _P, _P, _P, _P]),
     ("ri_b200_occlusion_points_f32", _I, [_P, _P, _P, _U64, _P]),
     ("ri_b200_occlusion_points_dev_f32", _I, [_P, _P, _P, _U64, _P, _P]),
     ("ri_b200_ao_point_rays_f32", _I, [_P, _P, _P, _U64, _P]),
@@ -508,9 +519,39 @@ class Accel:
         _check(self.lib.ri_b200_gather_points_f64(self._h(), C.byref(g), _ptr(pts), len(pts), _ptr(out), C.byref(nrays)))
         return out, nrays.value
 
+    def shade_trace(self, pr6, env=None) -> np.ndarray:
+        """The trace() shadeop (shader.c:895-976) for (P, R) pairs up to the call of the hit surface's shader procedure
+        (ri_b200_shade_trace_f64): records of TRACE_REC_DTYPE -- the shader's input block on a hit, the environment colour on a miss."""
+        pr = np.ascontiguousarray(pr6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(len(pr), dtype=TRACE_REC_DTYPE)
+        if env is not None:
+            env = np.ascontiguousarray(env, dtype=np.float32)
+        _check(self.lib.ri_b200_shade_trace_f64(self._h(), _ptr(pr), len(pr), None if env is None else _ptr(env),
+                                                0 if env is None else env.shape[1], 0 if env is None else env.shape[0], _ptr(out)))
+        return out
+
+    def light_samples(self, nsamples: int, angle: float, points6, env=None, seed: int = 4357, stream_offset: int = 0):
+        """The light samples of next_lightsource() (shader.c:1116-1310) at shading points (P, N) (ri_b200_light_samples_f64):
+        (L [n,m,3], Cl [n,m,3], visible [n,m] u8, shadow rays traced); visible marks the samples the reference's loop returns."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        g = Light()
+        g.nsamples, g.seed, g.stream_offset, g.angle = int(nsamples), int(seed), int(stream_offset), float(angle)
+        if env is not None:
+            env = np.ascontiguousarray(env, dtype=np.float32)
+            g.env_rgba, g.env_width, g.env_height = env.ctypes.data, env.shape[1], env.shape[0]
+        m = int(self.lib.ri_b200_light_samples_count(int(nsamples)))
+        L = np.zeros((len(pts), m, 3)); Cl = np.zeros((len(pts), m, 3)); vis = np.zeros((len(pts), m), dtype=np.uint8)
+        nrays = C.c_uint64(0)
+        got = self.lib.ri_b200_light_samples_f64(self._h(), C.byref(g), _ptr(pts), len(pts), _ptr(L), _ptr(Cl), _ptr(vis), C.byref(nrays))
+        if got < 0:
+            _check(got)
+        assert got == m
+        return L, Cl, vis, nrays.value
+
     def set_hit_exchange(self, fn):
         """rng_mode 0 on world > 1 (ri_b200_set_hit_exchange): fn(bucket_hits: np.ndarray[u32]) -> (bucket_base: array of u64, same
-        length; frame_hits: int).  None removes it."""
+        length; frame_hits: int).  fn(None) means "this rank failed before it had counts": fn still takes part in the exchange so the
+        other ranks are released, and the frame fails everywhere.  None removes the callback."""
         if fn is None:
             self._hit_cb = None
             _check(self.lib.ri_b200_set_hit_exchange(self._h(), None, None))
@@ -518,6 +559,9 @@ class Accel:
 
         def tramp(_user, hits_p, n, base_p, total_p):
             try:
+                if not hits_p and not base_p:     # the library's guard: this rank failed before the exchange
+                    fn(None)
+                    return 1
                 hits = np.ctypeslib.as_array(hits_p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
                 base, total = fn(hits)
                 base = np.asarray(base, dtype=np.uint64)

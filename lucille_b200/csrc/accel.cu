@@ -1073,6 +1073,7 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
 #include "beam.cuh"
 #include "whitted.cuh"
 #include "gather.cuh"
+#include "shade.cuh"
 #include "bvh_build_gpu.cuh"
 #include "hdr.cuh"
 

@@ -716,6 +716,14 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     std::vector<double> jit;
     // one MT19937 stream over several ranks: the per-bucket hit counts are exchanged through the host's callback (below)
     const bool shared_stream = f.rng_mode == 0 && f.world > 1;
+    if (shared_stream && !a->hit_exchange) return fail("rng_mode 0 on several ranks needs ri_b200_set_hit_exchange");
+    // The exchange callback is a collective of the host's (every rank of the frame calls it once).  A rank that fails BEFORE its
+    // call must not leave the others waiting in theirs: until the real call below this guard makes the call on any early return,
+    // with a NULL count array = "this rank has failed", so that the host's exchange fails the frame on every rank together.
+    struct ExchangeGuard {
+        ri_b200_accel *a; bool armed;
+        ~ExchangeGuard() { if (armed) a->hit_exchange(a->hit_exchange_user, nullptr, 0, nullptr, nullptr); }
+    } exchange_guard{a, shared_stream};
     std::vector<uint32_t> bfirst;
     pixel_order(f, pix, shared_stream ? &bfirst : nullptr);
     jitter_table(f.xsamples, f.ysamples, jit);
@@ -814,8 +822,9 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
             CUDA_OK(cudaMemcpyAsync(bhits.data(), d_bhits, (size_t)nbuckets * 4, cudaMemcpyDeviceToHost, st));
             CUDA_OK(cudaStreamSynchronize(st));
         }
+        exchange_guard.armed = false;
         if (a->hit_exchange(a->hit_exchange_user, bhits.data(), nbuckets, bbase.data(), &frame_hits) != 0)
-            return fail("the hit-count exchange callback failed");
+            return fail("the hit-count exchange failed (on this rank or on another one)");
         std::vector<long long> delta(nbuckets);
         uint64_t before = 0;
         for (uint32_t b = 0; b < nbuckets; ++b) {

@@ -233,6 +233,24 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                 spa = spa + (both ? kRow : 0u) - (pop ? kRow : 0u);
                 next = both ? near : (none ? popped : (h0 ? c0 : c1));
                 if (next == kIdle) retire(false);                                 // stack ran dry
+#if B200_PF_LEAF
+                // experiment (X1: bulk / TMA staging where the records really come from HBM): the lane will stand in this leaf until a
+                // leaf round takes it -- ask the TMA unit to pull the leaf's whole slab (<= 768 B) into L2 meanwhile, one instruction
+                if ((int32_t)next < 0 && next != kIdle) {
+                    const uint32_t nt = ((next >> kLeafShift) & 15u) + 1u;
+                    const char *slab = trisT + (size_t)(next & kSlotMask) * 48u;
+                    const uint32_t bytes = ((nt + 3u) >> 2) * 192u;               // round_up(ntris, 4) slots of 48 bytes
+#if B200_PF_LEAF == 2
+                    for (uint32_t o = 0; o < bytes; o += 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(slab + o));
+#else
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(slab), "r"(bytes) : "memory");
+#endif
+                }
+#endif
+#if B200_PF_FAR
+                // ... and the record of the far child the lane has just pushed (an inner node: 64 bytes)
+                if (both && far < kIdle) asm volatile("prefetch.global.L2 [%0];" :: "l"(S.nodes + far));
+#endif
                 prog = 0;
                 cur = next;
             }

@@ -107,15 +107,44 @@ def hit_exchange(rank: int, world: int, group=None, device=None):
     import torch.distributed as dist
 
     def fn(hits):
-        n = torch.tensor([len(hits)], dtype=torch.int64, device=device)
-        dist.all_reduce(n, op=dist.ReduceOp.MAX, group=group)
-        mine = torch.zeros(int(n.item()), dtype=torch.int64, device=device)
+        # hits is None when this rank failed before it had counts (the library's guard call): it still takes part, with the failure
+        # flag raised, and every rank leaves the exchange with an error instead of waiting for it
+        failed = hits is None
+        head = torch.tensor([0 if failed else len(hits), 1 if failed else 0], dtype=torch.int64, device=device)
+        dist.all_reduce(head, op=dist.ReduceOp.MAX, group=group)
+        if int(head[1].item()):
+            raise _accel.B200Error("hit-count exchange: a rank of the frame failed before the exchange")
+        mine = torch.zeros(int(head[0].item()), dtype=torch.int64, device=device)
         mine[:len(hits)] = torch.from_numpy(hits.astype(np.int64))
         parts = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine, group=group)
         bases, total = bucket_bases(torch.stack(parts).cpu().numpy(), world)
         return bases[rank][:len(hits)], total
     return fn
+
+
+def _frame_call_all_ranks(call, world: int, group=None, device=None):
+    """Run this rank's frame call; with several ranks, agree on the outcome before anybody enters the next collective: one all-reduce
+    of a failure flag (which also is the "every rank's stores have landed" barrier of the peer path).  A failure on any rank raises
+    on every rank -- nobody is left waiting in a gather or a barrier for a rank that has gone."""
+    import torch
+    import torch.distributed as dist
+
+    err = None
+    try:
+        out = call()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    except Exception as e:                         # noqa: BLE001 -- re-raised below, after the other ranks know
+        out, err = None, e
+    if world > 1:
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if err is None and int(flag.item()):
+            raise _accel.B200Error("the frame failed on another rank")
+    if err is not None:
+        raise err
+    return out
 
 
 class PeerFramebuffer:
@@ -159,10 +188,7 @@ def render_ao_distributed_peer(acc: "_accel.Accel", frame: "_accel.Frame", fb: P
         acc.set_hit_exchange(hit_exchange(fb.rank, fb.world, fb.group, device="cuda"))
     if fb.world > 1:
         dist.barrier(group=fb.group)                   # rank 0 has read the previous frame out of the buffer
-    stats = acc.render_ao_peer_dev(f, fb.ptr, stream)
-    torch.cuda.synchronize()
-    if fb.world > 1:
-        dist.barrier(group=fb.group)
+    stats = _frame_call_all_ranks(lambda: acc.render_ao_peer_dev(f, fb.ptr, stream), fb.world, fb.group, device="cuda")
     rgb = _accel.peer_read(fb.ptr, fb.shape, fb.device) if fb.rank == 0 else None
     return rgb, stats
 
@@ -177,6 +203,5 @@ def render_ao_distributed(acc: "_accel.Accel", frame: "_accel.Frame", rank: int,
         acc.set_hit_exchange(hit_exchange(rank, world, group, device="cuda"))
     npix = len(_accel.frame_pixels(f))
     slab = torch.empty((max(npix, 1), 3), dtype=torch.float32, device="cuda")
-    stats = acc.render_ao_tiles_dev(f, slab, stream)
-    torch.cuda.synchronize()
+    stats = _frame_call_all_ranks(lambda: acc.render_ao_tiles_dev(f, slab, stream), world, group, device="cuda")
     return gather_frame(slab[:npix], f, rank, world, group), stats

@@ -127,3 +127,52 @@ def test_hit_exchange_over_gloo_world2():
     for r in range(world):
         assert got[r][1] == hits.sum()
         assert np.array_equal(got[r][0].astype(np.int64), want[r::world])
+
+
+def _failure_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lucille_b200 import accel
+    out = []
+    # (1) rank 1 failed before it had counts: the library's guard calls the exchange with NULL -> fn(None); rank 0 is in its real call
+    try:
+        distributed.hit_exchange(rank, world)(None if rank == 1 else np.arange(4, dtype=np.uint32))
+        out.append("returned")
+    except accel.B200Error as e:
+        out.append("raised: " + str(e))
+    # (2) rank 1's frame call fails after the exchange: the outcome all-reduce raises on rank 0 too, before it would enter the gather
+
+    def call():
+        if rank == 1:
+            raise accel.B200Error("boom on rank 1")
+        return "stats"
+    try:
+        distributed._frame_call_all_ranks(call, world)
+        out.append("returned")
+    except accel.B200Error as e:
+        out.append("raised: " + str(e))
+    # (3) and a frame that succeeds everywhere goes through
+    out.append(distributed._frame_call_all_ranks(lambda: "stats", world))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_failures_fail_the_frame_on_every_rank_gloo_world2():
+    """A rank that fails around the hit-count exchange or in its frame call must not leave the others waiting in a collective
+    (900 s pytest timeout): the failure travels through the exchange / the outcome all-reduce and every rank raises."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_failure_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0][0].startswith("raised: hit-count exchange") and got[1][0].startswith("raised: hit-count exchange")
+    assert got[0][1] == "raised: the frame failed on another rank" and got[1][1] == "raised: boom on rank 1"
+    assert got[0][2] == "stats" and got[1][2] == "stats"

@@ -820,3 +820,68 @@ def test_point_gathers(oracle, golden_dir):
         got, _ = a.gather_points(accel.GATHER_OCCLUSION, 3, big[:m])
         want, _ = ot.point_gather(accel.GATHER_OCCLUSION, 3, big[:m])
         assert np.array_equal(got, want)
+
+
+def test_shade_callers(oracle, golden_dir):
+    """SURVEY 8f rank 2, the two shading-language callers of ri_raytrace as batched queries.  ri_b200_shade_trace_f64 = the trace()
+    shadeop (shader.c:895-976) up to the call of the hit surface's shader procedure: hit set, shader input block (Cs, P, N, Ng, dPdu,
+    dPdv, I, s, t) bit-identical to what the compiled reference hands its shader (golden vectors) and to the oracle; the environment
+    colour on a miss goes through acos -> 1e-9 relative.  ri_b200_light_samples_f64 = next_lightsource() (shader.c:1116-1310): the
+    samples the reference's illuminance loop returns, in order.  Directions come from device sin / cos / sqrt (last-place differences
+    from glibc's): L and Cl to 1e-12 / 1e-9 relative, the visible set itself identical."""
+    _need_gpu()
+    g = np.load(os.path.join(golden_dir, "shade_callers.npz"))
+    sizes = [int(x) for x in g["sizes"]]
+    tris = scenes.triangle_soup(sum(sizes), int(g["seed_t"]))
+    col, st, _flags, has_col, has_st, inside = ol.attribute_case(len(tris), sizes, int(g["attr_seed"]))
+    a = accel.Accel.bind().build(tris, accel.PREC_F64).set_attributes(col, has_col, st, has_st, inside)
+    env, pr = g["env"], g["pr"]
+    got = a.shade_trace(pr, env)
+    hit = got["hit"] == 1
+    assert np.array_equal(hit, g["trace_called"] == 1)
+    for f in ("Cs", "P", "N", "Ng", "dPdu", "dPdv", "I"):
+        assert np.array_equal(got[f][hit], g["trace_" + f][hit]), f
+        assert not got[f][~hit].any()
+    assert np.array_equal(got["s"][hit], g["trace_s"][hit]) and np.array_equal(got["tt"][hit], g["trace_t"][hit])
+    assert np.allclose(got["Ci"][~hit], g["trace_dst"][~hit], rtol=1e-9, atol=0.0) and not got["Ci"][hit].any()
+    assert np.all(got["prim"][~hit] == accel.MISS_PRIM)
+    ot = oracle.build(tris)
+    ot.set_attributes(col, has_col, st, has_st, inside)
+    rng = np.random.default_rng(12)
+    P = rng.uniform(-0.3, 1.3, (20000, 3))
+    big = np.concatenate([P, (rng.uniform(0.0, 1.0, (20000, 3)) - P) * rng.uniform(0.2, 3.0, (20000, 1))], axis=1)
+    got, want = a.shade_trace(big, None), ot.shade_trace(big, None, use_env=False)
+    hit = got["hit"] == 1
+    assert np.array_equal(hit, want["hits"]["hit"] == 1) and np.array_equal(got["prim"][hit], want["hits"]["prim"][hit])
+    assert np.array_equal(got["t"][hit], want["hits"]["t"][hit]) and np.array_equal(got["I"][hit], want["eye"][hit])
+    assert np.array_equal(got["Cs"][hit], want["exts"]["color"][hit]) and not got["Ci"].any()
+    assert len(a.shade_trace(np.zeros((0, 6)), env)) == 0
+    empty = accel.Accel.bind().build(np.zeros((0, 3, 3)), accel.PREC_F64)
+    e = empty.shade_trace(pr[:100], env)
+    assert not e["hit"].any() and np.allclose(e["Ci"], oracle.build(np.zeros((0, 3, 3))).shade_trace(pr[:100], env)["miss_rgb"], rtol=1e-9, atol=0.0)
+
+    # next_lightsource()
+    ltris = scenes.triangle_soup(int(g["ntris_l"]), int(g["seed_l"]))
+    la, lo = accel.Accel.bind().build(ltris, accel.PREC_F64), oracle.build(ltris)
+    pts = g["points"]
+    for i, (ns, angle) in enumerate(g["light_cases"]):
+        L, Cl, vis, nrays = la.light_samples(int(ns), float(angle), pts, env)
+        oL, oCl, ovis, onrays = lo.light_samples(int(ns), float(angle), pts, env)
+        assert L.shape == oL.shape and np.array_equal(vis, ovis) and nrays == onrays, (ns, angle)
+        assert np.allclose(L, oL, rtol=0.0, atol=1e-12) and np.allclose(Cl, oCl, rtol=1e-9, atol=1e-300)
+        cnt = g[f"light{i}_count"]
+        assert np.array_equal(vis.sum(axis=1), cnt) and not vis[:, -1].any()
+        for p in range(len(pts)):                              # the compiled reference's returned samples, in order
+            k = int(cnt[p])
+            assert np.allclose(L[p][vis[p] == 1], g[f"light{i}_L"][p, :k], rtol=0.0, atol=1e-12)
+            assert np.allclose(Cl[p][vis[p] == 1], g[f"light{i}_Cl"][p, :k], rtol=1e-9, atol=1e-300)
+    # a batch that continues the stream where an earlier one stopped; no points; an empty scene (everything inside the cone is visible)
+    half = len(pts) // 2
+    m = 3 * 4 * 4
+    whole = la.light_samples(48, 1.2, pts, env)
+    tail = la.light_samples(48, 1.2, pts[half:], env, stream_offset=2 * m * half)
+    assert all(np.array_equal(x, y[half:]) for x, y in zip(tail[:3], whole[:3]))
+    assert la.light_samples(48, 1.2, np.zeros((0, 6)), env)[0].shape == (0, m, 3)
+    eL, eCl, evis, en = empty.light_samples(27, 1.0, pts[:40], env)
+    oL, oCl, ovis, on = oracle.build(np.zeros((0, 3, 3))).light_samples(27, 1.0, pts[:40], env)
+    assert np.array_equal(evis, ovis) and en == on and evis.sum() > 0

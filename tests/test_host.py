@@ -234,6 +234,7 @@ int main(void) {
     S(ri_b200_hit_f32, prim); S(ri_b200_hit_f64, hit); S(ri_b200_state_f64, binormal); S(ri_b200_state_ext_f64, hit);
     S(ri_b200_info_t, build_seconds); S(ri_b200_counters_t, nhit_tris); S(ri_b200_frame_t, precision);
     S(ri_b200_frame_stats_t, ms_resolve); S(ri_b200_gather_t, qmc_instance); S(ri_b200_sunsky_t, nsun); S(ri_b200_path_frame_t, bucket_size);
+    S(ri_b200_trace_rec_f64, hit); S(ri_b200_light_t, env_height); S(ri_b200_ao_points_t, eps);
     return 0;
 }
 ''')
@@ -257,5 +258,7 @@ int main(void) {
         "ri_b200_frame_t": ct(accel.Frame, "precision"), "ri_b200_frame_stats_t": ct(accel.FrameStats, "ms_resolve"),
         "ri_b200_gather_t": ct(accel.Gather, "qmc_instance"), "ri_b200_sunsky_t": ct(accel.Sunsky, "nsun"),
         "ri_b200_path_frame_t": ct(accel.PathFrame, "bucket_size"),
+        "ri_b200_trace_rec_f64": nd(accel.TRACE_REC_DTYPE, "hit"), "ri_b200_light_t": ct(accel.Light, "env_height"),
+        "ri_b200_ao_points_t": ct(accel.AoPoints, "eps"),
     }
     assert got == want

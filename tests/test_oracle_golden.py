@@ -191,6 +191,40 @@ def test_point_gathers_golden(oracle, golden_dir):
         assert np.array_equal(got, g[f"q{kind}_n{ns}_d{dim}"]), (kind, ns, dim)
 
 
+def _shade_scene(g):
+    sizes = [int(x) for x in g["sizes"]]
+    tris = scenes.triangle_soup(sum(sizes), int(g["seed_t"]))
+    col, st, _flags, has_col, has_st, inside = ol.attribute_case(len(tris), sizes, int(g["attr_seed"]))
+    return tris, (col, has_col, st, has_st, inside)
+
+
+def test_shade_callers_golden(oracle, golden_dir):
+    """SURVEY 8f rank 2, the two shading-language callers of ri_raytrace: the compiled reference's trace() shadeop at 1500 (P, R)
+    pairs and its next_lightsource() loop at 250 shading points (tests/golden/make_shade_golden.py) -- the restatement reproduces the
+    shader input blocks, the miss colours and the returned light samples bit for bit."""
+    g = np.load(os.path.join(golden_dir, "shade_callers.npz"))
+    tris, attrs = _shade_scene(g)
+    t = oracle.build(tris)
+    t.set_attributes(*attrs)
+    got = t.shade_trace(g["pr"], g["env"])
+    hit = got["hits"]["hit"] == 1
+    assert np.array_equal(g["trace_called"] == 1, hit) and 0.2 < hit.mean() < 0.9
+    assert np.array_equal(g["trace_dst"][~hit], got["miss_rgb"][~hit])
+    for name, field in (("Cs", got["exts"]["color"]), ("P", got["states"]["P"]), ("N", got["states"]["Ns"]), ("Ng", got["states"]["Ng"]),
+                        ("dPdu", got["states"]["tangent"]), ("dPdv", got["states"]["binormal"]), ("I", got["eye"])):
+        assert np.array_equal(g["trace_" + name][hit], field[hit]), name
+    assert np.array_equal(g["trace_s"][hit], got["hits"]["u"][hit].astype(np.float32))
+    assert np.array_equal(g["trace_t"][hit], got["hits"]["v"][hit].astype(np.float32))
+    lt = oracle.build(scenes.triangle_soup(int(g["ntris_l"]), int(g["seed_l"])))
+    for i, (ns, angle) in enumerate(g["light_cases"]):
+        L, Cl, vis, nrays = lt.light_samples(int(ns), float(angle), g["points"], g["env"])
+        cnt = g[f"light{i}_count"]
+        assert np.array_equal(vis.sum(axis=1), cnt) and nrays >= vis.sum()
+        for p in range(len(cnt)):
+            k = int(cnt[p])
+            assert np.array_equal(L[p][vis[p] == 1], g[f"light{i}_L"][p, :k]) and np.array_equal(Cl[p][vis[p] == 1], g[f"light{i}_Cl"][p, :k])
+
+
 def test_socket_display_stream_golden(oracle, golden_dir):
     """The socket display driver's byte stream for the committed frames (sha256 + size in sockdrv.npz, captured from the compiled
     reference by tests/golden/make_sockdrv_golden.py)."""
