@@ -30,6 +30,10 @@ extern "C" {
 
 #define RI_B200_PREC_F32       1u            /* fp32 node/triangle records: the throughput path */
 #define RI_B200_PREC_F64       2u            /* double records: bit-identical to the CPU reference */
+/* With BOTH record sets resident, double OCCLUSION queries (ri_b200_occluded_*_f64, the AO / sun-sky / point gathers of double frames)
+ * run through the fp32 records with a certified error bound on every box and triangle decision and consult the double records only
+ * for the decisions fp32 cannot settle (csrc/hybrid.cuh): the double reference's answer for every ray at close to the fp32 rate.
+ * B200_HYBRID=0 in the environment turns this off (the double kernel runs instead), =2 forces it for scenes far from the origin too. */
 #define RI_B200_HOST_ONLY      0x100u        /* build + flatten on the host, no device upload: every trace call on
                                                 such an accelerator fails loudly (used by the CPU-only tests) */
 #define RI_B200_BUILD_DEVICE   0x200u        /* build the tree on the device (level-by-level binned SAH, csrc/bvh_build_gpu.cuh): the same
@@ -294,6 +298,13 @@ int ri_b200_occlusion_points_f32(ri_b200_accel_t *accel, const ri_b200_ao_points
 int ri_b200_occlusion_points_dev_f32(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *d_points, uint64_t n,
                                      uint32_t *d_occluded, void *stream);
 int ri_b200_ao_point_rays_f32(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *points, uint64_t n, float *rays_out);
+/* The same call in the reference's own precision: the N rays of a point are set up as above and traced as DOUBLE rays against the
+ * double records -- every count equals what the double reference finds for those rays (oracle: orc_ao_point_rays_f64 + the f64
+ * traversal).  This is the entry for real scenes, where fp32 ray records cannot hold an origin 1e-6 above a surface. */
+int ri_b200_occlusion_points_f64(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *points, uint64_t n,
+                                 uint32_t *occluded_out);
+int ri_b200_occlusion_points_dev_f64(ri_b200_accel_t *accel, const ri_b200_ao_points_t *params, const double *d_points, uint64_t n,
+                                     uint32_t *d_occluded, void *stream);
 
 /* rng_mode 0 (the reference's single MT19937 stream, random.c:211-247) on world > 1.  The stream position of a gather ray depends
  * on how many eye samples hit something in every bucket the reference renders EARLIER (render.c:1131-1146 in spiral order), and

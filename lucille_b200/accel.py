@@ -154,6 +154,8 @@ ABI = [
     ("ri_b200_occlusion_points_f32", _I, [_P, _P, _P, _U64, _P]),
     ("ri_b200_occlusion_points_dev_f32", _I, [_P, _P, _P, _U64, _P, _P]),
     ("ri_b200_ao_point_rays_f32", _I, [_P, _P, _P, _U64, _P]),
+    ("ri_b200_occlusion_points_f64", _I, [_P, _P, _P, _U64, _P]),
+    ("ri_b200_occlusion_points_dev_f64", _I, [_P, _P, _P, _U64, _P, _P]),
     ("ri_b200_peer_alloc", _P, [_U64, _I, _P]),
     ("ri_b200_peer_open", _P, [_P, _I]),
     ("ri_b200_peer_close", _I, [_P, _I]),
@@ -414,11 +416,14 @@ class Accel:
         _check(fn(self._h(), _ptr(d_rays), n, _ptr(d_out), C.c_void_p(stream) if stream else None))
 
     # -- calculate_occlusion as a batch: shading points in, occluded-ray counts out (rays generated on the device) ------
-    def occlusion_points(self, points6: np.ndarray, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6) -> np.ndarray:
+    def occlusion_points(self, points6: np.ndarray, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6, f64: bool = False) -> np.ndarray:
+        """calculate_occlusion for a batch of shading points (P, Ns): occluded-ray counts.  f64: double rays against the double records
+        (the double reference's answer for every ray) instead of fp32 ray records."""
         pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
         out = np.zeros(len(pts), dtype=np.uint32)
         par = AoPoints(ntheta, nphi, seed, eps)
-        _check(self.lib.ri_b200_occlusion_points_f32(self._h(), C.byref(par), _ptr(pts), len(pts), _ptr(out)))
+        fn = self.lib.ri_b200_occlusion_points_f64 if f64 else self.lib.ri_b200_occlusion_points_f32
+        _check(fn(self._h(), C.byref(par), _ptr(pts), len(pts), _ptr(out)))
         return out
 
     def occlusion_points_dev(self, d_points, n: int, d_out, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6,

@@ -75,6 +75,7 @@ struct ri_b200_accel {
     uint32_t  mt_states_cap = 0, mt_states_seed = 0;
     ri_b200_hit_exchange_fn hit_exchange = nullptr;      // rng_mode 0 over several ranks (frame.cuh)
     void     *hit_exchange_user = nullptr;
+    bool verts_f32 = false;               // every vertex coordinate is an fp32 number (hybrid.cuh: no absolute error in the fp32 slots)
     bool streamed_faulted = false;        // host_batch: the streamed upload timed out once -> launch-per-piece from then on
     unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
     std::atomic<unsigned> work_slot{0};   // the _dev entry points may be called from several host threads / streams
@@ -201,6 +202,7 @@ trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const
 #include "pool.cuh"
 #include "pool32.cuh"
 #include "pool_closest.cuh"
+#include "hybrid.cuh"
 
 static const char *pool_tris(const ri_b200_accel *a, float)  { return reinterpret_cast<const char *>(a->d_tris32t); }
 static const char *pool_tris(const ri_b200_accel *a, double) { return reinterpret_cast<const char *>(a->d_tris64t); }
@@ -262,6 +264,69 @@ static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uin
     return true;
 }
 static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, uint8_t *, uint32_t *, uint32_t, unsigned int *,
+                          const unsigned int *, unsigned int *, unsigned, cudaStream_t) { return false; }
+
+// hybrid.cuh: double-exact occlusion through the fp32 records with certified decisions, the double records only where fp32 cannot
+// decide.  Applies to double rays when BOTH record sets are resident and the tree fits a static stack; B200_HYBRID=0 turns it off.
+template <int kCap>
+static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
+                              uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+{
+    HybK H;
+    float bm = 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        H.bmax[k] = std::fmax(std::fabs(a->flat.smin32[k]), std::fabs(a->flat.smax32[k]));
+        bm = std::fmax(bm, H.bmax[k]);
+    }
+    H.eta0 = a->verts_f32 ? 0.0f : 5.9604645e-8f * bm;
+    H.de = 2.0f * H.eta0;
+    const SceneView<float> S = make_view<float>(a);
+    const SceneView<double> S64 = make_view<double>(a);
+    const char *tt = pool_tris(a, 0.0f);
+    const PackK K = make_pack_k();
+    const size_t smem = sizeof(HybSmem<kCap>);
+#define B200_HYB_LAUNCH(C, X) do { auto kern = occluded_hybrid_kernel<kCap, C, X>;                                               \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                      \
+        kern<<<blocks, kBlock, smem, st>>>(S, S64, tt, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, K, H); } while (0)
+    if (d_counts) { if (a->verts_f32) B200_HYB_LAUNCH(true, true); else B200_HYB_LAUNCH(true, false); }
+    else          { if (a->verts_f32) B200_HYB_LAUNCH(false, true); else B200_HYB_LAUNCH(false, false); }
+#undef B200_HYB_LAUNCH
+}
+static bool launch_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
+                          uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned, cudaStream_t st)
+{
+    const char *env = getenv("B200_HYBRID");                      // read per launch: tests and A/B scripts switch it inside one process
+    const int mode = env ? atoi(env) : 1;                         // 0: never, 1: where it pays, 2: whenever possible
+    const int cap = stack_capacity(a);
+    if (mode == 0 || cap > 28 || !a->d_nodes32 || !a->d_tris32t || !a->d_nodes64 || !a->d_tris64) return false;
+    // The fp32 records hold ABSOLUTE coordinates, so the error bounds grow with the scene's distance from the origin while the
+    // intervals they are compared with shrink with its size: far from the origin most decisions fall back to doubles and the double
+    // kernel is faster (measured: coordinates ~ 1000 on a scene of size 4: 386 against 504 Mrays/s; at the origin: 916 against 491).
+    if (mode == 1) {
+        double far = 0.0, ext = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            far = std::fmax(far, std::fmax(std::fabs(a->tree.bmin[k]), std::fabs(a->tree.bmax[k])));
+            ext = std::fmax(ext, a->tree.bmax[k] - a->tree.bmin[k]);
+        }
+        if (!(far <= 4.0 * ext)) return false;
+    }
+    auto blocks_for = [&](const void *kern, size_t smem) -> unsigned {
+        int per_sm = 0;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem);
+        if (per_sm < 1) per_sm = 1;
+        const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
+        uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
+        want = (want + (kBlock / 32) - 1) / (kBlock / 32);
+        return (unsigned)(want < capb ? want : capb);
+    };
+    if (cap <= 20) launch_hybrid_cap<20>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault,
+                                         blocks_for((const void *)occluded_hybrid_kernel<20, false, true>, sizeof(HybSmem<20>)), st);
+    else launch_hybrid_cap<28>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault,
+                               blocks_for((const void *)occluded_hybrid_kernel<28, false, true>, sizeof(HybSmem<28>)), st);
+    return true;
+}
+static bool launch_hybrid(ri_b200_accel *, const float *, uint32_t, uint32_t, uint8_t *, uint32_t *, uint32_t, unsigned int *,
                           const unsigned int *, unsigned int *, unsigned, cudaStream_t) { return false; }
 
 template <int kCap>
@@ -334,6 +399,9 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             CUDA_OK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
             if (pooled_closest)
                 launch_closest_pool<Real>(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_hits + done, ctr, refill_at, st);
+            else if (pooled && launch_hybrid(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_occ ? d_occ + done : nullptr,
+                                             d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, d_ready, d_fault, blocks, st))
+                ;                                // double rays, both record sets resident: certified fp32 decisions, doubles where needed (hybrid.cuh)
             else if (pooled && launch_pool32(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_occ ? d_occ + done : nullptr,
                                              d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, d_ready, d_fault, blocks, st))
                 ;                                // fp32 occlusion on a tree that fits a static stack: the specialised kernel (pool32.cuh)
@@ -415,6 +483,11 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
     if (!a) { fail("out of memory"); return nullptr; }
     a->device = device;
     a->precisions = precisions;
+    if ((precisions & RI_B200_PREC_F32) && (precisions & RI_B200_PREC_F64)) {       // hybrid.cuh: are all vertex coordinates fp32 numbers?
+        bool exact = true;
+        for (uint64_t i = 0; i < 9 * ntris && exact; ++i) exact = (double)(float)tri_xyz[i] == tri_xyz[i];
+        a->verts_f32 = exact;
+    }
 
     // Where the tree is built: RI_B200_BUILD_DEVICE / RI_B200_BUILD_HOST say so; otherwise scenes of at least 32 Ki triangles are built
     // on the device (1 M triangles: 30 ms against 170 ms with 16 host threads, same tree) and small ones on the host (a device

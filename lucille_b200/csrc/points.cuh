@@ -19,8 +19,10 @@ namespace b200 {
 
 struct AoPointsDev { int ntheta, nphi; uint64_t seed; double eps; };
 
+// Real = float: fp32 ray records (rounded once); Real = double: the rays in the reference's own precision, [n][6]
+template <typename Real>
 __global__ void __launch_bounds__(kBlock)
-ao_points_gen_kernel(const AoPointsDev G, const double *__restrict__ points, const uint64_t point0, const uint64_t nrays, float *__restrict__ rays_out)
+ao_points_gen_kernel(const AoPointsDev G, const double *__restrict__ points, const uint64_t point0, const uint64_t nrays, Real *__restrict__ rays_out)
 {
     // the shading frame of a point is shared by its N rays: the first thread of the block that touches a point computes
     // ri_ortho_basis once and parks it in shared memory (a block of 256 rays covers at most 256 points)
@@ -52,15 +54,22 @@ ao_points_gen_kernel(const AoPointsDev G, const double *__restrict__ points, con
     double sn, cs;
     det_sincos2pi(z1, sn, cs);
     const double lx = cs * ct, ly = sn * ct, lz = sqrt(1.0 - ct * ct);            // ambientocclusion.c:96-100
-    float4 *o = reinterpret_cast<float4 *>(rays_out) + 2 * gid;
-    float org[3], dir[3];
+    double org[3], dir[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        org[q] = (float)(pt[q] + n[q] * G.eps);                                   // ambientocclusion.c:73-75
-        dir[q] = (float)(lx * s_b0[local][q] + ly * s_b1[local][q] + lz * n[q]);  // ambientocclusion.c:106-111
+        org[q] = pt[q] + n[q] * G.eps;                                            // ambientocclusion.c:73-75
+        dir[q] = lx * s_b0[local][q] + ly * s_b1[local][q] + lz * n[q];           // ambientocclusion.c:106-111
     }
-    o[0] = make_float4(org[0], org[1], org[2], 0.0f);
-    o[1] = make_float4(dir[0], dir[1], dir[2], 1.0e38f);
+    if (sizeof(Real) == 4) {
+        float4 *o = reinterpret_cast<float4 *>(rays_out) + 2 * gid;
+        o[0] = make_float4((float)org[0], (float)org[1], (float)org[2], 0.0f);
+        o[1] = make_float4((float)dir[0], (float)dir[1], (float)dir[2], 1.0e38f);
+    } else {
+        double2 *o = reinterpret_cast<double2 *>(rays_out) + 3 * gid;
+        o[0] = make_double2(org[0], org[1]);
+        o[1] = make_double2(org[2], dir[0]);
+        o[2] = make_double2(dir[1], dir[2]);
+    }
 }
 
 }  // namespace b200
@@ -73,23 +82,25 @@ static int ao_points_check(const ri_b200_ao_points_t *g)
 }
 
 // device-resident points -> device-resident counts, asynchronous on `st`.  Up to 2^24 rays are in flight at a time.
+template <typename Real>
 static int ao_points_run(ri_b200_accel *a, const ri_b200_ao_points_t *g, const double *d_points, uint64_t n, uint32_t *d_counts, cudaStream_t st)
 {
     using namespace b200;
+    constexpr size_t kRay = RayIO<Real>::kRayStride * sizeof(Real);
     const uint64_t N = (uint64_t)g->ntheta * (uint64_t)g->nphi;
     const AoPointsDev G = {g->ntheta, g->nphi, g->seed, g->eps};
     const uint64_t chunk_points = ((1ull << 24) / N) ? (1ull << 24) / N : 1;
     const uint64_t buf_points = n < chunk_points ? n : chunk_points;
     void *p = nullptr;
-    if (frame_buf(a, 10, buf_points * N * 8 * sizeof(float), &p)) return -1;
-    float *d_rays = (float *)p;
+    if (frame_buf(a, 10, buf_points * N * kRay, &p)) return -1;
+    Real *d_rays = (Real *)p;
     CUDA_OK(cudaMemsetAsync(d_counts, 0, n * sizeof(uint32_t), st));
     for (uint64_t p0 = 0; p0 < n; p0 += chunk_points) {
         const uint64_t np = (n - p0) < chunk_points ? (n - p0) : chunk_points, nr = np * N;
-        ao_points_gen_kernel<<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_points, p0, nr, d_rays);
+        ao_points_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_points, p0, nr, d_rays);
         LAUNCHED();
         CUDA_OK(cudaGetLastError());
-        if (launch_trace<float, true, false>(a, d_rays, nr, nullptr, nullptr, nullptr, st, d_counts + p0, (uint32_t)N)) return -1;
+        if (launch_trace<Real, true, false>(a, d_rays, nr, nullptr, nullptr, nullptr, st, d_counts + p0, (uint32_t)N)) return -1;
     }
     return 0;
 }
@@ -102,13 +113,28 @@ extern "C" int ri_b200_occlusion_points_dev_f32(ri_b200_accel_t *a, const ri_b20
     if (!n) return 0;
     std::lock_guard<std::mutex> lock(a->mu);               // the ray scratch buffer belongs to the accelerator
     CUDA_OK(cudaSetDevice(a->device));
-    return ao_points_run(a, g, d_points, n, d_occluded, stream ? (cudaStream_t)stream : a->stream);
+    return ao_points_run<float>(a, g, d_points, n, d_occluded, stream ? (cudaStream_t)stream : a->stream);
 }
 
-extern "C" int ri_b200_occlusion_points_f32(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, const double *points, uint64_t n, uint32_t *occluded_out)
+// the same call in the reference's own precision: double rays, the double reference's answer for every ray (through hybrid.cuh when
+// the fp32 records are resident too, else the double kernel)
+extern "C" int ri_b200_occlusion_points_dev_f64(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, const double *d_points, uint64_t n,
+                                                uint32_t *d_occluded, void *stream)
+{
+    if (need(a, RI_B200_PREC_F64) || ao_points_check(g)) return -1;
+    if (n && (!d_points || !d_occluded)) return fail("null argument");
+    if (!n) return 0;
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    return ao_points_run<double>(a, g, d_points, n, d_occluded, stream ? (cudaStream_t)stream : a->stream);
+}
+
+template <typename Real>
+static int ao_points_host(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, const double *points, uint64_t n, uint32_t *occluded_out)
 {
     using namespace b200;
-    if (need(a, RI_B200_PREC_F32) || ao_points_check(g)) return -1;
+    constexpr size_t kRay = RayIO<Real>::kRayStride * sizeof(Real);
+    if (need(a, sizeof(Real) == 4 ? RI_B200_PREC_F32 : RI_B200_PREC_F64) || ao_points_check(g)) return -1;
     if (n && (!points || !occluded_out)) return fail("null argument");
     if (!n) return 0;
     std::lock_guard<std::mutex> lock(a->mu);
@@ -127,8 +153,8 @@ extern "C" int ri_b200_occlusion_points_f32(ri_b200_accel_t *a, const ri_b200_ao
     double *d_points = (double *)p;
     if (frame_buf(a, 1, n * sizeof(uint32_t), &p)) return -1;
     uint32_t *d_counts = (uint32_t *)p;
-    if (frame_buf(a, 10, buf_points * N * 8 * sizeof(float), &p)) return -1;
-    float *d_rays = (float *)p;
+    if (frame_buf(a, 10, buf_points * N * kRay, &p)) return -1;
+    Real *d_rays = (Real *)p;
     CUDA_OK(cudaEventRecord(a->ev[6], ks));                       // whatever the accelerator's stream was doing comes first
     CUDA_OK(cudaStreamWaitEvent(cs, a->ev[6], 0));
     CUDA_OK(cudaMemsetAsync(d_counts, 0, n * sizeof(uint32_t), ks));
@@ -141,11 +167,12 @@ extern "C" int ri_b200_occlusion_points_f32(ri_b200_accel_t *a, const ri_b200_ao
             CUDA_OK(cudaMemcpyAsync(d_points + 6 * q0, points + 6 * q0, (q1 - q0) * 6 * sizeof(double), cudaMemcpyHostToDevice, cs));
             CUDA_OK(cudaEventRecord(a->ev[k & 3], cs));
             CUDA_OK(cudaStreamWaitEvent(ks, a->ev[k & 3], 0));
-            ao_points_gen_kernel<<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, ks>>>(G, d_points, q0, nr, d_rays + (q0 - p0) * N * 8);
+            ao_points_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, ks>>>(G, d_points, q0, nr,
+                                                                                                   d_rays + (q0 - p0) * N * RayIO<Real>::kRayStride);
             LAUNCHED();
             CUDA_OK(cudaGetLastError());
         }
-        if (launch_trace<float, true, false>(a, d_rays, np * N, nullptr, nullptr, nullptr, ks, d_counts + p0, (uint32_t)N)) return -1;
+        if (launch_trace<Real, true, false>(a, d_rays, np * N, nullptr, nullptr, nullptr, ks, d_counts + p0, (uint32_t)N)) return -1;
         if (p0 + chunk_points < n) {                              // the next chunk's generation overwrites the ray buffer: wait for this traversal
             CUDA_OK(cudaEventRecord(a->ev[7], ks));
             CUDA_OK(cudaStreamWaitEvent(cs, a->ev[7], 0));
@@ -155,6 +182,11 @@ extern "C" int ri_b200_occlusion_points_f32(ri_b200_accel_t *a, const ri_b200_ao
     CUDA_OK(cudaStreamSynchronize(ks));
     return 0;
 }
+
+extern "C" int ri_b200_occlusion_points_f32(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, const double *points, uint64_t n, uint32_t *occluded_out)
+{ return ao_points_host<float>(a, g, points, n, occluded_out); }
+extern "C" int ri_b200_occlusion_points_f64(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, const double *points, uint64_t n, uint32_t *occluded_out)
+{ return ao_points_host<double>(a, g, points, n, occluded_out); }
 
 // the generated batch itself, [n * ntheta * nphi][8] fp32 ray records on the HOST: what the call above traces (tests; resident-ray benchmarks)
 extern "C" int ri_b200_ao_point_rays_f32(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, const double *points, uint64_t n, float *rays_out)
@@ -178,7 +210,7 @@ extern "C" int ri_b200_ao_point_rays_f32(ri_b200_accel_t *a, const ri_b200_ao_po
     CUDA_OK(cudaMemcpyAsync(d_points, points, n * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
     for (uint64_t p0 = 0; p0 < n; p0 += chunk_points) {
         const uint64_t np = (n - p0) < chunk_points ? (n - p0) : chunk_points, nr = np * N;
-        ao_points_gen_kernel<<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_points, p0, nr, d_rays);
+        ao_points_gen_kernel<float><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_points, p0, nr, d_rays);
         LAUNCHED();
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaMemcpyAsync(rays_out + p0 * N * 8, d_rays, nr * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -2003,6 +2003,39 @@ uint64_t orc_splitmix64(uint64_t x)
  * dir = sum local[k] * basis[k] -- in double, rounded once to the fp32 ray record [ox oy oz 0 dx dy dz 1e38].  Builder-stated
  * substitutions, shared with the device: u0, u1 = the counter-based uniforms of scenes.uniform01 keyed by
  * (seed, point, j, i) in place of the sequential randomMT2 stream, and sin / cos by orc_det_sincos2pi in place of libm. */
+/* the same batch with NO rounding to fp32: [n*ntheta*nphi][6] doubles (org, dir) -- what calculate_occlusion traces in the reference's
+ * own precision; the double-exact point entry ri_b200_occlusion_points_f64 is checked against it */
+void orc_ao_point_rays_f64(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, double *rays_out)
+{
+    const uint64_t N = (uint64_t)ntheta * (uint64_t)nphi;
+    uint64_t p;
+    for (p = 0; p < n; p++) {
+        const double *pt = points + 6 * p;
+        double basis[3][3], nrm[3];
+        uint32_t i, j; int k;
+        for (k = 0; k < 3; k++) nrm[k] = pt[3 + k];
+        ortho_basis_f64(basis, nrm);
+        for (j = 0; j < (uint32_t)nphi; j++) {
+            for (i = 0; i < (uint32_t)ntheta; i++) {
+                const uint64_t kk = (uint64_t)j * (uint64_t)ntheta + i, idx = ((first_point + p) * N + kk) * 2;
+                const double u0 = (double)(orc_splitmix64(seed + idx * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+                const double u1 = (double)(orc_splitmix64(seed + (idx + 1) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+                const double z0 = ((double)i + u0) / (double)ntheta;
+                const double z1 = ((double)j + u1) / (double)nphi;
+                const double ct = sqrt(z0);
+                double sn, cs, lx, ly, lz;
+                double *o = rays_out + 6 * (p * N + kk);
+                orc_det_sincos2pi(z1, &sn, &cs);
+                lx = cs * ct; ly = sn * ct; lz = sqrt(1.0 - ct * ct);
+                for (k = 0; k < 3; k++) {
+                    o[k] = pt[k] + nrm[k] * eps;
+                    o[3 + k] = lx * basis[0][k] + ly * basis[1][k] + lz * basis[2][k];
+                }
+            }
+        }
+    }
+}
+
 void orc_ao_point_rays_f32(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, float *rays_out)
 {
     const uint64_t N = (uint64_t)ntheta * (uint64_t)nphi;

@@ -159,6 +159,7 @@ int orc_light_samples(const orc_tree *T, int nsamples, double angle, uint32_t se
                       const float *env, int ew, int eh, double *L_out, double *Cl_out, uint8_t *visible, uint64_t *nrays_out);
 void orc_det_sincos2pi(double r, double *s, double *c);
 /* ray batch of the point-based AO call (calculate_occlusion's ray set-up, ambientocclusion.c:56-117): [n*ntheta*nphi][8] floats */
+void orc_ao_point_rays_f64(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, double *rays_out);
 void orc_ao_point_rays_f32(const double *points, uint64_t n, uint64_t first_point, int ntheta, int nphi, uint64_t seed, double eps, float *rays_out);
 
 /* ---- material texture of the AO transport (ambientocclusion.c:393-401): radiance *= ri_texture_fetch(texture, st) per channel.

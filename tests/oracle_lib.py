@@ -445,6 +445,7 @@ class Oracle:
         lib.orc_point_gather_qmc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                              C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         lib.orc_ao_point_rays_f32.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_void_p]
+        lib.orc_ao_point_rays_f64.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_void_p]
         lib.orc_shade_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
         lib.orc_light_samples.restype = C.c_int
         lib.orc_light_samples.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
@@ -467,6 +468,14 @@ class Oracle:
         pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
         out = np.zeros((len(pts) * ntheta * nphi, 8), dtype=np.float32)
         self.lib.orc_ao_point_rays_f32(_ptr(pts), C.c_uint64(len(pts)), C.c_uint64(first_point), ntheta, nphi, C.c_uint64(seed),
+                                       C.c_double(eps), _ptr(out))
+        return out
+
+    def ao_point_rays_f64(self, points6: np.ndarray, ntheta: int, nphi: int, seed: int, eps: float = 1.0e-6, first_point: int = 0) -> np.ndarray:
+        """The same batch without the rounding to fp32 records: [n*N, 6] doubles (org, dir)."""
+        pts = np.ascontiguousarray(points6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros((len(pts) * ntheta * nphi, 6), dtype=np.float64)
+        self.lib.orc_ao_point_rays_f64(_ptr(pts), C.c_uint64(len(pts)), C.c_uint64(first_point), ntheta, nphi, C.c_uint64(seed),
                                        C.c_double(eps), _ptr(out))
         return out
 

@@ -136,3 +136,36 @@ def test_config4_ten_million_triangles():
     ao = dev.ao_point_rays(pts, 8, 8, scenes.SEED_C5)
     counts = dev.occlusion_points(pts, 8, 8, scenes.SEED_C5)
     assert np.array_equal(counts, orc.occluded_f32(ao).reshape(len(pts), 64).sum(axis=1).astype(np.uint32))
+
+
+def test_config2_hybrid_double_exact_occlusion_full_size():
+    """csrc/hybrid.cuh at BASELINE configs[2] size: 1 M triangles, 4 Mi double AO rays (origins P + 1e-6 N in full double).  The hybrid
+    kernel's verdicts equal the plain double kernel's on EVERY ray and the oracle's f64 instantiation on 300 000 rays sampled across the
+    batch; the double point entry's counts are the per-point sums of those verdicts."""
+    _need_gpu()
+    import os
+    import torch
+    NT, NP, N = 1_000_000, 65_536, 64
+    tris = scenes.triangle_soup(NT, scenes.SEED_C3)
+    a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64)
+    orc = ol.Oracle().build(tris)
+    pts = _primary_points(a, tris[a.triorder()], NP)
+    rays = ol.Oracle().ao_point_rays_f64(pts, 8, 8, scenes.SEED_C3)
+    assert len(rays) == NP * N
+    d_rays = torch.from_numpy(rays).cuda()
+    d_h = torch.empty(len(rays), dtype=torch.uint8, device="cuda")
+    d_p = torch.empty(len(rays), dtype=torch.uint8, device="cuda")
+    a.occluded_dev(d_rays, len(rays), d_h, f64=True)                        # hybrid (both record sets resident)
+    os.environ["B200_HYBRID"] = "0"
+    try:
+        a.occluded_dev(d_rays, len(rays), d_p, f64=True)                    # the plain double kernel
+    finally:
+        os.environ.pop("B200_HYBRID", None)
+    torch.cuda.synchronize()
+    assert torch.equal(d_h, d_p)
+    occ = d_h.cpu().numpy()
+    sample = np.sort(np.random.default_rng(5).choice(len(rays), 300_000, replace=False))
+    assert np.array_equal(occ[sample] != 0, orc.occluded_f64(rays[sample]) != 0)
+    counts = a.occlusion_points(pts, 8, 8, scenes.SEED_C3, f64=True)
+    assert np.array_equal(counts, occ.reshape(NP, N).sum(axis=1, dtype=np.uint32))
+    assert 0.5 < occ.mean() < 0.75
