@@ -375,7 +375,8 @@ def main():
     nrays = npoints * NTHETA * NPHI
     t0 = time.time()
     tris = scenes.triangle_soup(NTRIS, scenes.SEED_C3)
-    a = accel.Accel.bind(accel.RI_ACCEL_B200).build(tris, accel.PREC_F32, device=local_rank)
+    # both record sets: fp32 for the headline batch, double for the double-exact leg (hybrid.cuh reads both)
+    a = accel.Accel.bind(accel.RI_ACCEL_B200).build(tris, accel.PREC_F32 | accel.PREC_F64, device=local_rank)
     info = a.info()
     order = a.triorder()
     P, n = primary_points(a.intersect, tris[order])
@@ -467,6 +468,37 @@ def main():
     ms_c = timed(step_closest, csteps)
     closest = world * nrays * csteps / (ms_c * 1e-3) / 1e6
 
+    # the same batch as DOUBLE rays with the double reference's answer for every ray (what real, RIB-scale scenes need): through the
+    # fp32 records with certified decisions (csrc/hybrid.cuh) and, for comparison, through the double kernel alone
+    d_rays64 = torch.from_numpy(np.ascontiguousarray(rays_np[:, [0, 1, 2, 4, 5, 6]].astype(np.float64))).cuda()
+    d_occ_h = torch.empty((nrays,), dtype=torch.uint8, device="cuda")
+    d_occ_p = torch.empty((nrays,), dtype=torch.uint8, device="cuda")
+    step_hyb = lambda: a.occluded_dev(d_rays64, nrays, d_occ_h, stream, f64=True)      # noqa: E731
+    step_f64 = lambda: a.occluded_dev(d_rays64, nrays, d_occ_p, stream, f64=True)      # noqa: E731
+    dsteps = 3
+    step_hyb()
+    ms_h = timed(step_hyb, dsteps)
+    os.environ["B200_HYBRID"] = "0"
+    step_f64()
+    ms_p = timed(step_f64, dsteps)
+    os.environ.pop("B200_HYBRID", None)
+    h_cnt64 = torch.empty((npoints,), dtype=torch.int32, pin_memory=True)
+
+    def e2e64_step():
+        accel._check(a.lib.ri_b200_occlusion_points_f64(a.data, accel.C.byref(accel.AoPoints(NTHETA, NPHI, seed, 1.0e-6)), accel._ptr(h_pts.numpy()),
+                                                        npoints, accel._ptr(h_cnt64.numpy())))
+    e2e64_step()
+    e2e64_ms = wall(e2e64_step, dsteps)
+    double_exact = {
+        "what": "the same batch as double rays, the DOUBLE reference's verdict for every ray",
+        "hybrid_mrays_s": world * nrays * dsteps / (ms_h * 1e-3) / 1e6,
+        "double_kernel_mrays_s": world * nrays * dsteps / (ms_p * 1e-3) / 1e6,
+        "identical_verdicts": bool(torch.equal(d_occ_h, d_occ_p)),
+        "e2e_points_f64_mrays_s": world * nrays * dsteps / (e2e64_ms * 1e-3) / 1e6,
+        "api": "ri_b200_occluded_dev_f64 / ri_b200_occlusion_points_f64 (host points in, double rays generated + traced on the device, counts out)",
+    }
+    del d_rays64, d_occ_h, d_occ_p
+
     # end to end through the reference-facing host call: calculate_occlusion for the batch's shading points.  Pinned host points in,
     # occluded-ray counts out; the rays are generated and traced on the device inside the call.
     par = accel.AoPoints(NTHETA, NPHI, seed, 1.0e-6)
@@ -531,7 +563,8 @@ def main():
             "config": {"workload": WORKLOAD, "kernel": "occlusion (any-hit) traversal, reference-identical binary BVH, leaf<=16",
                        "rays_per_gpu_per_step": nrays, "ntris": NTRIS, "inner_nodes": int(info.ninner), "depth": int(info.max_depth),
                        "l2": "ray batch (512 MiB) exceeds L2 every step; scene records (54 MB) are L2-resident by nature of the workload",
-                       "closest_hit_mrays_s": closest, "occluded_fraction": float(occ_host.mean()), "frames": frames},
+                       "closest_hit_mrays_s": closest, "double_exact": double_exact, "occluded_fraction": float(occ_host.mean()),
+                       "frames": frames},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": world * npoints * 48, "d2h_bytes_per_step": world * npoints * 4,
                     "ms_per_step": e2e_ms / esteps,
