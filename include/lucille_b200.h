@@ -428,6 +428,12 @@ int ri_b200_render_pathtrace_tiles_dev(ri_b200_accel_t *accel, const ri_b200_pat
  * accel == NULL: one CTA walks the stream on `device`; accel != NULL: the frame path -- window states at segment starts
  * by GF(2) jump-ahead (doubling tree, cached per seed in the accelerator), then one CTA per 638 976-word segment. */
 int ri_b200_mt_stream(ri_b200_accel_t *accel, uint32_t seed, uint64_t n, uint32_t *out_u32, int device);
+/* Optional warm-up: every entry point that draws from the reference's MT19937 stream (frames with rng_mode 0, ri_b200_gather_points_f64,
+ * ri_b200_light_samples_f64) generates the stream in parallel from a table of generator states at segment starts, built by GF(2)
+ * jump-ahead on first use and cached per (accelerator, seed).  Building it costs about 5 ms per doubling of the stream length beyond
+ * 638 976 words; this call builds it ahead of time for streams of up to max_words words, asynchronously on the accelerator's stream
+ * (lucille seeds its generators once, 4357: call it once after ri_b200_build). */
+int ri_b200_mt_prepare(ri_b200_accel_t *accel, uint32_t seed, uint64_t max_words);
 
 #ifdef __cplusplus
 }

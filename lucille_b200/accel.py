@@ -173,6 +173,7 @@ ABI = [
     ("ri_b200_render_pathtrace", _I, [_P, _P, _P, _P]),
     ("ri_b200_render_pathtrace_tiles_dev", _I, [_P, _P, _P, _P, _P]),
     ("ri_b200_mt_stream", _I, [_P, _U32, _U64, _P, _I]),
+    ("ri_b200_mt_prepare", _I, [_P, _U32, _U64]),
 ]
 
 _lib = None
@@ -523,6 +524,11 @@ class Accel:
         nrays = C.c_uint64(0)
         _check(self.lib.ri_b200_gather_points_f64(self._h(), C.byref(g), _ptr(pts), len(pts), _ptr(out), C.byref(nrays)))
         return out, nrays.value
+
+    def mt_prepare(self, max_words: int, seed: int = 4357) -> "Accel":
+        """Build the jump-ahead state table of the MT19937 stream ahead of the first call that needs it (ri_b200_mt_prepare)."""
+        _check(self.lib.ri_b200_mt_prepare(self._h(), int(seed), int(max_words)))
+        return self
 
     def shade_trace(self, pr6, env=None) -> np.ndarray:
         """The trace() shadeop (shader.c:895-976) for (P, R) pairs up to the call of the hit surface's shader procedure

@@ -334,13 +334,13 @@ static void launch_closest32_cap(ri_b200_accel *a, const float *d_rays, uint32_t
 {
     auto kern = closest_pool32_kernel<kCap>;
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCloseThreads, 0);
     if (per_sm < 1) per_sm = 1;
     const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
     uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
-    want = (want + (kBlock / 32) - 1) / (kBlock / 32);
+    want = (want + (kCloseThreads / 32) - 1) / (kCloseThreads / 32);
     const unsigned blocks = (unsigned)(want < capb ? want : capb);
-    kern<<<blocks, kBlock, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_hits, ctr, make_pack_k());
+    kern<<<blocks, kCloseThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_hits, ctr, make_pack_k());
 }
 static bool launch_closest32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st)
 {

@@ -668,15 +668,10 @@ static int frame_buf(ri_b200_accel *a, int slot, uint64_t bytes, void **out)
     return 0;
 }
 
-// The whole stream in parallel: window states at every segment start come from the doubling tree of jumps
-// (log2(segments) launches, cached per seed in the accelerator), then one CTA per segment regenerates its blocks.
-static int mt_stream_launch(ri_b200_accel *a, uint32_t seed, uint32_t segments, uint64_t total_blocks, uint32_t *d_out, cudaStream_t st)
+// window states at the first `segments` segment starts of the stream seeded `seed`, cached in the accelerator (rebuilt only for
+// another seed or a longer stream): log2(capacity) dependent launches, each one Horner pass over a 19937-term jump polynomial
+static int mt_states_ensure(ri_b200_accel *a, uint32_t seed, uint32_t segments, cudaStream_t st)
 {
-    if (segments <= 1) {
-        mt_kernel<<<1, 256, 0, st>>>(seed, nullptr, total_blocks, total_blocks, d_out);
-        LAUNCHED();
-        return 0;
-    }
     if (segments > (1u << kMtJumpPolys)) return fail("MT19937 stream too long for the jump table (%u segments)", segments);
     if (!a->d_mt_polys) {
         CUDA_OK(cudaMalloc((void **)&a->d_mt_polys, sizeof(kMtJumpPoly)));
@@ -702,10 +697,39 @@ static int mt_stream_launch(ri_b200_accel *a, uint32_t seed, uint32_t segments, 
         }
         a->mt_states_seed = seed;
     }
+    return 0;
+}
+
+// The whole stream in parallel: window states at every segment start come from the doubling tree of jumps
+// (log2(segments) launches, cached per seed in the accelerator), then one CTA per segment regenerates its blocks.
+static int mt_stream_launch(ri_b200_accel *a, uint32_t seed, uint32_t segments, uint64_t total_blocks, uint32_t *d_out, cudaStream_t st)
+{
+    if (segments <= 1) {
+        mt_kernel<<<1, 256, 0, st>>>(seed, nullptr, total_blocks, total_blocks, d_out);
+        LAUNCHED();
+        return 0;
+    }
+    if (mt_states_ensure(a, seed, segments, st)) return -1;
     mt_kernel<<<segments, 256, 0, st>>>(seed, a->d_mt_states, (uint64_t)kMtSegBlocks, total_blocks, d_out);
     LAUNCHED();
     CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// One-time cost made explicit: a caller that knows it will draw up to `max_words` words of the stream seeded `seed` (every frame and
+// gather entry point with rng_mode 0 / the MT19937 gathers) pays for the window-state table here, asynchronously on the
+// accelerator's stream, instead of inside its first big call (about 5 ms per doubling of the stream length beyond 638 976 words).
+extern "C" int ri_b200_mt_prepare(ri_b200_accel_t *a, uint32_t seed, uint64_t max_words)
+{
+    if (!a) return fail("null argument");
+    if (a->device < 0) return fail("host-only accelerator: no device records, no CPU fallback");
+    std::lock_guard<std::mutex> lock(a->mu);
+    CUDA_OK(cudaSetDevice(a->device));
+    const uint64_t blocks = (max_words + kMtN - 1) / kMtN;
+    const uint64_t segments = (blocks + kMtSegBlocks - 1) / kMtSegBlocks;
+    if (segments <= 1) return 0;
+    if (segments > (1ull << kMtJumpPolys)) return fail("MT19937 stream too long for the jump table (%llu segments)", (unsigned long long)segments);
+    return mt_states_ensure(a, seed, (uint32_t)segments, a->stream);
 }
 
 template <typename Real>

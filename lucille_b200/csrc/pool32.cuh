@@ -269,9 +269,13 @@ struct Close32Warp {
     float4 leaf[32];                     // per lane: the leaf-local winner so far (t, u, v, prim bits); its t is also in a register
     float4 best[32];                     // per lane: the committed closest hit so far; its t is also in a register
 };
+#ifndef B200_CLOSE_THREADS
+#define B200_CLOSE_THREADS 128
+#endif
+constexpr int kCloseThreads = B200_CLOSE_THREADS;      // CTA size of the closest-hit kernel (A/B knob with B200_CLOSE_CTAS)
 template <int kCap> struct Close32Smem {
-    uint32_t    stack[kCap * kBlock];
-    Close32Warp warp[kBlock / 32];
+    uint32_t    stack[kCap * kCloseThreads];
+    Close32Warp warp[kCloseThreads / 32];
 };
 __device__ __forceinline__ void atom_min_shared_u64(uint32_t a, unsigned long long v)
 { asm volatile("red.shared.min.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
@@ -279,18 +283,21 @@ __device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) { asm 
 __device__ __forceinline__ unsigned long long lds_u64(uint32_t a)
 { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
 
-// 3 CTAs per SM at 80 registers: measured 892 Mrays/s on the C3 batch against 838 with 4 CTAs at 64 registers (spills)
+// Occupancy, measured on the C3 batch (scripts/gpu_r2u.sh): CTAs of 128 threads, 7 per SM at 72 registers (28 warps, no spills):
+// 944 Mrays/s; 256 x 3 at 77 registers (24 warps): 892; 128 x 6 and 192 x 4 (24 warps): 891 / 892; 256 x 4 and 128 x 8 at 64
+// registers (32 warps, spills): 838 / 837.  The kernel waits on memory with 61 % of its issue slots used: warps in flight are what
+// it is short of, until the register allocation starts to spill.
 #ifndef B200_CLOSE_CTAS
-#define B200_CLOSE_CTAS 3
+#define B200_CLOSE_CTAS 7
 #endif
 template <int kCap>
-__global__ void __launch_bounds__(kBlock, B200_CLOSE_CTAS)
+__global__ void __launch_bounds__(kCloseThreads, B200_CLOSE_CTAS)
 closest_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
                       const uint32_t chunk, ri_b200_hit_f32 *__restrict__ hits_out, unsigned int *__restrict__ work_counter, const PackK K)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr uint32_t kRefillAt = 4u;
-    constexpr uint32_t kRow = kBlock * 4u;
+    constexpr uint32_t kRow = kCloseThreads * 4u;
     __shared__ __align__(16) Close32Smem<kCap> sm;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;

@@ -34,7 +34,10 @@ for it in range(3):
     a.occluded_dev(d32, nr, occ, st.cuda_stream)
     a.intersect_dev(d32, nr, h32, st.cuda_stream)
     if what == "c3":
-        a.occluded_dev(d64, nr, occ, st.cuda_stream, f64=True)
+        a.occluded_dev(d64, nr, occ, st.cuda_stream, f64=True)            # both record sets resident: hybrid.cuh
+        os.environ["B200_HYBRID"] = "0"
+        a.occluded_dev(d64, nr, occ, st.cuda_stream, f64=True)            # the plain double kernel
+        os.environ.pop("B200_HYBRID")
         a.intersect_dev(d64, nr, h64, st.cuda_stream, f64=True)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()

@@ -43,6 +43,7 @@ rays = scenes.rays_f32_to_f64(scenes.pinhole_rays(512, 512))
 h = a.intersect(rays); s = a.state(rays, h); m = h["hit"] == 1
 pts = np.concatenate([s["P"][m][:, :3], s["Ns"][m][:, :3]], axis=1)
 for kind, name in ((accel.GATHER_OCCLUSION, "occlusion() shadeop"), (accel.GATHER_IBL, "ibl cosweight"), (accel.GATHER_DOME, "dome light")):
+    a.mt_prepare(2 * 48 * len(pts))                                          # the stream's state table: once per (accelerator, seed)
     a.gather_points(kind, 48, pts[:1000], env)
     t0 = time.perf_counter(); out, n = a.gather_points(kind, 48, pts, env); dt = time.perf_counter() - t0
     print(f"gather {name:26s} {len(pts)} points x 48: {n/1e6:7.1f} Mrays {dt*1e3:9.2f} ms  {n/dt/1e6:8.1f} Mrays/s (host call incl. copies)", flush=True)
