@@ -170,7 +170,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sampled": True},
+        "config": {"workload": WORKLOAD, "kernel": "occlusion (any-hit) traversal, reference-identical binary BVH, leaf<=16",
+                   "rays_per_gpu_per_step": NRAYS, "ntris": NTRIS, "sampled": True,
+                   "sample": "each step traces a bounded sample of the batch (see cpu_baseline.sample): the rate is per ray"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample, "single_thread": single,
                          "baseline_kernel": BASELINE_KERNEL[kind]},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -229,13 +229,13 @@ static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m
     auto kern = closest_pool_kernel<Real>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPcThreads, smem);
     if (per_sm < 1) per_sm = 1;
     const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
     uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
-    want = (want + (kBlock / 32) - 1) / (kBlock / 32);
+    want = (want + (kPcThreads / 32) - 1) / (kPcThreads / 32);
     const unsigned blocks = (unsigned)(want < capb ? want : capb);
-    kern<<<blocks, kBlock, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays, m, chunk, d_hits, ctr, refill_at, (uint32_t)cap, make_pack_k());
+    kern<<<blocks, kPcThreads, smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays, m, chunk, d_hits, ctr, refill_at, (uint32_t)cap, make_pack_k());
 }
 
 // pool32.cuh: fp32 occlusion with static shared memory.  Returns false when it does not apply (fp64 records, a tree deeper than

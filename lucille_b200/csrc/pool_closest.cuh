@@ -51,12 +51,22 @@ template <> struct PoolRes<double> { double t, u, v; uint32_t prim, pad; };
 __device__ __forceinline__ unsigned long long abs_bits(float t)  { return (unsigned long long)(__float_as_uint(t) & 0x7fffffffu); }
 __device__ __forceinline__ unsigned long long abs_bits(double t) { return (unsigned long long)__double_as_longlong(t) & 0x7fffffffffffffffull; }
 
+// CTA size / CTAs per SM of this kernel (A/B knobs; the fp32 default path is pool32.cuh's specialised kernel).  Double records, C3
+// batch (scripts/gpu_r2v.sh): 128 threads x 5 CTAs at 96 registers (20 warps): 425 Mrays/s; 256 x 2 at 110 registers (16 warps):
+// 382; 128 x 4 at 110: 384; 128 x 6 and 256 x 3 at 80 registers (24 warps, spills): 364.
+#ifndef B200_PC_THREADS
+#define B200_PC_THREADS 128
+#endif
+#ifndef B200_PC64_CTAS
+#define B200_PC64_CTAS 5
+#endif
+constexpr int kPcThreads = B200_PC_THREADS;
 template <typename Real> constexpr size_t pool_closest_smem_bytes(int stack_cap)
-{ return (size_t)stack_cap * kBlock * sizeof(uint32_t) + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(PoolRes<Real>) + sizeof(uint32_t)); }
+{ return (size_t)stack_cap * kPcThreads * sizeof(uint32_t) + (size_t)kPcThreads * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(PoolRes<Real>) + sizeof(uint32_t)); }
 
 // fp32: 3 CTAs x 256 threads per SM at 79 registers: measured 909 Mrays/s on the C3 batch against 877 with 4 CTAs at 64 (spills)
 template <typename Real>
-__global__ void __launch_bounds__(kBlock, sizeof(Real) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(kPcThreads, sizeof(Real) == 4 ? (768 / kPcThreads) : B200_PC64_CTAS)
 closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, const Real *__restrict__ rays, const uint32_t n,
                     const uint32_t chunk, typename RayIO<Real>::Hit *__restrict__ hits_out, unsigned int *__restrict__ work_counter,
                     const uint32_t refill_at, const uint32_t stack_cap, const PackK K)
@@ -64,16 +74,16 @@ closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, con
     using P = Prec<Real>;
     using L = PoolLeaf<Real>;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) uint32_t s_stack[];  // [stack_cap][kBlock] words, ray slots, descriptors, keys, results
+    extern __shared__ __align__(16) uint32_t s_stack[];  // [stack_cap][kPcThreads] words, ray slots, descriptors, keys, results
     uint32_t *stk = s_stack + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
-    char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kBlock);
+    char *s_tail = reinterpret_cast<char *>(s_stack + (size_t)stack_cap * kPcThreads);
     char *s_rays = s_tail + (size_t)wbase * RaySlot<Real>::kBytes;
-    uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kBlock * RaySlot<Real>::kBytes) + wbase;
-    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2))) + wbase;
-    PoolRes<Real> *s_res = reinterpret_cast<PoolRes<Real> *>(s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long))) + wbase;
-    uint32_t *s_win = reinterpret_cast<uint32_t *>(s_tail + (size_t)kBlock * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(PoolRes<Real>))) + wbase;
+    uint2 *s_desc = reinterpret_cast<uint2 *>(s_tail + (size_t)kPcThreads * RaySlot<Real>::kBytes) + wbase;
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_tail + (size_t)kPcThreads * (RaySlot<Real>::kBytes + sizeof(uint2))) + wbase;
+    PoolRes<Real> *s_res = reinterpret_cast<PoolRes<Real> *>(s_tail + (size_t)kPcThreads * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long))) + wbase;
+    uint32_t *s_win = reinterpret_cast<uint32_t *>(s_tail + (size_t)kPcThreads * (RaySlot<Real>::kBytes + sizeof(uint2) + sizeof(unsigned long long) + sizeof(PoolRes<Real>))) + wbase;
 
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = false;
@@ -190,7 +200,7 @@ closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, con
                         best_t = commit ? tl : best_t; best_u = commit ? ul : best_u; best_v = commit ? vl : best_v;
                         best_prim = commit ? tprim : best_prim;
                         if (sp == 0u) { retire(); cur = kIdle; }
-                        else { --sp; enter(stk[sp * kBlock]); }
+                        else { --sp; enter(stk[sp * kPcThreads]); }
                     }
                 }
                 __syncwarp();                    // s_key / s_res are rewritten by the next round
@@ -211,8 +221,8 @@ closest_pool_kernel(const SceneView<Real> S, const char *__restrict__ trisT, con
                 const bool order = (axis == 0) ? sx : ((axis == 1) ? sy : sz);
                 const bool both = h0 && h1, none = !h0 && !h1;
                 const bool pop = none && (sp != 0u);
-                if (both) stk[sp * kBlock] = order ? c0 : c1;
-                const uint32_t popped = pop ? stk[(sp - 1u) * kBlock] : kIdle;
+                if (both) stk[sp * kPcThreads] = order ? c0 : c1;
+                const uint32_t popped = pop ? stk[(sp - 1u) * kPcThreads] : kIdle;
                 sp = sp + (both ? 1u : 0u) - (pop ? 1u : 0u);
                 const uint32_t one = h0 ? c0 : c1;
                 const uint32_t next = both ? (order ? c1 : c0) : (none ? popped : one);

@@ -72,4 +72,24 @@ th = [threading.Thread(target=run, args=(r,)) for r in (0, 1)]
 [t.start() for t in th]; [t.join() for t in th]
 one, _ = c1.render_ao(accel.make_frame(cam[:16], cam[16], bool(cam[17]), 70, 40, 2, 2, gather_nsamples=16))
 print("shared stream equal:", bool(np.array_equal(res[0] + res[1], one)))
+# round 2: the double-exact hybrid occlusion kernel (fp32-representable and not; forced where the dispatcher would decline), the
+# double routines it calls on undecided decisions (rays aimed at vertices and along axes), the point entries, the shade callers
+os.environ["B200_HYBRID"] = "2"
+for name, tt in (("exact", tris), ("inexact", tris * 1.1 + np.array([0.3, -0.2, 0.1])), ("far", tris * 3.7 + np.array([1000.0, -800.0, 400.0]))):
+    h = accel.Accel.bind().build(tt, accel.PREC_F32 | accel.PREC_F64)
+    lo, hi = tt.reshape(-1, 3).min(axis=0), tt.reshape(-1, 3).max(axis=0)
+    rng = np.random.default_rng(2)
+    org = lo + (hi - lo) * rng.uniform(-0.3, 1.3, (6000, 3))
+    aim = tt.reshape(-1, 3)[rng.integers(0, 9000, 6000)]
+    r = np.concatenate([org, aim - org], axis=1)
+    r[::5, 3:6] = [0.0, 0.0, 1.0]
+    occ = h.occluded(np.ascontiguousarray(r))
+    pts6 = np.concatenate([org[:300], np.tile([0.0, 0.0, 1.0], (300, 1))], axis=1)
+    print("hybrid", name, int(occ.sum()), int(h.occlusion_points(pts6, 4, 4, 7, f64=True).sum()), int(h.occlusion_points(pts6, 4, 4, 7).sum()))
+os.environ.pop("B200_HYBRID", None)
+pr = np.concatenate([pts[:, :3], np.random.default_rng(3).normal(size=(200, 3))], axis=1)
+rec = a.shade_trace(pr, env); print("shade_trace", int(rec["hit"].sum()), float(rec["Ci"].sum()))
+a.mt_prepare(1 << 21)
+L, Cl, vis, nr = a.light_samples(48, 1.2, pts, env); print("light_samples", int(vis.sum()), nr)
+L, Cl, vis, nr = a.light_samples(48, 1.2, np.tile(pts, (40, 1)), env); print("light_samples (jump table)", int(vis.sum()), nr)
 print("done")
