@@ -286,6 +286,7 @@ def frame_leg(args, rank, world, local_rank, torch, dist):
     distributed.render_ao_distributed_peer(a, fr, fb)                                           # warm-up (allocations, first launches)
     wall_p, (rgb_p, st_p) = _wall_max(lambda: distributed.render_ao_distributed_peer(a, fr, fb), world, dist, torch)
     dev_p, nrays = gather_stats(st_p)
+    distributed.render_ao_distributed(a, fr, rank, world)                                       # warm-up of this arm too (pixel lists, NCCL buffers)
     wall_n, (rgb_n, st_n) = _wall_max(lambda: distributed.render_ao_distributed(a, fr, rank, world), world, dist, torch)
     dev_n, _ = gather_stats(st_n)
     fb.close()
