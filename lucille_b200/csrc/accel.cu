@@ -218,12 +218,15 @@ template <int kCap>
 static void launch_closest32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st);
 static bool launch_closest32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f32 *d_hits, unsigned int *ctr, cudaStream_t st);
 static bool launch_closest32(ri_b200_accel *, const double *, uint32_t, uint32_t, ri_b200_hit_f64 *, unsigned int *, cudaStream_t) { return false; }
+static bool launch_closest_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f64 *d_hits, unsigned int *ctr, cudaStream_t st);
+static bool launch_closest_hybrid(ri_b200_accel *, const float *, uint32_t, uint32_t, ri_b200_hit_f32 *, unsigned int *, cudaStream_t);
 
 template <typename Real>
 static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m, uint32_t chunk, typename RayIO<Real>::Hit *d_hits,
                                 unsigned int *ctr, uint32_t refill_at, cudaStream_t st)
 {
     if (launch_closest32(a, d_rays, m, chunk, d_hits, ctr, st)) return;       // fp32 on a tree that fits a static stack: pool32.cuh
+    if (launch_closest_hybrid(a, d_rays, m, chunk, d_hits, ctr, st)) return;  // double rays, both record sets resident: hybrid.cuh
     const int cap = stack_capacity(a);
     const size_t smem = pool_closest_smem_bytes<Real>(cap);
     auto kern = closest_pool_kernel<Real>;
@@ -268,9 +271,26 @@ static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, u
 
 // hybrid.cuh: double-exact occlusion through the fp32 records with certified decisions, the double records only where fp32 cannot
 // decide.  Applies to double rays when BOTH record sets are resident and the tree fits a static stack; B200_HYBRID=0 turns it off.
-template <int kCap>
-static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
-                              uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+static bool hybrid_applies(const ri_b200_accel *a)
+{
+    const char *env = getenv("B200_HYBRID");                      // read per launch: tests and A/B scripts switch it inside one process
+    const int mode = env ? atoi(env) : 1;                         // 0: never, 1: where it pays, 2: whenever possible
+    if (mode == 0 || stack_capacity(a) > 28 || !a->d_nodes32 || !a->d_tris32t || !a->d_nodes64 || !a->d_tris64) return false;
+    // The fp32 records hold ABSOLUTE coordinates, so the error bounds grow with the scene's distance from the origin while the
+    // intervals they are compared with shrink with its size: far from the origin most decisions fall back to doubles and the double
+    // kernel is faster (measured: coordinates ~ 1000 on a scene of size 4: 386 against 504 Mrays/s; at the origin: 916 against 491).
+    if (mode == 1) {
+        double far = 0.0, ext = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            far = std::fmax(far, std::fmax(std::fabs(a->tree.bmin[k]), std::fabs(a->tree.bmax[k])));
+            ext = std::fmax(ext, a->tree.bmax[k] - a->tree.bmin[k]);
+        }
+        if (!(far <= 4.0 * ext)) return false;
+    }
+    return true;
+}
+
+static HybK hybrid_consts(const ri_b200_accel *a)
 {
     HybK H;
     float bm = 0.0f;
@@ -280,6 +300,43 @@ static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m
     }
     H.eta0 = a->verts_f32 ? 0.0f : 5.9604645e-8f * bm;
     H.de = 2.0f * H.eta0;
+    return H;
+}
+
+// double-exact closest hit through the fp32 records (hybrid.cuh, second kernel)
+template <int kCap>
+static void launch_closest_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f64 *d_hits, unsigned int *ctr, cudaStream_t st)
+{
+    const size_t smem = sizeof(HybCSmem<kCap>);
+    const HybK H = hybrid_consts(a);
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHcThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
+        uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
+        want = (want + (kHcThreads / 32) - 1) / (kHcThreads / 32);
+        const unsigned blocks = (unsigned)(want < capb ? want : capb);
+        kern<<<blocks, kHcThreads, smem, st>>>(make_view<float>(a), make_view<double>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_hits, ctr, make_pack_k(), H);
+    };
+    if (a->verts_f32) go(closest_hybrid_kernel<kCap, true>); else go(closest_hybrid_kernel<kCap, false>);
+}
+static bool launch_closest_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f64 *d_hits, unsigned int *ctr, cudaStream_t st)
+{
+    const char *env = getenv("B200_HYBRID_CLOSEST");
+    if ((env && atoi(env) == 0) || !hybrid_applies(a)) return false;
+    if (stack_capacity(a) <= 20) launch_closest_hybrid_cap<20>(a, d_rays, m, chunk, d_hits, ctr, st);
+    else launch_closest_hybrid_cap<28>(a, d_rays, m, chunk, d_hits, ctr, st);
+    return true;
+}
+static bool launch_closest_hybrid(ri_b200_accel *, const float *, uint32_t, uint32_t, ri_b200_hit_f32 *, unsigned int *, cudaStream_t) { return false; }
+
+template <int kCap>
+static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
+                              uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+{
+    const HybK H = hybrid_consts(a);
     const SceneView<float> S = make_view<float>(a);
     const SceneView<double> S64 = make_view<double>(a);
     const char *tt = pool_tris(a, 0.0f);
@@ -295,21 +352,9 @@ static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m
 static bool launch_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
                           uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned, cudaStream_t st)
 {
-    const char *env = getenv("B200_HYBRID");                      // read per launch: tests and A/B scripts switch it inside one process
-    const int mode = env ? atoi(env) : 1;                         // 0: never, 1: where it pays, 2: whenever possible
+    if (!hybrid_applies(a)) return false;
     const int cap = stack_capacity(a);
-    if (mode == 0 || cap > 28 || !a->d_nodes32 || !a->d_tris32t || !a->d_nodes64 || !a->d_tris64) return false;
-    // The fp32 records hold ABSOLUTE coordinates, so the error bounds grow with the scene's distance from the origin while the
-    // intervals they are compared with shrink with its size: far from the origin most decisions fall back to doubles and the double
-    // kernel is faster (measured: coordinates ~ 1000 on a scene of size 4: 386 against 504 Mrays/s; at the origin: 916 against 491).
-    if (mode == 1) {
-        double far = 0.0, ext = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            far = std::fmax(far, std::fmax(std::fabs(a->tree.bmin[k]), std::fabs(a->tree.bmax[k])));
-            ext = std::fmax(ext, a->tree.bmax[k] - a->tree.bmin[k]);
-        }
-        if (!(far <= 4.0 * ext)) return false;
-    }
+
     auto blocks_for = [&](const void *kern, size_t smem) -> unsigned {
         int per_sm = 0;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

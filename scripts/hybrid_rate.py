@@ -54,6 +54,11 @@ for v in variants:
         ms32 = ev(lambda: hyb.occluded_dev(d32, nr, o32, st.cuda_stream))
         line += f" | fp32 records {nr / ms32 / 1e3:.1f} Mrays/s, differ from double on {float((o32 != o_p).float().mean()):.2e} of the rays"
     print(line, flush=True)
+    h_h = torch.empty((nr, 4), dtype=torch.float64, device="cuda"); h_p = torch.empty((nr, 4), dtype=torch.float64, device="cuda")
+    ms_ch = ev(lambda: hyb.intersect_dev(d64, nr, h_h, st.cuda_stream, f64=True))
+    ms_cp = ev(lambda: plain.intersect_dev(d64, nr, h_p, st.cuda_stream, f64=True))
+    same_c = bool(torch.equal(h_h.view(torch.int64), h_p.view(torch.int64)))
+    print(f"{v:8s} closest hit: hybrid {ms_ch:.3f} ms = {nr / ms_ch / 1e3:.1f} Mrays/s | plain f64 {ms_cp:.3f} ms = {nr / ms_cp / 1e3:.1f} Mrays/s | identical records {same_c}", flush=True)
     if not same:
         bad = torch.nonzero(o_h != o_p).flatten()[:5].cpu().numpy()
         print("  MISMATCH at rays", bad, "hybrid", o_h[bad].cpu().numpy(), "plain", o_p[bad].cpu().numpy())

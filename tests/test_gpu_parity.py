@@ -889,8 +889,8 @@ def test_shade_callers(oracle, golden_dir):
 
 @pytest.mark.parametrize("case", ["soup", "soup_inexact", "soup_far", "box_city", "box_city_inexact"])
 def test_hybrid_occlusion_is_fp64_exact(case):
-    """csrc/hybrid.cuh: with both record sets resident, double occlusion queries run through the fp32 records with certified
-    decisions and the double records only where fp32 cannot decide.  The answer is the DOUBLE reference's for every ray: against the
+    """csrc/hybrid.cuh: with both record sets resident, double occlusion AND closest-hit queries run through the fp32 records with
+    certified decisions and the double records only where fp32 cannot decide.  The answer is the DOUBLE reference's for every ray: against the
     oracle's f64 instantiation and against the plain double kernel (an accelerator holding double records only), on
       soup              fp32-representable vertices (no absolute error in the fp32 slots)
       soup_inexact      the same soup scaled and shifted in double: vertices are not fp32 numbers
@@ -935,6 +935,12 @@ def test_hybrid_occlusion_is_fp64_exact(case):
             assert np.array_equal(got, want), (case, name, int((got != want).sum()))
             assert np.array_equal(plain.occluded(rays), want), (case, name)
             assert 0.02 < want.mean() < 0.999 or name == "axis", (case, name, want.mean())
+            # closest hit through the same filter (closest_hybrid_kernel): every field of every record is the double reference's
+            hw = ot.intersect_f64(rays)
+            for acc in (hyb, plain):
+                h = acc.intersect(rays)
+                for f in ("hit", "prim", "t", "u", "v"):
+                    assert np.array_equal(h[f], hw[f]), (case, name, f, acc is hyb, int((h[f] != hw[f]).sum()))
         # the point entry in the reference's own precision: counts == the oracle's double rays through its double traversal
         pts = np.concatenate([cam[::8, 0:3], cam[::8, 3:6]], axis=1)[:3000]
         cnt = hyb.occlusion_points(pts, 4, 4, 99, eps=1.0e-6, f64=True)
