@@ -485,6 +485,18 @@ def main():
     step_f64()
     ms_p = timed(step_f64, dsteps)
     os.environ.pop("B200_HYBRID", None)
+    d_h64a = torch.empty((nrays, 4), dtype=torch.float64, device="cuda")
+    d_h64b = torch.empty((nrays, 4), dtype=torch.float64, device="cuda")
+    step_ch = lambda: a.intersect_dev(d_rays64, nrays, d_h64a, stream, f64=True)       # noqa: E731
+    step_cp = lambda: a.intersect_dev(d_rays64, nrays, d_h64b, stream, f64=True)       # noqa: E731
+    step_ch()
+    ms_ch = timed(step_ch, dsteps)
+    os.environ["B200_HYBRID_CLOSEST"] = "0"
+    step_cp()
+    ms_cp = timed(step_cp, dsteps)
+    os.environ.pop("B200_HYBRID_CLOSEST", None)
+    closest_identical = bool(torch.equal(d_h64a.view(torch.int64), d_h64b.view(torch.int64)))
+    del d_h64a, d_h64b
     h_cnt64 = torch.empty((npoints,), dtype=torch.int32, pin_memory=True)
 
     def e2e64_step():
@@ -497,6 +509,9 @@ def main():
         "hybrid_mrays_s": world * nrays * dsteps / (ms_h * 1e-3) / 1e6,
         "double_kernel_mrays_s": world * nrays * dsteps / (ms_p * 1e-3) / 1e6,
         "identical_verdicts": bool(torch.equal(d_occ_h, d_occ_p)),
+        "closest_hit_hybrid_mrays_s": world * nrays * dsteps / (ms_ch * 1e-3) / 1e6,
+        "closest_hit_double_kernel_mrays_s": world * nrays * dsteps / (ms_cp * 1e-3) / 1e6,
+        "closest_hit_identical_records": closest_identical,
         "e2e_points_f64_mrays_s": world * nrays * dsteps / (e2e64_ms * 1e-3) / 1e6,
         "api": "ri_b200_occluded_dev_f64 / ri_b200_occlusion_points_f64 (host points in, double rays generated + traced on the device, counts out)",
     }

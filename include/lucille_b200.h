@@ -30,10 +30,12 @@ extern "C" {
 
 #define RI_B200_PREC_F32       1u            /* fp32 node/triangle records: the throughput path */
 #define RI_B200_PREC_F64       2u            /* double records: bit-identical to the CPU reference */
-/* With BOTH record sets resident, double OCCLUSION queries (ri_b200_occluded_*_f64, the AO / sun-sky / point gathers of double frames)
- * run through the fp32 records with a certified error bound on every box and triangle decision and consult the double records only
- * for the decisions fp32 cannot settle (csrc/hybrid.cuh): the double reference's answer for every ray at close to the fp32 rate.
- * B200_HYBRID=0 in the environment turns this off (the double kernel runs instead), =2 forces it for scenes far from the origin too. */
+/* With BOTH record sets resident, batched double queries -- occlusion (ri_b200_occluded_*_f64, the AO / sun-sky / point gathers of
+ * double frames) and closest hit (ri_b200_intersect_*_f64, the Whitted / dirt-map / trace() batches) -- run through the fp32 records
+ * with a certified error bound on every box and triangle decision and consult the double records only for the decisions fp32 cannot
+ * settle (csrc/hybrid.cuh): the double reference's answer for every ray, bit for bit, at 1.5-2x the rate of the double kernels.
+ * B200_HYBRID=0 in the environment turns this off (the double kernels run instead), =2 forces it for scenes far from the origin too;
+ * B200_HYBRID_CLOSEST=0 turns off the closest-hit form alone. */
 #define RI_B200_HOST_ONLY      0x100u        /* build + flatten on the host, no device upload: every trace call on
                                                 such an accelerator fails loudly (used by the CPU-only tests) */
 #define RI_B200_BUILD_DEVICE   0x200u        /* build the tree on the device (level-by-level binned SAH, csrc/bvh_build_gpu.cuh): the same

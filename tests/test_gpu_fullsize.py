@@ -169,3 +169,20 @@ def test_config2_hybrid_double_exact_occlusion_full_size():
     counts = a.occlusion_points(pts, 8, 8, scenes.SEED_C3, f64=True)
     assert np.array_equal(counts, occ.reshape(NP, N).sum(axis=1, dtype=np.uint32))
     assert 0.5 < occ.mean() < 0.75
+    # closest hit on the same 4 Mi double rays: closest_hybrid_kernel's records == the double kernel's, bit for bit, and == the oracle's
+    h_h = torch.empty((len(rays), 4), dtype=torch.float64, device="cuda")
+    h_p = torch.empty((len(rays), 4), dtype=torch.float64, device="cuda")
+    a.intersect_dev(d_rays, len(rays), h_h, f64=True)
+    os.environ["B200_HYBRID_CLOSEST"] = "0"
+    try:
+        a.intersect_dev(d_rays, len(rays), h_p, f64=True)
+    finally:
+        os.environ.pop("B200_HYBRID_CLOSEST", None)
+    torch.cuda.synchronize()
+    assert torch.equal(h_h.view(torch.int64), h_p.view(torch.int64))
+    pick = sample[:100_000]
+    got = h_h.cpu().numpy()[pick]
+    want = orc.intersect_f64(rays[pick])
+    assert np.array_equal(got[:, 0], want["t"]) and np.array_equal(got[:, 1], want["u"]) and np.array_equal(got[:, 2], want["v"])
+    assert np.array_equal(got[:, 3].view(np.uint64) & 0xFFFFFFFF, want["prim"].astype(np.uint64))
+    assert np.array_equal(got[:, 3].view(np.uint64) >> 32, want["hit"].astype(np.uint64))
