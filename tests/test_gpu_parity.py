@@ -1008,3 +1008,33 @@ def test_rib_scene_frames_through_the_hybrid_path(golden_dir):
     finally:
         os.environ.pop("B200_FUSED_AO_TEST", None)
         os.environ.pop("B200_HYBRID", None)
+
+
+def test_streamed_upload_with_ragged_piece_sizes(soup20k):
+    """the streamed host-buffer path (one persistent launch consuming the batch while the copy engine is still writing it)
+    with piece sizes that are NOT multiples of the warp chunk, a sector or anything else -- B200_PIECE is read once per process, so
+    the batch runs in fresh processes.  The rays are read through the coherent path (ld.global.cg), never ld.global.nc, while the copy
+    is in flight: results equal the in-process ones (which equal the oracle's, test_occlusion_matches_closest_hit_flag)."""
+    import hashlib
+    import subprocess
+    import sys
+    tris, a, orc = soup20k
+    rays8 = _mixed_rays(300000, 7)
+    rays6 = scenes.rays_f32_to_f64(rays8[:120000])
+    want32 = hashlib.sha256(a.occluded(rays8).tobytes()).hexdigest()
+    want64 = hashlib.sha256(a.occluded(rays6).tobytes()).hexdigest()
+    assert want32 == hashlib.sha256(orc.occluded_f32(rays8).tobytes()).hexdigest()
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from lucille_b200 import accel, scenes\n"
+            "import test_gpu_parity as t\n"
+            "a = accel.Accel.bind().build(scenes.triangle_soup(20000, scenes.SEED_C2))\n"
+            "r8 = t._mixed_rays(300000, 7); r6 = scenes.rays_f32_to_f64(r8[:120000])\n"
+            "print(hashlib.sha256(a.occluded(r8).tobytes()).hexdigest(), hashlib.sha256(a.occluded(r6).tobytes()).hexdigest())\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
+    for piece in ("100003", "4099", "33331"):
+        env = dict(os.environ, B200_PIECE=piece)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        got32, got64 = out.stdout.split()[-2:]
+        assert (got32, got64) == (want32, want64), piece
+        assert "cannot overlap" not in out.stderr                      # the streamed path itself ran, not its fallback
