@@ -76,6 +76,8 @@ struct ri_b200_accel {
     ri_b200_hit_exchange_fn hit_exchange = nullptr;      // rng_mode 0 over several ranks (frame.cuh)
     void     *hit_exchange_user = nullptr;
     bool verts_f32 = false;               // every vertex coordinate is an fp32 number (hybrid.cuh: no absolute error in the fp32 slots)
+    Node32 *d_nodesH = nullptr; Tri32 *d_trisH = nullptr;      // hybrid.cuh's own fp32 records, relative to hyb_c (NULL: it reads the shared ones)
+    double hyb_c[3] = {0.0, 0.0, 0.0};
     bool streamed_faulted = false;        // host_batch: the streamed upload timed out once -> launch-per-piece from then on
     unsigned int *d_work = nullptr;      // ring of work counters for the persistent kernels
     std::atomic<unsigned> work_slot{0};   // the _dev entry points may be called from several host threads / streams
@@ -274,33 +276,77 @@ static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, u
 static bool hybrid_applies(const ri_b200_accel *a)
 {
     const char *env = getenv("B200_HYBRID");                      // read per launch: tests and A/B scripts switch it inside one process
-    const int mode = env ? atoi(env) : 1;                         // 0: never, 1: where it pays, 2: whenever possible
-    if (mode == 0 || stack_capacity(a) > 28 || !a->d_nodes32 || !a->d_tris32t || !a->d_nodes64 || !a->d_tris64) return false;
-    // The fp32 records hold ABSOLUTE coordinates, so the error bounds grow with the scene's distance from the origin while the
-    // intervals they are compared with shrink with its size: far from the origin most decisions fall back to doubles and the double
-    // kernel is faster (measured: coordinates ~ 1000 on a scene of size 4: 386 against 504 Mrays/s; at the origin: 916 against 491).
-    if (mode == 1) {
-        double far = 0.0, ext = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            far = std::fmax(far, std::fmax(std::fabs(a->tree.bmin[k]), std::fabs(a->tree.bmax[k])));
-            ext = std::fmax(ext, a->tree.bmax[k] - a->tree.bmin[k]);
-        }
-        if (!(far <= 4.0 * ext)) return false;
+    const int mode = env ? atoi(env) : 1;                         // 0: never (the double kernels run)
+    return mode != 0 && stack_capacity(a) <= 28 && a->d_nodes32 && a->d_tris32t && a->d_nodes64 && a->d_tris64;
+}
+
+// is the scene close enough to the world origin for the SHARED fp32 records (absolute coordinates) to give good bounds?
+static bool hybrid_near_origin(const ri_b200_accel *a)
+{
+    double far = 0.0, ext = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        far = std::fmax(far, std::fmax(std::fabs(a->tree.bmin[k]), std::fabs(a->tree.bmax[k])));
+        ext = std::fmax(ext, a->tree.bmax[k] - a->tree.bmin[k]);
     }
-    return true;
+    return far <= 2.0 * ext;
 }
 
 static HybK hybrid_consts(const ri_b200_accel *a)
 {
     HybK H;
     float bm = 0.0f;
+    const bool own = a->d_nodesH != nullptr;
     for (int k = 0; k < 3; ++k) {
-        H.bmax[k] = std::fmax(std::fabs(a->flat.smin32[k]), std::fabs(a->flat.smax32[k]));
+        H.c[k] = own ? a->hyb_c[k] : 0.0;
+        const double lo = own ? a->tree.bmin[k] - H.c[k] : (double)a->flat.smin32[k], hi = own ? a->tree.bmax[k] - H.c[k] : (double)a->flat.smax32[k];
+        H.bmax[k] = std::nextafterf((float)std::fmax(std::fabs(lo), std::fabs(hi)), INFINITY);
         bm = std::fmax(bm, H.bmax[k]);
     }
-    H.eta0 = a->verts_f32 ? 0.0f : 5.9604645e-8f * bm;
-    H.de = 2.0f * H.eta0;
+    H.eta0 = (!own && a->verts_f32) ? 0.0f : 5.9604645e-8f * bm;   // own records: v0 - c is rounded once to fp32
+    H.de = own ? 0.0f : 2.0f * H.eta0;                             // own records: edges are the double edges rounded once (relative error only)
     return H;
+}
+static SceneView<float> hybrid_view(const ri_b200_accel *a)
+{
+    SceneView<float> S = make_view<float>(a);
+    if (a->d_nodesH) S.nodes = a->d_nodesH;
+    return S;
+}
+static const char *hybrid_tris(const ri_b200_accel *a)
+{ return a->d_trisH ? reinterpret_cast<const char *>(a->d_trisH) : pool_tris(a, 0.0f); }
+static bool hybrid_exact(const ri_b200_accel *a) { return a->verts_f32 && !a->d_nodesH; }
+
+// The filter's own records (hybrid.cuh, end): built when the shared fp32 records would bound poorly -- vertices that are not fp32
+// numbers (their slots carry an absolute error, and so do the edges subtracted in fp32) or a scene far from the world origin.
+// Measured on the C3 scene (4 Mi double AO rays): non-fp32 vertices 797 -> see DESIGN.md; moved out to |coordinates| ~ 1000 the
+// shared records lose to the double kernel (386 against 504 Mrays/s), the translated ones do not care where the scene sits.
+static int hybrid_build_records(ri_b200_accel *a)
+{
+    if (a->tree.empty || !a->d_nodes64 || !a->d_tris64 || !a->d_nodes32 || stack_capacity(a) > 28) return 0;
+    const char *env = getenv("B200_HYBRID_OWN");                   // A/B: 0 = never build them, 1 = always
+    const int force = env ? atoi(env) : -1;
+    if (force == 0 || (force != 1 && a->verts_f32 && hybrid_near_origin(a))) return 0;
+    for (int k = 0; k < 3; ++k) a->hyb_c[k] = (double)(float)(0.5 * (a->tree.bmin[k] + a->tree.bmax[k]));
+    const uint32_t ninner = a->flat.ninner;
+    const uint64_t nslots = a->flat.nslots;
+    CUDA_OK(cudaMalloc((void **)&a->d_trisH, nslots * sizeof(Tri32)));
+    CUDA_OK(cudaMemsetAsync(a->d_trisH, 0, nslots * sizeof(Tri32), a->stream));
+    CUDA_OK(cudaMalloc((void **)&a->d_nodesH, (size_t)(ninner ? ninner : 1) * sizeof(Node32)));
+    a->device_bytes += nslots * sizeof(Tri32) + (uint64_t)ninner * sizeof(Node32);
+    if (ninner) {
+        hyb_nodes_kernel<<<(ninner + 255) / 256, 256, 0, a->stream>>>(a->d_nodes64, ninner, a->hyb_c[0], a->hyb_c[1], a->hyb_c[2], a->d_nodesH);
+        LAUNCHED();
+        hyb_tris_kernel<<<(2 * ninner + 255) / 256, 256, 0, a->stream>>>(a->d_nodes64, 2 * ninner, 0u, a->d_tris64, a->hyb_c[0], a->hyb_c[1], a->hyb_c[2],
+                                                                            reinterpret_cast<char *>(a->d_trisH));
+        LAUNCHED();
+    } else if (a->flat.root_word & kLeafFlag) {
+        hyb_tris_kernel<<<1, 256, 0, a->stream>>>(a->d_nodes64, 1u, a->flat.root_word, a->d_tris64, a->hyb_c[0], a->hyb_c[1], a->hyb_c[2],
+                                                  reinterpret_cast<char *>(a->d_trisH));
+        LAUNCHED();
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(a->stream));
+    return 0;
 }
 
 // double-exact closest hit through the fp32 records (hybrid.cuh, second kernel)
@@ -318,9 +364,9 @@ static void launch_closest_hybrid_cap(ri_b200_accel *a, const double *d_rays, ui
         uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
         want = (want + (kHcThreads / 32) - 1) / (kHcThreads / 32);
         const unsigned blocks = (unsigned)(want < capb ? want : capb);
-        kern<<<blocks, kHcThreads, smem, st>>>(make_view<float>(a), make_view<double>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_hits, ctr, make_pack_k(), H);
+        kern<<<blocks, kHcThreads, smem, st>>>(hybrid_view(a), make_view<double>(a), hybrid_tris(a), d_rays, m, chunk, d_hits, ctr, make_pack_k(), H);
     };
-    if (a->verts_f32) go(closest_hybrid_kernel<kCap, true>); else go(closest_hybrid_kernel<kCap, false>);
+    if (hybrid_exact(a)) go(closest_hybrid_kernel<kCap, true>); else go(closest_hybrid_kernel<kCap, false>);
 }
 static bool launch_closest_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, ri_b200_hit_f64 *d_hits, unsigned int *ctr, cudaStream_t st)
 {
@@ -337,16 +383,17 @@ static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m
                               uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
 {
     const HybK H = hybrid_consts(a);
-    const SceneView<float> S = make_view<float>(a);
+    const SceneView<float> S = hybrid_view(a);
     const SceneView<double> S64 = make_view<double>(a);
-    const char *tt = pool_tris(a, 0.0f);
+    const char *tt = hybrid_tris(a);
+    const bool exact = hybrid_exact(a);
     const PackK K = make_pack_k();
     const size_t smem = sizeof(HybSmem<kCap>);
 #define B200_HYB_LAUNCH(C, X) do { auto kern = occluded_hybrid_kernel<kCap, C, X>;                                               \
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                      \
         kern<<<blocks, kBlock, smem, st>>>(S, S64, tt, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, K, H); } while (0)
-    if (d_counts) { if (a->verts_f32) B200_HYB_LAUNCH(true, true); else B200_HYB_LAUNCH(true, false); }
-    else          { if (a->verts_f32) B200_HYB_LAUNCH(false, true); else B200_HYB_LAUNCH(false, false); }
+    if (d_counts) { if (exact) B200_HYB_LAUNCH(true, true); else B200_HYB_LAUNCH(true, false); }
+    else          { if (exact) B200_HYB_LAUNCH(false, true); else B200_HYB_LAUNCH(false, false); }
 #undef B200_HYB_LAUNCH
 }
 static bool launch_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
@@ -586,6 +633,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         return 0;
     };
     if (body() != 0) { ri_b200_free(a); return nullptr; }
+    if ((precisions & RI_B200_PREC_F32) && (precisions & RI_B200_PREC_F64) && hybrid_build_records(a) != 0) { ri_b200_free(a); return nullptr; }
     a->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     // flat host copies are no longer needed (keep the small header fields)
     std::vector<Node32>().swap(a->flat.nodes32); std::vector<Tri32>().swap(a->flat.tris32);
@@ -601,6 +649,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
+    cudaFree(a->d_nodesH); cudaFree(a->d_trisH);
     cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags); cudaFree(a->d_tex);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     cudaFree(a->d_whole_in); cudaFree(a->d_whole_out);

@@ -34,9 +34,10 @@
 namespace b200 {
 
 struct HybK {
-    float bmax[3];          // max(|smin32_k|, |smax32_k|)
-    float eta0;             // absolute error of a vertex coordinate in fp32: 0 (all vertices are fp32 numbers) or u * max_k bmax_k
-    float de;               // absolute error of an fp32 edge component beyond its relative rounding: 0 or 2 * eta0 (v1 - v0 in fp32)
+    float  bmax[3];         // largest |coordinate| of the (translated) scene box per axis
+    float  eta0;            // absolute error of a vertex coordinate in the fp32 slots: 0 (all vertices are fp32 numbers) or u * max_k bmax_k
+    float  de;              // absolute error of an fp32 edge component beyond its relative rounding: 0 (edges rounded from doubles) or 2 * eta0
+    double c[3];            // origin of the fp32 records the kernel reads (hybrid_records.cuh): the filter works on coordinates minus c
 };
 
 struct HybWarp {
@@ -231,13 +232,15 @@ occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, co
                 float ol[3], d[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    org[k] = (float)O[k];
-                    ol[k] = (float)(O[k] - (double)org[k]);
+                    const double oc = O[k] - H.c[k];             // the filter's frame (one rounding of 2^-53 |O|: inside G0's 4 u^2 term)
+                    org[k] = (float)oc;
+                    ol[k] = (float)(oc - (double)org[k]);
                     d[k] = (float)D[k];
                     inv[k] = (float)I[k];
                 }
                 const float Md = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2]));
-                const float Mo = fmaxf(fmaxf(fabsf(org[0]), fabsf(org[1])), fabsf(org[2]));
+                const float Mo = fmaxf(fmaxf(fabsf(org[0]), fabsf(org[1])), fabsf(org[2])) +
+                                 (float)fmax(fmax(fabs(H.c[0]), fabs(H.c[1])), fabs(H.c[2]));
                 E = (8.0f * kU) * fmaxf(fmaxf(fabsf(inv[0]) * (H.bmax[0] + fabsf(org[0])), fabsf(inv[1]) * (H.bmax[1] + fabsf(org[1]))),
                                         fabsf(inv[2]) * (H.bmax[2] + fabsf(org[2])));
                 if (!(E < 1.0e30f)) E = __int_as_float(0x7f800000);       // a component of 1/dir beyond fp32 (or NaN): nothing is certain
@@ -508,13 +511,15 @@ closest_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, con
                 float ol[3], d[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    org[k] = (float)O[k];
-                    ol[k] = (float)(O[k] - (double)org[k]);
+                    const double oc = O[k] - H.c[k];             // the filter's frame (one rounding of 2^-53 |O|: inside G0's 4 u^2 term)
+                    org[k] = (float)oc;
+                    ol[k] = (float)(oc - (double)org[k]);
                     d[k] = (float)D[k];
                     inv[k] = (float)I[k];
                 }
                 const float Md = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2]));
-                const float Mo = fmaxf(fmaxf(fabsf(org[0]), fabsf(org[1])), fabsf(org[2]));
+                const float Mo = fmaxf(fmaxf(fabsf(org[0]), fabsf(org[1])), fabsf(org[2])) +
+                                 (float)fmax(fmax(fabs(H.c[0]), fabs(H.c[1])), fabs(H.c[2]));
                 E = (8.0f * kU) * fmaxf(fmaxf(fabsf(inv[0]) * (H.bmax[0] + fabsf(org[0])), fabsf(inv[1]) * (H.bmax[1] + fabsf(org[1]))),
                                         fabsf(inv[2]) * (H.bmax[2] + fabsf(org[2])));
                 if (!(E < 1.0e30f)) E = __int_as_float(0x7f800000);
@@ -670,6 +675,75 @@ closest_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, con
                 else enter(next);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// The filter's own fp32 records, derived on the device from the DOUBLE records (whichever builder made them) when the shared fp32
+// records would give poor bounds: coordinates relative to an origin c (the scene box's centre) so that the bounds scale with the
+// scene's size instead of its distance from the world origin, boxes rounded outward with directed roundings end to end, vertices
+// fl32(v0 - c), edges fl32 of the double edges (relative error only: no absolute term `de`).
+__global__ void __launch_bounds__(256)
+hyb_nodes_kernel(const Node64 *__restrict__ n64, const uint32_t ninner, const double cx, const double cy, const double cz, Node32 *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= ninner) return;
+    const Node64 s = n64[i];
+    Node32 d;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j & 1) {
+            d.x[j] = __double2float_ru(__dsub_ru(s.x[j], cx)); d.y[j] = __double2float_ru(__dsub_ru(s.y[j], cy)); d.z[j] = __double2float_ru(__dsub_ru(s.z[j], cz));
+        } else {
+            d.x[j] = __double2float_rd(__dsub_rd(s.x[j], cx)); d.y[j] = __double2float_rd(__dsub_rd(s.y[j], cy)); d.z[j] = __double2float_rd(__dsub_rd(s.z[j], cz));
+        }
+    }
+    d.c0 = s.c0; d.c1 = s.c1; d.axis = s.axis; d.pad = 0u;
+    out[i] = d;
+}
+
+// one thread per child word (2 per inner node; `root_leaf` != 0: the single leaf of a tree without inner nodes): the leaf's pairs in
+// the interleaved, leaf-transposed layout of FlatTree::tris32t (bvh_build.cpp)
+__global__ void __launch_bounds__(256)
+hyb_tris_kernel(const Node64 *__restrict__ n64, const uint32_t nwords, const uint32_t root_leaf, const Tri64 *__restrict__ t64,
+                const double cx, const double cy, const double cz, char *__restrict__ out)
+{
+    const uint32_t w = blockIdx.x * 256u + threadIdx.x;
+    if (w >= nwords) return;
+    const uint32_t word = root_leaf ? root_leaf : ((w & 1u) ? n64[w >> 1].c1 : n64[w >> 1].c0);
+    if (!(word & kLeafFlag)) return;
+    const uint32_t ntris = ((word >> kLeafShift) & 15u) + 1u, slot0 = word & kSlotMask;
+    const uint32_t m = ((ntris + 3u) >> 2) << 1, used = (ntris + 1u) >> 1;
+    const double c[3] = {cx, cy, cz};
+    char *dst = out + (size_t)slot0 * 48u;
+    for (uint32_t j = 0; j < m; ++j) {
+        uint32_t wd[20];
+#pragma unroll
+        for (int q = 0; q < 20; ++q) wd[q] = 0u;
+        wd[18] = wd[19] = 0xffffffffu;
+        for (uint32_t h = 0; h < 2u; ++h) {
+            const uint32_t k = 2u * j + h;
+            if (k < ntris) {
+                TriRegs<double> tr;
+                load_tri(t64 + slot0 + k, tr);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    wd[2 * q + h] = __float_as_uint((float)(tr.v0[q] - c[q]));
+                    wd[2 * (3 + q) + h] = __float_as_uint((float)tr.e1[q]);
+                    wd[2 * (6 + q) + h] = __float_as_uint((float)tr.e2[q]);
+                }
+                wd[18 + h] = tr.prim;
+            } else if (j + 1u == used) {                     // filler half of the last pair: unit edges (masked by its validity bit)
+                wd[2 * 3 + h] = __float_as_uint(1.0f);
+                wd[2 * 7 + h] = __float_as_uint(1.0f);
+            }
+        }
+        uint32_t *p0 = reinterpret_cast<uint32_t *>(dst + (size_t)j * 32u), *p1 = reinterpret_cast<uint32_t *>(dst + (size_t)(m + j) * 32u),
+                 *p2 = reinterpret_cast<uint32_t *>(dst + (size_t)2u * m * 32u + (size_t)j * 16u);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { p0[q] = wd[q]; p1[q] = wd[8 + q]; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p2[q] = wd[16 + q];
     }
 }
 

@@ -892,8 +892,9 @@ def test_hybrid_occlusion_is_fp64_exact(case):
     """csrc/hybrid.cuh: with both record sets resident, double occlusion AND closest-hit queries run through the fp32 records with
     certified decisions and the double records only where fp32 cannot decide.  The answer is the DOUBLE reference's for every ray: against the
     oracle's f64 instantiation and against the plain double kernel (an accelerator holding double records only), on
-      soup              fp32-representable vertices (no absolute error in the fp32 slots)
-      soup_inexact      the same soup scaled and shifted in double: vertices are not fp32 numbers
+      soup              fp32-representable vertices near the origin: the filter reads the shared fp32 records (no absolute error in them)
+      soup_inexact      the same soup scaled and shifted in double: vertices are not fp32 numbers -> the filter's own records
+                        (coordinates relative to the scene centre, rounded once from the doubles)
       soup_far          ... and moved out to |coordinates| ~ 1000, where the 1e-6 origin offset is 1/60 of an fp32 ulp
       box_city(_inexact) axis-aligned architecture: shared vertices, coplanar faces, rays along box faces and through edges
     with incoherent rays, rays from surface points (the AO pattern), axis-parallel rays and rays aimed exactly at vertices."""
@@ -926,7 +927,6 @@ def test_hybrid_occlusion_is_fp64_exact(case):
     verts = tris.reshape(-1, 3)
     aim = verts[rng.integers(0, len(verts), 40000)]                                          # straight at a vertex: u, v, u + v on the window's edge
     batches["vertices"] = np.concatenate([org[:40000], aim - org[:40000]], axis=1)
-    os.environ["B200_HYBRID"] = "2"                  # also where the dispatcher would prefer the double kernel (soup_far)
     try:
         for name, rays in batches.items():
             rays = np.ascontiguousarray(rays)
@@ -948,7 +948,7 @@ def test_hybrid_occlusion_is_fp64_exact(case):
         assert np.array_equal(cnt, want)
         assert np.array_equal(plain.occlusion_points(pts, 4, 4, 99, eps=1.0e-6, f64=True), want)
     finally:
-        os.environ.pop("B200_HYBRID", None)
+        pass
 
 
 def _surface_rays_camera(tris, ot):
@@ -1038,3 +1038,27 @@ def test_streamed_upload_with_ragged_piece_sizes(soup20k):
         got32, got64 = out.stdout.split()[-2:]
         assert (got32, got64) == (want32, want64), piece
         assert "cannot overlap" not in out.stderr                      # the streamed path itself ran, not its fallback
+
+
+@pytest.mark.parametrize("ntris", [0, 1, 16, 17, 300])
+def test_hybrid_own_records_on_tiny_trees(ntris):
+    """The filter's own (translated) fp32 records forced on trees with no inner node (a single leaf, the empty scene) and small ones:
+    occlusion and closest hit still the double reference's, record for record."""
+    _need_gpu()
+    tris = scenes.triangle_soup(ntris, 5) * 2.3 + np.array([7.0, -3.0, 11.0]) if ntris else np.zeros((0, 3, 3))
+    os.environ["B200_HYBRID_OWN"] = "1"
+    try:
+        a = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64)
+    finally:
+        os.environ.pop("B200_HYBRID_OWN", None)
+    ot = ol.Oracle().build(tris)
+    rng = np.random.default_rng(ntris)
+    lo, hi = (tris.reshape(-1, 3).min(axis=0), tris.reshape(-1, 3).max(axis=0)) if ntris else (np.zeros(3), np.ones(3))
+    org = lo + (hi - lo) * rng.uniform(-1.0, 2.0, (20000, 3))
+    tgt = (tris.reshape(-1, 3)[rng.integers(0, 3 * ntris, 20000)] + rng.normal(scale=0.02, size=(20000, 3))) if ntris else rng.uniform(0, 1, (20000, 3))
+    rays = np.ascontiguousarray(np.concatenate([org, tgt - org], axis=1))
+    assert np.array_equal(a.occluded(rays), ot.occluded_f64(rays))
+    h, w = a.intersect(rays), ot.intersect_f64(rays)
+    for f in ("hit", "prim", "t", "u", "v"):
+        assert np.array_equal(h[f], w[f]), f
+    assert ntris == 0 or 0.02 < w["hit"].mean() < 0.98
