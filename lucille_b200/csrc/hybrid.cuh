@@ -22,7 +22,9 @@
 //     (three-term dot products of two-term cross products: input roundings, product and sum roundings, all bounded through the
 //     max-norms).  The kernel uses 96 u and G = 8 eta0 + 72 u Ms, a third more than derived, which also covers the reference's own
 //     2^-53 roundings and the arithmetic that evaluates the bounds.  eta0 = the part of s's error that is not relative to s: 0 when
-//     every vertex coordinate of the scene is an fp32 number (RIB files hold floats; so does the synthetic soup), else u Bmax.
+//     every vertex coordinate of the scene is an fp32 number (RIB files hold floats; so does the synthetic soup), else u Bmax -- and then
+//     (or when the scene lies far from the world origin) the filter reads its OWN fp32 records, relative to the scene centre and
+//     rounded once from the double records (end of this file), so that Bmax is the scene's half extent wherever the scene sits.
 //     With sg = sign(a): u >= 0 <=> sg U >= 0, u + v <= 1 <=> sg (U + V) <= |a|, t >= 0 <=> sg T >= 0, |a| > 1e-14.  A triangle
 //     is certainly accepted / certainly rejected when every / some comparison holds with its bound to spare; otherwise its double
 //     slot is tested with the reference's expression tree (hyb_tri64).  NaNs and infinities make every comparison false = undecided.
