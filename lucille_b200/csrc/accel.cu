@@ -480,10 +480,12 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
             const uint32_t m = (uint32_t)((n - done) < kMax ? (n - done) : kMax);
             const uint64_t cap = (uint64_t)per_sm * (uint64_t)a->sm_count;
             const uint64_t warps = cap * (kBlock / 32);
-            // rays per atomic fetch: ~16 fetches per warp for load balance, between one warp-load and 128 rays
-            uint32_t chunk = (uint32_t)((uint64_t)m / (warps * 16));
-            chunk = chunk < 32u ? 32u : (chunk > 128u ? 128u : chunk);
-            chunk &= ~31u;
+            // rays per atomic fetch: one warp-load.  Measured on the C3 batch (scripts/gpu_r3f.sh): 32 / 64 / 128 / 256 / 512 rays ->
+            // 1113 / 1112 / 1106 / 1088 / 1053 Mrays/s -- the fetch is one atomic per 32 rays either way, a larger chunk only
+            // lengthens the tail of the launch
+            uint32_t chunk = 32u;
+            (void)warps;
+            if (const char *e = getenv("B200_RAYCHUNK")) { const int v = atoi(e); if (v >= 32) chunk = (uint32_t)v & ~31u; }   // A/B knob
             uint64_t want = ((uint64_t)m + chunk - 1) / chunk;             // one chunk per warp at least
             want = (want + (kBlock / 32) - 1) / (kBlock / 32);
             const unsigned blocks = (unsigned)(want < cap ? want : cap);

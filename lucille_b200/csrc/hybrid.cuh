@@ -162,7 +162,10 @@ occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, co
                        unsigned int *__restrict__ fault, const PackK K, const HybK H)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t kRefillAt = 4u, kLeafAt = 32u;
+#ifndef B200_HYB_REFILL
+#define B200_HYB_REFILL 8
+#endif
+    constexpr uint32_t kRefillAt = B200_HYB_REFILL, kLeafAt = 32u;
     constexpr uint32_t kRow = kBlock * 4u;
     constexpr float kU = 5.9604645e-8f;                                // 2^-24
     extern __shared__ __align__(16) unsigned char hyb_smem[];          // one HybSmem<kCap> (more than the 48 KB a static array may have)
@@ -443,7 +446,10 @@ closest_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, con
                       const PackK K, const HybK H)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t kRefillAt = 4u;
+#ifndef B200_HC_REFILL
+#define B200_HC_REFILL 8
+#endif
+    constexpr uint32_t kRefillAt = B200_HC_REFILL;
     constexpr uint32_t kRow = kHcThreads * 4u;
     constexpr float kU = 5.9604645e-8f;
     extern __shared__ __align__(16) unsigned char hyb_smem[];

@@ -83,7 +83,13 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                        const PackK K)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t kRefillAt = 4u, kLeafAt = 32u;                  // measured best on C3 (B200_REFILL / B200_LEAF_AT sweeps of pool.cuh)
+#ifndef B200_OCC_REFILL
+#define B200_OCC_REFILL 8        // 2 / 4 / 6 / 8 / 12 -> 1040 / 1079 / 1099 / 1105 / 1099 Mrays/s on C3 (scripts/gpu_r3e.sh)
+#endif
+#ifndef B200_OCC_LEAFAT
+#define B200_OCC_LEAFAT 32
+#endif
+    constexpr uint32_t kRefillAt = B200_OCC_REFILL, kLeafAt = B200_OCC_LEAFAT;
     constexpr uint32_t kRow = kBlock * 4u;                             // bytes between two stack levels of a lane
     __shared__ __align__(16) Pool32Smem<kCap> sm;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
@@ -296,7 +302,10 @@ closest_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, 
                       const uint32_t chunk, ri_b200_hit_f32 *__restrict__ hits_out, unsigned int *__restrict__ work_counter, const PackK K)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr uint32_t kRefillAt = 4u;
+#ifndef B200_CLOSE_REFILL
+#define B200_CLOSE_REFILL 8      // idle lanes that trigger a refill: 1 / 2 / 4 / 8 / 12 -> 876 / 915 / 945 / 958 / 948 Mrays/s on C3
+#endif
+    constexpr uint32_t kRefillAt = B200_CLOSE_REFILL;
     constexpr uint32_t kRow = kCloseThreads * 4u;
     __shared__ __align__(16) Close32Smem<kCap> sm;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
