@@ -8,6 +8,7 @@ $NCU -k regex:occluded_pool32 -s 2 -c 1 -o gpurun_out/r02_occ_f32_c3 python benc
 P="--profile-from-start off"
 $NCU $P -k regex:closest_pool32 -c 1 -o gpurun_out/r02_closest_f32_c3 python scripts/prof_r02.py c3 > gpurun_out/r02_ncu2.log 2>&1
 $NCU $P -k regex:occluded_hybrid -c 1 -o gpurun_out/r02_occ_hybrid_c3 python scripts/prof_r02.py c3 > gpurun_out/r02_ncu8.log 2>&1
+$NCU $P -k regex:closest_hybrid -c 1 -o gpurun_out/r02_closest_hybrid_c3 python scripts/prof_r02.py c3 > gpurun_out/r02_ncu9.log 2>&1
 $NCU $P -k regex:occluded_pool_kernel -c 1 -o gpurun_out/r02_occ_f64_c3 python scripts/prof_r02.py c3 > gpurun_out/r02_ncu3.log 2>&1
 $NCU $P -k regex:closest_pool_kernel -c 1 -o gpurun_out/r02_closest_f64_c3 python scripts/prof_r02.py c3 > gpurun_out/r02_ncu4.log 2>&1
 $NCU $P -k regex:occluded_pool32 -c 1 -o gpurun_out/r02_occ_f32_c5 python scripts/prof_r02.py c5 > gpurun_out/r02_ncu5.log 2>&1
@@ -21,10 +22,11 @@ T4="4194304"
 python scripts/ncu_md.py gpurun_out/r02_occ_f32_c3.ncu-rep $S/r02_occluded_f32_c3 "r02: fp32 occlusion (pool32.cuh), the timed kernel of bench.py: 1 M triangles, the 16 Mi-ray C3 batch" 16777216
 python scripts/ncu_md.py gpurun_out/r02_closest_f32_c3.ncu-rep $S/r02_closest_f32_c3 "r02: fp32 closest hit (pool32.cuh), 1 M triangles, first 4 Mi AO rays of the C3 batch" $T4
 python scripts/ncu_md.py gpurun_out/r02_occ_hybrid_c3.ncu-rep $S/r02_occluded_hybrid_c3 "r02: double-exact occlusion through the fp32 records (hybrid.cuh), 1 M triangles, first 4 Mi AO rays of the C3 batch as doubles" $T4
+python scripts/ncu_md.py gpurun_out/r02_closest_hybrid_c3.ncu-rep $S/r02_closest_hybrid_c3 "r02: double-exact closest hit through the fp32 records (hybrid.cuh), 1 M triangles, first 4 Mi AO rays of the C3 batch as doubles" $T4
 python scripts/ncu_md.py gpurun_out/r02_occ_f64_c3.ncu-rep $S/r02_occluded_f64_c3 "r02: double occlusion (pool.cuh, double records), 1 M triangles, first 4 Mi AO rays of the C3 batch" $T4
 python scripts/ncu_md.py gpurun_out/r02_closest_f64_c3.ncu-rep $S/r02_closest_f64_c3 "r02: double closest hit (pool_closest.cuh), 1 M triangles, first 4 Mi AO rays of the C3 batch" $T4
 python scripts/ncu_md.py gpurun_out/r02_occ_f32_c5.ncu-rep $S/r02_occluded_f32_c5 "r02: fp32 occlusion (pool32.cuh) on the 10 M-triangle soup of configs[4] -- 1.2 GB of records, beyond L2 -- 4 Mi AO rays" $T4
 python scripts/ncu_md.py gpurun_out/r02_occ_f32_c3_topsmem.ncu-rep $S/r02_occluded_f32_c3_topsmem "r02: X1 experiment -- generic pooled fp32 occlusion with the top 256 nodes staged in shared memory by cp.async.bulk (B200_POOL_TOPSMEM=1), first 4 Mi rays of C3" $T4
 python scripts/ncu_md.py gpurun_out/r02_occ_f32_c3_generic.ncu-rep $S/r02_occluded_f32_c3_generic "r02: generic pooled fp32 occlusion (pool.cuh, B200_POOL32=0), first 4 Mi rays of C3 -- the A/B arm of the two profiles beside it" $T4
-rm -f gpurun_out/r02_occ_f32_c3.ncu-rep gpurun_out/r02_occ_f64_c3.ncu-rep gpurun_out/r02_closest_f64_c3.ncu-rep gpurun_out/r02_occ_f32_c5.ncu-rep gpurun_out/r02_occ_f32_c3_topsmem.ncu-rep gpurun_out/r02_occ_f32_c3_generic.ncu-rep
+rm -f gpurun_out/r02_closest_f32_c3.ncu-rep gpurun_out/r02_occ_f32_c3.ncu-rep gpurun_out/r02_occ_f64_c3.ncu-rep gpurun_out/r02_closest_f64_c3.ncu-rep gpurun_out/r02_occ_f32_c5.ncu-rep gpurun_out/r02_occ_f32_c3_topsmem.ncu-rep gpurun_out/r02_occ_f32_c3_generic.ncu-rep
 du -sh gpurun_out

@@ -1,100 +1,63 @@
-"""Turn the ncu artefacts a `scripts/gpu_round.sh` run leaves in gpurun_out/ into the committed summaries under profiles/.
+"""Turn what `scripts/gpu_r2p.sh` leaves in gpurun_out/ into the committed summaries under profiles/ (round 2 and later):
 
-    python scripts/make_profiles.py r01
-"""
+    gpurun -- 'bash scripts/gpu_r2p.sh'      # on the GPU box: launch list + one `ncu --set full` capture per kernel, summarised there
+    python scripts/make_profiles.py r02      # here: copy the summaries, derive the files bench.py reads
+
+  profiles/<tag>_<kernel>.md / .json     metric table, instruction mix, hottest SASS lines (scripts/ncu_md.py, run on the box)
+  profiles/<tag>_kernel_metrics.json     the `roofline.limiter` block of the bench line: what physically limits the timed kernel
+  profiles/traffic.json                  DRAM bytes of one launch of the timed kernel (`roofline.traffic`)
+  profiles/<tag>_launches.md             kernel launch list of the bench command (shares, not absolutes: cold cache, serialised)
+(The round-1 form of this script, which read .ncu-rep files directly, is in the history: profiles/r01_* came from it.)"""
 import csv
+import glob
 import json
 import os
-import subprocess
+import shutil
 import sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-out_dir = os.path.join(ROOT, "profiles")
-os.makedirs(out_dir, exist_ok=True)
-gp = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+out_dir, gp = os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out")
 
-# ---- launch list ------------------------------------------------------------------------------------------------------
-rows = [r for r in csv.reader(open(os.path.join(gp, "launches.csv"))) if len(r) > 5 and r[0].isdigit()]
-d = defaultdict(list)
-for r in rows:
-    d[(r[4].split("(")[0].replace("void ", ""), r[8], r[7])].append(float(r[-1].replace(",", "")))
-tot = sum(sum(v) for v in d.values())
-with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
-    f.write(f"# {tag}: kernel launch list of `bench.py --steps 3 --warmup 3 --no-cpu-baseline`\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 600` (cold-cache, serialised: compare shares, not absolutes).\n"
-            "Setup launches (primary rays, statistics counters) and the chunked end-to-end launches are part of the list.\n\n"
-            "| kernel | grid | block | launches | avg ms | share of listed GPU time |\n|---|---|---|---:|---:|---:|\n")
-    for (k, grid, block), v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
-        f.write(f"| `{k}` | {grid} | {block} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {sum(v) / tot * 100:.1f} % |\n")
-    f.write("\nThe timed region of bench.py is `steps` launches of `occluded_pool_kernel<float, 4>` and nothing else (one launch = one step = the\n"
-            "whole 16 Mi-ray batch; `gpu_launches` = steps), so the kernel's share of a step is 100 %; everything else in this list is set-up\n"
-            "(tree build, primary rays, statistics counters), the closest-hit side measurement and the end-to-end calls.\n"
-            "\n`occluded_pool_kernel<float, 4>` = pooled occlusion (any-hit) traverser, the timed kernel: grid 592 = 4 CTAs x 148 SMs; every\n"
-            "16 Mi-ray launches are the warm-up and timed steps; the 2 Mi-ray (and ramp-up) ones are the host-buffer (e2e) calls in their\n"
-            "launch-per-piece form -- this pass runs with B200_STREAMED=0 because ncu serialises the copy stream behind the kernel; outside\n"
-            "the profiler an e2e call is ONE streamed launch.\n"
-            "`closest_pool_kernel` = pooled closest-hit traverser (reported as closest_hit_mrays_s, and the primary rays of the set-up).\n"
-            "`gb_*` = the device BVH builder (set-up, untimed: ~10 launches per tree level, 19 levels) and `gb_fill_slots`.\n"
-            "`trace_batch_kernel<..., 1>` = one-ray-per-thread kernel with the reference's traversal counters (I, T of the roofline formula), run once, untimed.\n")
+for f in sorted(glob.glob(os.path.join(gp, "summaries", f"{tag}_*"))):
+    shutil.copy(f, out_dir)
+    print("copied", os.path.basename(f))
 
-# ---- full capture of the timed kernel ---------------------------------------------------------------------------------
-rep = os.path.join(gp, "prof_bench.ncu-rep")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-hdr, units, vals = rr[0], rr[1], rr[2]
-m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
-keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
-        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "dram__bytes_read.sum.per_second", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
-        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__warps_eligible.avg.per_cycle_active",
-        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active"]
-name = m["Kernel Name"][0]
-to_bytes = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-rd = float(m["dram__bytes_read.sum"][0]) * to_bytes[m["dram__bytes_read.sum"][1]]
-wr = float(m["dram__bytes_write.sum"][0]) * to_bytes[m["dram__bytes_write.sum"][1]]
-with open(os.path.join(out_dir, f"{tag}_occluded_f32_c3.md"), "w") as f:
-    f.write(f"# {tag}: `ncu --set full --clock-control none` of the timed kernel of bench.py (one launch, 16 777 216 AO rays, 1 M triangles)\n\n"
-            f"kernel: `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
-    for k in keys:
-        if k in m:
-            f.write(f"| {k} | {m[k][0]} | {m[k][1]} |\n")
-    f.write(f"\nDRAM traffic of the launch: {rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written = {(rd + wr) / 1e6:.1f} MB "
-            "(the 512 MiB ray batch + the 54 MB scene once + 16 MiB of occlusion bytes); algorithmic bytes of the same launch: "
-            "174 GB (10.39 KB/ray) -- the scene records are re-read from L2, not from HBM.\n\n"
-            "Reading: no tensor pipe (by design), DRAM idle, L2 at a quarter of its peak; the kernel is limited by warp-instruction issue "
-            "(~77 % of the issue slots) with the L1 data pipe next (~75-80 % of its wavefronts: one per 32-byte sector of a lane's node record, "
-            "shared between neighbouring lanes for the leaf-transposed triangle rows); ~26 of 32 lanes are active per issued instruction "
-            "(15 in the vote-scheduled kernel this one replaced: profiles/r01_early_*).\n")
-with open(os.path.join(out_dir, "traffic.json"), "w") as f:
-    json.dump({"occluded_f32_c3_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": f"profiles/{tag}_occluded_f32_c3.md"}, f)
+timed = json.load(open(os.path.join(out_dir, f"{tag}_occluded_f32_c3.json")))
+lsu, issue = timed["lsu_wavefront_frac"], timed["issue_frac"]
+km = {
+    "source": f"profiles/{tag}_occluded_f32_c3.md (ncu --set full, one launch of the timed kernel on the bench batch; scripts/make_profiles.py)",
+    "what_limits": ("L1 data-pipe (LSU) wavefronts, with warp-instruction issue next" if lsu >= issue else "warp-instruction issue, with the L1 data pipe next")
+                   + "; DRAM is idle (records are L2-resident)",
+    "lsu_wavefront_frac": lsu, "issue_frac": issue, "fma_pipe_cycles_frac": timed["fma_pipe_cycles_frac"],
+    "alu_pipe_cycles_frac": timed["alu_pipe_cycles_frac"], "inst_per_ray": timed.get("inst_per_ray"), "lanes_per_inst": timed["lanes_per_inst"],
+    "dram_gb_s": timed["dram_gb_s"], "dram_bytes_per_launch": timed["dram_bytes"], "l2_hit_rate": timed["l2_hit_rate"],
+    "l1_hit_rate": timed["l1_hit_rate"], "registers": timed["registers"], "ms_under_ncu": timed["ms"],
+}
+json.dump(km, open(os.path.join(out_dir, f"{tag}_kernel_metrics.json"), "w"), indent=1)
+json.dump({"occluded_f32_c3_bytes_per_launch": timed["dram_bytes"], "source": f"profiles/{tag}_occluded_f32_c3.md"},
+          open(os.path.join(out_dir, "traffic.json"), "w"))
+print("wrote", f"{tag}_kernel_metrics.json", "traffic.json")
 
-# ---- hottest SASS ------------------------------------------------------------------------------------------------------
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-sr = list(csv.reader(src.splitlines()))
-h2 = sr[1]
-data = [r for r in sr[2:] if len(r) == len(h2) and r[0] != "Address"]
-ia, isrc, isamp, iavg = h2.index("Instructions Executed"), h2.index("Source"), h2.index("# Samples"), h2.index("Avg. Threads Executed")
-total = sum(int(r[ia]) for r in data)
-tots = sum(int(r[isamp]) for r in data)
-opc = defaultdict(int)
-for r in data:
-    opc[r[isrc].split()[0].split(".")[0] if not r[isrc].strip().startswith("@") else r[isrc].split()[1].split(".")[0]] += int(r[ia])
-with open(os.path.join(out_dir, f"{tag}_occluded_f32_c3_sass.md"), "w") as f:
-    f.write(f"# {tag}: instruction mix of the timed kernel (ncu source page, {total} warp instructions, {len(data)} SASS lines)\n\n"
-            "| opcode | share of executed warp instructions |\n|---|---:|\n")
-    for k, v in sorted(opc.items(), key=lambda kv: -kv[1])[:24]:
-        f.write(f"| {k} | {v / total * 100:.1f} % |\n")
-    f.write("\n`LDG.E.ENL2.256` = the 256-bit node / triangle-chunk loads; `FMNMX3` = 3-input min/max of the slab test; `VOTE`/`POPC`/`REDUX` = the pool bookkeeping (prefix sums from bit-sliced ballots, item totals).\n\n"
-            "## lines with the most stall samples\n\n| samples | executed | avg threads | SASS |\n|---:|---:|---:|---|\n")
-    for r in sorted(data, key=lambda r: -int(r[isamp]))[:25]:
-        f.write(f"| {int(r[isamp]) / tots * 100:.2f} % | {int(r[ia]) / total * 100:.2f} % | {r[iavg]} | `{r[isrc].strip()[:90]}` |\n")
-print("profiles written")
+lc = os.path.join(gp, f"{tag}_launches.csv")
+if os.path.exists(lc):
+    rows = [r for r in csv.reader(open(lc)) if len(r) > 5 and r[0].isdigit()]
+    d = defaultdict(list)
+    for r in rows:
+        d[(r[4].split("(")[0].replace("void ", ""), r[8], r[7])].append(float(r[-1].replace(",", "")))
+    tot = sum(sum(v) for v in d.values())
+    with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
+        f.write(f"# {tag}: kernel launch list of `B200_STREAMED=0 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-frames`\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 900` (cold-cache, serialised: compare shares, not absolutes).\n\n"
+                "| kernel | grid | block | launches | avg ms | share of listed GPU time |\n|---|---|---|---:|---:|---:|\n")
+        for (k, grid, block), v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"| `{k}` | {grid} | {block} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {sum(v) / tot * 100:.1f} % |\n")
+        f.write("\nThe timed region of bench.py is `steps` launches of `occluded_pool32_kernel<20, 0>` on the 16 Mi-ray batch and nothing else (one launch = one\n"
+                "step; `gpu_launches` = steps), so the kernel's share of a step is 100 %.  Everything else in the list is set-up (device BVH build `gb_*`,\n"
+                "primary rays, the reference-order counters `trace_batch_kernel<..., 1>` of the roofline formula), the side measurements (closest hit\n"
+                "`closest_pool32_kernel`, the double-exact leg `occluded_hybrid_kernel` / `closest_hybrid_kernel` against `occluded_pool_kernel<double>` /\n"
+                "`closest_pool_kernel<double>`) and the end-to-end calls (`ao_points_gen_kernel` + `occluded_pool32_kernel<20, 1>` = the point entry;\n"
+                "the short `occluded_pool32_kernel<20, 0>` launches = the host ray-batch path in its launch-per-piece form, because ncu serialises the\n"
+                "copy stream behind the kernel: outside the profiler an e2e call is ONE streamed launch).\n")
+    print("wrote", f"{tag}_launches.md")

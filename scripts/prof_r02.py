@@ -38,7 +38,10 @@ for it in range(3):
         os.environ["B200_HYBRID"] = "0"
         a.occluded_dev(d64, nr, occ, st.cuda_stream, f64=True)            # the plain double kernel
         os.environ.pop("B200_HYBRID")
-        a.intersect_dev(d64, nr, h64, st.cuda_stream, f64=True)
+        a.intersect_dev(d64, nr, h64, st.cuda_stream, f64=True)           # hybrid closest hit
+        os.environ["B200_HYBRID_CLOSEST"] = "0"
+        a.intersect_dev(d64, nr, h64, st.cuda_stream, f64=True)           # the double kernel
+        os.environ.pop("B200_HYBRID_CLOSEST")
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 cnt = a.count(rays[: 1 << 20], anyhit=True)
