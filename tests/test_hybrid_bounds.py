@@ -200,3 +200,42 @@ def test_certain_box_decisions_are_the_double_decisions(scale, offset):
     assert not ref[fail_c & ~pass_c].any(), int(ref[fail_c & ~pass_c].sum())
     und = ~pass_c & ~fail_c
     assert 0.1 < ref.mean() < 0.9 and pass_c.sum() > 1000 and fail_c.sum() > 1000 and und.mean() < 0.9
+
+
+@pytest.mark.parametrize("scale,offset,own", [(1.0, 0.0, False), (1.0, 0.0, True), (4.0, 1.0e3, True), (1.0e3, 0.0, True)])
+def test_beyond_best_t_filter_of_the_closest_hit_kernel(scale, offset, own):
+    """closest_hybrid_kernel skips a triangle when T_lo > round_up(best_t) * |a|_hi (hyb_tri_maybe): then the reference's t for that
+    triangle, if it accepts it at all, is strictly greater than best_t -- with best_t placed within hairs of the true t on both sides."""
+    rng = np.random.default_rng(int(scale) + int(offset) + own)
+    n = 400_000
+    off = np.array([offset, -0.7 * offset, 0.3 * offset])
+    O, D, v0, e1, e2 = _adversarial_triangles(rng, n, scale, off, snap32=not own)
+    c = off.astype(np.float32).astype(np.float64) if own else np.zeros(3)
+    bmax = float(np.abs(np.concatenate([v0, v0 + e1, v0 + e2]) - c).max())
+    with np.errstate(all="ignore"):
+        p = np.cross(D, e2)
+        a64 = (e1 * p).sum(axis=1)
+        t64 = (e2 * np.cross(O - v0, e1)).sum(axis=1) / a64
+    ref = _tri_ref(O, D, v0, e1, e2)
+    best_t = np.abs(t64) * (1.0 + 10.0 ** rng.uniform(-15.0, -2.0, n) * rng.choice([-1.0, 1.0], n))
+    best_t = np.where(np.isfinite(best_t) & (best_t > 0), best_t, 1.0)
+    best_hi = _f32_up(best_t)
+    # the fp32 quantities of _tri_class32, inlined for T_lo and |a|_hi
+    with np.errstate(all="ignore"):
+        oc = O - c
+        oh = oc.astype(np.float32); ol = (oc - oh.astype(np.float64)).astype(np.float32); d = D.astype(np.float32)
+        if own:
+            v0f, e1f, e2f, eta0, de, exact = (v0 - c).astype(np.float32), e1.astype(np.float32), e2.astype(np.float32), U * F(bmax), F(0.0), False
+        else:
+            v0f = v0.astype(np.float32); e1f = (v0 + e1).astype(np.float32) - v0f; e2f = (v0 + e2).astype(np.float32) - v0f
+            eta0, de, exact = F(0.0), F(0.0), True
+        pf = _cross32(d, e2f); a = _dot32(e1f, pf); s = (oh - v0f) + ol; q = _cross32(s, e1f); Tt = _dot32(e2f, q)
+        Md, Me1, Me2, Ms = (np.abs(x).max(axis=1) for x in (d, e1f, e2f, s))
+        Mo = np.abs(oh).max(axis=1) + F(np.abs(c).max())
+        G = F(72.0) * U * Ms + (F(8.0) * (eta0 + (F(4.0) * U * U) * Mo) + F(1.0e-30))
+        ea, eT = F(96.0) * U * (Md * (Me1 * Me2)), (Me1 * Me2) * G
+        Ts = Tt * np.where(np.signbit(a), F(-1.0), F(1.0))
+        skip = (Ts - eT) > best_hi * (np.abs(a) + ea) * F(1.000001)
+    wrong = skip & ref & ~(t64 > best_t)
+    assert not wrong.any(), int(wrong.sum())
+    assert skip.sum() > 1000 and (ref & ~skip).sum() > 1000
