@@ -119,6 +119,15 @@ def test_plane_sphere_ao_frame_with_vertex_normals(oracle, golden_dir):
     assert not np.array_equal(flat, g["rgb"])          # the normals matter
 
 
+def test_city_frame_golden(oracle, golden_dir):
+    """C6 (tests/golden/make_city_golden.py): a 15 552-triangle architectural scene at RIB scale whose world-space vertices are not fp32
+    numbers, rendered by the compiled reference -- the restatement's frame is bit-identical, with the reference's ray count."""
+    g = np.load(os.path.join(golden_dir, "c6_city.npz"))
+    t = oracle.build(g["tris"])
+    rgb, nrays = t.render_ao(ol.frame_params(g["cam"], int(g["width"]), int(g["height"]), xsamples=int(g["ps"]), ysamples=int(g["ps"]), gather=int(g["gather"])))
+    assert nrays == int(g["nrays"]) and np.array_equal(rgb, g["rgb"])
+
+
 def test_beam_visibility_golden(oracle, golden_dir):
     g = np.load(os.path.join(golden_dir, "beams.npz"))
     for k in range(3):
