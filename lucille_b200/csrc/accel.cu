@@ -249,12 +249,20 @@ template <int kCap>
 static void launch_pool32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
                               uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
 {
+    (void)blocks;                       // the caller's count assumes its own CTA size: this kernel has its own
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occluded_pool32_kernel<kCap, false>, kOccThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
+    uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
+    want = (want + (kOccThreads / 32) - 1) / (kOccThreads / 32);
+    const unsigned nb = (unsigned)(want < capb ? want : capb);
     if (d_counts)
-        occluded_pool32_kernel<kCap, true><<<blocks, kBlock, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, nullptr, d_counts,
-                                                                     rays_per_count, ctr, d_ready, d_fault, make_pack_k());
-    else
-        occluded_pool32_kernel<kCap, false><<<blocks, kBlock, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_occ, nullptr,
+        occluded_pool32_kernel<kCap, true><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, nullptr, d_counts,
                                                                       rays_per_count, ctr, d_ready, d_fault, make_pack_k());
+    else
+        occluded_pool32_kernel<kCap, false><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_occ, nullptr,
+                                                                       rays_per_count, ctr, d_ready, d_fault, make_pack_k());
 }
 static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
                           uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
@@ -391,7 +399,7 @@ static void launch_hybrid_cap(ri_b200_accel *a, const double *d_rays, uint32_t m
     const size_t smem = sizeof(HybSmem<kCap>);
 #define B200_HYB_LAUNCH(C, X) do { auto kern = occluded_hybrid_kernel<kCap, C, X>;                                               \
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                      \
-        kern<<<blocks, kBlock, smem, st>>>(S, S64, tt, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, K, H); } while (0)
+        kern<<<blocks, kHybThreads, smem, st>>>(S, S64, tt, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, K, H); } while (0)
     if (d_counts) { if (exact) B200_HYB_LAUNCH(true, true); else B200_HYB_LAUNCH(true, false); }
     else          { if (exact) B200_HYB_LAUNCH(false, true); else B200_HYB_LAUNCH(false, false); }
 #undef B200_HYB_LAUNCH
@@ -405,11 +413,11 @@ static bool launch_hybrid(ri_b200_accel *a, const double *d_rays, uint32_t m, ui
     auto blocks_for = [&](const void *kern, size_t smem) -> unsigned {
         int per_sm = 0;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHybThreads, smem);
         if (per_sm < 1) per_sm = 1;
         const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
         uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
-        want = (want + (kBlock / 32) - 1) / (kBlock / 32);
+        want = (want + (kHybThreads / 32) - 1) / (kHybThreads / 32);
         return (unsigned)(want < capb ? want : capb);
     };
     if (cap <= 20) launch_hybrid_cap<20>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault,

@@ -47,9 +47,16 @@ struct HybWarp {
     double r64[32 * 9];     // per lane: org.xyz dir.xyz inv.xyz in double, for the on-the-spot double tests
     uint2  desc[32];        // leaf-round descriptors
 };
+#ifndef B200_HYB_THREADS
+#define B200_HYB_THREADS 256
+#endif
+#ifndef B200_HYB_CTAS
+#define B200_HYB_CTAS 4
+#endif
+constexpr int kHybThreads = B200_HYB_THREADS;
 template <int kCap> struct HybSmem {
-    uint32_t stack[kCap * kBlock];
-    HybWarp  warp[kBlock / 32];
+    uint32_t stack[kCap * kHybThreads];
+    HybWarp  warp[kHybThreads / 32];
 };
 
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
@@ -155,7 +162,7 @@ __device__ __forceinline__ uint32_t hyb_pair(const PackK &K, const P4 &c0, const
 }
 
 template <int kCap, bool kCounts, bool kExact>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kHybThreads, B200_HYB_CTAS)
 occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, const char *__restrict__ trisT, const double *__restrict__ rays,
                        const uint32_t n, const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts,
                        const uint32_t rays_per_count, unsigned int *__restrict__ work_counter, const unsigned int *__restrict__ ready,
@@ -166,7 +173,7 @@ occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, co
 #define B200_HYB_REFILL 8
 #endif
     constexpr uint32_t kRefillAt = B200_HYB_REFILL, kLeafAt = 32u;
-    constexpr uint32_t kRow = kBlock * 4u;
+    constexpr uint32_t kRow = kHybThreads * 4u;
     constexpr float kU = 5.9604645e-8f;                                // 2^-24
     extern __shared__ __align__(16) unsigned char hyb_smem[];          // one HybSmem<kCap> (more than the 48 KB a static array may have)
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
@@ -430,7 +437,10 @@ struct HybCWarp {
     double leaf_uv[64], best_uv[64];   // per lane: (u, v) of the leaf-local / committed record; their t live in registers
     uint32_t win[32], leaf_prim[32], best_prim[32];
 };
-constexpr int kHcThreads = 128;
+#ifndef B200_HC_THREADS
+#define B200_HC_THREADS 128
+#endif
+constexpr int kHcThreads = B200_HC_THREADS;
 template <int kCap> struct HybCSmem {
     uint32_t stack[kCap * kHcThreads];
     HybCWarp warp[kHcThreads / 32];

@@ -70,13 +70,20 @@ struct Pool32Warp {
     float4 rays[64];                     // a lane's (org, dir): 32 bytes, read by the lanes that test its leaf items
     uint2  desc[32];                     // leaf-round descriptors of this warp (one address register serves both areas)
 };
+#ifndef B200_OCC_THREADS
+#define B200_OCC_THREADS 64       // C3 / C5 occlusion, Mrays/s (scripts/gpu_r3i.sh): 64 x 16: 1123 / 983; 256 x 4: 1113 / 968; 128 x 8: 1114 / 970;
+#endif
+#ifndef B200_OCC_CTAS
+#define B200_OCC_CTAS 16          // 192 x 5: 1093 / 937; 128 x 7 and 128 x 6 at 71 registers: 1072 / 927, 1079 / 938
+#endif
+constexpr int kOccThreads = B200_OCC_THREADS;       // CTA size / CTAs per SM of the occlusion kernel (A/B knobs)
 template <int kCap> struct Pool32Smem {
-    uint32_t   stack[kCap * kBlock];     // [depth][thread]: conflict-free columns
-    Pool32Warp warp[kBlock / 32];
+    uint32_t   stack[kCap * kOccThreads];     // [depth][thread]: conflict-free columns
+    Pool32Warp warp[kOccThreads / 32];
 };
 
 template <int kCap, bool kCounts>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kOccThreads, B200_OCC_CTAS)
 occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
                        const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
                        unsigned int *__restrict__ work_counter, const unsigned int *__restrict__ ready, unsigned int *__restrict__ fault,
@@ -90,7 +97,7 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
 #define B200_OCC_LEAFAT 32
 #endif
     constexpr uint32_t kRefillAt = B200_OCC_REFILL, kLeafAt = B200_OCC_LEAFAT;
-    constexpr uint32_t kRow = kBlock * 4u;                             // bytes between two stack levels of a lane
+    constexpr uint32_t kRow = kOccThreads * 4u;                        // bytes between two stack levels of a lane
     __shared__ __align__(16) Pool32Smem<kCap> sm;
     const unsigned lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
     const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
