@@ -245,24 +245,33 @@ static void launch_closest_pool(ri_b200_accel *a, const Real *d_rays, uint32_t m
 
 // pool32.cuh: fp32 occlusion with static shared memory.  Returns false when it does not apply (fp64 records, a tree deeper than
 // the largest instantiated stack, B200_POOL32=0 or one of pool.cuh's experiment knobs) and the generic pooled kernel should run.
+// Child order of the occlusion traversers (pool32.cuh has the measurements): longer-path-first while the fp32 records fit in L2 with
+// room to spare, nearer-box-first beyond; B200_ANYHIT_ORDER=0|1|2 overrides (0 = the reference's order).
+static int anyhit_order(const ri_b200_accel *a)
+{
+    if (const char *e = getenv("B200_ANYHIT_ORDER")) return atoi(e);
+    const uint64_t bytes = (uint64_t)a->flat.ninner * sizeof(Node32) + a->flat.nslots * sizeof(Tri32);
+    return bytes <= (96ull << 20) ? 1 : 2;
+}
+
 template <int kCap>
 static void launch_pool32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
                               uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
 {
     (void)blocks;                       // the caller's count assumes its own CTA size: this kernel has its own
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occluded_pool32_kernel<kCap, false>, kOccThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, occluded_pool32_kernel<kCap, false, 1>, kOccThreads, 0);
     if (per_sm < 1) per_sm = 1;
     const uint64_t capb = (uint64_t)per_sm * (uint64_t)a->sm_count;
     uint64_t want = ((uint64_t)m + chunk - 1) / chunk;
     want = (want + (kOccThreads / 32) - 1) / (kOccThreads / 32);
     const unsigned nb = (unsigned)(want < capb ? want : capb);
-    if (d_counts)
-        occluded_pool32_kernel<kCap, true><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, nullptr, d_counts,
-                                                                      rays_per_count, ctr, d_ready, d_fault, make_pack_k());
-    else
-        occluded_pool32_kernel<kCap, false><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, d_occ, nullptr,
-                                                                       rays_per_count, ctr, d_ready, d_fault, make_pack_k());
+    const int order = anyhit_order(a);
+#define B200_P32_LAUNCH(C, O) occluded_pool32_kernel<kCap, C, O><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, \
+        (C) ? nullptr : d_occ, (C) ? d_counts : nullptr, rays_per_count, ctr, d_ready, d_fault, make_pack_k())
+    if (d_counts) { if (order == 1) B200_P32_LAUNCH(true, 1); else if (order == 2) B200_P32_LAUNCH(true, 2); else B200_P32_LAUNCH(true, 0); }
+    else          { if (order == 1) B200_P32_LAUNCH(false, 1); else if (order == 2) B200_P32_LAUNCH(false, 2); else B200_P32_LAUNCH(false, 0); }
+#undef B200_P32_LAUNCH
 }
 static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
                           uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
@@ -281,6 +290,8 @@ static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, u
 
 // hybrid.cuh: double-exact occlusion through the fp32 records with certified decisions, the double records only where fp32 cannot
 // decide.  Applies to double rays when BOTH record sets are resident and the tree fits a static stack; B200_HYBRID=0 turns it off.
+static int anyhit_order(const ri_b200_accel *a);
+
 static bool hybrid_applies(const ri_b200_accel *a)
 {
     const char *env = getenv("B200_HYBRID");                      // read per launch: tests and A/B scripts switch it inside one process
@@ -312,6 +323,7 @@ static HybK hybrid_consts(const ri_b200_accel *a)
     }
     H.eta0 = (!own && a->verts_f32) ? 0.0f : 5.9604645e-8f * bm;   // own records: v0 - c is rounded once to fp32
     H.de = own ? 0.0f : 2.0f * H.eta0;                             // own records: edges are the double edges rounded once (relative error only)
+    H.order = anyhit_order(a);
     return H;
 }
 static SceneView<float> hybrid_view(const ri_b200_accel *a)

@@ -39,7 +39,8 @@ struct HybK {
     float  bmax[3];         // largest |coordinate| of the (translated) scene box per axis
     float  eta0;            // absolute error of a vertex coordinate in the fp32 slots: 0 (all vertices are fp32 numbers) or u * max_k bmax_k
     float  de;              // absolute error of an fp32 edge component beyond its relative rounding: 0 (edges rounded from doubles) or 2 * eta0
-    double c[3];            // origin of the fp32 records the kernel reads (hybrid_records.cuh): the filter works on coordinates minus c
+    double c[3];            // origin of the fp32 records the kernel reads (end of this file): the filter works on coordinates minus c
+    int    order;           // occlusion kernel: child order when both children are kept (pool32.cuh): 1 longer path first, 2 nearer first, 0 reference
 };
 
 struct HybWarp {
@@ -83,21 +84,6 @@ __device__ __noinline__ bool hyb_tri64(const Tri64 *__restrict__ tp, const uint3
     double t = 1.0e38, u = 0.0, v = 0.0;
     const bool ok = tri_test<double>(tr, org, dir, t, u, v);
     return ok && (t < 1.0e38);
-}
-
-// packed slab arithmetic of slab_pk (packed.cuh), returning the interval instead of the verdict
-__device__ __forceinline__ void slab_pk_t(const PackK &K, pk_t bx, pk_t by, pk_t bz, pk_t ox, pk_t oy, pk_t oz, pk_t ix, pk_t iy, pk_t iz,
-                                          bool sx, bool sy, bool sz, float &tmin, float &tmax)
-{
-    float lx, hx, ly, hy, lz, hz;
-    upk2(pmul(K, psub(K, bx, ox), ix), lx, hx);
-    upk2(pmul(K, psub(K, by, oy), iy), ly, hy);
-    upk2(pmul(K, psub(K, bz, oz), iz), lz, hz);
-    const float tnx = sx ? hx : lx, tfx = sx ? lx : hx;
-    const float tny = sy ? hy : ly, tfy = sy ? ly : hy;
-    const float tnz = sz ? hz : lz, tfz = sz ? lz : hz;
-    tmin = fmaxf(fmaxf(tnx, tny), tnz);
-    tmax = fminf(fminf(tfx, tfy), tfz);
 }
 
 // 1 = the reference certainly accepts, 0 = certainly rejects, 2 = undecided at fp32
@@ -348,7 +334,8 @@ occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, co
                     if (u1) h1 = hyb_box64(bx + 2, q, sgn);
                 }
                 const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
-                const bool order = ((sgn >> axis) & 1u) != 0u;
+                const bool order = H.order == 1 ? (tf1 - fmaxf(tn1, 0.0f)) > (tf0 - fmaxf(tn0, 0.0f))      // any order gives the same answer
+                                 : H.order == 2 ? tn1 < tn0 : ((sgn >> axis) & 1u) != 0u;
                 const uint32_t near = order ? c1 : c0, far = order ? c0 : c1;
                 const bool both = h0 && h1, none = !h0 && !h1;
                 const bool pop = none && (spa >= kRow);

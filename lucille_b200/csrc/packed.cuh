@@ -182,6 +182,21 @@ __device__ __forceinline__ bool slab_pk(const PackK &K, pk_t bx, pk_t by, pk_t b
     const float tmax = fminf(fminf(tfx, tfy), tfz);
     return (tmax > 0.0f) && (tmin <= tmax) && (tmin < best_t);
 }
+// packed slab arithmetic of slab_pk (packed.cuh), returning the interval instead of the verdict
+__device__ __forceinline__ void slab_pk_t(const PackK &K, pk_t bx, pk_t by, pk_t bz, pk_t ox, pk_t oy, pk_t oz, pk_t ix, pk_t iy, pk_t iz,
+                                          bool sx, bool sy, bool sz, float &tmin, float &tmax)
+{
+    float lx, hx, ly, hy, lz, hz;
+    upk2(pmul(K, psub(K, bx, ox), ix), lx, hx);
+    upk2(pmul(K, psub(K, by, oy), iy), ly, hy);
+    upk2(pmul(K, psub(K, bz, oz), iz), lz, hz);
+    const float tnx = sx ? hx : lx, tfx = sx ? lx : hx;
+    const float tny = sy ? hy : ly, tfy = sy ? ly : hy;
+    const float tnz = sz ? hz : lz, tfz = sz ? lz : hz;
+    tmin = fmaxf(fmaxf(tnx, tny), tnz);
+    tmax = fminf(fminf(tfx, tfy), tfz);
+}
+
 #endif
 
 }  // namespace b200

@@ -82,7 +82,7 @@ template <int kCap> struct Pool32Smem {
     Pool32Warp warp[kOccThreads / 32];
 };
 
-template <int kCap, bool kCounts>
+template <int kCap, bool kCounts, int kOrder>
 __global__ void __launch_bounds__(kOccThreads, B200_OCC_CTAS)
 occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
                        const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
@@ -233,10 +233,20 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                 const pk_t ox = pkb(org[0]), oy = pkb(org[1]), oz = pkb(org[2]);
                 const pk_t ix = pkb(inv[0]), iy = pkb(inv[1]), iz = pkb(inv[2]);
                 const bool sx = (sgn & 1u) != 0u, sy = (sgn & 2u) != 0u, sz = (sgn & 4u) != 0u;
-                const bool h0 = slab_pk(K, a.v[0], a.v[2], b.v[0], ox, oy, oz, ix, iy, iz, sx, sy, sz, 1.0e38f);
-                const bool h1 = slab_pk(K, a.v[1], a.v[3], b.v[1], ox, oy, oz, ix, iy, iz, sx, sy, sz, 1.0e38f);
+                // An occlusion query may visit the children in ANY order (pool.cuh): the answer is the OR over the same leaves.  Which
+                // child first finds a hit soonest?  kOrder 1: the one the ray runs through for longer (hit probability ~ path length
+                // x density) -- best when the records are L2-resident (C3: 1123 -> 1195 Mrays/s), but it sends the rays of one point to
+                // distant subtrees, which costs DRAM traffic on a scene beyond L2 (10 M triangles: 975 -> 914); kOrder 2: the nearer
+                // box by its entry distance (1137 / 989): the host picks by the size of the records.  kOrder 0: the reference's
+                // near child = child[sign[axis0]], kept for A/B.
+                float tn0, tf0, tn1, tf1;
+                slab_pk_t(K, a.v[0], a.v[2], b.v[0], ox, oy, oz, ix, iy, iz, sx, sy, sz, tn0, tf0);
+                slab_pk_t(K, a.v[1], a.v[3], b.v[1], ox, oy, oz, ix, iy, iz, sx, sy, sz, tn1, tf1);
+                const bool h0 = (tf0 > 0.0f) && (tn0 <= tf0) && (tn0 < 1.0e38f), h1 = (tf1 > 0.0f) && (tn1 <= tf1) && (tn1 < 1.0e38f);
                 const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
-                const bool order = ((sgn >> axis) & 1u) != 0u;                    // near child = child[sign[axis0]]
+                const bool order = kOrder == 1 ? (tf1 - fmaxf(tn1, 0.0f)) > (tf0 - fmaxf(tn0, 0.0f))
+                                 : kOrder == 2 ? tn1 < tn0
+                                               : ((sgn >> axis) & 1u) != 0u;
                 const uint32_t near = order ? c1 : c0, far = order ? c0 : c1;
                 uint32_t next;
                 const bool both = h0 && h1, none = !h0 && !h1;                   // predicated: measured 1080 vs 1072 Mrays/s for the branchy form
