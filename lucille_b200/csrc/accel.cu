@@ -269,8 +269,8 @@ static void launch_pool32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m,
     const int order = anyhit_order(a);
 #define B200_P32_LAUNCH(C, O) occluded_pool32_kernel<kCap, C, O><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, \
         (C) ? nullptr : d_occ, (C) ? d_counts : nullptr, rays_per_count, ctr, d_ready, d_fault, make_pack_k())
-    if (d_counts) { if (order == 1) B200_P32_LAUNCH(true, 1); else if (order == 2) B200_P32_LAUNCH(true, 2); else B200_P32_LAUNCH(true, 0); }
-    else          { if (order == 1) B200_P32_LAUNCH(false, 1); else if (order == 2) B200_P32_LAUNCH(false, 2); else B200_P32_LAUNCH(false, 0); }
+    if (d_counts) { if (order == 1) B200_P32_LAUNCH(true, 1); else if (order == 2) B200_P32_LAUNCH(true, 2); else if (order == 3) B200_P32_LAUNCH(true, 3); else B200_P32_LAUNCH(true, 0); }
+    else          { if (order == 1) B200_P32_LAUNCH(false, 1); else if (order == 2) B200_P32_LAUNCH(false, 2); else if (order == 3) B200_P32_LAUNCH(false, 3); else B200_P32_LAUNCH(false, 0); }
 #undef B200_P32_LAUNCH
 }
 static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,

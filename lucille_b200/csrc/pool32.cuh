@@ -10,7 +10,9 @@
 //   * the per-lane stack pointer is kept as a BYTE OFFSET that already contains the lane's column (push / pop = one add);
 //   * the ray's three sign bits live in one mask: near child = (mask >> axis) & 1 instead of two selects and a compare;
 //   * leaf-round / refill thresholds and the result kind (occlusion bytes or per-point counters) are template constants;
-//   * the acceptance window of triangle_isect is a chain of predicated SETPs (one instruction per comparison).
+//   * the acceptance window of triangle_isect is a chain of predicated SETPs (one instruction per comparison);
+//   * when both children of a node are kept, the one more likely to end the query is visited first (kOrder, at the node step): an
+//     occlusion query may visit leaves in any order, the near-child-first rule of the reference only matters for closest hits.
 // Arithmetic: packed.cuh (FFMA2 on (A, B) triangle pairs and (lo, hi) box planes, each result rounded like the scalar operation).
 // Trees deeper than the largest instantiated stack, fp64 records and the experiments stay with pool.cuh.
 #pragma once
@@ -244,8 +246,10 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                 slab_pk_t(K, a.v[1], a.v[3], b.v[1], ox, oy, oz, ix, iy, iz, sx, sy, sz, tn1, tf1);
                 const bool h0 = (tf0 > 0.0f) && (tn0 <= tf0) && (tn0 < 1.0e38f), h1 = (tf1 > 0.0f) && (tn1 <= tf1) && (tn1 < 1.0e38f);
                 const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
-                const bool order = kOrder == 1 ? (tf1 - fmaxf(tn1, 0.0f)) > (tf0 - fmaxf(tn0, 0.0f))
-                                 : kOrder == 2 ? tn1 < tn0
+                const bool longer = (tf1 - fmaxf(tn1, 0.0f)) > (tf0 - fmaxf(tn0, 0.0f)), nearer = tn1 < tn0;
+                const bool order = kOrder == 1 ? longer
+                                 : kOrder == 2 ? nearer
+                                 : kOrder == 3 ? (cur < S.top_count ? nearer : longer)       // experiment: locality at the top, probability below
                                                : ((sgn >> axis) & 1u) != 0u;
                 const uint32_t near = order ? c1 : c0, far = order ? c0 : c1;
                 uint32_t next;
