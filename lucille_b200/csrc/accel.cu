@@ -655,7 +655,13 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         return 0;
     };
     if (body() != 0) { ri_b200_free(a); return nullptr; }
-    if ((precisions & RI_B200_PREC_F32) && (precisions & RI_B200_PREC_F64) && hybrid_build_records(a) != 0) { ri_b200_free(a); return nullptr; }
+    if ((precisions & RI_B200_PREC_F32) && (precisions & RI_B200_PREC_F64) && hybrid_build_records(a) != 0) {
+        // not fatal: without them the filter reads the shared fp32 records with the wider bounds that go with them (same answers, slower)
+        fprintf(stderr, "[b200] the hybrid kernels' own fp32 records could not be built (%s); using the shared records\n", g_err);
+        cudaGetLastError();
+        cudaFree(a->d_nodesH); cudaFree(a->d_trisH);
+        a->d_nodesH = nullptr; a->d_trisH = nullptr;
+    }
     a->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     // flat host copies are no longer needed (keep the small header fields)
     std::vector<Node32>().swap(a->flat.nodes32); std::vector<Tri32>().swap(a->flat.tris32);
