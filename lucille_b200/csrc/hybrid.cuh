@@ -293,8 +293,8 @@ occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, co
                     if (!hit && (k & 6u)) {                                      // undecided triangles: the reference's test on the double slot
                         const Tri64 *tp = S64.tris + slot0 + 2u * item;
                         const uint32_t q = r64_a + own * 72u;
-                        if (k & 2u) hit = hyb_tri64(tp, q);
-                        if (!hit && (k & 4u)) hit = hyb_tri64(tp + 1, q);
+                        hit = hyb_tri64((k & 2u) ? tp : tp + 1, q);                 // ONE call site serves either triangle: the warp runs the
+                        if (!hit && (k & 6u) == 6u) hit = hyb_tri64(tp + 1, q);     // double routine once per round, twice only when a lane needs both
                     }
                 }
                 const unsigned hits = __ballot_sync(FULL, hit);
@@ -330,8 +330,9 @@ occluded_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, co
                 if (u0 || u1) {                                                  // undecided: the double record of this node
                     const double *bx = S64.nodes[cur].x;
                     const uint32_t q = r64_a + lane * 72u;
-                    if (u0) h0 = hyb_box64(bx, q, sgn);
-                    if (u1) h1 = hyb_box64(bx + 2, q, sgn);
+                    const bool r = hyb_box64(u0 ? bx : bx + 2, q, sgn);                 // one call site for either child
+                    if (u0) h0 = r; else h1 = r;
+                    if (u0 && u1) h1 = hyb_box64(bx + 2, q, sgn);
                 }
                 const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
                 const bool order = H.order == 1 ? (tf1 - fmaxf(tn1, 0.0f)) > (tf0 - fmaxf(tn0, 0.0f))      // any order gives the same answer
@@ -613,8 +614,8 @@ closest_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, con
                         uint32_t prim = 0xffffffffu;
                         const Tri64 *tp = S64.tris + slot0 + 2u * item;
                         const uint32_t q = r64_a + own * 72u;
-                        if (mA) hyb_tri64_hit(tp, q, t, u, v, prim);
-                        if (mB) hyb_tri64_hit(tp + 1, q, t, u, v, prim);
+                        hyb_tri64_hit(mA ? tp : tp + 1, q, t, u, v, prim);           // one call site for either triangle (see the occlusion kernel)
+                        if (mA && mB) hyb_tri64_hit(tp + 1, q, t, u, v, prim);
                         if (prim != 0xffffffffu) {
                             PoolRes<double> r;
                             r.t = t; r.u = u; r.v = v; r.prim = prim; r.pad = 0u;
@@ -664,8 +665,9 @@ closest_hybrid_kernel(const SceneView<float> S, const SceneView<double> S64, con
                 if (u0 || u1) {
                     const double *bx = S64.nodes[cur].x;
                     const uint32_t q = r64_a + lane * 72u;
-                    if (u0) h0 = hyb_box64_best(bx, q, sgn, best_t);
-                    if (u1) h1 = hyb_box64_best(bx + 2, q, sgn, best_t);
+                    const bool r = hyb_box64_best(u0 ? bx : bx + 2, q, sgn, best_t);    // one call site for either child
+                    if (u0) h0 = r; else h1 = r;
+                    if (u0 && u1) h1 = hyb_box64_best(bx + 2, q, sgn, best_t);
                 }
                 const uint32_t c0 = (uint32_t)b.v[2], c1 = (uint32_t)(b.v[2] >> 32), axis = (uint32_t)b.v[3];
                 const bool order = ((sgn >> axis) & 1u) != 0u;
