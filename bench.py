@@ -574,6 +574,9 @@ def main():
             roof["dram_frac"] = traffic / (ms / args.steps * 1e-3) / 1e9 / peak
         if km:
             roof["limiter"] = km
+            # `bound` above is the contract's label for the algorithmic-bytes roofline; what ncu shows as the limiting unit:
+            roof["physical_bound"] = ("l1_data_pipe_lsu_wavefronts" if km.get("lsu_wavefront_frac", 0) >= km.get("issue_frac", 0) else "warp_instruction_issue")
+            roof["physical_bound_frac"] = max(km.get("lsu_wavefront_frac", 0), km.get("issue_frac", 0))
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
