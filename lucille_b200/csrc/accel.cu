@@ -75,6 +75,7 @@ struct ri_b200_accel {
     uint32_t  mt_states_cap = 0, mt_states_seed = 0;
     ri_b200_hit_exchange_fn hit_exchange = nullptr;      // rng_mode 0 over several ranks (frame.cuh)
     void     *hit_exchange_user = nullptr;
+    float4 *d_k6_rays = nullptr; uint32_t *d_k6_perm = nullptr; unsigned int *d_k6_ctr = nullptr; uint64_t k6_cap = 0;   // reorder.cuh scratch (lock held)
     bool verts_f32 = false;               // every vertex coordinate is an fp32 number (hybrid.cuh: no absolute error in the fp32 slots)
     Node32 *d_nodesH = nullptr; Tri32 *d_trisH = nullptr;      // hybrid.cuh's own fp32 records, relative to hyb_c (NULL: it reads the shared ones)
     double hyb_c[3] = {0.0, 0.0, 0.0};
@@ -203,6 +204,7 @@ trace_batch_kernel(const SceneView<Real> S, const Real *__restrict__ rays, const
 #include "packed.cuh"
 #include "pool.cuh"
 #include "pool32.cuh"
+#include "reorder.cuh"
 #include "pool_closest.cuh"
 #include "hybrid.cuh"
 
@@ -256,7 +258,8 @@ static int anyhit_order(const ri_b200_accel *a)
 
 template <int kCap>
 static void launch_pool32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
-                              uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+                              uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st,
+                              const uint32_t *d_perm)
 {
     (void)blocks;                       // the caller's count assumes its own CTA size: this kernel has its own
     int per_sm = 0;
@@ -268,25 +271,31 @@ static void launch_pool32_cap(ri_b200_accel *a, const float *d_rays, uint32_t m,
     const unsigned nb = (unsigned)(want < capb ? want : capb);
     const int order = anyhit_order(a);
 #define B200_P32_LAUNCH(C, O) occluded_pool32_kernel<kCap, C, O><<<nb, kOccThreads, 0, st>>>(make_view<float>(a), pool_tris(a, 0.0f), d_rays, m, chunk, \
-        (C) ? nullptr : d_occ, (C) ? d_counts : nullptr, rays_per_count, ctr, d_ready, d_fault, make_pack_k())
+        (C) ? nullptr : d_occ, (C) ? d_counts : nullptr, rays_per_count, ctr, d_ready, d_fault, make_pack_k(), d_perm)
     if (d_counts) { if (order == 1) B200_P32_LAUNCH(true, 1); else if (order == 2) B200_P32_LAUNCH(true, 2); else if (order == 3) B200_P32_LAUNCH(true, 3); else B200_P32_LAUNCH(true, 0); }
     else          { if (order == 1) B200_P32_LAUNCH(false, 1); else if (order == 2) B200_P32_LAUNCH(false, 2); else if (order == 3) B200_P32_LAUNCH(false, 3); else B200_P32_LAUNCH(false, 0); }
 #undef B200_P32_LAUNCH
 }
-static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
-                          uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st)
+static bool pool32_applies(const ri_b200_accel *a)
 {
     static const bool off = (getenv("B200_POOL32") && atoi(getenv("B200_POOL32")) == 0) || getenv("B200_POOL_TOPSMEM") || getenv("B200_REFILL") ||
                             getenv("B200_LEAF_AT") || getenv("B200_QUADFETCH");
+    static const bool pool_off = getenv("B200_POOL") && atoi(getenv("B200_POOL")) == 0;
+    return !off && !pool_off && stack_capacity(a) <= 36;
+}
+static bool launch_pool32(ri_b200_accel *a, const float *d_rays, uint32_t m, uint32_t chunk, uint8_t *d_occ, uint32_t *d_counts,
+                          uint32_t rays_per_count, unsigned int *ctr, const unsigned int *d_ready, unsigned int *d_fault, unsigned blocks, cudaStream_t st,
+                          const uint32_t *d_perm)
+{
     const int cap = stack_capacity(a);
-    if (off || cap > 36) return false;
-    if (cap <= 20) launch_pool32_cap<20>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st);
-    else if (cap <= 28) launch_pool32_cap<28>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st);
-    else launch_pool32_cap<36>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st);
+    if (!pool32_applies(a)) return false;
+    if (cap <= 20) launch_pool32_cap<20>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st, d_perm);
+    else if (cap <= 28) launch_pool32_cap<28>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st, d_perm);
+    else launch_pool32_cap<36>(a, d_rays, m, chunk, d_occ, d_counts, rays_per_count, ctr, d_ready, d_fault, blocks, st, d_perm);
     return true;
 }
 static bool launch_pool32(ri_b200_accel *, const double *, uint32_t, uint32_t, uint8_t *, uint32_t *, uint32_t, unsigned int *,
-                          const unsigned int *, unsigned int *, unsigned, cudaStream_t) { return false; }
+                          const unsigned int *, unsigned int *, unsigned, cudaStream_t, const uint32_t *) { return false; }
 
 // hybrid.cuh: double-exact occlusion through the fp32 records with certified decisions, the double records only where fp32 cannot
 // decide.  Applies to double rays when BOTH record sets are resident and the tree fits a static stack; B200_HYBRID=0 turns it off.
@@ -467,7 +476,7 @@ static bool launch_closest32(ri_b200_accel *a, const float *d_rays, uint32_t m, 
 template <typename Real, bool ANYHIT, bool COUNT>
 static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typename RayIO<Real>::Hit *d_hits, uint8_t *d_occ,
                         unsigned long long *d_counters, cudaStream_t st, uint32_t *d_counts = nullptr, uint32_t rays_per_count = 1,
-                        const unsigned int *d_ready = nullptr, unsigned int *d_fault = nullptr)
+                        const unsigned int *d_ready = nullptr, unsigned int *d_fault = nullptr, const uint32_t *d_perm = nullptr)
 {
     if (n == 0) return 0;
     const int cap = stack_capacity(a);
@@ -517,7 +526,7 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
                                              d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, d_ready, d_fault, blocks, st))
                 ;                                // double rays, both record sets resident: certified fp32 decisions, doubles where needed (hybrid.cuh)
             else if (pooled && launch_pool32(a, d_rays + done * RayIO<Real>::kRayStride, m, chunk, d_occ ? d_occ + done : nullptr,
-                                             d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, d_ready, d_fault, blocks, st))
+                                             d_counts ? d_counts + done / rays_per_count : nullptr, rays_per_count, ctr, d_ready, d_fault, blocks, st, d_perm))
                 ;                                // fp32 occlusion on a tree that fits a static stack: the specialised kernel (pool32.cuh)
             else if (pooled)
                 pool<<<blocks, kBlock, pool_smem, st>>>(make_view<Real>(a), pool_tris(a, Real(0)), d_rays + done * RayIO<Real>::kRayStride, m, chunk,
@@ -540,6 +549,46 @@ static int launch_trace(ri_b200_accel *a, const Real *d_rays, uint64_t n, typena
     LAUNCHED();
     CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// Occlusion batches of the entry points that hold the accelerator's lock (frames, point entries): with B200_K6=1 the batch is first put
+// into octant-major order (reorder.cuh, K6) in the accelerator's scratch and traced through the permutation.
+template <typename Real>
+static int trace_occlusion_locked(ri_b200_accel *a, const Real *d_rays, uint64_t n, uint8_t *d_occ, uint32_t *d_counts, uint32_t rays_per_count,
+                                  cudaStream_t st)
+{ return launch_trace<Real, true, false>(a, d_rays, n, nullptr, d_occ, nullptr, st, d_counts, rays_per_count); }
+
+template <>
+int trace_occlusion_locked<float>(ri_b200_accel *a, const float *d_rays, uint64_t n, uint8_t *d_occ, uint32_t *d_counts, uint32_t rays_per_count,
+                                  cudaStream_t st)
+{
+    const char *env = getenv("B200_K6");
+    const int mode = env ? atoi(env) : -1;
+    const bool sort = mode == 1;          // off by default: see reorder.cuh for the measurements that decided it
+    if (!sort || !pool32_applies(a) || n >= (1ull << 31) || a->tree.empty)
+        return launch_trace<float, true, false>(a, d_rays, n, nullptr, d_occ, nullptr, st, d_counts, rays_per_count);
+    if (a->k6_cap < n) {
+        cudaFree(a->d_k6_rays); cudaFree(a->d_k6_perm); a->d_k6_rays = nullptr; a->d_k6_perm = nullptr; a->k6_cap = 0;
+        cudaFree(a->d_k6_ctr); a->d_k6_ctr = nullptr;
+        const uint64_t nt = (n + kK6Tile - 1) / kK6Tile;
+        if (cudaMalloc((void **)&a->d_k6_ctr, 8 * nt * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc((void **)&a->d_k6_rays, n * 32) != cudaSuccess || cudaMalloc((void **)&a->d_k6_perm, n * 4) != cudaSuccess) {
+            cudaGetLastError();                      // no room for the scratch batch: trace in input order
+            cudaFree(a->d_k6_rays); a->d_k6_rays = nullptr;
+            return launch_trace<float, true, false>(a, d_rays, n, nullptr, d_occ, nullptr, st, d_counts, rays_per_count);
+        }
+        a->k6_cap = n;
+    }
+    const uint32_t ntiles = (uint32_t)((n + kK6Tile - 1) / kK6Tile);
+    k6_hist_kernel<<<ntiles, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_rays), (uint32_t)n, ntiles, a->d_k6_ctr);
+    LAUNCHED();
+    k6_scan_kernel<<<1, 1024, 0, st>>>(a->d_k6_ctr, 8u * ntiles);
+    LAUNCHED();
+    k6_scatter_kernel<<<ntiles, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_rays), (uint32_t)n, ntiles, a->d_k6_ctr, a->d_k6_rays, a->d_k6_perm);
+    LAUNCHED();
+    CUDA_OK(cudaGetLastError());
+    return launch_trace<float, true, false>(a, reinterpret_cast<const float *>(a->d_k6_rays), n, nullptr, d_occ, nullptr, st, d_counts, rays_per_count,
+                                            nullptr, nullptr, a->d_k6_perm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,7 +726,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
-    cudaFree(a->d_nodesH); cudaFree(a->d_trisH);
+    cudaFree(a->d_nodesH); cudaFree(a->d_trisH); cudaFree(a->d_k6_rays); cudaFree(a->d_k6_perm); cudaFree(a->d_k6_ctr);
     cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags); cudaFree(a->d_tex);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }
     cudaFree(a->d_whole_in); cudaFree(a->d_whole_out);

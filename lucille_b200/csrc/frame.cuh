@@ -930,7 +930,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
                 const uint64_t nr = (uint64_t)ns * 64;
                 ao_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(F, nr, r0, d_rec, d_ranks, d_pix, d_mt, d_rays);
                 LAUNCHED();
-                if (launch_trace<Real, true, false>(a, d_rays, nr, nullptr, d_occ8, nullptr, st)) return -1;
+                if (trace_occlusion_locked<Real>(a, d_rays, nr, d_occ8, nullptr, 1, st)) return -1;
                 if (nsun) {
                     const uint64_t nsr = (uint64_t)ns * nsun;
                     sun_rays_kernel<Real><<<(unsigned)((nsr + 255) / 256), 256, 0, st>>>(d_sky, d_rec, r0, ns, d_sunrays);
@@ -986,7 +986,7 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
             LAUNCHED();
             if (d_dump && r0 == 0 && dump_count)
                 CUDA_OK(cudaMemcpyAsync(d_dump, d_rays, (dump_count < nr ? dump_count : nr) * ray_words * sizeof(Real), cudaMemcpyDeviceToDevice, st));
-            if (launch_trace<Real, true, false>(a, d_rays, nr, nullptr, nullptr, nullptr, st, d_occ + r0, (uint32_t)N)) return -1;
+            if (trace_occlusion_locked<Real>(a, d_rays, nr, nullptr, d_occ + r0, (uint32_t)N, st)) return -1;
         }
     }
     CUDA_OK(cudaEventRecord(a->ev[4], st));

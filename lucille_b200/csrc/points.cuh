@@ -100,7 +100,7 @@ static int ao_points_run(ri_b200_accel *a, const ri_b200_ao_points_t *g, const d
         ao_points_gen_kernel<Real><<<(unsigned)((nr + kBlock - 1) / kBlock), kBlock, 0, st>>>(G, d_points, p0, nr, d_rays);
         LAUNCHED();
         CUDA_OK(cudaGetLastError());
-        if (launch_trace<Real, true, false>(a, d_rays, nr, nullptr, nullptr, nullptr, st, d_counts + p0, (uint32_t)N)) return -1;
+        if (trace_occlusion_locked<Real>(a, d_rays, nr, nullptr, d_counts + p0, (uint32_t)N, st)) return -1;
     }
     return 0;
 }
@@ -172,7 +172,7 @@ static int ao_points_host(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, cons
             LAUNCHED();
             CUDA_OK(cudaGetLastError());
         }
-        if (launch_trace<Real, true, false>(a, d_rays, np * N, nullptr, nullptr, nullptr, ks, d_counts + p0, (uint32_t)N)) return -1;
+        if (trace_occlusion_locked<Real>(a, d_rays, np * N, nullptr, d_counts + p0, (uint32_t)N, ks)) return -1;
         if (p0 + chunk_points < n) {                              // the next chunk's generation overwrites the ray buffer: wait for this traversal
             CUDA_OK(cudaEventRecord(a->ev[7], ks));
             CUDA_OK(cudaStreamWaitEvent(cs, a->ev[7], 0));

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kOccThreads, B200_OCC_CTAS)
 occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT, const float *__restrict__ rays, const uint32_t n,
                        const uint32_t chunk, uint8_t *__restrict__ occ, uint32_t *__restrict__ counts, const uint32_t rays_per_count,
                        unsigned int *__restrict__ work_counter, const unsigned int *__restrict__ ready, unsigned int *__restrict__ fault,
-                       const PackK K)
+                       const PackK K, const uint32_t *__restrict__ perm)
 {
     constexpr unsigned FULL = 0xffffffffu;
 #ifndef B200_OCC_REFILL
@@ -158,6 +158,7 @@ occluded_pool32_kernel(const SceneView<float> S, const char *__restrict__ trisT,
                 float dir[3];
                 if (ready) RayIO<float>::load_coherent(rays, idx, org, dir);      // the copy engine is still writing this buffer: no ld.global.nc
                 else RayIO<float>::load(rays, idx, org, dir);
+                if (perm) idx = __ldg(perm + idx);          // a reordered batch (reorder.cuh): results go back to the ray's place in the input
                 sts128(rays_a + lane * 32u, make_float4(org[0], org[1], org[2], 0.0f));
                 sts128(rays_a + lane * 32u + 16u, make_float4(dir[0], dir[1], dir[2], 0.0f));
                 const bool sx = dir[0] < 0.0f, sy = dir[1] < 0.0f, sz = dir[2] < 0.0f;

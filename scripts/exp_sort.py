@@ -37,10 +37,12 @@ def part1by2(x):
 
 def main():
     npoints = int(os.environ.get("POINTS", bench.NPOINTS))
-    tris = scenes.triangle_soup(bench.NTRIS, scenes.SEED_C3)
+    ntris = int(os.environ.get("NTRIS", bench.NTRIS))                # NTRIS=10000000 SEED=c5: the beyond-L2 scene of configs[4]
+    seed = scenes.SEED_C5 if os.environ.get("SEED", "c3") == "c5" else scenes.SEED_C3
+    tris = scenes.triangle_soup(ntris, seed)
     a = accel.Accel.bind(accel.RI_ACCEL_B200).build(tris, accel.PREC_F32)
     P, n = bench.primary_points(a.intersect, tris[a.triorder()])
-    rays = scenes.ao_rays(P[:npoints], n[:npoints], bench.NTHETA, bench.NPHI, scenes.SEED_C3)
+    rays = scenes.ao_rays(P[:npoints], n[:npoints], bench.NTHETA, bench.NPHI, seed)
     nr = len(rays)
     octant = ((rays[:, 4] < 0).astype(np.uint64) | ((rays[:, 5] < 0).astype(np.uint64) << np.uint64(1)) |
               ((rays[:, 6] < 0).astype(np.uint64) << np.uint64(2)))
@@ -52,6 +54,8 @@ def main():
         "batch": np.arange(nr),
         "oct_point": np.argsort(point * np.uint64(8) + octant, kind="stable"),
         "oct_global": np.argsort(octant * np.uint64(1 << 32) + point, kind="stable"),
+        "oct_8pts": np.argsort((point // np.uint64(8)) * np.uint64(8) + octant, kind="stable"),     # 8 neighbouring points' rays grouped by octant
+        "oct_32pts": np.argsort((point // np.uint64(32)) * np.uint64(8) + octant, kind="stable"),
         "morton_oct": np.argsort((morton << np.uint64(35)) | (octant << np.uint64(32)) | point, kind="stable"),
         "random": rng.permutation(nr),
     }
