@@ -34,8 +34,9 @@ extern "C" {
  * double frames) and closest hit (ri_b200_intersect_*_f64, the Whitted / dirt-map / trace() batches) -- run through the fp32 records
  * with a certified error bound on every box and triangle decision and consult the double records only for the decisions fp32 cannot
  * settle (csrc/hybrid.cuh): the double reference's answer for every ray, bit for bit, at 1.5-2x the rate of the double kernels.
- * Scenes whose vertices are not fp32 numbers, or that lie far from the world origin, get a second set of fp32 records for this at
- * build time (coordinates relative to the scene's centre, derived on the device from the double records; + 48 B per triangle slot).
+ * Scenes whose vertices are not fp32 numbers, or that lie far from the world origin -- and accelerators built with double records
+ * only -- get a set of fp32 records of their own for this at build time (coordinates relative to the scene's centre, derived on the
+ * device from the double records; + 48 B per triangle slot, 64 B per node).
  * B200_HYBRID=0 in the environment turns the path off (the double kernels run instead); B200_HYBRID_CLOSEST=0 its closest-hit form alone. */
 #define RI_B200_HOST_ONLY      0x100u        /* build + flatten on the host, no device upload: every trace call on
                                                 such an accelerator fails loudly (used by the CPU-only tests) */

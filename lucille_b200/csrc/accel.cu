@@ -305,7 +305,8 @@ static bool hybrid_applies(const ri_b200_accel *a)
 {
     const char *env = getenv("B200_HYBRID");                      // read per launch: tests and A/B scripts switch it inside one process
     const int mode = env ? atoi(env) : 1;                         // 0: never (the double kernels run)
-    return mode != 0 && stack_capacity(a) <= 28 && a->d_nodes32 && a->d_tris32t && a->d_nodes64 && a->d_tris64;
+    return mode != 0 && stack_capacity(a) <= 28 && a->d_nodes64 && a->d_tris64 &&
+           ((a->d_nodesH && a->d_trisH) || (a->d_nodes32 && a->d_tris32t));      // its own fp32 records, or the shared ones
 }
 
 // is the scene close enough to the world origin for the SHARED fp32 records (absolute coordinates) to give good bounds?
@@ -351,10 +352,13 @@ static bool hybrid_exact(const ri_b200_accel *a) { return a->verts_f32 && !a->d_
 // shared records lose to the double kernel (386 against 504 Mrays/s), the translated ones do not care where the scene sits.
 static int hybrid_build_records(ri_b200_accel *a)
 {
-    if (a->tree.empty || !a->d_nodes64 || !a->d_tris64 || !a->d_nodes32 || stack_capacity(a) > 28) return 0;
+    if (a->tree.empty || !a->d_nodes64 || !a->d_tris64 || stack_capacity(a) > 28) return 0;
     const char *env = getenv("B200_HYBRID_OWN");                   // A/B: 0 = never build them, 1 = always
     const int force = env ? atoi(env) : -1;
-    if (force == 0 || (force != 1 && a->verts_f32 && hybrid_near_origin(a))) return 0;
+    const bool shared_ok = a->d_nodes32 && a->d_tris32t && a->verts_f32 && hybrid_near_origin(a);     // the shared records serve as well
+    if (force == 0 || (force != 1 && shared_ok)) return 0;
+    // (an accelerator built with double records ONLY gets them too: its batched double queries then run at the hybrid rate instead of
+    // the double kernels' -- + 48 bytes per triangle slot and 64 per node next to the 96 / 128 of the double records)
     for (int k = 0; k < 3; ++k) a->hyb_c[k] = (double)(float)(0.5 * (a->tree.bmin[k] + a->tree.bmax[k]));
     const uint32_t ninner = a->flat.ninner;
     const uint64_t nslots = a->flat.nslots;
@@ -646,7 +650,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
     if (!a) { fail("out of memory"); return nullptr; }
     a->device = device;
     a->precisions = precisions;
-    if ((precisions & RI_B200_PREC_F32) && (precisions & RI_B200_PREC_F64)) {       // hybrid.cuh: are all vertex coordinates fp32 numbers?
+    if (precisions & RI_B200_PREC_F64) {                                             // hybrid.cuh: are all vertex coordinates fp32 numbers?
         bool exact = true;
         for (uint64_t i = 0; i < 9 * ntris && exact; ++i) exact = (double)(float)tri_xyz[i] == tri_xyz[i];
         a->verts_f32 = exact;
@@ -704,7 +708,7 @@ extern "C" ri_b200_accel_t *ri_b200_build(const double *tri_xyz, uint64_t ntris,
         return 0;
     };
     if (body() != 0) { ri_b200_free(a); return nullptr; }
-    if ((precisions & RI_B200_PREC_F32) && (precisions & RI_B200_PREC_F64) && hybrid_build_records(a) != 0) {
+    if ((precisions & RI_B200_PREC_F64) && hybrid_build_records(a) != 0) {
         // not fatal: without them the filter reads the shared fp32 records with the wider bounds that go with them (same answers, slower)
         fprintf(stderr, "[b200] the hybrid kernels' own fp32 records could not be built (%s); using the shared records\n", g_err);
         cudaGetLastError();

@@ -45,7 +45,9 @@ for v in variants:
     d64 = torch.from_numpy(rays).cuda()
     o_h = torch.empty(nr, dtype=torch.uint8, device="cuda"); o_p = torch.empty(nr, dtype=torch.uint8, device="cuda")
     ms_h = ev(lambda: hyb.occluded_dev(d64, nr, o_h, st.cuda_stream, f64=True))
+    os.environ["B200_HYBRID"] = "0"                                    # the double kernels alone (a double-only accelerator is hybrid too)
     ms_p = ev(lambda: plain.occluded_dev(d64, nr, o_p, st.cuda_stream, f64=True))
+    os.environ.pop("B200_HYBRID")
     same = bool(torch.equal(o_h, o_p))
     line = f"{v:8s} {nr} rays: hybrid {ms_h:.3f} ms = {nr / ms_h / 1e3:.1f} Mrays/s | plain f64 {ms_p:.3f} ms = {nr / ms_p / 1e3:.1f} Mrays/s | identical {same} | occluded {float(o_p.float().mean()):.3f}"
     if v == "exact":
@@ -56,7 +58,9 @@ for v in variants:
     print(line, flush=True)
     h_h = torch.empty((nr, 4), dtype=torch.float64, device="cuda"); h_p = torch.empty((nr, 4), dtype=torch.float64, device="cuda")
     ms_ch = ev(lambda: hyb.intersect_dev(d64, nr, h_h, st.cuda_stream, f64=True))
+    os.environ["B200_HYBRID"] = "0"
     ms_cp = ev(lambda: plain.intersect_dev(d64, nr, h_p, st.cuda_stream, f64=True))
+    os.environ.pop("B200_HYBRID")
     same_c = bool(torch.equal(h_h.view(torch.int64), h_p.view(torch.int64)))
     print(f"{v:8s} closest hit: hybrid {ms_ch:.3f} ms = {nr / ms_ch / 1e3:.1f} Mrays/s | plain f64 {ms_cp:.3f} ms = {nr / ms_cp / 1e3:.1f} Mrays/s | identical records {same_c}", flush=True)
     if not same:

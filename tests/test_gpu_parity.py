@@ -909,7 +909,18 @@ def test_hybrid_occlusion_is_fp64_exact(case):
         tris = tris * 3.7 + np.array([1000.0, -800.0, 400.0])
     assert (np.array_equal(tris.astype(np.float32).astype(np.float64), tris)) == (case in ("soup", "box_city"))
     hyb = accel.Accel.bind().build(tris, accel.PREC_F32 | accel.PREC_F64)
-    plain = accel.Accel.bind().build(tris, accel.PREC_F64)
+    dbl = accel.Accel.bind().build(tris, accel.PREC_F64)          # double records only: hybrid too, through the filter's own records
+
+    class _Plain:                                                  # the double kernels alone: the same accelerator with B200_HYBRID=0
+        def __getattr__(self, name):
+            def call(*args, **kw):
+                os.environ["B200_HYBRID"] = "0"
+                try:
+                    return getattr(hyb, name)(*args, **kw)
+                finally:
+                    os.environ.pop("B200_HYBRID", None)
+            return call
+    plain = _Plain()
     ot = ol.Oracle().build(tris)
     lo, hi = tris.reshape(-1, 3).min(axis=0), tris.reshape(-1, 3).max(axis=0)
     rng = np.random.default_rng(11)
@@ -936,8 +947,9 @@ def test_hybrid_occlusion_is_fp64_exact(case):
             assert np.array_equal(plain.occluded(rays), want), (case, name)
             assert 0.02 < want.mean() < 0.999 or name == "axis", (case, name, want.mean())
             # closest hit through the same filter (closest_hybrid_kernel): every field of every record is the double reference's
+            assert np.array_equal(dbl.occluded(rays), want), (case, name)
             hw = ot.intersect_f64(rays)
-            for acc in (hyb, plain):
+            for acc in (hyb, plain, dbl):
                 h = acc.intersect(rays)
                 for f in ("hit", "prim", "t", "u", "v"):
                     assert np.array_equal(h[f], hw[f]), (case, name, f, acc is hyb, int((h[f] != hw[f]).sum()))
