@@ -80,7 +80,13 @@ def gather_frame(local_slab, frame: "_accel.Frame", rank: int, world: int, group
         fbuf = torch.zeros((frame.height * frame.width, 3), dtype=torch.float32, device=bufs[0].device)
         for r in range(world):
             fbuf[idx[r]] = bufs[r][: counts[r]]
-        return fbuf.reshape(frame.height, frame.width, 3).cpu().numpy()
+        host = _PINNED.get(key)
+        if host is None or host.shape != fbuf.shape:
+            _PINNED.clear()
+            host = _PINNED[key] = torch.empty(fbuf.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(fbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        return host.numpy().reshape(frame.height, frame.width, 3)          # a view of a cached pinned buffer: valid until the next gather
     lists = []
     for r in range(world):
         f = copy.copy(frame)
@@ -90,6 +96,7 @@ def gather_frame(local_slab, frame: "_accel.Frame", rank: int, world: int, group
 
 
 _SCATTER_CACHE = {}
+_PINNED = {}
 
 
 def bucket_bases(all_hits, world: int):
@@ -162,6 +169,23 @@ class PeerFramebuffer:
             dist.broadcast_object_list(box, src=0, group=group)
         if rank != 0:
             self.ptr = _accel.peer_open(box[0], device)
+        # rank 0 reads every frame into ONE pinned host buffer it keeps (a fresh pageable array per frame costs more than the kernels
+        # of a small frame: 201 MB at 4096^2 is ~40 ms of page faults and staged copies against ~8 ms into pinned memory)
+        self._host_ptr, self._host = None, None
+        if rank == 0:
+            nbytes = width * height * 3 * 4
+            self._host_ptr = _accel.load_library().ri_b200_host_alloc(nbytes)
+            if self._host_ptr:
+                import ctypes
+                self._host = np.ctypeslib.as_array(ctypes.cast(self._host_ptr, ctypes.POINTER(ctypes.c_float)), shape=(height, width, 3))
+
+    def read(self) -> np.ndarray:
+        """Rank 0: the frame, as a view of this object's pinned host buffer -- valid until the next read() or close(); copy it to keep it."""
+        if self._host is None:
+            return _accel.peer_read(self.ptr, self.shape, self.device)
+        _accel._check(_accel.load_library().ri_b200_peer_read(_accel.C.c_void_p(self.ptr), _accel.C.c_void_p(self._host_ptr), self._host.nbytes,
+                                                               self.device))
+        return self._host
 
     def close(self):
         import torch.distributed as dist
@@ -172,12 +196,17 @@ class PeerFramebuffer:
             dist.barrier(group=self.group)             # nobody frees or unmaps while another rank may still store
         (_accel.peer_free if self.rank == 0 else _accel.peer_close)(self.ptr, self.device)
         self.ptr = None
+        if self._host_ptr:
+            self._host = None
+            _accel.load_library().ri_b200_host_free(_accel.C.c_void_p(self._host_ptr))
+            self._host_ptr = None
 
 
 def render_ao_distributed_peer(acc: "_accel.Accel", frame: "_accel.Frame", fb: PeerFramebuffer, stream=None):
     """The same frame with the gather FUSED into the resolve kernels: every rank's resolve kernel stores its tiles straight into
     rank 0's framebuffer (ri_b200_render_ao_peer_dev); one barrier says the stores have landed, then rank 0 reads the frame.
-    Returns (framebuffer on rank 0 or None, FrameStats of this rank)."""
+    Returns (framebuffer on rank 0 or None, FrameStats of this rank); the framebuffer is a VIEW of fb's pinned host buffer -- copy it
+    if it must outlive the next frame rendered into fb or fb.close()."""
     import torch
     import torch.distributed as dist
 
@@ -189,7 +218,7 @@ def render_ao_distributed_peer(acc: "_accel.Accel", frame: "_accel.Frame", fb: P
     if fb.world > 1:
         dist.barrier(group=fb.group)                   # rank 0 has read the previous frame out of the buffer
     stats = _frame_call_all_ranks(lambda: acc.render_ao_peer_dev(f, fb.ptr, stream), fb.world, fb.group, device="cuda")
-    rgb = _accel.peer_read(fb.ptr, fb.shape, fb.device) if fb.rank == 0 else None
+    rgb = fb.read() if fb.rank == 0 else None          # a view of fb's pinned buffer: valid until the next frame / fb.close()
     return rgb, stats
 
 
