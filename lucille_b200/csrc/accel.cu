@@ -76,6 +76,7 @@ struct ri_b200_accel {
     ri_b200_hit_exchange_fn hit_exchange = nullptr;      // rng_mode 0 over several ranks (frame.cuh)
     void     *hit_exchange_user = nullptr;
     float4 *d_k6_rays = nullptr; uint32_t *d_k6_perm = nullptr; unsigned int *d_k6_ctr = nullptr; uint64_t k6_cap = 0;   // reorder.cuh scratch (lock held)
+    uint32_t *pixc_pix = nullptr; uint64_t pixc_cap = 0, pixc_n = 0; int pixc_w = 0, pixc_h = 0, pixc_bucket = 0, pixc_rank = 0, pixc_world = 0;   // frame.cuh: cached pixel list
     bool verts_f32 = false;               // every vertex coordinate is an fp32 number (hybrid.cuh: no absolute error in the fp32 slots)
     Node32 *d_nodesH = nullptr; Tri32 *d_trisH = nullptr;      // hybrid.cuh's own fp32 records, relative to hyb_c (NULL: it reads the shared ones)
     double hyb_c[3] = {0.0, 0.0, 0.0};
@@ -730,6 +731,7 @@ extern "C" void ri_b200_free(ri_b200_accel_t *a)
     if (a->device < 0) { delete a; return; }
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
+    cudaFree(a->pixc_pix);
     cudaFree(a->d_nodesH); cudaFree(a->d_trisH); cudaFree(a->d_k6_rays); cudaFree(a->d_k6_perm); cudaFree(a->d_k6_ctr);
     cudaFree(a->d_nodes32); cudaFree(a->d_tris32); cudaFree(a->d_nodes64); cudaFree(a->d_tris64); cudaFree(a->d_tris32t); cudaFree(a->d_tris64t); cudaFree(a->d_slot_of_prim); cudaFree(a->d_nrm64); cudaFree(a->d_nrm32); cudaFree(a->d_col); cudaFree(a->d_st); cudaFree(a->d_attr_flags); cudaFree(a->d_tex);
     for (int i = 0; i < 2; ++i) { cudaFree(a->d_in[i]); cudaFree(a->d_out[i]); }

@@ -749,9 +749,13 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
         ~ExchangeGuard() { if (armed) a->hit_exchange(a->hit_exchange_user, nullptr, 0, nullptr, nullptr); }
     } exchange_guard{a, shared_stream};
     std::vector<uint32_t> bfirst;
-    pixel_order(f, pix, shared_stream ? &bfirst : nullptr);
+    // the pixel list of a rank depends only on the frame's geometry: frame after frame of the same size it is kept on the device
+    // (4096^2: 16.7 M pixels = 30 ms of host work and a 67 MB upload per frame otherwise)
+    const bool pix_cached = !shared_stream && a->pixc_pix && a->pixc_w == f.width && a->pixc_h == f.height && a->pixc_bucket == f.bucket_size &&
+                            a->pixc_rank == f.rank && a->pixc_world == f.world;
+    if (!pix_cached) pixel_order(f, pix, shared_stream ? &bfirst : nullptr);
     jitter_table(f.xsamples, f.ysamples, jit);
-    const uint64_t npix = pix.size();
+    const uint64_t npix = pix_cached ? a->pixc_n : pix.size();
     const uint32_t nbuckets = shared_stream ? (uint32_t)bfirst.size() - 1 : 0;
     // the sun-sky transport gathers with a fixed 8 x 8 pattern whatever Option "gather" says (ambientocclusion.c:371-374)
     // ... and the dirt-map transport with a fixed 4 x 4 one (dirtmap.c:261-265)
@@ -805,7 +809,22 @@ static int render_ao_impl(ri_b200_accel *a, const ri_b200_frame_t &f, float *d_r
     CUDA_OK(cudaEventRecord(a->ev[0], st));
     if (npix) {
         CUDA_OK(cudaMemcpyAsync(d_jit, jit.data(), jit.size() * 8, cudaMemcpyHostToDevice, st));
-        CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
+        if (pix_cached) {
+            d_pix = a->pixc_pix;
+        } else if (!shared_stream) {                 // (re)fill the cache and read the list from there
+            if (a->pixc_cap < npix + 1) {
+                cudaFree(a->pixc_pix); a->pixc_pix = nullptr; a->pixc_cap = 0;
+                if (cudaMalloc((void **)&a->pixc_pix, (npix + 1) * 4) == cudaSuccess) a->pixc_cap = npix + 1; else cudaGetLastError();
+            }
+            if (a->pixc_pix) {
+                d_pix = a->pixc_pix;
+                a->pixc_w = f.width; a->pixc_h = f.height; a->pixc_bucket = f.bucket_size; a->pixc_rank = f.rank; a->pixc_world = f.world; a->pixc_n = npix;
+            }
+            CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
+            CUDA_OK(cudaStreamSynchronize(st));      // pix is a local; the cached copy must be complete before the key is trusted
+        } else {
+            CUDA_OK(cudaMemcpyAsync(d_pix, pix.data(), npix * 4, cudaMemcpyHostToDevice, st));
+        }
     }
     std::vector<uint32_t> pixb;
     if (shared_stream && npix) {
