@@ -262,3 +262,13 @@ int main(void) {
         "ri_b200_ao_points_t": ct(accel.AoPoints, "eps"),
     }
     assert got == want
+
+
+def test_light_sample_count_is_init_lightsource_s():
+    """ri_b200_light_samples_count = the number of samples init_lightsource() sets up for Option narealight_rays (shader.c:1263-1266):
+    ntheta = (int)sqrt((int)(n / 3.0)), at least 1; m = ntheta * 3 ntheta.  Pure host logic (no device needed)."""
+    import math
+    lib = accel.load_library()
+    for n in (1, 2, 3, 5, 11, 12, 26, 27, 47, 48, 75, 108, 300, 1000):
+        nt = max(1, int(math.sqrt(int(n / 3.0))))
+        assert lib.ri_b200_light_samples_count(n) == 3 * nt * nt, n
