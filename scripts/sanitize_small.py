@@ -85,8 +85,14 @@ for name, tt in (("exact", tris), ("inexact", tris * 1.1 + np.array([0.3, -0.2, 
     r[::5, 3:6] = [0.0, 0.0, 1.0]
     occ = h.occluded(np.ascontiguousarray(r))
     pts6 = np.concatenate([org[:300], np.tile([0.0, 0.0, 1.0], (300, 1))], axis=1)
-    print("hybrid", name, int(occ.sum()), int(h.occlusion_points(pts6, 4, 4, 7, f64=True).sum()), int(h.occlusion_points(pts6, 4, 4, 7).sum()))
+    hits = h.intersect(np.ascontiguousarray(r))                      # closest_hybrid_kernel (shared / own records)
+    print("hybrid", name, int(occ.sum()), int(hits["hit"].sum()), int(h.occlusion_points(pts6, 4, 4, 7, f64=True).sum()), int(h.occlusion_points(pts6, 4, 4, 7).sum()))
+    d = accel.Accel.bind().build(tt, accel.PREC_F64)                 # double records only: hybrid through its own records
+    print("hybrid, double-only build", name, int(d.occluded(np.ascontiguousarray(r)).sum()), int(d.intersect(np.ascontiguousarray(r))["hit"].sum()))
 os.environ.pop("B200_HYBRID", None)
+os.environ["B200_K6"] = "1"                                           # reorder.cuh forced: stable octant sort + permuted result writes
+print("k6 point entry", int(a.occlusion_points(np.tile(pts, (30, 1)), 4, 4, 3).sum()))
+os.environ.pop("B200_K6")
 pr = np.concatenate([pts[:, :3], np.random.default_rng(3).normal(size=(200, 3))], axis=1)
 rec = a.shade_trace(pr, env); print("shade_trace", int(rec["hit"].sum()), float(rec["Ci"].sum()))
 a.mt_prepare(1 << 21)
