@@ -879,6 +879,8 @@ def test_shade_callers(oracle, golden_dir):
     half = len(pts) // 2
     m = 3 * 4 * 4
     whole = la.light_samples(48, 1.2, pts, env)
+    la.mt_prepare(8 * 638976)                              # ri_b200_mt_prepare: the jump-ahead table built ahead of time changes nothing
+    assert all(np.array_equal(x, y) for x, y in zip(la.light_samples(48, 1.2, pts, env)[:3], whole[:3]))
     tail = la.light_samples(48, 1.2, pts[half:], env, stream_offset=2 * m * half)
     assert all(np.array_equal(x, y[half:]) for x, y in zip(tail[:3], whole[:3]))
     assert la.light_samples(48, 1.2, np.zeros((0, 6)), env)[0].shape == (0, m, 3)
