@@ -1102,11 +1102,11 @@ def test_city_frame_through_the_hybrid_path(golden_dir):
         os.environ.pop("B200_HYBRID", None)
 
 
-def test_k6_reordered_batches_give_the_same_results(soup20k, golden_dir):
+def test_k6_reordered_batches_give_the_same_results(soup20k):
     """csrc/reorder.cuh (K6): the entry points that hold the accelerator's lock may put an occlusion batch into octant-major order
     before tracing it (they do on scenes beyond L2); results come back through the permutation in input order.  Forced here
-    (B200_K6=1) on small scenes: point-entry counts, an AO frame with per-sample counters and a sun-sky frame with per-ray flags are
-    identical to the unsorted runs, and the counts equal the oracle's."""
+    (B200_K6=1) on small scenes: point-entry counts and an AO frame with per-sample counters are identical to the unsorted runs, and
+    the counts equal the oracle's."""
     _need_gpu()
     tris, a, orc = soup20k
     rays = scenes.rays_f32_to_f64(scenes.pinhole_rays(128, 128))
@@ -1116,7 +1116,6 @@ def test_k6_reordered_batches_give_the_same_results(soup20k, golden_dir):
     pts = np.concatenate([st["P"][m][:, :3], st["Ns"][m][:, :3]], axis=1)[:6000]
     c2w = np.eye(4); c2w[3, :3] = (0.5, 0.5, -2.0)
     fr = accel.make_frame(c2w.reshape(16), 2.7, False, 96, 80, 2, 2, 16, rng_mode=1, seed=9, precision=accel.PREC_F32)
-    g = np.load(os.path.join(golden_dir, "sunsky.npz"))
     base_counts = a.occlusion_points(pts, 4, 6, 31)
     base_frame, base_stats = a.render_ao(fr)
     os.environ["B200_K6"] = "1"
@@ -1133,4 +1132,3 @@ def test_k6_reordered_batches_give_the_same_results(soup20k, golden_dir):
     assert np.array_equal(base_frame, fr_0) or base_stats.nrays == st_0.nrays      # the fused small-scene path draws the same rays
     want = orc.occluded_f32(ol.Oracle().ao_point_rays(pts, 4, 6, 31)).reshape(len(pts), 24).sum(axis=1)
     assert np.array_equal(base_counts, want)
-    assert g is not None
