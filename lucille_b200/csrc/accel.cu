@@ -1317,6 +1317,14 @@ extern "C" int ri_b200_intersect1(ri_b200_accel_t *a, const double org[3], const
     return hit->hit ? 1 : 0;
 }
 
+// rays per wave of the wavefront entry points (generator -> traverser -> accumulator): 2^24, or B200_WAVE_RAYS (tests: a small value
+// drives the chunk loops of the point / gather / shade entry points with small inputs)
+static uint64_t wave_rays()
+{
+    if (const char *e = getenv("B200_WAVE_RAYS")) { const long long v = atoll(e); if (v >= 64) return (uint64_t)v; }
+    return 1ull << 24;
+}
+
 #include "frame.cuh"
 #include "pathtrace.cuh"
 #include "points.cuh"

@@ -298,7 +298,7 @@ extern "C" int ri_b200_gather_points_f64(ri_b200_accel_t *a, const ri_b200_gathe
         point_gather_kernel<<<(unsigned)blocks, kBlock, smem, st>>>(make_view<double>(a), G, d_points, n, d_mt, d_out, (uint32_t)cap);
         LAUNCHED();
     } else {                                                  // wavefront: <= 2^24 rays at a time through the pooled traverser
-        const uint64_t chunk_points = ((1ull << 24) / N) ? (1ull << 24) / N : 1;
+        const uint64_t chunk_points = (wave_rays() / N) ? wave_rays() / N : 1;
         const uint64_t buf_points = n < chunk_points ? n : chunk_points;
         if (frame_buf(a, 10, buf_points * N * 6 * sizeof(double), &p)) return -1;
         double *d_rays = (double *)p;

@@ -89,7 +89,7 @@ static int ao_points_run(ri_b200_accel *a, const ri_b200_ao_points_t *g, const d
     constexpr size_t kRay = RayIO<Real>::kRayStride * sizeof(Real);
     const uint64_t N = (uint64_t)g->ntheta * (uint64_t)g->nphi;
     const AoPointsDev G = {g->ntheta, g->nphi, g->seed, g->eps};
-    const uint64_t chunk_points = ((1ull << 24) / N) ? (1ull << 24) / N : 1;
+    const uint64_t chunk_points = (wave_rays() / N) ? wave_rays() / N : 1;
     const uint64_t buf_points = n < chunk_points ? n : chunk_points;
     void *p = nullptr;
     if (frame_buf(a, 10, buf_points * N * kRay, &p)) return -1;
@@ -145,7 +145,7 @@ static int ao_points_host(ri_b200_accel_t *a, const ri_b200_ao_points_t *g, cons
     // 16.18 ms against 16.12 for the plain sequence on C3.)
     const uint64_t N = (uint64_t)g->ntheta * (uint64_t)g->nphi;
     const AoPointsDev G = {g->ntheta, g->nphi, g->seed, g->eps};
-    const uint64_t chunk_points = ((1ull << 24) / N) ? (1ull << 24) / N : 1;
+    const uint64_t chunk_points = (wave_rays() / N) ? wave_rays() / N : 1;
     const uint64_t buf_points = n < chunk_points ? n : chunk_points;
     cudaStream_t ks = a->stream, cs = a->copy_stream[0];
     void *p = nullptr;
@@ -200,7 +200,7 @@ extern "C" int ri_b200_ao_point_rays_f32(ri_b200_accel_t *a, const ri_b200_ao_po
     cudaStream_t st = a->stream;
     const uint64_t N = (uint64_t)g->ntheta * (uint64_t)g->nphi;
     const AoPointsDev G = {g->ntheta, g->nphi, g->seed, g->eps};
-    const uint64_t chunk_points = ((1ull << 24) / N) ? (1ull << 24) / N : 1;
+    const uint64_t chunk_points = (wave_rays() / N) ? wave_rays() / N : 1;
     const uint64_t buf_points = n < chunk_points ? n : chunk_points;
     void *p = nullptr;
     if (frame_buf(a, 0, n * 6 * sizeof(double), &p)) return -1;

@@ -181,7 +181,7 @@ extern "C" int ri_b200_shade_trace_f64(ri_b200_accel_t *a, const double *pr, uin
         CUDA_OK(cudaMemcpyAsync(p, env_rgba, bytes, cudaMemcpyHostToDevice, st));
         env.data = (const float *)p;
     }
-    const uint64_t chunk = n < (1ull << 22) ? n : (1ull << 22);               // 4 Mi points at a time: 0.3 KB of records each
+    const uint64_t chunk = n < wave_rays() / 4 ? n : wave_rays() / 4;               // 4 Mi points at a time: 0.3 KB of records each
     if (frame_buf(a, 0, chunk * 6 * sizeof(double), &p)) return -1;
     double *d_pr = (double *)p;
     if (frame_buf(a, 1, chunk * 6 * sizeof(double), &p)) return -1;
@@ -259,7 +259,7 @@ extern "C" int ri_b200_light_samples_f64(ri_b200_accel_t *a, const ri_b200_light
     const uint64_t mt_blocks = (words + kMtN - 1) / kMtN;
     if (frame_buf(a, 5, (mt_blocks * kMtN + 4) * 4, &p)) return -1;
     uint32_t *d_mt = (uint32_t *)p;
-    const uint64_t chunk_points = ((1ull << 24) / m) ? (1ull << 24) / m : 1;
+    const uint64_t chunk_points = (wave_rays() / m) ? wave_rays() / m : 1;
     const uint64_t buf_points = n < chunk_points ? n : chunk_points;
     if (frame_buf(a, 10, buf_points * m * 6 * sizeof(double), &p)) return -1;
     double *d_rays = (double *)p;

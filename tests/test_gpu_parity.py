@@ -1132,3 +1132,30 @@ def test_k6_reordered_batches_give_the_same_results(soup20k):
     assert np.array_equal(base_frame, fr_0) or base_stats.nrays == st_0.nrays      # the fused small-scene path draws the same rays
     want = orc.occluded_f32(ol.Oracle().ao_point_rays(pts, 4, 6, 31)).reshape(len(pts), 24).sum(axis=1)
     assert np.array_equal(base_counts, want)
+
+
+def test_wave_chunk_loops_of_the_point_entries(soup20k, golden_dir):
+    """The wavefront entry points process at most 2^24 rays per wave; B200_WAVE_RAYS shrinks a wave so that small inputs run the chunk
+    loops (several generator -> traverser -> accumulator rounds, buffers reused between them): results equal the one-wave results."""
+    _need_gpu()
+    tris, a, orc = soup20k
+    g = np.load(os.path.join(golden_dir, "point_gathers.npz"))
+    pts, env = g["points"], g["env"]
+    rng = np.random.default_rng(3)
+    pr = np.concatenate([pts[:, :3], rng.normal(size=(len(pts), 3))], axis=1)
+
+    def run():
+        return (a.occlusion_points(pts, 4, 4, 7), a.occlusion_points(pts, 4, 4, 7, f64=True),
+                a.gather_points(accel.GATHER_DOME, 27, pts, None, (0.9, 0.5, 0.25), 2.5)[0],
+                a.gather_points(accel.GATHER_OCCLUSION, 48, pts)[0],
+                a.shade_trace(pr, env), *a.light_samples(48, 1.2, pts, env)[:3])
+    os.environ["B200_FUSED_AO_TEST"] = "0"
+    try:
+        one = run()
+        os.environ["B200_WAVE_RAYS"] = "4096"          # 800 points x 16 / 27 / 48 rays: 4 to 10 waves per call
+        many = run()
+    finally:
+        os.environ.pop("B200_WAVE_RAYS", None)
+        os.environ.pop("B200_FUSED_AO_TEST", None)
+    for x, y in zip(one, many):
+        assert np.array_equal(x, y)
